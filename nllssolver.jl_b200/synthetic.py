@@ -1,0 +1,132 @@
+"""Synthetic problem generators (numpy only; host-side test/bench data, no solver code).
+
+The Julia RNG stream is not reproducible outside Julia, so problems are regenerated from the reference's
+*construction rules* with numpy's default_rng:
+
+* create_ba_problem    — test/optimizeba.jl:6-36 (affine camera, banded visibility, noise-free measurements,
+                         camera-major cost order); perturb_ba_problem — test/optimizeba.jl:38-47.
+* create_bal_shaped    — BAL-*shaped* problems (Ladybug / Venice / Final sizes) built with the same rules:
+                         point l has centre camera linspace(2, ncam-1, npt)[l] and is seen by its k_l nearest
+                         cameras, k_l >= 2, sum k_l = nobs; measurements = projection + noise (+ outliers).
+* create_adaptive_problem — examples/adaptivekernel.jl:20-30 / test/adaptivecost.jl:33-38.
+"""
+import numpy as np
+
+CAM_OFFSET = np.array([1.0, 0.0, 0.0, 0.0, 1.0, 0.0])
+LM_OFFSET = np.array([-0.5, -0.5, 10.0])
+
+SHAPES = {  # (ncam, npt, nobs)  BASELINE.md §4
+    "ladybug": (49, 7776, 31843),
+    "venice": (1778, 993923, 5001946),
+    "final": (13682, 4456117, 28987644),
+}
+
+
+def project_affine(cams, pts):
+    """generatemeasurement(pose, X) = (pose[1:3].X, pose[4:6].X)   (test/optimizeba.jl:4)."""
+    return np.stack([np.einsum("ij,ij->i", cams[:, 0:3], pts), np.einsum("ij,ij->i", cams[:, 3:6], pts)], axis=1)
+
+
+class BAProblem:
+    """Plain container: cameras (ncam, dc), points (npt, 3), costs in storage order.
+    cam_idx / pt_idx are 1-based *global variable indices* (cameras first, then points), as varindices returns."""
+
+    def __init__(self, cameras, points, cam_idx, pt_idx, z):
+        self.cameras = np.ascontiguousarray(cameras, dtype=np.float64)
+        self.points = np.ascontiguousarray(points, dtype=np.float64)
+        self.cam_idx = np.ascontiguousarray(cam_idx, dtype=np.int64)
+        self.pt_idx = np.ascontiguousarray(pt_idx, dtype=np.int64)
+        self.z = np.ascontiguousarray(z, dtype=np.float64)
+
+    @property
+    def ncam(self):
+        return self.cameras.shape[0]
+
+    @property
+    def npt(self):
+        return self.points.shape[0]
+
+    @property
+    def nobs(self):
+        return self.z.shape[0]
+
+    def costs_aos(self):
+        """The memory image of Vector{SimpleError2{2,Float64,EV6,EV3}}: 32 B per cost =
+        measurement (2 x f64) then varind (2 x i64)   (src/residual.jl:4-7)."""
+        aos = np.zeros(self.nobs, dtype=np.dtype([("z", "<f8", 2), ("varind", "<i8", 2)]))
+        aos["z"] = self.z
+        aos["varind"][:, 0] = self.cam_idx
+        aos["varind"][:, 1] = self.pt_idx
+        return aos
+
+    def copy(self):
+        return BAProblem(self.cameras.copy(), self.points.copy(), self.cam_idx, self.pt_idx, self.z)
+
+
+def create_ba_problem(ncameras, nlandmarks, propvisible, rng):
+    """test/optimizeba.jl:6-36."""
+    cams = rng.standard_normal((ncameras, 6)) + CAM_OFFSET
+    pts = rng.random((nlandmarks, 3)) + LM_OFFSET
+    centres = np.linspace(2, ncameras - 1, nlandmarks)
+    vis = np.abs(np.arange(1, ncameras + 1)[:, None] - centres[None, :])
+    thresh = np.sort(vis.ravel())[int(np.ceil(vis.size * propvisible)) - 1]
+    vis = vis <= thresh
+    cam_l, lm_l = np.nonzero(vis)  # row-major nonzero == camera-major cost order (:24-32)
+    z = project_affine(cams[cam_l], pts[lm_l])
+    return BAProblem(cams, pts, cam_l + 1, lm_l + 1 + ncameras, z)
+
+
+def perturb_ba_problem(problem, pointnoise, posenoise, rng):
+    """test/optimizeba.jl:38-47."""
+    problem.cameras = problem.cameras + rng.standard_normal(problem.cameras.shape) * posenoise
+    problem.points = problem.points + rng.standard_normal(problem.points.shape) * pointnoise
+    return problem
+
+
+def create_bal_shaped(ncam, npt, nobs, rng, noise=0.01, outlier_frac=0.0, outlier_scale=50.0, camera_major=True):
+    """BAL-shaped synthetic BA with the reference test's affine camera model."""
+    assert nobs >= 2 * npt and ncam >= 2
+    cams = rng.standard_normal((ncam, 6)) + CAM_OFFSET
+    pts = rng.random((npt, 3)) + LM_OFFSET
+    # track lengths k_l >= 2 with sum == nobs
+    mean_extra = nobs / npt - 2.0
+    k = 2 + rng.poisson(mean_extra, npt)
+    k = np.minimum(k, ncam)
+    diff = int(nobs - k.sum())
+    while diff != 0:
+        if diff > 0:
+            cand = np.nonzero(k < ncam)[0]
+            sel = rng.choice(cand, size=min(diff, cand.size), replace=False)
+            k[sel] += 1
+        else:
+            cand = np.nonzero(k > 2)[0]
+            sel = rng.choice(cand, size=min(-diff, cand.size), replace=False)
+            k[sel] -= 1
+        diff = int(nobs - k.sum())
+    centres = np.linspace(2, ncam - 1, npt)
+    start = np.clip(np.ceil(centres - k / 2.0).astype(np.int64), 1, ncam - k + 1)  # 1-based first camera of the window
+    obs_start = np.concatenate([[0], np.cumsum(k)])
+    pt_l = np.repeat(np.arange(npt, dtype=np.int64), k)
+    cam_l = (np.arange(nobs, dtype=np.int64) - obs_start[pt_l]) + start[pt_l] - 1  # 0-based camera
+    if camera_major:
+        order = np.lexsort((pt_l, cam_l))
+        pt_l, cam_l = pt_l[order], cam_l[order]
+    z = project_affine(cams[cam_l], pts[pt_l])
+    z += rng.standard_normal(z.shape) * noise
+    if outlier_frac > 0:
+        nout = int(round(outlier_frac * nobs))
+        sel = rng.choice(nobs, size=nout, replace=False)
+        z[sel] += rng.standard_normal((nout, 2)) * (noise * outlier_scale)
+    return BAProblem(cams, pts, cam_l + 1, pt_l + 1 + ncam, z)
+
+
+def create_shape(name, rng, **kw):
+    ncam, npt, nobs = SHAPES[name]
+    return create_bal_shaped(ncam, npt, nobs, rng, **kw)
+
+
+def create_adaptive_problem(ninliers, noutliers, rng, inliersigma=1.0, outliersigma=10.0, offset=1.0):
+    """examples/adaptivekernel.jl:20-30: data = offset + [N(0, s_in) x ninliers ; N(0, s_out) x noutliers];
+    start ContaminatedGaussian(0.5, 5.0, 0.6), mean 0."""
+    data = offset + np.concatenate([rng.standard_normal(ninliers) * inliersigma, rng.standard_normal(noutliers) * outliersigma])
+    return {"data": data, "start_kernel": (0.5, 5.0, 0.6), "start_mean": 0.0}
