@@ -1,0 +1,34 @@
+"""Builds libnlls_b200.so in-tree with nvcc for sm_100a (cross-compiles without a GPU)."""
+import os
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SO = os.path.join(HERE, "libnlls_b200.so")
+SRCS = ["csrc/nlls_b200.cu"]
+DEPS = SRCS + ["csrc/kernels.cuh", "csrc/common.cuh", "csrc/residuals.cuh", "../include/nlls_b200.h"]
+NVCC_FLAGS = [
+    "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+    "-fmad=false",  # residual/assembly kernels are HBM-bound; keeping mul/add unfused tracks the reference's (unfused) Julia arithmetic
+    "-shared", "-Xcompiler", "-fPIC",
+]
+LIBS = ["-lcusolver", "-lcublas", "-ldl", "-Xlinker", "-rpath,/usr/local/cuda/lib64"]
+
+
+def needs_build():
+    if not os.path.exists(SO):
+        return True
+    t = os.path.getmtime(SO)
+    return any(os.path.getmtime(os.path.join(HERE, d)) > t for d in DEPS)
+
+
+def build(force=False, verbose=False):
+    if not force and not needs_build():
+        return SO
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", SO] + SRCS + LIBS
+    subprocess.check_call(cmd, cwd=HERE)
+    return SO
+
+
+if __name__ == "__main__":
+    print(build(force=True, verbose=True))

@@ -1,0 +1,561 @@
+// Kernels of the LM hot path (sm_100a, FP64).  Launch wrappers live in nlls_b200.cu.
+//
+// Data layout in HBM:
+//   observations, point-major ("reordercostsforschur!" order, src/problem.jl:177-199): obs_cam[nobs] (int32 local
+//   camera), obs_pt[nobs] (int32 local point), obs_z[nobs] (double2), obs_start[npt+1] (CSR by point);
+//   a second camera-major copy (cm_pt, cm_z) for the camera pass.
+//   H: the reference's BlockSparseMatrix.data for cameras-before-points variable order:
+//     [ U_c : nA blocks of DC x DC ][ for each point p: W_{p,c1} .. W_{p,ck} (3 x DC each, ascending camera), V_p (3x3) ]
+//   so the row of point p starts at hB + 3*DC*obs_start[p] + 9*p and one tile of consecutive points is ONE contiguous span.
+//   g: [ g_c : DC*nA ][ g_p : 3*nB ].
+#pragma once
+#include "common.cuh"
+#include "residuals.cuh"
+
+namespace nlls {
+
+struct DevProblem {
+    // point-major observations
+    const int* obs_cam;
+    const int* obs_pt;
+    const double2* obs_z;
+    const int* obs_start;
+    const int* tile_pt;  // [ntiles + 1]
+    int ntiles, nA, nB, nobs;
+    // camera-major copy
+    const int* cm_pt;
+    const double2* cm_z;
+    const int* item_cam;
+    const int* item_beg;
+    const int* item_end;
+    const int* cam_item_start;  // [nA + 1]
+    int nitems;
+    // linear system
+    double* H;
+    double* g;
+    long long hB;  // DC*DC*nA
+    long long gB;  // DC*nA
+    RobustParams rk;
+    int use_tma;
+};
+
+template <class R>
+struct LinSmem {
+    static constexpr int WB = 3 * R::DC;
+    static constexpr int OUT = WB * TILE_OBS + 9 * TILE_PTS;  // staged H span (doubles)
+    static constexpr int PC = 9 * TILE_OBS;                   // per-observation point contributions (6 V + 3 g)
+    static constexpr int XS = 3 * TILE_PTS;
+    static constexpr size_t bytes = (size_t)(OUT + PC + XS + 3 * TILE_PTS + 8) * sizeof(double) + (TILE_PTS + 4) * sizeof(int);
+};
+
+// ---------------------------------------------------------------------------------------------------
+// K1  lin_point: fused residual + analytic Jacobian + robust weights + J'WJ for one tile of points.
+// Replaces costgradhess! (src/cost.jl:29-52) -> computerescostgradhess (src/residual.jl:57-111) ->
+// updatesymlinearsystem! (src/linearsystem.jl:132-175) for the point rows of H (W and V blocks) and g_p.
+// One thread per observation; per-point sums run sequentially in observation order (deterministic, and the
+// same order as the reference when costs are stored camera-major).  The tile's H span is staged in shared
+// memory and written with one TMA bulk store.
+// ---------------------------------------------------------------------------------------------------
+template <class R>
+__global__ void __launch_bounds__(LIN_THREADS) lin_point_kernel(DevProblem p, const double* __restrict__ cams,
+                                                                const double* __restrict__ pts, double* __restrict__ cost_partials) {
+    constexpr int DC = R::DC, WB = 3 * DC;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* s_out = reinterpret_cast<double*>(smem_raw);
+    double* s_pc = s_out + LinSmem<R>::OUT;
+    double* s_X = s_pc + LinSmem<R>::PC;
+    double* s_gp = s_X + LinSmem<R>::XS;
+    double* s_red = s_gp + 3 * TILE_PTS;
+    int* s_ost = reinterpret_cast<int*>(s_red + 8);
+
+    const int tid = threadIdx.x;
+    const int t = blockIdx.x;
+    const int pt0 = p.tile_pt[t], pt1 = p.tile_pt[t + 1];
+    const int ob0 = p.obs_start[pt0], ob1 = p.obs_start[pt1];
+    const int npt = pt1 - pt0, nob = ob1 - ob0;
+
+    for (int i = tid; i < 3 * npt; i += LIN_THREADS) s_X[i] = pts[(size_t)3 * pt0 + i];
+    for (int i = tid; i <= npt; i += LIN_THREADS) s_ost[i] = p.obs_start[pt0 + i] - ob0;
+    __syncthreads();
+
+    double c = 0.0;
+    if (tid < nob) {
+        const int j = ob0 + tid;
+        const int cam = p.obs_cam[j];
+        const int pl = p.obs_pt[j] - pt0;
+        const double2 z = p.obs_z[j];
+        double cv[R::NC];
+        R::load_cam(cams, cam, cv);
+        const double X[3] = {s_X[3 * pl], s_X[3 * pl + 1], s_X[3 * pl + 2]};
+        double r[2], Jc[2][DC], Jp[2][3];
+        R::resjac(cv, X, z.x, z.y, r, Jc, Jp);
+        const double s = r[0] * r[0] + r[1] * r[1];               // sqnorm            src/residual.jl:72
+        double rho, d1, d2;
+        robustifydcost(p.rk, s, rho, d1, d2);                     //                   src/residual.jl:78
+        c = 0.5 * rho;                                            //                   src/residual.jl:110
+        double gc[DC], gp[3];
+#pragma unroll
+        for (int a = 0; a < DC; ++a) gc[a] = Jc[0][a] * r[0] + Jc[1][a] * r[1];   // g = J' r   :73
+#pragma unroll
+        for (int b = 0; b < 3; ++b) gp[b] = Jp[0][b] * r[0] + Jp[1][b] * r[1];
+        const double td2 = 2 * d2;
+        // W block (point row, camera column), column-major 3 x DC                     src/linearsystem.jl:149
+        double* w = s_out + WB * tid + 9 * pl;
+#pragma unroll
+        for (int a = 0; a < DC; ++a)
+#pragma unroll
+            for (int b = 0; b < 3; ++b) {
+                double h = Jp[0][b] * Jc[0][a] + Jp[1][b] * Jc[1][a];             // H = J' J   :74
+                if (d1 != 1.0) h *= d1;                                            // IRLS       :91-93
+                if (d2 != 0.0) h += (td2 * gp[b]) * gc[a];                         // Triggs     :95-97
+                w[b + 3 * a] = h;
+            }
+        // this observation's contribution to V_p (lower triangle) and g_p
+        double* pc = s_pc + 9 * tid;
+        int q = 0;
+#pragma unroll
+        for (int b2 = 0; b2 < 3; ++b2)
+#pragma unroll
+            for (int b = b2; b < 3; ++b) {
+                double h = Jp[0][b] * Jp[0][b2] + Jp[1][b] * Jp[1][b2];
+                if (d1 != 1.0) h *= d1;
+                if (d2 != 0.0) h += (td2 * gp[b]) * gp[b2];
+                pc[q++] = h;
+            }
+#pragma unroll
+        for (int b = 0; b < 3; ++b) pc[6 + b] = (d1 != 1.0) ? gp[b] * d1 : gp[b];  // g *= dc  :99-101
+    }
+    __syncthreads();
+
+    if (tid < npt) {  // sequential per-point accumulation:  block(A, p, p) += ..., b[p] += ...   :140,166
+        double v[9];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) v[i] = 0.0;
+        for (int j = s_ost[tid]; j < s_ost[tid + 1]; ++j) {
+#pragma unroll
+            for (int i = 0; i < 9; ++i) v[i] += s_pc[9 * j + i];
+        }
+        double* V = s_out + WB * s_ost[tid + 1] + 9 * tid;
+        V[0] = v[0]; V[1] = v[1]; V[2] = v[2];
+        V[3] = v[1]; V[4] = v[3]; V[5] = v[4];
+        V[6] = v[2]; V[7] = v[4]; V[8] = v[5];
+        s_gp[3 * tid] = v[6]; s_gp[3 * tid + 1] = v[7]; s_gp[3 * tid + 2] = v[8];
+    }
+    // cost of the tile (fixed reduction tree; the cost kernel uses the same one)
+    const double csum = block_sum(c, s_red);   // contains a __syncthreads after the s_out / s_gp writes of this warp's lanes
+    if (tid == 0) cost_partials[t] = csum;
+    if (p.use_tma) fence_proxy_async();
+    __syncthreads();
+
+    // write back: g_p (coalesced) and the H span (one contiguous range)
+    for (int i = tid; i < 3 * npt; i += LIN_THREADS) p.g[p.gB + (size_t)3 * pt0 + i] = s_gp[i];
+    const size_t span0 = (size_t)p.hB + (size_t)WB * ob0 + (size_t)9 * pt0;
+    const int span = WB * nob + 9 * npt;
+    double* gdst = p.H + span0;
+    const bool aligned = ((reinterpret_cast<uintptr_t>(gdst) & 15) == 0) && ((span & 1) == 0);
+    if (p.use_tma && aligned) {
+        if (tid == 0 && span > 0) {
+            bulk_store(gdst, s_out, (uint32_t)span * 8u);
+            bulk_store_wait();
+        }
+    } else {
+        for (int i = tid; i < span; i += LIN_THREADS) gdst[i] = s_out[i];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K3  cost: sum 0.5 rho(|r|^2) with the same tiling and reduction tree as K1.
+// Replaces cost(vars, costs) (src/cost.jl:11) -> computerescost (src/residual.jl:49-55).
+// ---------------------------------------------------------------------------------------------------
+template <class R>
+__global__ void __launch_bounds__(LIN_THREADS) cost_kernel(DevProblem p, const double* __restrict__ cams, const double* __restrict__ pts,
+                                                           double* __restrict__ cost_partials) {
+    __shared__ double s_red[8];
+    const int tid = threadIdx.x, t = blockIdx.x;
+    const int pt0 = p.tile_pt[t], pt1 = p.tile_pt[t + 1];
+    const int ob0 = p.obs_start[pt0], ob1 = p.obs_start[pt1];
+    double c = 0.0;
+    if (tid < ob1 - ob0) {
+        const int j = ob0 + tid;
+        const int cam = p.obs_cam[j];
+        const int pt = p.obs_pt[j];
+        const double2 z = p.obs_z[j];
+        double cv[R::NC];
+        R::load_cam(cams, cam, cv);
+        const double X[3] = {pts[(size_t)3 * pt], pts[(size_t)3 * pt + 1], pts[(size_t)3 * pt + 2]};
+        double r[2];
+        R::residual(cv, X, z.x, z.y, r);
+        c = 0.5 * robustify(p.rk, r[0] * r[0] + r[1] * r[1]);
+    }
+    const double csum = block_sum(c, s_red);
+    if (tid == 0) cost_partials[t] = csum;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K2  lin_cam: camera diagonal blocks U_c = sum J_c' W J_c and g_c over the camera-major observation copy.
+// One CTA per work item (a camera and at most CAM_CHUNK of its observations); fixed-shape reduction.
+// ---------------------------------------------------------------------------------------------------
+template <class R>
+__global__ void __launch_bounds__(256) lin_cam_kernel(DevProblem p, const double* __restrict__ cams, const double* __restrict__ pts,
+                                                      double* __restrict__ partials) {
+    constexpr int DC = R::DC, NU = DC * (DC + 1) / 2 + DC;
+    __shared__ double s_red[8][NU];
+    const int tid = threadIdx.x, item = blockIdx.x;
+    const int cam = p.item_cam[item];
+    const int beg = p.item_beg[item], end = p.item_end[item];
+    double cv[R::NC];
+    R::load_cam(cams, cam, cv);
+    double acc[NU];
+#pragma unroll
+    for (int i = 0; i < NU; ++i) acc[i] = 0.0;
+    for (int j = beg + tid; j < end; j += 256) {
+        const int pt = p.cm_pt[j];
+        const double2 z = p.cm_z[j];
+        const double X[3] = {__ldg(pts + (size_t)3 * pt), __ldg(pts + (size_t)3 * pt + 1), __ldg(pts + (size_t)3 * pt + 2)};
+        double r[2], Jc[2][DC], Jp[2][3];
+        R::resjac(cv, X, z.x, z.y, r, Jc, Jp);
+        const double s = r[0] * r[0] + r[1] * r[1];
+        double rho, d1, d2;
+        robustifydcost(p.rk, s, rho, d1, d2);
+        double gc[DC];
+#pragma unroll
+        for (int a = 0; a < DC; ++a) gc[a] = Jc[0][a] * r[0] + Jc[1][a] * r[1];
+        const double td2 = 2 * d2;
+        int q = 0;
+#pragma unroll
+        for (int a2 = 0; a2 < DC; ++a2)
+#pragma unroll
+            for (int a = a2; a < DC; ++a) {
+                double h = Jc[0][a] * Jc[0][a2] + Jc[1][a] * Jc[1][a2];
+                if (d1 != 1.0) h *= d1;
+                if (d2 != 0.0) h += (td2 * gc[a]) * gc[a2];
+                acc[q++] += h;
+            }
+#pragma unroll
+        for (int a = 0; a < DC; ++a) acc[q++] += (d1 != 1.0) ? gc[a] * d1 : gc[a];
+    }
+    const int lane = tid & 31, w = tid >> 5;
+#pragma unroll
+    for (int i = 0; i < NU; ++i) {
+        const double v = warp_sum(acc[i]);
+        if (lane == 0) s_red[w][i] = v;
+    }
+    __syncthreads();
+    if (tid < NU) {
+        double tsum = 0.0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) tsum += s_red[k][tid];
+        partials[(size_t)item * NU + tid] = tsum;
+    }
+}
+
+// K2b: per camera, add its work-item partials in order and write the full symmetric block + g_c.
+template <int DC>
+__global__ void cam_finalize_kernel(DevProblem p, const double* __restrict__ partials) {
+    constexpr int NU = DC * (DC + 1) / 2 + DC;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= p.nA * NU) return;
+    const int cam = idx / NU, e = idx - cam * NU;
+    double s = 0.0;
+    for (int it = p.cam_item_start[cam]; it < p.cam_item_start[cam + 1]; ++it) s += partials[(size_t)it * NU + e];
+    constexpr int NL = DC * (DC + 1) / 2;
+    if (e < NL) {
+        // e enumerates the lower triangle column by column: (a >= a2)
+        int a2 = 0, rem = e;
+        while (rem >= DC - a2) { rem -= DC - a2; ++a2; }
+        const int a = a2 + rem;
+        double* U = p.H + (size_t)DC * DC * cam;
+        U[a + DC * a2] = s;
+        U[a2 + DC * a] = s;
+    } else {
+        p.g[(size_t)DC * cam + (e - NL)] = s;
+    }
+}
+
+// Sum `n` partials in a fixed order into out[slot] (single CTA).  op: 0 sum, 1 nan-propagating max.
+__global__ void __launch_bounds__(1024) reduce_partials_kernel(const double* __restrict__ partials, int n, double* out, int op) {
+    __shared__ double s_red[32];
+    double v = 0.0;
+    if (op == 0) { for (int i = threadIdx.x; i < n; i += 1024) v += partials[i]; v = block_sum(v, s_red); }
+    else { for (int i = threadIdx.x; i < n; i += 1024) v = nanmax(v, partials[i]); v = block_nanmax(v, s_red); }
+    if (threadIdx.x == 0) *out = v;
+}
+
+// max_i |H_ii| over every diagonal entry (initlambda, src/iterators.jl:131-137). out must be zeroed first.
+template <int DC>
+__global__ void maxdiag_kernel(DevProblem p, unsigned long long* out) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long nc = (long long)DC * p.nA, np = 3LL * p.nB;
+    double v = 0.0;
+    if (idx < nc) {
+        const long long cam = idx / DC; const int a = (int)(idx - cam * DC);
+        v = fabs(p.H[(size_t)DC * DC * cam + a + DC * a]);
+    } else if (idx < nc + np) {
+        const long long k = idx - nc; const long long pt = k / 3; const int b = (int)(k - pt * 3);
+        v = fabs(p.H[(size_t)p.hB + (size_t)3 * DC * p.obs_start[pt + 1] + (size_t)9 * pt + 4 * b]);
+    }
+    v = warp_nanmax(v);
+    if ((threadIdx.x & 31) == 0) atomicMax(out, (unsigned long long)__double_as_longlong(v));  // non-negative doubles order like integers
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Schur elimination of the point blocks (new functionality, mathematically equal to the reference's
+// full-system solve (H + lambda I) x = g, src/linearsolver.jl:29 — SURVEY F3).
+//   A_p = V_p + lambda I ;  S = U + lambda I - sum_p W_p' A_p^-1 W_p ;  rhs = g_c - sum_p W_p' A_p^-1 g_p
+// S is the dense (DC nA)^2 reduced camera matrix, column-major, lower triangle.
+// ---------------------------------------------------------------------------------------------------
+template <int DC>
+__global__ void schur_init_kernel(DevProblem p, double* __restrict__ S, double* __restrict__ rhs, double lambda, int add_u) {
+    // one thread per (camera, element of the lower triangle incl. diagonal) + rhs
+    constexpr int NE = DC * DC;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long n = (long long)DC * p.nA;
+    if (idx < (long long)p.nA * NE) {
+        const long long cam = idx / NE; const int e = (int)(idx - cam * NE);
+        const int a = e % DC, b = e / DC;
+        if (a >= b && add_u) {
+            double v = p.H[(size_t)NE * cam + e];
+            if (a == b) v += lambda;
+            S[(size_t)(cam * DC + a) + (size_t)n * (cam * DC + b)] = v;
+        }
+    } else if (idx < (long long)p.nA * NE + n) {
+        const long long k = idx - (long long)p.nA * NE;
+        rhs[k] = add_u ? p.g[k] : 0.0;
+    }
+}
+
+template <int DC>
+struct SchurSmem {
+    static constexpr int WB = 3 * DC;
+    static constexpr int ROW = WB * TILE_OBS + 9 * TILE_PTS;
+    static constexpr int Y = WB * TILE_OBS;
+    static constexpr size_t bytes = (size_t)(ROW + Y + 6 * TILE_PTS + 3 * TILE_PTS + 2) * sizeof(double) + (TILE_PTS + 4) * sizeof(int) + 16;
+};
+
+// load the tile's contiguous H span into shared memory (TMA bulk load when 16-byte aligned)
+__device__ __forceinline__ void load_span(double* s_dst, const double* gsrc, int span, uint64_t* bar, int use_tma) {
+    const bool aligned = ((reinterpret_cast<uintptr_t>(gsrc) & 15) == 0) && ((span & 1) == 0);
+    if (use_tma && aligned && span > 0) {
+        if (threadIdx.x == 0) {
+            mbar_init(bar, 1);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            mbar_expect_tx(bar, (uint32_t)span * 8u);
+            bulk_load(s_dst, gsrc, (uint32_t)span * 8u, bar);
+        }
+        mbar_wait(bar, 0);
+    } else {
+        for (int i = threadIdx.x; i < span; i += blockDim.x) s_dst[i] = gsrc[i];
+        __syncthreads();
+    }
+}
+
+template <int DC>
+__global__ void __launch_bounds__(LIN_THREADS) schur_tile_kernel(DevProblem p, double* __restrict__ S, double* __restrict__ rhs,
+                                                                 double* __restrict__ Ainv_out, double lambda) {
+    constexpr int WB = 3 * DC;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* s_row = reinterpret_cast<double*>(smem_raw);
+    double* s_Y = s_row + SchurSmem<DC>::ROW;
+    double* s_Ai = s_Y + SchurSmem<DC>::Y;
+    double* s_t = s_Ai + 6 * TILE_PTS;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(s_t + 3 * TILE_PTS);
+    int* s_ost = reinterpret_cast<int*>(bar + 2);
+
+    const int tid = threadIdx.x, t = blockIdx.x;
+    const int pt0 = p.tile_pt[t], pt1 = p.tile_pt[t + 1];
+    const int ob0 = p.obs_start[pt0], ob1 = p.obs_start[pt1];
+    const int npt = pt1 - pt0, nob = ob1 - ob0;
+    const long long n = (long long)DC * p.nA;
+    for (int i = tid; i <= npt; i += LIN_THREADS) s_ost[i] = p.obs_start[pt0 + i] - ob0;
+    const size_t span0 = (size_t)p.hB + (size_t)WB * ob0 + (size_t)9 * pt0;
+    load_span(s_row, p.H + span0, WB * nob + 9 * npt, bar, p.use_tma);
+    __syncthreads();
+
+    if (tid < npt) {  // A_p^-1 and t_p = A_p^-1 g_p
+        const double* V = s_row + WB * s_ost[tid + 1] + 9 * tid;
+        const double a[6] = {V[0] + lambda, V[1], V[2], V[4] + lambda, V[5], V[8] + lambda};
+        double inv[6];
+        inv_sym3(a, inv);
+#pragma unroll
+        for (int i = 0; i < 6; ++i) { s_Ai[6 * tid + i] = inv[i]; Ainv_out[(size_t)6 * (pt0 + tid) + i] = inv[i]; }
+        const double* gp = p.g + p.gB + (size_t)3 * (pt0 + tid);
+        const double g0 = gp[0], g1 = gp[1], g2 = gp[2];
+        s_t[3 * tid] = inv[0] * g0 + inv[1] * g1 + inv[2] * g2;
+        s_t[3 * tid + 1] = inv[1] * g0 + inv[3] * g1 + inv[4] * g2;
+        s_t[3 * tid + 2] = inv[2] * g0 + inv[4] * g1 + inv[5] * g2;
+    }
+    __syncthreads();
+
+    double W[WB];
+    int cam = 0, pl = 0;
+    if (tid < nob) {
+        cam = p.obs_cam[ob0 + tid];
+        pl = p.obs_pt[ob0 + tid] - pt0;
+        const double* w = s_row + WB * tid + 9 * pl;
+#pragma unroll
+        for (int i = 0; i < WB; ++i) W[i] = w[i];
+        const double* ai = s_Ai + 6 * pl;
+        const double i00 = ai[0], i10 = ai[1], i20 = ai[2], i11 = ai[3], i21 = ai[4], i22 = ai[5];
+        const double t0 = s_t[3 * pl], t1 = s_t[3 * pl + 1], t2 = s_t[3 * pl + 2];
+        double* y = s_Y + WB * tid;
+#pragma unroll
+        for (int a = 0; a < DC; ++a) {
+            const double w0 = W[3 * a], w1 = W[3 * a + 1], w2 = W[3 * a + 2];
+            y[3 * a] = i00 * w0 + i10 * w1 + i20 * w2;
+            y[3 * a + 1] = i10 * w0 + i11 * w1 + i21 * w2;
+            y[3 * a + 2] = i20 * w0 + i21 * w1 + i22 * w2;
+            atomicAdd(rhs + (size_t)cam * DC + a, -(w0 * t0 + w1 * t1 + w2 * t2));
+        }
+    }
+    __syncthreads();
+    if (tid < nob) {
+        const int jbeg = s_ost[pl];
+        for (int j = jbeg; j <= tid; ++j) {   // cameras ascend within a point: cam_j <= cam_i -> lower triangle
+            const int camj = p.obs_cam[ob0 + j];
+            const double* y = s_Y + WB * j;
+            double* Sb = S + (size_t)cam * DC + (size_t)n * ((size_t)camj * DC);
+#pragma unroll
+            for (int b = 0; b < DC; ++b) {
+                const double y0 = y[3 * b], y1 = y[3 * b + 1], y2 = y[3 * b + 2];
+#pragma unroll
+                for (int a = 0; a < DC; ++a) {
+                    if (j == tid && a < b) continue;
+                    const double v = W[3 * a] * y0 + W[3 * a + 1] * y1 + W[3 * a + 2] * y2;
+                    atomicAdd(Sb + a + (size_t)n * b, -v);
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Back-substitution + variable update + step statistics for one tile of points.
+//   dx_p = A_p^-1 (g_p - sum_c W_pc dx_c);  x = -dx (negate!, src/iterators.jl:152);
+//   varnext[p] = update(variables[p], x)  (src/linearsystem.jl:206-213, src/variable.jl:10)
+// Partials per tile: [0] max|x_p|, [1] sum x_p^2, [2] x'Hx terms owned by the point rows, [3] g_p . x_p
+// (x'Hx uses the UNdamped H like src/iterators.jl:162-163).
+// ---------------------------------------------------------------------------------------------------
+template <int DC>
+__global__ void __launch_bounds__(LIN_THREADS) backsub_tile_kernel(DevProblem p, const double* __restrict__ dxc, const double* __restrict__ Ainv,
+                                                                   const double* __restrict__ pts, double* __restrict__ pts_next,
+                                                                   double* __restrict__ x, double* __restrict__ partials) {
+    constexpr int WB = 3 * DC;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* s_row = reinterpret_cast<double*>(smem_raw);
+    double* s_u = s_row + SchurSmem<DC>::ROW;       // 3 per observation: W_pc dx_c
+    double* s_red = s_u + 3 * TILE_OBS;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(s_red + 8);
+    int* s_ost = reinterpret_cast<int*>(bar + 2);
+
+    const int tid = threadIdx.x, t = blockIdx.x;
+    const int pt0 = p.tile_pt[t], pt1 = p.tile_pt[t + 1];
+    const int ob0 = p.obs_start[pt0], ob1 = p.obs_start[pt1];
+    const int npt = pt1 - pt0, nob = ob1 - ob0;
+    for (int i = tid; i <= npt; i += LIN_THREADS) s_ost[i] = p.obs_start[pt0 + i] - ob0;
+    const size_t span0 = (size_t)p.hB + (size_t)WB * ob0 + (size_t)9 * pt0;
+    load_span(s_row, p.H + span0, WB * nob + 9 * npt, bar, p.use_tma);
+    __syncthreads();
+
+    if (tid < nob) {
+        const int cam = p.obs_cam[ob0 + tid];
+        const int pl = p.obs_pt[ob0 + tid] - pt0;
+        const double* w = s_row + WB * tid + 9 * pl;
+        double u0 = 0, u1 = 0, u2 = 0;
+#pragma unroll
+        for (int a = 0; a < DC; ++a) {
+            const double d = dxc[(size_t)cam * DC + a];
+            u0 += w[3 * a] * d; u1 += w[3 * a + 1] * d; u2 += w[3 * a + 2] * d;
+        }
+        s_u[3 * tid] = u0; s_u[3 * tid + 1] = u1; s_u[3 * tid + 2] = u2;
+    }
+    __syncthreads();
+    double mx = 0.0, sq = 0.0, xhx = 0.0, gx = 0.0;
+    if (tid < npt) {
+        double u0 = 0, u1 = 0, u2 = 0;
+        for (int j = s_ost[tid]; j < s_ost[tid + 1]; ++j) { u0 += s_u[3 * j]; u1 += s_u[3 * j + 1]; u2 += s_u[3 * j + 2]; }
+        const size_t pt = (size_t)pt0 + tid;
+        const double* gp = p.g + p.gB + 3 * pt;
+        const double g0 = gp[0], g1 = gp[1], g2 = gp[2];
+        const double r0 = g0 - u0, r1 = g1 - u1, r2 = g2 - u2;
+        const double* ai = Ainv + 6 * pt;
+        const double x0 = -(ai[0] * r0 + ai[1] * r1 + ai[2] * r2);
+        const double x1 = -(ai[1] * r0 + ai[3] * r1 + ai[4] * r2);
+        const double x2 = -(ai[2] * r0 + ai[4] * r1 + ai[5] * r2);
+        x[p.gB + 3 * pt] = x0; x[p.gB + 3 * pt + 1] = x1; x[p.gB + 3 * pt + 2] = x2;
+        pts_next[3 * pt] = pts[3 * pt] + x0;
+        pts_next[3 * pt + 1] = pts[3 * pt + 1] + x1;
+        pts_next[3 * pt + 2] = pts[3 * pt + 2] + x2;
+        mx = nanmax(nanmax(fabs(x0), fabs(x1)), fabs(x2));
+        sq = x0 * x0 + x1 * x1 + x2 * x2;
+        gx = g0 * x0 + g1 * x1 + g2 * x2;
+        const double* V = s_row + WB * s_ost[tid + 1] + 9 * tid;
+        const double v0 = V[0] * x0 + V[3] * x1 + V[6] * x2;
+        const double v1 = V[1] * x0 + V[4] * x1 + V[7] * x2;
+        const double v2 = V[2] * x0 + V[5] * x1 + V[8] * x2;
+        // x_p' V x_p + 2 x_p' (sum_c W_pc x_c),  with x_c = -dx_c  =>  sum_c W_pc x_c = -u
+        xhx = (x0 * v0 + x1 * v1 + x2 * v2) - 2.0 * (x0 * u0 + x1 * u1 + x2 * u2);
+    }
+    const double rmx = block_nanmax(mx, s_red);
+    __syncthreads();
+    const double rsq = block_sum(sq, s_red);
+    __syncthreads();
+    const double rxhx = block_sum(xhx, s_red);
+    __syncthreads();
+    const double rgx = block_sum(gx, s_red);
+    if (tid == 0) {
+        partials[t] = rmx;
+        partials[p.ntiles + t] = rsq;
+        partials[2 * p.ntiles + t] = rxhx;
+        partials[3 * p.ntiles + t] = rgx;
+    }
+}
+
+// Camera side of the update: x_c = -dx_c, varnext[c] = update(variables[c], x_c), plus the camera terms of the step
+// statistics.  Single CTA (cameras are few); out4 = {max|x_c|, sum x_c^2, sum x_c' U_c x_c, g_c . x_c}.
+template <class R>
+__global__ void __launch_bounds__(256) cam_update_kernel(DevProblem p, const double* __restrict__ dxc, const double* __restrict__ cams,
+                                                         double* __restrict__ cams_next, double* __restrict__ x, double* __restrict__ out4) {
+    constexpr int DC = R::DC;
+    __shared__ double s_red[8];
+    double mx = 0.0, sq = 0.0, xhx = 0.0, gx = 0.0;
+    for (int cam = threadIdx.x; cam < p.nA; cam += 256) {
+        double xc[DC];
+#pragma unroll
+        for (int a = 0; a < DC; ++a) {
+            xc[a] = -dxc[(size_t)cam * DC + a];
+            x[(size_t)cam * DC + a] = xc[a];
+            mx = nanmax(mx, fabs(xc[a]));
+            sq += xc[a] * xc[a];
+            gx += p.g[(size_t)cam * DC + a] * xc[a];
+        }
+        const double* U = p.H + (size_t)DC * DC * cam;
+#pragma unroll
+        for (int b = 0; b < DC; ++b) {
+            double s = 0.0;
+#pragma unroll
+            for (int a = 0; a < DC; ++a) s += U[a + DC * b] * xc[a];
+            xhx += xc[b] * s;
+        }
+        R::update_cam(cams + (size_t)cam * R::CS, xc, cams_next + (size_t)cam * R::CS);
+    }
+    const double rmx = block_nanmax(mx, s_red);
+    __syncthreads();
+    const double rsq = block_sum(sq, s_red);
+    __syncthreads();
+    const double rxhx = block_sum(xhx, s_red);
+    __syncthreads();
+    const double rgx = block_sum(gx, s_red);
+    if (threadIdx.x == 0) { out4[0] = rmx; out4[1] = rsq; out4[2] = rxhx; out4[3] = rgx; }
+}
+
+// mirror the lower triangle of the dense n x n matrix into the upper one (LU fallback for non-PD systems)
+__global__ void symmetrize_kernel(double* S, long long n) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n * n) return;
+    const long long r = idx % n, c = idx / n;
+    if (r < c) S[idx] = S[c + n * r];
+}
+
+}  // namespace nlls

@@ -1,0 +1,1061 @@
+// libnlls_b200 — C ABI implementation (see include/nlls_b200.h for the reference call each symbol replaces).
+// Host logic mirrors src/optimize.jl:109-180 and src/iterators.jl:139-172; every numeric operation runs in the
+// sm_100a kernels of kernels.cuh.  There is no CPU compute path: without a CUDA device nlls_create fails.
+#include <cuda_runtime.h>
+#include <cusolverDn.h>
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <limits>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/nlls_b200.h"
+#include "kernels.cuh"
+
+using namespace nlls;
+
+// ---------------------------------------------------------------------------------------------------
+// NCCL, resolved lazily with dlopen so that single-GPU use has no NCCL dependency.
+// ---------------------------------------------------------------------------------------------------
+namespace {
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+enum { ncclSum = 0, ncclMax = 2 };
+enum { ncclFloat64 = 8 };
+struct NcclApi {
+    void* h = nullptr;
+    int (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    int (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    int (*CommDestroy)(ncclComm_t) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    bool load() {
+        if (h) return true;
+        const char* names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char* n : names) { h = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (h) break; }
+        if (!h) return false;
+        GetUniqueId = (int (*)(ncclUniqueId*))dlsym(h, "ncclGetUniqueId");
+        CommInitRank = (int (*)(ncclComm_t*, int, ncclUniqueId, int))dlsym(h, "ncclCommInitRank");
+        CommDestroy = (int (*)(ncclComm_t))dlsym(h, "ncclCommDestroy");
+        AllReduce = (int (*)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t))dlsym(h, "ncclAllReduce");
+        GroupStart = (int (*)())dlsym(h, "ncclGroupStart");
+        GroupEnd = (int (*)())dlsym(h, "ncclGroupEnd");
+        GetErrorString = (const char* (*)(int))dlsym(h, "ncclGetErrorString");
+        return GetUniqueId && CommInitRank && CommDestroy && AllReduce && GroupStart && GroupEnd;
+    }
+};
+NcclApi g_nccl;
+
+inline uint64_t now_ns() {
+    return (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+struct VarSet {
+    int vartype = 0;
+    int nstore = 0;
+    std::vector<int64_t> gidx;  // 1-based positions in problem.variables, ascending
+    std::vector<double> vals;   // n x nstore
+    bool stale = false;         // device copy is newer than `vals` (values were refreshed straight from the caller's buffer)
+};
+
+// scalar slots in the device/pinned scalar buffer
+enum Scal {
+    SC_COST_LIN = 0, SC_COST_TRY = 1,
+    SC_P_MAX = 2, SC_P_SQ = 3, SC_P_XHX = 4, SC_P_GX = 5,      // point-row terms (summed / maxed over ranks)
+    SC_C_MAX = 6, SC_C_SQ = 7, SC_C_XHX = 8, SC_C_GX = 9,      // camera terms (replicated)
+    SC_MAXDIAG = 10, SC_INFO = 11, SC_COUNT = 16
+};
+}  // namespace
+
+struct nlls_ctx {
+    int device = 0;
+    cudaStream_t st = nullptr, st2 = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_t0 = nullptr, ev_t1 = nullptr, ev_b0 = nullptr, ev_b1 = nullptr;
+    std::string err;
+    int64_t launches = 0;
+
+    // ---- definition
+    std::map<int, VarSet> vars;
+    int restype = 0;
+    int robust = 0;
+    double kparams[2] = {0, 1};
+    std::vector<int64_t> h_cam_g, h_pt_g;  // global 1-based indices per cost, storage order
+    std::vector<double> h_z;               // 2 per cost
+    bool prepared = false;
+
+    // ---- layout (host copies kept for read-back)
+    int vtA = 0, vtB = 0, DC = 0, NC = 0, CS = 0;
+    int64_t nA = 0, nB = 0, nobs = 0, dof = 0, hlen = 0, nred = 0;
+    bool cams_first = true;
+    std::vector<int> h_obs_cam, h_obs_pt, h_obs_start, h_tile_pt, h_cam_start, h_cm_obs;
+    int ntiles = 0, nitems = 0;
+
+    // ---- device
+    int *d_obs_cam = nullptr, *d_obs_pt = nullptr, *d_obs_start = nullptr, *d_tile_pt = nullptr;
+    double2* d_obs_z = nullptr;
+    int *d_cm_pt = nullptr, *d_item_cam = nullptr, *d_item_beg = nullptr, *d_item_end = nullptr, *d_cam_item_start = nullptr;
+    double2* d_cm_z = nullptr;
+    double *d_A[3] = {nullptr, nullptr, nullptr}, *d_B[3] = {nullptr, nullptr, nullptr};
+    int cur = 0, nxt = 1, bst = 2;
+    double *d_H = nullptr, *d_g = nullptr, *d_x = nullptr, *d_Ainv = nullptr, *d_S = nullptr, *d_rhs = nullptr;
+    double *d_cost_part = nullptr, *d_step_part = nullptr, *d_cam_part = nullptr;
+    double *d_scal = nullptr, *h_scal = nullptr;
+    void* d_flush = nullptr;
+    size_t flush_bytes = 0;
+    cusolverDnHandle_t cusolver = nullptr;
+    double* d_work = nullptr;
+    int lwork = 0;
+    int* d_info = nullptr;
+    int* d_ipiv = nullptr;
+    int use_tma = 1;
+
+    // ---- multi-GPU
+    int rank = 0, nranks = 1;
+    ncclComm_t comm = nullptr;
+
+    // ---- LM state (src/iterators.jl:120-126, src/optimize.jl:109-121)
+    nlls_options opts{};
+    double lambda = 0.0, bestcost = 0.0, cost = 0.0, startcost = 0.0, maxstep = 0.0;
+    int64_t fails = 0, iternum = 0, converged = 0;
+    int64_t costcomputations = 0, gradientcomputations = 0, linearsolvers = 0;
+    uint64_t starttime = 0, stoptime = 0, t_init = 0, t_cost = 0, t_grad = 0, t_solver = 0;
+    bool lm_active = false;
+    bool have_best = false;
+};
+
+#define CK(call)                                                                                              \
+    do {                                                                                                      \
+        cudaError_t e__ = (call);                                                                             \
+        if (e__ != cudaSuccess) {                                                                             \
+            ctx->err = std::string(#call) + ": " + cudaGetErrorString(e__);                                   \
+            return NLLS_ERR_CUDA;                                                                             \
+        }                                                                                                     \
+    } while (0)
+#define CKS(call)                                                                                             \
+    do {                                                                                                      \
+        cusolverStatus_t s__ = (call);                                                                        \
+        if (s__ != CUSOLVER_STATUS_SUCCESS) {                                                                 \
+            ctx->err = std::string(#call) + ": cusolver status " + std::to_string((int)s__);                  \
+            return NLLS_ERR_CUDA;                                                                             \
+        }                                                                                                     \
+    } while (0)
+#define CKN(call)                                                                                             \
+    do {                                                                                                      \
+        int r__ = (call);                                                                                     \
+        if (r__ != 0) {                                                                                       \
+            ctx->err = std::string(#call) + ": " + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r__) : "nccl error"); \
+            return NLLS_ERR_NCCL;                                                                             \
+        }                                                                                                     \
+    } while (0)
+#define FAIL(code, msg)        \
+    do {                       \
+        ctx->err = (msg);      \
+        return (code);         \
+    } while (0)
+#define TRY(call)                     \
+    do {                              \
+        int rc__ = (call);            \
+        if (rc__ != NLLS_OK) return rc__; \
+    } while (0)
+
+namespace {
+
+template <class T>
+int upload(nlls_ctx* ctx, T** dptr, const std::vector<T>& h) {
+    if (*dptr) { cudaFree(*dptr); *dptr = nullptr; }
+    size_t bytes = std::max<size_t>(h.size(), 1) * sizeof(T);
+    CK(cudaMalloc((void**)dptr, bytes));
+    if (!h.empty()) CK(cudaMemcpy(*dptr, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return NLLS_OK;
+}
+template <class T>
+int dalloc(nlls_ctx* ctx, T** dptr, size_t n) {
+    if (*dptr) { cudaFree(*dptr); *dptr = nullptr; }
+    CK(cudaMalloc((void**)dptr, std::max<size_t>(n, 1) * sizeof(T)));
+    return NLLS_OK;
+}
+
+DevProblem devproblem(const nlls_ctx* c) {
+    DevProblem p;
+    p.obs_cam = c->d_obs_cam; p.obs_pt = c->d_obs_pt; p.obs_z = c->d_obs_z; p.obs_start = c->d_obs_start;
+    p.tile_pt = c->d_tile_pt; p.ntiles = c->ntiles; p.nA = (int)c->nA; p.nB = (int)c->nB; p.nobs = (int)c->nobs;
+    p.cm_pt = c->d_cm_pt; p.cm_z = c->d_cm_z; p.item_cam = c->d_item_cam; p.item_beg = c->d_item_beg; p.item_end = c->d_item_end;
+    p.cam_item_start = c->d_cam_item_start; p.nitems = c->nitems;
+    p.H = c->d_H; p.g = c->d_g; p.hB = (long long)c->DC * c->DC * c->nA; p.gB = (long long)c->DC * c->nA;
+    p.rk.kind = c->robust & 15; p.rk.scaled = (c->robust & NLLS_ROBUST_SCALED) ? 1 : 0;
+    p.rk.width = c->kparams[0]; p.rk.width2 = c->kparams[0] * c->kparams[0]; p.rk.height = c->kparams[1];
+    p.use_tma = c->use_tma;
+    return p;
+}
+
+int vartype_nstore(int vt) {
+    switch (vt) {
+        case NLLS_VAR_SCALAR: return 1;
+        case NLLS_VAR_EUCLID3: return 3;
+        case NLLS_VAR_EUCLID6: return 6;
+        case NLLS_VAR_CONTAMGAUSS: return 3;
+        case NLLS_VAR_PINHOLE: return 15;
+    }
+    return 0;
+}
+
+// pack host variables (nstore per variable) into the device stride and upload to buffer `which`
+int upload_vars(nlls_ctx* ctx, const VarSet& vs, int dstride, double* dst) {
+    const int64_t n = (int64_t)vs.gidx.size();
+    if (dstride == vs.nstore) {
+        CK(cudaMemcpyAsync(dst, vs.vals.data(), sizeof(double) * n * dstride, cudaMemcpyHostToDevice, ctx->st));
+    } else {
+        std::vector<double> tmp((size_t)n * dstride, 0.0);
+        for (int64_t i = 0; i < n; ++i) std::memcpy(&tmp[(size_t)i * dstride], &vs.vals[(size_t)i * vs.nstore], sizeof(double) * vs.nstore);
+        CK(cudaMemcpyAsync(dst, tmp.data(), sizeof(double) * n * dstride, cudaMemcpyHostToDevice, ctx->st));
+        CK(cudaStreamSynchronize(ctx->st));
+    }
+    return NLLS_OK;
+}
+
+// ---- kernel launch helpers, dispatched on the registered residual type --------------------------------
+template <class R>
+int set_smem_attrs(nlls_ctx* ctx) {
+    CK(cudaFuncSetAttribute(lin_point_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LinSmem<R>::bytes));
+    CK(cudaFuncSetAttribute(schur_tile_kernel<R::DC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SchurSmem<R::DC>::bytes));
+    CK(cudaFuncSetAttribute(backsub_tile_kernel<R::DC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SchurSmem<R::DC>::bytes));
+    return NLLS_OK;
+}
+
+int allreduce(nlls_ctx* ctx, double* buf, size_t count, int op) {
+    if (ctx->nranks <= 1) return NLLS_OK;
+    CKN(g_nccl.AllReduce(buf, buf, count, ncclFloat64, op, ctx->comm, ctx->st));
+    return NLLS_OK;
+}
+
+template <class R>
+int launch_linearize(nlls_ctx* ctx, bool do_point = true, bool do_cam = true) {
+    DevProblem p = devproblem(ctx);
+    constexpr int NU = R::DC * (R::DC + 1) / 2 + R::DC;
+    if (do_cam) {
+        CK(cudaEventRecord(ctx->ev_fork, ctx->st));
+        CK(cudaStreamWaitEvent(ctx->st2, ctx->ev_fork, 0));
+        if (ctx->nitems > 0) { lin_cam_kernel<R><<<ctx->nitems, 256, 0, ctx->st2>>>(p, ctx->d_A[ctx->cur], ctx->d_B[ctx->cur], ctx->d_cam_part); ctx->launches++; }
+        const int tot = (int)ctx->nA * NU;
+        cam_finalize_kernel<R::DC><<<(tot + 255) / 256, 256, 0, ctx->st2>>>(p, ctx->d_cam_part); ctx->launches++;
+        CK(cudaEventRecord(ctx->ev_join, ctx->st2));
+    }
+    if (do_point && ctx->ntiles > 0) {
+        lin_point_kernel<R><<<ctx->ntiles, LIN_THREADS, LinSmem<R>::bytes, ctx->st>>>(p, ctx->d_A[ctx->cur], ctx->d_B[ctx->cur], ctx->d_cost_part);
+        ctx->launches++;
+    }
+    if (do_cam) CK(cudaStreamWaitEvent(ctx->st, ctx->ev_join, 0));
+    CK(cudaGetLastError());
+    return NLLS_OK;
+}
+
+template <class R>
+int launch_cost(nlls_ctx* ctx, int which, int slot) {
+    DevProblem p = devproblem(ctx);
+    if (ctx->ntiles > 0) { cost_kernel<R><<<ctx->ntiles, LIN_THREADS, 0, ctx->st>>>(p, ctx->d_A[which], ctx->d_B[which], ctx->d_cost_part); ctx->launches++; }
+    reduce_partials_kernel<<<1, 1024, 0, ctx->st>>>(ctx->d_cost_part, ctx->ntiles, ctx->d_scal + slot, 0); ctx->launches++;
+    CK(cudaGetLastError());
+    TRY(allreduce(ctx, ctx->d_scal + slot, 1, ncclSum));
+    return NLLS_OK;
+}
+
+template <class R>
+int launch_schur(nlls_ctx* ctx, double lambda) {
+    constexpr int DC = R::DC;
+    DevProblem p = devproblem(ctx);
+    const int64_t n = ctx->nred;
+    CK(cudaMemsetAsync(ctx->d_S, 0, sizeof(double) * (size_t)n * n, ctx->st));
+    const long long tot = (long long)ctx->nA * DC * DC + n;
+    schur_init_kernel<DC><<<(unsigned)((tot + 255) / 256), 256, 0, ctx->st>>>(p, ctx->d_S, ctx->d_rhs, lambda, ctx->rank == 0 ? 1 : 0); ctx->launches++;
+    if (ctx->ntiles > 0) {
+        schur_tile_kernel<DC><<<ctx->ntiles, LIN_THREADS, SchurSmem<DC>::bytes, ctx->st>>>(p, ctx->d_S, ctx->d_rhs, ctx->d_Ainv, lambda);
+        ctx->launches++;
+    }
+    CK(cudaGetLastError());
+    if (ctx->nranks > 1) {
+        CKN(g_nccl.GroupStart());
+        CKN(g_nccl.AllReduce(ctx->d_S, ctx->d_S, (size_t)n * n, ncclFloat64, ncclSum, ctx->comm, ctx->st));
+        CKN(g_nccl.AllReduce(ctx->d_rhs, ctx->d_rhs, (size_t)n, ncclFloat64, ncclSum, ctx->comm, ctx->st));
+        CKN(g_nccl.GroupEnd());
+    }
+    return NLLS_OK;
+}
+
+int launch_reduced_solve(nlls_ctx* ctx, bool lu) {
+    const int n = (int)ctx->nred;
+    if (!lu) {
+        CKS(cusolverDnDpotrf(ctx->cusolver, CUBLAS_FILL_MODE_LOWER, n, ctx->d_S, n, ctx->d_work, ctx->lwork, ctx->d_info));
+        // potrs on a failed factorisation yields garbage; the host checks info and redoes the try with LU
+        CKS(cusolverDnDpotrs(ctx->cusolver, CUBLAS_FILL_MODE_LOWER, n, 1, ctx->d_S, n, ctx->d_rhs, n, ctx->d_info + 1));
+    } else {
+        symmetrize_kernel<<<(unsigned)(((long long)n * n + 255) / 256), 256, 0, ctx->st>>>(ctx->d_S, n); ctx->launches++;
+        CKS(cusolverDnDgetrf(ctx->cusolver, n, n, ctx->d_S, n, ctx->d_work, ctx->d_ipiv, ctx->d_info));
+        CKS(cusolverDnDgetrs(ctx->cusolver, CUBLAS_OP_N, n, 1, ctx->d_S, n, ctx->d_ipiv, ctx->d_rhs, n, ctx->d_info + 1));
+    }
+    return NLLS_OK;
+}
+
+template <class R>
+int launch_update(nlls_ctx* ctx) {
+    constexpr int DC = R::DC;
+    DevProblem p = devproblem(ctx);
+    if (ctx->ntiles > 0) {
+        backsub_tile_kernel<DC><<<ctx->ntiles, LIN_THREADS, SchurSmem<DC>::bytes, ctx->st>>>(p, ctx->d_rhs, ctx->d_Ainv, ctx->d_B[ctx->cur],
+                                                                                              ctx->d_B[ctx->nxt], ctx->d_x, ctx->d_step_part);
+        ctx->launches++;
+    }
+    cam_update_kernel<R><<<1, 256, 0, ctx->st>>>(p, ctx->d_rhs, ctx->d_A[ctx->cur], ctx->d_A[ctx->nxt], ctx->d_x, ctx->d_scal + SC_C_MAX); ctx->launches++;
+    reduce_partials_kernel<<<1, 1024, 0, ctx->st>>>(ctx->d_step_part, ctx->ntiles, ctx->d_scal + SC_P_MAX, 1); ctx->launches++;
+    for (int k = 1; k < 4; ++k) {
+        reduce_partials_kernel<<<1, 1024, 0, ctx->st>>>(ctx->d_step_part + (size_t)k * ctx->ntiles, ctx->ntiles, ctx->d_scal + SC_P_MAX + k, 0); ctx->launches++;
+    }
+    CK(cudaGetLastError());
+    if (ctx->nranks > 1) {
+        CKN(g_nccl.GroupStart());
+        CKN(g_nccl.AllReduce(ctx->d_scal + SC_P_MAX, ctx->d_scal + SC_P_MAX, 1, ncclFloat64, ncclMax, ctx->comm, ctx->st));
+        CKN(g_nccl.AllReduce(ctx->d_scal + SC_P_SQ, ctx->d_scal + SC_P_SQ, 3, ncclFloat64, ncclSum, ctx->comm, ctx->st));
+        CKN(g_nccl.GroupEnd());
+    }
+    return NLLS_OK;
+}
+
+template <class R>
+int launch_maxdiag(nlls_ctx* ctx) {
+    DevProblem p = devproblem(ctx);
+    CK(cudaMemsetAsync(ctx->d_scal + SC_MAXDIAG, 0, sizeof(double), ctx->st));
+    const long long tot = ctx->dof;
+    maxdiag_kernel<R::DC><<<(unsigned)((tot + 255) / 256), 256, 0, ctx->st>>>(p, (unsigned long long*)(ctx->d_scal + SC_MAXDIAG)); ctx->launches++;
+    CK(cudaGetLastError());
+    TRY(allreduce(ctx, ctx->d_scal + SC_MAXDIAG, 1, ncclMax));
+    return NLLS_OK;
+}
+
+#define DISPATCH(ctx, fn, ...)                                                                 \
+    ((ctx)->restype == NLLS_RES_AFFINE_BA ? fn<AffineBA>(__VA_ARGS__)                          \
+     : (ctx)->restype == NLLS_RES_PINHOLE_BA ? fn<PinholeBA>(__VA_ARGS__)                      \
+                                             : (int)NLLS_ERR_NO_KERNEL)
+
+int fetch_scalars(nlls_ctx* ctx) {
+    CK(cudaMemcpyAsync(ctx->h_scal, ctx->d_scal, sizeof(double) * SC_COUNT, cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaMemcpyAsync(ctx->h_scal + SC_COUNT, ctx->d_info, sizeof(int) * 2, cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    return NLLS_OK;
+}
+
+int do_linearize(nlls_ctx* ctx, double* cost) {
+    TRY(DISPATCH(ctx, launch_linearize, ctx, true, true));
+    if (ctx->nranks > 1) {  // camera blocks + camera gradient are sums over all ranks' observations
+        CKN(g_nccl.GroupStart());
+        CKN(g_nccl.AllReduce(ctx->d_H, ctx->d_H, (size_t)ctx->DC * ctx->DC * ctx->nA, ncclFloat64, ncclSum, ctx->comm, ctx->st));
+        CKN(g_nccl.AllReduce(ctx->d_g, ctx->d_g, (size_t)ctx->DC * ctx->nA, ncclFloat64, ncclSum, ctx->comm, ctx->st));
+        CKN(g_nccl.GroupEnd());
+    }
+    reduce_partials_kernel<<<1, 1024, 0, ctx->st>>>(ctx->d_cost_part, ctx->ntiles, ctx->d_scal + SC_COST_LIN, 0); ctx->launches++;
+    CK(cudaGetLastError());
+    TRY(allreduce(ctx, ctx->d_scal + SC_COST_LIN, 1, ncclSum));
+    TRY(fetch_scalars(ctx));
+    if (cost) *cost = ctx->h_scal[SC_COST_LIN];
+    return NLLS_OK;
+}
+
+// one LM try without the host sync: damp + Schur + reduced solve + back-substitution/update + cost(varnext)
+int enqueue_try(nlls_ctx* ctx, double lambda, bool lu) {
+    TRY(DISPATCH(ctx, launch_schur, ctx, lambda));
+    TRY(launch_reduced_solve(ctx, lu));
+    TRY(DISPATCH(ctx, launch_update, ctx));
+    TRY(DISPATCH(ctx, launch_cost, ctx, ctx->nxt, SC_COST_TRY));
+    return NLLS_OK;
+}
+
+int do_try(nlls_ctx* ctx, double lambda) {
+    TRY(enqueue_try(ctx, lambda, false));
+    TRY(fetch_scalars(ctx));
+    const int* info = reinterpret_cast<const int*>(ctx->h_scal + SC_COUNT);
+    if (info[0] != 0) {  // not positive definite: the reference falls back to QR / pivot-free LDL' (src/linearsolver.jl:20-26,29); we use LU
+        TRY(enqueue_try(ctx, lambda, true));
+        TRY(fetch_scalars(ctx));
+    }
+    return NLLS_OK;
+}
+
+}  // namespace
+
+// =====================================================================================================
+extern "C" {
+
+int nlls_version(void) { return 100; }
+
+int nlls_create(nlls_ctx** out, int device) {
+    if (!out) return NLLS_ERR_INVALID;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) return NLLS_ERR_NO_DEVICE;
+    nlls_ctx* ctx = new nlls_ctx();
+    ctx->device = device;
+    if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return NLLS_ERR_CUDA; }
+    cudaStreamCreateWithFlags(&ctx->st, cudaStreamNonBlocking);
+    cudaStreamCreateWithFlags(&ctx->st2, cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
+    cudaEventCreate(&ctx->ev_t0);
+    cudaEventCreate(&ctx->ev_t1);
+    cudaEventCreate(&ctx->ev_b0);
+    cudaEventCreate(&ctx->ev_b1);
+    cudaMalloc((void**)&ctx->d_scal, sizeof(double) * SC_COUNT);
+    cudaMemset(ctx->d_scal, 0, sizeof(double) * SC_COUNT);
+    cudaMallocHost((void**)&ctx->h_scal, sizeof(double) * (SC_COUNT + 2));
+    cudaMalloc((void**)&ctx->d_info, sizeof(int) * 2);
+    cudaMemset(ctx->d_info, 0, sizeof(int) * 2);
+    if (cusolverDnCreate(&ctx->cusolver) != CUSOLVER_STATUS_SUCCESS) { delete ctx; return NLLS_ERR_CUDA; }
+    cusolverDnSetStream(ctx->cusolver, ctx->st);
+    const char* e = getenv("NLLS_B200_TMA");
+    ctx->use_tma = (e && e[0] == '0') ? 0 : 1;
+    if (cudaGetLastError() != cudaSuccess) { delete ctx; return NLLS_ERR_CUDA; }
+    *out = ctx;
+    return NLLS_OK;
+}
+
+int nlls_destroy(nlls_ctx* ctx) {
+    if (!ctx) return NLLS_OK;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    void* ptrs[] = {ctx->d_obs_cam, ctx->d_obs_pt, ctx->d_obs_start, ctx->d_tile_pt, ctx->d_obs_z, ctx->d_cm_pt, ctx->d_item_cam, ctx->d_item_beg,
+                    ctx->d_item_end, ctx->d_cam_item_start, ctx->d_cm_z, ctx->d_A[0], ctx->d_A[1], ctx->d_A[2], ctx->d_B[0], ctx->d_B[1], ctx->d_B[2],
+                    ctx->d_H, ctx->d_g, ctx->d_x, ctx->d_Ainv, ctx->d_S, ctx->d_rhs, ctx->d_cost_part, ctx->d_step_part, ctx->d_cam_part, ctx->d_scal,
+                    ctx->d_flush, ctx->d_work, ctx->d_info, ctx->d_ipiv};
+    for (void* p : ptrs) if (p) cudaFree(p);
+    if (ctx->h_scal) cudaFreeHost(ctx->h_scal);
+    if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
+    if (ctx->cusolver) cusolverDnDestroy(ctx->cusolver);
+    cudaEventDestroy(ctx->ev_fork); cudaEventDestroy(ctx->ev_join); cudaEventDestroy(ctx->ev_t0); cudaEventDestroy(ctx->ev_t1); cudaEventDestroy(ctx->ev_b0); cudaEventDestroy(ctx->ev_b1);
+    cudaStreamDestroy(ctx->st); cudaStreamDestroy(ctx->st2);
+    delete ctx;
+    return NLLS_OK;
+}
+
+const char* nlls_last_error(nlls_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int nlls_comm_unique_id(void* id128) {
+    if (!g_nccl.load()) return NLLS_ERR_NCCL;
+    ncclUniqueId id;
+    if (g_nccl.GetUniqueId(&id) != 0) return NLLS_ERR_NCCL;
+    std::memcpy(id128, &id, 128);
+    return NLLS_OK;
+}
+
+int nlls_comm_init(nlls_ctx* ctx, int rank, int nranks, const void* id128) {
+    if (!ctx || nranks < 1 || rank < 0 || rank >= nranks) return NLLS_ERR_INVALID;
+    ctx->rank = rank; ctx->nranks = nranks;
+    if (nranks == 1) return NLLS_OK;
+    if (!g_nccl.load()) FAIL(NLLS_ERR_NCCL, "libnccl.so.2 not found");
+    CK(cudaSetDevice(ctx->device));
+    ncclUniqueId id;
+    std::memcpy(&id, id128, 128);
+    CKN(g_nccl.CommInitRank(&ctx->comm, nranks, id, rank));
+    return NLLS_OK;
+}
+
+int nlls_set_variables(nlls_ctx* ctx, int vartype, const double* aos, int64_t n, int64_t stride, int64_t first_index, const int64_t* indices) {
+    if (!ctx || !aos || n < 0) return NLLS_ERR_INVALID;
+    const int ns = vartype_nstore(vartype);
+    if (ns == 0) FAIL(NLLS_ERR_NO_KERNEL, "variable type " + std::to_string(vartype) + " has no registered update kernel");
+    if (stride < ns) FAIL(NLLS_ERR_INVALID, "stride smaller than the variable's stored size");
+    VarSet& vs = ctx->vars[vartype];
+    // same structure as before?  (values-only refresh of problem.variables: one H2D copy straight from the caller's buffer)
+    bool same = ctx->prepared && vs.vartype == vartype && (int64_t)vs.gidx.size() == n && n > 0;
+    if (same) {
+        if (indices) { for (int64_t i = 0; i < n && same; ++i) same = (indices[i] == vs.gidx[(size_t)i]); }
+        else same = (vs.gidx.front() == first_index && vs.gidx.back() == first_index + n - 1);
+    }
+    if (same && (vartype == ctx->vtA || vartype == ctx->vtB)) {
+        CK(cudaSetDevice(ctx->device));
+        const bool isA = vartype == ctx->vtA;
+        const int ds = isA ? ctx->CS : 3;
+        double* dst = isA ? ctx->d_A[ctx->cur] : ctx->d_B[ctx->cur];
+        if (ds == stride) {
+            CK(cudaMemcpyAsync(dst, aos, sizeof(double) * n * ds, cudaMemcpyHostToDevice, ctx->st));
+        } else {
+            CK(cudaMemcpy2DAsync(dst, sizeof(double) * ds, aos, sizeof(double) * stride, sizeof(double) * ns, (size_t)n, cudaMemcpyHostToDevice, ctx->st));
+        }
+        CK(cudaStreamSynchronize(ctx->st));
+        vs.stale = true;
+        return NLLS_OK;
+    }
+    std::vector<int64_t> gi((size_t)n);
+    for (int64_t i = 0; i < n; ++i) {
+        gi[(size_t)i] = indices ? indices[i] : first_index + i;
+        if (gi[(size_t)i] < 1 || (i > 0 && gi[(size_t)i] <= gi[(size_t)i - 1])) FAIL(NLLS_ERR_INVALID, "variable indices must be 1-based and ascending");
+    }
+    vs.vartype = vartype; vs.nstore = ns; vs.stale = false;
+    vs.gidx.swap(gi);
+    vs.vals.resize((size_t)n * ns);
+    for (int64_t i = 0; i < n; ++i) std::memcpy(&vs.vals[(size_t)i * ns], aos + (size_t)i * stride, sizeof(double) * ns);
+    ctx->prepared = false;
+    return NLLS_OK;
+}
+
+int nlls_set_costs(nlls_ctx* ctx, int restype, const void* aos, int64_t stride_bytes, int64_t n, int robust, const double* kparams, int nkparams,
+                   int64_t kernel_var) {
+    (void)kernel_var;
+    if (!ctx || (!aos && n > 0) || n < 0) return NLLS_ERR_INVALID;
+    if (restype != NLLS_RES_AFFINE_BA && restype != NLLS_RES_PINHOLE_BA)
+        FAIL(NLLS_ERR_NO_KERNEL, "residual type " + std::to_string(restype) + " has no registered sm_100a kernel (no CPU fallback)");
+    const int kind = robust & 15;
+    if (kind > NLLS_ROBUST_GEMANMCCLURE || (robust & ~(15 | NLLS_ROBUST_SCALED)))
+        FAIL(NLLS_ERR_NO_KERNEL, "robust kernel " + std::to_string(robust) + " has no registered device implementation");
+    if (stride_bytes < 32) FAIL(NLLS_ERR_INVALID, "cost stride must be >= 32 bytes (2 x f64 measurement + 2 x i64 varind)");
+    ctx->restype = restype; ctx->robust = robust;
+    ctx->kparams[0] = 0.0; ctx->kparams[1] = 1.0;
+    if (kind != NLLS_ROBUST_NONE) {
+        if (nkparams < 1 || !kparams) FAIL(NLLS_ERR_INVALID, "robust kernel needs its width in kparams[0]");
+        ctx->kparams[0] = kparams[0];
+    }
+    if (robust & NLLS_ROBUST_SCALED) {
+        if (nkparams < 2 || !kparams) FAIL(NLLS_ERR_INVALID, "Scaled kernel needs (width, height) in kparams");
+        ctx->kparams[1] = kparams[1];
+    }
+    ctx->h_cam_g.resize((size_t)n); ctx->h_pt_g.resize((size_t)n); ctx->h_z.resize((size_t)2 * n);
+    const unsigned char* base = (const unsigned char*)aos;
+    for (int64_t i = 0; i < n; ++i) {
+        const unsigned char* e = base + (size_t)i * stride_bytes;
+        double z[2]; int64_t vi[2];
+        std::memcpy(z, e, 16); std::memcpy(vi, e + 16, 16);
+        ctx->h_z[(size_t)2 * i] = z[0]; ctx->h_z[(size_t)2 * i + 1] = z[1];
+        ctx->h_cam_g[(size_t)i] = vi[0]; ctx->h_pt_g[(size_t)i] = vi[1];
+    }
+    ctx->prepared = false;
+    return NLLS_OK;
+}
+
+int nlls_prepare(nlls_ctx* ctx) {
+    if (!ctx) return NLLS_ERR_INVALID;
+    if (ctx->prepared) return NLLS_OK;
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->restype == 0) FAIL(NLLS_ERR_INVALID, "no costs set");
+    ctx->vtA = (ctx->restype == NLLS_RES_AFFINE_BA) ? NLLS_VAR_EUCLID6 : NLLS_VAR_PINHOLE;
+    ctx->vtB = NLLS_VAR_EUCLID3;
+    ctx->DC = (ctx->restype == NLLS_RES_AFFINE_BA) ? AffineBA::DC : PinholeBA::DC;
+    ctx->NC = (ctx->restype == NLLS_RES_AFFINE_BA) ? AffineBA::NC : PinholeBA::NC;
+    ctx->CS = (ctx->restype == NLLS_RES_AFFINE_BA) ? AffineBA::CS : PinholeBA::CS;
+    if (!ctx->vars.count(ctx->vtA) || !ctx->vars.count(ctx->vtB)) FAIL(NLLS_ERR_INVALID, "camera and point variables must be set before prepare");
+    for (auto& kv : ctx->vars)
+        if (kv.first != ctx->vtA && kv.first != ctx->vtB && !kv.second.gidx.empty())
+            FAIL(NLLS_ERR_UNSUPPORTED, "variables of a type the registered residual does not use");
+    for (int vt : {ctx->vtA, ctx->vtB}) {  // values refreshed on the device since the last full set: pull them back first
+        VarSet& vs = ctx->vars[vt];
+        if (!vs.stale) continue;
+        const bool isA = vt == ctx->vtA;
+        const int ds = isA ? ctx->CS : 3;
+        CK(cudaMemcpy2D(vs.vals.data(), sizeof(double) * vs.nstore, isA ? ctx->d_A[ctx->cur] : ctx->d_B[ctx->cur], sizeof(double) * ds,
+                        sizeof(double) * vs.nstore, vs.gidx.size(), cudaMemcpyDeviceToHost));
+        vs.stale = false;
+    }
+    const VarSet& A = ctx->vars[ctx->vtA];
+    const VarSet& B = ctx->vars[ctx->vtB];
+    ctx->nA = (int64_t)A.gidx.size(); ctx->nB = (int64_t)B.gidx.size();
+    ctx->nobs = (int64_t)ctx->h_cam_g.size();
+    if (ctx->nA == 0 || ctx->nB == 0) FAIL(NLLS_ERR_INVALID, "empty variable set");
+    if (ctx->nobs >= (1LL << 31) - 1024) FAIL(NLLS_ERR_UNSUPPORTED, "more than 2^31 costs per rank");
+    const int DC = ctx->DC, WB = 3 * DC;
+    const int64_t maxidx = std::max(A.gidx.back(), B.gidx.back());
+    if (maxidx >= (1LL << 30)) FAIL(NLLS_ERR_UNSUPPORTED, "variable index too large");
+    ctx->cams_first = A.gidx.back() < B.gidx.front();
+    // global -> local lookup
+    std::vector<int> g2l((size_t)maxidx + 1, -1);
+    std::vector<unsigned char> g2c((size_t)maxidx + 1, 0);
+    for (size_t i = 0; i < A.gidx.size(); ++i) { g2l[(size_t)A.gidx[i]] = (int)i; g2c[(size_t)A.gidx[i]] = 1; }
+    for (size_t i = 0; i < B.gidx.size(); ++i) {
+        if (g2c[(size_t)B.gidx[i]]) FAIL(NLLS_ERR_INVALID, "variable index used by two variable types");
+        g2l[(size_t)B.gidx[i]] = (int)i; g2c[(size_t)B.gidx[i]] = 2;
+    }
+    const int64_t nobs = ctx->nobs, nA = ctx->nA, nB = ctx->nB;
+    // counting sort by point (≙ reordercostsforschur!, src/problem.jl:186-196), then by camera inside a point
+    std::vector<int> cnt((size_t)nB + 1, 0);
+    std::vector<int> caml((size_t)nobs), ptl((size_t)nobs);
+    for (int64_t i = 0; i < nobs; ++i) {
+        const int64_t cg = ctx->h_cam_g[(size_t)i], pg = ctx->h_pt_g[(size_t)i];
+        if (cg < 1 || cg > maxidx || g2c[(size_t)cg] != 1) FAIL(NLLS_ERR_INVALID, "cost " + std::to_string(i + 1) + ": varind[1] is not a camera variable");
+        if (pg < 1 || pg > maxidx || g2c[(size_t)pg] != 2) FAIL(NLLS_ERR_INVALID, "cost " + std::to_string(i + 1) + ": varind[2] is not a point variable owned by this rank");
+        caml[(size_t)i] = g2l[(size_t)cg]; ptl[(size_t)i] = g2l[(size_t)pg];
+        cnt[(size_t)ptl[(size_t)i] + 1]++;
+    }
+    ctx->h_obs_start.assign((size_t)nB + 1, 0);
+    for (int64_t p = 0; p < nB; ++p) ctx->h_obs_start[(size_t)p + 1] = ctx->h_obs_start[(size_t)p] + cnt[(size_t)p + 1];
+    std::vector<int> fill(ctx->h_obs_start.begin(), ctx->h_obs_start.end() - 1);
+    std::vector<int> order((size_t)nobs);
+    for (int64_t i = 0; i < nobs; ++i) order[(size_t)fill[(size_t)ptl[(size_t)i]]++] = (int)i;
+    for (int64_t p = 0; p < nB; ++p) {
+        int* b = order.data() + ctx->h_obs_start[(size_t)p];
+        int* e = order.data() + ctx->h_obs_start[(size_t)p + 1];
+        if (e - b > TILE_OBS) FAIL(NLLS_ERR_UNSUPPORTED, "a point with more than " + std::to_string(TILE_OBS) + " observations");
+        std::stable_sort(b, e, [&](int x, int y) { return caml[(size_t)x] < caml[(size_t)y]; });
+        for (int* q = b + 1; q < e; ++q)
+            if (caml[(size_t)*q] == caml[(size_t)*(q - 1)]) FAIL(NLLS_ERR_UNSUPPORTED, "two costs on the same (camera, point) pair");
+    }
+    ctx->h_obs_cam.resize((size_t)nobs); ctx->h_obs_pt.resize((size_t)nobs);
+    std::vector<double2> obs_z((size_t)nobs);
+    for (int64_t j = 0; j < nobs; ++j) {
+        const int i = order[(size_t)j];
+        ctx->h_obs_cam[(size_t)j] = caml[(size_t)i]; ctx->h_obs_pt[(size_t)j] = ptl[(size_t)i];
+        obs_z[(size_t)j] = make_double2(ctx->h_z[(size_t)2 * i], ctx->h_z[(size_t)2 * i + 1]);
+    }
+    // tiles: consecutive points, <= TILE_OBS observations and <= TILE_PTS points, boundaries 16-byte aligned in H when possible
+    ctx->h_tile_pt.clear();
+    ctx->h_tile_pt.push_back(0);
+    {
+        auto aligned = [&](int64_t pt) { return ((WB * (int64_t)ctx->h_obs_start[(size_t)pt] + 9 * pt) & 1) == 0; };
+        int64_t p0 = 0;
+        while (p0 < nB) {
+            int64_t p1 = p0;
+            while (p1 < nB && (p1 - p0) < TILE_PTS && (ctx->h_obs_start[(size_t)p1 + 1] - ctx->h_obs_start[(size_t)p0]) <= TILE_OBS) ++p1;
+            if (p1 < nB && !aligned(p1) && p1 - 1 > p0 && aligned(p1 - 1)) --p1;
+            ctx->h_tile_pt.push_back((int)p1);
+            p0 = p1;
+        }
+    }
+    ctx->ntiles = (int)ctx->h_tile_pt.size() - 1;
+    // camera-major copy + work items
+    ctx->h_cam_start.assign((size_t)nA + 1, 0);
+    for (int64_t j = 0; j < nobs; ++j) ctx->h_cam_start[(size_t)ctx->h_obs_cam[(size_t)j] + 1]++;
+    for (int64_t c = 0; c < nA; ++c) ctx->h_cam_start[(size_t)c + 1] += ctx->h_cam_start[(size_t)c];
+    std::vector<int> cfill(ctx->h_cam_start.begin(), ctx->h_cam_start.end() - 1);
+    ctx->h_cm_obs.resize((size_t)nobs);
+    std::vector<int> cm_pt((size_t)nobs);
+    std::vector<double2> cm_z((size_t)nobs);
+    for (int64_t j = 0; j < nobs; ++j) {
+        const int k = cfill[(size_t)ctx->h_obs_cam[(size_t)j]]++;
+        ctx->h_cm_obs[(size_t)k] = (int)j; cm_pt[(size_t)k] = ctx->h_obs_pt[(size_t)j]; cm_z[(size_t)k] = obs_z[(size_t)j];
+    }
+    std::vector<int> item_cam, item_beg, item_end, cam_item_start((size_t)nA + 1, 0);
+    for (int64_t c = 0; c < nA; ++c) {
+        cam_item_start[(size_t)c] = (int)item_cam.size();
+        for (int b = ctx->h_cam_start[(size_t)c]; b < ctx->h_cam_start[(size_t)c + 1]; b += CAM_CHUNK) {
+            item_cam.push_back((int)c); item_beg.push_back(b); item_end.push_back(std::min(b + CAM_CHUNK, ctx->h_cam_start[(size_t)c + 1]));
+        }
+    }
+    cam_item_start[(size_t)nA] = (int)item_cam.size();
+    ctx->nitems = (int)item_cam.size();
+
+    ctx->dof = (int64_t)DC * nA + 3 * nB;
+    ctx->hlen = (int64_t)DC * DC * nA + (int64_t)WB * nobs + 9 * nB;
+    ctx->nred = (int64_t)DC * nA;
+    if (ctx->nred > 46000) FAIL(NLLS_ERR_UNSUPPORTED, "reduced camera system larger than 46000 (dense path only in this build)");
+
+    TRY(upload(ctx, &ctx->d_obs_cam, ctx->h_obs_cam)); TRY(upload(ctx, &ctx->d_obs_pt, ctx->h_obs_pt)); TRY(upload(ctx, &ctx->d_obs_z, obs_z));
+    TRY(upload(ctx, &ctx->d_obs_start, ctx->h_obs_start)); TRY(upload(ctx, &ctx->d_tile_pt, ctx->h_tile_pt));
+    TRY(upload(ctx, &ctx->d_cm_pt, cm_pt)); TRY(upload(ctx, &ctx->d_cm_z, cm_z));
+    TRY(upload(ctx, &ctx->d_item_cam, item_cam)); TRY(upload(ctx, &ctx->d_item_beg, item_beg)); TRY(upload(ctx, &ctx->d_item_end, item_end));
+    TRY(upload(ctx, &ctx->d_cam_item_start, cam_item_start));
+    for (int k = 0; k < 3; ++k) { TRY(dalloc(ctx, &ctx->d_A[k], (size_t)nA * ctx->CS)); TRY(dalloc(ctx, &ctx->d_B[k], (size_t)nB * 3)); }
+    ctx->cur = 0; ctx->nxt = 1; ctx->bst = 2;
+    TRY(upload_vars(ctx, A, ctx->CS, ctx->d_A[0])); TRY(upload_vars(ctx, B, 3, ctx->d_B[0]));
+    TRY(dalloc(ctx, &ctx->d_H, (size_t)ctx->hlen)); TRY(dalloc(ctx, &ctx->d_g, (size_t)ctx->dof)); TRY(dalloc(ctx, &ctx->d_x, (size_t)ctx->dof));
+    CK(cudaMemsetAsync(ctx->d_H, 0, sizeof(double) * ctx->hlen, ctx->st));
+    CK(cudaMemsetAsync(ctx->d_g, 0, sizeof(double) * ctx->dof, ctx->st));
+    CK(cudaMemsetAsync(ctx->d_x, 0, sizeof(double) * ctx->dof, ctx->st));
+    TRY(dalloc(ctx, &ctx->d_Ainv, (size_t)6 * nB));
+    TRY(dalloc(ctx, &ctx->d_S, (size_t)ctx->nred * ctx->nred)); TRY(dalloc(ctx, &ctx->d_rhs, (size_t)ctx->nred));
+    TRY(dalloc(ctx, &ctx->d_cost_part, (size_t)ctx->ntiles)); TRY(dalloc(ctx, &ctx->d_step_part, (size_t)4 * ctx->ntiles));
+    const int NU = DC * (DC + 1) / 2 + DC;
+    TRY(dalloc(ctx, &ctx->d_cam_part, (size_t)ctx->nitems * NU));
+    int lw1 = 0, lw2 = 0;
+    CKS(cusolverDnDpotrf_bufferSize(ctx->cusolver, CUBLAS_FILL_MODE_LOWER, (int)ctx->nred, ctx->d_S, (int)ctx->nred, &lw1));
+    CKS(cusolverDnDgetrf_bufferSize(ctx->cusolver, (int)ctx->nred, (int)ctx->nred, ctx->d_S, (int)ctx->nred, &lw2));
+    ctx->lwork = std::max(lw1, lw2);
+    TRY(dalloc(ctx, &ctx->d_work, (size_t)ctx->lwork));
+    TRY(dalloc(ctx, &ctx->d_ipiv, (size_t)ctx->nred));
+    TRY(DISPATCH(ctx, set_smem_attrs, ctx));
+    CK(cudaStreamSynchronize(ctx->st));
+    ctx->prepared = true;
+    ctx->lm_active = false;
+    return NLLS_OK;
+}
+
+int nlls_linearize(nlls_ctx* ctx, double* cost) {
+    if (!ctx) return NLLS_ERR_INVALID;
+    TRY(nlls_prepare(ctx));
+    CK(cudaSetDevice(ctx->device));
+    return do_linearize(ctx, cost);
+}
+
+int nlls_cost(nlls_ctx* ctx, int which, double* cost) {
+    if (!ctx || which < 0 || which > 2) return NLLS_ERR_INVALID;
+    TRY(nlls_prepare(ctx));
+    CK(cudaSetDevice(ctx->device));
+    const int buf = which == 0 ? ctx->cur : (which == 1 ? ctx->nxt : ctx->bst);
+    TRY(DISPATCH(ctx, launch_cost, ctx, buf, SC_COST_TRY));
+    TRY(fetch_scalars(ctx));
+    if (cost) *cost = ctx->h_scal[SC_COST_TRY];
+    return NLLS_OK;
+}
+
+int nlls_solve(nlls_ctx* ctx, double lambda) {
+    if (!ctx || !ctx->prepared) return NLLS_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    TRY(DISPATCH(ctx, launch_schur, ctx, lambda));
+    TRY(launch_reduced_solve(ctx, false));
+    TRY(fetch_scalars(ctx));
+    const int* info = reinterpret_cast<const int*>(ctx->h_scal + SC_COUNT);
+    if (info[0] != 0) {
+        TRY(DISPATCH(ctx, launch_schur, ctx, lambda));
+        TRY(launch_reduced_solve(ctx, true));
+    }
+    // back-substitution also writes x and varnext; nlls_update is then a no-op kept for API symmetry
+    TRY(DISPATCH(ctx, launch_update, ctx));
+    TRY(fetch_scalars(ctx));
+    return NLLS_OK;
+}
+
+int nlls_update(nlls_ctx* ctx) {
+    if (!ctx || !ctx->prepared) return NLLS_ERR_INVALID;
+    return NLLS_OK;  // varnext is produced by the fused back-substitution in nlls_solve
+}
+
+// ---- LM -----------------------------------------------------------------------------------------------
+int nlls_lm_begin(nlls_ctx* ctx, const nlls_options* opts) {
+    if (!ctx || !opts) return NLLS_ERR_INVALID;
+    const uint64_t t0 = now_ns();
+    if (opts->iterator != NLLS_ITER_LM) FAIL(NLLS_ERR_UNSUPPORTED, "only the Levenberg-Marquardt iterator is implemented");
+    TRY(nlls_prepare(ctx));
+    CK(cudaSetDevice(ctx->device));
+    ctx->opts = *opts;
+    ctx->starttime = t0;
+    ctx->stoptime = t0 + opts->maxtime_ns;                       // src/optimize.jl:115
+    ctx->lambda = 0.0;                                           // LevMarData(0.0)  src/iterators.jl:124
+    ctx->fails = 0; ctx->iternum = 0; ctx->converged = 0;
+    ctx->costcomputations = ctx->gradientcomputations = ctx->linearsolvers = 0;
+    ctx->t_init = ctx->t_cost = ctx->t_grad = ctx->t_solver = 0;
+    ctx->have_best = false;
+    ctx->t_init += now_ns() - t0;                                // :116
+    const uint64_t tg = now_ns();
+    double c = 0.0;
+    TRY(do_linearize(ctx, &c));                                  // :118
+    ctx->t_grad += now_ns() - tg;
+    ctx->gradientcomputations += 1;
+    ctx->cost = c; ctx->bestcost = c; ctx->startcost = c;        // :120-121
+    ctx->lm_active = true;
+    return NLLS_OK;
+}
+
+int nlls_lm_iterate(nlls_ctx* ctx, nlls_iterinfo* info) {
+    if (!ctx || !ctx->lm_active) return NLLS_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    const nlls_options& o = ctx->opts;
+    ctx->iternum += 1;                                           // src/optimize.jl:124
+    // ---- iterate!(::LevMarData)                                 src/iterators.jl:139-172
+    if (ctx->lambda == 0) {                                      // initlambda  :131-137,142-144
+        TRY(DISPATCH(ctx, launch_maxdiag, ctx));
+        TRY(fetch_scalars(ctx));
+        ctx->lambda = ctx->h_scal[SC_MAXDIAG] * 1e-6;
+    }
+    double mu = 2.0, cost_ = 0.0, maxstep = 0.0, sq = 0.0;
+    int64_t ntries = 0, accepted = 0;
+    while (true) {
+        const uint64_t ts = now_ns();
+        TRY(do_try(ctx, ctx->lambda));                           // :149-157 (damp, solve, negate, update, cost)
+        ctx->t_solver += now_ns() - ts;                          // the fused try (solve + update + cost) is booked as solver time
+        ctx->linearsolvers += 1; ctx->costcomputations += 1; ntries += 1;
+        const double* s = ctx->h_scal;
+        cost_ = s[SC_COST_TRY];
+        maxstep = (std::isnan(s[SC_P_MAX]) || std::isnan(s[SC_C_MAX])) ? std::numeric_limits<double>::quiet_NaN() : std::max(s[SC_P_MAX], s[SC_C_MAX]);
+        sq = s[SC_P_SQ] + s[SC_C_SQ];
+        if (!(cost_ > ctx->bestcost) || maxstep < o.dstep) {     // :160
+            accepted = !(cost_ > ctx->bestcost);
+            const double xhx = s[SC_P_XHX] + s[SC_C_XHX], gx = s[SC_P_GX] + s[SC_C_GX];
+            const double q = (cost_ - ctx->bestcost) / (0.5 * xhx + gx);   // :163
+            const double t = 2 * q - 1;
+            ctx->lambda *= q < 0.983 ? 1 - t * t * t : 0.1;     // :164
+            break;
+        }
+        ctx->lambda *= mu;                                       // :169-170
+        mu *= 2.0;
+    }
+    ctx->cost = cost_;
+    ctx->maxstep = maxstep;
+    if (info) { info->cost = cost_; info->lambda = ctx->lambda; info->maxstep = maxstep; info->stepnorm = std::sqrt(sq); info->ntries = ntries; info->accepted = accepted; }
+    return NLLS_OK;
+}
+
+int nlls_lm_advance(nlls_ctx* ctx, double cost, int64_t terminate, int64_t* converged) {
+    if (!ctx || !ctx->lm_active) return NLLS_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    const nlls_options& o = ctx->opts;
+    const double maxstep = ctx->maxstep;
+    // ---- optimizeinternal! after the callback                    src/optimize.jl:130-171
+    double dcost = ctx->bestcost - cost;
+    if (dcost >= 0) { ctx->bestcost = cost; ctx->fails = 0; }
+    else {
+        dcost = cost;                                            // sic :135
+        ctx->fails += 1;
+        if (ctx->fails == 1) {                                   // :137-144: keep the current (best) variables
+            CK(cudaMemcpyAsync(ctx->d_A[ctx->bst], ctx->d_A[ctx->cur], sizeof(double) * ctx->nA * ctx->CS, cudaMemcpyDeviceToDevice, ctx->st));
+            CK(cudaMemcpyAsync(ctx->d_B[ctx->bst], ctx->d_B[ctx->cur], sizeof(double) * ctx->nB * 3, cudaMemcpyDeviceToDevice, ctx->st));
+            ctx->have_best = true;
+        }
+    }
+    std::swap(ctx->cur, ctx->nxt);                               // updatefromnext!  :147,207-209
+    ctx->cost = cost;
+    int64_t conv = 0;                                            // :150-161
+    conv |= (int64_t)std::isinf(cost) << 0;
+    conv |= (int64_t)std::isnan(cost) << 1;
+    conv |= (int64_t)(dcost < ctx->bestcost * o.reldcost) << 2;
+    conv |= (int64_t)(dcost < o.absdcost) << 3;
+    conv |= (int64_t)std::isinf(maxstep) << 4;
+    conv |= (int64_t)std::isnan(maxstep) << 5;
+    conv |= (int64_t)(maxstep < o.dstep) << 6;
+    conv |= (int64_t)(ctx->fails > o.maxfails) << 7;
+    conv |= (int64_t)(ctx->iternum >= o.maxiters) << 8;
+    conv |= (int64_t)(now_ns() > ctx->stoptime) << 9;
+    conv |= terminate << 16;
+    ctx->converged = conv;
+    if (converged) *converged = conv;
+    if (conv == 0) {                                             // :167-171
+        const uint64_t tg = now_ns();
+        TRY(do_linearize(ctx, nullptr));
+        ctx->t_grad += now_ns() - tg;
+        ctx->gradientcomputations += 1;
+    }
+    return NLLS_OK;
+}
+
+int nlls_lm_end(nlls_ctx* ctx, nlls_result* r) {
+    if (!ctx || !ctx->lm_active) return NLLS_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    if (!(ctx->bestcost >= ctx->cost) && ctx->have_best) std::swap(ctx->cur, ctx->bst);   // src/optimize.jl:173-176
+    CK(cudaStreamSynchronize(ctx->st));
+    ctx->lm_active = false;
+    if (r) {
+        r->startcost = ctx->startcost; r->bestcost = ctx->bestcost;
+        r->timetotal = (now_ns() - ctx->starttime) * 1e-9;       // :178
+        r->timeinit = ctx->t_init * 1e-9; r->timecost = ctx->t_cost * 1e-9; r->timegradient = ctx->t_grad * 1e-9; r->timesolver = ctx->t_solver * 1e-9;
+        r->termination = ctx->converged; r->niterations = ctx->iternum;
+        r->costcomputations = ctx->costcomputations; r->gradientcomputations = ctx->gradientcomputations; r->linearsolvers = ctx->linearsolvers;
+    }
+    return NLLS_OK;
+}
+
+int nlls_optimize(nlls_ctx* ctx, const nlls_options* opts, nlls_result* result) {
+    TRY(nlls_lm_begin(ctx, opts));
+    int64_t conv = 0;
+    while (conv == 0) {
+        nlls_iterinfo info;
+        TRY(nlls_lm_iterate(ctx, &info));
+        TRY(nlls_lm_advance(ctx, info.cost, 0, &conv));          // nullcallback returns (cost, 0)  src/callbacks.jl:20
+    }
+    return nlls_lm_end(ctx, result);
+}
+
+// ---- read-back -----------------------------------------------------------------------------------------
+int nlls_get_variables(nlls_ctx* ctx, int vartype, int which, double* aos, int64_t n, int64_t stride) {
+    if (!ctx || !ctx->prepared || !aos || which < 0 || which > 2) return NLLS_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    const int buf = which == 0 ? ctx->cur : (which == 1 ? ctx->nxt : ctx->bst);
+    const bool isA = vartype == ctx->vtA;
+    if (!isA && vartype != ctx->vtB) return NLLS_ERR_INVALID;
+    const int64_t cnt = isA ? ctx->nA : ctx->nB;
+    const int ds = isA ? ctx->CS : 3, ns = isA ? ctx->NC : 3;
+    if (n != cnt || stride < ns) FAIL(NLLS_ERR_INVALID, "size mismatch in nlls_get_variables");
+    if (ds == stride) {
+        CK(cudaMemcpyAsync(aos, isA ? ctx->d_A[buf] : ctx->d_B[buf], sizeof(double) * cnt * ds, cudaMemcpyDeviceToHost, ctx->st));
+        CK(cudaStreamSynchronize(ctx->st));
+    } else {
+        std::vector<double> tmp((size_t)cnt * ds);
+        CK(cudaMemcpyAsync(tmp.data(), isA ? ctx->d_A[buf] : ctx->d_B[buf], sizeof(double) * cnt * ds, cudaMemcpyDeviceToHost, ctx->st));
+        CK(cudaStreamSynchronize(ctx->st));
+        for (int64_t i = 0; i < cnt; ++i) std::memcpy(aos + (size_t)i * stride, &tmp[(size_t)i * ds], sizeof(double) * ns);
+    }
+    return NLLS_OK;
+}
+
+int64_t nlls_dof(nlls_ctx* ctx) { return (ctx && ctx->prepared) ? ctx->dof : -1; }
+int64_t nlls_hessian_len(nlls_ctx* ctx) { return (ctx && ctx->prepared) ? ctx->hlen : -1; }
+int64_t nlls_hessian_nblocks(nlls_ctx* ctx) { return (ctx && ctx->prepared) ? ctx->nA + ctx->nB + ctx->nobs : -1; }
+
+}  // extern "C"
+
+namespace {
+// vector in reference (variable-index) order from the internal [cameras | points] order
+int reorder_vec(nlls_ctx* ctx, const double* dsrc, double* out) {
+    std::vector<double> tmp((size_t)ctx->dof);
+    CK(cudaMemcpyAsync(tmp.data(), dsrc, sizeof(double) * ctx->dof, cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    if (ctx->cams_first) { std::memcpy(out, tmp.data(), sizeof(double) * ctx->dof); return NLLS_OK; }
+    const VarSet& A = ctx->vars[ctx->vtA];
+    const VarSet& B = ctx->vars[ctx->vtB];
+    size_t ia = 0, ib = 0, o = 0;
+    const int DC = ctx->DC;
+    while (ia < A.gidx.size() || ib < B.gidx.size()) {
+        const bool takeA = ib >= B.gidx.size() || (ia < A.gidx.size() && A.gidx[ia] < B.gidx[ib]);
+        if (takeA) { std::memcpy(out + o, &tmp[(size_t)DC * ia], sizeof(double) * DC); o += DC; ++ia; }
+        else { std::memcpy(out + o, &tmp[(size_t)DC * ctx->nA + 3 * ib], sizeof(double) * 3); o += 3; ++ib; }
+    }
+    return NLLS_OK;
+}
+
+// Walk the reference's BlockSparseMatrix in storage order (block rows by variable index, blocks by ascending block column,
+// src/BlockSparseMatrix.jl:37-44, src/linearsystem.jl:108-115) and hand every block to `emit`.
+template <class F>
+void walk_reference_blocks(nlls_ctx* ctx, F emit) {
+    const VarSet& A = ctx->vars[ctx->vtA];
+    const VarSet& B = ctx->vars[ctx->vtB];
+    const int DC = ctx->DC, WB = 3 * DC;
+    const int64_t hB = (int64_t)DC * DC * ctx->nA;
+    // block index (1-based rank among all variables) of every camera / point
+    std::vector<int64_t> blkA(A.gidx.size()), blkB(B.gidx.size());
+    {
+        size_t ia = 0, ib = 0; int64_t r = 1;
+        while (ia < A.gidx.size() || ib < B.gidx.size()) {
+            const bool takeA = ib >= B.gidx.size() || (ia < A.gidx.size() && A.gidx[ia] < B.gidx[ib]);
+            if (takeA) blkA[ia++] = r++; else blkB[ib++] = r++;
+        }
+    }
+    size_t ia = 0, ib = 0;
+    while (ia < A.gidx.size() || ib < B.gidx.size()) {
+        const bool takeA = ib >= B.gidx.size() || (ia < A.gidx.size() && A.gidx[ia] < B.gidx[ib]);
+        if (takeA) {
+            const int c = (int)ia;
+            for (int k = ctx->h_cam_start[(size_t)c]; k < ctx->h_cam_start[(size_t)c + 1]; ++k) {   // points ascending
+                const int j = ctx->h_cm_obs[(size_t)k];
+                const int p = ctx->h_obs_pt[(size_t)j];
+                if (B.gidx[(size_t)p] < A.gidx[ia])  // (camera row, point column): transpose of W
+                    emit(blkA[ia], blkB[(size_t)p], DC, 3, hB + (int64_t)WB * j + 9 * (int64_t)p, true);
+            }
+            emit(blkA[ia], blkA[ia], DC, DC, (int64_t)DC * DC * c, false);
+            ++ia;
+        } else {
+            const int p = (int)ib;
+            for (int j = ctx->h_obs_start[(size_t)p]; j < ctx->h_obs_start[(size_t)p + 1]; ++j) {     // cameras ascending
+                const int c = ctx->h_obs_cam[(size_t)j];
+                if (A.gidx[(size_t)c] < B.gidx[ib]) emit(blkB[ib], blkA[(size_t)c], 3, DC, hB + (int64_t)WB * j + 9 * (int64_t)p, false);
+            }
+            emit(blkB[ib], blkB[ib], 3, 3, hB + (int64_t)WB * ctx->h_obs_start[(size_t)p + 1] + 9 * (int64_t)p, false);
+            ++ib;
+        }
+    }
+}
+}  // namespace
+
+extern "C" {
+
+int nlls_get_gradient(nlls_ctx* ctx, double* b) {
+    if (!ctx || !ctx->prepared || !b) return NLLS_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    return reorder_vec(ctx, ctx->d_g, b);
+}
+int nlls_get_step(nlls_ctx* ctx, double* x) {
+    if (!ctx || !ctx->prepared || !x) return NLLS_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    return reorder_vec(ctx, ctx->d_x, x);
+}
+
+int nlls_get_hessian_blocks(nlls_ctx* ctx, double* data) {
+    if (!ctx || !ctx->prepared || !data) return NLLS_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->cams_first) {  // internal layout == reference layout
+        CK(cudaMemcpyAsync(data, ctx->d_H, sizeof(double) * ctx->hlen, cudaMemcpyDeviceToHost, ctx->st));
+        CK(cudaStreamSynchronize(ctx->st));
+        return NLLS_OK;
+    }
+    std::vector<double> tmp((size_t)ctx->hlen);
+    CK(cudaMemcpyAsync(tmp.data(), ctx->d_H, sizeof(double) * ctx->hlen, cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    int64_t o = 0;
+    walk_reference_blocks(ctx, [&](int64_t, int64_t, int rows, int cols, int64_t src, bool transposed) {
+        if (!transposed) { std::memcpy(data + o, &tmp[(size_t)src], sizeof(double) * rows * cols); }
+        else {  // stored block is cols x rows (column-major); emit its transpose
+            for (int c = 0; c < cols; ++c) for (int r = 0; r < rows; ++r) data[o + r + (int64_t)rows * c] = tmp[(size_t)(src + c + (int64_t)cols * r)];
+        }
+        o += (int64_t)rows * cols;
+    });
+    return NLLS_OK;
+}
+
+int nlls_get_hessian_index(nlls_ctx* ctx, int64_t* rowblock, int64_t* colblock, int64_t* start) {
+    if (!ctx || !ctx->prepared || !rowblock || !colblock || !start) return NLLS_ERR_INVALID;
+    int64_t o = 1, k = 0;
+    walk_reference_blocks(ctx, [&](int64_t rb, int64_t cb, int rows, int cols, int64_t, bool) {
+        rowblock[k] = rb; colblock[k] = cb; start[k] = o; ++k;
+        o += (int64_t)rows * cols;
+    });
+    return NLLS_OK;
+}
+
+// ---- measurement hooks -----------------------------------------------------------------------------------
+int64_t nlls_kernel_launches(nlls_ctx* ctx) { return ctx ? ctx->launches : -1; }
+
+int nlls_timer_start(nlls_ctx* ctx) {
+    if (!ctx) return NLLS_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->st));
+    CK(cudaEventRecord(ctx->ev_b0, ctx->st));
+    return NLLS_OK;
+}
+int nlls_timer_stop(nlls_ctx* ctx, double* ms) {
+    if (!ctx || !ms) return NLLS_ERR_INVALID;
+    CK(cudaEventRecord(ctx->ev_b1, ctx->st));
+    CK(cudaEventSynchronize(ctx->ev_b1));
+    float f = 0.f;
+    CK(cudaEventElapsedTime(&f, ctx->ev_b0, ctx->ev_b1));
+    *ms = f;
+    return NLLS_OK;
+}
+
+int nlls_algorithmic_bytes(nlls_ctx* ctx, int which, double* bytes) {
+    if (!ctx || !ctx->prepared || !bytes) return NLLS_ERR_INVALID;
+    const double nobs = (double)ctx->nobs, nA = (double)ctx->nA, nB = (double)ctx->nB, DC = ctx->DC;
+    const double rd = nobs * (8 * 2 + 8) + 8 * (nA * ctx->NC + nB * 3);   // measurement + 2 x int32 index, each variable once
+    const double wr = 8 * (nobs * DC * 3 + nA * DC * DC + nB * 9 + nA * DC + nB * 3);
+    switch (which) {
+        case NLLS_TIME_LINEARIZE: *bytes = rd + wr; break;                                  // B_lin
+        case NLLS_TIME_LIN_POINT: *bytes = rd + 8 * (nobs * DC * 3 + nB * 9 + nB * 3); break;
+        case NLLS_TIME_LIN_CAM: *bytes = rd + 8 * (nA * DC * DC + nA * DC); break;
+        case NLLS_TIME_COST: *bytes = rd; break;
+        default: *bytes = 0; return NLLS_ERR_INVALID;
+    }
+    return NLLS_OK;
+}
+
+int nlls_time_kernels(nlls_ctx* ctx, int which, int reps, int flush_l2, double* ms_per_call) {
+    if (!ctx || !ctx->prepared || reps < 1 || !ms_per_call) return NLLS_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    if (flush_l2 && !ctx->d_flush) {
+        ctx->flush_bytes = (size_t)256 << 20;  // larger than the 126 MB L2
+        CK(cudaMalloc(&ctx->d_flush, ctx->flush_bytes));
+    }
+    double lambda = ctx->lambda;
+    if (lambda == 0) lambda = 1e-3;
+    double total = 0.0;
+    for (int r = 0; r < reps; ++r) {
+        if (flush_l2) CK(cudaMemsetAsync(ctx->d_flush, r & 0xff, ctx->flush_bytes, ctx->st));
+        CK(cudaEventRecord(ctx->ev_t0, ctx->st));
+        switch (which) {
+            case NLLS_TIME_LINEARIZE: TRY(DISPATCH(ctx, launch_linearize, ctx, true, true)); break;
+            case NLLS_TIME_LIN_POINT: TRY(DISPATCH(ctx, launch_linearize, ctx, true, false)); break;
+            case NLLS_TIME_LIN_CAM: TRY(DISPATCH(ctx, launch_linearize, ctx, false, true)); break;
+            case NLLS_TIME_COST: TRY(DISPATCH(ctx, launch_cost, ctx, ctx->cur, SC_COST_TRY)); break;
+            case NLLS_TIME_SCHUR: TRY(DISPATCH(ctx, launch_schur, ctx, lambda)); break;
+            case NLLS_TIME_SOLVE_REDUCED: TRY(DISPATCH(ctx, launch_schur, ctx, lambda)); CK(cudaEventRecord(ctx->ev_t0, ctx->st)); TRY(launch_reduced_solve(ctx, false)); break;
+            case NLLS_TIME_BACKSUB: TRY(DISPATCH(ctx, launch_update, ctx)); break;
+            case NLLS_TIME_TRY: TRY(enqueue_try(ctx, lambda, false)); break;
+            default: return NLLS_ERR_INVALID;
+        }
+        CK(cudaEventRecord(ctx->ev_t1, ctx->st));
+        CK(cudaEventSynchronize(ctx->ev_t1));
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, ctx->ev_t0, ctx->ev_t1));
+        total += ms;
+    }
+    *ms_per_call = total / reps;
+    return NLLS_OK;
+}
+
+}  // extern "C"

@@ -757,12 +757,13 @@ void Problem::makesymmvls() {                                                   
         hess = makesparseindices(A, true);                                                // :58-60
         hessval.assign(hess.nzval.size(), 0.0);
         // Fill-reducing order.  The reference calls AMD inside ldl_analyze; AMD is not restated here.
-        // Blocks are ordered by ascending degree (stable), which like AMD eliminates the low-degree
-        // point blocks before the camera blocks.  The permutation changes rounding only.
+        // Blocks are ordered by ascending degree (stable, degrees above 64 tied so that high-degree
+        // camera blocks keep their natural, band-preserving order), which like AMD eliminates the
+        // low-degree point blocks before the camera blocks.  The permutation changes rounding only.
         std::vector<int64_t> deg(nb, 0), order(nb);
         for (size_t r = 0; r < nb; ++r) for (int64_t p = colptr[r] - 1; p < colptr[r + 1] - 1; ++p) { deg[r]++; if ((size_t)(rowval[p] - 1) != r) deg[rowval[p] - 1]++; }
         std::iota(order.begin(), order.end(), 0);
-        std::stable_sort(order.begin(), order.end(), [&](int64_t a, int64_t c) { return deg[a] < deg[c]; });
+        std::stable_sort(order.begin(), order.end(), [&](int64_t a, int64_t c) { return std::min<int64_t>(deg[a], 64) < std::min<int64_t>(deg[c], 64); });
         std::vector<int64_t> perm; perm.reserve((size_t)dof);
         for (int64_t blk : order) for (int k = 0; k < bs[blk]; ++k) perm.push_back(boffsets[blk] - 1 + k);
         ldl_analyze(hess, perm, ldl);                                                     // :68

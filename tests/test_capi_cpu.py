@@ -1,0 +1,53 @@
+"""CPU-side checks of the C ABI: the library loads, exports every symbol the header declares, and refuses to compute
+without a CUDA device (no fallback)."""
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_exports_match_header(pkg):
+    hdr = open(os.path.join(ROOT, "include", "nlls_b200.h")).read()
+    declared = set(re.findall(r"\b(nlls_[a-z0-9_]+)\s*\(", hdr))
+    L = pkg.capi.lib()
+    missing = [s for s in declared if not hasattr(L, s)]
+    assert not missing, missing
+    assert set(pkg.capi.EXPORTS) == declared
+
+
+def test_struct_sizes(pkg):
+    import ctypes as C
+    assert C.sizeof(pkg.capi.Options) == 56
+    assert C.sizeof(pkg.capi.Result) == 96
+    assert C.sizeof(pkg.capi.IterInfo) == 48
+    assert pkg.COST_DTYPE.itemsize == 32  # SimpleError2{2,Float64,..}: 2 x f64 + 2 x i64 (src/residual.jl:4-7)
+
+
+def test_no_device_no_fallback(pkg):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA device present")
+    with pytest.raises(pkg.capi.NLLSError) as e:
+        pkg.capi.Context(0)
+    assert e.value.code == pkg.capi.ERR_NO_DEVICE
+
+
+def test_unregistered_residual_rejected(pkg):
+    prob = pkg.NLLSProblem()
+    a = prob.addvariable(pkg.EuclideanVector([0.0] * 6))
+    b = prob.addvariable(pkg.EuclideanVector([0.0] * 3))
+    prob.addcost(pkg.SimpleError2([0.0, 0.0], a, b))  # generic SimpleError2 without generatemeasurement: no kernel
+    with pytest.raises(pkg.capi.NLLSError) as e:
+        prob._cost_aos()
+    assert e.value.code == pkg.capi.ERR_NO_KERNEL
+
+
+def test_unsupported_options(pkg):
+    prob = pkg.NLLSProblem()
+    prob.addvariable(pkg.EuclideanVector([0.0] * 6))
+    with pytest.raises(pkg.capi.NLLSError):
+        pkg.optimize(prob, pkg.NLLSOptions(iterator=pkg.newton))
+    with pytest.raises(pkg.capi.NLLSError):
+        pkg.optimize(prob, pkg.NLLSOptions(), unfixed=[True])

@@ -1,0 +1,321 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle on identical seeded inputs.
+
+Tolerances are BASELINE.json's: Hessian blocks and gradient <= 1e-12 relative, per-iteration cost <= 1e-10 relative,
+identical accept/reject (inner-try) sequence, final cost <= 1e-8 relative."""
+import os
+
+import numpy as np
+import pytest
+
+from helpers import blockwise_relerr, cuda_context, densify, oracle_problem, relerr
+
+pytestmark = pytest.mark.gpu
+
+TOL_H = 1e-12
+TOL_COST = 1e-10
+TOL_FINAL = 1e-8
+
+
+def _ba(pkg, ncam, npt, prop, seed=1, perturb=1e-3):
+    rng = np.random.default_rng(seed)
+    p = pkg.synthetic.create_ba_problem(ncam, npt, prop, rng)
+    pkg.synthetic.perturb_ba_problem(p, perturb, perturb, rng)
+    return p
+
+
+def _bal(pkg, ncam, npt, nobs, seed=0, **kw):
+    rng = np.random.default_rng(seed)
+    p = pkg.synthetic.create_bal_shaped(ncam, npt, nobs, rng, **kw)
+    pkg.synthetic.perturb_ba_problem(p, 1e-3, 1e-3, rng)
+    return p
+
+
+def _block_layout(p):
+    """(starts, sizes) of every block of the reference BSM for cameras-first BA."""
+    starts, sizes = [], []
+    o = 0
+    for _ in range(p.ncam):
+        starts.append(o); sizes.append(36); o += 36
+    k = np.bincount(p.pt_idx - p.ncam - 1, minlength=p.npt)
+    for kp in k:
+        for _ in range(kp):
+            starts.append(o); sizes.append(18); o += 18
+        starts.append(o); sizes.append(9); o += 9
+    return starts, sizes
+
+
+@pytest.mark.parametrize("tma", ["1", "0"])
+def test_linearize_c1_sparse(pkg, orc, tma):
+    # test/optimizeba.jl 10 x 50 @ 30% -> sparse BSM path in the reference
+    os.environ["NLLS_B200_TMA"] = tma
+    try:
+        p = _ba(pkg, 10, 50, 0.3)
+        P = oracle_problem(orc, p)
+        c_ref = P.linearize()
+        assert P.is_sparse
+        ctx = cuda_context(pkg, p)
+        c = ctx.linearize()
+        assert abs(c - c_ref) <= TOL_COST * abs(c_ref)
+        H, H_ref = ctx.hessian_blocks(), P.hess_data()
+        assert H.shape == H_ref.shape == (3510,)
+        starts, sizes = _block_layout(p)
+        assert blockwise_relerr(H, H_ref, starts, sizes) <= TOL_H
+        assert relerr(ctx.gradient(), P.grad()) <= TOL_H
+        assert abs(ctx.cost(0) - P.cost()) <= TOL_COST * P.cost()
+        ctx.close()
+    finally:
+        os.environ.pop("NLLS_B200_TMA", None)
+
+
+def test_linearize_c1_dense(pkg, orc):
+    # 3 x 5 full visibility: 33 DoF -> the reference uses its dense path; compare dense images
+    p = _ba(pkg, 3, 5, 1.0)
+    P = oracle_problem(orc, p)
+    c_ref = P.linearize()
+    assert not P.is_sparse
+    ctx = cuda_context(pkg, p)
+    c = ctx.linearize()
+    assert abs(c - c_ref) <= TOL_COST * abs(c_ref)
+    D = densify(ctx, [6] * 3 + [3] * 5)
+    assert relerr(D, P.hess_dense()) <= TOL_H
+    assert relerr(ctx.gradient(), P.grad()) <= TOL_H
+    ctx.close()
+
+
+KERNELS = {
+    "none": ((0, 0.0, False, 1.0), 0, ()),
+    "huber": ((1, 0.02, False, 1.0), 1, (0.02,)),
+    "huber2o": ((2, 0.02, False, 1.0), 2, (0.02,)),
+    "gemanmcclure": ((3, 0.05, False, 1.0), 3, (0.05,)),
+    "scaled_huber2o": ((2, 0.02, True, 3.0), 2 | 16, (0.02, 3.0)),
+    "scaled_none": ((0, 0.0, True, 2.0), 0 | 16, (0.0, 2.0)),
+}
+
+
+@pytest.mark.parametrize("kname", list(KERNELS))
+def test_linearize_ladybug_shape_robust(pkg, orc, kname):
+    # C2: Ladybug-shaped (49 / 7776 / 31843) with noise + outliers, every fixed robust kernel
+    ok, rid, kp = KERNELS[kname]
+    p = _bal(pkg, *pkg.synthetic.SHAPES["ladybug"], noise=0.01, outlier_frac=0.05)
+    P = oracle_problem(orc, p, kernel=ok)
+    c_ref = P.linearize()
+    ctx = cuda_context(pkg, p, rid, kp)
+    c = ctx.linearize()
+    assert abs(c - c_ref) <= TOL_COST * abs(c_ref)
+    H, H_ref = ctx.hessian_blocks(), P.hess_data()
+    starts, sizes = _block_layout(p)
+    assert blockwise_relerr(H, H_ref, starts, sizes) <= TOL_H
+    assert relerr(ctx.gradient(), P.grad()) <= TOL_H
+    assert abs(ctx.cost(0) - P.cost()) <= TOL_COST * P.cost()
+    ctx.close()
+
+
+def test_linearize_deterministic(pkg):
+    p = _bal(pkg, 49, 7776, 31843, noise=0.01)
+    ctx = cuda_context(pkg, p, 1, (0.02,))
+    c1 = ctx.linearize(); H1 = ctx.hessian_blocks(); g1 = ctx.gradient()
+    c2 = ctx.linearize(); H2 = ctx.hessian_blocks(); g2 = ctx.gradient()
+    assert c1 == c2 and np.array_equal(H1, H2) and np.array_equal(g1, g2)
+    assert ctx.cost(0) == ctx.cost(0)
+    ctx.close()
+
+
+def test_interleaved_variable_order(pkg, orc):
+    # variables added point, camera, point, camera ...: the reference stores each cross block in block row max(i, j)
+    rng = np.random.default_rng(5)
+    p = pkg.synthetic.create_ba_problem(6, 9, 0.6, rng)
+    pkg.synthetic.perturb_ba_problem(p, 1e-3, 1e-3, rng)
+    # new global order: interleave
+    cam_pos, pt_pos, order = {}, {}, []
+    ci = pi = 0
+    while ci < p.ncam or pi < p.npt:
+        if pi < p.npt:
+            order.append(("p", pi)); pi += 1
+        if ci < p.ncam:
+            order.append(("c", ci)); ci += 1
+        if pi < p.npt:
+            order.append(("p", pi)); pi += 1
+    for g, (kind, i) in enumerate(order):
+        (cam_pos if kind == "c" else pt_pos)[i] = g + 1
+    cam_g = np.array([cam_pos[i] for i in range(p.ncam)], dtype=np.int64)
+    pt_g = np.array([pt_pos[i] for i in range(p.npt)], dtype=np.int64)
+    vi = np.stack([cam_g[p.cam_idx - 1], pt_g[p.pt_idx - p.ncam - 1]], 1)
+    P = orc.Problem()
+    for kind, i in order:
+        P.add_variables(orc.VT_EUCLID, [p.cameras[i] if kind == "c" else p.points[i]])
+    # pad to >= 40 DoF is already true (6*6 + 9*3 = 63) -> BSM path
+    P.add_costs(orc.RT_AFFINE_BA, vi, p.z)
+    c_ref = P.linearize()
+    capi = pkg.capi
+    ctx = capi.Context(0)
+    ctx.set_variables(capi.VAR_EUCLID6, p.cameras, indices=cam_g)
+    ctx.set_variables(capi.VAR_EUCLID3, p.points, indices=pt_g)
+    aos = np.zeros(p.nobs, dtype=pkg.COST_DTYPE)
+    aos["z"] = p.z
+    aos["varind"] = vi
+    ctx.set_costs(capi.RES_AFFINE_BA, aos)
+    c = ctx.linearize()
+    assert abs(c - c_ref) <= TOL_COST * abs(c_ref)
+    if P.is_sparse:
+        assert relerr(ctx.hessian_blocks(), P.hess_data()) <= TOL_H
+    bs = [6 if k == "c" else 3 for k, _ in order]
+    assert relerr(densify(ctx, bs), P.hess_dense()) <= TOL_H
+    assert relerr(ctx.gradient(), P.grad()) <= TOL_H
+    ctx.close()
+
+
+@pytest.mark.parametrize("lam", [0.0, 1e-3, 10.0])
+def test_damped_solve_matches_full_system(pkg, orc, lam):
+    # Schur elimination + reduced solve == the reference's full-system solve x = -(H + lambda I)^-1 g  
+    p = _ba(pkg, 10, 50, 0.3)
+    P = oracle_problem(orc, p)
+    P.linearize()
+    x_ref = P.solve(lam)
+    ctx = cuda_context(pkg, p)
+    ctx.linearize()
+    ctx.solve(lam)
+    assert relerr(ctx.step(), x_ref) <= 1e-9
+    ctx.close()
+
+
+def _compare_trajectories(pkg, orc, p, kernel_o=None, robust=0, kparams=(), maxiters=100):
+    P = oracle_problem(orc, p, kernel=kernel_o)
+    res_ref, tr_ref = P.optimize(orc.Options(maxiters=maxiters))
+    ctx = cuda_context(pkg, p, robust, kparams)
+    ctx.lm_begin(pkg.NLLSOptions(maxiters=maxiters).c())
+    tr = []
+    conv = 0
+    while conv == 0:
+        info = ctx.lm_iterate()
+        tr.append((info.cost, info.ntries, info.lambda_))
+        conv = ctx.lm_advance(info.cost, 0)
+    res = ctx.lm_end()
+    return res, tr, res_ref, tr_ref, ctx, P
+
+
+def test_lm_trajectory_c1(pkg, orc):
+    # test/optimizeba.jl:71-75 — noise-free: costs collapse to rounding level, compare while they are meaningful
+    p = _ba(pkg, 10, 50, 0.3)
+    res, tr, res_ref, tr_ref, ctx, P = _compare_trajectories(pkg, orc, p)
+    assert res.startcost == pytest.approx(res_ref.startcost, rel=TOL_COST)
+    for (c, nt, lam), r in zip(tr, tr_ref):
+        if r.cost < 1e-18 * res_ref.startcost:
+            break
+        assert c == pytest.approx(r.cost, rel=1e-6)  # noise-free costs are differences of nearly equal numbers
+        assert nt == r.ntries
+    assert res.bestcost < 1e-15 and res_ref.bestcost < 1e-15           # :75
+    assert ctx.cost(0) == res.bestcost                                 # :74
+    ctx.close()
+
+
+@pytest.mark.parametrize("kname", ["none", "huber", "huber2o"])
+def test_lm_trajectory_ladybug_shape(pkg, orc, kname):
+    ok, rid, kp = KERNELS[kname]
+    p = _bal(pkg, *pkg.synthetic.SHAPES["ladybug"], noise=0.01, outlier_frac=0.05 if kname != "none" else 0.0)
+    res, tr, res_ref, tr_ref, ctx, P = _compare_trajectories(pkg, orc, p, ok, rid, kp, maxiters=30)
+    assert res.startcost == pytest.approx(res_ref.startcost, rel=TOL_COST)
+    n = min(len(tr), len(tr_ref))
+    assert n >= 3
+    compared = 0
+    for i in range(n):
+        c, nt, lam = tr[i]
+        r = tr_ref[i]
+        # once successive costs agree to ~1e-12 the accept/reject decisions are decided by rounding noise
+        if i > 0 and abs(tr_ref[i - 1].cost - r.cost) <= 1e-11 * r.cost:
+            break
+        assert c == pytest.approx(r.cost, rel=TOL_COST), (i, c, r.cost)
+        assert nt == r.ntries, (i, nt, r.ntries)
+        assert lam == pytest.approx(r.lambda_, rel=1e-6)
+        compared += 1
+    assert compared >= 3
+    assert res.bestcost == pytest.approx(res_ref.bestcost, rel=TOL_FINAL)
+    assert ctx.cost(0) == res.bestcost
+    ctx.close()
+
+
+def test_python_api_optimizeba(pkg):
+    # the reference test driven through the mirrored user API (NLLSProblem / addvariable! / addcost! / optimize!)
+    rng = np.random.default_rng(1)
+    for (nc, nl, pv) in [(3, 5, 1.0), (10, 50, 0.3)]:
+        p = pkg.synthetic.create_ba_problem(nc, nl, pv, rng)
+        pkg.synthetic.perturb_ba_problem(p, 1e-3, 1e-3, rng)
+        prob = pkg.NLLSProblem()
+        for c in p.cameras:
+            prob.addvariable(pkg.EuclideanVector(c))
+        for x in p.points:
+            prob.addvariable(pkg.EuclideanVector(x))
+        for z, ci, pi in zip(p.z, p.cam_idx, p.pt_idx):
+            prob.addcost(pkg.AffineReprojection(z, ci, pi))
+        result = pkg.optimize(prob)
+        assert pkg.cost(prob) == result.bestcost                       # test/optimizeba.jl:67,74
+        assert result.bestcost < 1e-15                                 # :68,75
+        # callbacks: storecostscallback sees monotone costs (test/functional.jl:74)
+        def perturb():
+            for i in range(len(prob.variables)):
+                v = np.asarray(prob.variables[i])
+                prob.variables[i] = pkg.EuclideanVector(v + rng.standard_normal(v.size) * 1e-3)
+        perturb()
+        ct = pkg.CostTrajectory()
+        result = pkg.optimize(prob, pkg.NLLSOptions(), None, pkg.storecostscallback(ct))
+        assert len(ct.costs) == result.niterations and all(b <= a for a, b in zip(ct.costs, ct.costs[1:]))
+        assert all(len(x) == 6 * nc + 3 * nl for x in ct.trajectory)
+        assert pkg.cost(prob) == result.bestcost
+        # callback termination flag + maxtime (test/functional.jl:51-54)
+        perturb()
+        result = pkg.optimize(prob, pkg.NLLSOptions(maxtime=0.0), None, lambda cost, *a: (cost, 13))
+        assert result.termination == (1 << 9) | (13 << 16) and result.niterations == 1
+        assert pkg.cost(prob) == result.bestcost
+
+
+def test_errors_through_abi(pkg):
+    capi = pkg.capi
+    p = _ba(pkg, 3, 5, 1.0)
+    ctx = capi.Context(0)
+    ctx.set_variables(capi.VAR_EUCLID6, p.cameras, first_index=1)
+    ctx.set_variables(capi.VAR_EUCLID3, p.points, first_index=p.ncam + 1)
+    with pytest.raises(capi.NLLSError) as e:
+        ctx.set_costs(99, p.costs_aos())
+    assert e.value.code == capi.ERR_NO_KERNEL
+    with pytest.raises(capi.NLLSError) as e:
+        ctx.set_costs(capi.RES_AFFINE_BA, p.costs_aos(), robust=7, kparams=(1.0,))
+    assert e.value.code == capi.ERR_NO_KERNEL
+    bad = p.costs_aos()
+    bad["varind"][0, 1] = 1  # a camera index where a point is expected
+    ctx.set_costs(capi.RES_AFFINE_BA, bad)
+    with pytest.raises(capi.NLLSError) as e:
+        ctx.linearize()
+    assert e.value.code == capi.ERR_INVALID
+    ctx.close()
+
+
+def test_venice_scale_properties(pkg):
+    # C4 at full size (1778 / 993923 / 5001946): size-independent properties instead of the (slow) oracle
+    p = _bal(pkg, *pkg.synthetic.SHAPES["venice"], noise=0.01, outlier_frac=0.02)
+    ctx = cuda_context(pkg, p, 1, (0.03,))
+    c0 = ctx.linearize()
+    assert c0 == ctx.cost(0) or abs(c0 - ctx.cost(0)) <= 1e-13 * c0     # same tiles, same tree
+    H1 = ctx.hessian_blocks()
+    ctx.linearize()
+    assert np.array_equal(H1, ctx.hessian_blocks())                    # deterministic assembly
+    g = ctx.gradient()
+    # directional derivative of the cost along a random direction d equals g . d (central differences)
+    rng = np.random.default_rng(7)
+    d_c = rng.standard_normal(p.cameras.shape)
+    d_p = rng.standard_normal(p.points.shape)
+    eps = 1e-6
+    gd = g[:6 * p.ncam] @ d_c.ravel() + g[6 * p.ncam:] @ d_p.ravel()
+    capi = pkg.capi
+    ctx.set_variables(capi.VAR_EUCLID6, p.cameras + eps * d_c, first_index=1)
+    ctx.set_variables(capi.VAR_EUCLID3, p.points + eps * d_p, first_index=p.ncam + 1)
+    cp = ctx.cost(0)
+    ctx.set_variables(capi.VAR_EUCLID6, p.cameras - eps * d_c, first_index=1)
+    ctx.set_variables(capi.VAR_EUCLID3, p.points - eps * d_p, first_index=p.ncam + 1)
+    cm = ctx.cost(0)
+    assert (cp - cm) / (2 * eps) == pytest.approx(gd, rel=1e-5)
+    # a few LM iterations: monotone decrease, cost(problem) == bestcost
+    ctx.set_variables(capi.VAR_EUCLID6, p.cameras, first_index=1)
+    ctx.set_variables(capi.VAR_EUCLID3, p.points, first_index=p.ncam + 1)
+    res = ctx.optimize(pkg.NLLSOptions(maxiters=4, maxtime=600.0).c())
+    assert res.bestcost < res.startcost
+    assert ctx.cost(0) == res.bestcost
+    ctx.close()
