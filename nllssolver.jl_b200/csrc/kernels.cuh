@@ -11,6 +11,7 @@
 #pragma once
 #include "common.cuh"
 #include "residuals.cuh"
+#include "reduced.cuh"
 
 namespace nlls {
 
@@ -37,6 +38,12 @@ struct DevProblem {
     long long gB;  // DC*nA
     RobustParams rk;
     int use_tma;
+    int schur_stride;
+    // reduced camera system: tile-sparse (tile_id[I * NT + J], -1 = structurally zero) or dense n x n
+    const int* tile_id;
+    const int* tile_pos;   // natural camera tile -> position in the elimination order
+    int NT;
+    int s_tiled;
 };
 
 template <class R>
@@ -363,7 +370,14 @@ __global__ void __launch_bounds__(LIN_THREADS) schur_tile_kernel(DevProblem p, d
     uint64_t* bar = reinterpret_cast<uint64_t*>(s_t + 3 * TILE_PTS);
     int* s_ost = reinterpret_cast<int*>(bar + 2);
 
-    const int tid = threadIdx.x, t = blockIdx.x;
+    const int tid = threadIdx.x;
+    // Co-resident CTAs would otherwise work on neighbouring points, i.e. the same few cameras, and serialise their
+    // reductions on the same S blocks in L2: stride the tile order so that concurrent CTAs touch distant cameras.
+    const int G = p.schur_stride;
+    const int per = (p.ntiles + G - 1) / G;
+    int t = (blockIdx.x % G) * per + blockIdx.x / G;
+    if (G <= 1) t = blockIdx.x;
+    if (t >= p.ntiles) return;
     const int pt0 = p.tile_pt[t], pt1 = p.tile_pt[t + 1];
     const int ob0 = p.obs_start[pt0], ob1 = p.obs_start[pt1];
     const int npt = pt1 - pt0, nob = ob1 - ob0;
@@ -415,7 +429,19 @@ __global__ void __launch_bounds__(LIN_THREADS) schur_tile_kernel(DevProblem p, d
         for (int j = jbeg; j <= tid; ++j) {   // cameras ascend within a point: cam_j <= cam_i -> lower triangle
             const int camj = p.obs_cam[ob0 + j];
             const double* y = s_Y + WB * j;
-            double* Sb = S + (size_t)cam * DC + (size_t)n * ((size_t)camj * DC);
+            double* Sb;
+            size_t sa, sb;   // strides of the block's row index a and column index b
+            if (p.s_tiled) {
+                constexpr int TC = ST / DC;
+                const int I = cam / TC, Jt = camj / TC;
+                const int r0 = (cam - I * TC) * DC, c0 = (camj - Jt * TC) * DC;
+                const int pI = p.tile_pos[I], pJ = p.tile_pos[Jt];
+                if (pI >= pJ) { Sb = S + (size_t)p.tile_id[(size_t)pI * p.NT + pJ] * ST2 + r0 + (size_t)ST * c0; sa = 1; sb = ST; }
+                else { Sb = S + (size_t)p.tile_id[(size_t)pJ * p.NT + pI] * ST2 + c0 + (size_t)ST * r0; sa = ST; sb = 1; }   // stored transposed
+            } else {
+                Sb = S + (size_t)cam * DC + (size_t)n * ((size_t)camj * DC);
+                sa = 1; sb = (size_t)n;
+            }
 #pragma unroll
             for (int b = 0; b < DC; ++b) {
                 const double y0 = y[3 * b], y1 = y[3 * b + 1], y2 = y[3 * b + 2];
@@ -423,7 +449,7 @@ __global__ void __launch_bounds__(LIN_THREADS) schur_tile_kernel(DevProblem p, d
                 for (int a = 0; a < DC; ++a) {
                     if (j == tid && a < b) continue;
                     const double v = W[3 * a] * y0 + W[3 * a + 1] * y1 + W[3 * a + 2] * y2;
-                    atomicAdd(Sb + a + (size_t)n * b, -v);
+                    atomicAdd(Sb + sa * a + sb * b, -v);
                 }
             }
         }

@@ -117,6 +117,20 @@ struct nlls_ctx {
     int* d_info = nullptr;
     int* d_ipiv = nullptr;
     int use_tma = 1;
+    int schur_stride = 296;
+    // reduced camera system (tile-sparse level-scheduled LDL' by default; NLLS_B200_REDUCED=dense selects dense storage + cuSOLVER)
+    int s_tiled = 1;
+    int NT = 0;
+    int64_t ntiles_alloc = 0;
+    int red_levels = 0;
+    struct RedLaunch { int kind, off, cnt; };          // kind 0 diag, 1 trsm, 2 update
+    std::vector<RedLaunch> fact_launches;
+    std::vector<std::pair<int, int>> lvl_cols;           // (offset, count) into d_lvl_cols per level
+    int *d_tile_id = nullptr, *d_pos = nullptr, *d_diag_tile = nullptr, *d_diag_tile_nat = nullptr, *d_diag_tasks = nullptr, *d_lvl_cols = nullptr;
+    int2* d_trsm_tasks = nullptr;
+    int4* d_upd_tasks = nullptr;
+    int *d_rowptr = nullptr, *d_row_tile = nullptr, *d_row_col = nullptr, *d_colptr = nullptr, *d_col_tile = nullptr, *d_col_row = nullptr;
+    double *d_Linv = nullptr, *d_xp = nullptr;
 
     // ---- multi-GPU
     int rank = 0, nranks = 1;
@@ -194,6 +208,8 @@ DevProblem devproblem(const nlls_ctx* c) {
     p.rk.kind = c->robust & 15; p.rk.scaled = (c->robust & NLLS_ROBUST_SCALED) ? 1 : 0;
     p.rk.width = c->kparams[0]; p.rk.width2 = c->kparams[0] * c->kparams[0]; p.rk.height = c->kparams[1];
     p.use_tma = c->use_tma;
+    p.schur_stride = c->schur_stride;
+    p.tile_id = c->d_tile_id; p.tile_pos = c->d_pos; p.NT = c->NT; p.s_tiled = c->s_tiled;
     return p;
 }
 
@@ -228,6 +244,10 @@ int set_smem_attrs(nlls_ctx* ctx) {
     CK(cudaFuncSetAttribute(lin_point_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LinSmem<R>::bytes));
     CK(cudaFuncSetAttribute(schur_tile_kernel<R::DC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SchurSmem<R::DC>::bytes));
     CK(cudaFuncSetAttribute(backsub_tile_kernel<R::DC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SchurSmem<R::DC>::bytes));
+    const int red_smem = 2 * ST * LDT * (int)sizeof(double);
+    CK(cudaFuncSetAttribute(ldl_trsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (ST * LDT + 2 * ST) * (int)sizeof(double)));
+    CK(cudaFuncSetAttribute(ldl_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, red_smem));
+    CK(cudaFuncSetAttribute(ldl_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, red_smem));
     return NLLS_OK;
 }
 
@@ -268,23 +288,42 @@ int launch_cost(nlls_ctx* ctx, int which, int slot) {
     return NLLS_OK;
 }
 
+RedSolveLists redlists(const nlls_ctx* c) {
+    RedSolveLists t;
+    t.diag_tile = c->d_diag_tile; t.rowptr = c->d_rowptr; t.row_tile = c->d_row_tile; t.row_col = c->d_row_col;
+    t.colptr = c->d_colptr; t.col_tile = c->d_col_tile; t.col_row = c->d_col_row;
+    return t;
+}
+
 template <class R>
 int launch_schur(nlls_ctx* ctx, double lambda) {
     constexpr int DC = R::DC;
     DevProblem p = devproblem(ctx);
     const int64_t n = ctx->nred;
-    CK(cudaMemsetAsync(ctx->d_S, 0, sizeof(double) * (size_t)n * n, ctx->st));
-    const long long tot = (long long)ctx->nA * DC * DC + n;
-    schur_init_kernel<DC><<<(unsigned)((tot + 255) / 256), 256, 0, ctx->st>>>(p, ctx->d_S, ctx->d_rhs, lambda, ctx->rank == 0 ? 1 : 0); ctx->launches++;
+    size_t scount;
+    if (ctx->s_tiled) {
+        scount = (size_t)ctx->ntiles_alloc * ST2;
+        CK(cudaMemsetAsync(ctx->d_S, 0, sizeof(double) * scount, ctx->st));
+        red_init_kernel<DC><<<ctx->NT, 256, 0, ctx->st>>>(ctx->d_S, ctx->d_diag_tile_nat, ctx->d_H, ctx->d_g, ctx->d_rhs, (int)ctx->nA, lambda,
+                                                            ctx->rank == 0 ? 1 : 0);
+        ctx->launches++;
+    } else {
+        scount = (size_t)n * n;
+        CK(cudaMemsetAsync(ctx->d_S, 0, sizeof(double) * scount, ctx->st));
+        const long long tot = (long long)ctx->nA * DC * DC + n;
+        schur_init_kernel<DC><<<(unsigned)((tot + 255) / 256), 256, 0, ctx->st>>>(p, ctx->d_S, ctx->d_rhs, lambda, ctx->rank == 0 ? 1 : 0); ctx->launches++;
+    }
     if (ctx->ntiles > 0) {
-        schur_tile_kernel<DC><<<ctx->ntiles, LIN_THREADS, SchurSmem<DC>::bytes, ctx->st>>>(p, ctx->d_S, ctx->d_rhs, ctx->d_Ainv, lambda);
+        const int G = std::max(1, ctx->schur_stride);
+        const int grid = G * ((ctx->ntiles + G - 1) / G);
+        schur_tile_kernel<DC><<<grid, LIN_THREADS, SchurSmem<DC>::bytes, ctx->st>>>(p, ctx->d_S, ctx->d_rhs, ctx->d_Ainv, lambda);
         ctx->launches++;
     }
     CK(cudaGetLastError());
     if (ctx->nranks > 1) {
         CKN(g_nccl.GroupStart());
-        CKN(g_nccl.AllReduce(ctx->d_S, ctx->d_S, (size_t)n * n, ncclFloat64, ncclSum, ctx->comm, ctx->st));
-        CKN(g_nccl.AllReduce(ctx->d_rhs, ctx->d_rhs, (size_t)n, ncclFloat64, ncclSum, ctx->comm, ctx->st));
+        CKN(g_nccl.AllReduce(ctx->d_S, ctx->d_S, scount, ncclFloat64, ncclSum, ctx->comm, ctx->st));
+        CKN(g_nccl.AllReduce(ctx->d_rhs, ctx->d_rhs, (size_t)(ctx->s_tiled ? (int64_t)ctx->NT * ST : n), ncclFloat64, ncclSum, ctx->comm, ctx->st));
         CKN(g_nccl.GroupEnd());
     }
     return NLLS_OK;
@@ -292,6 +331,30 @@ int launch_schur(nlls_ctx* ctx, double lambda) {
 
 int launch_reduced_solve(nlls_ctx* ctx, bool lu) {
     const int n = (int)ctx->nred;
+    if (ctx->s_tiled) {
+        const RedSolveLists t = redlists(ctx);
+        const int smem2 = 2 * ST * LDT * (int)sizeof(double), smem_trsm = (ST * LDT + 2 * ST) * (int)sizeof(double);
+        for (const auto& l : ctx->fact_launches) {
+            if (l.kind == 0) ldl_diag_kernel<<<l.cnt, RED_THREADS, 0, ctx->st>>>(ctx->d_S, ctx->d_diag_tasks + l.off);
+            else if (l.kind == 1) ldl_trsm_kernel<<<l.cnt, RED_THREADS, smem_trsm, ctx->st>>>(ctx->d_S, ctx->d_trsm_tasks + l.off);
+            else ldl_update_kernel<<<l.cnt, RED_THREADS, smem2, ctx->st>>>(ctx->d_S, ctx->d_upd_tasks + l.off);
+            ctx->launches++;
+        }
+        ldl_inv_kernel<<<ctx->NT, RED_THREADS, smem2, ctx->st>>>(ctx->d_S, ctx->d_diag_tile, ctx->d_Linv); ctx->launches++;
+        const int nx = ctx->NT * ST;
+        red_permute_kernel<<<(nx + 255) / 256, 256, 0, ctx->st>>>(ctx->d_rhs, ctx->d_xp, ctx->d_pos, ctx->NT, 1); ctx->launches++;
+        for (size_t l = 0; l < ctx->lvl_cols.size(); ++l) {
+            ldl_fwd_kernel<<<ctx->lvl_cols[l].second, SOLVE_THREADS, 0, ctx->st>>>(ctx->d_S, ctx->d_Linv, t, ctx->d_lvl_cols + ctx->lvl_cols[l].first, ctx->d_xp);
+            ctx->launches++;
+        }
+        for (size_t l = ctx->lvl_cols.size(); l-- > 0;) {
+            ldl_bwd_kernel<<<ctx->lvl_cols[l].second, SOLVE_THREADS, 0, ctx->st>>>(ctx->d_S, ctx->d_Linv, t, ctx->d_lvl_cols + ctx->lvl_cols[l].first, ctx->d_xp);
+            ctx->launches++;
+        }
+        red_permute_kernel<<<(nx + 255) / 256, 256, 0, ctx->st>>>(ctx->d_xp, ctx->d_rhs, ctx->d_pos, ctx->NT, 0); ctx->launches++;
+        CK(cudaGetLastError());
+        return NLLS_OK;
+    }
     if (!lu) {
         CKS(cusolverDnDpotrf(ctx->cusolver, CUBLAS_FILL_MODE_LOWER, n, ctx->d_S, n, ctx->d_work, ctx->lwork, ctx->d_info));
         // potrs on a failed factorisation yields garbage; the host checks info and redoes the try with LU
@@ -380,7 +443,7 @@ int do_try(nlls_ctx* ctx, double lambda) {
     TRY(enqueue_try(ctx, lambda, false));
     TRY(fetch_scalars(ctx));
     const int* info = reinterpret_cast<const int*>(ctx->h_scal + SC_COUNT);
-    if (info[0] != 0) {  // not positive definite: the reference falls back to QR / pivot-free LDL' (src/linearsolver.jl:20-26,29); we use LU
+    if (!ctx->s_tiled && info[0] != 0) {  // dense path, not positive definite: the reference falls back to QR (src/linearsolver.jl:20-26); we use LU
         TRY(enqueue_try(ctx, lambda, true));
         TRY(fetch_scalars(ctx));
     }
@@ -419,6 +482,8 @@ int nlls_create(nlls_ctx** out, int device) {
     cusolverDnSetStream(ctx->cusolver, ctx->st);
     const char* e = getenv("NLLS_B200_TMA");
     ctx->use_tma = (e && e[0] == '0') ? 0 : 1;
+    if (const char* g = getenv("NLLS_B200_SCHUR_STRIDE")) ctx->schur_stride = std::max(1, atoi(g));
+    if (const char* g = getenv("NLLS_B200_REDUCED")) ctx->s_tiled = (std::string(g) == "dense") ? 0 : 1;
     if (cudaGetLastError() != cudaSuccess) { delete ctx; return NLLS_ERR_CUDA; }
     *out = ctx;
     return NLLS_OK;
@@ -431,7 +496,9 @@ int nlls_destroy(nlls_ctx* ctx) {
     void* ptrs[] = {ctx->d_obs_cam, ctx->d_obs_pt, ctx->d_obs_start, ctx->d_tile_pt, ctx->d_obs_z, ctx->d_cm_pt, ctx->d_item_cam, ctx->d_item_beg,
                     ctx->d_item_end, ctx->d_cam_item_start, ctx->d_cm_z, ctx->d_A[0], ctx->d_A[1], ctx->d_A[2], ctx->d_B[0], ctx->d_B[1], ctx->d_B[2],
                     ctx->d_H, ctx->d_g, ctx->d_x, ctx->d_Ainv, ctx->d_S, ctx->d_rhs, ctx->d_cost_part, ctx->d_step_part, ctx->d_cam_part, ctx->d_scal,
-                    ctx->d_flush, ctx->d_work, ctx->d_info, ctx->d_ipiv};
+                    ctx->d_flush, ctx->d_work, ctx->d_info, ctx->d_ipiv, ctx->d_tile_id, ctx->d_pos, ctx->d_diag_tile, ctx->d_diag_tile_nat,
+                    ctx->d_diag_tasks, ctx->d_lvl_cols, ctx->d_trsm_tasks, ctx->d_upd_tasks, ctx->d_rowptr, ctx->d_row_tile, ctx->d_row_col, ctx->d_colptr,
+                    ctx->d_col_tile, ctx->d_col_row, ctx->d_Linv, ctx->d_xp};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (ctx->h_scal) cudaFreeHost(ctx->h_scal);
     if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
@@ -648,7 +715,128 @@ int nlls_prepare(nlls_ctx* ctx) {
     ctx->dof = (int64_t)DC * nA + 3 * nB;
     ctx->hlen = (int64_t)DC * DC * nA + (int64_t)WB * nobs + 9 * nB;
     ctx->nred = (int64_t)DC * nA;
-    if (ctx->nred > 46000) FAIL(NLLS_ERR_UNSUPPORTED, "reduced camera system larger than 46000 (dense path only in this build)");
+    // ---- reduced camera system: tile order, tile-level symbolic factorisation, level schedule
+    std::vector<int> tile_id, pos, diag_tile, diag_tile_nat, diag_tasks, lvl_cols_flat, rowptr, row_tile, row_col, colptr, col_tile, col_row;
+    std::vector<int2> trsm_tasks;
+    std::vector<int4> upd_tasks;
+    if (ctx->s_tiled) {
+        const int TC = ST / DC;
+        const int NT = (int)((nA + TC - 1) / TC);
+        ctx->NT = NT;
+        if ((int64_t)NT * NT > (1LL << 28)) FAIL(NLLS_ERR_UNSUPPORTED, "too many camera tiles for the tile map");
+        std::vector<unsigned char> natpat((size_t)NT * NT, 0);   // natural numbering, lower triangle
+        for (int I = 0; I < NT; ++I) natpat[(size_t)I * NT + I] = 1;
+        std::vector<int> tl;
+        for (int64_t pnt = 0; pnt < nB; ++pnt) {
+            tl.clear();
+            for (int j = ctx->h_obs_start[(size_t)pnt]; j < ctx->h_obs_start[(size_t)pnt + 1]; ++j) {
+                const int tI = ctx->h_obs_cam[(size_t)j] / TC;
+                if (tl.empty() || tl.back() != tI) tl.push_back(tI);   // cameras ascend within a point
+            }
+            for (size_t a = 0; a < tl.size(); ++a) for (size_t b = 0; b <= a; ++b) natpat[(size_t)tl[a] * NT + tl[b]] = 1;
+        }
+        if (ctx->nranks > 1) {  // ranks see different points: every rank needs the union pattern (same tile map, same factorisation)
+            unsigned char* d_pat = nullptr;
+            CK(cudaMalloc((void**)&d_pat, natpat.size()));
+            CK(cudaMemcpy(d_pat, natpat.data(), natpat.size(), cudaMemcpyHostToDevice));
+            CKN(g_nccl.AllReduce(d_pat, d_pat, natpat.size(), /*ncclUint8*/ 1, ncclMax, ctx->comm, ctx->st));
+            CK(cudaStreamSynchronize(ctx->st));
+            CK(cudaMemcpy(natpat.data(), d_pat, natpat.size(), cudaMemcpyDeviceToHost));
+            CK(cudaFree(d_pat));
+        }
+        // tile order: nested dissection by index when the pattern is banded (half-bandwidth w tiles), identity otherwise
+        int w = 0;
+        for (int I = 0; I < NT; ++I) for (int J2 = 0; J2 < I; ++J2) if (natpat[(size_t)I * NT + J2]) w = std::max(w, I - J2);
+        std::vector<int> nat_of_pos;
+        nat_of_pos.reserve((size_t)NT);
+        const bool use_nd = w >= 1 && NT >= 8 * w && !getenv("NLLS_B200_NO_ND");
+        if (use_nd) {
+            const int leaf = std::max(2 * w, 4);
+            struct Rec { static void nd(int lo, int hi, int w, int leaf, std::vector<int>& out) {
+                if (hi - lo <= leaf + w) { for (int i = lo; i < hi; ++i) out.push_back(i); return; }
+                const int s0 = lo + (hi - lo - w) / 2;
+                nd(lo, s0, w, leaf, out); nd(s0 + w, hi, w, leaf, out);
+                for (int i = s0; i < s0 + w; ++i) out.push_back(i);
+            } };
+            Rec::nd(0, NT, w, leaf, nat_of_pos);
+        } else {
+            for (int i = 0; i < NT; ++i) nat_of_pos.push_back(i);
+        }
+        pos.assign((size_t)NT, 0);
+        for (int q = 0; q < NT; ++q) pos[(size_t)nat_of_pos[(size_t)q]] = q;
+        std::vector<unsigned char> pat((size_t)NT * NT, 0);      // permuted numbering, lower triangle
+        for (int I = 0; I < NT; ++I) for (int J2 = 0; J2 <= I; ++J2) if (natpat[(size_t)I * NT + J2]) {
+            const int a = std::max(pos[(size_t)I], pos[(size_t)J2]), b = std::min(pos[(size_t)I], pos[(size_t)J2]);
+            pat[(size_t)a * NT + b] = 1;
+        }
+        std::vector<std::vector<int>> rows((size_t)NT);
+        for (int J2 = 0; J2 < NT; ++J2) {   // symbolic fill: eliminating column J couples every pair of its rows
+            std::vector<int>& r = rows[(size_t)J2];
+            for (int I = J2 + 1; I < NT; ++I) if (pat[(size_t)I * NT + J2]) r.push_back(I);
+            for (size_t a = 0; a < r.size(); ++a) for (size_t b = 0; b <= a; ++b) pat[(size_t)r[a] * NT + r[b]] = 1;
+        }
+        tile_id.assign((size_t)NT * NT, -1);
+        int nt = 0;
+        for (int J2 = 0; J2 < NT; ++J2) for (int I = J2; I < NT; ++I) if (pat[(size_t)I * NT + J2]) tile_id[(size_t)I * NT + J2] = nt++;
+        ctx->ntiles_alloc = nt;
+        if ((double)nt * ST2 * 8.0 > 60e9) FAIL(NLLS_ERR_UNSUPPORTED, "reduced camera system needs more than 60 GB");
+        diag_tile.resize((size_t)NT); diag_tile_nat.resize((size_t)NT);
+        for (int J2 = 0; J2 < NT; ++J2) diag_tile[(size_t)J2] = tile_id[(size_t)J2 * NT + J2];
+        for (int o = 0; o < NT; ++o) diag_tile_nat[(size_t)o] = diag_tile[(size_t)pos[(size_t)o]];
+        // levels of the elimination tree: column I waits for every column J < I that has I among its rows
+        std::vector<int> level((size_t)NT, 0);
+        int nlev = 0;
+        for (int J2 = 0; J2 < NT; ++J2) {
+            for (int I : rows[(size_t)J2]) level[(size_t)I] = std::max(level[(size_t)I], level[(size_t)J2] + 1);
+            nlev = std::max(nlev, level[(size_t)J2] + 1);
+        }
+        ctx->red_levels = nlev;
+        ctx->fact_launches.clear(); ctx->lvl_cols.clear();
+        std::vector<int> seen((size_t)nt, 0);
+        for (int lv = 0; lv < nlev; ++lv) {
+            const int c0 = (int)lvl_cols_flat.size(), d0 = (int)diag_tasks.size(), t0 = (int)trsm_tasks.size();
+            std::vector<std::pair<int, int4>> ups;   // (round, task)
+            std::vector<int> touched;
+            for (int J2 = 0; J2 < NT; ++J2) {
+                if (level[(size_t)J2] != lv) continue;
+                lvl_cols_flat.push_back(J2);
+                diag_tasks.push_back(diag_tile[(size_t)J2]);
+                const std::vector<int>& r = rows[(size_t)J2];
+                for (int I : r) trsm_tasks.push_back(make_int2(tile_id[(size_t)I * NT + J2], diag_tile[(size_t)J2]));
+                for (size_t a = 0; a < r.size(); ++a) for (size_t b = 0; b <= a; ++b) {
+                    const int tc = tile_id[(size_t)r[a] * NT + r[b]];
+                    ups.push_back({seen[(size_t)tc]++, make_int4(tile_id[(size_t)r[a] * NT + J2], tile_id[(size_t)r[b] * NT + J2], tc, diag_tile[(size_t)J2])});
+                    touched.push_back(tc);
+                }
+            }
+            for (int tc : touched) seen[(size_t)tc] = 0;
+            ctx->lvl_cols.push_back({c0, (int)lvl_cols_flat.size() - c0});
+            ctx->fact_launches.push_back({0, d0, (int)diag_tasks.size() - d0});
+            if ((int)trsm_tasks.size() > t0) ctx->fact_launches.push_back({1, t0, (int)trsm_tasks.size() - t0});
+            std::stable_sort(ups.begin(), ups.end(), [](const std::pair<int, int4>& x, const std::pair<int, int4>& y) { return x.first < y.first; });
+            size_t i0 = 0;
+            while (i0 < ups.size()) {   // one launch per round: tasks of a round hit distinct target tiles
+                size_t i1 = i0;
+                const int u0 = (int)upd_tasks.size();
+                while (i1 < ups.size() && ups[i1].first == ups[i0].first) upd_tasks.push_back(ups[i1++].second);
+                ctx->fact_launches.push_back({2, u0, (int)upd_tasks.size() - u0});
+                i0 = i1;
+            }
+        }
+        if (getenv("NLLS_B200_VERBOSE"))
+            fprintf(stderr, "[nlls] reduced system: NT=%d tiles=%d half-bandwidth=%d nd=%d levels=%d fact_launches=%zu trsm=%zu upd=%zu\n", NT, nt, w,
+                    (int)use_nd, nlev, ctx->fact_launches.size(), trsm_tasks.size(), upd_tasks.size());
+        // block-row and block-column lists of L for the sweeps
+        rowptr.assign((size_t)NT + 1, 0); colptr.assign((size_t)NT + 1, 0);
+        for (int J2 = 0; J2 < NT; ++J2) {
+            for (int K = 0; K < J2; ++K) if (tile_id[(size_t)J2 * NT + K] >= 0) { row_tile.push_back(tile_id[(size_t)J2 * NT + K]); row_col.push_back(K); }
+            rowptr[(size_t)J2 + 1] = (int)row_tile.size();
+            for (int I : rows[(size_t)J2]) { col_tile.push_back(tile_id[(size_t)I * NT + J2]); col_row.push_back(I); }
+            colptr[(size_t)J2 + 1] = (int)col_tile.size();
+        }
+    } else {
+        if (ctx->nred > 46000) FAIL(NLLS_ERR_UNSUPPORTED, "reduced camera system larger than 46000 (dense cuSOLVER path)");
+    }
 
     TRY(upload(ctx, &ctx->d_obs_cam, ctx->h_obs_cam)); TRY(upload(ctx, &ctx->d_obs_pt, ctx->h_obs_pt)); TRY(upload(ctx, &ctx->d_obs_z, obs_z));
     TRY(upload(ctx, &ctx->d_obs_start, ctx->h_obs_start)); TRY(upload(ctx, &ctx->d_tile_pt, ctx->h_tile_pt));
@@ -663,16 +851,29 @@ int nlls_prepare(nlls_ctx* ctx) {
     CK(cudaMemsetAsync(ctx->d_g, 0, sizeof(double) * ctx->dof, ctx->st));
     CK(cudaMemsetAsync(ctx->d_x, 0, sizeof(double) * ctx->dof, ctx->st));
     TRY(dalloc(ctx, &ctx->d_Ainv, (size_t)6 * nB));
-    TRY(dalloc(ctx, &ctx->d_S, (size_t)ctx->nred * ctx->nred)); TRY(dalloc(ctx, &ctx->d_rhs, (size_t)ctx->nred));
+    if (ctx->s_tiled) {
+        TRY(dalloc(ctx, &ctx->d_S, (size_t)ctx->ntiles_alloc * ST2)); TRY(dalloc(ctx, &ctx->d_rhs, (size_t)ctx->NT * ST));
+        TRY(dalloc(ctx, &ctx->d_Linv, (size_t)ctx->NT * ST2)); TRY(dalloc(ctx, &ctx->d_xp, (size_t)ctx->NT * ST));
+        TRY(upload(ctx, &ctx->d_tile_id, tile_id)); TRY(upload(ctx, &ctx->d_pos, pos));
+        TRY(upload(ctx, &ctx->d_diag_tile, diag_tile)); TRY(upload(ctx, &ctx->d_diag_tile_nat, diag_tile_nat));
+        TRY(upload(ctx, &ctx->d_diag_tasks, diag_tasks)); TRY(upload(ctx, &ctx->d_trsm_tasks, trsm_tasks)); TRY(upload(ctx, &ctx->d_upd_tasks, upd_tasks));
+        TRY(upload(ctx, &ctx->d_lvl_cols, lvl_cols_flat));
+        TRY(upload(ctx, &ctx->d_rowptr, rowptr)); TRY(upload(ctx, &ctx->d_row_tile, row_tile)); TRY(upload(ctx, &ctx->d_row_col, row_col));
+        TRY(upload(ctx, &ctx->d_colptr, colptr)); TRY(upload(ctx, &ctx->d_col_tile, col_tile)); TRY(upload(ctx, &ctx->d_col_row, col_row));
+    } else {
+        TRY(dalloc(ctx, &ctx->d_S, (size_t)ctx->nred * ctx->nred)); TRY(dalloc(ctx, &ctx->d_rhs, (size_t)ctx->nred));
+    }
     TRY(dalloc(ctx, &ctx->d_cost_part, (size_t)ctx->ntiles)); TRY(dalloc(ctx, &ctx->d_step_part, (size_t)4 * ctx->ntiles));
     const int NU = DC * (DC + 1) / 2 + DC;
     TRY(dalloc(ctx, &ctx->d_cam_part, (size_t)ctx->nitems * NU));
-    int lw1 = 0, lw2 = 0;
-    CKS(cusolverDnDpotrf_bufferSize(ctx->cusolver, CUBLAS_FILL_MODE_LOWER, (int)ctx->nred, ctx->d_S, (int)ctx->nred, &lw1));
-    CKS(cusolverDnDgetrf_bufferSize(ctx->cusolver, (int)ctx->nred, (int)ctx->nred, ctx->d_S, (int)ctx->nred, &lw2));
-    ctx->lwork = std::max(lw1, lw2);
-    TRY(dalloc(ctx, &ctx->d_work, (size_t)ctx->lwork));
-    TRY(dalloc(ctx, &ctx->d_ipiv, (size_t)ctx->nred));
+    if (!ctx->s_tiled) {
+        int lw1 = 0, lw2 = 0;
+        CKS(cusolverDnDpotrf_bufferSize(ctx->cusolver, CUBLAS_FILL_MODE_LOWER, (int)ctx->nred, ctx->d_S, (int)ctx->nred, &lw1));
+        CKS(cusolverDnDgetrf_bufferSize(ctx->cusolver, (int)ctx->nred, (int)ctx->nred, ctx->d_S, (int)ctx->nred, &lw2));
+        ctx->lwork = std::max(lw1, lw2);
+        TRY(dalloc(ctx, &ctx->d_work, (size_t)ctx->lwork));
+        TRY(dalloc(ctx, &ctx->d_ipiv, (size_t)ctx->nred));
+    }
     TRY(DISPATCH(ctx, set_smem_attrs, ctx));
     CK(cudaStreamSynchronize(ctx->st));
     ctx->prepared = true;
@@ -705,7 +906,7 @@ int nlls_solve(nlls_ctx* ctx, double lambda) {
     TRY(launch_reduced_solve(ctx, false));
     TRY(fetch_scalars(ctx));
     const int* info = reinterpret_cast<const int*>(ctx->h_scal + SC_COUNT);
-    if (info[0] != 0) {
+    if (!ctx->s_tiled && info[0] != 0) {
         TRY(DISPATCH(ctx, launch_schur, ctx, lambda));
         TRY(launch_reduced_solve(ctx, true));
     }
