@@ -14,6 +14,7 @@
 #include <limits>
 #include <map>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/nlls_b200.h"
@@ -131,6 +132,12 @@ struct nlls_ctx {
     int4* d_upd_tasks = nullptr;
     int *d_rowptr = nullptr, *d_row_tile = nullptr, *d_row_col = nullptr, *d_colptr = nullptr, *d_col_tile = nullptr, *d_col_row = nullptr;
     double *d_Linv = nullptr, *d_xp = nullptr;
+    // Schur v2 plan (per-tile sorted contribution lists)
+    int schur_v2 = 1;
+    int nstiles = 0;
+    int *d_stile_pt = nullptr, *d_chunk_off = nullptr;
+    SchurChunk* d_chunks = nullptr;
+    unsigned int* d_ents = nullptr;
 
     // ---- multi-GPU
     int rank = 0, nranks = 1;
@@ -244,8 +251,9 @@ int set_smem_attrs(nlls_ctx* ctx) {
     CK(cudaFuncSetAttribute(lin_point_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LinSmem<R>::bytes));
     CK(cudaFuncSetAttribute(schur_tile_kernel<R::DC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SchurSmem<R::DC>::bytes));
     CK(cudaFuncSetAttribute(backsub_tile_kernel<R::DC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SchurSmem<R::DC>::bytes));
+    CK(cudaFuncSetAttribute(schur2_kernel<R::DC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Schur2Smem<R::DC>::bytes));
     const int red_smem = 2 * ST * LDT * (int)sizeof(double);
-    CK(cudaFuncSetAttribute(ldl_trsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (ST * LDT + 2 * ST) * (int)sizeof(double)));
+    CK(cudaFuncSetAttribute(ldl_trsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (ST * LDT + ST * LDP) * (int)sizeof(double)));
     CK(cudaFuncSetAttribute(ldl_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, red_smem));
     CK(cudaFuncSetAttribute(ldl_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, red_smem));
     return NLLS_OK;
@@ -313,7 +321,15 @@ int launch_schur(nlls_ctx* ctx, double lambda) {
         const long long tot = (long long)ctx->nA * DC * DC + n;
         schur_init_kernel<DC><<<(unsigned)((tot + 255) / 256), 256, 0, ctx->st>>>(p, ctx->d_S, ctx->d_rhs, lambda, ctx->rank == 0 ? 1 : 0); ctx->launches++;
     }
-    if (ctx->ntiles > 0) {
+    if (ctx->schur_v2 && ctx->nstiles > 0) {
+        SchurPlan sp;
+        sp.stile_pt = ctx->d_stile_pt; sp.chunk_off = ctx->d_chunk_off; sp.chunks = ctx->d_chunks; sp.ents = ctx->d_ents; sp.nstiles = ctx->nstiles;
+        sp.ld = ctx->s_tiled ? ST : n;
+        const int G = std::max(1, ctx->schur_stride);
+        const int grid = G * ((ctx->nstiles + G - 1) / G);
+        schur2_kernel<DC><<<grid, SCH_THREADS, Schur2Smem<DC>::bytes, ctx->st>>>(p, sp, ctx->d_S, ctx->d_rhs, ctx->d_Ainv, lambda);
+        ctx->launches++;
+    } else if (ctx->ntiles > 0) {
         const int G = std::max(1, ctx->schur_stride);
         const int grid = G * ((ctx->ntiles + G - 1) / G);
         schur_tile_kernel<DC><<<grid, LIN_THREADS, SchurSmem<DC>::bytes, ctx->st>>>(p, ctx->d_S, ctx->d_rhs, ctx->d_Ainv, lambda);
@@ -333,14 +349,14 @@ int launch_reduced_solve(nlls_ctx* ctx, bool lu) {
     const int n = (int)ctx->nred;
     if (ctx->s_tiled) {
         const RedSolveLists t = redlists(ctx);
-        const int smem2 = 2 * ST * LDT * (int)sizeof(double), smem_trsm = (ST * LDT + 2 * ST) * (int)sizeof(double);
+        const int smem2 = 2 * ST * LDT * (int)sizeof(double), smem_trsm = (ST * LDT + ST * LDP) * (int)sizeof(double);
         for (const auto& l : ctx->fact_launches) {
             if (l.kind == 0) ldl_diag_kernel<<<l.cnt, RED_THREADS, 0, ctx->st>>>(ctx->d_S, ctx->d_diag_tasks + l.off);
             else if (l.kind == 1) ldl_trsm_kernel<<<l.cnt, RED_THREADS, smem_trsm, ctx->st>>>(ctx->d_S, ctx->d_trsm_tasks + l.off);
             else ldl_update_kernel<<<l.cnt, RED_THREADS, smem2, ctx->st>>>(ctx->d_S, ctx->d_upd_tasks + l.off);
             ctx->launches++;
         }
-        ldl_inv_kernel<<<ctx->NT, RED_THREADS, smem2, ctx->st>>>(ctx->d_S, ctx->d_diag_tile, ctx->d_Linv); ctx->launches++;
+        ldl_inv_kernel<<<ctx->NT, RED_THREADS, (ST * LDT + NB * LDT) * (int)sizeof(double), ctx->st>>>(ctx->d_S, ctx->d_diag_tile, ctx->d_Linv); ctx->launches++;
         const int nx = ctx->NT * ST;
         red_permute_kernel<<<(nx + 255) / 256, 256, 0, ctx->st>>>(ctx->d_rhs, ctx->d_xp, ctx->d_pos, ctx->NT, 1); ctx->launches++;
         for (size_t l = 0; l < ctx->lvl_cols.size(); ++l) {
@@ -484,6 +500,7 @@ int nlls_create(nlls_ctx** out, int device) {
     ctx->use_tma = (e && e[0] == '0') ? 0 : 1;
     if (const char* g = getenv("NLLS_B200_SCHUR_STRIDE")) ctx->schur_stride = std::max(1, atoi(g));
     if (const char* g = getenv("NLLS_B200_REDUCED")) ctx->s_tiled = (std::string(g) == "dense") ? 0 : 1;
+    if (const char* g = getenv("NLLS_B200_SCHUR")) ctx->schur_v2 = (std::string(g) == "v1") ? 0 : 1;
     if (cudaGetLastError() != cudaSuccess) { delete ctx; return NLLS_ERR_CUDA; }
     *out = ctx;
     return NLLS_OK;
@@ -498,7 +515,7 @@ int nlls_destroy(nlls_ctx* ctx) {
                     ctx->d_H, ctx->d_g, ctx->d_x, ctx->d_Ainv, ctx->d_S, ctx->d_rhs, ctx->d_cost_part, ctx->d_step_part, ctx->d_cam_part, ctx->d_scal,
                     ctx->d_flush, ctx->d_work, ctx->d_info, ctx->d_ipiv, ctx->d_tile_id, ctx->d_pos, ctx->d_diag_tile, ctx->d_diag_tile_nat,
                     ctx->d_diag_tasks, ctx->d_lvl_cols, ctx->d_trsm_tasks, ctx->d_upd_tasks, ctx->d_rowptr, ctx->d_row_tile, ctx->d_row_col, ctx->d_colptr,
-                    ctx->d_col_tile, ctx->d_col_row, ctx->d_Linv, ctx->d_xp};
+                    ctx->d_col_tile, ctx->d_col_row, ctx->d_Linv, ctx->d_xp, ctx->d_stile_pt, ctx->d_chunk_off, ctx->d_chunks, ctx->d_ents};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (ctx->h_scal) cudaFreeHost(ctx->h_scal);
     if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
@@ -836,6 +853,95 @@ int nlls_prepare(nlls_ctx* ctx) {
         }
     } else {
         if (ctx->nred > 46000) FAIL(NLLS_ERR_UNSUPPORTED, "reduced camera system larger than 46000 (dense cuSOLVER path)");
+    }
+
+    // ---- Schur v2 plan: larger point tiles + per-tile contribution lists sorted by target block
+    if (ctx->schur_v2) {
+        std::vector<int> stile_pt;
+        stile_pt.push_back(0);
+        {
+            auto aligned = [&](int64_t pt) { return ((WB * (int64_t)ctx->h_obs_start[(size_t)pt] + 9 * pt) & 1) == 0; };
+            int64_t p0 = 0;
+            while (p0 < nB) {
+                int64_t p1 = p0;
+                while (p1 < nB && (p1 - p0) < SCH_PTS && (ctx->h_obs_start[(size_t)p1 + 1] - ctx->h_obs_start[(size_t)p0]) <= SCH_OBS) ++p1;
+                if (p1 < nB && !aligned(p1) && p1 - 1 > p0 && aligned(p1 - 1)) --p1;
+                stile_pt.push_back((int)p1);
+                p0 = p1;
+            }
+        }
+        const int nst = (int)stile_pt.size() - 1;
+        ctx->nstiles = nst;
+        const int TC = ST / DC;
+        const int NTl = ctx->NT;
+        const long long nn = ctx->nred;
+        struct TilePlan { std::vector<SchurChunk> chunks; std::vector<unsigned int> ents; };
+        std::vector<TilePlan> plans((size_t)nst);
+        auto build = [&](int t0, int t1) {
+            std::vector<unsigned long long> keys;
+            for (int t = t0; t < t1; ++t) {
+                const int pa = stile_pt[(size_t)t], pb = stile_pt[(size_t)t + 1];
+                const int ob0 = ctx->h_obs_start[(size_t)pa];
+                keys.clear();
+                for (int pp = pa; pp < pb; ++pp) {
+                    const int b = ctx->h_obs_start[(size_t)pp], e = ctx->h_obs_start[(size_t)pp + 1];
+                    for (int i = b; i < e; ++i) for (int j = b; j <= i; ++j) {
+                        const unsigned long long key = ((unsigned long long)ctx->h_obs_cam[(size_t)i] << 22) | (unsigned long long)ctx->h_obs_cam[(size_t)j];   // 22 + 22 + 10 + 10 bits
+                        keys.push_back((key << 20) | ((unsigned long long)(i - ob0) << 10) | (unsigned long long)(j - ob0));   // SCH_OBS <= 1024
+                    }
+                }
+                std::sort(keys.begin(), keys.end());
+                TilePlan& pl = plans[(size_t)t];
+                pl.ents.resize(keys.size());
+                size_t k0 = 0;
+                while (k0 < keys.size()) {
+                    const unsigned long long key = keys[k0] >> 20;
+                    size_t k1 = k0;
+                    while (k1 < keys.size() && (keys[k1] >> 20) == key) ++k1;
+                    const int cam = (int)(key >> 22), camj = (int)(key & 0x3fffffu);
+                    long long soff; short flags = (cam == camj) ? 2 : 0;
+                    if (ctx->s_tiled) {
+                        const int I = cam / TC, Jt = camj / TC, r0 = (cam - I * TC) * DC, c0 = (camj - Jt * TC) * DC;
+                        const int pI = pos[(size_t)I], pJ = pos[(size_t)Jt];
+                        if (pI >= pJ) soff = (long long)tile_id[(size_t)pI * NTl + pJ] * ST2 + r0 + (long long)ST * c0;
+                        else { soff = (long long)tile_id[(size_t)pJ * NTl + pI] * ST2 + c0 + (long long)ST * r0; flags |= 1; }
+                    } else {
+                        soff = (long long)cam * DC + nn * ((long long)camj * DC);
+                    }
+                    for (size_t k = k0; k < k1; k += SCH_CHUNK) {
+                        SchurChunk ck;
+                        ck.soff = soff; ck.ent0 = (int)k; ck.cam = cam; ck.n = (short)std::min<size_t>(SCH_CHUNK, k1 - k); ck.flags = flags;
+                        pl.chunks.push_back(ck);
+                    }
+                    for (size_t k = k0; k < k1; ++k) pl.ents[k] = (unsigned int)((((keys[k] >> 10) & 0x3ffu) << 16) | (keys[k] & 0x3ffu));
+                    k0 = k1;
+                }
+            }
+        };
+        if (nA >= (1 << 22)) FAIL(NLLS_ERR_UNSUPPORTED, "more than 2^22 cameras");
+        {
+            const int nth = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+            std::vector<std::thread> th;
+            for (int k = 0; k < nth; ++k) th.emplace_back(build, (int)((int64_t)nst * k / nth), (int)((int64_t)nst * (k + 1) / nth));
+            for (auto& x : th) x.join();
+        }
+        std::vector<int> chunk_off((size_t)nst + 1, 0);
+        size_t nent = 0, nch = 0;
+        for (int t = 0; t < nst; ++t) { nent += plans[(size_t)t].ents.size(); nch += plans[(size_t)t].chunks.size(); }
+        if (nent >= (1ull << 31)) FAIL(NLLS_ERR_UNSUPPORTED, "too many Schur contributions per rank");
+        std::vector<SchurChunk> chunks; chunks.reserve(nch);
+        std::vector<unsigned int> ents; ents.reserve(nent);
+        for (int t = 0; t < nst; ++t) {
+            const int base = (int)ents.size();
+            for (SchurChunk ck : plans[(size_t)t].chunks) { ck.ent0 += base; chunks.push_back(ck); }
+            ents.insert(ents.end(), plans[(size_t)t].ents.begin(), plans[(size_t)t].ents.end());
+            chunk_off[(size_t)t + 1] = (int)chunks.size();
+            plans[(size_t)t] = TilePlan();
+        }
+        if (getenv("NLLS_B200_VERBOSE"))
+            fprintf(stderr, "[nlls] schur plan: %d tiles, %zu contributions, %zu chunks (%.2f contributions per chunk)\n", nst, nent, nch, (double)nent / std::max<size_t>(nch, 1));
+        TRY(upload(ctx, &ctx->d_stile_pt, stile_pt)); TRY(upload(ctx, &ctx->d_chunk_off, chunk_off));
+        TRY(upload(ctx, &ctx->d_chunks, chunks)); TRY(upload(ctx, &ctx->d_ents, ents));
     }
 
     TRY(upload(ctx, &ctx->d_obs_cam, ctx->h_obs_cam)); TRY(upload(ctx, &ctx->d_obs_pt, ctx->h_obs_pt)); TRY(upload(ctx, &ctx->d_obs_z, obs_z));

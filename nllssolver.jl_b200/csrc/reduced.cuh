@@ -39,13 +39,19 @@ struct RedSolveLists {        // device pointers for the triangular sweeps
     const int* col_row;
 };
 
+constexpr int NB = 8;            // panel width of the blocked tile algorithms
+constexpr int LDP = NB + 1;      // padded leading dimension of panel buffers
+
 // ---------------------------------------------------------------------------------------------------
-// In-place LDL' of diagonal tiles.  On exit the strict lower triangle holds L (unit diagonal implied) and the diagonal
-// holds D; the upper triangle is not referenced.  Register-resident right-looking elimination, one barrier per pivot.
+// In-place LDL' of diagonal tiles, blocked by panels of NB columns.  On exit the strict lower triangle holds L (unit
+// diagonal implied) and the diagonal holds D; the upper triangle is not referenced.
+// Per panel: (1) owners publish the panel, (2) 8 lanes factor the 8 x 8 diagonal block, (3) one thread per row below it
+// solves its row of L21, (4) the panel is written out, (5) all threads apply the rank-8 update to their registers.
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(RED_THREADS) ldl_diag_kernel(double* __restrict__ S, const int* __restrict__ tasks) {
-    __shared__ double u[2][ST];      // column j below the diagonal before scaling (= L D), double-buffered
-    __shared__ double dj[2];
+    __shared__ double Up[ST * LDP];   // panel of A, then U = L D
+    __shared__ double Lp[ST * LDP];   // panel of L
+    __shared__ double dd[NB], rdd[NB], col[NB];
     double* T = S + (size_t)tasks[blockIdx.x] * ST2;
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     double R[RB][RB];
@@ -56,50 +62,97 @@ __global__ void __launch_bounds__(RED_THREADS) ldl_diag_kernel(double* __restric
             const int i = ty + 16 * a, k = tx + 16 * b;
             R[a][b] = (i < ST && k < ST && i >= k) ? T[i + ST * k] : 0.0;
         }
-    for (int j = 0; j < ST; ++j) {
-        const int jb = j >> 4, jx = j & 15, buf = j & 1;
-        if (tx == jx) {              // owners of column j publish it
+    for (int j0 = 0; j0 < ST; j0 += NB) {
+        const int jb = j0 >> 4, jx0 = j0 & 15;
+        // (1) owners of columns j0 .. j0+7 publish rows >= j0
+        if (tx >= jx0 && tx < jx0 + NB) {
+            const int t = tx - jx0;
 #pragma unroll
             for (int b = 0; b < RB; ++b)
                 if (b == jb) {
 #pragma unroll
-                    for (int a = 0; a < RB; ++a) {
-                        const int i = ty + 16 * a;
-                        if (i < ST && i > j) u[buf][i] = R[a][b];
-                        if (i == j) dj[buf] = R[a][b];
-                    }
+                    for (int a = 0; a < RB; ++a) { const int i = ty + 16 * a; if (i >= j0 && i < ST) Up[i * LDP + t] = R[a][b]; }
                 }
         }
         __syncthreads();
-        const double rd = 1.0 / dj[buf];
-        double li[RB], uk[RB];
+        // (2) 8 x 8 diagonal block: lane r owns row r
+        if (tid < NB) {
+            const int r = tid;
+            double A[NB];
 #pragma unroll
-        for (int a = 0; a < RB; ++a) { const int i = ty + 16 * a; li[a] = (i < ST && i > j) ? u[buf][i] * rd : 0.0; }
+            for (int c = 0; c < NB; ++c) A[c] = (c <= r) ? Up[(j0 + r) * LDP + c] : 0.0;
 #pragma unroll
-        for (int b = 0; b < RB; ++b) { const int k = tx + 16 * b; uk[b] = (k < ST && k > j) ? u[buf][k] : 0.0; }
+            for (int t = 0; t < NB; ++t) {
+                if (r >= t) col[r] = A[t];
+                __syncwarp(0xffu);
+                const double d = col[t];
+                if (r > t) {
+                    const double l = A[t] / d;
 #pragma unroll
-        for (int a = 0; a < RB; ++a)
-#pragma unroll
-            for (int b = 0; b < RB; ++b) {
-                const int i = ty + 16 * a, k = tx + 16 * b;
-                if (i >= k) R[a][b] = fma(-li[a], uk[b], R[a][b]);   // uk = 0 for k <= j, li = 0 for i <= j
-                if (k == j && i > j && i < ST) R[a][b] = li[a];       // store L in column j
+                    for (int c = t + 1; c < NB; ++c) if (c <= r) A[c] = fma(-l, col[c], A[c]);
+                    A[t] = l;
+                }
+                __syncwarp(0xffu);
             }
-    }
 #pragma unroll
-    for (int a = 0; a < RB; ++a)
-#pragma unroll
-        for (int b = 0; b < RB; ++b) {
-            const int i = ty + 16 * a, k = tx + 16 * b;
-            if (i < ST && k < ST && i >= k) T[i + ST * k] = R[a][b];
+            for (int c = 0; c < NB; ++c) if (c < r) Lp[(j0 + r) * LDP + c] = A[c];
+            dd[r] = A[r];
+            rdd[r] = 1.0 / A[r];
         }
+        __syncthreads();
+        // (3) rows below the block: U21 L11' = A21, L21 = U21 D11^-1
+        if (tid < ST && tid >= j0 + NB) {
+            const int i = tid;
+            double uu[NB];
+#pragma unroll
+            for (int t = 0; t < NB; ++t) {
+                double v = Up[i * LDP + t];
+#pragma unroll
+                for (int q = 0; q < t; ++q) v = fma(-uu[q], Lp[(j0 + t) * LDP + q], v);
+                uu[t] = v;
+            }
+#pragma unroll
+            for (int t = 0; t < NB; ++t) { Up[i * LDP + t] = uu[t]; Lp[i * LDP + t] = uu[t] * rdd[t]; }
+        }
+        __syncthreads();
+        // (4) write the finished panel columns
+        for (int e = tid; e < ST * NB; e += RED_THREADS) {
+            const int i = e % ST, t = e / ST, k = j0 + t;
+            if (i > k) T[i + ST * k] = Lp[i * LDP + t];
+            else if (i == k) T[i + ST * k] = dd[t];
+        }
+        // (5) trailing update A22 -= L21 U21'
+        if (j0 + NB < ST) {
+#pragma unroll
+            for (int a = 0; a < RB; ++a) {
+                const int i = ty + 16 * a;
+                if (16 * a + 15 < j0 + NB || i >= ST) continue;
+                double lv[NB];
+#pragma unroll
+                for (int t = 0; t < NB; ++t) lv[t] = (i >= j0 + NB) ? Lp[i * LDP + t] : 0.0;
+#pragma unroll
+                for (int b = 0; b < RB; ++b) {
+                    const int k = tx + 16 * b;
+                    if (b > a || 16 * b + 15 < j0 + NB) continue;
+                    if (k >= j0 + NB && k <= i) {
+                        double acc = R[a][b];
+#pragma unroll
+                        for (int t = 0; t < NB; ++t) acc = fma(-lv[t], Up[k * LDP + t], acc);
+                        R[a][b] = acc;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
 }
 
-// L_IJ = T_IJ L_JJ^-T D_J^-1 : column sweep X[:,k] -= X[:,j] L[k][j] (X in registers), then scale column k by 1/D_k.
+// L_IJ = T_IJ L_JJ^-T D_J^-1, blocked: per panel the final columns X[:, P] = (X[:, P] raw) L11^-T (one thread per row), then
+// all threads apply X[:, >P] -= X[:, P] L[>P, P]'.  Finally column k is scaled by 1 / D_k.
 __global__ void __launch_bounds__(RED_THREADS) ldl_trsm_kernel(double* __restrict__ S, const int2* __restrict__ tasks) {
     extern __shared__ double sm[];
     double* L = sm;                  // L_JJ: L[k * LDT + j] (strict lower) with D on the diagonal
-    double* xc = sm + ST * LDT;      // [2][ST] published column of X
+    double* Xp = sm + ST * LDT;      // [ST][LDP] panel of X
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     const int2 tk = tasks[blockIdx.x];
     double* T = S + (size_t)tk.x * ST2;
@@ -114,26 +167,63 @@ __global__ void __launch_bounds__(RED_THREADS) ldl_trsm_kernel(double* __restric
             R[a][b] = (r < ST && c < ST) ? T[r + ST * c] : 0.0;
         }
     __syncthreads();
-    for (int j = 0; j < ST - 1; ++j) {
-        const int jb = j >> 4, jx = j & 15, buf = j & 1;
-        if (tx == jx) {
+    for (int j0 = 0; j0 < ST; j0 += NB) {
+        const int jb = j0 >> 4, jx0 = j0 & 15;
+        const bool owner = tx >= jx0 && tx < jx0 + NB;
+        if (owner) {
+            const int t = tx - jx0;
 #pragma unroll
             for (int b = 0; b < RB; ++b)
                 if (b == jb) {
 #pragma unroll
-                    for (int a = 0; a < RB; ++a) { const int r = ty + 16 * a; if (r < ST) xc[buf * ST + r] = R[a][b]; }
+                    for (int a = 0; a < RB; ++a) { const int r = ty + 16 * a; if (r < ST) Xp[r * LDP + t] = R[a][b]; }
                 }
         }
         __syncthreads();
-        double xr[RB], lk[RB];
+        if (tid < ST) {              // row tid: x_t = raw_t - sum_{q<t} x_q L[j0+t][j0+q]
+            double x[NB];
 #pragma unroll
-        for (int a = 0; a < RB; ++a) { const int r = ty + 16 * a; xr[a] = (r < ST) ? xc[buf * ST + r] : 0.0; }
+            for (int t = 0; t < NB; ++t) {
+                double v = Xp[tid * LDP + t];
 #pragma unroll
-        for (int b = 0; b < RB; ++b) { const int k = tx + 16 * b; lk[b] = (k < ST && k > j) ? L[k * LDT + j] : 0.0; }
+                for (int q = 0; q < t; ++q) v = fma(-x[q], L[(j0 + t) * LDT + j0 + q], v);
+                x[t] = v;
+            }
 #pragma unroll
-        for (int a = 0; a < RB; ++a)
+            for (int t = 0; t < NB; ++t) Xp[tid * LDP + t] = x[t];
+        }
+        __syncthreads();
+        if (owner) {                 // owners take the final panel values back
+            const int t = tx - jx0;
 #pragma unroll
-            for (int b = 0; b < RB; ++b) R[a][b] = fma(-xr[a], lk[b], R[a][b]);
+            for (int b = 0; b < RB; ++b)
+                if (b == jb) {
+#pragma unroll
+                    for (int a = 0; a < RB; ++a) { const int r = ty + 16 * a; if (r < ST) R[a][b] = Xp[r * LDP + t]; }
+                }
+        }
+        if (j0 + NB < ST) {          // X[:, k] -= sum_t X[:, j0+t] L[k][j0+t] for k >= j0 + NB
+#pragma unroll
+            for (int a = 0; a < RB; ++a) {
+                const int r = ty + 16 * a;
+                if (r >= ST) continue;
+                double xv[NB];
+#pragma unroll
+                for (int t = 0; t < NB; ++t) xv[t] = Xp[r * LDP + t];
+#pragma unroll
+                for (int b = 0; b < RB; ++b) {
+                    const int k = tx + 16 * b;
+                    if (16 * b + 15 < j0 + NB) continue;
+                    if (k >= j0 + NB && k < ST) {
+                        double acc = R[a][b];
+#pragma unroll
+                        for (int t = 0; t < NB; ++t) acc = fma(-xv[t], L[k * LDT + j0 + t], acc);
+                        R[a][b] = acc;
+                    }
+                }
+            }
+        }
+        __syncthreads();
     }
 #pragma unroll
     for (int a = 0; a < RB; ++a)
@@ -187,26 +277,86 @@ __global__ void __launch_bounds__(RED_THREADS) ldl_update_kernel(double* __restr
 }
 
 // Linv_J = L_JJ^-1 (unit lower triangular, explicit ones on the diagonal, zeros above) for every diagonal tile, in parallel
-// after the factorisation; turns the triangular sweeps of the solve into mat-vecs.
+// after the factorisation; turns the triangular sweeps of the solve into mat-vecs.  Blocked forward substitution of
+// L X = I by row panels: X[P, :] = L11^-1 X[P, :] (one thread per column), then X[>P, :] -= L[>P, P] X[P, :].
 __global__ void __launch_bounds__(RED_THREADS) ldl_inv_kernel(const double* __restrict__ S, const int* __restrict__ diag_tile, double* __restrict__ Linv) {
     extern __shared__ double sm[];
-    double* L = sm;
-    double* X = sm + ST * LDT;            // X[i * LDT + c]: column c of the inverse
-    const int tid = threadIdx.x, J = blockIdx.x;
+    double* L = sm;                       // L[i * LDT + j]
+    double* Xp = sm + ST * LDT;           // [NB][LDT] row panel of X
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4, J = blockIdx.x;
     const double* T = S + (size_t)diag_tile[J] * ST2;
     for (int e = tid; e < ST2; e += RED_THREADS) { const int r = e % ST, c = e / ST; L[r * LDT + c] = T[e]; }
+    double R[RB][RB];
+#pragma unroll
+    for (int a = 0; a < RB; ++a)
+#pragma unroll
+        for (int b = 0; b < RB; ++b) R[a][b] = (ty + 16 * a == tx + 16 * b) ? 1.0 : 0.0;
     __syncthreads();
-    if (tid < ST) {                       // column tid of the inverse: forward substitution of L x = e_tid
-        const int c = tid;
-        for (int i = 0; i < ST; ++i) {
-            double s = (i == c) ? 1.0 : 0.0;
-            for (int k = c; k < i; ++k) s = fma(-L[i * LDT + k], X[k * LDT + c], s);
-            X[i * LDT + c] = (i < c) ? 0.0 : s;
+    for (int j0 = 0; j0 < ST; j0 += NB) {
+        const int ja = j0 >> 4, jy0 = j0 & 15;
+        const bool owner = ty >= jy0 && ty < jy0 + NB;
+        if (owner) {
+            const int t = ty - jy0;
+#pragma unroll
+            for (int a = 0; a < RB; ++a)
+                if (a == ja) {
+#pragma unroll
+                    for (int b = 0; b < RB; ++b) { const int k = tx + 16 * b; if (k < ST) Xp[t * LDT + k] = R[a][b]; }
+                }
         }
+        __syncthreads();
+        if (tid < ST) {              // column tid: x_t = raw_t - sum_{q<t} L[j0+t][j0+q] x_q
+            double x[NB];
+#pragma unroll
+            for (int t = 0; t < NB; ++t) {
+                double v = Xp[t * LDT + tid];
+#pragma unroll
+                for (int q = 0; q < t; ++q) v = fma(-L[(j0 + t) * LDT + j0 + q], x[q], v);
+                x[t] = v;
+            }
+#pragma unroll
+            for (int t = 0; t < NB; ++t) Xp[t * LDT + tid] = x[t];
+        }
+        __syncthreads();
+        if (owner) {
+            const int t = ty - jy0;
+#pragma unroll
+            for (int a = 0; a < RB; ++a)
+                if (a == ja) {
+#pragma unroll
+                    for (int b = 0; b < RB; ++b) { const int k = tx + 16 * b; if (k < ST) R[a][b] = Xp[t * LDT + k]; }
+                }
+        }
+        if (j0 + NB < ST) {          // X[i, :] -= sum_t L[i][j0+t] X[j0+t, :] for i >= j0 + NB
+#pragma unroll
+            for (int a = 0; a < RB; ++a) {
+                const int i = ty + 16 * a;
+                if (16 * a + 15 < j0 + NB || i >= ST || i < j0 + NB) continue;
+                double lv[NB];
+#pragma unroll
+                for (int t = 0; t < NB; ++t) lv[t] = L[i * LDT + j0 + t];
+#pragma unroll
+                for (int b = 0; b < RB; ++b) {
+                    const int k = tx + 16 * b;
+                    if (k < ST) {
+                        double acc = R[a][b];
+#pragma unroll
+                        for (int t = 0; t < NB; ++t) acc = fma(-lv[t], Xp[t * LDT + k], acc);
+                        R[a][b] = acc;
+                    }
+                }
+            }
+        }
+        __syncthreads();
     }
-    __syncthreads();
     double* out = Linv + (size_t)J * ST2;
-    for (int e = tid; e < ST2; e += RED_THREADS) { const int r = e % ST, c = e / ST; out[e] = X[r * LDT + c]; }
+#pragma unroll
+    for (int a = 0; a < RB; ++a)
+#pragma unroll
+        for (int b = 0; b < RB; ++b) {
+            const int i = ty + 16 * a, k = tx + 16 * b;
+            if (i < ST && k < ST) out[i + ST * k] = R[a][b];
+        }
 }
 
 // ---------------------------------------------------------------------------------------------------
