@@ -25,6 +25,14 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 from __graft_entry__ import load_package  # noqa: E402
 
+_T0 = time.perf_counter()
+
+
+def _log(msg):
+    """phase timing on stderr (the JSON line on stdout stays alone)"""
+    print(f"[bench {time.perf_counter() - _T0:7.1f}s] {msg}", file=sys.stderr, flush=True)
+
+
 HUBER_WIDTH = 0.03
 NOISE, OUTLIERS = 0.01, 0.02
 PERTURB = 1e-3
@@ -158,7 +166,7 @@ def main():
     ap.add_argument("--workload", default="venice", choices=["venice", "ladybug", "final"])
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-iters", type=int, default=3)
+    ap.add_argument("--cpu-iters", type=int, default=2)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -177,7 +185,9 @@ def main():
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
+    _log("package loaded")
     p = make_problem(pkg, args.workload)
+    _log("problem generated")
     pts_sel, obs_sel = shard_by_point(p, rank, world)
     ctx = capi.Context(local_rank)
     if world > 1:
@@ -195,6 +205,7 @@ def main():
     ctx.set_costs(capi.RES_AFFINE_BA, aos, capi.ROBUST_HUBER, (HUBER_WIDTH,))
     ctx.prepare()
     t_setup = time.perf_counter() - t0
+    _log(f"context prepared ({t_setup:.2f}s)")
 
     opts = pkg.NLLSOptions(maxiters=10 ** 6, maxtime=1e5).c()
     ctx.lm_begin(opts)
@@ -225,6 +236,7 @@ def main():
         ms = float(t.item())
         dist.barrier()
     launches = ctx.kernel_launches() - launches0
+    _log("timed region done")
     ntries = sum(t[1] for t in trace[args.warmup:])
     value = p.nobs * args.steps / (ms * 1e-3)
 
@@ -248,6 +260,7 @@ def main():
                 "linearize_total": {"algorithmic_bytes": ctx.algorithmic_bytes(capi.TIME_LINEARIZE), "ms": kern["linearize"],
                                     "achieved": ctx.algorithmic_bytes(capi.TIME_LINEARIZE) / (kern["linearize"] * 1e-3) / 1e9}}
 
+    _log("kernel timing done")
     # ---- end to end through the C ABI with host buffers: every step uploads problem.variables from pinned host memory,
     # runs one LM iteration and reads the updated variables + cost back
     e2e = None
@@ -288,6 +301,7 @@ def main():
     except Exception as ex:  # pragma: no cover
         e2e = {"value": None, "error": repr(ex)}
 
+    _log("e2e done")
     line = {
         "metric": "residual blocks/s through full LM iterations", "value": value, "unit": "residual blocks/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
@@ -302,9 +316,11 @@ def main():
         line["cpu_baseline"] = cpu_baseline(p, args.cpu_iters)
     elif rank == 0:
         line["cpu_baseline"] = None
+    _log("cpu baseline done")
     if rank == 0:
         print(json.dumps(line), flush=True)
     ctx.close()
+    _log("context closed")
     if dist is not None:
         dist.destroy_process_group()
 

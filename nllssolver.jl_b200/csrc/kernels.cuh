@@ -199,6 +199,207 @@ __global__ void __launch_bounds__(LIN_THREADS) cost_kernel(DevProblem p, const d
 }
 
 // ---------------------------------------------------------------------------------------------------
+// K1p / K3p  persistent, software-pipelined versions of lin_point and cost (the default path).
+// The one-tile-per-CTA kernels above expose a chain of four dependent global loads (tile -> obs_start -> observation ->
+// camera) per CTA and hold their shared memory until the TMA engine has drained it; ncu showed them latency bound (32 %
+// warps active, long_scoreboard + barrier stalls, 35 % DRAM).  Here a CTA loops over tiles t = blockIdx.x + k gridDim.x:
+//   * one int4 descriptor per tile (pt0, npt, ob0, nob) replaces the tile_pt / obs_start chain;
+//   * the next tile's observation (cam, pt, z), CSR slice and then its camera / point values are loaded into registers while the
+//     current tile is computed and stored, so every global load has a full tile of work to hide behind;
+//   * the staged H span is double buffered: the bulk store of tile k drains while tile k+1 is computed;
+//   * the span is placed in shared memory at the parity of its global offset, so that EVERY tile goes out as one 16-byte
+//     aligned cp.async.bulk (plus at most one scalar head/tail element), and W blocks are staged with 128-bit shared stores
+//     (the 144-byte block stride makes 64-bit stores 2-way bank conflicted).
+// Arithmetic per observation, per-point summation order and the cost reduction tree are identical to K1/K3.
+// ---------------------------------------------------------------------------------------------------
+template <class R>
+struct Lin2Smem {
+    static constexpr int WB = 3 * R::DC;
+    static constexpr int OUT = WB * TILE_OBS + 9 * TILE_PTS + 2;   // staged H span + parity slot (even)
+    static constexpr int PC = 9 * TILE_OBS;                        // per-observation point contributions, SoA
+    static constexpr size_t bytes = (size_t)(2 * OUT + PC + 16) * sizeof(double);
+};
+
+template <class R>
+__global__ void __launch_bounds__(LIN_THREADS) lin_point2_kernel(DevProblem p, const int4* __restrict__ tiles, const double* __restrict__ cams,
+                                                                 const double* __restrict__ pts, double* __restrict__ cost_partials) {
+    constexpr int DC = R::DC, WB = 3 * DC, NP = (WB - 1) / 2;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* s_out0 = reinterpret_cast<double*>(smem_raw);
+    double* s_pc = s_out0 + 2 * Lin2Smem<R>::OUT;
+    double* s_red = s_pc + Lin2Smem<R>::PC;
+
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int G = gridDim.x;
+    int t = blockIdx.x;
+    if (t >= p.ntiles) return;
+    int4 d = tiles[t];
+    // pipeline registers of the current tile
+    int cam = 0, ptg = 0, ost_lo = 0, ost_hi = 0;
+    double2 z = make_double2(0.0, 0.0);
+    double cv[R::NC], X[3];
+    if (tid < d.w) { const int j = d.z + tid; cam = p.obs_cam[j]; ptg = p.obs_pt[j]; z = p.obs_z[j]; }
+    if (tid < d.y) { ost_lo = p.obs_start[d.x + tid] - d.z; ost_hi = p.obs_start[d.x + tid + 1] - d.z; }
+    R::load_cam(cams, cam, cv);
+    X[0] = __ldg(pts + (size_t)3 * ptg); X[1] = __ldg(pts + (size_t)3 * ptg + 1); X[2] = __ldg(pts + (size_t)3 * ptg + 2);
+
+    for (int it = 0;; ++it) {
+        const int tn = t + G;
+        const bool has_next = tn < p.ntiles;
+        int4 dn = make_int4(0, 0, 0, 0);
+        if (has_next) dn = tiles[tn];
+        const int pt0 = d.x, npt = d.y, ob0 = d.z, nob = d.w;
+        const size_t span0 = (size_t)p.hB + (size_t)WB * ob0 + (size_t)9 * pt0;
+        const int par = (int)(span0 & 1);
+        double* s_base = s_out0 + (it & 1) * Lin2Smem<R>::OUT + par;   // element e of the span lives at s_base[e]: same parity as H + span0 + e
+
+        double c = 0.0;
+        if (tid < nob) {
+            const int pl = ptg - pt0;
+            double r[2], Jc[2][DC], Jp[2][3];
+            R::resjac(cv, X, z.x, z.y, r, Jc, Jp);
+            const double s = r[0] * r[0] + r[1] * r[1];               // sqnorm            src/residual.jl:72
+            double rho, d1, d2;
+            robustifydcost(p.rk, s, rho, d1, d2);                     //                   src/residual.jl:78
+            c = 0.5 * rho;                                            //                   src/residual.jl:110
+            double gc[DC], gp[3];
+#pragma unroll
+            for (int a = 0; a < DC; ++a) gc[a] = Jc[0][a] * r[0] + Jc[1][a] * r[1];   // g = J' r   :73
+#pragma unroll
+            for (int b = 0; b < 3; ++b) gp[b] = Jp[0][b] * r[0] + Jp[1][b] * r[1];
+            const double td2 = 2 * d2;
+            double w[WB];                                             // W block, column-major 3 x DC   src/linearsystem.jl:149
+#pragma unroll
+            for (int a = 0; a < DC; ++a)
+#pragma unroll
+                for (int b = 0; b < 3; ++b) {
+                    double h = Jp[0][b] * Jc[0][a] + Jp[1][b] * Jc[1][a];             // H = J' J   :74
+                    if (d1 != 1.0) h *= d1;                                            // IRLS       :91-93
+                    if (d2 != 0.0) h += (td2 * gp[b]) * gc[a];                         // Triggs     :95-97
+                    w[b + 3 * a] = h;
+                }
+            // 128-bit shared stores at the block's own parity
+            const int off = WB * tid + 9 * pl;
+            double* wd = s_base + off;
+            const bool odd = ((par + off) & 1) != 0;
+            double2* wd2 = reinterpret_cast<double2*>(wd + (odd ? 1 : 0));
+#pragma unroll
+            for (int k = 0; k < NP; ++k) wd2[k] = make_double2(odd ? w[2 * k + 1] : w[2 * k], odd ? w[2 * k + 2] : w[2 * k + 1]);
+            if (odd) wd[0] = w[0];
+#pragma unroll
+            for (int e = 2 * NP; e < WB; ++e) if (e >= 2 * NP + (odd ? 1 : 0)) wd[e] = w[e];
+            // this observation's contribution to V_p (lower triangle) and g_p
+            int q = 0;
+#pragma unroll
+            for (int b2 = 0; b2 < 3; ++b2)
+#pragma unroll
+                for (int b = b2; b < 3; ++b) {
+                    double h = Jp[0][b] * Jp[0][b2] + Jp[1][b] * Jp[1][b2];
+                    if (d1 != 1.0) h *= d1;
+                    if (d2 != 0.0) h += (td2 * gp[b]) * gp[b2];
+                    s_pc[(q++) * TILE_OBS + tid] = h;
+                }
+#pragma unroll
+            for (int b = 0; b < 3; ++b) s_pc[(6 + b) * TILE_OBS + tid] = (d1 != 1.0) ? gp[b] * d1 : gp[b];  // g *= dc  :99-101
+        }
+        // level-1 prefetch of the next tile
+        int ncam = 0, nptg = 0, nlo = 0, nhi = 0;
+        double2 nz = make_double2(0.0, 0.0);
+        if (tid < dn.w) { const int j = dn.z + tid; ncam = p.obs_cam[j]; nptg = p.obs_pt[j]; nz = p.obs_z[j]; }
+        if (tid < dn.y) { nlo = p.obs_start[dn.x + tid] - dn.z; nhi = p.obs_start[dn.x + tid + 1] - dn.z; }
+        __syncthreads();
+
+        if (tid < npt) {  // sequential per-point accumulation:  block(A, p, p) += ..., b[p] += ...   :140,166
+            double v[9];
+#pragma unroll
+            for (int i = 0; i < 9; ++i) v[i] = 0.0;
+            for (int j = ost_lo; j < ost_hi; ++j) {
+#pragma unroll
+                for (int i = 0; i < 9; ++i) v[i] += s_pc[i * TILE_OBS + j];
+            }
+            double* V = s_base + WB * ost_hi + 9 * tid;
+            V[0] = v[0]; V[1] = v[1]; V[2] = v[2];
+            V[3] = v[1]; V[4] = v[3]; V[5] = v[4];
+            V[6] = v[2]; V[7] = v[4]; V[8] = v[5];
+            double* gp = p.g + p.gB + (size_t)3 * (pt0 + tid);
+            gp[0] = v[6]; gp[1] = v[7]; gp[2] = v[8];
+        }
+        // cost of the tile: the reduction tree of block_sum
+        c = warp_sum(c);
+        if (lane == 0) s_red[(it & 1) * 8 + wid] = c;
+        // level-2 prefetch (addresses from the level-1 registers)
+        double ncv[R::NC], nX[3];
+        R::load_cam(cams, ncam, ncv);
+        nX[0] = __ldg(pts + (size_t)3 * nptg); nX[1] = __ldg(pts + (size_t)3 * nptg + 1); nX[2] = __ldg(pts + (size_t)3 * nptg + 2);
+        if (tid == 0) bulk_store_wait();     // the previous tile's store has drained: the other stage is free again
+        fence_proxy_async();
+        __syncthreads();
+
+        if (tid == 0) {
+            double tsum = 0.0;
+#pragma unroll
+            for (int i = 0; i < LIN_THREADS / 32; ++i) tsum += s_red[(it & 1) * 8 + i];
+            cost_partials[t] = tsum;
+            const int span = WB * nob + 9 * npt;
+            double* gdst = p.H + span0;
+            const int body = (span - par) & ~1;
+            if (par && span > 0) gdst[0] = s_base[0];
+            if (body > 0) bulk_store(gdst + par, s_base + par, (uint32_t)body * 8u);
+            if (par + body < span) gdst[span - 1] = s_base[span - 1];
+        }
+        if (!has_next) break;
+        t = tn; d = dn; cam = ncam; ptg = nptg; z = nz; ost_lo = nlo; ost_hi = nhi;
+#pragma unroll
+        for (int i = 0; i < R::NC; ++i) cv[i] = ncv[i];
+        X[0] = nX[0]; X[1] = nX[1]; X[2] = nX[2];
+    }
+    if (tid == 0) bulk_store_wait();
+}
+
+template <class R>
+__global__ void __launch_bounds__(LIN_THREADS) cost2_kernel(DevProblem p, const int4* __restrict__ tiles, const double* __restrict__ cams,
+                                                            const double* __restrict__ pts, double* __restrict__ cost_partials) {
+    __shared__ double s_red[16];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int G = gridDim.x;
+    int t = blockIdx.x;
+    if (t >= p.ntiles) return;
+    int4 d = tiles[t];
+    int cam = 0, ptg = 0;
+    double2 z = make_double2(0.0, 0.0);
+    if (tid < d.w) { const int j = d.z + tid; cam = p.obs_cam[j]; ptg = p.obs_pt[j]; z = p.obs_z[j]; }
+    for (int it = 0;; ++it) {
+        const int tn = t + G;
+        const bool has_next = tn < p.ntiles;
+        int4 dn = make_int4(0, 0, 0, 0);
+        if (has_next) dn = tiles[tn];
+        double cv[R::NC];
+        R::load_cam(cams, cam, cv);
+        const double X[3] = {__ldg(pts + (size_t)3 * ptg), __ldg(pts + (size_t)3 * ptg + 1), __ldg(pts + (size_t)3 * ptg + 2)};
+        int ncam = 0, nptg = 0;
+        double2 nz = make_double2(0.0, 0.0);
+        if (tid < dn.w) { const int j = dn.z + tid; ncam = p.obs_cam[j]; nptg = p.obs_pt[j]; nz = p.obs_z[j]; }
+        double c = 0.0;
+        if (tid < d.w) {
+            double r[2];
+            R::residual(cv, X, z.x, z.y, r);
+            c = 0.5 * robustify(p.rk, r[0] * r[0] + r[1] * r[1]);
+        }
+        c = warp_sum(c);
+        if (lane == 0) s_red[(it & 1) * 8 + wid] = c;
+        __syncthreads();
+        if (tid == 0) {
+            double tsum = 0.0;
+#pragma unroll
+            for (int i = 0; i < LIN_THREADS / 32; ++i) tsum += s_red[(it & 1) * 8 + i];
+            cost_partials[t] = tsum;
+        }
+        if (!has_next) break;
+        t = tn; d = dn; cam = ncam; ptg = nptg; z = nz;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // K2  lin_cam: camera diagonal blocks U_c = sum J_c' W J_c and g_c over the camera-major observation copy.
 // One CTA per work item (a camera and at most CAM_CHUNK of its observations); fixed-shape reduction.
 // ---------------------------------------------------------------------------------------------------

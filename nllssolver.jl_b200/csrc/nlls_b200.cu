@@ -118,6 +118,9 @@ struct nlls_ctx {
     int* d_info = nullptr;
     int* d_ipiv = nullptr;
     int use_tma = 1;
+    int lin_v2 = 1;                 // persistent pipelined linearisation / cost kernels (NLLS_B200_LIN=v1 selects the one-tile-per-CTA ones)
+    int4* d_tiles = nullptr;        // (pt0, npt, ob0, nob) per point tile
+    int nsm = 148, lin_grid = 0, cost_grid = 0;
     int schur_stride = 296;
     // reduced camera system (tile-sparse level-scheduled LDL' by default; NLLS_B200_REDUCED=dense selects dense storage + cuSOLVER)
     int s_tiled = 1;
@@ -249,6 +252,16 @@ int upload_vars(nlls_ctx* ctx, const VarSet& vs, int dstride, double* dst) {
 template <class R>
 int set_smem_attrs(nlls_ctx* ctx) {
     CK(cudaFuncSetAttribute(lin_point_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LinSmem<R>::bytes));
+    CK(cudaFuncSetAttribute(lin_point2_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Lin2Smem<R>::bytes));
+    {
+        int occ = 1;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, lin_point2_kernel<R>, LIN_THREADS, Lin2Smem<R>::bytes));
+        ctx->lin_grid = std::max(1, std::min(ctx->ntiles, ctx->nsm * std::max(1, occ)));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, cost2_kernel<R>, LIN_THREADS, 0));
+        ctx->cost_grid = std::max(1, std::min(ctx->ntiles, ctx->nsm * std::max(1, std::min(occ, 4))));
+        if (const char* g = getenv("NLLS_B200_LIN_GRID")) ctx->lin_grid = std::max(1, std::min(ctx->ntiles, atoi(g)));
+        if (const char* g = getenv("NLLS_B200_COST_GRID")) ctx->cost_grid = std::max(1, std::min(ctx->ntiles, atoi(g)));
+    }
     CK(cudaFuncSetAttribute(schur_tile_kernel<R::DC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SchurSmem<R::DC>::bytes));
     CK(cudaFuncSetAttribute(backsub_tile_kernel<R::DC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SchurSmem<R::DC>::bytes));
     CK(cudaFuncSetAttribute(schur2_kernel<R::DC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Schur2Smem<R::DC>::bytes));
@@ -278,7 +291,10 @@ int launch_linearize(nlls_ctx* ctx, bool do_point = true, bool do_cam = true) {
         CK(cudaEventRecord(ctx->ev_join, ctx->st2));
     }
     if (do_point && ctx->ntiles > 0) {
-        lin_point_kernel<R><<<ctx->ntiles, LIN_THREADS, LinSmem<R>::bytes, ctx->st>>>(p, ctx->d_A[ctx->cur], ctx->d_B[ctx->cur], ctx->d_cost_part);
+        if (ctx->lin_v2)
+            lin_point2_kernel<R><<<ctx->lin_grid, LIN_THREADS, Lin2Smem<R>::bytes, ctx->st>>>(p, ctx->d_tiles, ctx->d_A[ctx->cur], ctx->d_B[ctx->cur], ctx->d_cost_part);
+        else
+            lin_point_kernel<R><<<ctx->ntiles, LIN_THREADS, LinSmem<R>::bytes, ctx->st>>>(p, ctx->d_A[ctx->cur], ctx->d_B[ctx->cur], ctx->d_cost_part);
         ctx->launches++;
     }
     if (do_cam) CK(cudaStreamWaitEvent(ctx->st, ctx->ev_join, 0));
@@ -289,7 +305,11 @@ int launch_linearize(nlls_ctx* ctx, bool do_point = true, bool do_cam = true) {
 template <class R>
 int launch_cost(nlls_ctx* ctx, int which, int slot) {
     DevProblem p = devproblem(ctx);
-    if (ctx->ntiles > 0) { cost_kernel<R><<<ctx->ntiles, LIN_THREADS, 0, ctx->st>>>(p, ctx->d_A[which], ctx->d_B[which], ctx->d_cost_part); ctx->launches++; }
+    if (ctx->ntiles > 0) {
+        if (ctx->lin_v2) cost2_kernel<R><<<ctx->cost_grid, LIN_THREADS, 0, ctx->st>>>(p, ctx->d_tiles, ctx->d_A[which], ctx->d_B[which], ctx->d_cost_part);
+        else cost_kernel<R><<<ctx->ntiles, LIN_THREADS, 0, ctx->st>>>(p, ctx->d_A[which], ctx->d_B[which], ctx->d_cost_part);
+        ctx->launches++;
+    }
     reduce_partials_kernel<<<1, 1024, 0, ctx->st>>>(ctx->d_cost_part, ctx->ntiles, ctx->d_scal + slot, 0); ctx->launches++;
     CK(cudaGetLastError());
     TRY(allreduce(ctx, ctx->d_scal + slot, 1, ncclSum));
@@ -501,6 +521,8 @@ int nlls_create(nlls_ctx** out, int device) {
     if (const char* g = getenv("NLLS_B200_SCHUR_STRIDE")) ctx->schur_stride = std::max(1, atoi(g));
     if (const char* g = getenv("NLLS_B200_REDUCED")) ctx->s_tiled = (std::string(g) == "dense") ? 0 : 1;
     if (const char* g = getenv("NLLS_B200_SCHUR")) ctx->schur_v2 = (std::string(g) == "v1") ? 0 : 1;
+    if (const char* g = getenv("NLLS_B200_LIN")) ctx->lin_v2 = (std::string(g) == "v1") ? 0 : 1;
+    { int v = 0; if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && v > 0) ctx->nsm = v; }
     if (cudaGetLastError() != cudaSuccess) { delete ctx; return NLLS_ERR_CUDA; }
     *out = ctx;
     return NLLS_OK;
@@ -515,7 +537,7 @@ int nlls_destroy(nlls_ctx* ctx) {
                     ctx->d_H, ctx->d_g, ctx->d_x, ctx->d_Ainv, ctx->d_S, ctx->d_rhs, ctx->d_cost_part, ctx->d_step_part, ctx->d_cam_part, ctx->d_scal,
                     ctx->d_flush, ctx->d_work, ctx->d_info, ctx->d_ipiv, ctx->d_tile_id, ctx->d_pos, ctx->d_diag_tile, ctx->d_diag_tile_nat,
                     ctx->d_diag_tasks, ctx->d_lvl_cols, ctx->d_trsm_tasks, ctx->d_upd_tasks, ctx->d_rowptr, ctx->d_row_tile, ctx->d_row_col, ctx->d_colptr,
-                    ctx->d_col_tile, ctx->d_col_row, ctx->d_Linv, ctx->d_xp, ctx->d_stile_pt, ctx->d_chunk_off, ctx->d_chunks, ctx->d_ents};
+                    ctx->d_col_tile, ctx->d_col_row, ctx->d_Linv, ctx->d_xp, ctx->d_stile_pt, ctx->d_chunk_off, ctx->d_chunks, ctx->d_ents, ctx->d_tiles};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (ctx->h_scal) cudaFreeHost(ctx->h_scal);
     if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
@@ -946,6 +968,14 @@ int nlls_prepare(nlls_ctx* ctx) {
 
     TRY(upload(ctx, &ctx->d_obs_cam, ctx->h_obs_cam)); TRY(upload(ctx, &ctx->d_obs_pt, ctx->h_obs_pt)); TRY(upload(ctx, &ctx->d_obs_z, obs_z));
     TRY(upload(ctx, &ctx->d_obs_start, ctx->h_obs_start)); TRY(upload(ctx, &ctx->d_tile_pt, ctx->h_tile_pt));
+    {
+        std::vector<int4> tiles((size_t)ctx->ntiles);
+        for (int t = 0; t < ctx->ntiles; ++t) {
+            const int a = ctx->h_tile_pt[(size_t)t], b = ctx->h_tile_pt[(size_t)t + 1];
+            tiles[(size_t)t] = make_int4(a, b - a, ctx->h_obs_start[(size_t)a], ctx->h_obs_start[(size_t)b] - ctx->h_obs_start[(size_t)a]);
+        }
+        TRY(upload(ctx, &ctx->d_tiles, tiles));
+    }
     TRY(upload(ctx, &ctx->d_cm_pt, cm_pt)); TRY(upload(ctx, &ctx->d_cm_z, cm_z));
     TRY(upload(ctx, &ctx->d_item_cam, item_cam)); TRY(upload(ctx, &ctx->d_item_beg, item_beg)); TRY(upload(ctx, &ctx->d_item_end, item_end));
     TRY(upload(ctx, &ctx->d_cam_item_start, cam_item_start));
