@@ -46,212 +46,68 @@ struct DevProblem {
     int s_tiled;
 };
 
-template <class R>
-struct LinSmem {
-    static constexpr int WB = 3 * R::DC;
-    static constexpr int OUT = WB * TILE_OBS + 9 * TILE_PTS;  // staged H span (doubles)
-    static constexpr int PC = 9 * TILE_OBS;                   // per-observation point contributions (6 V + 3 g)
-    static constexpr int XS = 3 * TILE_PTS;
-    static constexpr size_t bytes = (size_t)(OUT + PC + XS + 3 * TILE_PTS + 8) * sizeof(double) + (TILE_PTS + 4) * sizeof(int);
-};
-
 // ---------------------------------------------------------------------------------------------------
-// K1  lin_point: fused residual + analytic Jacobian + robust weights + J'WJ for one tile of points.
+// K1  lin_point: fused residual + analytic Jacobian + robust weights + J'WJ for tiles of points (persistent, pipelined).
 // Replaces costgradhess! (src/cost.jl:29-52) -> computerescostgradhess (src/residual.jl:57-111) ->
 // updatesymlinearsystem! (src/linearsystem.jl:132-175) for the point rows of H (W and V blocks) and g_p.
-// One thread per observation; per-point sums run sequentially in observation order (deterministic, and the
-// same order as the reference when costs are stored camera-major).  The tile's H span is staged in shared
-// memory and written with one TMA bulk store.
-// ---------------------------------------------------------------------------------------------------
-template <class R>
-__global__ void __launch_bounds__(LIN_THREADS) lin_point_kernel(DevProblem p, const double* __restrict__ cams,
-                                                                const double* __restrict__ pts, double* __restrict__ cost_partials) {
-    constexpr int DC = R::DC, WB = 3 * DC;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    double* s_out = reinterpret_cast<double*>(smem_raw);
-    double* s_pc = s_out + LinSmem<R>::OUT;
-    double* s_X = s_pc + LinSmem<R>::PC;
-    double* s_gp = s_X + LinSmem<R>::XS;
-    double* s_red = s_gp + 3 * TILE_PTS;
-    int* s_ost = reinterpret_cast<int*>(s_red + 8);
-
-    const int tid = threadIdx.x;
-    const int t = blockIdx.x;
-    const int pt0 = p.tile_pt[t], pt1 = p.tile_pt[t + 1];
-    const int ob0 = p.obs_start[pt0], ob1 = p.obs_start[pt1];
-    const int npt = pt1 - pt0, nob = ob1 - ob0;
-
-    for (int i = tid; i < 3 * npt; i += LIN_THREADS) s_X[i] = pts[(size_t)3 * pt0 + i];
-    for (int i = tid; i <= npt; i += LIN_THREADS) s_ost[i] = p.obs_start[pt0 + i] - ob0;
-    __syncthreads();
-
-    double c = 0.0;
-    if (tid < nob) {
-        const int j = ob0 + tid;
-        const int cam = p.obs_cam[j];
-        const int pl = p.obs_pt[j] - pt0;
-        const double2 z = p.obs_z[j];
-        double cv[R::NC];
-        R::load_cam(cams, cam, cv);
-        const double X[3] = {s_X[3 * pl], s_X[3 * pl + 1], s_X[3 * pl + 2]};
-        double r[2], Jc[2][DC], Jp[2][3];
-        R::resjac(cv, X, z.x, z.y, r, Jc, Jp);
-        const double s = r[0] * r[0] + r[1] * r[1];               // sqnorm            src/residual.jl:72
-        double rho, d1, d2;
-        robustifydcost(p.rk, s, rho, d1, d2);                     //                   src/residual.jl:78
-        c = 0.5 * rho;                                            //                   src/residual.jl:110
-        double gc[DC], gp[3];
-#pragma unroll
-        for (int a = 0; a < DC; ++a) gc[a] = Jc[0][a] * r[0] + Jc[1][a] * r[1];   // g = J' r   :73
-#pragma unroll
-        for (int b = 0; b < 3; ++b) gp[b] = Jp[0][b] * r[0] + Jp[1][b] * r[1];
-        const double td2 = 2 * d2;
-        // W block (point row, camera column), column-major 3 x DC                     src/linearsystem.jl:149
-        double* w = s_out + WB * tid + 9 * pl;
-#pragma unroll
-        for (int a = 0; a < DC; ++a)
-#pragma unroll
-            for (int b = 0; b < 3; ++b) {
-                double h = Jp[0][b] * Jc[0][a] + Jp[1][b] * Jc[1][a];             // H = J' J   :74
-                if (d1 != 1.0) h *= d1;                                            // IRLS       :91-93
-                if (d2 != 0.0) h += (td2 * gp[b]) * gc[a];                         // Triggs     :95-97
-                w[b + 3 * a] = h;
-            }
-        // this observation's contribution to V_p (lower triangle) and g_p
-        double* pc = s_pc + 9 * tid;
-        int q = 0;
-#pragma unroll
-        for (int b2 = 0; b2 < 3; ++b2)
-#pragma unroll
-            for (int b = b2; b < 3; ++b) {
-                double h = Jp[0][b] * Jp[0][b2] + Jp[1][b] * Jp[1][b2];
-                if (d1 != 1.0) h *= d1;
-                if (d2 != 0.0) h += (td2 * gp[b]) * gp[b2];
-                pc[q++] = h;
-            }
-#pragma unroll
-        for (int b = 0; b < 3; ++b) pc[6 + b] = (d1 != 1.0) ? gp[b] * d1 : gp[b];  // g *= dc  :99-101
-    }
-    __syncthreads();
-
-    if (tid < npt) {  // sequential per-point accumulation:  block(A, p, p) += ..., b[p] += ...   :140,166
-        double v[9];
-#pragma unroll
-        for (int i = 0; i < 9; ++i) v[i] = 0.0;
-        for (int j = s_ost[tid]; j < s_ost[tid + 1]; ++j) {
-#pragma unroll
-            for (int i = 0; i < 9; ++i) v[i] += s_pc[9 * j + i];
-        }
-        double* V = s_out + WB * s_ost[tid + 1] + 9 * tid;
-        V[0] = v[0]; V[1] = v[1]; V[2] = v[2];
-        V[3] = v[1]; V[4] = v[3]; V[5] = v[4];
-        V[6] = v[2]; V[7] = v[4]; V[8] = v[5];
-        s_gp[3 * tid] = v[6]; s_gp[3 * tid + 1] = v[7]; s_gp[3 * tid + 2] = v[8];
-    }
-    // cost of the tile (fixed reduction tree; the cost kernel uses the same one)
-    const double csum = block_sum(c, s_red);   // contains a __syncthreads after the s_out / s_gp writes of this warp's lanes
-    if (tid == 0) cost_partials[t] = csum;
-    if (p.use_tma) fence_proxy_async();
-    __syncthreads();
-
-    // write back: g_p (coalesced) and the H span (one contiguous range)
-    for (int i = tid; i < 3 * npt; i += LIN_THREADS) p.g[p.gB + (size_t)3 * pt0 + i] = s_gp[i];
-    const size_t span0 = (size_t)p.hB + (size_t)WB * ob0 + (size_t)9 * pt0;
-    const int span = WB * nob + 9 * npt;
-    double* gdst = p.H + span0;
-    const bool aligned = ((reinterpret_cast<uintptr_t>(gdst) & 15) == 0) && ((span & 1) == 0);
-    if (p.use_tma && aligned) {
-        if (tid == 0 && span > 0) {
-            bulk_store(gdst, s_out, (uint32_t)span * 8u);
-            bulk_store_wait();
-        }
-    } else {
-        for (int i = tid; i < span; i += LIN_THREADS) gdst[i] = s_out[i];
-    }
-}
-
-// ---------------------------------------------------------------------------------------------------
-// K3  cost: sum 0.5 rho(|r|^2) with the same tiling and reduction tree as K1.
-// Replaces cost(vars, costs) (src/cost.jl:11) -> computerescost (src/residual.jl:49-55).
-// ---------------------------------------------------------------------------------------------------
-template <class R>
-__global__ void __launch_bounds__(LIN_THREADS) cost_kernel(DevProblem p, const double* __restrict__ cams, const double* __restrict__ pts,
-                                                           double* __restrict__ cost_partials) {
-    __shared__ double s_red[8];
-    const int tid = threadIdx.x, t = blockIdx.x;
-    const int pt0 = p.tile_pt[t], pt1 = p.tile_pt[t + 1];
-    const int ob0 = p.obs_start[pt0], ob1 = p.obs_start[pt1];
-    double c = 0.0;
-    if (tid < ob1 - ob0) {
-        const int j = ob0 + tid;
-        const int cam = p.obs_cam[j];
-        const int pt = p.obs_pt[j];
-        const double2 z = p.obs_z[j];
-        double cv[R::NC];
-        R::load_cam(cams, cam, cv);
-        const double X[3] = {pts[(size_t)3 * pt], pts[(size_t)3 * pt + 1], pts[(size_t)3 * pt + 2]};
-        double r[2];
-        R::residual(cv, X, z.x, z.y, r);
-        c = 0.5 * robustify(p.rk, r[0] * r[0] + r[1] * r[1]);
-    }
-    const double csum = block_sum(c, s_red);
-    if (tid == 0) cost_partials[t] = csum;
-}
-
-// ---------------------------------------------------------------------------------------------------
-// K1p / K3p  persistent, software-pipelined versions of lin_point and cost (the default path).
-// The one-tile-per-CTA kernels above expose a chain of four dependent global loads (tile -> obs_start -> observation ->
-// camera) per CTA and hold their shared memory until the TMA engine has drained it; ncu showed them latency bound (32 %
-// warps active, long_scoreboard + barrier stalls, 35 % DRAM).  Here a CTA loops over tiles t = blockIdx.x + k gridDim.x:
-//   * one int4 descriptor per tile (pt0, npt, ob0, nob) replaces the tile_pt / obs_start chain;
-//   * the next tile's observation (cam, pt, z), CSR slice and then its camera / point values are loaded into registers while the
-//     current tile is computed and stored, so every global load has a full tile of work to hide behind;
+//
+// A CTA loops over tiles t = blockIdx.x + k gridDim.x (one thread per observation of the tile):
+//   * one int4 descriptor per tile (pt0, npt, ob0, nob) replaces the tile -> obs_start chain;
+//   * register pipeline, three tiles deep: the observation (cam, pt, z) and CSR slice of tile k+2 and the camera / point
+//     values of tile k+1 are in flight while tile k is computed, so no global load is waited for where it is issued
+//     (the one-tile-per-CTA v0 kernel was latency bound on exactly that chain: ncu long_scoreboard + barrier, 35 % DRAM);
 //   * the staged H span is double buffered: the bulk store of tile k drains while tile k+1 is computed;
-//   * the span is placed in shared memory at the parity of its global offset, so that EVERY tile goes out as one 16-byte
-//     aligned cp.async.bulk (plus at most one scalar head/tail element), and W blocks are staged with 128-bit shared stores
-//     (the 144-byte block stride makes 64-bit stores 2-way bank conflicted).
-// Arithmetic per observation, per-point summation order and the cost reduction tree are identical to K1/K3.
+//   * the span sits in shared memory at the parity of its global offset, so EVERY tile goes out as one 16-byte aligned
+//     cp.async.bulk (SASS UBLKCP) plus at most one scalar head/tail element; W blocks are staged with 128-bit stores;
+//   * per-point sums (V_p, g_p) run over (point, element) items in parallel, each in observation order (deterministic, and
+//     the reference's order when costs are stored camera-major).
 // ---------------------------------------------------------------------------------------------------
-template <class R>
-struct Lin2Smem {
+template <class R, int TO, int TP>
+struct LinSmem {
     static constexpr int WB = 3 * R::DC;
-    static constexpr int OUT = WB * TILE_OBS + 9 * TILE_PTS + 2;   // staged H span + parity slot (even)
-    static constexpr int PC = 9 * TILE_OBS;                        // per-observation point contributions, SoA
-    static constexpr size_t bytes = (size_t)(2 * OUT + PC + 16) * sizeof(double);
+    static constexpr int OUT = WB * TO + 9 * TP + 2;     // staged H span + parity slot (even)
+    static constexpr int PC = 9 * TO;                    // per-observation point contributions (6 V + 3 g), SoA
+    static constexpr size_t bytes = (size_t)(2 * OUT + PC + 16) * sizeof(double) + (size_t)(TP + 4) * sizeof(int);
 };
 
-template <class R>
-__global__ void __launch_bounds__(LIN_THREADS) lin_point2_kernel(DevProblem p, const int4* __restrict__ tiles, const double* __restrict__ cams,
-                                                                 const double* __restrict__ pts, double* __restrict__ cost_partials) {
-    constexpr int DC = R::DC, WB = 3 * DC, NP = (WB - 1) / 2;
+template <class R, int TO, int TP>
+__global__ void __launch_bounds__(TO) lin_point_kernel(DevProblem p, const int4* __restrict__ tiles, const double* __restrict__ cams,
+                                                       const double* __restrict__ pts, double* __restrict__ cost_partials) {
+    constexpr int DC = R::DC, WB = 3 * DC, NP = (WB - 1) / 2, NW = TO / 32;
+    using SM = LinSmem<R, TO, TP>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* s_out0 = reinterpret_cast<double*>(smem_raw);
-    double* s_pc = s_out0 + 2 * Lin2Smem<R>::OUT;
-    double* s_red = s_pc + Lin2Smem<R>::PC;
+    double* s_pc = s_out0 + 2 * SM::OUT;
+    double* s_red = s_pc + SM::PC;
+    int* s_ost = reinterpret_cast<int*>(s_red + 16);
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int G = gridDim.x;
     int t = blockIdx.x;
     if (t >= p.ntiles) return;
+    // pipeline registers: tile k (level 2 complete), tile k+1 (level 1), tile k+2 (being loaded), descriptor of tile k+3.
+    // Every prefetch is an unconditional load from a clamped (always valid) address straight into its register: a predicated
+    // load or arithmetic on the loaded value would make the warp wait for it right where it is issued.
+    const int last = p.ntiles - 1;
     int4 d = tiles[t];
-    // pipeline registers of the current tile
-    int cam = 0, ptg = 0, ost_lo = 0, ost_hi = 0;
-    double2 z = make_double2(0.0, 0.0);
+    int4 dn = tiles[min(t + G, last)];
+    int4 dn2 = tiles[min(t + 2 * G, last)];
+    int cam, ptg, lo, ncam, nptg, nlo;
+    double2 z, nz;
+    { const int j = d.z + min(tid, max(d.w - 1, 0)); cam = p.obs_cam[j]; ptg = p.obs_pt[j]; z = p.obs_z[j]; lo = p.obs_start[d.x + min(tid, d.y)]; }
+    { const int j = dn.z + min(tid, max(dn.w - 1, 0)); ncam = p.obs_cam[j]; nptg = p.obs_pt[j]; nz = p.obs_z[j]; nlo = p.obs_start[dn.x + min(tid, dn.y)]; }
     double cv[R::NC], X[3];
-    if (tid < d.w) { const int j = d.z + tid; cam = p.obs_cam[j]; ptg = p.obs_pt[j]; z = p.obs_z[j]; }
-    if (tid < d.y) { ost_lo = p.obs_start[d.x + tid] - d.z; ost_hi = p.obs_start[d.x + tid + 1] - d.z; }
     R::load_cam(cams, cam, cv);
     X[0] = __ldg(pts + (size_t)3 * ptg); X[1] = __ldg(pts + (size_t)3 * ptg + 1); X[2] = __ldg(pts + (size_t)3 * ptg + 2);
 
     for (int it = 0;; ++it) {
-        const int tn = t + G;
-        const bool has_next = tn < p.ntiles;
-        int4 dn = make_int4(0, 0, 0, 0);
-        if (has_next) dn = tiles[tn];
+        const bool has_next = t + G < p.ntiles;
+        const int4 dn3 = tiles[min(t + 3 * G, last)];
         const int pt0 = d.x, npt = d.y, ob0 = d.z, nob = d.w;
         const size_t span0 = (size_t)p.hB + (size_t)WB * ob0 + (size_t)9 * pt0;
         const int par = (int)(span0 & 1);
-        double* s_base = s_out0 + (it & 1) * Lin2Smem<R>::OUT + par;   // element e of the span lives at s_base[e]: same parity as H + span0 + e
+        double* s_base = s_out0 + (it & 1) * SM::OUT + par;   // element e of the span lives at s_base[e]: same parity as H + span0 + e
+        if (tid <= npt) s_ost[tid] = lo - ob0;
 
         double c = 0.0;
         if (tid < nob) {
@@ -297,88 +153,111 @@ __global__ void __launch_bounds__(LIN_THREADS) lin_point2_kernel(DevProblem p, c
                     double h = Jp[0][b] * Jp[0][b2] + Jp[1][b] * Jp[1][b2];
                     if (d1 != 1.0) h *= d1;
                     if (d2 != 0.0) h += (td2 * gp[b]) * gp[b2];
-                    s_pc[(q++) * TILE_OBS + tid] = h;
+                    s_pc[9 * tid + (q++)] = h;
                 }
 #pragma unroll
-            for (int b = 0; b < 3; ++b) s_pc[(6 + b) * TILE_OBS + tid] = (d1 != 1.0) ? gp[b] * d1 : gp[b];  // g *= dc  :99-101
+            for (int b = 0; b < 3; ++b) s_pc[9 * tid + 6 + b] = (d1 != 1.0) ? gp[b] * d1 : gp[b];  // g *= dc  :99-101
         }
-        // level-1 prefetch of the next tile
-        int ncam = 0, nptg = 0, nlo = 0, nhi = 0;
-        double2 nz = make_double2(0.0, 0.0);
-        if (tid < dn.w) { const int j = dn.z + tid; ncam = p.obs_cam[j]; nptg = p.obs_pt[j]; nz = p.obs_z[j]; }
-        if (tid < dn.y) { nlo = p.obs_start[dn.x + tid] - dn.z; nhi = p.obs_start[dn.x + tid + 1] - dn.z; }
-        __syncthreads();
-
-        if (tid < npt) {  // sequential per-point accumulation:  block(A, p, p) += ..., b[p] += ...   :140,166
-            double v[9];
-#pragma unroll
-            for (int i = 0; i < 9; ++i) v[i] = 0.0;
-            for (int j = ost_lo; j < ost_hi; ++j) {
-#pragma unroll
-                for (int i = 0; i < 9; ++i) v[i] += s_pc[i * TILE_OBS + j];
-            }
-            double* V = s_base + WB * ost_hi + 9 * tid;
-            V[0] = v[0]; V[1] = v[1]; V[2] = v[2];
-            V[3] = v[1]; V[4] = v[3]; V[5] = v[4];
-            V[6] = v[2]; V[7] = v[4]; V[8] = v[5];
-            double* gp = p.g + p.gB + (size_t)3 * (pt0 + tid);
-            gp[0] = v[6]; gp[1] = v[7]; gp[2] = v[8];
-        }
-        // cost of the tile: the reduction tree of block_sum
-        c = warp_sum(c);
-        if (lane == 0) s_red[(it & 1) * 8 + wid] = c;
-        // level-2 prefetch (addresses from the level-1 registers)
+        // level-2 loads of tile k+1 (their addresses arrived one iteration ago)
         double ncv[R::NC], nX[3];
         R::load_cam(cams, ncam, ncv);
         nX[0] = __ldg(pts + (size_t)3 * nptg); nX[1] = __ldg(pts + (size_t)3 * nptg + 1); nX[2] = __ldg(pts + (size_t)3 * nptg + 2);
-        if (tid == 0) bulk_store_wait();     // the previous tile's store has drained: the other stage is free again
-        fence_proxy_async();
+        // level-1 loads of tile k+2 (its descriptor arrived one iteration ago)
+        int n2cam, n2ptg, n2lo;
+        double2 n2z;
+        { const int j = dn2.z + min(tid, max(dn2.w - 1, 0)); n2cam = p.obs_cam[j]; n2ptg = p.obs_pt[j]; n2z = p.obs_z[j]; n2lo = p.obs_start[dn2.x + min(tid, dn2.y)]; }
         __syncthreads();
 
+        // per-point sums over (point, element) items:  block(A, p, p) += ..., b[p] += ...   src/linearsystem.jl:140,166
+        // (observation order; loads are issued four at a time, adding an exact 0.0 past the end of the point)
+        for (int item = tid; item < 9 * npt; item += TO) {
+            const int q = item / 9, i = item - 9 * q;
+            const int j0 = s_ost[q], j1 = s_ost[q + 1];
+            double v = 0.0;
+            for (int j = j0; j < j1; j += 4) {
+                double a[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) a[e] = (j + e < j1) ? s_pc[9 * (j + e) + i] : 0.0;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) v += a[e];
+            }
+            if (i < 6) {   // lower-triangle element i of V_p -> its position(s) in the full column-major 3 x 3 block
+                double* V = s_base + WB * j1 + 9 * q;
+                const int pa = (0x854210 >> (4 * i)) & 15, pb = (0x874630 >> (4 * i)) & 15;
+                V[pa] = v;
+                if (pb != pa) V[pb] = v;
+            } else {
+                p.g[p.gB + (size_t)3 * (pt0 + q) + (i - 6)] = v;
+            }
+        }
+        // cost of the tile: xor-shuffle tree inside a warp, then the warps in order (the cost kernel uses the same tree)
+        c = warp_sum(c);
+        if (lane == 0) s_red[wid] = c;
+        if (p.use_tma) {
+            if (tid == 0) bulk_store_wait();     // the previous tile's store has drained: the other stage is free again
+            fence_proxy_async();
+        }
+        __syncthreads();
+
+        const int span = WB * nob + 9 * npt;
+        double* gdst = p.H + span0;
         if (tid == 0) {
             double tsum = 0.0;
 #pragma unroll
-            for (int i = 0; i < LIN_THREADS / 32; ++i) tsum += s_red[(it & 1) * 8 + i];
+            for (int i = 0; i < NW; ++i) tsum += s_red[i];
             cost_partials[t] = tsum;
-            const int span = WB * nob + 9 * npt;
-            double* gdst = p.H + span0;
-            const int body = (span - par) & ~1;
-            if (par && span > 0) gdst[0] = s_base[0];
-            if (body > 0) bulk_store(gdst + par, s_base + par, (uint32_t)body * 8u);
-            if (par + body < span) gdst[span - 1] = s_base[span - 1];
+            if (p.use_tma) {
+                const int body = (span - par) & ~1;
+                if (par) gdst[0] = s_base[0];
+                if (body > 0) bulk_store(gdst + par, s_base + par, (uint32_t)body * 8u);
+                if (par + body < span) gdst[span - 1] = s_base[span - 1];
+            }
         }
+        if (!p.use_tma) { for (int i = tid; i < span; i += TO) gdst[i] = s_base[i]; }
         if (!has_next) break;
-        t = tn; d = dn; cam = ncam; ptg = nptg; z = nz; ost_lo = nlo; ost_hi = nhi;
+        t += G; d = dn; dn = dn2; dn2 = dn3;
+        cam = ncam; ptg = nptg; z = nz; lo = nlo;
+        ncam = n2cam; nptg = n2ptg; nz = n2z; nlo = n2lo;
 #pragma unroll
         for (int i = 0; i < R::NC; ++i) cv[i] = ncv[i];
         X[0] = nX[0]; X[1] = nX[1]; X[2] = nX[2];
     }
-    if (tid == 0) bulk_store_wait();
+    if (p.use_tma && tid == 0) bulk_store_wait();
 }
 
-template <class R>
-__global__ void __launch_bounds__(LIN_THREADS) cost2_kernel(DevProblem p, const int4* __restrict__ tiles, const double* __restrict__ cams,
-                                                            const double* __restrict__ pts, double* __restrict__ cost_partials) {
-    __shared__ double s_red[16];
+// ---------------------------------------------------------------------------------------------------
+// K3  cost: sum 0.5 rho(|r|^2) with the same tiling and reduction tree as K1 (bit-identical cost for identical variables).
+// Replaces cost(vars, costs) (src/cost.jl:11) -> computerescost (src/residual.jl:49-55).  Persistent, register-pipelined.
+// ---------------------------------------------------------------------------------------------------
+template <class R, int TO>
+__global__ void __launch_bounds__(TO) cost_kernel(DevProblem p, const int4* __restrict__ tiles, const double* __restrict__ cams,
+                                                  const double* __restrict__ pts, double* __restrict__ cost_partials) {
+    constexpr int NW = TO / 32;
+    __shared__ double s_red[2 * NW];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int G = gridDim.x;
     int t = blockIdx.x;
     if (t >= p.ntiles) return;
+    const int last = p.ntiles - 1;
     int4 d = tiles[t];
-    int cam = 0, ptg = 0;
-    double2 z = make_double2(0.0, 0.0);
-    if (tid < d.w) { const int j = d.z + tid; cam = p.obs_cam[j]; ptg = p.obs_pt[j]; z = p.obs_z[j]; }
+    int4 dn = tiles[min(t + G, last)];
+    int4 dn2 = tiles[min(t + 2 * G, last)];
+    int cam, ptg, ncam, nptg;
+    double2 z, nz;
+    { const int j = d.z + min(tid, max(d.w - 1, 0)); cam = p.obs_cam[j]; ptg = p.obs_pt[j]; z = p.obs_z[j]; }
+    { const int j = dn.z + min(tid, max(dn.w - 1, 0)); ncam = p.obs_cam[j]; nptg = p.obs_pt[j]; nz = p.obs_z[j]; }
+    double cv[R::NC], X[3];
+    R::load_cam(cams, cam, cv);
+    X[0] = __ldg(pts + (size_t)3 * ptg); X[1] = __ldg(pts + (size_t)3 * ptg + 1); X[2] = __ldg(pts + (size_t)3 * ptg + 2);
     for (int it = 0;; ++it) {
-        const int tn = t + G;
-        const bool has_next = tn < p.ntiles;
-        int4 dn = make_int4(0, 0, 0, 0);
-        if (has_next) dn = tiles[tn];
-        double cv[R::NC];
-        R::load_cam(cams, cam, cv);
-        const double X[3] = {__ldg(pts + (size_t)3 * ptg), __ldg(pts + (size_t)3 * ptg + 1), __ldg(pts + (size_t)3 * ptg + 2)};
-        int ncam = 0, nptg = 0;
-        double2 nz = make_double2(0.0, 0.0);
-        if (tid < dn.w) { const int j = dn.z + tid; ncam = p.obs_cam[j]; nptg = p.obs_pt[j]; nz = p.obs_z[j]; }
+        const bool has_next = t + G < p.ntiles;
+        const int4 dn3 = tiles[min(t + 3 * G, last)];
+        double ncv[R::NC], nX[3];
+        R::load_cam(cams, ncam, ncv);
+        nX[0] = __ldg(pts + (size_t)3 * nptg); nX[1] = __ldg(pts + (size_t)3 * nptg + 1); nX[2] = __ldg(pts + (size_t)3 * nptg + 2);
+        int n2cam, n2ptg;
+        double2 n2z;
+        { const int j = dn2.z + min(tid, max(dn2.w - 1, 0)); n2cam = p.obs_cam[j]; n2ptg = p.obs_pt[j]; n2z = p.obs_z[j]; }
         double c = 0.0;
         if (tid < d.w) {
             double r[2];
@@ -386,16 +265,21 @@ __global__ void __launch_bounds__(LIN_THREADS) cost2_kernel(DevProblem p, const 
             c = 0.5 * robustify(p.rk, r[0] * r[0] + r[1] * r[1]);
         }
         c = warp_sum(c);
-        if (lane == 0) s_red[(it & 1) * 8 + wid] = c;
+        if (lane == 0) s_red[(it & 1) * NW + wid] = c;
         __syncthreads();
         if (tid == 0) {
             double tsum = 0.0;
 #pragma unroll
-            for (int i = 0; i < LIN_THREADS / 32; ++i) tsum += s_red[(it & 1) * 8 + i];
+            for (int i = 0; i < NW; ++i) tsum += s_red[(it & 1) * NW + i];
             cost_partials[t] = tsum;
         }
         if (!has_next) break;
-        t = tn; d = dn; cam = ncam; ptg = nptg; z = nz;
+        t += G; d = dn; dn = dn2; dn2 = dn3;
+        cam = ncam; ptg = nptg; z = nz;
+        ncam = n2cam; nptg = n2ptg; nz = n2z;
+#pragma unroll
+        for (int i = 0; i < R::NC; ++i) cv[i] = ncv[i];
+        X[0] = nX[0]; X[1] = nX[1]; X[2] = nX[2];
     }
 }
 
@@ -532,14 +416,6 @@ __global__ void schur_init_kernel(DevProblem p, double* __restrict__ S, double* 
     }
 }
 
-template <int DC>
-struct SchurSmem {
-    static constexpr int WB = 3 * DC;
-    static constexpr int ROW = WB * TILE_OBS + 9 * TILE_PTS;
-    static constexpr int Y = WB * TILE_OBS;
-    static constexpr size_t bytes = (size_t)(ROW + Y + 6 * TILE_PTS + 3 * TILE_PTS + 2) * sizeof(double) + (TILE_PTS + 4) * sizeof(int) + 16;
-};
-
 // load the tile's contiguous H span into shared memory (TMA bulk load when 16-byte aligned)
 __device__ __forceinline__ void load_span(double* s_dst, const double* gsrc, int span, uint64_t* bar, int use_tma) {
     const bool aligned = ((reinterpret_cast<uintptr_t>(gsrc) & 15) == 0) && ((span & 1) == 0);
@@ -556,104 +432,6 @@ __device__ __forceinline__ void load_span(double* s_dst, const double* gsrc, int
     } else {
         for (int i = threadIdx.x; i < span; i += blockDim.x) s_dst[i] = gsrc[i];
         __syncthreads();
-    }
-}
-
-template <int DC>
-__global__ void __launch_bounds__(LIN_THREADS) schur_tile_kernel(DevProblem p, double* __restrict__ S, double* __restrict__ rhs,
-                                                                 double* __restrict__ Ainv_out, double lambda) {
-    constexpr int WB = 3 * DC;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    double* s_row = reinterpret_cast<double*>(smem_raw);
-    double* s_Y = s_row + SchurSmem<DC>::ROW;
-    double* s_Ai = s_Y + SchurSmem<DC>::Y;
-    double* s_t = s_Ai + 6 * TILE_PTS;
-    uint64_t* bar = reinterpret_cast<uint64_t*>(s_t + 3 * TILE_PTS);
-    int* s_ost = reinterpret_cast<int*>(bar + 2);
-
-    const int tid = threadIdx.x;
-    // Co-resident CTAs would otherwise work on neighbouring points, i.e. the same few cameras, and serialise their
-    // reductions on the same S blocks in L2: stride the tile order so that concurrent CTAs touch distant cameras.
-    const int G = p.schur_stride;
-    const int per = (p.ntiles + G - 1) / G;
-    int t = (blockIdx.x % G) * per + blockIdx.x / G;
-    if (G <= 1) t = blockIdx.x;
-    if (t >= p.ntiles) return;
-    const int pt0 = p.tile_pt[t], pt1 = p.tile_pt[t + 1];
-    const int ob0 = p.obs_start[pt0], ob1 = p.obs_start[pt1];
-    const int npt = pt1 - pt0, nob = ob1 - ob0;
-    const long long n = (long long)DC * p.nA;
-    for (int i = tid; i <= npt; i += LIN_THREADS) s_ost[i] = p.obs_start[pt0 + i] - ob0;
-    const size_t span0 = (size_t)p.hB + (size_t)WB * ob0 + (size_t)9 * pt0;
-    load_span(s_row, p.H + span0, WB * nob + 9 * npt, bar, p.use_tma);
-    __syncthreads();
-
-    if (tid < npt) {  // A_p^-1 and t_p = A_p^-1 g_p
-        const double* V = s_row + WB * s_ost[tid + 1] + 9 * tid;
-        const double a[6] = {V[0] + lambda, V[1], V[2], V[4] + lambda, V[5], V[8] + lambda};
-        double inv[6];
-        inv_sym3(a, inv);
-#pragma unroll
-        for (int i = 0; i < 6; ++i) { s_Ai[6 * tid + i] = inv[i]; Ainv_out[(size_t)6 * (pt0 + tid) + i] = inv[i]; }
-        const double* gp = p.g + p.gB + (size_t)3 * (pt0 + tid);
-        const double g0 = gp[0], g1 = gp[1], g2 = gp[2];
-        s_t[3 * tid] = inv[0] * g0 + inv[1] * g1 + inv[2] * g2;
-        s_t[3 * tid + 1] = inv[1] * g0 + inv[3] * g1 + inv[4] * g2;
-        s_t[3 * tid + 2] = inv[2] * g0 + inv[4] * g1 + inv[5] * g2;
-    }
-    __syncthreads();
-
-    double W[WB];
-    int cam = 0, pl = 0;
-    if (tid < nob) {
-        cam = p.obs_cam[ob0 + tid];
-        pl = p.obs_pt[ob0 + tid] - pt0;
-        const double* w = s_row + WB * tid + 9 * pl;
-#pragma unroll
-        for (int i = 0; i < WB; ++i) W[i] = w[i];
-        const double* ai = s_Ai + 6 * pl;
-        const double i00 = ai[0], i10 = ai[1], i20 = ai[2], i11 = ai[3], i21 = ai[4], i22 = ai[5];
-        const double t0 = s_t[3 * pl], t1 = s_t[3 * pl + 1], t2 = s_t[3 * pl + 2];
-        double* y = s_Y + WB * tid;
-#pragma unroll
-        for (int a = 0; a < DC; ++a) {
-            const double w0 = W[3 * a], w1 = W[3 * a + 1], w2 = W[3 * a + 2];
-            y[3 * a] = i00 * w0 + i10 * w1 + i20 * w2;
-            y[3 * a + 1] = i10 * w0 + i11 * w1 + i21 * w2;
-            y[3 * a + 2] = i20 * w0 + i21 * w1 + i22 * w2;
-            atomicAdd(rhs + (size_t)cam * DC + a, -(w0 * t0 + w1 * t1 + w2 * t2));
-        }
-    }
-    __syncthreads();
-    if (tid < nob) {
-        const int jbeg = s_ost[pl];
-        for (int j = jbeg; j <= tid; ++j) {   // cameras ascend within a point: cam_j <= cam_i -> lower triangle
-            const int camj = p.obs_cam[ob0 + j];
-            const double* y = s_Y + WB * j;
-            double* Sb;
-            size_t sa, sb;   // strides of the block's row index a and column index b
-            if (p.s_tiled) {
-                constexpr int TC = ST / DC;
-                const int I = cam / TC, Jt = camj / TC;
-                const int r0 = (cam - I * TC) * DC, c0 = (camj - Jt * TC) * DC;
-                const int pI = p.tile_pos[I], pJ = p.tile_pos[Jt];
-                if (pI >= pJ) { Sb = S + (size_t)p.tile_id[(size_t)pI * p.NT + pJ] * ST2 + r0 + (size_t)ST * c0; sa = 1; sb = ST; }
-                else { Sb = S + (size_t)p.tile_id[(size_t)pJ * p.NT + pI] * ST2 + c0 + (size_t)ST * r0; sa = ST; sb = 1; }   // stored transposed
-            } else {
-                Sb = S + (size_t)cam * DC + (size_t)n * ((size_t)camj * DC);
-                sa = 1; sb = (size_t)n;
-            }
-#pragma unroll
-            for (int b = 0; b < DC; ++b) {
-                const double y0 = y[3 * b], y1 = y[3 * b + 1], y2 = y[3 * b + 2];
-#pragma unroll
-                for (int a = 0; a < DC; ++a) {
-                    if (j == tid && a < b) continue;
-                    const double v = W[3 * a] * y0 + W[3 * a + 1] * y1 + W[3 * a + 2] * y2;
-                    atomicAdd(Sb + sa * a + sb * b, -v);
-                }
-            }
-        }
     }
 }
 
@@ -806,96 +584,194 @@ __global__ void __launch_bounds__(SCH_THREADS, 2) schur2_kernel(DevProblem p, Sc
 }
 
 // ---------------------------------------------------------------------------------------------------
-// Back-substitution + variable update + step statistics for one tile of points.
+// Back-substitution + variable update + step statistics over tiles of points (persistent, pipelined).
 //   dx_p = A_p^-1 (g_p - sum_c W_pc dx_c);  x = -dx (negate!, src/iterators.jl:152);
 //   varnext[p] = update(variables[p], x)  (src/linearsystem.jl:206-213, src/variable.jl:10)
-// Partials per tile: [0] max|x_p|, [1] sum x_p^2, [2] x'Hx terms owned by the point rows, [3] g_p . x_p
-// (x'Hx uses the UNdamped H like src/iterators.jl:162-163).
+// Per CTA partials (n = gridDim.x): [b] max|x_p|, [n + b] sum x_p^2, [2n + b] x'Hx terms owned by the point rows,
+// [3n + b] g_p . x_p   (x'Hx uses the UNdamped H like src/iterators.jl:162-163).
+// The tile's H span arrives by a double-buffered cp.async.bulk load (mbarrier complete_tx) placed at the parity of its
+// global offset; observation indices, camera steps and per-point vectors ride the same register pipeline as K1.
 // ---------------------------------------------------------------------------------------------------
-template <int DC>
-__global__ void __launch_bounds__(LIN_THREADS) backsub_tile_kernel(DevProblem p, const double* __restrict__ dxc, const double* __restrict__ Ainv,
-                                                                   const double* __restrict__ pts, double* __restrict__ pts_next,
-                                                                   double* __restrict__ x, double* __restrict__ partials) {
-    constexpr int WB = 3 * DC;
+// WB consecutive doubles from shared memory with 128-bit loads at the block's own 16-byte parity (the 144-byte block stride
+// makes 64-bit accesses 2-way bank conflicted)
+template <int WB>
+__device__ __forceinline__ void load_wblock(const double* wd, double w[WB]) {
+    constexpr int NP = (WB - 1) / 2;
+    const bool odd = (reinterpret_cast<uintptr_t>(wd) & 8) != 0;
+    const double2* wd2 = reinterpret_cast<const double2*>(wd + (odd ? 1 : 0));
+    double2 v[NP];
+#pragma unroll
+    for (int k = 0; k < NP; ++k) v[k] = wd2[k];
+    const double xa = wd[odd ? 0 : 2 * NP];
+    w[0] = odd ? xa : v[0].x;
+#pragma unroll
+    for (int e = 1; e < 2 * NP; ++e) w[e] = odd ? ((e & 1) ? v[(e - 1) / 2].x : v[(e - 2) / 2].y) : ((e & 1) ? v[(e - 1) / 2].y : v[e / 2].x);
+    w[2 * NP] = odd ? v[NP - 1].y : xa;
+    if (WB > 2 * NP + 1) w[WB - 1] = wd[WB - 1];
+}
+
+template <int DC, int TO, int TP>
+struct BacksubSmem {
+    static constexpr int WB = 3 * DC;
+    static constexpr int ROW = WB * TO + 9 * TP + 2;
+    static constexpr size_t bytes = (size_t)(2 * ROW + 3 * TO + 4 * (TO / 32) + 2) * sizeof(double) + (size_t)(TP + 4) * sizeof(int);
+};
+
+template <int DC, int TO, int TP>
+__global__ void __launch_bounds__(TO) backsub_kernel(DevProblem p, const int4* __restrict__ tiles, const double* __restrict__ dxc,
+                                                     const double* __restrict__ Ainv, const double* __restrict__ pts, double* __restrict__ pts_next,
+                                                     double* __restrict__ x, double* __restrict__ partials) {
+    constexpr int WB = 3 * DC, NW = TO / 32;
+    using SM = BacksubSmem<DC, TO, TP>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double* s_row = reinterpret_cast<double*>(smem_raw);
-    double* s_u = s_row + SchurSmem<DC>::ROW;       // 3 per observation: W_pc dx_c
-    double* s_red = s_u + 3 * TILE_OBS;
-    uint64_t* bar = reinterpret_cast<uint64_t*>(s_red + 8);
+    double* s_row0 = reinterpret_cast<double*>(smem_raw);
+    double* s_u = s_row0 + 2 * SM::ROW;             // 3 per observation (SoA): W_pc dx_c
+    double* s_red = s_u + 3 * TO;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(s_red + 4 * NW);   // 2 mbarriers
     int* s_ost = reinterpret_cast<int*>(bar + 2);
 
-    const int tid = threadIdx.x, t = blockIdx.x;
-    const int pt0 = p.tile_pt[t], pt1 = p.tile_pt[t + 1];
-    const int ob0 = p.obs_start[pt0], ob1 = p.obs_start[pt1];
-    const int npt = pt1 - pt0, nob = ob1 - ob0;
-    for (int i = tid; i <= npt; i += LIN_THREADS) s_ost[i] = p.obs_start[pt0 + i] - ob0;
-    const size_t span0 = (size_t)p.hB + (size_t)WB * ob0 + (size_t)9 * pt0;
-    load_span(s_row, p.H + span0, WB * nob + 9 * npt, bar, p.use_tma);
-    __syncthreads();
-
-    if (tid < nob) {
-        const int cam = p.obs_cam[ob0 + tid];
-        const int pl = p.obs_pt[ob0 + tid] - pt0;
-        const double* w = s_row + WB * tid + 9 * pl;
-        double u0 = 0, u1 = 0, u2 = 0;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int G = gridDim.x;
+    int t = blockIdx.x;
+    double mx = 0.0, sq = 0.0, xhx = 0.0, gx = 0.0;   // running step statistics of this thread's points
+    if (t < p.ntiles) {
+        const int last = p.ntiles - 1;
+        if (tid == 0) { mbar_init(bar, 1); mbar_init(bar + 1, 1); }
+        __syncthreads();
+        // issue the span load of tile descriptor dd into stage st
+        auto issue = [&](const int4& dd, int st) {
+            const size_t span0 = (size_t)p.hB + (size_t)WB * dd.z + (size_t)9 * dd.x;
+            const int par = (int)(span0 & 1), span = WB * dd.w + 9 * dd.y;
+            double* sb = s_row0 + st * SM::ROW + par;
+            const double* gs = p.H + span0;
+            if (p.use_tma) {
+                const int body = (span - par) & ~1;
+                if (tid == 0) {
+                    mbar_expect_tx(bar + st, (uint32_t)body * 8u);
+                    bulk_load(sb + par, gs + par, (uint32_t)body * 8u, bar + st);
+                }
+                if (tid == 32 % TO) {
+                    if (par) sb[0] = gs[0];
+                    if (par + body < span) sb[span - 1] = gs[span - 1];
+                }
+            } else {
+                for (int i = tid; i < span; i += TO) sb[i] = gs[i];
+            }
+        };
+        int4 d = tiles[t];
+        int4 dn = tiles[min(t + G, last)];
+        int4 dn2 = tiles[min(t + 2 * G, last)];
+        issue(d, 0);
+        __syncthreads();                              // the scalar head/tail elements of stage 0 are visible
+        // register pipeline as in K1: unconditional loads from clamped addresses, no arithmetic on a value in flight
+        int cam, ptg, lo, ncam, nptg, nlo;
+        { const int j = d.z + min(tid, max(d.w - 1, 0)); cam = p.obs_cam[j]; ptg = p.obs_pt[j]; lo = p.obs_start[d.x + min(tid, d.y)]; }
+        { const int j = dn.z + min(tid, max(dn.w - 1, 0)); ncam = p.obs_cam[j]; nptg = p.obs_pt[j]; nlo = p.obs_start[dn.x + min(tid, dn.y)]; }
+        double dx[DC], pg[3], pa[6], pX[3];
 #pragma unroll
-        for (int a = 0; a < DC; ++a) {
-            const double d = dxc[(size_t)cam * DC + a];
-            u0 += w[3 * a] * d; u1 += w[3 * a + 1] * d; u2 += w[3 * a + 2] * d;
+        for (int a = 0; a < DC; ++a) dx[a] = dxc[(size_t)cam * DC + a];
+        {
+            const size_t pt = (size_t)d.x + min(tid, max(d.y - 1, 0));
+#pragma unroll
+            for (int i = 0; i < 3; ++i) { pg[i] = p.g[p.gB + 3 * pt + i]; pX[i] = pts[3 * pt + i]; }
+#pragma unroll
+            for (int i = 0; i < 6; ++i) pa[i] = Ainv[6 * pt + i];
         }
-        s_u[3 * tid] = u0; s_u[3 * tid + 1] = u1; s_u[3 * tid + 2] = u2;
+        for (int it = 0;; ++it) {
+            const bool has_next = t + G < p.ntiles;
+            const int4 dn3 = tiles[min(t + 3 * G, last)];
+            const int pt0 = d.x, npt = d.y, ob0 = d.z, nob = d.w;
+            const size_t span0 = (size_t)p.hB + (size_t)WB * ob0 + (size_t)9 * pt0;
+            const int st = it & 1;
+            const double* s_base = s_row0 + st * SM::ROW + (int)(span0 & 1);
+            if (has_next) issue(dn, st ^ 1);          // the other stage was released by the barrier that ended iteration it-1
+            if (tid <= npt) s_ost[tid] = lo - ob0;
+            if (p.use_tma) mbar_wait(bar + st, (uint32_t)((it >> 1) & 1));
+            else __syncthreads();
+            if (tid < nob) {
+                const int pl = ptg - pt0;
+                double w[WB];
+                load_wblock<WB>(s_base + WB * tid + 9 * pl, w);
+                double u0 = 0, u1 = 0, u2 = 0;
+#pragma unroll
+                for (int a = 0; a < DC; ++a) { u0 += w[3 * a] * dx[a]; u1 += w[3 * a + 1] * dx[a]; u2 += w[3 * a + 2] * dx[a]; }
+                s_u[tid] = u0; s_u[TO + tid] = u1; s_u[2 * TO + tid] = u2;
+            }
+            // level-2 loads of tile k+1, level-1 loads of tile k+2
+            double ndx[DC], npg[3], npa[6], npX[3];
+#pragma unroll
+            for (int a = 0; a < DC; ++a) ndx[a] = dxc[(size_t)ncam * DC + a];
+            {
+                const size_t pt = (size_t)dn.x + min(tid, max(dn.y - 1, 0));
+#pragma unroll
+                for (int i = 0; i < 3; ++i) { npg[i] = p.g[p.gB + 3 * pt + i]; npX[i] = pts[3 * pt + i]; }
+#pragma unroll
+                for (int i = 0; i < 6; ++i) npa[i] = Ainv[6 * pt + i];
+            }
+            int n2cam, n2ptg, n2lo;
+            { const int j = dn2.z + min(tid, max(dn2.w - 1, 0)); n2cam = p.obs_cam[j]; n2ptg = p.obs_pt[j]; n2lo = p.obs_start[dn2.x + min(tid, dn2.y)]; }
+            __syncthreads();
+            if (tid < npt) {
+                const int j0 = s_ost[tid], j1 = s_ost[tid + 1];
+                double u0 = 0, u1 = 0, u2 = 0;
+                for (int j = j0; j < j1; ++j) { u0 += s_u[j]; u1 += s_u[TO + j]; u2 += s_u[2 * TO + j]; }
+                const size_t pt = (size_t)pt0 + tid;
+                const double r0 = pg[0] - u0, r1 = pg[1] - u1, r2 = pg[2] - u2;
+                const double x0 = -(pa[0] * r0 + pa[1] * r1 + pa[2] * r2);
+                const double x1 = -(pa[1] * r0 + pa[3] * r1 + pa[4] * r2);
+                const double x2 = -(pa[2] * r0 + pa[4] * r1 + pa[5] * r2);
+                x[p.gB + 3 * pt] = x0; x[p.gB + 3 * pt + 1] = x1; x[p.gB + 3 * pt + 2] = x2;
+                pts_next[3 * pt] = pX[0] + x0;
+                pts_next[3 * pt + 1] = pX[1] + x1;
+                pts_next[3 * pt + 2] = pX[2] + x2;
+                mx = nanmax(mx, nanmax(nanmax(fabs(x0), fabs(x1)), fabs(x2)));
+                sq += x0 * x0 + x1 * x1 + x2 * x2;
+                gx += pg[0] * x0 + pg[1] * x1 + pg[2] * x2;
+                const double* V = s_base + WB * j1 + 9 * tid;
+                const double v0 = V[0] * x0 + V[3] * x1 + V[6] * x2;
+                const double v1 = V[1] * x0 + V[4] * x1 + V[7] * x2;
+                const double v2 = V[2] * x0 + V[5] * x1 + V[8] * x2;
+                // x_p' V x_p + 2 x_p' (sum_c W_pc x_c),  with x_c = -dx_c  =>  sum_c W_pc x_c = -u
+                xhx += (x0 * v0 + x1 * v1 + x2 * v2) - 2.0 * (x0 * u0 + x1 * u1 + x2 * u2);
+            }
+            __syncthreads();                           // releases this stage, s_u and s_ost
+            if (!has_next) break;
+            t += G; d = dn; dn = dn2; dn2 = dn3;
+            cam = ncam; ptg = nptg; lo = nlo; ncam = n2cam; nptg = n2ptg; nlo = n2lo;
+#pragma unroll
+            for (int a = 0; a < DC; ++a) dx[a] = ndx[a];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) { pg[i] = npg[i]; pX[i] = npX[i]; }
+#pragma unroll
+            for (int i = 0; i < 6; ++i) pa[i] = npa[i];
+        }
     }
+    // block reduction of the running statistics (fixed tree), one partial per CTA
+    mx = warp_nanmax(mx); sq = warp_sum(sq); xhx = warp_sum(xhx); gx = warp_sum(gx);
+    if (lane == 0) { s_red[wid] = mx; s_red[NW + wid] = sq; s_red[2 * NW + wid] = xhx; s_red[3 * NW + wid] = gx; }
     __syncthreads();
-    double mx = 0.0, sq = 0.0, xhx = 0.0, gx = 0.0;
-    if (tid < npt) {
-        double u0 = 0, u1 = 0, u2 = 0;
-        for (int j = s_ost[tid]; j < s_ost[tid + 1]; ++j) { u0 += s_u[3 * j]; u1 += s_u[3 * j + 1]; u2 += s_u[3 * j + 2]; }
-        const size_t pt = (size_t)pt0 + tid;
-        const double* gp = p.g + p.gB + 3 * pt;
-        const double g0 = gp[0], g1 = gp[1], g2 = gp[2];
-        const double r0 = g0 - u0, r1 = g1 - u1, r2 = g2 - u2;
-        const double* ai = Ainv + 6 * pt;
-        const double x0 = -(ai[0] * r0 + ai[1] * r1 + ai[2] * r2);
-        const double x1 = -(ai[1] * r0 + ai[3] * r1 + ai[4] * r2);
-        const double x2 = -(ai[2] * r0 + ai[4] * r1 + ai[5] * r2);
-        x[p.gB + 3 * pt] = x0; x[p.gB + 3 * pt + 1] = x1; x[p.gB + 3 * pt + 2] = x2;
-        pts_next[3 * pt] = pts[3 * pt] + x0;
-        pts_next[3 * pt + 1] = pts[3 * pt + 1] + x1;
-        pts_next[3 * pt + 2] = pts[3 * pt + 2] + x2;
-        mx = nanmax(nanmax(fabs(x0), fabs(x1)), fabs(x2));
-        sq = x0 * x0 + x1 * x1 + x2 * x2;
-        gx = g0 * x0 + g1 * x1 + g2 * x2;
-        const double* V = s_row + WB * s_ost[tid + 1] + 9 * tid;
-        const double v0 = V[0] * x0 + V[3] * x1 + V[6] * x2;
-        const double v1 = V[1] * x0 + V[4] * x1 + V[7] * x2;
-        const double v2 = V[2] * x0 + V[5] * x1 + V[8] * x2;
-        // x_p' V x_p + 2 x_p' (sum_c W_pc x_c),  with x_c = -dx_c  =>  sum_c W_pc x_c = -u
-        xhx = (x0 * v0 + x1 * v1 + x2 * v2) - 2.0 * (x0 * u0 + x1 * u1 + x2 * u2);
-    }
-    const double rmx = block_nanmax(mx, s_red);
-    __syncthreads();
-    const double rsq = block_sum(sq, s_red);
-    __syncthreads();
-    const double rxhx = block_sum(xhx, s_red);
-    __syncthreads();
-    const double rgx = block_sum(gx, s_red);
     if (tid == 0) {
-        partials[t] = rmx;
-        partials[p.ntiles + t] = rsq;
-        partials[2 * p.ntiles + t] = rxhx;
-        partials[3 * p.ntiles + t] = rgx;
+        double a = 0.0, b = 0.0, c = 0.0, e = 0.0;
+#pragma unroll
+        for (int i = 0; i < NW; ++i) { a = nanmax(a, s_red[i]); b += s_red[NW + i]; c += s_red[2 * NW + i]; e += s_red[3 * NW + i]; }
+        partials[blockIdx.x] = a;
+        partials[G + blockIdx.x] = b;
+        partials[2 * G + blockIdx.x] = c;
+        partials[3 * G + blockIdx.x] = e;
     }
 }
 
 // Camera side of the update: x_c = -dx_c, varnext[c] = update(variables[c], x_c), plus the camera terms of the step
-// statistics.  Single CTA (cameras are few); out4 = {max|x_c|, sum x_c^2, sum x_c' U_c x_c, g_c . x_c}.
+// statistics.  One thread per camera; per CTA partials (n = gridDim.x): [b] max|x_c|, [n + b] sum x_c^2,
+// [2n + b] sum x_c' U_c x_c, [3n + b] g_c . x_c.
 template <class R>
-__global__ void __launch_bounds__(256) cam_update_kernel(DevProblem p, const double* __restrict__ dxc, const double* __restrict__ cams,
-                                                         double* __restrict__ cams_next, double* __restrict__ x, double* __restrict__ out4) {
+__global__ void __launch_bounds__(128) cam_update_kernel(DevProblem p, const double* __restrict__ dxc, const double* __restrict__ cams,
+                                                         double* __restrict__ cams_next, double* __restrict__ x, double* __restrict__ partials) {
     constexpr int DC = R::DC;
-    __shared__ double s_red[8];
+    __shared__ double s_red[16];
     double mx = 0.0, sq = 0.0, xhx = 0.0, gx = 0.0;
-    for (int cam = threadIdx.x; cam < p.nA; cam += 256) {
+    const int cam = blockIdx.x * 128 + threadIdx.x;
+    if (cam < p.nA) {
         double xc[DC];
 #pragma unroll
         for (int a = 0; a < DC; ++a) {
@@ -915,14 +791,28 @@ __global__ void __launch_bounds__(256) cam_update_kernel(DevProblem p, const dou
         }
         R::update_cam(cams + (size_t)cam * R::CS, xc, cams_next + (size_t)cam * R::CS);
     }
-    const double rmx = block_nanmax(mx, s_red);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    mx = warp_nanmax(mx); sq = warp_sum(sq); xhx = warp_sum(xhx); gx = warp_sum(gx);
+    if (lane == 0) { s_red[wid] = mx; s_red[4 + wid] = sq; s_red[8 + wid] = xhx; s_red[12 + wid] = gx; }
     __syncthreads();
-    const double rsq = block_sum(sq, s_red);
-    __syncthreads();
-    const double rxhx = block_sum(xhx, s_red);
-    __syncthreads();
-    const double rgx = block_sum(gx, s_red);
-    if (threadIdx.x == 0) { out4[0] = rmx; out4[1] = rsq; out4[2] = rxhx; out4[3] = rgx; }
+    if (threadIdx.x == 0) {
+        double a = 0.0, b = 0.0, c = 0.0, e = 0.0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { a = nanmax(a, s_red[i]); b += s_red[4 + i]; c += s_red[8 + i]; e += s_red[12 + i]; }
+        const int G = gridDim.x;
+        partials[blockIdx.x] = a; partials[G + blockIdx.x] = b; partials[2 * G + blockIdx.x] = c; partials[3 * G + blockIdx.x] = e;
+    }
+}
+
+// CTA k reduces partials[k * n .. (k+1) * n) in a fixed order into out[k]; k == 0 is a NaN-propagating max, the others sums
+// (the {max|x|, sum x^2, x'Hx, g.x} quadruple of the step statistics).
+__global__ void __launch_bounds__(256) reduce_stats_kernel(const double* __restrict__ partials, int n, double* __restrict__ out) {
+    __shared__ double s_red[8];
+    const double* src = partials + (size_t)blockIdx.x * n;
+    double v = 0.0;
+    if (blockIdx.x == 0) { for (int i = threadIdx.x; i < n; i += 256) v = nanmax(v, src[i]); v = block_nanmax(v, s_red); }
+    else { for (int i = threadIdx.x; i < n; i += 256) v += src[i]; v = block_sum(v, s_red); }
+    if (threadIdx.x == 0) out[blockIdx.x] = v;
 }
 
 // mirror the lower triangle of the dense n x n matrix into the upper one (LU fallback for non-PD systems)

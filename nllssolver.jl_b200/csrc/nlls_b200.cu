@@ -108,7 +108,7 @@ struct nlls_ctx {
     double *d_A[3] = {nullptr, nullptr, nullptr}, *d_B[3] = {nullptr, nullptr, nullptr};
     int cur = 0, nxt = 1, bst = 2;
     double *d_H = nullptr, *d_g = nullptr, *d_x = nullptr, *d_Ainv = nullptr, *d_S = nullptr, *d_rhs = nullptr;
-    double *d_cost_part = nullptr, *d_step_part = nullptr, *d_cam_part = nullptr;
+    double *d_cost_part = nullptr, *d_step_part = nullptr, *d_cam_part = nullptr, *d_camstat_part = nullptr;
     double *d_scal = nullptr, *h_scal = nullptr;
     void* d_flush = nullptr;
     size_t flush_bytes = 0;
@@ -118,21 +118,21 @@ struct nlls_ctx {
     int* d_info = nullptr;
     int* d_ipiv = nullptr;
     int use_tma = 1;
-    int lin_v2 = 1;                 // persistent pipelined linearisation / cost kernels (NLLS_B200_LIN=v1 selects the one-tile-per-CTA ones)
+    int tile_obs = 256;             // observations per point tile = threads per CTA of the tile kernels (NLLS_B200_TILE=128|256)
     int4* d_tiles = nullptr;        // (pt0, npt, ob0, nob) per point tile
-    int nsm = 148, lin_grid = 0, cost_grid = 0;
+    int nsm = 148, lin_grid = 0, cost_grid = 0, bs_grid = 0;
     int schur_stride = 296;
     // reduced camera system (tile-sparse level-scheduled LDL' by default; NLLS_B200_REDUCED=dense selects dense storage + cuSOLVER)
     int s_tiled = 1;
     int NT = 0;
     int64_t ntiles_alloc = 0;
     int red_levels = 0;
-    struct RedLaunch { int kind, off, cnt; };          // kind 0 diag, 1 trsm, 2 update
+    struct RedLaunch { int kind, off, cnt; };          // kind 0: diagonal tiles of a level, 1: its off-diagonal tiles
     std::vector<RedLaunch> fact_launches;
+    RedTask* d_red_tasks = nullptr;
+    RedUpd* d_red_upds = nullptr;
     std::vector<std::pair<int, int>> lvl_cols;           // (offset, count) into d_lvl_cols per level
-    int *d_tile_id = nullptr, *d_pos = nullptr, *d_diag_tile = nullptr, *d_diag_tile_nat = nullptr, *d_diag_tasks = nullptr, *d_lvl_cols = nullptr;
-    int2* d_trsm_tasks = nullptr;
-    int4* d_upd_tasks = nullptr;
+    int *d_tile_id = nullptr, *d_pos = nullptr, *d_diag_tile = nullptr, *d_diag_tile_nat = nullptr, *d_lvl_cols = nullptr;
     int *d_rowptr = nullptr, *d_row_tile = nullptr, *d_row_col = nullptr, *d_colptr = nullptr, *d_col_tile = nullptr, *d_col_row = nullptr;
     double *d_Linv = nullptr, *d_xp = nullptr;
     // Schur v2 plan (per-tile sorted contribution lists)
@@ -249,26 +249,35 @@ int upload_vars(nlls_ctx* ctx, const VarSet& vs, int dstride, double* dst) {
 }
 
 // ---- kernel launch helpers, dispatched on the registered residual type --------------------------------
+template <class R, int TO>
+int set_tile_attrs(nlls_ctx* ctx) {
+    constexpr int TP = TO / 2;
+    CK(cudaFuncSetAttribute(lin_point_kernel<R, TO, TP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LinSmem<R, TO, TP>::bytes));
+    CK(cudaFuncSetAttribute(backsub_kernel<R::DC, TO, TP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BacksubSmem<R::DC, TO, TP>::bytes));
+    int occ = 1;
+    auto grid_for = [&](int o, const char* env) {
+        int g = std::max(1, std::min(ctx->ntiles, ctx->nsm * std::max(1, o)));
+        if (const char* e = getenv(env)) g = std::max(1, std::min(ctx->ntiles, atoi(e)));
+        return g;
+    };
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, lin_point_kernel<R, TO, TP>, TO, LinSmem<R, TO, TP>::bytes));
+    ctx->lin_grid = grid_for(occ, "NLLS_B200_LIN_GRID");
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, cost_kernel<R, TO>, TO, 0));
+    ctx->cost_grid = grid_for(std::min(occ, 1024 / TO), "NLLS_B200_COST_GRID");
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, backsub_kernel<R::DC, TO, TP>, TO, BacksubSmem<R::DC, TO, TP>::bytes));
+    ctx->bs_grid = grid_for(occ, "NLLS_B200_BS_GRID");
+    return NLLS_OK;
+}
+
 template <class R>
 int set_smem_attrs(nlls_ctx* ctx) {
-    CK(cudaFuncSetAttribute(lin_point_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LinSmem<R>::bytes));
-    CK(cudaFuncSetAttribute(lin_point2_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Lin2Smem<R>::bytes));
-    {
-        int occ = 1;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, lin_point2_kernel<R>, LIN_THREADS, Lin2Smem<R>::bytes));
-        ctx->lin_grid = std::max(1, std::min(ctx->ntiles, ctx->nsm * std::max(1, occ)));
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, cost2_kernel<R>, LIN_THREADS, 0));
-        ctx->cost_grid = std::max(1, std::min(ctx->ntiles, ctx->nsm * std::max(1, std::min(occ, 4))));
-        if (const char* g = getenv("NLLS_B200_LIN_GRID")) ctx->lin_grid = std::max(1, std::min(ctx->ntiles, atoi(g)));
-        if (const char* g = getenv("NLLS_B200_COST_GRID")) ctx->cost_grid = std::max(1, std::min(ctx->ntiles, atoi(g)));
-    }
-    CK(cudaFuncSetAttribute(schur_tile_kernel<R::DC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SchurSmem<R::DC>::bytes));
-    CK(cudaFuncSetAttribute(backsub_tile_kernel<R::DC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SchurSmem<R::DC>::bytes));
+    if (ctx->tile_obs == 64) TRY((set_tile_attrs<R, 64>(ctx)));
+    else if (ctx->tile_obs == 128) TRY((set_tile_attrs<R, 128>(ctx)));
+    else TRY((set_tile_attrs<R, 256>(ctx)));
     CK(cudaFuncSetAttribute(schur2_kernel<R::DC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Schur2Smem<R::DC>::bytes));
-    const int red_smem = 2 * ST * LDT * (int)sizeof(double);
-    CK(cudaFuncSetAttribute(ldl_trsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (ST * LDT + ST * LDP) * (int)sizeof(double)));
-    CK(cudaFuncSetAttribute(ldl_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, red_smem));
-    CK(cudaFuncSetAttribute(ldl_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, red_smem));
+    CK(cudaFuncSetAttribute(ldl_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RedSmem::bytes));
+    CK(cudaFuncSetAttribute(ldl_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RedSmem::bytes));
+    CK(cudaFuncSetAttribute(ldl_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWD_SMEM));
     return NLLS_OK;
 }
 
@@ -291,10 +300,12 @@ int launch_linearize(nlls_ctx* ctx, bool do_point = true, bool do_cam = true) {
         CK(cudaEventRecord(ctx->ev_join, ctx->st2));
     }
     if (do_point && ctx->ntiles > 0) {
-        if (ctx->lin_v2)
-            lin_point2_kernel<R><<<ctx->lin_grid, LIN_THREADS, Lin2Smem<R>::bytes, ctx->st>>>(p, ctx->d_tiles, ctx->d_A[ctx->cur], ctx->d_B[ctx->cur], ctx->d_cost_part);
+        if (ctx->tile_obs == 64)
+            lin_point_kernel<R, 64, 32><<<ctx->lin_grid, 64, LinSmem<R, 64, 32>::bytes, ctx->st>>>(p, ctx->d_tiles, ctx->d_A[ctx->cur], ctx->d_B[ctx->cur], ctx->d_cost_part);
+        else if (ctx->tile_obs == 128)
+            lin_point_kernel<R, 128, 64><<<ctx->lin_grid, 128, LinSmem<R, 128, 64>::bytes, ctx->st>>>(p, ctx->d_tiles, ctx->d_A[ctx->cur], ctx->d_B[ctx->cur], ctx->d_cost_part);
         else
-            lin_point_kernel<R><<<ctx->ntiles, LIN_THREADS, LinSmem<R>::bytes, ctx->st>>>(p, ctx->d_A[ctx->cur], ctx->d_B[ctx->cur], ctx->d_cost_part);
+            lin_point_kernel<R, 256, 128><<<ctx->lin_grid, 256, LinSmem<R, 256, 128>::bytes, ctx->st>>>(p, ctx->d_tiles, ctx->d_A[ctx->cur], ctx->d_B[ctx->cur], ctx->d_cost_part);
         ctx->launches++;
     }
     if (do_cam) CK(cudaStreamWaitEvent(ctx->st, ctx->ev_join, 0));
@@ -306,8 +317,9 @@ template <class R>
 int launch_cost(nlls_ctx* ctx, int which, int slot) {
     DevProblem p = devproblem(ctx);
     if (ctx->ntiles > 0) {
-        if (ctx->lin_v2) cost2_kernel<R><<<ctx->cost_grid, LIN_THREADS, 0, ctx->st>>>(p, ctx->d_tiles, ctx->d_A[which], ctx->d_B[which], ctx->d_cost_part);
-        else cost_kernel<R><<<ctx->ntiles, LIN_THREADS, 0, ctx->st>>>(p, ctx->d_A[which], ctx->d_B[which], ctx->d_cost_part);
+        if (ctx->tile_obs == 64) cost_kernel<R, 64><<<ctx->cost_grid, 64, 0, ctx->st>>>(p, ctx->d_tiles, ctx->d_A[which], ctx->d_B[which], ctx->d_cost_part);
+        else if (ctx->tile_obs == 128) cost_kernel<R, 128><<<ctx->cost_grid, 128, 0, ctx->st>>>(p, ctx->d_tiles, ctx->d_A[which], ctx->d_B[which], ctx->d_cost_part);
+        else cost_kernel<R, 256><<<ctx->cost_grid, 256, 0, ctx->st>>>(p, ctx->d_tiles, ctx->d_A[which], ctx->d_B[which], ctx->d_cost_part);
         ctx->launches++;
     }
     reduce_partials_kernel<<<1, 1024, 0, ctx->st>>>(ctx->d_cost_part, ctx->ntiles, ctx->d_scal + slot, 0); ctx->launches++;
@@ -349,11 +361,6 @@ int launch_schur(nlls_ctx* ctx, double lambda) {
         const int grid = G * ((ctx->nstiles + G - 1) / G);
         schur2_kernel<DC><<<grid, SCH_THREADS, Schur2Smem<DC>::bytes, ctx->st>>>(p, sp, ctx->d_S, ctx->d_rhs, ctx->d_Ainv, lambda);
         ctx->launches++;
-    } else if (ctx->ntiles > 0) {
-        const int G = std::max(1, ctx->schur_stride);
-        const int grid = G * ((ctx->ntiles + G - 1) / G);
-        schur_tile_kernel<DC><<<grid, LIN_THREADS, SchurSmem<DC>::bytes, ctx->st>>>(p, ctx->d_S, ctx->d_rhs, ctx->d_Ainv, lambda);
-        ctx->launches++;
     }
     CK(cudaGetLastError());
     if (ctx->nranks > 1) {
@@ -369,22 +376,15 @@ int launch_reduced_solve(nlls_ctx* ctx, bool lu) {
     const int n = (int)ctx->nred;
     if (ctx->s_tiled) {
         const RedSolveLists t = redlists(ctx);
-        const int smem2 = 2 * ST * LDT * (int)sizeof(double), smem_trsm = (ST * LDT + ST * LDP) * (int)sizeof(double);
-        for (const auto& l : ctx->fact_launches) {
-            if (l.kind == 0) ldl_diag_kernel<<<l.cnt, RED_THREADS, 0, ctx->st>>>(ctx->d_S, ctx->d_diag_tasks + l.off);
-            else if (l.kind == 1) ldl_trsm_kernel<<<l.cnt, RED_THREADS, smem_trsm, ctx->st>>>(ctx->d_S, ctx->d_trsm_tasks + l.off);
-            else ldl_update_kernel<<<l.cnt, RED_THREADS, smem2, ctx->st>>>(ctx->d_S, ctx->d_upd_tasks + l.off);
-            ctx->launches++;
-        }
-        ldl_inv_kernel<<<ctx->NT, RED_THREADS, (ST * LDT + NB * LDT) * (int)sizeof(double), ctx->st>>>(ctx->d_S, ctx->d_diag_tile, ctx->d_Linv); ctx->launches++;
         const int nx = ctx->NT * ST;
         red_permute_kernel<<<(nx + 255) / 256, 256, 0, ctx->st>>>(ctx->d_rhs, ctx->d_xp, ctx->d_pos, ctx->NT, 1); ctx->launches++;
-        for (size_t l = 0; l < ctx->lvl_cols.size(); ++l) {
-            ldl_fwd_kernel<<<ctx->lvl_cols[l].second, SOLVE_THREADS, 0, ctx->st>>>(ctx->d_S, ctx->d_Linv, t, ctx->d_lvl_cols + ctx->lvl_cols[l].first, ctx->d_xp);
+        for (const auto& l : ctx->fact_launches) {   // factorisation + forward substitution (fused into the diagonal tasks)
+            if (l.kind == 0) ldl_tile_kernel<true><<<l.cnt, RED_THREADS, RedSmem::bytes, ctx->st>>>(ctx->d_S, ctx->d_Linv, ctx->d_red_tasks + l.off, ctx->d_red_upds, t, ctx->d_xp);
+            else ldl_tile_kernel<false><<<l.cnt, RED_THREADS, RedSmem::bytes, ctx->st>>>(ctx->d_S, ctx->d_Linv, ctx->d_red_tasks + l.off, ctx->d_red_upds, t, ctx->d_xp);
             ctx->launches++;
         }
         for (size_t l = ctx->lvl_cols.size(); l-- > 0;) {
-            ldl_bwd_kernel<<<ctx->lvl_cols[l].second, SOLVE_THREADS, 0, ctx->st>>>(ctx->d_S, ctx->d_Linv, t, ctx->d_lvl_cols + ctx->lvl_cols[l].first, ctx->d_xp);
+            ldl_bwd_kernel<<<ctx->lvl_cols[l].second, RED_THREADS, BWD_SMEM, ctx->st>>>(ctx->d_S, ctx->d_Linv, t, ctx->d_lvl_cols + ctx->lvl_cols[l].first, ctx->d_xp);
             ctx->launches++;
         }
         red_permute_kernel<<<(nx + 255) / 256, 256, 0, ctx->st>>>(ctx->d_xp, ctx->d_rhs, ctx->d_pos, ctx->NT, 0); ctx->launches++;
@@ -407,16 +407,23 @@ template <class R>
 int launch_update(nlls_ctx* ctx) {
     constexpr int DC = R::DC;
     DevProblem p = devproblem(ctx);
+    const int bg = ctx->bs_grid;
     if (ctx->ntiles > 0) {
-        backsub_tile_kernel<DC><<<ctx->ntiles, LIN_THREADS, SchurSmem<DC>::bytes, ctx->st>>>(p, ctx->d_rhs, ctx->d_Ainv, ctx->d_B[ctx->cur],
-                                                                                              ctx->d_B[ctx->nxt], ctx->d_x, ctx->d_step_part);
+        if (ctx->tile_obs == 64)
+            backsub_kernel<DC, 64, 32><<<bg, 64, BacksubSmem<DC, 64, 32>::bytes, ctx->st>>>(p, ctx->d_tiles, ctx->d_rhs, ctx->d_Ainv, ctx->d_B[ctx->cur],
+                                                                                             ctx->d_B[ctx->nxt], ctx->d_x, ctx->d_step_part);
+        else if (ctx->tile_obs == 128)
+            backsub_kernel<DC, 128, 64><<<bg, 128, BacksubSmem<DC, 128, 64>::bytes, ctx->st>>>(p, ctx->d_tiles, ctx->d_rhs, ctx->d_Ainv, ctx->d_B[ctx->cur],
+                                                                                                ctx->d_B[ctx->nxt], ctx->d_x, ctx->d_step_part);
+        else
+            backsub_kernel<DC, 256, 128><<<bg, 256, BacksubSmem<DC, 256, 128>::bytes, ctx->st>>>(p, ctx->d_tiles, ctx->d_rhs, ctx->d_Ainv, ctx->d_B[ctx->cur],
+                                                                                                  ctx->d_B[ctx->nxt], ctx->d_x, ctx->d_step_part);
         ctx->launches++;
     }
-    cam_update_kernel<R><<<1, 256, 0, ctx->st>>>(p, ctx->d_rhs, ctx->d_A[ctx->cur], ctx->d_A[ctx->nxt], ctx->d_x, ctx->d_scal + SC_C_MAX); ctx->launches++;
-    reduce_partials_kernel<<<1, 1024, 0, ctx->st>>>(ctx->d_step_part, ctx->ntiles, ctx->d_scal + SC_P_MAX, 1); ctx->launches++;
-    for (int k = 1; k < 4; ++k) {
-        reduce_partials_kernel<<<1, 1024, 0, ctx->st>>>(ctx->d_step_part + (size_t)k * ctx->ntiles, ctx->ntiles, ctx->d_scal + SC_P_MAX + k, 0); ctx->launches++;
-    }
+    const int cg = (int)((ctx->nA + 127) / 128);
+    cam_update_kernel<R><<<cg, 128, 0, ctx->st>>>(p, ctx->d_rhs, ctx->d_A[ctx->cur], ctx->d_A[ctx->nxt], ctx->d_x, ctx->d_camstat_part); ctx->launches++;
+    reduce_stats_kernel<<<4, 256, 0, ctx->st>>>(ctx->d_step_part, ctx->ntiles > 0 ? bg : 0, ctx->d_scal + SC_P_MAX); ctx->launches++;
+    reduce_stats_kernel<<<4, 256, 0, ctx->st>>>(ctx->d_camstat_part, cg, ctx->d_scal + SC_C_MAX); ctx->launches++;
     CK(cudaGetLastError());
     if (ctx->nranks > 1) {
         CKN(g_nccl.GroupStart());
@@ -521,7 +528,7 @@ int nlls_create(nlls_ctx** out, int device) {
     if (const char* g = getenv("NLLS_B200_SCHUR_STRIDE")) ctx->schur_stride = std::max(1, atoi(g));
     if (const char* g = getenv("NLLS_B200_REDUCED")) ctx->s_tiled = (std::string(g) == "dense") ? 0 : 1;
     if (const char* g = getenv("NLLS_B200_SCHUR")) ctx->schur_v2 = (std::string(g) == "v1") ? 0 : 1;
-    if (const char* g = getenv("NLLS_B200_LIN")) ctx->lin_v2 = (std::string(g) == "v1") ? 0 : 1;
+    if (const char* g = getenv("NLLS_B200_TILE")) { const int v = atoi(g); ctx->tile_obs = (v == 64 || v == 128) ? v : 256; }
     { int v = 0; if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && v > 0) ctx->nsm = v; }
     if (cudaGetLastError() != cudaSuccess) { delete ctx; return NLLS_ERR_CUDA; }
     *out = ctx;
@@ -536,8 +543,8 @@ int nlls_destroy(nlls_ctx* ctx) {
                     ctx->d_item_end, ctx->d_cam_item_start, ctx->d_cm_z, ctx->d_A[0], ctx->d_A[1], ctx->d_A[2], ctx->d_B[0], ctx->d_B[1], ctx->d_B[2],
                     ctx->d_H, ctx->d_g, ctx->d_x, ctx->d_Ainv, ctx->d_S, ctx->d_rhs, ctx->d_cost_part, ctx->d_step_part, ctx->d_cam_part, ctx->d_scal,
                     ctx->d_flush, ctx->d_work, ctx->d_info, ctx->d_ipiv, ctx->d_tile_id, ctx->d_pos, ctx->d_diag_tile, ctx->d_diag_tile_nat,
-                    ctx->d_diag_tasks, ctx->d_lvl_cols, ctx->d_trsm_tasks, ctx->d_upd_tasks, ctx->d_rowptr, ctx->d_row_tile, ctx->d_row_col, ctx->d_colptr,
-                    ctx->d_col_tile, ctx->d_col_row, ctx->d_Linv, ctx->d_xp, ctx->d_stile_pt, ctx->d_chunk_off, ctx->d_chunks, ctx->d_ents, ctx->d_tiles};
+                    ctx->d_lvl_cols, ctx->d_red_tasks, ctx->d_red_upds, ctx->d_rowptr, ctx->d_row_tile, ctx->d_row_col, ctx->d_colptr,
+                    ctx->d_col_tile, ctx->d_col_row, ctx->d_Linv, ctx->d_xp, ctx->d_stile_pt, ctx->d_chunk_off, ctx->d_chunks, ctx->d_ents, ctx->d_tiles, ctx->d_camstat_part};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (ctx->h_scal) cudaFreeHost(ctx->h_scal);
     if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
@@ -702,7 +709,7 @@ int nlls_prepare(nlls_ctx* ctx) {
     for (int64_t p = 0; p < nB; ++p) {
         int* b = order.data() + ctx->h_obs_start[(size_t)p];
         int* e = order.data() + ctx->h_obs_start[(size_t)p + 1];
-        if (e - b > TILE_OBS) FAIL(NLLS_ERR_UNSUPPORTED, "a point with more than " + std::to_string(TILE_OBS) + " observations");
+        if (e - b > ctx->tile_obs) FAIL(NLLS_ERR_UNSUPPORTED, "a point with more than " + std::to_string(ctx->tile_obs) + " observations");
         std::stable_sort(b, e, [&](int x, int y) { return caml[(size_t)x] < caml[(size_t)y]; });
         for (int* q = b + 1; q < e; ++q)
             if (caml[(size_t)*q] == caml[(size_t)*(q - 1)]) FAIL(NLLS_ERR_UNSUPPORTED, "two costs on the same (camera, point) pair");
@@ -714,16 +721,14 @@ int nlls_prepare(nlls_ctx* ctx) {
         ctx->h_obs_cam[(size_t)j] = caml[(size_t)i]; ctx->h_obs_pt[(size_t)j] = ptl[(size_t)i];
         obs_z[(size_t)j] = make_double2(ctx->h_z[(size_t)2 * i], ctx->h_z[(size_t)2 * i + 1]);
     }
-    // tiles: consecutive points, <= TILE_OBS observations and <= TILE_PTS points, boundaries 16-byte aligned in H when possible
+    // tiles: consecutive points, <= tile_obs observations and <= tile_obs / 2 points
     ctx->h_tile_pt.clear();
     ctx->h_tile_pt.push_back(0);
     {
-        auto aligned = [&](int64_t pt) { return ((WB * (int64_t)ctx->h_obs_start[(size_t)pt] + 9 * pt) & 1) == 0; };
         int64_t p0 = 0;
         while (p0 < nB) {
             int64_t p1 = p0;
-            while (p1 < nB && (p1 - p0) < TILE_PTS && (ctx->h_obs_start[(size_t)p1 + 1] - ctx->h_obs_start[(size_t)p0]) <= TILE_OBS) ++p1;
-            if (p1 < nB && !aligned(p1) && p1 - 1 > p0 && aligned(p1 - 1)) --p1;
+            while (p1 < nB && (p1 - p0) < ctx->tile_obs / 2 && (ctx->h_obs_start[(size_t)p1 + 1] - ctx->h_obs_start[(size_t)p0]) <= ctx->tile_obs) ++p1;
             ctx->h_tile_pt.push_back((int)p1);
             p0 = p1;
         }
@@ -755,9 +760,9 @@ int nlls_prepare(nlls_ctx* ctx) {
     ctx->hlen = (int64_t)DC * DC * nA + (int64_t)WB * nobs + 9 * nB;
     ctx->nred = (int64_t)DC * nA;
     // ---- reduced camera system: tile order, tile-level symbolic factorisation, level schedule
-    std::vector<int> tile_id, pos, diag_tile, diag_tile_nat, diag_tasks, lvl_cols_flat, rowptr, row_tile, row_col, colptr, col_tile, col_row;
-    std::vector<int2> trsm_tasks;
-    std::vector<int4> upd_tasks;
+    std::vector<int> tile_id, pos, diag_tile, diag_tile_nat, lvl_cols_flat, rowptr, row_tile, row_col, colptr, col_tile, col_row;
+    std::vector<RedTask> red_tasks;
+    std::vector<RedUpd> red_upds;
     if (ctx->s_tiled) {
         const int TC = ST / DC;
         const int NT = (int)((nA + TC - 1) / TC);
@@ -831,40 +836,39 @@ int nlls_prepare(nlls_ctx* ctx) {
         }
         ctx->red_levels = nlev;
         ctx->fact_launches.clear(); ctx->lvl_cols.clear();
-        std::vector<int> seen((size_t)nt, 0);
-        for (int lv = 0; lv < nlev; ++lv) {
-            const int c0 = (int)lvl_cols_flat.size(), d0 = (int)diag_tasks.size(), t0 = (int)trsm_tasks.size();
-            std::vector<std::pair<int, int4>> ups;   // (round, task)
-            std::vector<int> touched;
-            for (int J2 = 0; J2 < NT; ++J2) {
-                if (level[(size_t)J2] != lv) continue;
-                lvl_cols_flat.push_back(J2);
-                diag_tasks.push_back(diag_tile[(size_t)J2]);
-                const std::vector<int>& r = rows[(size_t)J2];
-                for (int I : r) trsm_tasks.push_back(make_int2(tile_id[(size_t)I * NT + J2], diag_tile[(size_t)J2]));
-                for (size_t a = 0; a < r.size(); ++a) for (size_t b = 0; b <= a; ++b) {
-                    const int tc = tile_id[(size_t)r[a] * NT + r[b]];
-                    ups.push_back({seen[(size_t)tc]++, make_int4(tile_id[(size_t)r[a] * NT + J2], tile_id[(size_t)r[b] * NT + J2], tc, diag_tile[(size_t)J2])});
-                    touched.push_back(tc);
-                }
-            }
-            for (int tc : touched) seen[(size_t)tc] = 0;
-            ctx->lvl_cols.push_back({c0, (int)lvl_cols_flat.size() - c0});
-            ctx->fact_launches.push_back({0, d0, (int)diag_tasks.size() - d0});
-            if ((int)trsm_tasks.size() > t0) ctx->fact_launches.push_back({1, t0, (int)trsm_tasks.size() - t0});
-            std::stable_sort(ups.begin(), ups.end(), [](const std::pair<int, int4>& x, const std::pair<int, int4>& y) { return x.first < y.first; });
-            size_t i0 = 0;
-            while (i0 < ups.size()) {   // one launch per round: tasks of a round hit distinct target tiles
-                size_t i1 = i0;
-                const int u0 = (int)upd_tasks.size();
-                while (i1 < ups.size() && ups[i1].first == ups[i0].first) upd_tasks.push_back(ups[i1++].second);
-                ctx->fact_launches.push_back({2, u0, (int)upd_tasks.size() - u0});
-                i0 = i1;
+        // left-looking update lists: eliminating column K couples every pair (a >= b) of its rows -> tile (r[a], r[b]) gathers
+        // L_{r[a],K} D_K L_{r[b],K}' ; lists are filled in ascending K (fixed summation order)
+        std::vector<std::vector<RedUpd>> tile_upds((size_t)nt);
+        for (int K = 0; K < NT; ++K) {
+            const std::vector<int>& r = rows[(size_t)K];
+            for (size_t a = 0; a < r.size(); ++a) for (size_t b = 0; b <= a; ++b) {
+                RedUpd u; u.a = tile_id[(size_t)r[a] * NT + K]; u.b = tile_id[(size_t)r[b] * NT + K]; u.dk = diag_tile[(size_t)K]; u.pad = 0;
+                tile_upds[(size_t)tile_id[(size_t)r[a] * NT + r[b]]].push_back(u);
             }
         }
+        auto add_task = [&](int tile, int J2) {
+            RedTask tk; tk.tile = tile; tk.dtile = diag_tile[(size_t)J2]; tk.col = J2; tk.upd0 = (int)red_upds.size();
+            for (const RedUpd& u : tile_upds[(size_t)tile]) red_upds.push_back(u);
+            tk.upd1 = (int)red_upds.size(); tk.pad0 = tk.pad1 = tk.pad2 = 0;
+            red_tasks.push_back(tk);
+        };
+        size_t nupd_total = 0;
+        for (int lv = 0; lv < nlev; ++lv) {
+            const int c0 = (int)lvl_cols_flat.size(), d0 = (int)red_tasks.size();
+            for (int J2 = 0; J2 < NT; ++J2) if (level[(size_t)J2] == lv) { lvl_cols_flat.push_back(J2); add_task(diag_tile[(size_t)J2], J2); }
+            const int o0 = (int)red_tasks.size();
+            for (int q = c0; q < (int)lvl_cols_flat.size(); ++q) {
+                const int J2 = lvl_cols_flat[(size_t)q];
+                for (int I : rows[(size_t)J2]) add_task(tile_id[(size_t)I * NT + J2], J2);
+            }
+            ctx->lvl_cols.push_back({c0, (int)lvl_cols_flat.size() - c0});
+            ctx->fact_launches.push_back({0, d0, o0 - d0});
+            if ((int)red_tasks.size() > o0) ctx->fact_launches.push_back({1, o0, (int)red_tasks.size() - o0});
+        }
+        nupd_total = red_upds.size();
         if (getenv("NLLS_B200_VERBOSE"))
-            fprintf(stderr, "[nlls] reduced system: NT=%d tiles=%d half-bandwidth=%d nd=%d levels=%d fact_launches=%zu trsm=%zu upd=%zu\n", NT, nt, w,
-                    (int)use_nd, nlev, ctx->fact_launches.size(), trsm_tasks.size(), upd_tasks.size());
+            fprintf(stderr, "[nlls] reduced system: NT=%d tiles=%d half-bandwidth=%d nd=%d levels=%d fact_launches=%zu tasks=%zu updates=%zu\n", NT, nt, w,
+                    (int)use_nd, nlev, ctx->fact_launches.size(), red_tasks.size(), nupd_total);
         // block-row and block-column lists of L for the sweeps
         rowptr.assign((size_t)NT + 1, 0); colptr.assign((size_t)NT + 1, 0);
         for (int J2 = 0; J2 < NT; ++J2) {
@@ -992,7 +996,8 @@ int nlls_prepare(nlls_ctx* ctx) {
         TRY(dalloc(ctx, &ctx->d_Linv, (size_t)ctx->NT * ST2)); TRY(dalloc(ctx, &ctx->d_xp, (size_t)ctx->NT * ST));
         TRY(upload(ctx, &ctx->d_tile_id, tile_id)); TRY(upload(ctx, &ctx->d_pos, pos));
         TRY(upload(ctx, &ctx->d_diag_tile, diag_tile)); TRY(upload(ctx, &ctx->d_diag_tile_nat, diag_tile_nat));
-        TRY(upload(ctx, &ctx->d_diag_tasks, diag_tasks)); TRY(upload(ctx, &ctx->d_trsm_tasks, trsm_tasks)); TRY(upload(ctx, &ctx->d_upd_tasks, upd_tasks));
+        TRY(upload(ctx, &ctx->d_red_tasks, red_tasks)); TRY(upload(ctx, &ctx->d_red_upds, red_upds));
+        CK(cudaMemsetAsync(ctx->d_Linv, 0, sizeof(double) * (size_t)ctx->NT * ST2, ctx->st));
         TRY(upload(ctx, &ctx->d_lvl_cols, lvl_cols_flat));
         TRY(upload(ctx, &ctx->d_rowptr, rowptr)); TRY(upload(ctx, &ctx->d_row_tile, row_tile)); TRY(upload(ctx, &ctx->d_row_col, row_col));
         TRY(upload(ctx, &ctx->d_colptr, colptr)); TRY(upload(ctx, &ctx->d_col_tile, col_tile)); TRY(upload(ctx, &ctx->d_col_row, col_row));
@@ -1002,6 +1007,7 @@ int nlls_prepare(nlls_ctx* ctx) {
     TRY(dalloc(ctx, &ctx->d_cost_part, (size_t)ctx->ntiles)); TRY(dalloc(ctx, &ctx->d_step_part, (size_t)4 * ctx->ntiles));
     const int NU = DC * (DC + 1) / 2 + DC;
     TRY(dalloc(ctx, &ctx->d_cam_part, (size_t)ctx->nitems * NU));
+    TRY(dalloc(ctx, &ctx->d_camstat_part, (size_t)4 * ((nA + 127) / 128)));
     if (!ctx->s_tiled) {
         int lw1 = 0, lw2 = 0;
         CKS(cusolverDnDpotrf_bufferSize(ctx->cusolver, CUBLAS_FILL_MODE_LOWER, (int)ctx->nred, ctx->d_S, (int)ctx->nred, &lw1));
@@ -1383,6 +1389,7 @@ int nlls_time_kernels(nlls_ctx* ctx, int which, int reps, int flush_l2, double* 
             case NLLS_TIME_SOLVE_REDUCED: TRY(DISPATCH(ctx, launch_schur, ctx, lambda)); CK(cudaEventRecord(ctx->ev_t0, ctx->st)); TRY(launch_reduced_solve(ctx, false)); break;
             case NLLS_TIME_BACKSUB: TRY(DISPATCH(ctx, launch_update, ctx)); break;
             case NLLS_TIME_TRY: TRY(enqueue_try(ctx, lambda, false)); break;
+            case NLLS_TIME_MEMSET_H: CK(cudaMemsetAsync(ctx->d_H + (size_t)ctx->DC * ctx->DC * ctx->nA, 0, sizeof(double) * (size_t)(ctx->hlen - (int64_t)ctx->DC * ctx->DC * ctx->nA), ctx->st)); break;
             default: return NLLS_ERR_INVALID;
         }
         CK(cudaEventRecord(ctx->ev_t1, ctx->st));

@@ -1,4 +1,4 @@
-// Reduced camera system S x = rhs: tile-sparse storage + level-scheduled tile LDL' (no pivoting) + triangular solves.
+// Reduced camera system S x = rhs: tile-sparse storage + level-scheduled, left-looking tile LDL' (no pivoting) + sweeps.
 //
 // S (DC nA square, symmetric) is cut into ST x ST tiles aligned to camera blocks (ST = 72 = 12 affine or 8 pinhole cameras).
 // Camera tiles are renumbered by a fill-reducing / parallelism-exposing order computed on the host (nested dissection by
@@ -8,16 +8,15 @@
 // (LDLFactorizations.ldl_factorize!, src/linearsolver.jl:29), so indefinite systems (Triggs-corrected robust Hessians)
 // follow the same trajectory instead of failing over.
 //
-// Tile columns are grouped into levels of the elimination tree; all columns of a level are independent and are processed
-// by the same launches (task lists are built at prepare time):
-//   ldl_diag_kernel    T_JJ = L_JJ D_J L_JJ'                      (1 CTA per column of the level)
-//   ldl_trsm_kernel    L_IJ = T_IJ L_JJ^-T D_J^-1  for I > J      (1 CTA per tile)
-//   ldl_update_kernel  T_{I1,I2} -= L_{I1,J} D_J L_{I2,J}'        (1 CTA per pair; tasks hitting the same target tile are
-//                                                                 split into rounds = separate launches, fixed order)
-// then ldl_inv_kernel (all diagonal tiles) and the level-scheduled sweeps ldl_fwd_kernel / ldl_bwd_kernel.
+// Tile columns are grouped into levels of the elimination tree; per level two launches (task lists built at prepare time):
+//   ldl_tile_kernel<true>   one CTA per column J of the level:  T_JJ -= sum_K L_JK D_K L_JK'  (left-looking gather of every
+//                           update, accumulated in registers), then in-register LDL' of the 72 x 72 tile together with
+//                           Linv_J = L_JJ^-1 (the row operations applied to an identity), then the forward substitution of the
+//                           right-hand side  y_J = Linv_J (b_J - sum_{K<J} L_JK y_K)
+//   ldl_tile_kernel<false>  one CTA per tile (I, J), I > J:  T_IJ -= sum_K L_IK D_K L_JK';  L_IJ = T_IJ Linv_J' D_J^-1  (a GEMM)
+// then the backward sweep ldl_bwd_kernel, one launch per level in reverse order.
 //
-// Thread layout of the tile kernels: 256 threads as 16 x 16; thread (ty, tx) owns the 5 x 5 elements
-// (ty + 16 a, tx + 16 b) of a 72 x 72 tile in registers (a = 4 exists only for ty < 8, likewise b for tx).
+// Thread layout of the tile kernels: 144 threads as 12 x 12; thread (ty, tx) owns the 6 x 6 block (6 ty + a, 6 tx + b).
 #pragma once
 #include "common.cuh"
 
@@ -25,9 +24,9 @@ namespace nlls {
 
 constexpr int ST = 72;
 constexpr int ST2 = ST * ST;
-constexpr int RED_THREADS = 256;
-constexpr int LDT = ST + 1;   // padded leading dimension of smem tiles
-constexpr int RB = 5;         // register block edge: ceil(72 / 16)
+constexpr int TB = 6;                 // register block edge
+constexpr int TG = ST / TB;           // 12 x 12 thread grid
+constexpr int RED_THREADS = TG * TG;  // 144
 
 struct RedSolveLists {        // device pointers for the triangular sweeps
     const int* diag_tile;     // [NT] tile id of (J, J), permuted numbering
@@ -39,379 +38,280 @@ struct RedSolveLists {        // device pointers for the triangular sweeps
     const int* col_row;
 };
 
-constexpr int NB = 8;            // panel width of the blocked tile algorithms
-constexpr int LDP = NB + 1;      // padded leading dimension of panel buffers
+struct RedTask {              // one CTA of ldl_tile_kernel
+    int tile;                 // target tile id
+    int dtile;                // diagonal tile of the target's column J
+    int col;                  // J (permuted numbering)
+    int upd0, upd1;           // range of its updates in the RedUpd array
+    int pad0, pad1, pad2;
+};
+struct RedUpd { int a, b, dk, pad; };   // tiles L_IK, L_JK and the diagonal tile of K
 
-// ---------------------------------------------------------------------------------------------------
-// In-place LDL' of diagonal tiles, blocked by panels of NB columns.  On exit the strict lower triangle holds L (unit
-// diagonal implied) and the diagonal holds D; the upper triangle is not referenced.
-// Per panel: (1) owners publish the panel, (2) 8 lanes factor the 8 x 8 diagonal block, (3) one thread per row below it
-// solves its row of L21, (4) the panel is written out, (5) all threads apply the rank-8 update to their registers.
-// ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(RED_THREADS) ldl_diag_kernel(double* __restrict__ S, const int* __restrict__ tasks) {
-    __shared__ double Up[ST * LDP];   // panel of A, then U = L D
-    __shared__ double Lp[ST * LDP];   // panel of L
-    __shared__ double dd[NB], rdd[NB], col[NB];
-    double* T = S + (size_t)tasks[blockIdx.x] * ST2;
-    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-    double R[RB][RB];
+// reciprocal to ~1 ulp: MUFU seed + two Newton steps (the IEEE division is ~3x longer and sits on the 72-pivot critical path)
+__device__ __forceinline__ double rcp_fast(double d) {
+    double x;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(d));
+    double e = fma(-d, x, 1.0);
+    x = fma(x, e, x);
+    e = fma(-d, x, 1.0);
+    x = fma(x, e, x);
+    return x;
+}
+
+__device__ __forceinline__ void cp_async16(void* sdst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(sdst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// whole tile (41 472 B, contiguous) global -> shared, 16 bytes per request
+__device__ __forceinline__ void tile_to_smem(double* sdst, const double* gsrc) {
+    for (int q = threadIdx.x; q < ST2 / 2; q += RED_THREADS) cp_async16(sdst + 2 * q, gsrc + 2 * q);
+}
+
+struct RedSmem {
+    static constexpr size_t bytes = (size_t)(3 * ST2 + 8 * ST) * sizeof(double);
+};
+
+template <bool DIAG>
+__global__ void __launch_bounds__(RED_THREADS) ldl_tile_kernel(double* __restrict__ S, double* __restrict__ Linv, const RedTask* __restrict__ tasks,
+                                                               const RedUpd* __restrict__ upds, RedSolveLists lists, double* __restrict__ xp) {
+    extern __shared__ __align__(16) double sm[];
+    double* As = sm;                  // [k][i]  (a tile as stored: column-major)
+    double* Bs = sm + ST2;
+    double* Cs = sm + 2 * ST2;        // Linv_J (off-diagonal tasks) / partial sums (diagonal tasks)
+    double* Ds = sm + 3 * ST2;        // [ST] diagonal of D_K / D_J
+    double* colA = Ds + ST;           // [2][ST] published column of A
+    double* rowM = colA + 2 * ST;     // [2][ST] published row of M
+    double* vs = rowM + 2 * ST;       // [ST] right-hand side segment
+    const int tid = threadIdx.x, tx = tid % TG, ty = tid / TG;
+    const RedTask tk = tasks[blockIdx.x];
+    double* T = S + (size_t)tk.tile * ST2;
+    const bool work = DIAG ? (ty >= tx) : true;
+
+    if (!DIAG) tile_to_smem(Cs, Linv + (size_t)tk.col * ST2);   // ready since the previous launch; lands while the updates run
+
+    // ---- forward substitution, first half: v = b_J - sum_{K<J} L_JK y_K (rows coalesced, k split in two halves)
+    if (DIAG) {
+        const int r = tid % ST, h = tid / ST;
+        double acc = 0.0;
+        for (int q = lists.rowptr[tk.col]; q < lists.rowptr[tk.col + 1]; ++q) {
+            const double* M = S + (size_t)lists.row_tile[q] * ST2 + r + (size_t)ST * (ST / 2) * h;
+            const double* y = xp + (size_t)lists.row_col[q] * ST + (ST / 2) * h;
+            double m[ST / 2];
 #pragma unroll
-    for (int a = 0; a < RB; ++a)
+            for (int k = 0; k < ST / 2; ++k) m[k] = M[(size_t)ST * k];
 #pragma unroll
-        for (int b = 0; b < RB; ++b) {
-            const int i = ty + 16 * a, k = tx + 16 * b;
-            R[a][b] = (i < ST && k < ST && i >= k) ? T[i + ST * k] : 0.0;
+            for (int k = 0; k < ST / 2; ++k) acc = fma(m[k], y[k], acc);
         }
-    for (int j0 = 0; j0 < ST; j0 += NB) {
-        const int jb = j0 >> 4, jx0 = j0 & 15;
-        // (1) owners of columns j0 .. j0+7 publish rows >= j0
-        if (tx >= jx0 && tx < jx0 + NB) {
-            const int t = tx - jx0;
+        Cs[h * ST + r] = acc;
+    }
+
+    // ---- target block into registers
+    double R[TB][TB];
 #pragma unroll
-            for (int b = 0; b < RB; ++b)
-                if (b == jb) {
+    for (int b = 0; b < TB; ++b) {
+        const double2* src = reinterpret_cast<const double2*>(T + (size_t)ST * (TB * tx + b) + TB * ty);
 #pragma unroll
-                    for (int a = 0; a < RB; ++a) { const int i = ty + 16 * a; if (i >= j0 && i < ST) Up[i * LDP + t] = R[a][b]; }
-                }
-        }
+        for (int a = 0; a < TB / 2; ++a) { const double2 v = work ? src[a] : make_double2(0.0, 0.0); R[2 * a][b] = v.x; R[2 * a + 1][b] = v.y; }
+    }
+
+    // ---- left-looking updates:  R -= (L_IK D_K) L_JK'
+    for (int u = tk.upd0; u < tk.upd1; ++u) {
+        const RedUpd up = upds[u];
+        __syncthreads();                                   // previous As / Bs / Ds readers are done
+        tile_to_smem(As, S + (size_t)up.a * ST2);
+        if (up.b != up.a) tile_to_smem(Bs, S + (size_t)up.b * ST2);
+        if (tid < ST) Ds[tid] = S[(size_t)up.dk * ST2 + (size_t)(ST + 1) * tid];
+        cp_async_wait_all();
         __syncthreads();
-        // (2) 8 x 8 diagonal block: lane r owns row r
-        if (tid < NB) {
-            const int r = tid;
-            double A[NB];
+        const double* Bt = (up.b != up.a) ? Bs : As;
+        if (work) {
+#pragma unroll 4
+            for (int k = 0; k < ST; ++k) {
+                const double dk = Ds[k];
+                const double2* ap = reinterpret_cast<const double2*>(As + k * ST + TB * ty);
+                const double2* bp = reinterpret_cast<const double2*>(Bt + k * ST + TB * tx);
+                double av[TB], bv[TB];
 #pragma unroll
-            for (int c = 0; c < NB; ++c) A[c] = (c <= r) ? Up[(j0 + r) * LDP + c] : 0.0;
+                for (int a = 0; a < TB / 2; ++a) { const double2 v = ap[a]; av[2 * a] = v.x * dk; av[2 * a + 1] = v.y * dk; }
 #pragma unroll
-            for (int t = 0; t < NB; ++t) {
-                if (r >= t) col[r] = A[t];
-                __syncwarp(0xffu);
-                const double d = col[t];
-                if (r > t) {
-                    const double l = A[t] / d;
+                for (int b = 0; b < TB / 2; ++b) { const double2 v = bp[b]; bv[2 * b] = v.x; bv[2 * b + 1] = v.y; }
 #pragma unroll
-                    for (int c = t + 1; c < NB; ++c) if (c <= r) A[c] = fma(-l, col[c], A[c]);
-                    A[t] = l;
-                }
-                __syncwarp(0xffu);
+                for (int a = 0; a < TB; ++a)
+#pragma unroll
+                    for (int b = 0; b < TB; ++b) R[a][b] = fma(-av[a], bv[b], R[a][b]);
             }
-#pragma unroll
-            for (int c = 0; c < NB; ++c) if (c < r) Lp[(j0 + r) * LDP + c] = A[c];
-            dd[r] = A[r];
-            rdd[r] = 1.0 / A[r];
         }
+    }
+
+    if constexpr (!DIAG) {
+        // ---- L_IJ = R Linv_J' D_J^-1 :  X[i][c] = sum_{k <= c} R[i][k] Linv[c][k] / d_c
         __syncthreads();
-        // (3) rows below the block: U21 L11' = A21, L21 = U21 D11^-1
-        if (tid < ST && tid >= j0 + NB) {
-            const int i = tid;
-            double uu[NB];
 #pragma unroll
-            for (int t = 0; t < NB; ++t) {
-                double v = Up[i * LDP + t];
+        for (int b = 0; b < TB; ++b) {
+            double2* dst = reinterpret_cast<double2*>(As + (TB * tx + b) * ST + TB * ty);
 #pragma unroll
-                for (int q = 0; q < t; ++q) v = fma(-uu[q], Lp[(j0 + t) * LDP + q], v);
-                uu[t] = v;
+            for (int a = 0; a < TB / 2; ++a) dst[a] = make_double2(R[2 * a][b], R[2 * a + 1][b]);
+        }
+        if (tid < ST) Ds[tid] = S[(size_t)tk.dtile * ST2 + (size_t)(ST + 1) * tid];
+        cp_async_wait_all();
+        __syncthreads();
+        double X[TB][TB];
+#pragma unroll
+        for (int a = 0; a < TB; ++a)
+#pragma unroll
+            for (int b = 0; b < TB; ++b) X[a][b] = 0.0;
+        const int kend = TB * tx + TB;                     // Linv is lower triangular: Linv[c][k] = 0 for k > c
+#pragma unroll 4
+        for (int k = 0; k < kend; ++k) {
+            const double2* ap = reinterpret_cast<const double2*>(As + k * ST + TB * ty);
+            const double2* bp = reinterpret_cast<const double2*>(Cs + k * ST + TB * tx);
+            double av[TB], bv[TB];
+#pragma unroll
+            for (int a = 0; a < TB / 2; ++a) { const double2 v = ap[a]; av[2 * a] = v.x; av[2 * a + 1] = v.y; }
+#pragma unroll
+            for (int b = 0; b < TB / 2; ++b) { const double2 v = bp[b]; bv[2 * b] = v.x; bv[2 * b + 1] = v.y; }
+#pragma unroll
+            for (int a = 0; a < TB; ++a)
+#pragma unroll
+                for (int b = 0; b < TB; ++b) X[a][b] = fma(av[a], bv[b], X[a][b]);
+        }
+#pragma unroll
+        for (int b = 0; b < TB; ++b) {
+            const double rd = rcp_fast(Ds[TB * tx + b]);
+            double2* dst = reinterpret_cast<double2*>(T + (size_t)ST * (TB * tx + b) + TB * ty);
+#pragma unroll
+            for (int a = 0; a < TB / 2; ++a) dst[a] = make_double2(X[2 * a][b] * rd, X[2 * a + 1][b] * rd);
+        }
+    } else {
+    // ---- diagonal tile: in-register LDL' with the row operations mirrored on M (-> M = L^-1).  One barrier per pivot:
+    // the owners of column j / row j publish them (double buffered), everybody below applies the rank-1 update.
+    double M[TB][TB];
+#pragma unroll
+    for (int a = 0; a < TB; ++a)
+#pragma unroll
+        for (int b = 0; b < TB; ++b) M[a][b] = (ty == tx && a == b) ? 1.0 : 0.0;
+    __syncthreads();
+    if (tid < ST) vs[tid] = xp[(size_t)tk.col * ST + tid] - (Cs[tid] + Cs[ST + tid]);
+    for (int jb = 0; jb < TG; ++jb) {
+#pragma unroll
+        for (int jj = 0; jj < TB; ++jj) {
+            const int j = TB * jb + jj, buf = j & 1;
+            if (tx == jb && ty >= jb) {
+#pragma unroll
+                for (int a = 0; a < TB; ++a) colA[buf * ST + TB * ty + a] = R[a][jj];
             }
+            if (ty == jb && tx <= jb) {
 #pragma unroll
-            for (int t = 0; t < NB; ++t) { Up[i * LDP + t] = uu[t]; Lp[i * LDP + t] = uu[t] * rdd[t]; }
-        }
-        __syncthreads();
-        // (4) write the finished panel columns
-        for (int e = tid; e < ST * NB; e += RED_THREADS) {
-            const int i = e % ST, t = e / ST, k = j0 + t;
-            if (i > k) T[i + ST * k] = Lp[i * LDP + t];
-            else if (i == k) T[i + ST * k] = dd[t];
-        }
-        // (5) trailing update A22 -= L21 U21'
-        if (j0 + NB < ST) {
+                for (int b = 0; b < TB; ++b) rowM[buf * ST + TB * tx + b] = M[jj][b];
+            }
+            __syncthreads();
+            if (ty >= jb && tx <= ty) {
+                const double rd = rcp_fast(colA[buf * ST + j]);
+                double li[TB];
 #pragma unroll
-            for (int a = 0; a < RB; ++a) {
-                const int i = ty + 16 * a;
-                if (16 * a + 15 < j0 + NB || i >= ST) continue;
-                double lv[NB];
+                for (int a = 0; a < TB; ++a) li[a] = (TB * ty + a > j) ? colA[buf * ST + TB * ty + a] * rd : 0.0;
+                if (tx >= jb) {
 #pragma unroll
-                for (int t = 0; t < NB; ++t) lv[t] = (i >= j0 + NB) ? Lp[i * LDP + t] : 0.0;
+                    for (int b = 0; b < TB; ++b) {
+                        const double ck = (TB * tx + b > j) ? colA[buf * ST + TB * tx + b] : 0.0;
 #pragma unroll
-                for (int b = 0; b < RB; ++b) {
-                    const int k = tx + 16 * b;
-                    if (b > a || 16 * b + 15 < j0 + NB) continue;
-                    if (k >= j0 + NB && k <= i) {
-                        double acc = R[a][b];
+                        for (int a = 0; a < TB; ++a) R[a][b] = fma(-li[a], ck, R[a][b]);
+                    }
+                    if (tx == jb) {
 #pragma unroll
-                        for (int t = 0; t < NB; ++t) acc = fma(-lv[t], Up[k * LDP + t], acc);
-                        R[a][b] = acc;
+                        for (int a = 0; a < TB; ++a) if (TB * ty + a > j) R[a][jj] = li[a];
+                    }
+                }
+                if (tx <= jb) {
+#pragma unroll
+                    for (int b = 0; b < TB; ++b) {
+                        const double mr = rowM[buf * ST + TB * tx + b];
+#pragma unroll
+                        for (int a = 0; a < TB; ++a) M[a][b] = fma(-li[a], mr, M[a][b]);
                     }
                 }
             }
         }
-        __syncthreads();
     }
-}
-
-// L_IJ = T_IJ L_JJ^-T D_J^-1, blocked: per panel the final columns X[:, P] = (X[:, P] raw) L11^-T (one thread per row), then
-// all threads apply X[:, >P] -= X[:, P] L[>P, P]'.  Finally column k is scaled by 1 / D_k.
-__global__ void __launch_bounds__(RED_THREADS) ldl_trsm_kernel(double* __restrict__ S, const int2* __restrict__ tasks) {
-    extern __shared__ double sm[];
-    double* L = sm;                  // L_JJ: L[k * LDT + j] (strict lower) with D on the diagonal
-    double* Xp = sm + ST * LDT;      // [ST][LDP] panel of X
-    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-    const int2 tk = tasks[blockIdx.x];
-    double* T = S + (size_t)tk.x * ST2;
-    const double* D = S + (size_t)tk.y * ST2;
-    for (int e = tid; e < ST2; e += RED_THREADS) { const int r = e % ST, c = e / ST; L[r * LDT + c] = D[e]; }
-    double R[RB][RB];
+    // ---- write L (strict lower) + D (diagonal) and Linv; forward substitution, second half: y_J = Linv_J v
+    double* Li = Linv + (size_t)tk.col * ST2;
+    if (ty >= tx) {
 #pragma unroll
-    for (int a = 0; a < RB; ++a)
+        for (int b = 0; b < TB; ++b) {
+            double2* dst = reinterpret_cast<double2*>(T + (size_t)ST * (TB * tx + b) + TB * ty);
+            double2* dsi = reinterpret_cast<double2*>(Li + (size_t)ST * (TB * tx + b) + TB * ty);
 #pragma unroll
-        for (int b = 0; b < RB; ++b) {
-            const int r = ty + 16 * a, c = tx + 16 * b;
-            R[a][b] = (r < ST && c < ST) ? T[r + ST * c] : 0.0;
+            for (int a = 0; a < TB / 2; ++a) { dst[a] = make_double2(R[2 * a][b], R[2 * a + 1][b]); dsi[a] = make_double2(M[2 * a][b], M[2 * a + 1][b]); }
         }
-    __syncthreads();
-    for (int j0 = 0; j0 < ST; j0 += NB) {
-        const int jb = j0 >> 4, jx0 = j0 & 15;
-        const bool owner = tx >= jx0 && tx < jx0 + NB;
-        if (owner) {
-            const int t = tx - jx0;
 #pragma unroll
-            for (int b = 0; b < RB; ++b)
-                if (b == jb) {
+        for (int a = 0; a < TB; ++a) {
+            double s = 0.0;
 #pragma unroll
-                    for (int a = 0; a < RB; ++a) { const int r = ty + 16 * a; if (r < ST) Xp[r * LDP + t] = R[a][b]; }
-                }
+            for (int b = 0; b < TB; ++b) s = fma(M[a][b], vs[TB * tx + b], s);
+            As[tx * ST + TB * ty + a] = s;
         }
-        __syncthreads();
-        if (tid < ST) {              // row tid: x_t = raw_t - sum_{q<t} x_q L[j0+t][j0+q]
-            double x[NB];
-#pragma unroll
-            for (int t = 0; t < NB; ++t) {
-                double v = Xp[tid * LDP + t];
-#pragma unroll
-                for (int q = 0; q < t; ++q) v = fma(-x[q], L[(j0 + t) * LDT + j0 + q], v);
-                x[t] = v;
-            }
-#pragma unroll
-            for (int t = 0; t < NB; ++t) Xp[tid * LDP + t] = x[t];
-        }
-        __syncthreads();
-        if (owner) {                 // owners take the final panel values back
-            const int t = tx - jx0;
-#pragma unroll
-            for (int b = 0; b < RB; ++b)
-                if (b == jb) {
-#pragma unroll
-                    for (int a = 0; a < RB; ++a) { const int r = ty + 16 * a; if (r < ST) R[a][b] = Xp[r * LDP + t]; }
-                }
-        }
-        if (j0 + NB < ST) {          // X[:, k] -= sum_t X[:, j0+t] L[k][j0+t] for k >= j0 + NB
-#pragma unroll
-            for (int a = 0; a < RB; ++a) {
-                const int r = ty + 16 * a;
-                if (r >= ST) continue;
-                double xv[NB];
-#pragma unroll
-                for (int t = 0; t < NB; ++t) xv[t] = Xp[r * LDP + t];
-#pragma unroll
-                for (int b = 0; b < RB; ++b) {
-                    const int k = tx + 16 * b;
-                    if (16 * b + 15 < j0 + NB) continue;
-                    if (k >= j0 + NB && k < ST) {
-                        double acc = R[a][b];
-#pragma unroll
-                        for (int t = 0; t < NB; ++t) acc = fma(-xv[t], L[k * LDT + j0 + t], acc);
-                        R[a][b] = acc;
-                    }
-                }
-            }
-        }
-        __syncthreads();
-    }
-#pragma unroll
-    for (int a = 0; a < RB; ++a)
-#pragma unroll
-        for (int b = 0; b < RB; ++b) {
-            const int r = ty + 16 * a, c = tx + 16 * b;
-            if (r < ST && c < ST) T[r + ST * c] = R[a][b] / L[c * LDT + c];
-        }
-}
-
-// T_{I1,I2} -= (L_{I1,J} D_J) L_{I2,J}'
-__global__ void __launch_bounds__(RED_THREADS) ldl_update_kernel(double* __restrict__ S, const int4* __restrict__ tasks) {
-    extern __shared__ double sm[];
-    double* A = sm;                 // (L_{I1,J} D)  A[k * LDT + r]
-    double* B = sm + ST * LDT;      // L_{I2,J}      B[k * LDT + c]
-    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-    const int4 tk = tasks[blockIdx.x];
-    const double* Ta = S + (size_t)tk.x * ST2;
-    const double* Tb = S + (size_t)tk.y * ST2;
-    double* Tc = S + (size_t)tk.z * ST2;
-    const double* D = S + (size_t)tk.w * ST2;
-    for (int e = tid; e < ST2; e += RED_THREADS) {
-        const int r = e % ST, k = e / ST;
-        A[k * LDT + r] = Ta[e] * D[k * ST + k];
-        B[k * LDT + r] = Tb[e];
     }
     __syncthreads();
-    double acc[RB][RB];
-#pragma unroll
-    for (int a = 0; a < RB; ++a)
-#pragma unroll
-        for (int b = 0; b < RB; ++b) acc[a][b] = 0.0;
-    for (int k = 0; k < ST; ++k) {
-        double av[RB], bv[RB];
-#pragma unroll
-        for (int a = 0; a < RB; ++a) { const int r = ty + 16 * a; av[a] = (r < ST) ? A[k * LDT + r] : 0.0; }
-#pragma unroll
-        for (int b = 0; b < RB; ++b) { const int c = tx + 16 * b; bv[b] = (c < ST) ? B[k * LDT + c] : 0.0; }
-#pragma unroll
-        for (int a = 0; a < RB; ++a)
-#pragma unroll
-            for (int b = 0; b < RB; ++b) acc[a][b] = fma(av[a], bv[b], acc[a][b]);
+    if (tid < ST) {
+        double s = 0.0;
+        for (int c = 0; c <= tid / TB; ++c) s += As[c * ST + tid];
+        xp[(size_t)tk.col * ST + tid] = s;
     }
-#pragma unroll
-    for (int b = 0; b < RB; ++b)
-#pragma unroll
-        for (int a = 0; a < RB; ++a) {
-            const int r = ty + 16 * a, c = tx + 16 * b;
-            if (r < ST && c < ST) Tc[r + ST * c] -= acc[a][b];
-        }
-}
-
-// Linv_J = L_JJ^-1 (unit lower triangular, explicit ones on the diagonal, zeros above) for every diagonal tile, in parallel
-// after the factorisation; turns the triangular sweeps of the solve into mat-vecs.  Blocked forward substitution of
-// L X = I by row panels: X[P, :] = L11^-1 X[P, :] (one thread per column), then X[>P, :] -= L[>P, P] X[P, :].
-__global__ void __launch_bounds__(RED_THREADS) ldl_inv_kernel(const double* __restrict__ S, const int* __restrict__ diag_tile, double* __restrict__ Linv) {
-    extern __shared__ double sm[];
-    double* L = sm;                       // L[i * LDT + j]
-    double* Xp = sm + ST * LDT;           // [NB][LDT] row panel of X
-    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4, J = blockIdx.x;
-    const double* T = S + (size_t)diag_tile[J] * ST2;
-    for (int e = tid; e < ST2; e += RED_THREADS) { const int r = e % ST, c = e / ST; L[r * LDT + c] = T[e]; }
-    double R[RB][RB];
-#pragma unroll
-    for (int a = 0; a < RB; ++a)
-#pragma unroll
-        for (int b = 0; b < RB; ++b) R[a][b] = (ty + 16 * a == tx + 16 * b) ? 1.0 : 0.0;
-    __syncthreads();
-    for (int j0 = 0; j0 < ST; j0 += NB) {
-        const int ja = j0 >> 4, jy0 = j0 & 15;
-        const bool owner = ty >= jy0 && ty < jy0 + NB;
-        if (owner) {
-            const int t = ty - jy0;
-#pragma unroll
-            for (int a = 0; a < RB; ++a)
-                if (a == ja) {
-#pragma unroll
-                    for (int b = 0; b < RB; ++b) { const int k = tx + 16 * b; if (k < ST) Xp[t * LDT + k] = R[a][b]; }
-                }
-        }
-        __syncthreads();
-        if (tid < ST) {              // column tid: x_t = raw_t - sum_{q<t} L[j0+t][j0+q] x_q
-            double x[NB];
-#pragma unroll
-            for (int t = 0; t < NB; ++t) {
-                double v = Xp[t * LDT + tid];
-#pragma unroll
-                for (int q = 0; q < t; ++q) v = fma(-L[(j0 + t) * LDT + j0 + q], x[q], v);
-                x[t] = v;
-            }
-#pragma unroll
-            for (int t = 0; t < NB; ++t) Xp[t * LDT + tid] = x[t];
-        }
-        __syncthreads();
-        if (owner) {
-            const int t = ty - jy0;
-#pragma unroll
-            for (int a = 0; a < RB; ++a)
-                if (a == ja) {
-#pragma unroll
-                    for (int b = 0; b < RB; ++b) { const int k = tx + 16 * b; if (k < ST) R[a][b] = Xp[t * LDT + k]; }
-                }
-        }
-        if (j0 + NB < ST) {          // X[i, :] -= sum_t L[i][j0+t] X[j0+t, :] for i >= j0 + NB
-#pragma unroll
-            for (int a = 0; a < RB; ++a) {
-                const int i = ty + 16 * a;
-                if (16 * a + 15 < j0 + NB || i >= ST || i < j0 + NB) continue;
-                double lv[NB];
-#pragma unroll
-                for (int t = 0; t < NB; ++t) lv[t] = L[i * LDT + j0 + t];
-#pragma unroll
-                for (int b = 0; b < RB; ++b) {
-                    const int k = tx + 16 * b;
-                    if (k < ST) {
-                        double acc = R[a][b];
-#pragma unroll
-                        for (int t = 0; t < NB; ++t) acc = fma(-lv[t], Xp[t * LDT + k], acc);
-                        R[a][b] = acc;
-                    }
-                }
-            }
-        }
-        __syncthreads();
     }
-    double* out = Linv + (size_t)J * ST2;
-#pragma unroll
-    for (int a = 0; a < RB; ++a)
-#pragma unroll
-        for (int b = 0; b < RB; ++b) {
-            const int i = ty + 16 * a, k = tx + 16 * b;
-            if (i < ST && k < ST) out[i + ST * k] = R[a][b];
-        }
 }
 
 // ---------------------------------------------------------------------------------------------------
-// Triangular sweeps, one CTA per tile column of the current level ("pull" form: a CTA only writes its own x_J).
-//   forward : y_J = Linv_J (x_J - sum_{K<J} L_JK y_K)
-//   backward: x_J = Linv_J' (y_J / D_J - sum_{I>J} L_IJ' x_I)
-// 216 threads = (row, k-third); x lives in global memory (length NT*ST, permuted numbering).
+// Backward sweep, one CTA per tile column of the current level ("pull" form: a CTA only writes its own x_J):
+//   x_J = Linv_J' (y_J / D_J - sum_{I>J} L_IJ' x_I)
+// Tiles are staged in shared memory (coalesced 16-byte requests, double buffered); thread (c, half) owns column c.
 // ---------------------------------------------------------------------------------------------------
-constexpr int SOLVE_THREADS = 3 * ST;
-
-__device__ __forceinline__ double gemv_part(const double* __restrict__ M, const double* xin, int r, int seg, bool transposed) {
-    double s = 0.0;
-    if (!transposed) { for (int c = seg * 24; c < seg * 24 + 24; ++c) s = fma(M[r + ST * c], xin[c], s); }
-    else { for (int k = seg * 24; k < seg * 24 + 24; ++k) s = fma(M[k + ST * r], xin[k], s); }
-    return s;
-}
-
-__global__ void __launch_bounds__(SOLVE_THREADS) ldl_fwd_kernel(const double* __restrict__ S, const double* __restrict__ Linv, RedSolveLists t,
-                                                                const int* __restrict__ cols, double* __restrict__ x) {
-    __shared__ double xj[ST], xk[ST], part[SOLVE_THREADS];
-    const int tid = threadIdx.x, r = tid % ST, seg = tid / ST;
+constexpr size_t BWD_SMEM = (size_t)(2 * ST2 + 5 * ST) * sizeof(double);
+__global__ void __launch_bounds__(RED_THREADS) ldl_bwd_kernel(const double* __restrict__ S, const double* __restrict__ Linv, RedSolveLists t,
+                                                              const int* __restrict__ cols, double* __restrict__ x) {
+    extern __shared__ __align__(16) double sm[];
+    double* Ts = sm;                 // [2][ST2]
+    double* xi = sm + 2 * ST2;       // [2][ST]
+    double* part = xi + 2 * ST;      // [2][ST]
+    double* w = part + 2 * ST;       // [ST]
+    const int tid = threadIdx.x, c = tid % ST, h = tid / ST;
     const int J = cols[blockIdx.x];
-    if (tid < ST) xj[tid] = x[(size_t)J * ST + tid];
-    for (int q = t.rowptr[J]; q < t.rowptr[J + 1]; ++q) {
+    const int q0 = t.colptr[J], q1 = t.colptr[J + 1];
+    double acc = 0.0;
+    if (q0 < q1) {
+        tile_to_smem(Ts, S + (size_t)t.col_tile[q0] * ST2);
+        if (tid < ST) xi[tid] = x[(size_t)t.col_row[q0] * ST + tid];
+    }
+    for (int q = q0; q < q1; ++q) {
+        const int st = (q - q0) & 1;
+        cp_async_wait_all();
         __syncthreads();
-        if (tid < ST) xk[tid] = x[(size_t)t.row_col[q] * ST + tid];
-        __syncthreads();
-        part[tid] = gemv_part(S + (size_t)t.row_tile[q] * ST2, xk, r, seg, false);
-        __syncthreads();
-        if (tid < ST) xj[tid] -= (part[tid] + part[tid + ST]) + part[tid + 2 * ST];
+        if (q + 1 < q1) {
+            tile_to_smem(Ts + (st ^ 1) * ST2, S + (size_t)t.col_tile[q + 1] * ST2);
+            if (tid < ST) xi[(st ^ 1) * ST + tid] = x[(size_t)t.col_row[q + 1] * ST + tid];
+        }
+        const double* M = Ts + st * ST2 + (size_t)ST * c + (ST / 2) * h;
+        const double* xv = xi + st * ST + (ST / 2) * h;
+#pragma unroll 12
+        for (int i = 0; i < ST / 2; ++i) acc = fma(M[i], xv[i], acc);
     }
     __syncthreads();
-    part[tid] = gemv_part(Linv + (size_t)J * ST2, xj, r, seg, false);
+    tile_to_smem(Ts, Linv + (size_t)J * ST2);
+    part[h * ST + c] = acc;
+    cp_async_wait_all();
     __syncthreads();
-    if (tid < ST) x[(size_t)J * ST + tid] = (part[tid] + part[tid + ST]) + part[tid + 2 * ST];
-}
-
-__global__ void __launch_bounds__(SOLVE_THREADS) ldl_bwd_kernel(const double* __restrict__ S, const double* __restrict__ Linv, RedSolveLists t,
-                                                                const int* __restrict__ cols, double* __restrict__ x) {
-    __shared__ double xj[ST], xi[ST], part[SOLVE_THREADS];
-    const int tid = threadIdx.x, r = tid % ST, seg = tid / ST;
-    const int J = cols[blockIdx.x];
-    if (tid < ST) xj[tid] = x[(size_t)J * ST + tid] / S[(size_t)t.diag_tile[J] * ST2 + tid + ST * tid];
-    for (int q = t.colptr[J]; q < t.colptr[J + 1]; ++q) {
-        __syncthreads();
-        if (tid < ST) xi[tid] = x[(size_t)t.col_row[q] * ST + tid];
-        __syncthreads();
-        part[tid] = gemv_part(S + (size_t)t.col_tile[q] * ST2, xi, r, seg, true);
-        __syncthreads();
-        if (tid < ST) xj[tid] -= (part[tid] + part[tid + ST]) + part[tid + 2 * ST];
+    if (tid < ST) w[tid] = x[(size_t)J * ST + tid] / S[(size_t)t.diag_tile[J] * ST2 + (size_t)(ST + 1) * tid] - (part[tid] + part[ST + tid]);
+    __syncthreads();
+    {   // x_J[c] = sum_{i >= c} Linv[i][c] w[i]
+        const double* M = Ts + (size_t)ST * c + (ST / 2) * h;
+        const double* wv = w + (ST / 2) * h;
+        double s = 0.0;
+#pragma unroll 12
+        for (int i = 0; i < ST / 2; ++i) s = fma(((ST / 2) * h + i >= c) ? M[i] : 0.0, wv[i], s);
+        part[h * ST + c] = s;
     }
     __syncthreads();
-    part[tid] = gemv_part(Linv + (size_t)J * ST2, xj, r, seg, true);
-    __syncthreads();
-    if (tid < ST) x[(size_t)J * ST + tid] = (part[tid] + part[tid + ST]) + part[tid + 2 * ST];
+    if (tid < ST) x[(size_t)J * ST + tid] = part[tid] + part[ST + tid];
 }
 
 // natural <-> permuted tile numbering of the right-hand side / solution

@@ -14,6 +14,6 @@ ctx.lm_begin(pkg.NLLSOptions(maxiters=100, maxtime=1e5).c())
 for _ in range(2):
     info = ctx.lm_iterate(); ctx.lm_advance(info.cost, 0)
 out = {}
-for name in ["LINEARIZE", "LIN_POINT", "LIN_CAM", "COST", "SCHUR", "SOLVE_REDUCED", "BACKSUB", "TRY"]:
+for name in ["LINEARIZE", "LIN_POINT", "LIN_CAM", "COST", "SCHUR", "SOLVE_REDUCED", "BACKSUB", "TRY", "MEMSET_H", "LIN_POINT"]:
     out[name] = round(ctx.time_kernels(getattr(capi, "TIME_" + name), reps=5, flush_l2=True), 4)
 print(wl, json.dumps(out))
