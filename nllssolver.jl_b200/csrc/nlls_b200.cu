@@ -127,13 +127,13 @@ struct nlls_ctx {
     int NT = 0;
     int64_t ntiles_alloc = 0;
     int red_levels = 0;
-    struct RedLaunch { int kind, off, cnt; };          // kind 0: diagonal tiles of a level, 1: its off-diagonal tiles
+    struct RedLaunch { int kind, off, cnt; };          // kind 0: diagonal tiles of a level, 1: its off-diagonal tiles, 2: its updates
     std::vector<RedLaunch> fact_launches;
     RedTask* d_red_tasks = nullptr;
     RedUpd* d_red_upds = nullptr;
     std::vector<std::pair<int, int>> lvl_cols;           // (offset, count) into d_lvl_cols per level
     int *d_tile_id = nullptr, *d_pos = nullptr, *d_diag_tile = nullptr, *d_diag_tile_nat = nullptr, *d_lvl_cols = nullptr;
-    int *d_rowptr = nullptr, *d_row_tile = nullptr, *d_row_col = nullptr, *d_colptr = nullptr, *d_col_tile = nullptr, *d_col_row = nullptr;
+    int *d_colptr = nullptr, *d_col_tile = nullptr, *d_col_row = nullptr;
     double *d_Linv = nullptr, *d_xp = nullptr;
     // Schur v2 plan (per-tile sorted contribution lists)
     int schur_v2 = 1;
@@ -275,8 +275,9 @@ int set_smem_attrs(nlls_ctx* ctx) {
     else if (ctx->tile_obs == 128) TRY((set_tile_attrs<R, 128>(ctx)));
     else TRY((set_tile_attrs<R, 256>(ctx)));
     CK(cudaFuncSetAttribute(schur2_kernel<R::DC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Schur2Smem<R::DC>::bytes));
-    CK(cudaFuncSetAttribute(ldl_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RedSmem::bytes));
-    CK(cudaFuncSetAttribute(ldl_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RedSmem::bytes));
+    CK(cudaFuncSetAttribute(ldl_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DIAG_SMEM));
+    CK(cudaFuncSetAttribute(ldl_off_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OFF_SMEM));
+    CK(cudaFuncSetAttribute(ldl_upd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UPD_SMEM));
     CK(cudaFuncSetAttribute(ldl_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWD_SMEM));
     return NLLS_OK;
 }
@@ -330,7 +331,7 @@ int launch_cost(nlls_ctx* ctx, int which, int slot) {
 
 RedSolveLists redlists(const nlls_ctx* c) {
     RedSolveLists t;
-    t.diag_tile = c->d_diag_tile; t.rowptr = c->d_rowptr; t.row_tile = c->d_row_tile; t.row_col = c->d_row_col;
+    t.diag_tile = c->d_diag_tile;
     t.colptr = c->d_colptr; t.col_tile = c->d_col_tile; t.col_row = c->d_col_row;
     return t;
 }
@@ -379,8 +380,9 @@ int launch_reduced_solve(nlls_ctx* ctx, bool lu) {
         const int nx = ctx->NT * ST;
         red_permute_kernel<<<(nx + 255) / 256, 256, 0, ctx->st>>>(ctx->d_rhs, ctx->d_xp, ctx->d_pos, ctx->NT, 1); ctx->launches++;
         for (const auto& l : ctx->fact_launches) {   // factorisation + forward substitution (fused into the diagonal tasks)
-            if (l.kind == 0) ldl_tile_kernel<true><<<l.cnt, RED_THREADS, RedSmem::bytes, ctx->st>>>(ctx->d_S, ctx->d_Linv, ctx->d_red_tasks + l.off, ctx->d_red_upds, t, ctx->d_xp);
-            else ldl_tile_kernel<false><<<l.cnt, RED_THREADS, RedSmem::bytes, ctx->st>>>(ctx->d_S, ctx->d_Linv, ctx->d_red_tasks + l.off, ctx->d_red_upds, t, ctx->d_xp);
+            if (l.kind == 0) ldl_diag_kernel<<<l.cnt, DIAG_THREADS, DIAG_SMEM, ctx->st>>>(ctx->d_S, ctx->d_Linv, ctx->d_red_tasks + l.off, ctx->d_xp);
+            else if (l.kind == 1) ldl_off_kernel<<<2 * l.cnt, HALF_THREADS, OFF_SMEM, ctx->st>>>(ctx->d_S, ctx->d_Linv, ctx->d_red_tasks + l.off, ctx->d_xp);
+            else ldl_upd_kernel<<<2 * l.cnt, HALF_THREADS, UPD_SMEM, ctx->st>>>(ctx->d_S, ctx->d_red_upds + l.off);
             ctx->launches++;
         }
         for (size_t l = ctx->lvl_cols.size(); l-- > 0;) {
@@ -543,7 +545,7 @@ int nlls_destroy(nlls_ctx* ctx) {
                     ctx->d_item_end, ctx->d_cam_item_start, ctx->d_cm_z, ctx->d_A[0], ctx->d_A[1], ctx->d_A[2], ctx->d_B[0], ctx->d_B[1], ctx->d_B[2],
                     ctx->d_H, ctx->d_g, ctx->d_x, ctx->d_Ainv, ctx->d_S, ctx->d_rhs, ctx->d_cost_part, ctx->d_step_part, ctx->d_cam_part, ctx->d_scal,
                     ctx->d_flush, ctx->d_work, ctx->d_info, ctx->d_ipiv, ctx->d_tile_id, ctx->d_pos, ctx->d_diag_tile, ctx->d_diag_tile_nat,
-                    ctx->d_lvl_cols, ctx->d_red_tasks, ctx->d_red_upds, ctx->d_rowptr, ctx->d_row_tile, ctx->d_row_col, ctx->d_colptr,
+                    ctx->d_lvl_cols, ctx->d_red_tasks, ctx->d_red_upds, ctx->d_colptr,
                     ctx->d_col_tile, ctx->d_col_row, ctx->d_Linv, ctx->d_xp, ctx->d_stile_pt, ctx->d_chunk_off, ctx->d_chunks, ctx->d_ents, ctx->d_tiles, ctx->d_camstat_part};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (ctx->h_scal) cudaFreeHost(ctx->h_scal);
@@ -760,7 +762,7 @@ int nlls_prepare(nlls_ctx* ctx) {
     ctx->hlen = (int64_t)DC * DC * nA + (int64_t)WB * nobs + 9 * nB;
     ctx->nred = (int64_t)DC * nA;
     // ---- reduced camera system: tile order, tile-level symbolic factorisation, level schedule
-    std::vector<int> tile_id, pos, diag_tile, diag_tile_nat, lvl_cols_flat, rowptr, row_tile, row_col, colptr, col_tile, col_row;
+    std::vector<int> tile_id, pos, diag_tile, diag_tile_nat, lvl_cols_flat, colptr, col_tile, col_row;
     std::vector<RedTask> red_tasks;
     std::vector<RedUpd> red_upds;
     if (ctx->s_tiled) {
@@ -836,44 +838,38 @@ int nlls_prepare(nlls_ctx* ctx) {
         }
         ctx->red_levels = nlev;
         ctx->fact_launches.clear(); ctx->lvl_cols.clear();
-        // left-looking update lists: eliminating column K couples every pair (a >= b) of its rows -> tile (r[a], r[b]) gathers
-        // L_{r[a],K} D_K L_{r[b],K}' ; lists are filled in ascending K (fixed summation order)
-        std::vector<std::vector<RedUpd>> tile_upds((size_t)nt);
-        for (int K = 0; K < NT; ++K) {
-            const std::vector<int>& r = rows[(size_t)K];
-            for (size_t a = 0; a < r.size(); ++a) for (size_t b = 0; b <= a; ++b) {
-                RedUpd u; u.a = tile_id[(size_t)r[a] * NT + K]; u.b = tile_id[(size_t)r[b] * NT + K]; u.dk = diag_tile[(size_t)K]; u.pad = 0;
-                tile_upds[(size_t)tile_id[(size_t)r[a] * NT + r[b]]].push_back(u);
-            }
-        }
-        auto add_task = [&](int tile, int J2) {
-            RedTask tk; tk.tile = tile; tk.dtile = diag_tile[(size_t)J2]; tk.col = J2; tk.upd0 = (int)red_upds.size();
-            for (const RedUpd& u : tile_upds[(size_t)tile]) red_upds.push_back(u);
-            tk.upd1 = (int)red_upds.size(); tk.pad0 = tk.pad1 = tk.pad2 = 0;
-            red_tasks.push_back(tk);
-        };
         size_t nupd_total = 0;
         for (int lv = 0; lv < nlev; ++lv) {
             const int c0 = (int)lvl_cols_flat.size(), d0 = (int)red_tasks.size();
-            for (int J2 = 0; J2 < NT; ++J2) if (level[(size_t)J2] == lv) { lvl_cols_flat.push_back(J2); add_task(diag_tile[(size_t)J2], J2); }
-            const int o0 = (int)red_tasks.size();
+            for (int J2 = 0; J2 < NT; ++J2) if (level[(size_t)J2] == lv) {
+                lvl_cols_flat.push_back(J2);
+                RedTask tk; tk.tile = diag_tile[(size_t)J2]; tk.dtile = tk.tile; tk.col = J2; tk.row = J2;
+                red_tasks.push_back(tk);
+            }
+            const int o0 = (int)red_tasks.size(), u0 = (int)red_upds.size();
             for (int q = c0; q < (int)lvl_cols_flat.size(); ++q) {
                 const int J2 = lvl_cols_flat[(size_t)q];
-                for (int I : rows[(size_t)J2]) add_task(tile_id[(size_t)I * NT + J2], J2);
+                const std::vector<int>& r = rows[(size_t)J2];
+                for (int I : r) { RedTask tk; tk.tile = tile_id[(size_t)I * NT + J2]; tk.dtile = diag_tile[(size_t)J2]; tk.col = J2; tk.row = I; red_tasks.push_back(tk); }
+                // eliminating column J couples every pair (a >= b) of its rows: T_{r[a], r[b]} -= L_{r[a],J} D_J L_{r[b],J}'
+                for (size_t a = 0; a < r.size(); ++a) for (size_t b = 0; b <= a; ++b) {
+                    RedUpd u; u.a = tile_id[(size_t)r[a] * NT + J2]; u.b = tile_id[(size_t)r[b] * NT + J2]; u.dk = diag_tile[(size_t)J2];
+                    u.target = tile_id[(size_t)r[a] * NT + r[b]];
+                    red_upds.push_back(u);
+                }
             }
             ctx->lvl_cols.push_back({c0, (int)lvl_cols_flat.size() - c0});
             ctx->fact_launches.push_back({0, d0, o0 - d0});
             if ((int)red_tasks.size() > o0) ctx->fact_launches.push_back({1, o0, (int)red_tasks.size() - o0});
+            if ((int)red_upds.size() > u0) ctx->fact_launches.push_back({2, u0, (int)red_upds.size() - u0});
         }
         nupd_total = red_upds.size();
         if (getenv("NLLS_B200_VERBOSE"))
             fprintf(stderr, "[nlls] reduced system: NT=%d tiles=%d half-bandwidth=%d nd=%d levels=%d fact_launches=%zu tasks=%zu updates=%zu\n", NT, nt, w,
                     (int)use_nd, nlev, ctx->fact_launches.size(), red_tasks.size(), nupd_total);
         // block-row and block-column lists of L for the sweeps
-        rowptr.assign((size_t)NT + 1, 0); colptr.assign((size_t)NT + 1, 0);
+        colptr.assign((size_t)NT + 1, 0);
         for (int J2 = 0; J2 < NT; ++J2) {
-            for (int K = 0; K < J2; ++K) if (tile_id[(size_t)J2 * NT + K] >= 0) { row_tile.push_back(tile_id[(size_t)J2 * NT + K]); row_col.push_back(K); }
-            rowptr[(size_t)J2 + 1] = (int)row_tile.size();
             for (int I : rows[(size_t)J2]) { col_tile.push_back(tile_id[(size_t)I * NT + J2]); col_row.push_back(I); }
             colptr[(size_t)J2 + 1] = (int)col_tile.size();
         }
@@ -999,7 +995,6 @@ int nlls_prepare(nlls_ctx* ctx) {
         TRY(upload(ctx, &ctx->d_red_tasks, red_tasks)); TRY(upload(ctx, &ctx->d_red_upds, red_upds));
         CK(cudaMemsetAsync(ctx->d_Linv, 0, sizeof(double) * (size_t)ctx->NT * ST2, ctx->st));
         TRY(upload(ctx, &ctx->d_lvl_cols, lvl_cols_flat));
-        TRY(upload(ctx, &ctx->d_rowptr, rowptr)); TRY(upload(ctx, &ctx->d_row_tile, row_tile)); TRY(upload(ctx, &ctx->d_row_col, row_col));
         TRY(upload(ctx, &ctx->d_colptr, colptr)); TRY(upload(ctx, &ctx->d_col_tile, col_tile)); TRY(upload(ctx, &ctx->d_col_row, col_row));
     } else {
         TRY(dalloc(ctx, &ctx->d_S, (size_t)ctx->nred * ctx->nred)); TRY(dalloc(ctx, &ctx->d_rhs, (size_t)ctx->nred));

@@ -1,4 +1,4 @@
-// Reduced camera system S x = rhs: tile-sparse storage + level-scheduled, left-looking tile LDL' (no pivoting) + sweeps.
+// Reduced camera system S x = rhs: tile-sparse storage + level-scheduled tile LDL' (no pivoting) + sweeps.
 //
 // S (DC nA square, symmetric) is cut into ST x ST tiles aligned to camera blocks (ST = 72 = 12 affine or 8 pinhole cameras).
 // Camera tiles are renumbered by a fill-reducing / parallelism-exposing order computed on the host (nested dissection by
@@ -8,15 +8,17 @@
 // (LDLFactorizations.ldl_factorize!, src/linearsolver.jl:29), so indefinite systems (Triggs-corrected robust Hessians)
 // follow the same trajectory instead of failing over.
 //
-// Tile columns are grouped into levels of the elimination tree; per level two launches (task lists built at prepare time):
-//   ldl_tile_kernel<true>   one CTA per column J of the level:  T_JJ -= sum_K L_JK D_K L_JK'  (left-looking gather of every
-//                           update, accumulated in registers), then in-register LDL' of the 72 x 72 tile together with
-//                           Linv_J = L_JJ^-1 (the row operations applied to an identity), then the forward substitution of the
-//                           right-hand side  y_J = Linv_J (b_J - sum_{K<J} L_JK y_K)
-//   ldl_tile_kernel<false>  one CTA per tile (I, J), I > J:  T_IJ -= sum_K L_IK D_K L_JK';  L_IJ = T_IJ Linv_J' D_J^-1  (a GEMM)
+// Tile columns are grouped into levels of the elimination tree; per level three launches (task lists built at prepare time):
+//   ldl_diag_kernel  one CTA per column J of the level: in-register LDL' of the 72 x 72 tile, Linv_J = L_JJ^-1 obtained by
+//                    mirroring the row operations on an identity, and the forward substitution y_J = L_JJ^-1 b_J carried as
+//                    an extra column.  One barrier per pivot; the pivot reciprocal is computed one step ahead by its owner.
+//   ldl_off_kernel   two CTAs per tile (I, J), I > J:  L_IJ = T_IJ Linv_J' D_J^-1 (a triangular GEMM), then the right-hand
+//                    side push  b_I -= L_IJ y_J
+//   ldl_upd_kernel   two CTAs per pair (a >= b) of rows of J:  T_{ab} -= (L_aJ D_J) L_bJ'  (FP64 RED into the target tile)
 // then the backward sweep ldl_bwd_kernel, one launch per level in reverse order.
 //
-// Thread layout of the tile kernels: 144 threads as 12 x 12; thread (ty, tx) owns the 6 x 6 block (6 ty + a, 6 tx + b).
+// Measured on B200 (scripts/ubench/fp64_lat.cu): DFMA 8.4 cycles dependent / 2.07 cycles issue per warp and SM sub-partition,
+// STS+BAR+LDS handshake 60 cycles, reciprocal chain 48 cycles — the kernels below are laid out around those numbers.
 #pragma once
 #include "common.cuh"
 
@@ -25,29 +27,23 @@ namespace nlls {
 constexpr int ST = 72;
 constexpr int ST2 = ST * ST;
 constexpr int TB = 6;                 // register block edge
-constexpr int TG = ST / TB;           // 12 x 12 thread grid
-constexpr int RED_THREADS = TG * TG;  // 144
+constexpr int TG = ST / TB;           // 12 x 12 blocks per tile
+constexpr int NLB = TG * (TG + 1) / 2;  // 78 lower-triangular blocks
+constexpr int DIAG_THREADS = 224;     // 3 warps of L blocks, 3 warps of Linv blocks, 1 right-hand-side warp
+constexpr int HALF_THREADS = 96;      // off-diagonal / update kernels: 72 workers (6 x 12 blocks of half a tile)
+constexpr int RED_THREADS = 144;      // backward sweep
 
-struct RedSolveLists {        // device pointers for the triangular sweeps
+struct RedSolveLists {        // device pointers for the backward sweep
     const int* diag_tile;     // [NT] tile id of (J, J), permuted numbering
-    const int* rowptr;        // [NT + 1] tiles (J, K), K < J, of block row J
-    const int* row_tile;
-    const int* row_col;
     const int* colptr;        // [NT + 1] tiles (I, J), I > J, of block column J
     const int* col_tile;
     const int* col_row;
 };
 
-struct RedTask {              // one CTA of ldl_tile_kernel
-    int tile;                 // target tile id
-    int dtile;                // diagonal tile of the target's column J
-    int col;                  // J (permuted numbering)
-    int upd0, upd1;           // range of its updates in the RedUpd array
-    int pad0, pad1, pad2;
-};
-struct RedUpd { int a, b, dk, pad; };   // tiles L_IK, L_JK and the diagonal tile of K
+struct RedTask { int tile, dtile, col, row; };        // diag: (tile, -, J, -); off-diagonal: (tile (I,J), diag tile of J, J, I)
+struct RedUpd { int a, b, dk, target; };              // tiles L_aJ, L_bJ, diagonal tile of J, target tile (a, b)
 
-// reciprocal to ~1 ulp: MUFU seed + two Newton steps (the IEEE division is ~3x longer and sits on the 72-pivot critical path)
+// reciprocal to ~1 ulp: MUFU seed + two Newton steps
 __device__ __forceinline__ double rcp_fast(double d) {
     double x;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(d));
@@ -64,201 +60,272 @@ __device__ __forceinline__ void cp_async16(void* sdst, const void* gsrc) {
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 // whole tile (41 472 B, contiguous) global -> shared, 16 bytes per request
+template <int NT_>
 __device__ __forceinline__ void tile_to_smem(double* sdst, const double* gsrc) {
-    for (int q = threadIdx.x; q < ST2 / 2; q += RED_THREADS) cp_async16(sdst + 2 * q, gsrc + 2 * q);
+    for (int q = threadIdx.x; q < ST2 / 2; q += NT_) cp_async16(sdst + 2 * q, gsrc + 2 * q);
 }
 
-struct RedSmem {
-    static constexpr size_t bytes = (size_t)(3 * ST2 + 8 * ST) * sizeof(double);
-};
+// ---------------------------------------------------------------------------------------------------
+// Diagonal tile.  Warp roles (warp w runs on SM sub-partition w % 4; early-finishing and late-starting warps share one):
+//   w0 = L blocks 52..77   w1 = Linv blocks 52..77   w2 = L blocks 26..51   w3 = Linv blocks 26..51
+//   w4 = L blocks 0..25    w5 = Linv blocks 0..25    w6 = right-hand side
+// L blocks are numbered by (tx, ty) ascending — block (ty, tx) is touched by pivots j < 6 tx + 6, so low numbers retire first;
+// Linv blocks by (ty, tx) ascending — block (ty, tx) is touched by pivots 6 tx <= j < 6 ty + 6.
+// ---------------------------------------------------------------------------------------------------
+constexpr size_t DIAG_SMEM = (size_t)(ST2 + 4 * ST + 4) * sizeof(double);
 
-template <bool DIAG>
-__global__ void __launch_bounds__(RED_THREADS) ldl_tile_kernel(double* __restrict__ S, double* __restrict__ Linv, const RedTask* __restrict__ tasks,
-                                                               const RedUpd* __restrict__ upds, RedSolveLists lists, double* __restrict__ xp) {
+__global__ void __launch_bounds__(DIAG_THREADS) ldl_diag_kernel(double* __restrict__ S, double* __restrict__ Linv, const RedTask* __restrict__ tasks,
+                                                                double* __restrict__ xp) {
     extern __shared__ __align__(16) double sm[];
-    double* As = sm;                  // [k][i]  (a tile as stored: column-major)
-    double* Bs = sm + ST2;
-    double* Cs = sm + 2 * ST2;        // Linv_J (off-diagonal tasks) / partial sums (diagonal tasks)
-    double* Ds = sm + 3 * ST2;        // [ST] diagonal of D_K / D_J
-    double* colA = Ds + ST;           // [2][ST] published column of A
+    double* As = sm;                  // the tile as stored (column-major)
+    double* colA = sm + ST2;          // [2][ST] published column of A
     double* rowM = colA + 2 * ST;     // [2][ST] published row of M
-    double* vs = rowM + 2 * ST;       // [ST] right-hand side segment
-    const int tid = threadIdx.x, tx = tid % TG, ty = tid / TG;
+    double* rdb = rowM + 2 * ST;      // [2] published pivot reciprocal
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const RedTask tk = tasks[blockIdx.x];
     double* T = S + (size_t)tk.tile * ST2;
-    const bool work = DIAG ? (ty >= tx) : true;
+    tile_to_smem<DIAG_THREADS>(As, T);
 
-    if (!DIAG) tile_to_smem(Cs, Linv + (size_t)tk.col * ST2);   // ready since the previous launch; lands while the updates run
+    const int kind = (w == 6) ? 2 : (w & 1);              // 0: L blocks, 1: Linv blocks, 2: right-hand side
+    const int grp = 2 - (w >> 1);                         // block group 0..2
+    const bool has_blk = kind < 2 && lane < NLB / 3;
+    int ty = 0, tx = 0;
+    if (kind < 2) {
+        int n = (NLB / 3) * grp + min(lane, NLB / 3 - 1);
+        if (kind == 0) { while (n >= TG - tx) { n -= TG - tx; ++tx; } ty = tx + n; }      // by tx, then ty
+        else { while (n >= ty + 1) { n -= ty + 1; ++ty; } tx = n; }                          // by ty, then tx
+    }
+    // last pivot that touches any block of this warp (warp-uniform early exit)
+    const int last_j = (kind == 2) ? ST - 1 : (kind == 0 ? (grp == 0 ? 17 : (grp == 1 ? 35 : ST - 1)) : (grp == 0 ? 41 : (grp == 1 ? 59 : ST - 1)));
 
-    // ---- forward substitution, first half: v = b_J - sum_{K<J} L_JK y_K (rows coalesced, k split in two halves)
-    if (DIAG) {
-        const int r = tid % ST, h = tid / ST;
-        double acc = 0.0;
-        for (int q = lists.rowptr[tk.col]; q < lists.rowptr[tk.col + 1]; ++q) {
-            const double* M = S + (size_t)lists.row_tile[q] * ST2 + r + (size_t)ST * (ST / 2) * h;
-            const double* y = xp + (size_t)lists.row_col[q] * ST + (ST / 2) * h;
-            double m[ST / 2];
+    double v[3] = {0.0, 0.0, 0.0};
+    if (kind == 2) {
 #pragma unroll
-            for (int k = 0; k < ST / 2; ++k) m[k] = M[(size_t)ST * k];
+        for (int s3 = 0; s3 < 3; ++s3) if (lane + 32 * s3 < ST) v[s3] = xp[(size_t)tk.col * ST + lane + 32 * s3];
+    }
+    cp_async_wait_all();
+    __syncthreads();
+    double B[TB][TB];                                     // L block (kind 0) or Linv block (kind 1)
 #pragma unroll
-            for (int k = 0; k < ST / 2; ++k) acc = fma(m[k], y[k], acc);
-        }
-        Cs[h * ST + r] = acc;
+    for (int a = 0; a < TB; ++a)
+#pragma unroll
+        for (int b = 0; b < TB; ++b) B[a][b] = (kind == 0) ? As[(TB * tx + b) * ST + TB * ty + a] : ((ty == tx && a == b) ? 1.0 : 0.0);
+    if (kind == 0 && has_blk && tx == 0) {
+#pragma unroll
+        for (int a = 0; a < TB; ++a) colA[TB * ty + a] = B[a][0];
+        if (ty == 0) rdb[0] = rcp_fast(B[0][0]);
+    }
+    if (kind == 1 && has_blk && ty == 0) {
+#pragma unroll
+        for (int b = 0; b < TB; ++b) rowM[TB * tx + b] = B[0][b];
     }
 
-    // ---- target block into registers
-    double R[TB][TB];
+    for (int jb = 0; jb < TG; ++jb) {
 #pragma unroll
-    for (int b = 0; b < TB; ++b) {
-        const double2* src = reinterpret_cast<const double2*>(T + (size_t)ST * (TB * tx + b) + TB * ty);
+        for (int jj = 0; jj < TB; ++jj) {
+            const int j = TB * jb + jj, buf = j & 1, nb = buf ^ 1;
+            __syncthreads();
+            if (j > last_j) continue;
+            const double rd = rdb[buf];
+            if (kind == 0) {
+                if (has_blk && tx >= jb) {
+                    double li[TB], ck[TB];
 #pragma unroll
-        for (int a = 0; a < TB / 2; ++a) { const double2 v = work ? src[a] : make_double2(0.0, 0.0); R[2 * a][b] = v.x; R[2 * a + 1][b] = v.y; }
-    }
-
-    // ---- left-looking updates:  R -= (L_IK D_K) L_JK'
-    for (int u = tk.upd0; u < tk.upd1; ++u) {
-        const RedUpd up = upds[u];
-        __syncthreads();                                   // previous As / Bs / Ds readers are done
-        tile_to_smem(As, S + (size_t)up.a * ST2);
-        if (up.b != up.a) tile_to_smem(Bs, S + (size_t)up.b * ST2);
-        if (tid < ST) Ds[tid] = S[(size_t)up.dk * ST2 + (size_t)(ST + 1) * tid];
-        cp_async_wait_all();
-        __syncthreads();
-        const double* Bt = (up.b != up.a) ? Bs : As;
-        if (work) {
-#pragma unroll 4
-            for (int k = 0; k < ST; ++k) {
-                const double dk = Ds[k];
-                const double2* ap = reinterpret_cast<const double2*>(As + k * ST + TB * ty);
-                const double2* bp = reinterpret_cast<const double2*>(Bt + k * ST + TB * tx);
-                double av[TB], bv[TB];
+                    for (int a = 0; a < TB; ++a) li[a] = (TB * ty + a > j) ? colA[buf * ST + TB * ty + a] * rd : 0.0;
 #pragma unroll
-                for (int a = 0; a < TB / 2; ++a) { const double2 v = ap[a]; av[2 * a] = v.x * dk; av[2 * a + 1] = v.y * dk; }
+                    for (int b = 0; b < TB; ++b) ck[b] = (TB * tx + b > j) ? colA[buf * ST + TB * tx + b] : 0.0;
+                    // next pivot column first: its owners publish it (and the next reciprocal) while the rest of the block updates
+                    const int jn = (jj + 1) % TB;
+                    const bool own_next = (jj + 1 < TB) ? (tx == jb) : (tx == jb + 1);
 #pragma unroll
-                for (int b = 0; b < TB / 2; ++b) { const double2 v = bp[b]; bv[2 * b] = v.x; bv[2 * b + 1] = v.y; }
+                    for (int a = 0; a < TB; ++a) B[a][jn] = fma(-li[a], ck[jn], B[a][jn]);
+                    if (own_next) {
 #pragma unroll
-                for (int a = 0; a < TB; ++a)
+                        for (int a = 0; a < TB; ++a) colA[nb * ST + TB * ty + a] = B[a][jn];
+                        if (ty == tx) rdb[nb] = rcp_fast(B[jn][jn]);
+                    }
 #pragma unroll
-                    for (int b = 0; b < TB; ++b) R[a][b] = fma(-av[a], bv[b], R[a][b]);
+                    for (int b = 0; b < TB; ++b) {
+                        if (b == jn) continue;
+#pragma unroll
+                        for (int a = 0; a < TB; ++a) B[a][b] = fma(-li[a], ck[b], B[a][b]);
+                    }
+                    if (tx == jb) {
+#pragma unroll
+                        for (int a = 0; a < TB; ++a) if (TB * ty + a > j) B[a][jj] = li[a];
+                    }
+                }
+            } else if (kind == 1) {
+                if (has_blk && tx <= jb && ty >= jb) {
+                    double li[TB];
+#pragma unroll
+                    for (int a = 0; a < TB; ++a) li[a] = (TB * ty + a > j) ? colA[buf * ST + TB * ty + a] * rd : 0.0;
+#pragma unroll
+                    for (int b = 0; b < TB; ++b) {
+                        const double mr = rowM[buf * ST + TB * tx + b];
+#pragma unroll
+                        for (int a = 0; a < TB; ++a) B[a][b] = fma(-li[a], mr, B[a][b]);
+                    }
+                    // row j + 1 of M is final now: publish it
+                    const int jn = (jj + 1) % TB;
+                    const bool own_next = (jj + 1 < TB) ? (ty == jb) : false;
+                    if (own_next) {
+#pragma unroll
+                        for (int b = 0; b < TB; ++b) rowM[nb * ST + TB * tx + b] = B[jn][b];
+                    }
+                }
+                if (has_blk && jj + 1 == TB && ty == jb + 1 && tx <= jb + 1) {   // first row of the next block row (untouched by pivots >= its own)
+#pragma unroll
+                    for (int b = 0; b < TB; ++b) rowM[nb * ST + TB * tx + b] = B[0][b];
+                }
+            } else {
+                // forward substitution carried as an extra column: v_i -= l_ij v_j
+                const int sj = j >> 5;
+                const double vsel = (sj == 0) ? v[0] : (sj == 1 ? v[1] : v[2]);
+                const double vj = __shfl_sync(0xffffffffu, vsel, j & 31);
+#pragma unroll
+                for (int s3 = 0; s3 < 3; ++s3) {
+                    const int i = lane + 32 * s3;
+                    if (i > j && i < ST) v[s3] = fma(-(colA[buf * ST + i] * rd), vj, v[s3]);
+                }
             }
         }
     }
-
-    if constexpr (!DIAG) {
-        // ---- L_IJ = R Linv_J' D_J^-1 :  X[i][c] = sum_{k <= c} R[i][k] Linv[c][k] / d_c
-        __syncthreads();
+    // ---- write L (strict lower) + D (diagonal), Linv, and y_J
+    if (has_blk) {
+        double* dst0 = (kind == 0) ? T : Linv + (size_t)tk.col * ST2;
 #pragma unroll
         for (int b = 0; b < TB; ++b) {
-            double2* dst = reinterpret_cast<double2*>(As + (TB * tx + b) * ST + TB * ty);
+            double2* dst = reinterpret_cast<double2*>(dst0 + (size_t)ST * (TB * tx + b) + TB * ty);
 #pragma unroll
-            for (int a = 0; a < TB / 2; ++a) dst[a] = make_double2(R[2 * a][b], R[2 * a + 1][b]);
+            for (int a = 0; a < TB / 2; ++a) dst[a] = make_double2(B[2 * a][b], B[2 * a + 1][b]);
         }
-        if (tid < ST) Ds[tid] = S[(size_t)tk.dtile * ST2 + (size_t)(ST + 1) * tid];
-        cp_async_wait_all();
-        __syncthreads();
-        double X[TB][TB];
+    }
+    if (kind == 2) {
 #pragma unroll
-        for (int a = 0; a < TB; ++a)
+        for (int s3 = 0; s3 < 3; ++s3) if (lane + 32 * s3 < ST) xp[(size_t)tk.col * ST + lane + 32 * s3] = v[s3];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Off-diagonal tile (I, J):  L_IJ = T_IJ Linv_J' D_J^-1, i.e. X[i][c] = sum_{k <= c} T[i][k] Linv[c][k] / d_c ; then the
+// right-hand side push b_I -= L_IJ y_J.  Two CTAs per tile (rows 0..35 / 36..71); thread (ty, tx) owns a 6 x 6 block.
+// ---------------------------------------------------------------------------------------------------
+constexpr size_t OFF_SMEM = (size_t)(2 * ST2 + 2 * ST + TG * (ST / 2)) * sizeof(double);
+
+__global__ void __launch_bounds__(HALF_THREADS) ldl_off_kernel(double* __restrict__ S, const double* __restrict__ Linv, const RedTask* __restrict__ tasks,
+                                                               double* __restrict__ xp) {
+    extern __shared__ __align__(16) double sm[];
+    double* As = sm;                  // T_IJ   [k][i]
+    double* Bs = sm + ST2;            // Linv_J [k][c]
+    double* Ds = sm + 2 * ST2;        // [ST] 1 / D_J
+    double* ys = Ds + ST;             // [ST] y_J
+    double* part = ys + ST;           // [TG][ST / 2]
+    const int tid = threadIdx.x, half = blockIdx.x & 1;
+    const RedTask tk = tasks[blockIdx.x >> 1];
+    double* T = S + (size_t)tk.tile * ST2;
+    tile_to_smem<HALF_THREADS>(As, T);
+    tile_to_smem<HALF_THREADS>(Bs, Linv + (size_t)tk.col * ST2);
+    if (tid < ST) {
+        Ds[tid] = rcp_fast(S[(size_t)tk.dtile * ST2 + (size_t)(ST + 1) * tid]);
+        ys[tid] = xp[(size_t)tk.col * ST + tid];
+    }
+    cp_async_wait_all();
+    __syncthreads();
+    const bool work = tid < (TG / 2) * TG;
+    const int tx = tid % TG, tyl = (tid / TG) % (TG / 2), ty = tyl + (TG / 2) * half;
+    double X[TB][TB];
 #pragma unroll
-            for (int b = 0; b < TB; ++b) X[a][b] = 0.0;
+    for (int a = 0; a < TB; ++a)
+#pragma unroll
+        for (int b = 0; b < TB; ++b) X[a][b] = 0.0;
+    if (work) {
         const int kend = TB * tx + TB;                     // Linv is lower triangular: Linv[c][k] = 0 for k > c
-#pragma unroll 4
+#pragma unroll 2
         for (int k = 0; k < kend; ++k) {
             const double2* ap = reinterpret_cast<const double2*>(As + k * ST + TB * ty);
-            const double2* bp = reinterpret_cast<const double2*>(Cs + k * ST + TB * tx);
+            const double2* bp = reinterpret_cast<const double2*>(Bs + k * ST + TB * tx);
             double av[TB], bv[TB];
 #pragma unroll
-            for (int a = 0; a < TB / 2; ++a) { const double2 v = ap[a]; av[2 * a] = v.x; av[2 * a + 1] = v.y; }
+            for (int a = 0; a < TB / 2; ++a) { const double2 q = ap[a]; av[2 * a] = q.x; av[2 * a + 1] = q.y; }
 #pragma unroll
-            for (int b = 0; b < TB / 2; ++b) { const double2 v = bp[b]; bv[2 * b] = v.x; bv[2 * b + 1] = v.y; }
+            for (int b = 0; b < TB / 2; ++b) { const double2 q = bp[b]; bv[2 * b] = q.x; bv[2 * b + 1] = q.y; }
 #pragma unroll
             for (int a = 0; a < TB; ++a)
 #pragma unroll
                 for (int b = 0; b < TB; ++b) X[a][b] = fma(av[a], bv[b], X[a][b]);
         }
+        double pr[TB];
+#pragma unroll
+        for (int a = 0; a < TB; ++a) pr[a] = 0.0;
 #pragma unroll
         for (int b = 0; b < TB; ++b) {
-            const double rd = rcp_fast(Ds[TB * tx + b]);
+            const double rd = Ds[TB * tx + b], yc = ys[TB * tx + b];
             double2* dst = reinterpret_cast<double2*>(T + (size_t)ST * (TB * tx + b) + TB * ty);
 #pragma unroll
-            for (int a = 0; a < TB / 2; ++a) dst[a] = make_double2(X[2 * a][b] * rd, X[2 * a + 1][b] * rd);
+            for (int a = 0; a < TB; ++a) { X[a][b] *= rd; pr[a] = fma(X[a][b], yc, pr[a]); }
+#pragma unroll
+            for (int a = 0; a < TB / 2; ++a) dst[a] = make_double2(X[2 * a][b], X[2 * a + 1][b]);
         }
-    } else {
-    // ---- diagonal tile: in-register LDL' with the row operations mirrored on M (-> M = L^-1).  One barrier per pivot:
-    // the owners of column j / row j publish them (double buffered), everybody below applies the rank-1 update.
-    double M[TB][TB];
+#pragma unroll
+        for (int a = 0; a < TB; ++a) part[tx * (ST / 2) + TB * tyl + a] = pr[a];
+    }
+    __syncthreads();
+    if (tid < ST / 2) {
+        double s = 0.0;
+#pragma unroll
+        for (int c = 0; c < TG; ++c) s += part[c * (ST / 2) + tid];
+        atomicAdd(xp + (size_t)tk.row * ST + (ST / 2) * half + tid, -s);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Update  T_{ab} -= (L_aJ D_J) L_bJ'  for one pair of rows of column J.  Two CTAs per pair (target rows 0..35 / 36..71);
+// results are subtracted from the target tile with FP64 reductions (several columns of a level can hit the same tile).
+// ---------------------------------------------------------------------------------------------------
+constexpr size_t UPD_SMEM = (size_t)(2 * ST2 + ST) * sizeof(double);
+
+__global__ void __launch_bounds__(HALF_THREADS) ldl_upd_kernel(double* __restrict__ S, const RedUpd* __restrict__ upds) {
+    extern __shared__ __align__(16) double sm[];
+    double* As = sm;                  // L_aJ [k][i]
+    double* Bs = sm + ST2;            // L_bJ [k][c]
+    double* Ds = sm + 2 * ST2;        // [ST] D_J
+    const int tid = threadIdx.x, half = blockIdx.x & 1;
+    const RedUpd up = upds[blockIdx.x >> 1];
+    tile_to_smem<HALF_THREADS>(As, S + (size_t)up.a * ST2);
+    if (up.b != up.a) tile_to_smem<HALF_THREADS>(Bs, S + (size_t)up.b * ST2);
+    if (tid < ST) Ds[tid] = S[(size_t)up.dk * ST2 + (size_t)(ST + 1) * tid];
+    cp_async_wait_all();
+    __syncthreads();
+    const double* Bt = (up.b != up.a) ? Bs : As;
+    const int tx = tid % TG, tyl = (tid / TG) % (TG / 2), ty = tyl + (TG / 2) * half;
+    const bool work = tid < (TG / 2) * TG && (up.b != up.a || ty >= tx);   // diagonal targets: lower blocks only
+    if (!work) return;
+    double X[TB][TB];
 #pragma unroll
     for (int a = 0; a < TB; ++a)
 #pragma unroll
-        for (int b = 0; b < TB; ++b) M[a][b] = (ty == tx && a == b) ? 1.0 : 0.0;
-    __syncthreads();
-    if (tid < ST) vs[tid] = xp[(size_t)tk.col * ST + tid] - (Cs[tid] + Cs[ST + tid]);
-    for (int jb = 0; jb < TG; ++jb) {
+        for (int b = 0; b < TB; ++b) X[a][b] = 0.0;
+#pragma unroll 2
+    for (int k = 0; k < ST; ++k) {
+        const double dk = Ds[k];
+        const double2* ap = reinterpret_cast<const double2*>(As + k * ST + TB * ty);
+        const double2* bp = reinterpret_cast<const double2*>(Bt + k * ST + TB * tx);
+        double av[TB], bv[TB];
 #pragma unroll
-        for (int jj = 0; jj < TB; ++jj) {
-            const int j = TB * jb + jj, buf = j & 1;
-            if (tx == jb && ty >= jb) {
+        for (int a = 0; a < TB / 2; ++a) { const double2 q = ap[a]; av[2 * a] = q.x * dk; av[2 * a + 1] = q.y * dk; }
 #pragma unroll
-                for (int a = 0; a < TB; ++a) colA[buf * ST + TB * ty + a] = R[a][jj];
-            }
-            if (ty == jb && tx <= jb) {
+        for (int b = 0; b < TB / 2; ++b) { const double2 q = bp[b]; bv[2 * b] = q.x; bv[2 * b + 1] = q.y; }
 #pragma unroll
-                for (int b = 0; b < TB; ++b) rowM[buf * ST + TB * tx + b] = M[jj][b];
-            }
-            __syncthreads();
-            if (ty >= jb && tx <= ty) {
-                const double rd = rcp_fast(colA[buf * ST + j]);
-                double li[TB];
+        for (int a = 0; a < TB; ++a)
 #pragma unroll
-                for (int a = 0; a < TB; ++a) li[a] = (TB * ty + a > j) ? colA[buf * ST + TB * ty + a] * rd : 0.0;
-                if (tx >= jb) {
-#pragma unroll
-                    for (int b = 0; b < TB; ++b) {
-                        const double ck = (TB * tx + b > j) ? colA[buf * ST + TB * tx + b] : 0.0;
-#pragma unroll
-                        for (int a = 0; a < TB; ++a) R[a][b] = fma(-li[a], ck, R[a][b]);
-                    }
-                    if (tx == jb) {
-#pragma unroll
-                        for (int a = 0; a < TB; ++a) if (TB * ty + a > j) R[a][jj] = li[a];
-                    }
-                }
-                if (tx <= jb) {
-#pragma unroll
-                    for (int b = 0; b < TB; ++b) {
-                        const double mr = rowM[buf * ST + TB * tx + b];
-#pragma unroll
-                        for (int a = 0; a < TB; ++a) M[a][b] = fma(-li[a], mr, M[a][b]);
-                    }
-                }
-            }
-        }
+            for (int b = 0; b < TB; ++b) X[a][b] = fma(av[a], bv[b], X[a][b]);
     }
-    // ---- write L (strict lower) + D (diagonal) and Linv; forward substitution, second half: y_J = Linv_J v
-    double* Li = Linv + (size_t)tk.col * ST2;
-    if (ty >= tx) {
+    double* T = S + (size_t)up.target * ST2;
 #pragma unroll
-        for (int b = 0; b < TB; ++b) {
-            double2* dst = reinterpret_cast<double2*>(T + (size_t)ST * (TB * tx + b) + TB * ty);
-            double2* dsi = reinterpret_cast<double2*>(Li + (size_t)ST * (TB * tx + b) + TB * ty);
+    for (int b = 0; b < TB; ++b)
 #pragma unroll
-            for (int a = 0; a < TB / 2; ++a) { dst[a] = make_double2(R[2 * a][b], R[2 * a + 1][b]); dsi[a] = make_double2(M[2 * a][b], M[2 * a + 1][b]); }
-        }
-#pragma unroll
-        for (int a = 0; a < TB; ++a) {
-            double s = 0.0;
-#pragma unroll
-            for (int b = 0; b < TB; ++b) s = fma(M[a][b], vs[TB * tx + b], s);
-            As[tx * ST + TB * ty + a] = s;
-        }
-    }
-    __syncthreads();
-    if (tid < ST) {
-        double s = 0.0;
-        for (int c = 0; c <= tid / TB; ++c) s += As[c * ST + tid];
-        xp[(size_t)tk.col * ST + tid] = s;
-    }
-    }
+        for (int a = 0; a < TB; ++a) atomicAdd(T + (size_t)ST * (TB * tx + b) + TB * ty + a, -X[a][b]);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -279,7 +346,7 @@ __global__ void __launch_bounds__(RED_THREADS) ldl_bwd_kernel(const double* __re
     const int q0 = t.colptr[J], q1 = t.colptr[J + 1];
     double acc = 0.0;
     if (q0 < q1) {
-        tile_to_smem(Ts, S + (size_t)t.col_tile[q0] * ST2);
+        tile_to_smem<RED_THREADS>(Ts, S + (size_t)t.col_tile[q0] * ST2);
         if (tid < ST) xi[tid] = x[(size_t)t.col_row[q0] * ST + tid];
     }
     for (int q = q0; q < q1; ++q) {
@@ -287,7 +354,7 @@ __global__ void __launch_bounds__(RED_THREADS) ldl_bwd_kernel(const double* __re
         cp_async_wait_all();
         __syncthreads();
         if (q + 1 < q1) {
-            tile_to_smem(Ts + (st ^ 1) * ST2, S + (size_t)t.col_tile[q + 1] * ST2);
+            tile_to_smem<RED_THREADS>(Ts + (st ^ 1) * ST2, S + (size_t)t.col_tile[q + 1] * ST2);
             if (tid < ST) xi[(st ^ 1) * ST + tid] = x[(size_t)t.col_row[q + 1] * ST + tid];
         }
         const double* M = Ts + st * ST2 + (size_t)ST * c + (ST / 2) * h;
@@ -296,7 +363,7 @@ __global__ void __launch_bounds__(RED_THREADS) ldl_bwd_kernel(const double* __re
         for (int i = 0; i < ST / 2; ++i) acc = fma(M[i], xv[i], acc);
     }
     __syncthreads();
-    tile_to_smem(Ts, Linv + (size_t)J * ST2);
+    tile_to_smem<RED_THREADS>(Ts, Linv + (size_t)J * ST2);
     part[h * ST + c] = acc;
     cp_async_wait_all();
     __syncthreads();
