@@ -253,10 +253,17 @@ def main():
     peak = float(peaks.get("hbm_gbs", 6650.0))
     alg_bytes = ctx.algorithmic_bytes(capi.TIME_LIN_POINT)
     achieved = alg_bytes / (kern["lin_point"] * 1e-3) / 1e9
+    traffic = None
+    try:  # DRAM bytes of the same kernel from the committed ncu --set full capture (1-GPU venice only)
+        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload, {}).get("lin_point_kernel")
+        if tr and tr.get("gpus") == world:
+            traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "kernel": "lin_point_kernel<AffineBA> (fused residual + Jacobian + robust + J'WJ, TMA tile store)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
-                "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": kern["lin_point"], "traffic": None,
+                "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": kern["lin_point"], "traffic": traffic,
                 "linearize_total": {"algorithmic_bytes": ctx.algorithmic_bytes(capi.TIME_LINEARIZE), "ms": kern["linearize"],
                                     "achieved": ctx.algorithmic_bytes(capi.TIME_LINEARIZE) / (kern["linearize"] * 1e-3) / 1e9}}
 

@@ -118,7 +118,9 @@ struct nlls_ctx {
     int* d_info = nullptr;
     int* d_ipiv = nullptr;
     int use_tma = 1;
-    int tile_obs = 256;             // observations per point tile = threads per CTA of the tile kernels (NLLS_B200_TILE=128|256)
+    int tile_obs = 0;               // observations per point tile = threads per CTA of the tile kernels: the smallest of 64 / 128 / 256 that
+                                    // holds the longest track (NLLS_B200_TILE overrides)
+    int tile_env = 0;
     int4* d_tiles = nullptr;        // (pt0, npt, ob0, nob) per point tile
     int nsm = 148, lin_grid = 0, cost_grid = 0, bs_grid = 0;
     int schur_stride = 296;
@@ -530,7 +532,7 @@ int nlls_create(nlls_ctx** out, int device) {
     if (const char* g = getenv("NLLS_B200_SCHUR_STRIDE")) ctx->schur_stride = std::max(1, atoi(g));
     if (const char* g = getenv("NLLS_B200_REDUCED")) ctx->s_tiled = (std::string(g) == "dense") ? 0 : 1;
     if (const char* g = getenv("NLLS_B200_SCHUR")) ctx->schur_v2 = (std::string(g) == "v1") ? 0 : 1;
-    if (const char* g = getenv("NLLS_B200_TILE")) { const int v = atoi(g); ctx->tile_obs = (v == 64 || v == 128) ? v : 256; }
+    if (const char* g = getenv("NLLS_B200_TILE")) { const int v = atoi(g); ctx->tile_env = (v == 64 || v == 128) ? v : 256; }
     { int v = 0; if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && v > 0) ctx->nsm = v; }
     if (cudaGetLastError() != cudaSuccess) { delete ctx; return NLLS_ERR_CUDA; }
     *out = ctx;
@@ -705,6 +707,11 @@ int nlls_prepare(nlls_ctx* ctx) {
     }
     ctx->h_obs_start.assign((size_t)nB + 1, 0);
     for (int64_t p = 0; p < nB; ++p) ctx->h_obs_start[(size_t)p + 1] = ctx->h_obs_start[(size_t)p] + cnt[(size_t)p + 1];
+    {
+        int maxk = 0;
+        for (int64_t p = 0; p < nB; ++p) maxk = std::max(maxk, cnt[(size_t)p + 1]);
+        ctx->tile_obs = ctx->tile_env ? ctx->tile_env : (maxk <= 64 ? 64 : (maxk <= 128 ? 128 : 256));
+    }
     std::vector<int> fill(ctx->h_obs_start.begin(), ctx->h_obs_start.end() - 1);
     std::vector<int> order((size_t)nobs);
     for (int64_t i = 0; i < nobs; ++i) order[(size_t)fill[(size_t)ptl[(size_t)i]]++] = (int)i;

@@ -71,16 +71,26 @@ __device__ __forceinline__ void tile_to_smem(double* sdst, const double* gsrc) {
 //   w4 = L blocks 0..25    w5 = Linv blocks 0..25    w6 = right-hand side
 // L blocks are numbered by (tx, ty) ascending — block (ty, tx) is touched by pivots j < 6 tx + 6, so low numbers retire first;
 // Linv blocks by (ty, tx) ascending — block (ty, tx) is touched by pivots 6 tx <= j < 6 ty + 6.
+// A single warp issues dependent instructions ~5 cycles apart, so the per-pivot instruction count is what matters:
+//   * finished entries are "retired" to shared memory the moment they are final (column j of L, row j+1 of Linv, d_j), after
+//     which their registers may hold garbage — the rank-1 updates then need no row / column masks at all;
+//   * every role has its own loop (named barrier, explicit thread count), so nothing role-dependent is re-evaluated per pivot;
+//   * the next pivot and its reciprocal are computed by every thread in the shadow of the 36 updates, only the owner stores.
 // ---------------------------------------------------------------------------------------------------
-constexpr size_t DIAG_SMEM = (size_t)(ST2 + 4 * ST + 4) * sizeof(double);
+constexpr int LDM = ST + 1;           // padded row stride of the Linv staging tile (conflict-free transposed read-out)
+constexpr size_t DIAG_SMEM = (size_t)(ST2 + ST * LDM + 5 * ST + 4) * sizeof(double);
+
+__device__ __forceinline__ void diag_bar() { asm volatile("bar.sync 1, %0;" ::"n"(DIAG_THREADS) : "memory"); }
 
 __global__ void __launch_bounds__(DIAG_THREADS) ldl_diag_kernel(double* __restrict__ S, double* __restrict__ Linv, const RedTask* __restrict__ tasks,
                                                                 double* __restrict__ xp) {
     extern __shared__ __align__(16) double sm[];
-    double* As = sm;                  // the tile as stored (column-major)
-    double* colA = sm + ST2;          // [2][ST] published column of A
+    double* As = sm;                  // the tile as stored (column-major); retired columns of L overwrite it
+    double* Ms = sm + ST2;            // [ST][LDM] retired rows of M = L^-1
+    double* colA = Ms + ST * LDM;     // [2][ST] published column of A
     double* rowM = colA + 2 * ST;     // [2][ST] published row of M
-    double* rdb = rowM + 2 * ST;      // [2] published pivot reciprocal
+    double* dbuf = rowM + 2 * ST;     // [ST] pivots
+    double* rdb = dbuf + ST;          // [2] published pivot reciprocal
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const RedTask tk = tasks[blockIdx.x];
     double* T = S + (size_t)tk.tile * ST2;
@@ -95,9 +105,6 @@ __global__ void __launch_bounds__(DIAG_THREADS) ldl_diag_kernel(double* __restri
         if (kind == 0) { while (n >= TG - tx) { n -= TG - tx; ++tx; } ty = tx + n; }      // by tx, then ty
         else { while (n >= ty + 1) { n -= ty + 1; ++ty; } tx = n; }                          // by ty, then tx
     }
-    // last pivot that touches any block of this warp (warp-uniform early exit)
-    const int last_j = (kind == 2) ? ST - 1 : (kind == 0 ? (grp == 0 ? 17 : (grp == 1 ? 35 : ST - 1)) : (grp == 0 ? 41 : (grp == 1 ? 59 : ST - 1)));
-
     double v[3] = {0.0, 0.0, 0.0};
     if (kind == 2) {
 #pragma unroll
@@ -113,97 +120,119 @@ __global__ void __launch_bounds__(DIAG_THREADS) ldl_diag_kernel(double* __restri
     if (kind == 0 && has_blk && tx == 0) {
 #pragma unroll
         for (int a = 0; a < TB; ++a) colA[TB * ty + a] = B[a][0];
-        if (ty == 0) rdb[0] = rcp_fast(B[0][0]);
+        if (ty == 0) { rdb[0] = rcp_fast(B[0][0]); dbuf[0] = B[0][0]; }
     }
     if (kind == 1 && has_blk && ty == 0) {
 #pragma unroll
-        for (int b = 0; b < TB; ++b) rowM[TB * tx + b] = B[0][b];
+        for (int b = 0; b < TB; ++b) { rowM[b] = B[0][b]; Ms[b] = B[0][b]; }
     }
+    __syncthreads();                                      // every thread holds its block: As may now receive retired columns
 
-    for (int jb = 0; jb < TG; ++jb) {
+    if (kind == 0) {
+        // ---------------- L blocks: rank-1 update, retire column j, publish column j + 1 and its pivot ----------------
+        const int last_j = grp == 0 ? 17 : (grp == 1 ? 35 : ST - 1);
+        const double* cty = colA + TB * ty;
+        const double* ctx = colA + TB * tx;
+        for (int jb = 0; jb < TG; ++jb) {
+            const bool live = has_blk && tx >= jb;
+            const bool own = live && tx == jb;
 #pragma unroll
-        for (int jj = 0; jj < TB; ++jj) {
-            const int j = TB * jb + jj, buf = j & 1, nb = buf ^ 1;
-            __syncthreads();
-            if (j > last_j) continue;
-            const double rd = rdb[buf];
-            if (kind == 0) {
-                if (has_blk && tx >= jb) {
-                    double li[TB], ck[TB];
+            for (int jj = 0; jj < TB; ++jj) {
+                const int j = TB * jb + jj, buf = j & 1, nb = buf ^ 1;
+                const int jn = (jj + 1) % TB;
+                diag_bar();
+                if (j > last_j || !live) continue;
+                const double rd = rdb[buf];
+                double li[TB], ck[TB];
 #pragma unroll
-                    for (int a = 0; a < TB; ++a) li[a] = (TB * ty + a > j) ? colA[buf * ST + TB * ty + a] * rd : 0.0;
-#pragma unroll
-                    for (int b = 0; b < TB; ++b) ck[b] = (TB * tx + b > j) ? colA[buf * ST + TB * tx + b] : 0.0;
-                    // next pivot column first: its owners publish it (and the next reciprocal) while the rest of the block updates
-                    const int jn = (jj + 1) % TB;
-                    const bool own_next = (jj + 1 < TB) ? (tx == jb) : (tx == jb + 1);
-#pragma unroll
-                    for (int a = 0; a < TB; ++a) B[a][jn] = fma(-li[a], ck[jn], B[a][jn]);
-                    if (own_next) {
-#pragma unroll
-                        for (int a = 0; a < TB; ++a) colA[nb * ST + TB * ty + a] = B[a][jn];
-                        if (ty == tx) rdb[nb] = rcp_fast(B[jn][jn]);
-                    }
-#pragma unroll
-                    for (int b = 0; b < TB; ++b) {
-                        if (b == jn) continue;
-#pragma unroll
-                        for (int a = 0; a < TB; ++a) B[a][b] = fma(-li[a], ck[b], B[a][b]);
-                    }
-                    if (tx == jb) {
-#pragma unroll
-                        for (int a = 0; a < TB; ++a) if (TB * ty + a > j) B[a][jj] = li[a];
-                    }
+                for (int a = 0; a < TB / 2; ++a) {
+                    const double2 q = reinterpret_cast<const double2*>(cty + buf * ST)[a];
+                    li[2 * a] = q.x * rd; li[2 * a + 1] = q.y * rd;
+                    const double2 r2 = reinterpret_cast<const double2*>(ctx + buf * ST)[a];
+                    ck[2 * a] = r2.x; ck[2 * a + 1] = r2.y;
                 }
-            } else if (kind == 1) {
-                if (has_blk && tx <= jb && ty >= jb) {
-                    double li[TB];
+                // next pivot (meaningful on its diagonal block only) and its reciprocal, in the shadow of the updates
+                const double dn = fma(-li[jn], ck[jn], B[jn][jn]);
+                const double rn = rcp_fast(dn);
+                const bool own_next = (jj + 1 < TB) ? own : (has_blk && tx == jb + 1);
+                if (own_next && ty == tx) { rdb[nb] = rn; dbuf[j + 1 < ST ? j + 1 : j] = dn; }
 #pragma unroll
-                    for (int a = 0; a < TB; ++a) li[a] = (TB * ty + a > j) ? colA[buf * ST + TB * ty + a] * rd : 0.0;
+                for (int b = 0; b < TB; ++b)
 #pragma unroll
-                    for (int b = 0; b < TB; ++b) {
-                        const double mr = rowM[buf * ST + TB * tx + b];
+                    for (int a = 0; a < TB; ++a) B[a][b] = fma(-li[a], ck[b], B[a][b]);
+                if (own) {                                  // column j of L is final: retire it
+                    double2* dst = reinterpret_cast<double2*>(As + j * ST + TB * ty);
 #pragma unroll
-                        for (int a = 0; a < TB; ++a) B[a][b] = fma(-li[a], mr, B[a][b]);
-                    }
-                    // row j + 1 of M is final now: publish it
-                    const int jn = (jj + 1) % TB;
-                    const bool own_next = (jj + 1 < TB) ? (ty == jb) : false;
-                    if (own_next) {
-#pragma unroll
-                        for (int b = 0; b < TB; ++b) rowM[nb * ST + TB * tx + b] = B[jn][b];
-                    }
+                    for (int a = 0; a < TB / 2; ++a) dst[a] = make_double2(li[2 * a], li[2 * a + 1]);
                 }
-                if (has_blk && jj + 1 == TB && ty == jb + 1 && tx <= jb + 1) {   // first row of the next block row (untouched by pivots >= its own)
+                if (own_next) {
+                    double2* dst = reinterpret_cast<double2*>(colA + nb * ST + TB * ty);
 #pragma unroll
-                    for (int b = 0; b < TB; ++b) rowM[nb * ST + TB * tx + b] = B[0][b];
-                }
-            } else {
-                // forward substitution carried as an extra column: v_i -= l_ij v_j
-                const int sj = j >> 5;
-                const double vsel = (sj == 0) ? v[0] : (sj == 1 ? v[1] : v[2]);
-                const double vj = __shfl_sync(0xffffffffu, vsel, j & 31);
-#pragma unroll
-                for (int s3 = 0; s3 < 3; ++s3) {
-                    const int i = lane + 32 * s3;
-                    if (i > j && i < ST) v[s3] = fma(-(colA[buf * ST + i] * rd), vj, v[s3]);
+                    for (int a = 0; a < TB / 2; ++a) dst[a] = make_double2(B[2 * a][jn], B[2 * a + 1][jn]);
                 }
             }
         }
-    }
-    // ---- write L (strict lower) + D (diagonal), Linv, and y_J
-    if (has_blk) {
-        double* dst0 = (kind == 0) ? T : Linv + (size_t)tk.col * ST2;
+    } else if (kind == 1) {
+        // ---------------- Linv blocks: the same row operations on the identity; retire / publish row j + 1 ----------------
+        const int last_j = grp == 0 ? 41 : (grp == 1 ? 59 : ST - 1);
+        const double* cty = colA + TB * ty;
+        const double* rtx = rowM + TB * tx;
+        for (int jb = 0; jb < TG; ++jb) {
+            const bool live = has_blk && tx <= jb && ty >= jb;
 #pragma unroll
-        for (int b = 0; b < TB; ++b) {
-            double2* dst = reinterpret_cast<double2*>(dst0 + (size_t)ST * (TB * tx + b) + TB * ty);
+            for (int jj = 0; jj < TB; ++jj) {
+                const int j = TB * jb + jj, buf = j & 1, nb = buf ^ 1;
+                const int jn = (jj + 1) % TB;
+                diag_bar();
+                if (j > last_j) continue;
+                if (live) {
+                    const double rd = rdb[buf];
+                    double li[TB], mr[TB];
 #pragma unroll
-            for (int a = 0; a < TB / 2; ++a) dst[a] = make_double2(B[2 * a][b], B[2 * a + 1][b]);
+                    for (int a = 0; a < TB / 2; ++a) {
+                        const double2 q = reinterpret_cast<const double2*>(cty + buf * ST)[a];
+                        li[2 * a] = q.x * rd; li[2 * a + 1] = q.y * rd;
+                        const double2 r2 = reinterpret_cast<const double2*>(rtx + buf * ST)[a];
+                        mr[2 * a] = r2.x; mr[2 * a + 1] = r2.y;
+                    }
+#pragma unroll
+                    for (int b = 0; b < TB; ++b)
+#pragma unroll
+                        for (int a = 0; a < TB; ++a) B[a][b] = fma(-li[a], mr[b], B[a][b]);
+                }
+                // row j + 1 of M is final now: retire and publish it
+                const bool own_next = has_blk && ((jj + 1 < TB) ? (live && ty == jb) : (ty == jb + 1 && tx <= jb + 1));
+                if (own_next) {
+#pragma unroll
+                    for (int b = 0; b < TB; ++b) { rowM[nb * ST + TB * tx + b] = B[jn][b]; Ms[(j + 1) * LDM + TB * tx + b] = B[jn][b]; }
+                }
+            }
         }
-    }
-    if (kind == 2) {
+    } else {
+        // ---------------- right-hand side: forward substitution carried as an extra column, v_i -= l_ij v_j ----------------
+        for (int j = 0; j < ST; ++j) {
+            const int buf = j & 1;
+            diag_bar();
+            const double rd = rdb[buf];
+            const int sj = j >> 5;
+            const double vsel = (sj == 0) ? v[0] : (sj == 1 ? v[1] : v[2]);
+            const double vj = __shfl_sync(0xffffffffu, vsel, j & 31);
+#pragma unroll
+            for (int s3 = 0; s3 < 3; ++s3) {
+                const int i = lane + 32 * s3;
+                if (i > j && i < ST) v[s3] = fma(-(colA[buf * ST + i] * rd), vj, v[s3]);
+            }
+        }
 #pragma unroll
         for (int s3 = 0; s3 < 3; ++s3) if (lane + 32 * s3 < ST) xp[(size_t)tk.col * ST + lane + 32 * s3] = v[s3];
+    }
+    __syncthreads();
+    // ---- write L (strict lower) + D (diagonal) and Linv (lower incl. the unit diagonal; the upper triangle stays zero)
+    double* Li = Linv + (size_t)tk.col * ST2;
+    for (int e = tid; e < ST2; e += DIAG_THREADS) {
+        const int i = e % ST, k = e / ST;
+        if (i > k) { T[e] = As[e]; Li[e] = Ms[i * LDM + k]; }
+        else if (i == k) { T[e] = dbuf[k]; Li[e] = 1.0; }
     }
 }
 
