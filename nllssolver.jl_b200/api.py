@@ -45,9 +45,34 @@ class PinholeCamera:
         return cls(np.asarray(v[:9]).reshape(3, 3, order="F"), v[9:12], v[12], v[13], v[14])
 
 
+class ContaminatedGaussian:
+    """ContaminatedGaussian(sigma1, sigma2, w): adaptive robust kernel *and* 3-DoF variable (src/robustadaptive.jl:3-23).
+    Stored as (1/sigma1, 1/sigma2, w) with the narrowest Gaussian first; w is not flipped by the re-sort (:12-15)."""
+
+    def __init__(self, s1, s2, w):
+        a, b = 1.0 / float(s1), 1.0 / float(s2)
+        if not (a >= b):
+            a, b = b, a
+        self.invsigma1, self.invsigma2, self.w = a, b, float(w)
+
+    def stored(self):
+        return np.array([self.invsigma1, self.invsigma2, self.w])
+
+    @classmethod
+    def from_stored(cls, v):
+        k = cls.__new__(cls)
+        k.invsigma1, k.invsigma2, k.w = float(v[0]), float(v[1]), float(v[2])
+        return k
+
+    def params(self):                                                      # src/robustadaptive.jl:23
+        return np.array([1.0 / self.invsigma1, 1.0 / self.invsigma2, self.w])
+
+
 def _vartype(v):
     if isinstance(v, PinholeCamera):
         return capi.VAR_PINHOLE, v.stored()
+    if isinstance(v, ContaminatedGaussian):
+        return capi.VAR_CONTAMGAUSS, v.stored()
     if isinstance(v, (float, int)):
         return capi.VAR_SCALAR, np.array([float(v)])
     a = np.asarray(v, dtype=np.float64).reshape(-1)
@@ -114,6 +139,20 @@ class AffineReprojection(SimpleError2):
 class PinholeReprojection(SimpleError2):
     """Pinhole (BAL convention) reprojection error of a PinholeCamera and a 3-D point (repo-defined)."""
     restype = capi.RES_PINHOLE_BA
+
+
+ADAPTIVE_DTYPE = np.dtype([("data", "<f8"), ("varind", "<i8")])  # memory image of SimpleResidual (test/adaptivecost.jl:3-6)
+
+
+class OffsetResidual:
+    """AbstractAdaptiveResidual r = mean - data (examples/adaptivekernel.jl:9-18, test/adaptivecost.jl:3-13):
+    varindices = (kernel variable, mean variable); the ContaminatedGaussian kernel is the first variable of the block."""
+    restype = capi.RES_ADAPTIVE_OFFSET
+    robustkernel = NoRobust()
+
+    def __init__(self, data, varind, kernelind=1):
+        self.data = float(data)
+        self.varind = (int(kernelind), int(varind))
 
 
 def robustified(base, kernel):
@@ -183,8 +222,10 @@ class NLLSProblem:
 
     def addcost(self, cost):
         """addcost!(problem, cost)  (src/problem.jl:90-107)."""
-        if not isinstance(cost, SimpleError2):
+        if not isinstance(cost, (SimpleError2, OffsetResidual)):
             raise TypeError("unsupported cost")
+        if isinstance(cost, OffsetResidual):                               # src/problem.jl:97
+            assert isinstance(self.variables[cost.varind[0] - 1], ContaminatedGaussian), "adaptive residual: first variable must be the kernel"
         for vi in cost.varind:
             assert 1 <= vi <= len(self.variables), "Problem with varindices()"
         lst = self.costs.setdefault(type(cost), [])
@@ -194,8 +235,8 @@ class NLLSProblem:
         self._dirty = True
 
     def addcosts(self, costtype, aos):
-        """Bulk addcost!: `aos` is the memory image of Vector{costtype} (COST_DTYPE)."""
-        aos = np.ascontiguousarray(aos, dtype=COST_DTYPE)
+        """Bulk addcost!: `aos` is the memory image of Vector{costtype} (COST_DTYPE / ADAPTIVE_DTYPE)."""
+        aos = np.ascontiguousarray(aos, dtype=ADAPTIVE_DTYPE if costtype.restype == capi.RES_ADAPTIVE_OFFSET else COST_DTYPE)
         if costtype in self.costs and len(self.costs[costtype]):
             raise ValueError("bulk load into a non-empty cost vector")
         self.costs[costtype] = aos
@@ -228,6 +269,13 @@ class NLLSProblem:
             raise capi.NLLSError(capi.ERR_NO_KERNEL, f"residual type {ctype.__name__} has no registered sm_100a kernel (no CPU fallback)")
         if isinstance(lst, np.ndarray):
             aos = lst
+        elif ctype.restype == capi.RES_ADAPTIVE_OFFSET:
+            aos = np.zeros(len(lst), dtype=ADAPTIVE_DTYPE)
+            aos["data"] = [c.data for c in lst]
+            aos["varind"] = [c.varind[1] for c in lst]
+            kinds = {c.varind[0] for c in lst}
+            assert len(kinds) == 1, "all adaptive residuals must share one kernel variable"
+            self._kernel_var = kinds.pop()
         else:
             aos = np.zeros(len(lst), dtype=COST_DTYPE)
             aos["z"] = np.stack([c.measurement for c in lst])
@@ -247,7 +295,10 @@ class NLLSProblem:
             for vt, (idx, vals) in groups.items():
                 self._ctx.set_variables(vt, vals, indices=idx)
             k = ctype.robustkernel
-            self._ctx.set_costs(ctype.restype, aos, k.id, k.params)
+            kernel_var = 0
+            if ctype.restype == capi.RES_ADAPTIVE_OFFSET:
+                kernel_var = getattr(self, "_kernel_var", None) or next(i + 1 for i, v in enumerate(self.variables) if isinstance(v, ContaminatedGaussian))
+            self._ctx.set_costs(ctype.restype, aos, k.id, k.params, kernel_var)
             self._ctx.prepare()
             self._dirty = False
         else:
@@ -263,6 +314,8 @@ class NLLSProblem:
                 old = self.variables[i - 1]
                 if isinstance(old, PinholeCamera):
                     self.variables[i - 1] = PinholeCamera.from_stored(row)
+                elif isinstance(old, ContaminatedGaussian):
+                    self.variables[i - 1] = ContaminatedGaussian.from_stored(row)
                 elif isinstance(old, (float, int)):
                     self.variables[i - 1] = float(row[0])
                 else:

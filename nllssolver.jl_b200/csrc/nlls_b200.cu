@@ -19,6 +19,7 @@
 
 #include "../../include/nlls_b200.h"
 #include "kernels.cuh"
+#include "adaptive.cuh"
 
 using namespace nlls;
 
@@ -94,7 +95,17 @@ struct nlls_ctx {
     bool prepared = false;
 
     // ---- layout (host copies kept for read-back)
-    int vtA = 0, vtB = 0, DC = 0, NC = 0, CS = 0;
+    int vtA = 0, vtB = 0, DC = 0, NC = 0, CS = 0, BS = 3;   // BS: stored doubles per variable of the second class (3: points, 1: scalar means)
+    // adaptive-kernel problems (NLLS_RES_ADAPTIVE_OFFSET): one ContaminatedGaussian variable + scalar means, small dense system
+    bool adaptive = false;
+    int64_t kernel_var = 0;
+    int ad_nchunks = 0;
+    std::vector<int> h_ad_moff;
+    int ad_koff = 0;
+    double* d_ad_data = nullptr;
+    int4* d_ad_chunks = nullptr;
+    int* d_ad_moff = nullptr;
+    double* d_ad_part = nullptr;
     int64_t nA = 0, nB = 0, nobs = 0, dof = 0, hlen = 0, nred = 0;
     bool cams_first = true;
     std::vector<int> h_obs_cam, h_obs_pt, h_obs_start, h_tile_pt, h_cam_start, h_cm_obs;
@@ -449,6 +460,46 @@ int launch_maxdiag(nlls_ctx* ctx) {
     return NLLS_OK;
 }
 
+
+// ---- adaptive-kernel problems: small dense system, pure reductions (adaptive.cuh) ---------------------------------
+AdaptDev adaptdev(const nlls_ctx* c) {
+    AdaptDev p;
+    p.data = c->d_ad_data; p.chunks = c->d_ad_chunks; p.nchunks = c->ad_nchunks; p.nmeans = (int)c->nB; p.dof = (int)c->dof;
+    p.moff = c->d_ad_moff; p.koff = c->ad_koff;
+    return p;
+}
+int adapt_linearize(nlls_ctx* ctx) {
+    const AdaptDev p = adaptdev(ctx);
+    if (ctx->ad_nchunks > 0) { adapt_lin_kernel<<<ctx->ad_nchunks, AD_THREADS, 0, ctx->st>>>(p, ctx->d_A[ctx->cur], ctx->d_B[ctx->cur], ctx->d_ad_part); ctx->launches++; }
+    adapt_assemble_kernel<<<1, 64, 0, ctx->st>>>(p, ctx->d_ad_part, ctx->d_H, ctx->d_g, ctx->d_scal + SC_COST_LIN); ctx->launches++;
+    CK(cudaGetLastError());
+    if (ctx->nranks > 1) {   // residuals are sharded: every entry of the dense system is a sum over all ranks
+        CKN(g_nccl.GroupStart());
+        CKN(g_nccl.AllReduce(ctx->d_H, ctx->d_H, (size_t)ctx->dof * ctx->dof, ncclFloat64, ncclSum, ctx->comm, ctx->st));
+        CKN(g_nccl.AllReduce(ctx->d_g, ctx->d_g, (size_t)ctx->dof, ncclFloat64, ncclSum, ctx->comm, ctx->st));
+        CKN(g_nccl.AllReduce(ctx->d_scal + SC_COST_LIN, ctx->d_scal + SC_COST_LIN, 1, ncclFloat64, ncclSum, ctx->comm, ctx->st));
+        CKN(g_nccl.GroupEnd());
+    }
+    return NLLS_OK;
+}
+int adapt_cost(nlls_ctx* ctx, int which, int slot) {
+    const AdaptDev p = adaptdev(ctx);
+    if (ctx->ad_nchunks > 0) { adapt_cost_kernel<<<ctx->ad_nchunks, AD_THREADS, 0, ctx->st>>>(p, ctx->d_A[which], ctx->d_B[which], ctx->d_cost_part); ctx->launches++; }
+    reduce_partials_kernel<<<1, 1024, 0, ctx->st>>>(ctx->d_cost_part, ctx->ad_nchunks, ctx->d_scal + slot, 0); ctx->launches++;
+    CK(cudaGetLastError());
+    TRY(allreduce(ctx, ctx->d_scal + slot, 1, ncclSum));
+    return NLLS_OK;
+}
+int adapt_solve_update(nlls_ctx* ctx, double lambda) {
+    const AdaptDev p = adaptdev(ctx);
+    CK(cudaMemsetAsync(ctx->d_scal + SC_P_MAX, 0, 4 * sizeof(double), ctx->st));   // no second variable class on this path
+    adapt_solve_kernel<<<1, 32, 0, ctx->st>>>(p, ctx->d_H, ctx->d_g, lambda, ctx->d_A[ctx->cur], ctx->d_B[ctx->cur], ctx->d_A[ctx->nxt], ctx->d_B[ctx->nxt],
+                                              ctx->d_x, ctx->d_scal + SC_C_MAX);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return NLLS_OK;
+}
+
 #define DISPATCH(ctx, fn, ...)                                                                 \
     ((ctx)->restype == NLLS_RES_AFFINE_BA ? fn<AffineBA>(__VA_ARGS__)                          \
      : (ctx)->restype == NLLS_RES_PINHOLE_BA ? fn<PinholeBA>(__VA_ARGS__)                      \
@@ -462,6 +513,12 @@ int fetch_scalars(nlls_ctx* ctx) {
 }
 
 int do_linearize(nlls_ctx* ctx, double* cost) {
+    if (ctx->adaptive) {
+        TRY(adapt_linearize(ctx));
+        TRY(fetch_scalars(ctx));
+        if (cost) *cost = ctx->h_scal[SC_COST_LIN];
+        return NLLS_OK;
+    }
     TRY(DISPATCH(ctx, launch_linearize, ctx, true, true));
     if (ctx->nranks > 1) {  // camera blocks + camera gradient are sums over all ranks' observations
         CKN(g_nccl.GroupStart());
@@ -479,6 +536,10 @@ int do_linearize(nlls_ctx* ctx, double* cost) {
 
 // one LM try without the host sync: damp + Schur + reduced solve + back-substitution/update + cost(varnext)
 int enqueue_try(nlls_ctx* ctx, double lambda, bool lu) {
+    if (ctx->adaptive) {
+        TRY(adapt_solve_update(ctx, lambda));
+        return adapt_cost(ctx, ctx->nxt, SC_COST_TRY);
+    }
     TRY(DISPATCH(ctx, launch_schur, ctx, lambda));
     TRY(launch_reduced_solve(ctx, lu));
     TRY(DISPATCH(ctx, launch_update, ctx));
@@ -490,13 +551,85 @@ int do_try(nlls_ctx* ctx, double lambda) {
     TRY(enqueue_try(ctx, lambda, false));
     TRY(fetch_scalars(ctx));
     const int* info = reinterpret_cast<const int*>(ctx->h_scal + SC_COUNT);
-    if (!ctx->s_tiled && info[0] != 0) {  // dense path, not positive definite: the reference falls back to QR (src/linearsolver.jl:20-26); we use LU
+    if (!ctx->adaptive && !ctx->s_tiled && info[0] != 0) {  // dense path, not positive definite: the reference falls back to QR (src/linearsolver.jl:20-26); we use LU
         TRY(enqueue_try(ctx, lambda, true));
         TRY(fetch_scalars(ctx));
     }
     return NLLS_OK;
 }
 
+}  // namespace
+
+
+namespace {
+// makesymmvls for an adaptive-kernel problem: variable -> offset map (block order = variable order, src/linearsystem.jl:93-102),
+// residuals grouped by mean variable and cut into single-mean chunks.
+int prepare_adaptive(nlls_ctx* ctx) {
+    ctx->adaptive = true;
+    ctx->vtA = NLLS_VAR_CONTAMGAUSS; ctx->vtB = NLLS_VAR_SCALAR;
+    ctx->DC = 3; ctx->NC = 3; ctx->CS = 3; ctx->BS = 1;
+    if (!ctx->vars.count(ctx->vtA) || !ctx->vars.count(ctx->vtB)) FAIL(NLLS_ERR_INVALID, "kernel and mean variables must be set before prepare");
+    for (auto& kv : ctx->vars)
+        if (kv.first != ctx->vtA && kv.first != ctx->vtB && !kv.second.gidx.empty())
+            FAIL(NLLS_ERR_UNSUPPORTED, "variables of a type the registered residual does not use");
+    for (int vt : {ctx->vtA, ctx->vtB}) {
+        VarSet& vs = ctx->vars[vt];
+        if (!vs.stale) continue;
+        CK(cudaMemcpy(vs.vals.data(), vt == ctx->vtA ? ctx->d_A[ctx->cur] : ctx->d_B[ctx->cur], sizeof(double) * vs.vals.size(), cudaMemcpyDeviceToHost));
+        vs.stale = false;
+    }
+    const VarSet& A = ctx->vars[ctx->vtA];
+    const VarSet& B = ctx->vars[ctx->vtB];
+    if (A.gidx.size() != 1 || A.gidx[0] != ctx->kernel_var) FAIL(NLLS_ERR_INVALID, "exactly one ContaminatedGaussian variable, at index kernel_var, is expected");
+    ctx->nA = 1; ctx->nB = (int64_t)B.gidx.size(); ctx->nobs = (int64_t)ctx->h_pt_g.size();
+    if (ctx->nB < 1) FAIL(NLLS_ERR_INVALID, "no mean variable");
+    ctx->dof = 3 + ctx->nB;
+    if (ctx->dof > AD_MAXDOF) FAIL(NLLS_ERR_UNSUPPORTED, "more than " + std::to_string(AD_MAXDOF - 3) + " mean variables");
+    if (ctx->nobs >= (1LL << 31) - 1024) FAIL(NLLS_ERR_UNSUPPORTED, "more than 2^31 costs per rank");
+    ctx->hlen = ctx->dof * ctx->dof; ctx->nred = 0; ctx->ntiles = 0; ctx->nitems = 0; ctx->cams_first = true;
+    // offsets in variable order
+    ctx->h_ad_moff.assign((size_t)ctx->nB, 0);
+    {
+        int off = 0; size_t ib = 0; bool kdone = false;
+        while (ib < B.gidx.size() || !kdone) {
+            const bool takeK = !kdone && (ib >= B.gidx.size() || A.gidx[0] < B.gidx[ib]);
+            if (takeK) { ctx->ad_koff = off; off += 3; kdone = true; }
+            else { if (B.gidx[ib] == A.gidx[0]) FAIL(NLLS_ERR_INVALID, "variable index used by two variable types"); ctx->h_ad_moff[ib++] = off; off += 1; }
+        }
+    }
+    // group residuals by mean variable (stable), chunks of one mean
+    const int64_t n = ctx->nobs, M = ctx->nB;
+    std::vector<int> ml((size_t)n), cnt((size_t)M + 1, 0);
+    for (int64_t i = 0; i < n; ++i) {
+        const int64_t gi = ctx->h_pt_g[(size_t)i];
+        auto it = std::lower_bound(B.gidx.begin(), B.gidx.end(), gi);
+        if (it == B.gidx.end() || *it != gi) FAIL(NLLS_ERR_INVALID, "cost " + std::to_string(i + 1) + ": varind is not a scalar mean variable");
+        ml[(size_t)i] = (int)(it - B.gidx.begin());
+        cnt[(size_t)ml[(size_t)i] + 1]++;
+    }
+    for (int64_t m = 0; m < M; ++m) cnt[(size_t)m + 1] += cnt[(size_t)m];
+    std::vector<int> fill(cnt.begin(), cnt.end() - 1);
+    std::vector<double> data((size_t)n);
+    for (int64_t i = 0; i < n; ++i) data[(size_t)fill[(size_t)ml[(size_t)i]]++] = ctx->h_z[(size_t)i];
+    constexpr int AD_CHUNK = 4096;
+    std::vector<int4> chunks;
+    for (int64_t m = 0; m < M; ++m)
+        for (int b = cnt[(size_t)m]; b < cnt[(size_t)m + 1]; b += AD_CHUNK) chunks.push_back(make_int4((int)m, b, std::min(b + AD_CHUNK, cnt[(size_t)m + 1]), 0));
+    ctx->ad_nchunks = (int)chunks.size();
+    TRY(upload(ctx, &ctx->d_ad_data, data)); TRY(upload(ctx, &ctx->d_ad_chunks, chunks)); TRY(upload(ctx, &ctx->d_ad_moff, ctx->h_ad_moff));
+    for (int k = 0; k < 3; ++k) { TRY(dalloc(ctx, &ctx->d_A[k], (size_t)3)); TRY(dalloc(ctx, &ctx->d_B[k], (size_t)M)); }
+    ctx->cur = 0; ctx->nxt = 1; ctx->bst = 2;
+    TRY(upload_vars(ctx, A, 3, ctx->d_A[0])); TRY(upload_vars(ctx, B, 1, ctx->d_B[0]));
+    TRY(dalloc(ctx, &ctx->d_H, (size_t)ctx->hlen)); TRY(dalloc(ctx, &ctx->d_g, (size_t)ctx->dof)); TRY(dalloc(ctx, &ctx->d_x, (size_t)ctx->dof));
+    CK(cudaMemsetAsync(ctx->d_H, 0, sizeof(double) * ctx->hlen, ctx->st));
+    CK(cudaMemsetAsync(ctx->d_g, 0, sizeof(double) * ctx->dof, ctx->st));
+    CK(cudaMemsetAsync(ctx->d_x, 0, sizeof(double) * ctx->dof, ctx->st));
+    TRY(dalloc(ctx, &ctx->d_cost_part, (size_t)ctx->ad_nchunks)); TRY(dalloc(ctx, &ctx->d_ad_part, (size_t)ctx->ad_nchunks * AD_NP));
+    CK(cudaStreamSynchronize(ctx->st));
+    ctx->prepared = true;
+    ctx->lm_active = false;
+    return NLLS_OK;
+}
 }  // namespace
 
 // =====================================================================================================
@@ -548,7 +681,8 @@ int nlls_destroy(nlls_ctx* ctx) {
                     ctx->d_H, ctx->d_g, ctx->d_x, ctx->d_Ainv, ctx->d_S, ctx->d_rhs, ctx->d_cost_part, ctx->d_step_part, ctx->d_cam_part, ctx->d_scal,
                     ctx->d_flush, ctx->d_work, ctx->d_info, ctx->d_ipiv, ctx->d_tile_id, ctx->d_pos, ctx->d_diag_tile, ctx->d_diag_tile_nat,
                     ctx->d_lvl_cols, ctx->d_red_tasks, ctx->d_red_upds, ctx->d_colptr,
-                    ctx->d_col_tile, ctx->d_col_row, ctx->d_Linv, ctx->d_xp, ctx->d_stile_pt, ctx->d_chunk_off, ctx->d_chunks, ctx->d_ents, ctx->d_tiles, ctx->d_camstat_part};
+                    ctx->d_col_tile, ctx->d_col_row, ctx->d_Linv, ctx->d_xp, ctx->d_stile_pt, ctx->d_chunk_off, ctx->d_chunks, ctx->d_ents, ctx->d_tiles, ctx->d_camstat_part,
+                    ctx->d_ad_data, ctx->d_ad_chunks, ctx->d_ad_moff, ctx->d_ad_part};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (ctx->h_scal) cudaFreeHost(ctx->h_scal);
     if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
@@ -596,7 +730,7 @@ int nlls_set_variables(nlls_ctx* ctx, int vartype, const double* aos, int64_t n,
     if (same && (vartype == ctx->vtA || vartype == ctx->vtB)) {
         CK(cudaSetDevice(ctx->device));
         const bool isA = vartype == ctx->vtA;
-        const int ds = isA ? ctx->CS : 3;
+        const int ds = isA ? ctx->CS : ctx->BS;
         double* dst = isA ? ctx->d_A[ctx->cur] : ctx->d_B[ctx->cur];
         if (ds == stride) {
             CK(cudaMemcpyAsync(dst, aos, sizeof(double) * n * ds, cudaMemcpyHostToDevice, ctx->st));
@@ -622,8 +756,22 @@ int nlls_set_variables(nlls_ctx* ctx, int vartype, const double* aos, int64_t n,
 
 int nlls_set_costs(nlls_ctx* ctx, int restype, const void* aos, int64_t stride_bytes, int64_t n, int robust, const double* kparams, int nkparams,
                    int64_t kernel_var) {
-    (void)kernel_var;
     if (!ctx || (!aos && n > 0) || n < 0) return NLLS_ERR_INVALID;
+    if (restype == NLLS_RES_ADAPTIVE_OFFSET) {
+        // AbstractAdaptiveResidual: the robust kernel is variable `kernel_var` (src/residual.jl:47, src/problem.jl:97)
+        if (robust != NLLS_ROBUST_NONE) FAIL(NLLS_ERR_INVALID, "adaptive residuals take their kernel from a variable, not from robustkernel()");
+        if (stride_bytes < 16) FAIL(NLLS_ERR_INVALID, "cost stride must be >= 16 bytes (f64 data + i64 varind)");
+        if (kernel_var < 1) FAIL(NLLS_ERR_INVALID, "kernel_var must be the 1-based index of the ContaminatedGaussian variable");
+        ctx->restype = restype; ctx->robust = robust; ctx->kernel_var = kernel_var;
+        ctx->h_cam_g.clear(); ctx->h_pt_g.resize((size_t)n); ctx->h_z.resize((size_t)n);
+        const unsigned char* base = (const unsigned char*)aos;
+        for (int64_t i = 0; i < n; ++i) {
+            std::memcpy(&ctx->h_z[(size_t)i], base + (size_t)i * stride_bytes, 8);
+            std::memcpy(&ctx->h_pt_g[(size_t)i], base + (size_t)i * stride_bytes + 8, 8);
+        }
+        ctx->prepared = false;
+        return NLLS_OK;
+    }
     if (restype != NLLS_RES_AFFINE_BA && restype != NLLS_RES_PINHOLE_BA)
         FAIL(NLLS_ERR_NO_KERNEL, "residual type " + std::to_string(restype) + " has no registered sm_100a kernel (no CPU fallback)");
     const int kind = robust & 15;
@@ -658,6 +806,8 @@ int nlls_prepare(nlls_ctx* ctx) {
     if (ctx->prepared) return NLLS_OK;
     CK(cudaSetDevice(ctx->device));
     if (ctx->restype == 0) FAIL(NLLS_ERR_INVALID, "no costs set");
+    if (ctx->restype == NLLS_RES_ADAPTIVE_OFFSET) return prepare_adaptive(ctx);
+    ctx->adaptive = false; ctx->BS = 3;
     ctx->vtA = (ctx->restype == NLLS_RES_AFFINE_BA) ? NLLS_VAR_EUCLID6 : NLLS_VAR_PINHOLE;
     ctx->vtB = NLLS_VAR_EUCLID3;
     ctx->DC = (ctx->restype == NLLS_RES_AFFINE_BA) ? AffineBA::DC : PinholeBA::DC;
@@ -1037,7 +1187,8 @@ int nlls_cost(nlls_ctx* ctx, int which, double* cost) {
     TRY(nlls_prepare(ctx));
     CK(cudaSetDevice(ctx->device));
     const int buf = which == 0 ? ctx->cur : (which == 1 ? ctx->nxt : ctx->bst);
-    TRY(DISPATCH(ctx, launch_cost, ctx, buf, SC_COST_TRY));
+    if (ctx->adaptive) TRY(adapt_cost(ctx, buf, SC_COST_TRY));
+    else TRY(DISPATCH(ctx, launch_cost, ctx, buf, SC_COST_TRY));
     TRY(fetch_scalars(ctx));
     if (cost) *cost = ctx->h_scal[SC_COST_TRY];
     return NLLS_OK;
@@ -1046,6 +1197,7 @@ int nlls_cost(nlls_ctx* ctx, int which, double* cost) {
 int nlls_solve(nlls_ctx* ctx, double lambda) {
     if (!ctx || !ctx->prepared) return NLLS_ERR_INVALID;
     CK(cudaSetDevice(ctx->device));
+    if (ctx->adaptive) { TRY(adapt_solve_update(ctx, lambda)); return fetch_scalars(ctx); }
     TRY(DISPATCH(ctx, launch_schur, ctx, lambda));
     TRY(launch_reduced_solve(ctx, false));
     TRY(fetch_scalars(ctx));
@@ -1098,7 +1250,8 @@ int nlls_lm_iterate(nlls_ctx* ctx, nlls_iterinfo* info) {
     ctx->iternum += 1;                                           // src/optimize.jl:124
     // ---- iterate!(::LevMarData)                                 src/iterators.jl:139-172
     if (ctx->lambda == 0) {                                      // initlambda  :131-137,142-144
-        TRY(DISPATCH(ctx, launch_maxdiag, ctx));
+        if (ctx->adaptive) { adapt_maxdiag_kernel<<<1, 32, 0, ctx->st>>>(ctx->d_H, (int)ctx->dof, ctx->d_scal + SC_MAXDIAG); ctx->launches++; CK(cudaGetLastError()); }
+        else TRY(DISPATCH(ctx, launch_maxdiag, ctx));
         TRY(fetch_scalars(ctx));
         ctx->lambda = ctx->h_scal[SC_MAXDIAG] * 1e-6;
     }
@@ -1143,7 +1296,7 @@ int nlls_lm_advance(nlls_ctx* ctx, double cost, int64_t terminate, int64_t* conv
         ctx->fails += 1;
         if (ctx->fails == 1) {                                   // :137-144: keep the current (best) variables
             CK(cudaMemcpyAsync(ctx->d_A[ctx->bst], ctx->d_A[ctx->cur], sizeof(double) * ctx->nA * ctx->CS, cudaMemcpyDeviceToDevice, ctx->st));
-            CK(cudaMemcpyAsync(ctx->d_B[ctx->bst], ctx->d_B[ctx->cur], sizeof(double) * ctx->nB * 3, cudaMemcpyDeviceToDevice, ctx->st));
+            CK(cudaMemcpyAsync(ctx->d_B[ctx->bst], ctx->d_B[ctx->cur], sizeof(double) * ctx->nB * ctx->BS, cudaMemcpyDeviceToDevice, ctx->st));
             ctx->have_best = true;
         }
     }
@@ -1207,7 +1360,7 @@ int nlls_get_variables(nlls_ctx* ctx, int vartype, int which, double* aos, int64
     const bool isA = vartype == ctx->vtA;
     if (!isA && vartype != ctx->vtB) return NLLS_ERR_INVALID;
     const int64_t cnt = isA ? ctx->nA : ctx->nB;
-    const int ds = isA ? ctx->CS : 3, ns = isA ? ctx->NC : 3;
+    const int ds = isA ? ctx->CS : ctx->BS, ns = isA ? ctx->NC : ctx->BS;
     if (n != cnt || stride < ns) FAIL(NLLS_ERR_INVALID, "size mismatch in nlls_get_variables");
     if (ds == stride) {
         CK(cudaMemcpyAsync(aos, isA ? ctx->d_A[buf] : ctx->d_B[buf], sizeof(double) * cnt * ds, cudaMemcpyDeviceToHost, ctx->st));
@@ -1223,7 +1376,7 @@ int nlls_get_variables(nlls_ctx* ctx, int vartype, int which, double* aos, int64
 
 int64_t nlls_dof(nlls_ctx* ctx) { return (ctx && ctx->prepared) ? ctx->dof : -1; }
 int64_t nlls_hessian_len(nlls_ctx* ctx) { return (ctx && ctx->prepared) ? ctx->hlen : -1; }
-int64_t nlls_hessian_nblocks(nlls_ctx* ctx) { return (ctx && ctx->prepared) ? ctx->nA + ctx->nB + ctx->nobs : -1; }
+int64_t nlls_hessian_nblocks(nlls_ctx* ctx) { return (ctx && ctx->prepared && !ctx->adaptive) ? ctx->nA + ctx->nB + ctx->nobs : -1; }
 
 }  // extern "C"
 
@@ -1326,6 +1479,7 @@ int nlls_get_hessian_blocks(nlls_ctx* ctx, double* data) {
 
 int nlls_get_hessian_index(nlls_ctx* ctx, int64_t* rowblock, int64_t* colblock, int64_t* start) {
     if (!ctx || !ctx->prepared || !rowblock || !colblock || !start) return NLLS_ERR_INVALID;
+    if (ctx->adaptive) FAIL(NLLS_ERR_UNSUPPORTED, "adaptive problems use the dense layout: nlls_get_hessian_blocks returns the dof x dof matrix");
     int64_t o = 1, k = 0;
     walk_reference_blocks(ctx, [&](int64_t rb, int64_t cb, int rows, int cols, int64_t, bool) {
         rowblock[k] = rb; colblock[k] = cb; start[k] = o; ++k;
@@ -1356,6 +1510,7 @@ int nlls_timer_stop(nlls_ctx* ctx, double* ms) {
 
 int nlls_algorithmic_bytes(nlls_ctx* ctx, int which, double* bytes) {
     if (!ctx || !ctx->prepared || !bytes) return NLLS_ERR_INVALID;
+    if (ctx->adaptive) { *bytes = 8.0 * (double)ctx->nobs; return (which == NLLS_TIME_LINEARIZE || which == NLLS_TIME_COST) ? NLLS_OK : NLLS_ERR_INVALID; }
     const double nobs = (double)ctx->nobs, nA = (double)ctx->nA, nB = (double)ctx->nB, DC = ctx->DC;
     const double rd = nobs * (8 * 2 + 8) + 8 * (nA * ctx->NC + nB * 3);   // measurement + 2 x int32 index, each variable once
     const double wr = 8 * (nobs * DC * 3 + nA * DC * DC + nB * 9 + nA * DC + nB * 3);
@@ -1382,6 +1537,12 @@ int nlls_time_kernels(nlls_ctx* ctx, int which, int reps, int flush_l2, double* 
     for (int r = 0; r < reps; ++r) {
         if (flush_l2) CK(cudaMemsetAsync(ctx->d_flush, r & 0xff, ctx->flush_bytes, ctx->st));
         CK(cudaEventRecord(ctx->ev_t0, ctx->st));
+        if (ctx->adaptive) {
+            if (which == NLLS_TIME_LINEARIZE) TRY(adapt_linearize(ctx));
+            else if (which == NLLS_TIME_COST) TRY(adapt_cost(ctx, ctx->cur, SC_COST_TRY));
+            else if (which == NLLS_TIME_TRY) TRY(enqueue_try(ctx, lambda, false));
+            else return NLLS_ERR_INVALID;
+        } else
         switch (which) {
             case NLLS_TIME_LINEARIZE: TRY(DISPATCH(ctx, launch_linearize, ctx, true, true)); break;
             case NLLS_TIME_LIN_POINT: TRY(DISPATCH(ctx, launch_linearize, ctx, true, false)); break;
