@@ -37,6 +37,7 @@ struct NcclApi {
     int (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
     int (*CommDestroy)(ncclComm_t) = nullptr;
     int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*Broadcast)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     int (*GroupStart)() = nullptr;
     int (*GroupEnd)() = nullptr;
     const char* (*GetErrorString)(int) = nullptr;
@@ -49,10 +50,11 @@ struct NcclApi {
         CommInitRank = (int (*)(ncclComm_t*, int, ncclUniqueId, int))dlsym(h, "ncclCommInitRank");
         CommDestroy = (int (*)(ncclComm_t))dlsym(h, "ncclCommDestroy");
         AllReduce = (int (*)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t))dlsym(h, "ncclAllReduce");
+        Broadcast = (int (*)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t))dlsym(h, "ncclBroadcast");
         GroupStart = (int (*)())dlsym(h, "ncclGroupStart");
         GroupEnd = (int (*)())dlsym(h, "ncclGroupEnd");
         GetErrorString = (const char* (*)(int))dlsym(h, "ncclGetErrorString");
-        return GetUniqueId && CommInitRank && CommDestroy && AllReduce && GroupStart && GroupEnd;
+        return GetUniqueId && CommInitRank && CommDestroy && AllReduce && Broadcast && GroupStart && GroupEnd;
     }
 };
 NcclApi g_nccl;
@@ -394,8 +396,8 @@ int launch_reduced_solve(nlls_ctx* ctx, bool lu) {
         red_permute_kernel<<<(nx + 255) / 256, 256, 0, ctx->st>>>(ctx->d_rhs, ctx->d_xp, ctx->d_pos, ctx->NT, 1); ctx->launches++;
         for (const auto& l : ctx->fact_launches) {   // factorisation + forward substitution (fused into the diagonal tasks)
             if (l.kind == 0) ldl_diag_kernel<<<l.cnt, DIAG_THREADS, DIAG_SMEM, ctx->st>>>(ctx->d_S, ctx->d_Linv, ctx->d_red_tasks + l.off, ctx->d_xp);
-            else if (l.kind == 1) ldl_off_kernel<<<2 * l.cnt, HALF_THREADS, OFF_SMEM, ctx->st>>>(ctx->d_S, ctx->d_Linv, ctx->d_red_tasks + l.off, ctx->d_xp);
-            else ldl_upd_kernel<<<2 * l.cnt, HALF_THREADS, UPD_SMEM, ctx->st>>>(ctx->d_S, ctx->d_red_upds + l.off);
+            else if (l.kind == 1) ldl_off_kernel<<<GEMM_CTAS * l.cnt, GEMM_THREADS, OFF_SMEM, ctx->st>>>(ctx->d_S, ctx->d_Linv, ctx->d_red_tasks + l.off, ctx->d_xp);
+            else ldl_upd_kernel<<<GEMM_CTAS * l.cnt, GEMM_THREADS, UPD_SMEM, ctx->st>>>(ctx->d_S, ctx->d_red_upds + l.off);
             ctx->launches++;
         }
         for (size_t l = ctx->lvl_cols.size(); l-- > 0;) {
@@ -404,6 +406,9 @@ int launch_reduced_solve(nlls_ctx* ctx, bool lu) {
         }
         red_permute_kernel<<<(nx + 255) / 256, 256, 0, ctx->st>>>(ctx->d_xp, ctx->d_rhs, ctx->d_pos, ctx->NT, 0); ctx->launches++;
         CK(cudaGetLastError());
+        // every rank factors the same all-reduced system, but the update kernel's FP64 reductions commute only up to rounding:
+        // rank 0's camera step is broadcast so that the camera replicas stay bit-identical
+        if (ctx->nranks > 1) CKN(g_nccl.Broadcast(ctx->d_rhs, ctx->d_rhs, (size_t)nx, ncclFloat64, 0, ctx->comm, ctx->st));
         return NLLS_OK;
     }
     if (!lu) {

@@ -30,7 +30,6 @@ constexpr int TB = 6;                 // register block edge
 constexpr int TG = ST / TB;           // 12 x 12 blocks per tile
 constexpr int NLB = TG * (TG + 1) / 2;  // 78 lower-triangular blocks
 constexpr int DIAG_THREADS = 224;     // 3 warps of L blocks, 3 warps of Linv blocks, 1 right-hand-side warp
-constexpr int HALF_THREADS = 96;      // off-diagonal / update kernels: 72 workers (6 x 12 blocks of half a tile)
 constexpr int RED_THREADS = 144;      // backward sweep
 
 struct RedSolveLists {        // device pointers for the backward sweep
@@ -237,124 +236,134 @@ __global__ void __launch_bounds__(DIAG_THREADS) ldl_diag_kernel(double* __restri
 }
 
 // ---------------------------------------------------------------------------------------------------
-// Off-diagonal tile (I, J):  L_IJ = T_IJ Linv_J' D_J^-1, i.e. X[i][c] = sum_{k <= c} T[i][k] Linv[c][k] / d_c ; then the
-// right-hand side push b_I -= L_IJ y_J.  Two CTAs per tile (rows 0..35 / 36..71); thread (ty, tx) owns a 6 x 6 block.
+// FP64 tensor-core GEMMs on 72 x 72 tiles (mma.sync.m8n8k4.f64, SASS DMMA).  Measured on B200: a register outer product
+// with three distinct operands issues one DFMA per ~4.7 cycles per SM sub-partition, DMMA sustains 256 FMA per 16.7 cycles
+// (61 FMA/clk/SM, the FP64 peak) — so every tile GEMM of the factorisation goes through DMMA.
+// Both operands are read with the same pattern from column-major tiles staged in shared memory with a row stride of 76
+// doubles (76 / 2 = 6 (mod 16) puts the 4 x 4 fragment rows of a half-warp on 16 distinct 8-byte bank pairs):
+//   A fragment (8 x 4, row):  lane l holds A[l >> 2][l & 3]  =  tileA[(k0 + (l & 3)) * 76 + i0 + (l >> 2)]
+//   B fragment (4 x 8, col):  lane l holds B[l & 3][l >> 2]  =  tileB[(k0 + (l & 3)) * 76 + c0 + (l >> 2)]     (B = tileB')
+//   C fragment (8 x 8):       lane l holds C[l >> 2][2 (l & 3) + {0, 1}]
+// A CTA has 3 warps; warp w of CTA r owns the 8 rows of row block 3 r + w and all 9 column blocks (18 accumulators).
 // ---------------------------------------------------------------------------------------------------
-constexpr size_t OFF_SMEM = (size_t)(2 * ST2 + 2 * ST + TG * (ST / 2)) * sizeof(double);
+constexpr int LDT = 76;
+constexpr int GEMM_THREADS = 96;
+constexpr int GEMM_CTAS = 3;          // CTAs per tile task
+constexpr int NBLK = ST / 8;          // 9 blocks of 8 per tile edge
 
-__global__ void __launch_bounds__(HALF_THREADS) ldl_off_kernel(double* __restrict__ S, const double* __restrict__ Linv, const RedTask* __restrict__ tasks,
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+// tile (contiguous, column-major, leading dimension 72) -> shared memory with leading dimension LDT
+template <int NT_>
+__device__ __forceinline__ void tile_to_smem_ld(double* sdst, const double* gsrc) {
+    for (int q = threadIdx.x; q < ST2 / 2; q += NT_) {
+        const int k = q / (ST / 2), c = q - k * (ST / 2);
+        cp_async16(sdst + k * LDT + 2 * c, gsrc + k * ST + 2 * c);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Off-diagonal tile (I, J):  L_IJ = T_IJ Linv_J' D_J^-1, i.e. X[i][c] = sum_{k <= c} T[i][k] Linv[c][k] / d_c ; then the
+// right-hand side push b_I -= L_IJ y_J.
+// ---------------------------------------------------------------------------------------------------
+constexpr size_t OFF_SMEM = (size_t)(2 * ST * LDT + 2 * ST) * sizeof(double);
+
+__global__ void __launch_bounds__(GEMM_THREADS) ldl_off_kernel(double* __restrict__ S, const double* __restrict__ Linv, const RedTask* __restrict__ tasks,
                                                                double* __restrict__ xp) {
     extern __shared__ __align__(16) double sm[];
     double* As = sm;                  // T_IJ   [k][i]
-    double* Bs = sm + ST2;            // Linv_J [k][c]
-    double* Ds = sm + 2 * ST2;        // [ST] 1 / D_J
+    double* Bs = sm + ST * LDT;       // Linv_J [k][c]
+    double* Ds = Bs + ST * LDT;       // [ST] 1 / D_J
     double* ys = Ds + ST;             // [ST] y_J
-    double* part = ys + ST;           // [TG][ST / 2]
-    const int tid = threadIdx.x, half = blockIdx.x & 1;
-    const RedTask tk = tasks[blockIdx.x >> 1];
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const RedTask tk = tasks[blockIdx.x / GEMM_CTAS];
+    const int I = GEMM_CTAS * (blockIdx.x % GEMM_CTAS) + w;      // row block of this warp
     double* T = S + (size_t)tk.tile * ST2;
-    tile_to_smem<HALF_THREADS>(As, T);
-    tile_to_smem<HALF_THREADS>(Bs, Linv + (size_t)tk.col * ST2);
+    tile_to_smem_ld<GEMM_THREADS>(As, T);
+    tile_to_smem_ld<GEMM_THREADS>(Bs, Linv + (size_t)tk.col * ST2);
     if (tid < ST) {
         Ds[tid] = rcp_fast(S[(size_t)tk.dtile * ST2 + (size_t)(ST + 1) * tid]);
         ys[tid] = xp[(size_t)tk.col * ST + tid];
     }
     cp_async_wait_all();
     __syncthreads();
-    const bool work = tid < (TG / 2) * TG;
-    const int tx = tid % TG, tyl = (tid / TG) % (TG / 2), ty = tyl + (TG / 2) * half;
-    double X[TB][TB];
+    const int fr = lane >> 2, fk = lane & 3;
+    double c0[NBLK], c1[NBLK];
 #pragma unroll
-    for (int a = 0; a < TB; ++a)
+    for (int cb = 0; cb < NBLK; ++cb) { c0[cb] = 0.0; c1[cb] = 0.0; }
+    const double* ap = As + fk * LDT + 8 * I + fr;
+    const double* bp = Bs + fk * LDT + fr;
 #pragma unroll
-        for (int b = 0; b < TB; ++b) X[a][b] = 0.0;
-    if (work) {
-        const int kend = TB * tx + TB;                     // Linv is lower triangular: Linv[c][k] = 0 for k > c
-#pragma unroll 2
-        for (int k = 0; k < kend; ++k) {
-            const double2* ap = reinterpret_cast<const double2*>(As + k * ST + TB * ty);
-            const double2* bp = reinterpret_cast<const double2*>(Bs + k * ST + TB * tx);
-            double av[TB], bv[TB];
+    for (int ks = 0; ks < ST / 4; ++ks) {
+        const double a = ap[ks * 4 * LDT];
 #pragma unroll
-            for (int a = 0; a < TB / 2; ++a) { const double2 q = ap[a]; av[2 * a] = q.x; av[2 * a + 1] = q.y; }
-#pragma unroll
-            for (int b = 0; b < TB / 2; ++b) { const double2 q = bp[b]; bv[2 * b] = q.x; bv[2 * b + 1] = q.y; }
-#pragma unroll
-            for (int a = 0; a < TB; ++a)
-#pragma unroll
-                for (int b = 0; b < TB; ++b) X[a][b] = fma(av[a], bv[b], X[a][b]);
+        for (int cb = 0; cb < NBLK; ++cb) {
+            if (cb < ks / 2) continue;                        // Linv is lower triangular: Linv[c][k] = 0 for k > c
+            dmma884(c0[cb], c1[cb], a, bp[ks * 4 * LDT + 8 * cb]);
         }
-        double pr[TB];
-#pragma unroll
-        for (int a = 0; a < TB; ++a) pr[a] = 0.0;
-#pragma unroll
-        for (int b = 0; b < TB; ++b) {
-            const double rd = Ds[TB * tx + b], yc = ys[TB * tx + b];
-            double2* dst = reinterpret_cast<double2*>(T + (size_t)ST * (TB * tx + b) + TB * ty);
-#pragma unroll
-            for (int a = 0; a < TB; ++a) { X[a][b] *= rd; pr[a] = fma(X[a][b], yc, pr[a]); }
-#pragma unroll
-            for (int a = 0; a < TB / 2; ++a) dst[a] = make_double2(X[2 * a][b], X[2 * a + 1][b]);
-        }
-#pragma unroll
-        for (int a = 0; a < TB; ++a) part[tx * (ST / 2) + TB * tyl + a] = pr[a];
     }
-    __syncthreads();
-    if (tid < ST / 2) {
-        double s = 0.0;
+    // scale by 1 / d_c, store L_IJ, and push the right-hand side:  b_I -= L_IJ y_J
+    double pr = 0.0;
 #pragma unroll
-        for (int c = 0; c < TG; ++c) s += part[c * (ST / 2) + tid];
-        atomicAdd(xp + (size_t)tk.row * ST + (ST / 2) * half + tid, -s);
+    for (int cb = 0; cb < NBLK; ++cb) {
+        const int c = 8 * cb + 2 * fk;
+        const double x0 = c0[cb] * Ds[c], x1 = c1[cb] * Ds[c + 1];
+        T[(size_t)ST * c + 8 * I + fr] = x0;
+        T[(size_t)ST * (c + 1) + 8 * I + fr] = x1;
+        pr = fma(x0, ys[c], pr);
+        pr = fma(x1, ys[c + 1], pr);
     }
+    pr += __shfl_xor_sync(0xffffffffu, pr, 1);
+    pr += __shfl_xor_sync(0xffffffffu, pr, 2);
+    if (fk == 0) atomicAdd(xp + (size_t)tk.row * ST + 8 * I + fr, -pr);
 }
 
 // ---------------------------------------------------------------------------------------------------
-// Update  T_{ab} -= (L_aJ D_J) L_bJ'  for one pair of rows of column J.  Two CTAs per pair (target rows 0..35 / 36..71);
-// results are subtracted from the target tile with FP64 reductions (several columns of a level can hit the same tile).
+// Update  T_{ab} -= (L_aJ D_J) L_bJ'  for one pair of rows of column J; results are subtracted from the target tile with FP64
+// reductions (several columns of a level can hit the same tile).
 // ---------------------------------------------------------------------------------------------------
-constexpr size_t UPD_SMEM = (size_t)(2 * ST2 + ST) * sizeof(double);
+constexpr size_t UPD_SMEM = (size_t)(2 * ST * LDT + ST) * sizeof(double);
 
-__global__ void __launch_bounds__(HALF_THREADS) ldl_upd_kernel(double* __restrict__ S, const RedUpd* __restrict__ upds) {
+__global__ void __launch_bounds__(GEMM_THREADS) ldl_upd_kernel(double* __restrict__ S, const RedUpd* __restrict__ upds) {
     extern __shared__ __align__(16) double sm[];
     double* As = sm;                  // L_aJ [k][i]
-    double* Bs = sm + ST2;            // L_bJ [k][c]
-    double* Ds = sm + 2 * ST2;        // [ST] D_J
-    const int tid = threadIdx.x, half = blockIdx.x & 1;
-    const RedUpd up = upds[blockIdx.x >> 1];
-    tile_to_smem<HALF_THREADS>(As, S + (size_t)up.a * ST2);
-    if (up.b != up.a) tile_to_smem<HALF_THREADS>(Bs, S + (size_t)up.b * ST2);
+    double* Bs = sm + ST * LDT;       // L_bJ [k][c]
+    double* Ds = Bs + ST * LDT;       // [ST] D_J
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const RedUpd up = upds[blockIdx.x / GEMM_CTAS];
+    const int I = GEMM_CTAS * (blockIdx.x % GEMM_CTAS) + w;
+    const bool diag = up.b == up.a;
+    tile_to_smem_ld<GEMM_THREADS>(As, S + (size_t)up.a * ST2);
+    if (!diag) tile_to_smem_ld<GEMM_THREADS>(Bs, S + (size_t)up.b * ST2);
     if (tid < ST) Ds[tid] = S[(size_t)up.dk * ST2 + (size_t)(ST + 1) * tid];
     cp_async_wait_all();
     __syncthreads();
-    const double* Bt = (up.b != up.a) ? Bs : As;
-    const int tx = tid % TG, tyl = (tid / TG) % (TG / 2), ty = tyl + (TG / 2) * half;
-    const bool work = tid < (TG / 2) * TG && (up.b != up.a || ty >= tx);   // diagonal targets: lower blocks only
-    if (!work) return;
-    double X[TB][TB];
+    const double* Bt = diag ? As : Bs;
+    const int fr = lane >> 2, fk = lane & 3;
+    const int ncb = diag ? I + 1 : NBLK;                      // diagonal targets: lower blocks only
+    double c0[NBLK], c1[NBLK];
 #pragma unroll
-    for (int a = 0; a < TB; ++a)
+    for (int cb = 0; cb < NBLK; ++cb) { c0[cb] = 0.0; c1[cb] = 0.0; }
+    const double* ap = As + fk * LDT + 8 * I + fr;
+    const double* bp = Bt + fk * LDT + fr;
 #pragma unroll
-        for (int b = 0; b < TB; ++b) X[a][b] = 0.0;
-#pragma unroll 2
-    for (int k = 0; k < ST; ++k) {
-        const double dk = Ds[k];
-        const double2* ap = reinterpret_cast<const double2*>(As + k * ST + TB * ty);
-        const double2* bp = reinterpret_cast<const double2*>(Bt + k * ST + TB * tx);
-        double av[TB], bv[TB];
+    for (int ks = 0; ks < ST / 4; ++ks) {
+        const double a = ap[ks * 4 * LDT] * Ds[4 * ks + fk];
 #pragma unroll
-        for (int a = 0; a < TB / 2; ++a) { const double2 q = ap[a]; av[2 * a] = q.x * dk; av[2 * a + 1] = q.y * dk; }
-#pragma unroll
-        for (int b = 0; b < TB / 2; ++b) { const double2 q = bp[b]; bv[2 * b] = q.x; bv[2 * b + 1] = q.y; }
-#pragma unroll
-        for (int a = 0; a < TB; ++a)
-#pragma unroll
-            for (int b = 0; b < TB; ++b) X[a][b] = fma(av[a], bv[b], X[a][b]);
+        for (int cb = 0; cb < NBLK; ++cb) {
+            if (cb >= ncb) continue;
+            dmma884(c0[cb], c1[cb], a, bp[ks * 4 * LDT + 8 * cb]);
+        }
     }
     double* T = S + (size_t)up.target * ST2;
 #pragma unroll
-    for (int b = 0; b < TB; ++b)
-#pragma unroll
-        for (int a = 0; a < TB; ++a) atomicAdd(T + (size_t)ST * (TB * tx + b) + TB * ty + a, -X[a][b]);
+    for (int cb = 0; cb < NBLK; ++cb) {
+        if (cb >= ncb) continue;
+        const int c = 8 * cb + 2 * fk;
+        atomicAdd(T + (size_t)ST * c + 8 * I + fr, -c0[cb]);
+        atomicAdd(T + (size_t)ST * (c + 1) + 8 * I + fr, -c1[cb]);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------
