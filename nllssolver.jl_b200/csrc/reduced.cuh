@@ -29,7 +29,6 @@ constexpr int ST2 = ST * ST;
 constexpr int TB = 6;                 // register block edge
 constexpr int TG = ST / TB;           // 12 x 12 blocks per tile
 constexpr int NLB = TG * (TG + 1) / 2;  // 78 lower-triangular blocks
-constexpr int DIAG_THREADS = 224;     // 3 warps of L blocks, 3 warps of Linv blocks, 1 right-hand-side warp
 constexpr int RED_THREADS = 144;      // backward sweep
 
 struct RedSolveLists {        // device pointers for the backward sweep
@@ -65,177 +64,6 @@ __device__ __forceinline__ void tile_to_smem(double* sdst, const double* gsrc) {
 }
 
 // ---------------------------------------------------------------------------------------------------
-// Diagonal tile.  Warp roles (warp w runs on SM sub-partition w % 4; early-finishing and late-starting warps share one):
-//   w0 = L blocks 52..77   w1 = Linv blocks 52..77   w2 = L blocks 26..51   w3 = Linv blocks 26..51
-//   w4 = L blocks 0..25    w5 = Linv blocks 0..25    w6 = right-hand side
-// L blocks are numbered by (tx, ty) ascending — block (ty, tx) is touched by pivots j < 6 tx + 6, so low numbers retire first;
-// Linv blocks by (ty, tx) ascending — block (ty, tx) is touched by pivots 6 tx <= j < 6 ty + 6.
-// A single warp issues dependent instructions ~5 cycles apart, so the per-pivot instruction count is what matters:
-//   * finished entries are "retired" to shared memory the moment they are final (column j of L, row j+1 of Linv, d_j), after
-//     which their registers may hold garbage — the rank-1 updates then need no row / column masks at all;
-//   * every role has its own loop (named barrier, explicit thread count), so nothing role-dependent is re-evaluated per pivot;
-//   * the next pivot and its reciprocal are computed by every thread in the shadow of the 36 updates, only the owner stores.
-// ---------------------------------------------------------------------------------------------------
-constexpr int LDM = ST + 1;           // padded row stride of the Linv staging tile (conflict-free transposed read-out)
-constexpr size_t DIAG_SMEM = (size_t)(ST2 + ST * LDM + 5 * ST + 4) * sizeof(double);
-
-__device__ __forceinline__ void diag_bar() { asm volatile("bar.sync 1, %0;" ::"n"(DIAG_THREADS) : "memory"); }
-
-__global__ void __launch_bounds__(DIAG_THREADS) ldl_diag_kernel(double* __restrict__ S, double* __restrict__ Linv, const RedTask* __restrict__ tasks,
-                                                                double* __restrict__ xp) {
-    extern __shared__ __align__(16) double sm[];
-    double* As = sm;                  // the tile as stored (column-major); retired columns of L overwrite it
-    double* Ms = sm + ST2;            // [ST][LDM] retired rows of M = L^-1
-    double* colA = Ms + ST * LDM;     // [2][ST] published column of A
-    double* rowM = colA + 2 * ST;     // [2][ST] published row of M
-    double* dbuf = rowM + 2 * ST;     // [ST] pivots
-    double* rdb = dbuf + ST;          // [2] published pivot reciprocal
-    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-    const RedTask tk = tasks[blockIdx.x];
-    double* T = S + (size_t)tk.tile * ST2;
-    tile_to_smem<DIAG_THREADS>(As, T);
-
-    const int kind = (w == 6) ? 2 : (w & 1);              // 0: L blocks, 1: Linv blocks, 2: right-hand side
-    const int grp = 2 - (w >> 1);                         // block group 0..2
-    const bool has_blk = kind < 2 && lane < NLB / 3;
-    int ty = 0, tx = 0;
-    if (kind < 2) {
-        int n = (NLB / 3) * grp + min(lane, NLB / 3 - 1);
-        if (kind == 0) { while (n >= TG - tx) { n -= TG - tx; ++tx; } ty = tx + n; }      // by tx, then ty
-        else { while (n >= ty + 1) { n -= ty + 1; ++ty; } tx = n; }                          // by ty, then tx
-    }
-    double v[3] = {0.0, 0.0, 0.0};
-    if (kind == 2) {
-#pragma unroll
-        for (int s3 = 0; s3 < 3; ++s3) if (lane + 32 * s3 < ST) v[s3] = xp[(size_t)tk.col * ST + lane + 32 * s3];
-    }
-    cp_async_wait_all();
-    __syncthreads();
-    double B[TB][TB];                                     // L block (kind 0) or Linv block (kind 1)
-#pragma unroll
-    for (int a = 0; a < TB; ++a)
-#pragma unroll
-        for (int b = 0; b < TB; ++b) B[a][b] = (kind == 0) ? As[(TB * tx + b) * ST + TB * ty + a] : ((ty == tx && a == b) ? 1.0 : 0.0);
-    if (kind == 0 && has_blk && tx == 0) {
-#pragma unroll
-        for (int a = 0; a < TB; ++a) colA[TB * ty + a] = B[a][0];
-        if (ty == 0) { rdb[0] = rcp_fast(B[0][0]); dbuf[0] = B[0][0]; }
-    }
-    if (kind == 1 && has_blk && ty == 0) {
-#pragma unroll
-        for (int b = 0; b < TB; ++b) { rowM[b] = B[0][b]; Ms[b] = B[0][b]; }
-    }
-    __syncthreads();                                      // every thread holds its block: As may now receive retired columns
-
-    if (kind == 0) {
-        // ---------------- L blocks: rank-1 update, retire column j, publish column j + 1 and its pivot ----------------
-        const int last_j = grp == 0 ? 17 : (grp == 1 ? 35 : ST - 1);
-        const double* cty = colA + TB * ty;
-        const double* ctx = colA + TB * tx;
-        for (int jb = 0; jb < TG; ++jb) {
-            const bool live = has_blk && tx >= jb;
-            const bool own = live && tx == jb;
-#pragma unroll
-            for (int jj = 0; jj < TB; ++jj) {
-                const int j = TB * jb + jj, buf = j & 1, nb = buf ^ 1;
-                const int jn = (jj + 1) % TB;
-                diag_bar();
-                if (j > last_j || !live) continue;
-                const double rd = rdb[buf];
-                double li[TB], ck[TB];
-#pragma unroll
-                for (int a = 0; a < TB / 2; ++a) {
-                    const double2 q = reinterpret_cast<const double2*>(cty + buf * ST)[a];
-                    li[2 * a] = q.x * rd; li[2 * a + 1] = q.y * rd;
-                    const double2 r2 = reinterpret_cast<const double2*>(ctx + buf * ST)[a];
-                    ck[2 * a] = r2.x; ck[2 * a + 1] = r2.y;
-                }
-                // next pivot (meaningful on its diagonal block only) and its reciprocal, in the shadow of the updates
-                const double dn = fma(-li[jn], ck[jn], B[jn][jn]);
-                const double rn = rcp_fast(dn);
-                const bool own_next = (jj + 1 < TB) ? own : (has_blk && tx == jb + 1);
-                if (own_next && ty == tx) { rdb[nb] = rn; dbuf[j + 1 < ST ? j + 1 : j] = dn; }
-#pragma unroll
-                for (int b = 0; b < TB; ++b)
-#pragma unroll
-                    for (int a = 0; a < TB; ++a) B[a][b] = fma(-li[a], ck[b], B[a][b]);
-                if (own) {                                  // column j of L is final: retire it
-                    double2* dst = reinterpret_cast<double2*>(As + j * ST + TB * ty);
-#pragma unroll
-                    for (int a = 0; a < TB / 2; ++a) dst[a] = make_double2(li[2 * a], li[2 * a + 1]);
-                }
-                if (own_next) {
-                    double2* dst = reinterpret_cast<double2*>(colA + nb * ST + TB * ty);
-#pragma unroll
-                    for (int a = 0; a < TB / 2; ++a) dst[a] = make_double2(B[2 * a][jn], B[2 * a + 1][jn]);
-                }
-            }
-        }
-    } else if (kind == 1) {
-        // ---------------- Linv blocks: the same row operations on the identity; retire / publish row j + 1 ----------------
-        const int last_j = grp == 0 ? 41 : (grp == 1 ? 59 : ST - 1);
-        const double* cty = colA + TB * ty;
-        const double* rtx = rowM + TB * tx;
-        for (int jb = 0; jb < TG; ++jb) {
-            const bool live = has_blk && tx <= jb && ty >= jb;
-#pragma unroll
-            for (int jj = 0; jj < TB; ++jj) {
-                const int j = TB * jb + jj, buf = j & 1, nb = buf ^ 1;
-                const int jn = (jj + 1) % TB;
-                diag_bar();
-                if (j > last_j) continue;
-                if (live) {
-                    const double rd = rdb[buf];
-                    double li[TB], mr[TB];
-#pragma unroll
-                    for (int a = 0; a < TB / 2; ++a) {
-                        const double2 q = reinterpret_cast<const double2*>(cty + buf * ST)[a];
-                        li[2 * a] = q.x * rd; li[2 * a + 1] = q.y * rd;
-                        const double2 r2 = reinterpret_cast<const double2*>(rtx + buf * ST)[a];
-                        mr[2 * a] = r2.x; mr[2 * a + 1] = r2.y;
-                    }
-#pragma unroll
-                    for (int b = 0; b < TB; ++b)
-#pragma unroll
-                        for (int a = 0; a < TB; ++a) B[a][b] = fma(-li[a], mr[b], B[a][b]);
-                }
-                // row j + 1 of M is final now: retire and publish it
-                const bool own_next = has_blk && ((jj + 1 < TB) ? (live && ty == jb) : (ty == jb + 1 && tx <= jb + 1));
-                if (own_next) {
-#pragma unroll
-                    for (int b = 0; b < TB; ++b) { rowM[nb * ST + TB * tx + b] = B[jn][b]; Ms[(j + 1) * LDM + TB * tx + b] = B[jn][b]; }
-                }
-            }
-        }
-    } else {
-        // ---------------- right-hand side: forward substitution carried as an extra column, v_i -= l_ij v_j ----------------
-        for (int j = 0; j < ST; ++j) {
-            const int buf = j & 1;
-            diag_bar();
-            const double rd = rdb[buf];
-            const int sj = j >> 5;
-            const double vsel = (sj == 0) ? v[0] : (sj == 1 ? v[1] : v[2]);
-            const double vj = __shfl_sync(0xffffffffu, vsel, j & 31);
-#pragma unroll
-            for (int s3 = 0; s3 < 3; ++s3) {
-                const int i = lane + 32 * s3;
-                if (i > j && i < ST) v[s3] = fma(-(colA[buf * ST + i] * rd), vj, v[s3]);
-            }
-        }
-#pragma unroll
-        for (int s3 = 0; s3 < 3; ++s3) if (lane + 32 * s3 < ST) xp[(size_t)tk.col * ST + lane + 32 * s3] = v[s3];
-    }
-    __syncthreads();
-    // ---- write L (strict lower) + D (diagonal) and Linv (lower incl. the unit diagonal; the upper triangle stays zero)
-    double* Li = Linv + (size_t)tk.col * ST2;
-    for (int e = tid; e < ST2; e += DIAG_THREADS) {
-        const int i = e % ST, k = e / ST;
-        if (i > k) { T[e] = As[e]; Li[e] = Ms[i * LDM + k]; }
-        else if (i == k) { T[e] = dbuf[k]; Li[e] = 1.0; }
-    }
-}
-
-// ---------------------------------------------------------------------------------------------------
 // FP64 tensor-core GEMMs on 72 x 72 tiles (mma.sync.m8n8k4.f64, SASS DMMA).  Measured on B200: a register outer product
 // with three distinct operands issues one DFMA per ~4.7 cycles per SM sub-partition, DMMA sustains 256 FMA per 16.7 cycles
 // (61 FMA/clk/SM, the FP64 peak) — so every tile GEMM of the factorisation goes through DMMA.
@@ -261,6 +89,233 @@ __device__ __forceinline__ void tile_to_smem_ld(double* sdst, const double* gsrc
         const int k = q / (ST / 2), c = q - k * (ST / 2);
         cp_async16(sdst + k * LDT + 2 * c, gsrc + k * ST + 2 * c);
     }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Diagonal tile: blocked right-looking LDL' with panels of 8 columns (9 panels), everything in shared memory, with look-ahead:
+//   A1 (warp 0)        LDL' of the next 8 x 8 diagonal block in registers (lane = row; pivot row / reciprocal broadcast by
+//                      shuffles, the next reciprocal issued before the bulk of the current update) together with
+//                      N11 = L11^-1 (the same row operations on an 8 x 8 identity) — runs while warps 1-7 do B / C of the
+//                      current panel;
+//   A2 (all warps)     L21 = A21 N11' D^-1  as DMMA products, one 8-row block per warp;
+//   B  (warps 1-7)     trailing update  A22 -= L21 D L21'  as DMMA rank-8 updates (warp 0 updates the next diagonal block itself);
+//   C  (warps 1-7)     R = [ I | b_J ] is carried along:  Mfin[panel rows] = N11 R[panel rows],  R[rows below] -= L21 Mfin[panel rows].
+// Mfin ends up as [ Linv_J | y_J ]: L_JJ^-1 and the forward-substituted right-hand side.  Two barriers per panel; a per-pivot
+// register formulation measured 25 us per tile (one warp issues dependent FP64 instructions ~5 cycles apart).
+// ---------------------------------------------------------------------------------------------------
+constexpr int DIAG_THREADS = 512;                          // many warps: one warp issues dependent instructions only every ~5 cycles
+constexpr int DIAG_WARPS = DIAG_THREADS / 32;
+constexpr int MCOLS = ST + 8;                              // Linv columns + one block holding the right-hand side
+
+// Static task table of the B / C phase (element offsets precomputed: a warp spends its time in dependent integer
+// instructions otherwise).  For panel p, entry t = {kind, o0, o1, o2}:
+//   kind 0  trailing block (I, J):            C at As + o0,  A operand rows at As + o1,  B operand rows at As + o2
+//   kind 1  Mfin[p][J] = N11 R[p][J]:         R operand at Rs + o0,  output at Mf + o1
+//   kind 2  R[I][J] -= L21[I] (N11 R[p][J]):  R operand at Rs + o0,  C at Rs + o1,  A operand rows at As + o2
+// (lane-dependent parts are added by the kernel: fragment row / k offsets.)
+struct DiagTaskTable {
+    int n[NBLK];
+    int v[NBLK][64][4];
+    constexpr DiagTaskTable() : n(), v() {
+        for (int p = 0; p < NBLK; ++p) {
+            const int nb = NBLK - 1 - p, c0 = 8 * p;
+            int c = 0;
+            for (int I = 0; I < nb; ++I)
+                for (int J = (I == 0) ? 1 : 0; J <= I; ++J) {       // (0, 0) = the next diagonal block, left to warp 0
+                    const int gi = 8 * (p + 1 + I), gj = 8 * (p + 1 + J);
+                    v[p][c][0] = 0; v[p][c][1] = gj * LDT + gi; v[p][c][2] = c0 * LDT + gi; v[p][c][3] = c0 * LDT + gj; ++c;
+                }
+            for (int jj = 0; jj < p + 2; ++jj)
+                for (int ii = 0; ii <= nb; ++ii) {
+                    const int J = (jj == p + 1) ? NBLK : jj, I = p + ii;
+                    v[p][c][0] = ii == 0 ? 1 : 2; v[p][c][1] = 8 * J * LDT + c0;
+                    v[p][c][2] = ii == 0 ? 8 * J * LDT + c0 : 8 * J * LDT + 8 * I; v[p][c][3] = c0 * LDT + 8 * I; ++c;
+                }
+            n[p] = c;
+        }
+    }
+};
+__constant__ DiagTaskTable c_diag_tasks = DiagTaskTable();
+constexpr size_t DIAG_SMEM = (size_t)(ST * LDT + 2 * MCOLS * LDT + 2 * 128 + ST + 16 + DIAG_WARPS * 64) * sizeof(double);
+
+#ifdef LDL_PROFILE
+#define LDL_STAMP(i) do { if (threadIdx.x == 0) prof[i] = clock64(); } while (0)
+#define LDL_T0() t_ph = clock64()
+#define LDL_ACC(i) do { const long long t_now = clock64(); t_acc[(i) - 64] += t_now - t_ph; t_ph = t_now; } while (0)
+#else
+#define LDL_STAMP(i)
+#define LDL_T0()
+#define LDL_ACC(i)
+#endif
+
+// LDL' of the 8 x 8 block at (c0, c0) of As, N11 = L11^-1 and W = N11' D^-1 (one warp).  Lane (r, g) = 4 r + g owns columns
+// 2 g, 2 g + 1 of row r of both the block and N11, so a pivot costs 6 shuffles, one reciprocal and 4 FMAs per lane; the
+// critical chain per pivot is reciprocal -> l = a / d -> next pivot element -> shuffle.
+__device__ __forceinline__ void diag_block_factor(double* As, int c0, double* N11, double* W11, double* dpan, double* dall) {
+    const int lane = threadIdx.x & 31, r = lane >> 2, g = lane & 3;
+    double P[2], N[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) { P[e] = As[(c0 + 2 * g + e) * LDT + c0 + r]; N[e] = (r == 2 * g + e) ? 1.0 : 0.0; }
+    double rdrow = 0.0;                                                     // 1 / d_r
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int gj = j >> 1, ej = j & 1;                                  // column j lives in lanes (., gj), slot ej
+        const double d = __shfl_sync(0xffffffffu, P[ej], 4 * j + gj);
+        const double rd = rcp_fast(d);
+        const double arj = __shfl_sync(0xffffffffu, P[ej], (lane & ~3) | gj);          // A[r][j]
+        const double ak0 = __shfl_sync(0xffffffffu, P[ej], 4 * (2 * g) + gj);          // A[2g][j], A[2g+1][j]
+        const double ak1 = __shfl_sync(0xffffffffu, P[ej], 4 * (2 * g + 1) + gj);
+        const double nj0 = __shfl_sync(0xffffffffu, N[0], 4 * j + g);                  // N[j][2g], N[j][2g+1]
+        const double nj1 = __shfl_sync(0xffffffffu, N[1], 4 * j + g);
+        if (lane == 4 * j) { dpan[j] = d; dall[c0 + j] = d; }
+        if (r == j) rdrow = rd;
+        if (r > j) {
+            const double li = arj * rd;
+            if (2 * g > j) P[0] = fma(-li, ak0, P[0]);
+            if (2 * g + 1 > j) P[1] = fma(-li, ak1, P[1]);
+            if (2 * g == j) P[0] = li;
+            if (2 * g + 1 == j) P[1] = li;
+            if (2 * g <= j) N[0] = fma(-li, nj0, N[0]);
+            if (2 * g + 1 <= j) N[1] = fma(-li, nj1, N[1]);
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+        const int k = 2 * g + e;
+        if (k < r) As[(c0 + k) * LDT + c0 + r] = P[e];                      // L11, strict lower
+        N11[r * 8 + k] = N[e];
+        W11[k * 8 + r] = N[e] * rdrow;                                      // W = N11' D^-1  (L21 = A21 W)
+    }
+}
+
+__global__ void __launch_bounds__(DIAG_THREADS) ldl_diag_kernel(double* __restrict__ S, double* __restrict__ Linv, const RedTask* __restrict__ tasks,
+                                                                double* __restrict__ xp
+#ifdef LDL_PROFILE
+                                                                , long long* prof
+#endif
+                                                                ) {
+    extern __shared__ __align__(16) double sm[];
+    LDL_STAMP(0);
+#ifdef LDL_PROFILE
+    long long t_ph = 0, t_acc[6] = {0, 0, 0, 0, 0, 0};
+#endif
+    double* As = sm;                     // [k][i], leading dimension LDT
+    double* Rs = As + ST * LDT;          // R (working right-hand sides [ I | b ]), column-major: Rs[col * LDT + row], MCOLS columns
+    double* Mf = Rs + MCOLS * LDT;       // finished rows of [ Linv | y ], same layout
+    double* NW = Mf + MCOLS * LDT;       // 2 x { N11 [8][8] row-major, W11 [8][8] (W[k * 8 + c] = N11[c][k] / d_c) }
+    double* dall = NW + 2 * 128;         // [ST] pivots
+    double* dpan2 = dall + ST;           // 2 x [8] pivots of a panel
+    double* scr = dpan2 + 16;            // per-warp 8 x 8 scratch (C-fragment -> B-fragment layout change)
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int fr = lane >> 2, fk = lane & 3;
+    const RedTask tk = tasks[blockIdx.x];
+    double* T = S + (size_t)tk.tile * ST2;
+    tile_to_smem_ld<DIAG_THREADS>(As, T);
+    for (int q = tid; q < MCOLS * LDT / 2; q += DIAG_THREADS) reinterpret_cast<double2*>(Rs)[q] = make_double2(0.0, 0.0);
+    const double bval = (tid < ST) ? xp[(size_t)tk.col * ST + tid] : 0.0;
+    __syncthreads();
+    if (tid < ST) { Rs[tid * LDT + tid] = 1.0; Rs[ST * LDT + tid] = bval; }
+    cp_async_wait_all();
+    __syncthreads();
+    LDL_STAMP(1);
+    if (w == 0) diag_block_factor(As, 0, NW, NW + 64, dpan2, dall);
+    __syncthreads();
+
+    for (int p = 0; p < NBLK; ++p) {
+        const int c0 = 8 * p, pb = p & 1;
+        const double* N11 = NW + pb * 128;
+        const double* W11 = N11 + 64;
+        const double* dpan = dpan2 + 8 * pb;
+        LDL_T0();
+        // ---------------- A2: L21 = A21 W, one 8-row block per warp (in place)
+        for (int I = p + 1 + w; I < NBLK; I += DIAG_WARPS) {
+            double c0r = 0.0, c1r = 0.0, aq[2];
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks) aq[ks] = As[(c0 + 4 * ks + fk) * LDT + 8 * I + fr];
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks) dmma884(c0r, c1r, aq[ks], W11[(4 * ks + fk) * 8 + fr]);
+            __syncwarp();
+            double* cp = As + (c0 + 2 * fk) * LDT + 8 * I + fr;
+            cp[0] = c0r; cp[LDT] = c1r;
+        }
+        LDL_ACC(64);
+        __syncthreads();
+        LDL_ACC(65);
+        const int nb = NBLK - 1 - p;                                            // block rows below the panel
+        if (w == 0) {
+            // ---------------- look-ahead: update the next diagonal block, then factor it (A1 of panel p + 1)
+            if (nb > 0) {
+                const int g = c0 + 8;
+                double* cp = As + (g + 2 * fk) * LDT + g + fr;
+                double c0r = cp[0], c1r = cp[LDT];
+#pragma unroll
+                for (int ks = 0; ks < 2; ++ks) {
+                    const double a = -(As[(c0 + 4 * ks + fk) * LDT + g + fr] * dpan[4 * ks + fk]);
+                    dmma884(c0r, c1r, a, As[(c0 + 4 * ks + fk) * LDT + g + fr]);
+                }
+                cp[0] = c0r; cp[LDT] = c1r;
+                __syncwarp();
+                diag_block_factor(As, g, NW + (pb ^ 1) * 128, NW + (pb ^ 1) * 128 + 64, dpan2 + 8 * (pb ^ 1), dall);
+            }
+        } else {
+            // ---------------- B: trailing blocks (I, J), p < J <= I, except the next diagonal block;  C: (I, J) with I >= p and
+            // J in {0..p, rhs}: Mfin[p][J] = N11 R[p][J] (I == p), R[I][J] -= L21[I] (N11 R[p][J]) (I > p)
+            double* my = scr + w * 64;
+            double n11f[2], dpf[2];
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks) { n11f[ks] = N11[fr * 8 + 4 * ks + fk]; dpf[ks] = dpan[4 * ks + fk]; }
+            const int ntask = c_diag_tasks.n[p];
+            const int laneA = fk * LDT + fr, laneC = 2 * fk * LDT + fr, laneR = fr * LDT + fk;
+            for (int t = w - 1; t < ntask; t += DIAG_WARPS - 1) {
+                const int4 td = *reinterpret_cast<const int4*>(c_diag_tasks.v[p][t]);
+                if (td.x == 0) {
+                    double* cp = As + td.y + laneC;
+                    const double* ap = As + td.z + laneA;
+                    const double* bp = As + td.w + laneA;
+                    double c0r = cp[0], c1r = cp[LDT];
+                    dmma884(c0r, c1r, -(ap[0] * dpf[0]), bp[0]);
+                    dmma884(c0r, c1r, -(ap[4 * LDT] * dpf[1]), bp[4 * LDT]);
+                    cp[0] = c0r; cp[LDT] = c1r;
+                } else {
+                    const double* rp = Rs + td.y + laneR;
+                    double m0 = 0.0, m1 = 0.0;                                    // N11 R[p][J]
+                    dmma884(m0, m1, n11f[0], rp[0]);
+                    dmma884(m0, m1, n11f[1], rp[4]);
+                    if (td.x == 1) {
+                        double* cp = Mf + td.z + laneC;
+                        cp[0] = m0; cp[LDT] = m1;
+                    } else {
+                        double* cp = Rs + td.z + laneC;
+                        const double* ap = As + td.w + laneA;
+                        double c0r = cp[0], c1r = cp[LDT];
+                        const double a0 = -ap[0], a1 = -ap[4 * LDT];
+                        __syncwarp();
+                        my[(2 * fk) * 8 + fr] = m0; my[(2 * fk + 1) * 8 + fr] = m1;   // scratch[col][row]
+                        __syncwarp();
+                        dmma884(c0r, c1r, a0, my[fr * 8 + fk]);
+                        dmma884(c0r, c1r, a1, my[fr * 8 + 4 + fk]);
+                        cp[0] = c0r; cp[LDT] = c1r;
+                    }
+                }
+            }
+        }
+        LDL_ACC(66);
+        __syncthreads();
+        LDL_ACC(67);
+    }
+    LDL_STAMP(2);
+    // ---- write L (strict lower) + D (diagonal), Linv (lower incl. the unit diagonal; the upper triangle stays zero) and y_J
+    double* Li = Linv + (size_t)tk.col * ST2;
+    for (int k = w; k < ST; k += DIAG_WARPS)
+        for (int i = k + lane; i < ST; i += 32) {
+            if (i > k) { T[k * ST + i] = As[k * LDT + i]; Li[k * ST + i] = Mf[k * LDT + i]; }
+            else { T[k * ST + i] = dall[k]; Li[k * ST + i] = 1.0; }
+        }
+    if (tid < ST) xp[(size_t)tk.col * ST + tid] = Mf[ST * LDT + tid];
+    LDL_STAMP(3);
+#ifdef LDL_PROFILE
+    if (lane == 0) for (int i = 0; i < 6; ++i) prof[64 + 8 * w + i] = t_acc[i];
+#endif
 }
 
 // ---------------------------------------------------------------------------------------------------

@@ -27,7 +27,12 @@ int main(int argc, char** argv) {
         for (int g = 0; g < NG; ++g) { cudaMemcpy(dS + (size_t)g * n * n, A.data(), 8 * n * n, cudaMemcpyHostToDevice); cudaMemcpy(dx + (size_t)g * n, b.data(), 8 * n, cudaMemcpyHostToDevice); }
         cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
         cudaEventRecord(e0);
+#ifdef LDL_PROFILE
+        cudaMemset(dprof, 0, 8 * 1024);
+        ldl_diag_kernel<<<NG, DIAG_THREADS, DIAG_SMEM>>>(dS, dL, dt, dx, dprof);
+#else
         ldl_diag_kernel<<<NG, DIAG_THREADS, DIAG_SMEM>>>(dS, dL, dt, dx);
+#endif
         cudaEventRecord(e1); cudaEventSynchronize(e1);
         float ms; cudaEventElapsedTime(&ms, e0, e1); best = fminf(best, ms);
     }
@@ -41,5 +46,10 @@ int main(int argc, char** argv) {
     for (int i = 0; i < n; ++i) for (int j = 0; j < n; ++j) { double s = 0; for (int k = 0; k < n; ++k) s += L(i, k) * Li[k + n * j]; e2 = fmax(e2, fabs(s - (i == j))); }
     for (int i = 0; i < n; ++i) { double s = 0; for (int k = 0; k < n; ++k) s += L(i, k) * y[k]; e3 = fmax(e3, fabs(s - b[i])); }
     printf("max |LDL' - A| = %.3e   max |L Linv - I| = %.3e   max |L y - b| = %.3e\n", e1, e2, e3);
+#ifdef LDL_PROFILE
+    std::vector<long long> pr(1024); cudaMemcpy(pr.data(), dprof, 8 * 1024, cudaMemcpyDeviceToHost);
+    printf("prologue %lld  loop %lld  epilogue %lld (cycles)\n", pr[1] - pr[0], pr[2] - pr[1], pr[3] - pr[2]);
+    for (int w = 0; w < 8; ++w) printf("warp %d: A2 %lld  sync %lld  M-tasks (or A1) %lld  sync %lld  T-tasks %lld\n", w, pr[64 + 8 * w], pr[65 + 8 * w], pr[66 + 8 * w], pr[67 + 8 * w], pr[68 + 8 * w]);
+#endif
     return 0;
 }
