@@ -442,11 +442,12 @@ __device__ __forceinline__ void load_span(double* s_dst, const double* gsrc, int
 // blocks, the rhs segment) in registers from shared memory in a fixed order and issues one FP64 reduction per element —
 // the number of global reductions drops by the in-tile multiplicity of a block (~8x on Venice-shaped data).
 // ---------------------------------------------------------------------------------------------------
-constexpr int SCH_OBS = 384;
-constexpr int SCH_PTS = 192;
+constexpr int SCH_OBS = 256;
+constexpr int SCH_PTS = 128;
 constexpr int SCH_THREADS = 256;
 constexpr int SCH_CHUNK = 16;
 constexpr int SCH_CBW = 3;      // block columns per thread: a chunk is processed by DC / SCH_CBW threads
+constexpr int SCH_YS = 3 * SCH_CBW + 1;   // padded stride of one column group of Y = A^-1 W (16-byte aligned rows)
 
 struct SchurChunk {
     long long soff;   // element offset of block element (0,0) in S
@@ -458,7 +459,8 @@ struct SchurChunk {
 struct SchurPlan {
     const int* stile_pt;          // [nstiles + 1]
     const int* chunk_off;         // [nstiles + 1]
-    const SchurChunk* chunks;
+    const int* ent_off;           // [nstiles + 1] entry range of a tile
+    const SchurChunk* chunks;     // per tile sorted by length (long first)
     const unsigned int* ents;     // (i_local << 16) | j_local
     int nstiles;
     long long ld;                 // leading dimension of an S tile (ST) or of the dense S (n)
@@ -470,7 +472,8 @@ struct Schur2Smem {
     static constexpr int ROW = WB * SCH_OBS + 9 * SCH_PTS;
     static constexpr int MAXENT = 2048;    // staged contribution entries per tile (tiles with more read them from global memory)
     static constexpr int MAXCH = 256;      // staged chunk descriptors per tile
-    static constexpr size_t bytes = (size_t)(ROW + 6 * SCH_PTS + 3 * SCH_PTS + 2) * sizeof(double) + (size_t)SCH_OBS * sizeof(unsigned short) + 32 +
+    static constexpr int YSZ = SCH_OBS * (DC / SCH_CBW) * SCH_YS;   // Y = A_p^-1 W per observation, column groups padded
+    static constexpr size_t bytes = (size_t)(ROW + YSZ + 6 * SCH_PTS + 3 * SCH_PTS + 2) * sizeof(double) + (size_t)SCH_OBS * sizeof(unsigned short) + 32 +
                                     (size_t)MAXENT * sizeof(unsigned int) + (size_t)MAXCH * sizeof(SchurChunk);
 };
 
@@ -482,7 +485,8 @@ __global__ void __launch_bounds__(SCH_THREADS, 2) schur2_kernel(DevProblem p, Sc
     static_assert(DC % SCH_CBW == 0, "block columns must split evenly");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* s_row = reinterpret_cast<double*>(smem_raw);
-    double* s_Ai = s_row + Schur2Smem<DC>::ROW;
+    double* s_Y = s_row + Schur2Smem<DC>::ROW;
+    double* s_Ai = s_Y + Schur2Smem<DC>::YSZ;
     double* s_t = s_Ai + 6 * SCH_PTS;
     uint64_t* bar = reinterpret_cast<uint64_t*>(s_t + 3 * SCH_PTS);
     unsigned short* s_pl = reinterpret_cast<unsigned short*>(bar + 2);
@@ -499,8 +503,7 @@ __global__ void __launch_bounds__(SCH_THREADS, 2) schur2_kernel(DevProblem p, Sc
     const int ob0 = p.obs_start[pt0], ob1 = p.obs_start[pt1];
     const int npt = pt1 - pt0, nob = ob1 - ob0;
     const int c0 = sp.chunk_off[t], c1 = sp.chunk_off[t + 1];
-    const int e0 = (c1 > c0) ? sp.chunks[c0].ent0 : 0;
-    const int e1 = (c1 > c0) ? sp.chunks[c1 - 1].ent0 + sp.chunks[c1 - 1].n : 0;
+    const int e0 = sp.ent_off[t], e1 = sp.ent_off[t + 1];
     const bool staged = (c1 - c0) <= Schur2Smem<DC>::MAXCH && (e1 - e0) <= Schur2Smem<DC>::MAXENT;
     const size_t span0 = (size_t)p.hB + (size_t)WB * ob0 + (size_t)9 * pt0;
     load_span(s_row, p.H + span0, WB * nob + 9 * npt, bar, p.use_tma);
@@ -526,6 +529,23 @@ __global__ void __launch_bounds__(SCH_THREADS, 2) schur2_kernel(DevProblem p, Sc
         s_t[3 * q + 2] = inv[2] * g0 + inv[4] * g1 + inv[5] * g2;
     }
     __syncthreads();
+    // Y_i = A_p^-1 W_i once per observation (every pair (i, j) of the point reuses it), stored by column group
+    for (int i = tid; i < nob; i += SCH_THREADS) {
+        const int pl = s_pl[i];
+        const double* w = s_row + WB * i + 9 * pl;
+        const double* ai = s_Ai + 6 * pl;
+        const double i00 = ai[0], i10 = ai[1], i20 = ai[2], i11 = ai[3], i21 = ai[4], i22 = ai[5];
+        double* y = s_Y + (size_t)i * NG * SCH_YS;
+#pragma unroll
+        for (int a = 0; a < DC; ++a) {
+            const double w0 = w[3 * a], w1 = w[3 * a + 1], w2 = w[3 * a + 2];
+            double* ya = y + (a / SCH_CBW) * SCH_YS + 3 * (a % SCH_CBW);
+            ya[0] = fma(i20, w2, fma(i10, w1, i00 * w0));
+            ya[1] = fma(i21, w2, fma(i11, w1, i10 * w0));
+            ya[2] = fma(i22, w2, fma(i21, w1, i20 * w0));
+        }
+    }
+    __syncthreads();
 
     const int nunits = (c1 - c0) * NG;
     for (int u = tid; u < nunits; u += SCH_THREADS) {
@@ -546,16 +566,14 @@ __global__ void __launch_bounds__(SCH_THREADS, 2) schur2_kernel(DevProblem p, Sc
             const int i = (int)(en >> 16), j = (int)(en & 0xffffu);
             const int pl = s_pl[i];
             const double* wi = s_row + WB * i + 9 * pl;
-            const double* wj = s_row + WB * j + 9 * pl + 3 * b0;
-            const double* ai = s_Ai + 6 * pl;
-            const double i00 = ai[0], i10 = ai[1], i20 = ai[2], i11 = ai[3], i21 = ai[4], i22 = ai[5];
-            double T[SCH_CBW][3];   // T = A^-1 W_j (columns b0 .. b0+2)
+            double T[SCH_CBW][3];   // T = A^-1 W_j (columns b0 .. b0+2), precomputed
+            {
+                const double2* yj = reinterpret_cast<const double2*>(s_Y + ((size_t)j * NG + b0 / SCH_CBW) * SCH_YS);
+                double yv[SCH_YS + 1];
 #pragma unroll
-            for (int b = 0; b < SCH_CBW; ++b) {
-                const double w0 = wj[3 * b], w1 = wj[3 * b + 1], w2 = wj[3 * b + 2];
-                T[b][0] = fma(i20, w2, fma(i10, w1, i00 * w0));
-                T[b][1] = fma(i21, w2, fma(i11, w1, i10 * w0));
-                T[b][2] = fma(i22, w2, fma(i21, w1, i20 * w0));
+                for (int q = 0; q < (SCH_YS + 1) / 2; ++q) { const double2 v = yj[q]; yv[2 * q] = v.x; yv[2 * q + 1] = v.y; }
+#pragma unroll
+                for (int b = 0; b < SCH_CBW; ++b) { T[b][0] = yv[3 * b]; T[b][1] = yv[3 * b + 1]; T[b][2] = yv[3 * b + 2]; }
             }
             double t0 = 0.0, t1 = 0.0, t2 = 0.0;
             if (do_rhs) { t0 = s_t[3 * pl]; t1 = s_t[3 * pl + 1]; t2 = s_t[3 * pl + 2]; }
@@ -580,6 +598,248 @@ __global__ void __launch_bounds__(SCH_THREADS, 2) schur2_kernel(DevProblem p, Sc
 #pragma unroll
             for (int a = 0; a < DC; ++a) atomicAdd(rhs + (size_t)ck.cam * DC + a, -racc[a]);
         }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Schur v4: persistent, software-pipelined FP64 tensor-core accumulation over runs of consecutive tiles ("super-tiles").
+// ncu on v2: shared-memory wavefronts at 80 % of peak (half of them bank conflicts — every lane walks its own block's
+// contributions, so the operand rows it reads are scattered), FP64 pipe 33 %, and ~11 us of exposed latency per tile
+// (dependent index loads -> TMA -> inverse -> products, separated by CTA barriers).  Here:
+//  * a WARP owns an S block for a whole super-tile and evaluates  S_ij -= sum_p W_pi' Y_pj  as ONE long GEMM over the
+//    concatenated inner index (contribution, d) with mma.sync.m8n8k4.f64:  A[a][kk] = W_i[d][a]  (rows a < DC of 8),
+//    B[kk][b] = Y_j[d][b]  (b < DC; column DC carries t_p = A_p^-1 g_p, so the rhs segment of a diagonal block falls out of
+//    the same product); four consecutive contributions feed three DMMA steps (12 inner indices).  A fragment load touches
+//    at most two contiguous operand rows, the block accumulator is two registers per lane, and the reductions into S are
+//    issued once per (block, super-tile).  Blocks are dealt to the warps by the host (longest-processing-time first); the
+//    contribution lists are padded to groups of four with entries that point at zeros.
+//  * one CTA per SM walks a contiguous range of tiles with a two-stage pipeline: while the warps run the products of tile k
+//    they also compute Y for tile k+1 (both stages resident), and the TMA bulk loads of tile k+2 (its H span and its
+//    contribution list / per-observation table) are in flight — ONE CTA barrier per tile.
+// A super-tile with more than WARPS * NB distinct blocks (a single unusually wide tile) is walked once per round.
+// ---------------------------------------------------------------------------------------------------
+constexpr int SCH4_WARPS = 16;
+constexpr int SCH4_THREADS = 32 * SCH4_WARPS;
+template <int DC> struct Schur4Cfg {
+    static constexpr int OBS = (DC <= 7) ? 256 : 128;   // tile capacity (observations / points) — two stages must fit 227 KB
+    static constexpr int PTS = OBS / 2;
+    static constexpr int MT = (DC + 7) / 8;         // 8-row fragments of a block
+    static constexpr int NTC = (DC + 1 + 7) / 8;    // 8-column fragments (DC block columns + the rhs column)
+    static constexpr int NB = (MT * NTC == 1) ? 16 : 4;   // block slots per warp (accumulators: NB * MT * NTC * 2 doubles per lane)
+    static constexpr int WB = 3 * DC;
+    static constexpr int YS = WB + 3;               // doubles per observation in s_Y: Y_j (3 x DC, column-major) then t_p
+    static constexpr int ZPAD = 3 * 8 * NTC + 8;    // zeros behind the operand arrays: target of the padding entries
+    static constexpr int ROW = WB * OBS + 9 * PTS;  // doubles of H span per stage
+    static constexpr int ROWS = ROW + 2 + ZPAD + 2; // + slack of an 8-byte-misaligned span, + zeros
+    static constexpr int YSZ = YS * OBS + ZPAD;
+    static constexpr int MAXENT = 2560;             // staged contribution entries per tile (longer lists are read from global memory)
+    static constexpr int BLOB = MAXENT + OBS;       // u32 per stage: [per-observation table | contribution entries]
+    static constexpr size_t bytes = 2 * ((size_t)(ROWS + YSZ) * sizeof(double) + (size_t)BLOB * sizeof(unsigned int)) + 64;
+};
+struct SchurUnit {
+    long long soff;   // element offset of block element (0,0) in S
+    int cam;          // camera of the block row (rhs segment) — used by diagonal blocks
+    int flags;        // bit0: stored transposed; bit1: diagonal block; bit3: slot in use
+};
+struct SchurItem {    // one (tile, round) visit of a CTA, 48 bytes
+    int pt0, npt, ob0, nob;
+    int blob0, ne4, wrow, urow;   // first u32 of the tile's blob, padded entry count, row of wtab, row of units to flush after this item (-1: none)
+    int flags, pad0, pad1, pad2;  // bit0: first item of a (super-tile, round): clear the accumulators; bit1: round 0 (write A_p^-1)
+};
+struct SchurPlan4 {
+    const int* cta_item;          // [ncta + 1]
+    const SchurItem* items;
+    const SchurUnit* units;       // [urow][WARPS * NB]
+    const unsigned int* blob;     // per tile: [nob padded to 4: (first obs of its point << 31) | (obs index behind the point's W blocks << 16) | local point]
+                                  //           [ne4 entries: (smem offset of W_i << 16) | smem offset of Y_j, sorted by block, groups of 4]
+    const unsigned int* wtab;     // [wrow][WARPS * NB]: (first entry relative to the tile << 12) | groups of 4     (20 + 12 bits)
+    long long ld;
+};
+
+template <int DC>
+__global__ void __launch_bounds__(SCH4_THREADS, 1) schur4_kernel(DevProblem p, SchurPlan4 sp, double* __restrict__ S, double* __restrict__ rhs,
+                                                                  double* __restrict__ Ainv_out, double lambda) {
+    using C = Schur4Cfg<DC>;
+    constexpr int WB = C::WB, YS = C::YS, NB = C::NB, MT = C::MT, NTC = C::NTC;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* s_row0 = reinterpret_cast<double*>(smem_raw);                 // [2][ROWS]
+    double* s_Y0 = s_row0 + 2 * C::ROWS;                                  // [2][YSZ]
+    unsigned int* s_blob0 = reinterpret_cast<unsigned int*>(s_Y0 + 2 * C::YSZ);   // [2][BLOB]
+    uint64_t* bar = reinterpret_cast<uint64_t*>(s_blob0 + 2 * C::BLOB);   // [2]
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int ka = sp.cta_item[blockIdx.x], nitem = sp.cta_item[blockIdx.x + 1] - ka;
+    if (nitem <= 0) return;
+    const SchurItem* items = sp.items + ka;
+    const int fr = lane >> 2, fk = lane & 3;
+    // inner index kk = fk of DMMA step s within a group of four contributions: contribution (4 s + fk) / 3, coordinate (4 s + fk) % 3
+    const int d0 = fk % 3, d1 = (4 + fk) % 3, d2 = (8 + fk) % 3;
+
+    if (tid == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); }
+    for (int i = tid; i < 2 * C::ZPAD; i += SCH4_THREADS) {
+        const int st = i / C::ZPAD, k = i - st * C::ZPAD;
+        s_Y0[st * C::YSZ + YS * C::OBS + k] = 0.0;
+    }
+    for (int i = tid; i < 2 * (C::ZPAD + 2); i += SCH4_THREADS) {
+        const int st = i / (C::ZPAD + 2), k = i - st * (C::ZPAD + 2);
+        s_row0[st * C::ROWS + C::ROW + 2 + k] = 0.0;
+    }
+    __syncthreads();
+
+    auto issue = [&](int k) {   // thread 0: TMA bulk loads of item k into stage k & 1
+        const SchurItem it = items[k];
+        const int st = k & 1;
+        const int mis = (it.flags >> 2) & 1;   // the span starts 8 bytes off a 16-byte boundary: load from the element before it
+        const double* gsrc = p.H + (size_t)p.hB + (size_t)WB * it.ob0 + (size_t)9 * it.pt0 - mis;
+        const uint32_t span = (uint32_t)((WB * it.nob + 9 * it.npt + mis + 1) & ~1) * 8u;
+        const uint32_t nob4 = (uint32_t)((it.nob + 3) & ~3);
+        const uint32_t bl = (nob4 + (it.ne4 <= C::MAXENT ? (uint32_t)it.ne4 : 0u)) * 4u;
+        mbar_expect_tx(&bar[st], span + bl);
+        bulk_load(s_row0 + st * C::ROWS, gsrc, span, &bar[st]);
+        if (bl) bulk_load(s_blob0 + st * C::BLOB, sp.blob + it.blob0, bl, &bar[st]);
+    };
+    auto yphase = [&](int k) {   // Y for item k (stage k & 1); two threads per observation
+        const int st = k & 1;
+        const int pt0 = items[k].pt0, nob = items[k].nob, fl = items[k].flags;
+        const double* row = s_row0 + st * C::ROWS + ((fl >> 2) & 1);
+        const unsigned int* info = s_blob0 + st * C::BLOB;
+        double* Y = s_Y0 + st * C::YSZ;
+        for (int u = tid; u < 2 * nob; u += SCH4_THREADS) {
+            const int i = u >> 1, h = u & 1;
+            const unsigned int in = info[i];
+            const int q = (int)(in & 0xffffu), oe = (int)((in >> 16) & 0x7fffu);
+            const double* V = row + WB * oe + 9 * q;
+            const double a[6] = {V[0] + lambda, V[1], V[2], V[4] + lambda, V[5], V[8] + lambda};
+            double inv[6];
+            inv_sym3(a, inv);   // recomputed by every observation of the point — latency-bound either way
+            double* y = Y + (size_t)i * YS;
+            if (h == 0) {
+                const int pg = pt0 + q;
+                if ((in >> 31) && (fl & 2)) {
+#pragma unroll
+                    for (int e = 0; e < 6; ++e) Ainv_out[(size_t)6 * pg + e] = inv[e];
+                }
+                const double* gp = p.g + p.gB + (size_t)3 * pg;
+                const double g0 = gp[0], g1 = gp[1], g2 = gp[2];
+                y[WB] = inv[0] * g0 + inv[1] * g1 + inv[2] * g2;
+                y[WB + 1] = inv[1] * g0 + inv[3] * g1 + inv[4] * g2;
+                y[WB + 2] = inv[2] * g0 + inv[4] * g1 + inv[5] * g2;
+            }
+            const double* w = row + WB * i + 9 * q;
+#pragma unroll
+            for (int c2 = 0; c2 < (DC + 1) / 2; ++c2) {
+                const int c = 2 * c2 + h;
+                if (c < DC) {
+                    const double w0 = w[3 * c], w1 = w[3 * c + 1], w2 = w[3 * c + 2];
+                    y[3 * c] = fma(inv[2], w2, fma(inv[1], w1, inv[0] * w0));
+                    y[3 * c + 1] = fma(inv[4], w2, fma(inv[3], w1, inv[1] * w0));
+                    y[3 * c + 2] = fma(inv[5], w2, fma(inv[4], w1, inv[2] * w0));
+                }
+            }
+        }
+    };
+
+    if (tid == 0) { issue(0); if (nitem > 1) issue(1); }
+    mbar_wait(&bar[0], 0);
+    yphase(0);
+    unsigned int wt_next = 0;
+    if (lane < NB) wt_next = sp.wtab[(size_t)items[0].wrow * (SCH4_WARPS * NB) + warp * NB + lane];
+    __syncthreads();
+
+    // per-lane operand bases (shared-memory byte addresses): fragment row / column fr, coordinate d_s of DMMA step s.
+    // Lanes of fragment rows >= DC (and of the column behind the rhs column) read whatever follows the operand row — finite
+    // or not, it only reaches accumulator rows / columns that are never written back.
+    const uint32_t rowb0 = smem_u32(s_row0), yb0 = smem_u32(s_Y0);
+    const uint32_t la0 = 8u * (3 * fr + d0), la1 = 8u * (3 * fr + d1), la2 = 8u * (3 * fr + d2);
+    const bool fk3 = fk == 3, fk01 = fk < 2, fk0 = fk == 0;
+    double acc[NB][MT][NTC][2];
+    for (int k = 0; k < nitem; ++k) {
+        const int st = k & 1;
+        const SchurItem it = items[k];
+        const unsigned int wt = wt_next;
+        if (k + 1 < nitem && lane < NB) wt_next = sp.wtab[(size_t)items[k + 1].wrow * (SCH4_WARPS * NB) + warp * NB + lane];
+        if (it.flags & 1) {
+#pragma unroll
+            for (int b = 0; b < NB; ++b)
+#pragma unroll
+                for (int m = 0; m < MT; ++m)
+#pragma unroll
+                    for (int n = 0; n < NTC; ++n) { acc[b][m][n][0] = 0.0; acc[b][m][n][1] = 0.0; }
+        }
+        {
+            const uint32_t rowb = rowb0 + 8u * (uint32_t)(st * C::ROWS + ((it.flags >> 2) & 1));
+            const uint32_t yb = yb0 + 8u * (uint32_t)(st * C::YSZ);
+            const uint32_t a0 = rowb + la0, a1 = rowb + la1, a2 = rowb + la2;
+            const uint32_t b0a = yb + la0, b1a = yb + la1, b2a = yb + la2;
+            const unsigned int nob4 = (unsigned int)((it.nob + 3) & ~3);
+            const unsigned int* ents = (it.ne4 <= C::MAXENT) ? (s_blob0 + st * C::BLOB + nob4) : (sp.blob + it.blob0 + nob4);
+#pragma unroll
+            for (int b = 0; b < NB; ++b) {
+                const unsigned int ue = __shfl_sync(0xffffffffu, wt, b);
+                const int ng = (int)(ue & 0xfffu);
+                if (ng == 0) continue;
+                const uint4* eb = reinterpret_cast<const uint4*>(ents + (ue >> 12));
+#pragma unroll 2
+                for (int g = 0; g < ng; ++g) {
+                    const uint4 e4 = eb[g];
+                    // the lane's three (contribution, d) pairs: fk = 0: (0,0) (1,1) (2,2); 1: (0,1) (1,2) (3,0); 2: (0,2) (2,0) (3,1); 3: (1,0) (2,1) (3,2)
+                    const unsigned int en0 = fk3 ? e4.y : e4.x;
+                    const unsigned int en1 = fk01 ? e4.y : e4.z;
+                    const unsigned int en2 = fk0 ? e4.z : e4.w;
+                    double av[3][MT], bv[3][NTC];
+#pragma unroll
+                    for (int m = 0; m < MT; ++m) {
+                        av[0][m] = lds_f64(a0 + (en0 >> 16) + 192u * m);
+                        av[1][m] = lds_f64(a1 + (en1 >> 16) + 192u * m);
+                        av[2][m] = lds_f64(a2 + (en2 >> 16) + 192u * m);
+                    }
+#pragma unroll
+                    for (int n = 0; n < NTC; ++n) {
+                        bv[0][n] = lds_f64(b0a + (en0 & 0xffffu) + 192u * n);
+                        bv[1][n] = lds_f64(b1a + (en1 & 0xffffu) + 192u * n);
+                        bv[2][n] = lds_f64(b2a + (en2 & 0xffffu) + 192u * n);
+                    }
+#pragma unroll
+                    for (int s3 = 0; s3 < 3; ++s3)
+#pragma unroll
+                        for (int m = 0; m < MT; ++m)
+#pragma unroll
+                            for (int n = 0; n < NTC; ++n) dmma884(acc[b][m][n][0], acc[b][m][n][1], av[s3][m], bv[s3][n]);
+                }
+            }
+        }
+        if (it.urow >= 0) {   // one FP64 reduction per block element for the whole (super-tile, round)
+            SchurUnit un;
+            un.soff = 0; un.cam = 0; un.flags = 0;
+            if (lane < NB) un = sp.units[(size_t)it.urow * (SCH4_WARPS * NB) + warp * NB + lane];
+#pragma unroll
+            for (int b = 0; b < NB; ++b) {
+                const long long soff = __shfl_sync(0xffffffffu, un.soff, b);
+                const int cam = __shfl_sync(0xffffffffu, un.cam, b);
+                const int flags = __shfl_sync(0xffffffffu, un.flags, b);
+                if (!(flags & 8)) continue;
+                const bool diag = (flags & 2) != 0;
+                double* Sb = S + soff;
+                const long long sa = (flags & 1) ? sp.ld : 1, sb = (flags & 1) ? 1 : sp.ld;
+#pragma unroll
+                for (int m = 0; m < MT; ++m)
+#pragma unroll
+                    for (int n = 0; n < NTC; ++n)
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            const int a = 8 * m + fr, c = 8 * n + 2 * fk + h;
+                            if (a >= DC) continue;
+                            if (c < DC) { if (!(diag && a < c)) atomicAdd(Sb + sa * a + sb * c, -acc[b][m][n][h]); }
+                            else if (c == DC && diag) atomicAdd(rhs + (size_t)cam * DC + a, -acc[b][m][n][h]);
+                        }
+            }
+        }
+        if (k + 1 < nitem) {   // the bulk loads of item k+1 had the products above to land
+            mbar_wait(&bar[st ^ 1], (uint32_t)(((k + 1) >> 1) & 1));
+            yphase(k + 1);
+        }
+        __syncthreads();   // stage st is free, Y of item k+1 is complete
+        if (tid == 0 && k + 2 < nitem) issue(k + 2);
     }
 }
 

@@ -153,7 +153,13 @@ struct nlls_ctx {
     // Schur v2 plan (per-tile sorted contribution lists)
     int schur_v2 = 1;
     int nstiles = 0;
-    int *d_stile_pt = nullptr, *d_chunk_off = nullptr;
+    int *d_stile_pt = nullptr, *d_chunk_off = nullptr, *d_ent_off = nullptr;
+    // Schur v4 plan (super-tiles: tensor-core accumulation of whole S blocks across consecutive tiles); 2 = forced
+    int schur_v4 = 1, nsuper = 0;   // nsuper: CTAs of the v4 kernel (0: v2 path)
+    int* d_cta_item = nullptr;
+    SchurItem* d_items = nullptr;
+    SchurUnit* d_units = nullptr;
+    unsigned int *d_wtab = nullptr, *d_blob = nullptr;
     SchurChunk* d_chunks = nullptr;
     unsigned int* d_ents = nullptr;
 
@@ -290,6 +296,7 @@ int set_smem_attrs(nlls_ctx* ctx) {
     else if (ctx->tile_obs == 128) TRY((set_tile_attrs<R, 128>(ctx)));
     else TRY((set_tile_attrs<R, 256>(ctx)));
     CK(cudaFuncSetAttribute(schur2_kernel<R::DC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Schur2Smem<R::DC>::bytes));
+    CK(cudaFuncSetAttribute(schur4_kernel<R::DC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Schur4Cfg<R::DC>::bytes));
     CK(cudaFuncSetAttribute(ldl_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DIAG_SMEM));
     CK(cudaFuncSetAttribute(ldl_off_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OFF_SMEM));
     CK(cudaFuncSetAttribute(ldl_upd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UPD_SMEM));
@@ -369,9 +376,15 @@ int launch_schur(nlls_ctx* ctx, double lambda) {
         const long long tot = (long long)ctx->nA * DC * DC + n;
         schur_init_kernel<DC><<<(unsigned)((tot + 255) / 256), 256, 0, ctx->st>>>(p, ctx->d_S, ctx->d_rhs, lambda, ctx->rank == 0 ? 1 : 0); ctx->launches++;
     }
-    if (ctx->schur_v2 && ctx->nstiles > 0) {
+    if (ctx->schur_v4 && ctx->nsuper > 0) {
+        SchurPlan4 sp;
+        sp.cta_item = ctx->d_cta_item; sp.items = ctx->d_items; sp.units = ctx->d_units; sp.blob = ctx->d_blob; sp.wtab = ctx->d_wtab;
+        sp.ld = ctx->s_tiled ? ST : n;
+        schur4_kernel<DC><<<ctx->nsuper, SCH4_THREADS, Schur4Cfg<DC>::bytes, ctx->st>>>(p, sp, ctx->d_S, ctx->d_rhs, ctx->d_Ainv, lambda);
+        ctx->launches++;
+    } else if (ctx->schur_v2 && ctx->nstiles > 0) {
         SchurPlan sp;
-        sp.stile_pt = ctx->d_stile_pt; sp.chunk_off = ctx->d_chunk_off; sp.chunks = ctx->d_chunks; sp.ents = ctx->d_ents; sp.nstiles = ctx->nstiles;
+        sp.stile_pt = ctx->d_stile_pt; sp.chunk_off = ctx->d_chunk_off; sp.ent_off = ctx->d_ent_off; sp.chunks = ctx->d_chunks; sp.ents = ctx->d_ents; sp.nstiles = ctx->nstiles;
         sp.ld = ctx->s_tiled ? ST : n;
         const int G = std::max(1, ctx->schur_stride);
         const int grid = G * ((ctx->nstiles + G - 1) / G);
@@ -669,7 +682,7 @@ int nlls_create(nlls_ctx** out, int device) {
     ctx->use_tma = (e && e[0] == '0') ? 0 : 1;
     if (const char* g = getenv("NLLS_B200_SCHUR_STRIDE")) ctx->schur_stride = std::max(1, atoi(g));
     if (const char* g = getenv("NLLS_B200_REDUCED")) ctx->s_tiled = (std::string(g) == "dense") ? 0 : 1;
-    if (const char* g = getenv("NLLS_B200_SCHUR")) ctx->schur_v2 = (std::string(g) == "v1") ? 0 : 1;
+    if (const char* g = getenv("NLLS_B200_SCHUR")) ctx->schur_v4 = (std::string(g) == "v2") ? 0 : ((std::string(g) == "v4") ? 2 : 1);
     if (const char* g = getenv("NLLS_B200_TILE")) { const int v = atoi(g); ctx->tile_env = (v == 64 || v == 128) ? v : 256; }
     { int v = 0; if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && v > 0) ctx->nsm = v; }
     if (cudaGetLastError() != cudaSuccess) { delete ctx; return NLLS_ERR_CUDA; }
@@ -687,7 +700,7 @@ int nlls_destroy(nlls_ctx* ctx) {
                     ctx->d_flush, ctx->d_work, ctx->d_info, ctx->d_ipiv, ctx->d_tile_id, ctx->d_pos, ctx->d_diag_tile, ctx->d_diag_tile_nat,
                     ctx->d_lvl_cols, ctx->d_red_tasks, ctx->d_red_upds, ctx->d_colptr,
                     ctx->d_col_tile, ctx->d_col_row, ctx->d_Linv, ctx->d_xp, ctx->d_stile_pt, ctx->d_chunk_off, ctx->d_chunks, ctx->d_ents, ctx->d_tiles, ctx->d_camstat_part,
-                    ctx->d_ad_data, ctx->d_ad_chunks, ctx->d_ad_moff, ctx->d_ad_part};
+                    ctx->d_ad_data, ctx->d_ad_chunks, ctx->d_ad_moff, ctx->d_ad_part, ctx->d_ent_off, ctx->d_cta_item, ctx->d_items, ctx->d_units, ctx->d_wtab, ctx->d_blob};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (ctx->h_scal) cudaFreeHost(ctx->h_scal);
     if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
@@ -1045,11 +1058,13 @@ int nlls_prepare(nlls_ctx* ctx) {
         stile_pt.push_back(0);
         {
             auto aligned = [&](int64_t pt) { return ((WB * (int64_t)ctx->h_obs_start[(size_t)pt] + 9 * pt) & 1) == 0; };
+            const int sobs = (DC <= 7) ? SCH_OBS : SCH_OBS / 2, spts = sobs / 2;   // == Schur4Cfg<DC>::OBS / PTS
             int64_t p0 = 0;
             while (p0 < nB) {
                 int64_t p1 = p0;
-                while (p1 < nB && (p1 - p0) < SCH_PTS && (ctx->h_obs_start[(size_t)p1 + 1] - ctx->h_obs_start[(size_t)p0]) <= SCH_OBS) ++p1;
+                while (p1 < nB && (p1 - p0) < spts && (ctx->h_obs_start[(size_t)p1 + 1] - ctx->h_obs_start[(size_t)p0]) <= sobs) ++p1;
                 if (p1 < nB && !aligned(p1) && p1 - 1 > p0 && aligned(p1 - 1)) --p1;
+                if (p1 == p0) FAIL(NLLS_ERR_UNSUPPORTED, "a point with more observations than a Schur tile holds");
                 stile_pt.push_back((int)p1);
                 p0 = p1;
             }
@@ -1059,7 +1074,7 @@ int nlls_prepare(nlls_ctx* ctx) {
         const int TC = ST / DC;
         const int NTl = ctx->NT;
         const long long nn = ctx->nred;
-        struct TilePlan { std::vector<SchurChunk> chunks; std::vector<unsigned int> ents; };
+        struct TilePlan { std::vector<SchurChunk> chunks; std::vector<unsigned int> ents, ents4; std::vector<unsigned long long> bkey; std::vector<int> bstart; };
         std::vector<TilePlan> plans((size_t)nst);
         auto build = [&](int t0, int t1) {
             std::vector<unsigned long long> keys;
@@ -1076,12 +1091,13 @@ int nlls_prepare(nlls_ctx* ctx) {
                 }
                 std::sort(keys.begin(), keys.end());
                 TilePlan& pl = plans[(size_t)t];
-                pl.ents.resize(keys.size());
+                pl.ents.resize(keys.size()); pl.ents4.resize(keys.size());
                 size_t k0 = 0;
                 while (k0 < keys.size()) {
                     const unsigned long long key = keys[k0] >> 20;
                     size_t k1 = k0;
                     while (k1 < keys.size() && (keys[k1] >> 20) == key) ++k1;
+                    pl.bkey.push_back(key); pl.bstart.push_back((int)k0);   // distinct blocks of the tile, in key order, with their first entry
                     const int cam = (int)(key >> 22), camj = (int)(key & 0x3fffffu);
                     long long soff; short flags = (cam == camj) ? 2 : 0;
                     if (ctx->s_tiled) {
@@ -1097,9 +1113,17 @@ int nlls_prepare(nlls_ctx* ctx) {
                         ck.soff = soff; ck.ent0 = (int)k; ck.cam = cam; ck.n = (short)std::min<size_t>(SCH_CHUNK, k1 - k); ck.flags = flags;
                         pl.chunks.push_back(ck);
                     }
-                    for (size_t k = k0; k < k1; ++k) pl.ents[k] = (unsigned int)((((keys[k] >> 10) & 0x3ffu) << 16) | (keys[k] & 0x3ffu));
+                    for (size_t k = k0; k < k1; ++k) {
+                        const unsigned int il = (unsigned int)((keys[k] >> 10) & 0x3ffu), jl = (unsigned int)(keys[k] & 0x3ffu);
+                        pl.ents[k] = (il << 16) | jl;
+                        // v4: shared-memory byte offsets of W_i (inside the staged H span) and of Y_j
+                        pl.ents4[k] = ((8u * (unsigned int)(WB * il + 9u * (unsigned int)(ctx->h_obs_pt[(size_t)ob0 + il] - pa))) << 16) | (8u * (unsigned int)((WB + 3) * jl));   // bytes
+                    }
                     k0 = k1;
                 }
+                pl.bstart.push_back((int)keys.size());
+                // long chunks first: the lanes of a warp then run loops of similar length
+                std::stable_sort(pl.chunks.begin(), pl.chunks.end(), [](const SchurChunk& x, const SchurChunk& y) { return x.n > y.n; });
             }
         };
         if (nA >= (1 << 22)) FAIL(NLLS_ERR_UNSUPPORTED, "more than 2^22 cameras");
@@ -1109,23 +1133,190 @@ int nlls_prepare(nlls_ctx* ctx) {
             for (int k = 0; k < nth; ++k) th.emplace_back(build, (int)((int64_t)nst * k / nth), (int)((int64_t)nst * (k + 1) / nth));
             for (auto& x : th) x.join();
         }
-        std::vector<int> chunk_off((size_t)nst + 1, 0);
-        size_t nent = 0, nch = 0;
-        for (int t = 0; t < nst; ++t) { nent += plans[(size_t)t].ents.size(); nch += plans[(size_t)t].chunks.size(); }
-        if (nent >= (1ull << 31)) FAIL(NLLS_ERR_UNSUPPORTED, "too many Schur contributions per rank");
-        std::vector<SchurChunk> chunks; chunks.reserve(nch);
-        std::vector<unsigned int> ents; ents.reserve(nent);
-        for (int t = 0; t < nst; ++t) {
-            const int base = (int)ents.size();
-            for (SchurChunk ck : plans[(size_t)t].chunks) { ck.ent0 += base; chunks.push_back(ck); }
-            ents.insert(ents.end(), plans[(size_t)t].ents.begin(), plans[(size_t)t].ents.end());
-            chunk_off[(size_t)t + 1] = (int)chunks.size();
-            plans[(size_t)t] = TilePlan();
+        // ---- Schur v4: one persistent CTA per SM walks a contiguous tile range, cut into super-tiles (runs of consecutive tiles
+        //      whose distinct S blocks fit the warps' accumulator slots); see schur4_kernel
+        const int NB4 = (DC <= 7) ? 16 : 4;   // == Schur4Cfg<DC>::NB
+        const int cap4 = SCH4_WARPS * NB4;
+        const int obs4 = (DC <= 7) ? 256 : 128, row4 = WB * obs4 + 9 * (obs4 / 2), ys4 = WB + 3;
+        std::vector<int> cta_item;
+        std::vector<SchurItem> items;
+        std::vector<SchurUnit> units;
+        std::vector<unsigned int> wtab, blob;
+        bool v4ok = ctx->schur_v4 != 0;
+        ctx->nsuper = 0;
+        if (v4ok) {
+            // per tile: padded entry lists (groups of four per block) and the blob [per-observation table | entries]
+            std::vector<long long> tile_groups((size_t)nst, 0);
+            std::vector<int> blob0((size_t)nst, 0), ne4((size_t)nst, 0);
+            std::vector<std::vector<int>> bstart4((size_t)nst);
+            long long ngroups = 0, ncontrib = 0;
+            const unsigned int nullent = ((8u * (unsigned int)(row4 + 2)) << 16) | (8u * (unsigned int)(ys4 * obs4));   // byte offsets of the zero pads
+            for (int t = 0; t < nst; ++t) {
+                const TilePlan& pl = plans[(size_t)t];
+                const int pa = stile_pt[(size_t)t], pb = stile_pt[(size_t)t + 1];
+                const int oa = ctx->h_obs_start[(size_t)pa], ob = ctx->h_obs_start[(size_t)pb];
+                blob0[(size_t)t] = (int)blob.size();
+                for (int i = oa; i < ob; ++i) {
+                    const int pp = ctx->h_obs_pt[(size_t)i];
+                    const unsigned int first = (i == ctx->h_obs_start[(size_t)pp]) ? 0x80000000u : 0u;
+                    blob.push_back(first | ((unsigned int)(ctx->h_obs_start[(size_t)pp + 1] - oa) << 16) | (unsigned int)(pp - pa));
+                }
+                while (blob.size() & 3) blob.push_back(0u);
+                const size_t eb = blob.size();
+                std::vector<int>& bs4 = bstart4[(size_t)t];
+                for (size_t bb = 0; bb < pl.bkey.size(); ++bb) {
+                    bs4.push_back((int)(blob.size() - eb));
+                    for (int k = pl.bstart[bb]; k < pl.bstart[bb + 1]; ++k) blob.push_back(pl.ents4[(size_t)k]);
+                    while ((blob.size() - eb) & 3) blob.push_back(nullent);
+                    ncontrib += pl.bstart[bb + 1] - pl.bstart[bb];
+                }
+                bs4.push_back((int)(blob.size() - eb));
+                ne4[(size_t)t] = (int)(blob.size() - eb);
+                tile_groups[(size_t)t] = ne4[(size_t)t] / 4;
+                ngroups += tile_groups[(size_t)t];
+                if (blob.size() >= (1ull << 31)) FAIL(NLLS_ERR_UNSUPPORTED, "too many Schur contributions per rank");
+                if (ne4[(size_t)t] >= (1 << 20)) v4ok = false;
+            }
+            // contiguous tile ranges of similar weight, one per CTA
+            const int ncta = std::max(1, std::min(ctx->nsm, nst));
+            std::vector<long long> wsum((size_t)nst + 1, 0);
+            for (int t = 0; t < nst; ++t) wsum[(size_t)t + 1] = wsum[(size_t)t] + tile_groups[(size_t)t] + 64;
+            std::vector<int> cta_tile((size_t)ncta + 1, nst);
+            cta_tile[0] = 0;
+            for (int c = 1; c < ncta; ++c)
+                cta_tile[(size_t)c] = (int)(std::lower_bound(wsum.begin(), wsum.end(), wsum[(size_t)nst] * c / ncta) - wsum.begin());
+            for (int c = 1; c <= ncta; ++c) cta_tile[(size_t)c] = std::max(cta_tile[(size_t)c], cta_tile[(size_t)c - 1]);
+            int maxrun = 64;
+            if (const char* g = getenv("NLLS_B200_SCHUR_RUN")) maxrun = std::max(1, atoi(g));
+            cta_item.assign((size_t)ncta + 1, 0);
+            std::vector<unsigned long long> cur, merged, keys_su;
+            std::vector<long long> cnt_su;
+            std::vector<int> order, slot_of, su_first;
+            int nsu_total = 0;
+            for (int c = 0; c < ncta; ++c) {
+                // super-tiles of this CTA's range
+                su_first.clear();
+                const int ta0 = cta_tile[(size_t)c], tb0 = cta_tile[(size_t)c + 1];
+                cur.clear();
+                bool wide = false;   // the open super-tile is a single oversize tile (it must stand alone)
+                for (int t = ta0; t < tb0; ++t) {
+                    const std::vector<unsigned long long>& bk = plans[(size_t)t].bkey;
+                    const bool big = (int)bk.size() > cap4;
+                    if (t == ta0 || wide || big) { su_first.push_back(t); cur = bk; wide = big; continue; }
+                    merged.clear();
+                    std::set_union(cur.begin(), cur.end(), bk.begin(), bk.end(), std::back_inserter(merged));
+                    if ((int)merged.size() > cap4 || t - su_first.back() >= maxrun) { su_first.push_back(t); cur = bk; }
+                    else cur.swap(merged);
+                }
+                su_first.push_back(tb0);
+                for (size_t q = 0; q + 1 < su_first.size(); ++q) {
+                    const int ta = su_first[q], tb = su_first[q + 1];
+                    if (ta >= tb) continue;
+                    ++nsu_total;
+                    keys_su.clear();
+                    for (int t = ta; t < tb; ++t) keys_su.insert(keys_su.end(), plans[(size_t)t].bkey.begin(), plans[(size_t)t].bkey.end());
+                    std::sort(keys_su.begin(), keys_su.end());
+                    keys_su.erase(std::unique(keys_su.begin(), keys_su.end()), keys_su.end());
+                    const int nblk = (int)keys_su.size();
+                    cnt_su.assign((size_t)nblk, 0);
+                    for (int t = ta; t < tb; ++t) {
+                        const TilePlan& pl = plans[(size_t)t];
+                        for (size_t bb = 0; bb < pl.bkey.size(); ++bb) {
+                            const int idx = (int)(std::lower_bound(keys_su.begin(), keys_su.end(), pl.bkey[bb]) - keys_su.begin());
+                            cnt_su[(size_t)idx] += (bstart4[(size_t)t][bb + 1] - bstart4[(size_t)t][bb]) / 4 + 1;
+                        }
+                    }
+                    // heaviest blocks first, each to the least-loaded warp of its round that still has a free slot
+                    order.resize((size_t)nblk);
+                    for (int k = 0; k < nblk; ++k) order[(size_t)k] = k;
+                    std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return cnt_su[(size_t)x] > cnt_su[(size_t)y]; });
+                    const int nrounds = std::max(1, (nblk + cap4 - 1) / cap4);
+                    slot_of.assign((size_t)nblk, 0);
+                    const int urow0 = (int)(units.size() / (size_t)cap4);
+                    SchurUnit none; none.soff = 0; none.cam = 0; none.flags = 0;
+                    units.resize(units.size() + (size_t)nrounds * cap4, none);
+                    for (int r = 0; r < nrounds; ++r) {
+                        long long load[SCH4_WARPS] = {0};
+                        int used[SCH4_WARPS] = {0};
+                        for (int k = r; k < nblk; k += nrounds) {   // round r takes every nrounds-th block of the sorted order
+                            const int idx = order[(size_t)k];
+                            int w = -1;
+                            for (int q2 = 0; q2 < SCH4_WARPS; ++q2) if (used[q2] < NB4 && (w < 0 || load[q2] < load[w])) w = q2;
+                            const int slot = r * cap4 + w * NB4 + used[w]++;
+                            load[w] += cnt_su[(size_t)idx];
+                            slot_of[(size_t)idx] = slot;
+                            const unsigned long long key = keys_su[(size_t)idx];
+                            const int cam = (int)(key >> 22), camj = (int)(key & 0x3fffffu);
+                            SchurUnit u; u.cam = cam; u.flags = 8 | ((cam == camj) ? 2 : 0);
+                            if (ctx->s_tiled) {
+                                const int I = cam / TC, Jt = camj / TC, r0 = (cam - I * TC) * DC, c0 = (camj - Jt * TC) * DC;
+                                const int pI = pos[(size_t)I], pJ = pos[(size_t)Jt];
+                                if (pI >= pJ) u.soff = (long long)tile_id[(size_t)pI * NTl + pJ] * ST2 + r0 + (long long)ST * c0;
+                                else { u.soff = (long long)tile_id[(size_t)pJ * NTl + pI] * ST2 + c0 + (long long)ST * r0; u.flags |= 1; }
+                            } else {
+                                u.soff = (long long)cam * DC + nn * ((long long)camj * DC);
+                            }
+                            units[(size_t)urow0 * cap4 + (size_t)slot] = u;
+                        }
+                    }
+                    for (int r = 0; r < nrounds; ++r)
+                        for (int t = ta; t < tb; ++t) {
+                            const TilePlan& pl = plans[(size_t)t];
+                            SchurItem it;
+                            it.pt0 = stile_pt[(size_t)t]; it.npt = stile_pt[(size_t)t + 1] - it.pt0;
+                            it.ob0 = ctx->h_obs_start[(size_t)it.pt0]; it.nob = ctx->h_obs_start[(size_t)stile_pt[(size_t)t + 1]] - it.ob0;
+                            it.blob0 = blob0[(size_t)t]; it.ne4 = ne4[(size_t)t];
+                            it.wrow = (int)(wtab.size() / (size_t)cap4);
+                            it.urow = (t == tb - 1) ? urow0 + r : -1;
+                            it.flags = ((t == ta) ? 1 : 0) | ((r == 0) ? 2 : 0) |
+                                       ((((long long)DC * DC * nA + (long long)WB * it.ob0 + 9ll * it.pt0) & 1) ? 4 : 0);   // bit2: the H span starts 8 bytes off a 16-byte boundary
+                            it.pad0 = it.pad1 = it.pad2 = 0;
+                            items.push_back(it);
+                            const size_t wb = wtab.size();
+                            wtab.resize(wb + (size_t)cap4, 0u);
+                            for (size_t bb = 0; bb < pl.bkey.size(); ++bb) {
+                                const int idx = (int)(std::lower_bound(keys_su.begin(), keys_su.end(), pl.bkey[bb]) - keys_su.begin());
+                                const int slot = slot_of[(size_t)idx];
+                                if (slot / cap4 != r) continue;
+                                const int f4 = bstart4[(size_t)t][bb], g4 = (bstart4[(size_t)t][bb + 1] - f4) / 4;
+                                wtab[wb + (size_t)(slot - r * cap4)] = ((unsigned int)f4 << 12) | (unsigned int)g4;
+                                if (g4 >= (1 << 12)) v4ok = false;
+                            }
+                        }
+                }
+                cta_item[(size_t)c + 1] = (int)items.size();
+            }
+            // blocks that recur too rarely (unsorted points) leave the tensor-core groups mostly empty: keep the v2 path then
+            const double fill = (double)ncontrib / std::max(1.0, 4.0 * (double)ngroups);
+            if (getenv("NLLS_B200_VERBOSE"))
+                fprintf(stderr, "[nlls] schur v4 plan: %d CTAs, %d super-tiles over %d tiles, %zu items, DMMA group fill %.2f\n", ncta, nsu_total, nst, items.size(), fill);
+            if (fill < 0.3 && ctx->schur_v4 != 2) v4ok = false;
+            if (v4ok) ctx->nsuper = ncta;
         }
-        if (getenv("NLLS_B200_VERBOSE"))
-            fprintf(stderr, "[nlls] schur plan: %d tiles, %zu contributions, %zu chunks (%.2f contributions per chunk)\n", nst, nent, nch, (double)nent / std::max<size_t>(nch, 1));
-        TRY(upload(ctx, &ctx->d_stile_pt, stile_pt)); TRY(upload(ctx, &ctx->d_chunk_off, chunk_off));
-        TRY(upload(ctx, &ctx->d_chunks, chunks)); TRY(upload(ctx, &ctx->d_ents, ents));
+        if (ctx->nsuper == 0) {   // v2 structures
+            std::vector<int> chunk_off((size_t)nst + 1, 0), ent_off((size_t)nst + 1, 0);
+            size_t nent = 0, nch = 0;
+            for (int t = 0; t < nst; ++t) { nent += plans[(size_t)t].ents.size(); nch += plans[(size_t)t].chunks.size(); }
+            if (nent >= (1ull << 31)) FAIL(NLLS_ERR_UNSUPPORTED, "too many Schur contributions per rank");
+            std::vector<SchurChunk> chunks; chunks.reserve(nch);
+            std::vector<unsigned int> ents; ents.reserve(nent);
+            for (int t = 0; t < nst; ++t) {
+                const int base = (int)ents.size();
+                for (SchurChunk ck : plans[(size_t)t].chunks) { ck.ent0 += base; chunks.push_back(ck); }
+                ents.insert(ents.end(), plans[(size_t)t].ents.begin(), plans[(size_t)t].ents.end());
+                chunk_off[(size_t)t + 1] = (int)chunks.size();
+                ent_off[(size_t)t + 1] = (int)ents.size();
+                plans[(size_t)t] = TilePlan();
+            }
+            if (getenv("NLLS_B200_VERBOSE"))
+                fprintf(stderr, "[nlls] schur v2 plan: %d tiles, %zu contributions, %zu chunks (%.2f contributions per chunk)\n", nst, nent, nch, (double)nent / std::max<size_t>(nch, 1));
+            TRY(upload(ctx, &ctx->d_stile_pt, stile_pt)); TRY(upload(ctx, &ctx->d_chunk_off, chunk_off)); TRY(upload(ctx, &ctx->d_ent_off, ent_off));
+            TRY(upload(ctx, &ctx->d_chunks, chunks)); TRY(upload(ctx, &ctx->d_ents, ents));
+        }
+        if (ctx->nsuper > 0) {
+            TRY(upload(ctx, &ctx->d_cta_item, cta_item)); TRY(upload(ctx, &ctx->d_items, items));
+            TRY(upload(ctx, &ctx->d_units, units)); TRY(upload(ctx, &ctx->d_wtab, wtab)); TRY(upload(ctx, &ctx->d_blob, blob));
+        }
     }
 
     TRY(upload(ctx, &ctx->d_obs_cam, ctx->h_obs_cam)); TRY(upload(ctx, &ctx->d_obs_pt, ctx->h_obs_pt)); TRY(upload(ctx, &ctx->d_obs_z, obs_z));
@@ -1144,8 +1335,9 @@ int nlls_prepare(nlls_ctx* ctx) {
     for (int k = 0; k < 3; ++k) { TRY(dalloc(ctx, &ctx->d_A[k], (size_t)nA * ctx->CS)); TRY(dalloc(ctx, &ctx->d_B[k], (size_t)nB * 3)); }
     ctx->cur = 0; ctx->nxt = 1; ctx->bst = 2;
     TRY(upload_vars(ctx, A, ctx->CS, ctx->d_A[0])); TRY(upload_vars(ctx, B, 3, ctx->d_B[0]));
-    TRY(dalloc(ctx, &ctx->d_H, (size_t)ctx->hlen)); TRY(dalloc(ctx, &ctx->d_g, (size_t)ctx->dof)); TRY(dalloc(ctx, &ctx->d_x, (size_t)ctx->dof));
-    CK(cudaMemsetAsync(ctx->d_H, 0, sizeof(double) * ctx->hlen, ctx->st));
+    TRY(dalloc(ctx, &ctx->d_H, (size_t)ctx->hlen + 2));   // + slack: the Schur kernel's 16-byte-aligned bulk loads may read one element past a span
+    TRY(dalloc(ctx, &ctx->d_g, (size_t)ctx->dof)); TRY(dalloc(ctx, &ctx->d_x, (size_t)ctx->dof));
+    CK(cudaMemsetAsync(ctx->d_H, 0, sizeof(double) * (ctx->hlen + 2), ctx->st));
     CK(cudaMemsetAsync(ctx->d_g, 0, sizeof(double) * ctx->dof, ctx->st));
     CK(cudaMemsetAsync(ctx->d_x, 0, sizeof(double) * ctx->dof, ctx->st));
     TRY(dalloc(ctx, &ctx->d_Ainv, (size_t)6 * nB));

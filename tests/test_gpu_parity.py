@@ -164,18 +164,43 @@ def test_interleaved_variable_order(pkg, orc):
     ctx.close()
 
 
+@pytest.mark.parametrize("schur", ["v2", "v4"])   # v2: per-thread chunks; v4: tensor-core super-tiles (forced, also where its plan would be declined)
 @pytest.mark.parametrize("lam", [1e-5, 1e-3, 10.0])  # lambda = 0 is singular: affine BA has a 12-DoF gauge freedom
-def test_damped_solve_matches_full_system(pkg, orc, lam):
+def test_damped_solve_matches_full_system(pkg, orc, lam, schur):
     # Schur elimination + reduced solve == the reference's full-system solve x = -(H + lambda I)^-1 g  
     p = _ba(pkg, 10, 50, 0.3)
     P = oracle_problem(orc, p)
     P.linearize()
     x_ref = P.solve(lam)
-    ctx = cuda_context(pkg, p)
-    ctx.linearize()
-    ctx.solve(lam)
-    assert relerr(ctx.step(), x_ref) <= 1e-9
-    ctx.close()
+    os.environ["NLLS_B200_SCHUR"] = schur
+    try:
+        ctx = cuda_context(pkg, p)
+        ctx.linearize()
+        ctx.solve(lam)
+        assert relerr(ctx.step(), x_ref) <= 1e-9
+        ctx.close()
+    finally:
+        os.environ.pop("NLLS_B200_SCHUR", None)
+
+
+@pytest.mark.parametrize("schur", ["v2", "v4"])
+def test_damped_solve_ladybug_shape(pkg, orc, schur):
+    # the same identity on the Ladybug-shaped problem (many tiles per super-tile, ragged track lengths, Huber weights)
+    ok, rid, kp = KERNELS["huber"]
+    p = _bal(pkg, *pkg.synthetic.SHAPES["ladybug"], noise=0.01, outlier_frac=0.05)
+    P = oracle_problem(orc, p, kernel=ok)
+    P.linearize()
+    lam = 1e-2
+    x_ref = P.solve(lam)
+    os.environ["NLLS_B200_SCHUR"] = schur
+    try:
+        ctx = cuda_context(pkg, p, rid, kp)
+        ctx.linearize()
+        ctx.solve(lam)
+        assert relerr(ctx.step(), x_ref) <= 1e-9
+        ctx.close()
+    finally:
+        os.environ.pop("NLLS_B200_SCHUR", None)
 
 
 def _compare_trajectories(pkg, orc, p, kernel_o=None, robust=0, kparams=(), maxiters=100):
@@ -330,3 +355,56 @@ def test_venice_scale_properties(pkg):
     assert res.bestcost < res.startcost
     assert ctx.cost(0) == res.bestcost
     ctx.close()
+
+
+def _pinhole_problem(pkg, orc, ncam, npt, nobs, seed=3):
+    """Pinhole (BAL convention) BA: 9-DoF cameras (rotation, translation, f, k1, k2) x 3-D points; measurements are the oracle's
+    own projections plus noise, so the problem is consistent by construction."""
+    rng = np.random.default_rng(seed)
+    shape = pkg.synthetic.create_bal_shaped(ncam, npt, nobs, rng, noise=0.0)
+    cams = np.stack([orc.make_pinhole(rng.standard_normal(3) * 0.05, np.array([0.0, 0.0, -10.0]) + rng.standard_normal(3) * 0.1,
+                                      500.0 + 20.0 * rng.standard_normal(), 1e-2 * rng.standard_normal(), 1e-3 * rng.standard_normal())
+                     for _ in range(ncam)])
+    pts = rng.uniform(-1.0, 1.0, (npt, 3))
+    z = np.zeros((shape.nobs, 2))
+    for o in range(shape.nobs):
+        c, l = shape.cam_idx[o] - 1, shape.pt_idx[o] - ncam - 1
+        r, _ = orc.resjac(orc.RT_PINHOLE_BA, [0.0, 0.0], [(orc.VT_PINHOLE, cams[c]), (orc.VT_EUCLID, pts[l])])
+        z[o] = r
+    z += rng.standard_normal(z.shape) * 0.5
+    pts = pts + rng.standard_normal(pts.shape) * 1e-2
+    return cams, pts, shape.cam_idx, shape.pt_idx, z
+
+
+@pytest.mark.parametrize("schur", ["v2", "v4"])
+def test_pinhole_linearize_and_solve(pkg, orc, schur):
+    # 9-DoF camera blocks (two 8-row DMMA fragments per block in the v4 Schur kernel), SO(3) update on the cameras
+    capi = pkg.capi
+    ncam, npt, nobs = 12, 400, 1900
+    cams, pts, cam_idx, pt_idx, z = _pinhole_problem(pkg, orc, ncam, npt, nobs)
+    P = orc.Problem()
+    P.add_variables(orc.VT_PINHOLE, cams)
+    P.add_variables(orc.VT_EUCLID, pts)
+    P.add_costs(orc.RT_PINHOLE_BA, np.stack([cam_idx, pt_idx], 1), z, kernel=(1, 2.0, False, 1.0))
+    c_ref = P.linearize()
+    aos = np.zeros(len(z), dtype=pkg.api.COST_DTYPE)
+    aos["z"] = z
+    aos["varind"][:, 0] = cam_idx
+    aos["varind"][:, 1] = pt_idx
+    os.environ["NLLS_B200_SCHUR"] = schur
+    try:
+        ctx = capi.Context(0)
+        ctx.set_variables(capi.VAR_PINHOLE, cams, first_index=1)
+        ctx.set_variables(capi.VAR_EUCLID3, pts, first_index=ncam + 1)
+        ctx.set_costs(capi.RES_PINHOLE_BA, aos, capi.ROBUST_HUBER, (2.0,))
+        c = ctx.linearize()
+        assert abs(c - c_ref) <= TOL_COST * abs(c_ref)
+        assert relerr(ctx.hessian_blocks(), P.hess_data()) <= 1e-11   # trigonometric / division chains: a few ulp more than the affine model
+        assert relerr(ctx.gradient(), P.grad()) <= 1e-11
+        lam = 1e-4 * float(np.max(np.abs(P.hess_data())))
+        x_ref = P.solve(lam)
+        ctx.solve(lam)
+        assert relerr(ctx.step(), x_ref) <= 1e-8
+        ctx.close()
+    finally:
+        os.environ.pop("NLLS_B200_SCHUR", None)
