@@ -120,18 +120,18 @@ __global__ void __launch_bounds__(TO) lin_point_kernel(DevProblem p, const int4*
             c = 0.5 * rho;                                            //                   src/residual.jl:110
             double gc[DC], gp[3];
 #pragma unroll
-            for (int a = 0; a < DC; ++a) gc[a] = Jc[0][a] * r[0] + Jc[1][a] * r[1];   // g = J' r   :73
+            for (int a = 0; a < DC; ++a) gc[a] = fma(Jc[1][a], r[1], Jc[0][a] * r[0]);   // g = J' r   :73   (explicit FMAs: -fmad=false)
 #pragma unroll
-            for (int b = 0; b < 3; ++b) gp[b] = Jp[0][b] * r[0] + Jp[1][b] * r[1];
+            for (int b = 0; b < 3; ++b) gp[b] = fma(Jp[1][b], r[1], Jp[0][b] * r[0]);
             const double td2 = 2 * d2;
             double w[WB];                                             // W block, column-major 3 x DC   src/linearsystem.jl:149
 #pragma unroll
             for (int a = 0; a < DC; ++a)
 #pragma unroll
                 for (int b = 0; b < 3; ++b) {
-                    double h = Jp[0][b] * Jc[0][a] + Jp[1][b] * Jc[1][a];             // H = J' J   :74
+                    double h = fma(Jp[1][b], Jc[1][a], Jp[0][b] * Jc[0][a]);          // H = J' J   :74
                     if (d1 != 1.0) h *= d1;                                            // IRLS       :91-93
-                    if (d2 != 0.0) h += (td2 * gp[b]) * gc[a];                         // Triggs     :95-97
+                    if (d2 != 0.0) h = fma(td2 * gp[b], gc[a], h);                     // Triggs     :95-97
                     w[b + 3 * a] = h;
                 }
             // 128-bit shared stores at the block's own parity
@@ -150,9 +150,9 @@ __global__ void __launch_bounds__(TO) lin_point_kernel(DevProblem p, const int4*
             for (int b2 = 0; b2 < 3; ++b2)
 #pragma unroll
                 for (int b = b2; b < 3; ++b) {
-                    double h = Jp[0][b] * Jp[0][b2] + Jp[1][b] * Jp[1][b2];
+                    double h = fma(Jp[1][b], Jp[1][b2], Jp[0][b] * Jp[0][b2]);
                     if (d1 != 1.0) h *= d1;
-                    if (d2 != 0.0) h += (td2 * gp[b]) * gp[b2];
+                    if (d2 != 0.0) h = fma(td2 * gp[b], gp[b2], h);
                     s_pc[9 * tid + (q++)] = h;
                 }
 #pragma unroll
@@ -288,7 +288,7 @@ __global__ void __launch_bounds__(TO) cost_kernel(DevProblem p, const int4* __re
 // One CTA per work item (a camera and at most CAM_CHUNK of its observations); fixed-shape reduction.
 // ---------------------------------------------------------------------------------------------------
 template <class R>
-__global__ void __launch_bounds__(256) lin_cam_kernel(DevProblem p, const double* __restrict__ cams, const double* __restrict__ pts,
+__global__ void __launch_bounds__(256, (R::DC <= 6) ? 2 : 1) lin_cam_kernel(DevProblem p, const double* __restrict__ cams, const double* __restrict__ pts,
                                                       double* __restrict__ partials) {
     constexpr int DC = R::DC, NU = DC * (DC + 1) / 2 + DC;
     __shared__ double s_red[8][NU];
@@ -300,31 +300,46 @@ __global__ void __launch_bounds__(256) lin_cam_kernel(DevProblem p, const double
     double acc[NU];
 #pragma unroll
     for (int i = 0; i < NU; ++i) acc[i] = 0.0;
-    for (int j = beg + tid; j < end; j += 256) {
-        const int pt = p.cm_pt[j];
-        const double2 z = p.cm_z[j];
-        const double X[3] = {__ldg(pts + (size_t)3 * pt), __ldg(pts + (size_t)3 * pt + 1), __ldg(pts + (size_t)3 * pt + 2)};
-        double r[2], Jc[2][DC], Jp[2][3];
-        R::resjac(cv, X, z.x, z.y, r, Jc, Jp);
-        const double s = r[0] * r[0] + r[1] * r[1];
-        double rho, d1, d2;
-        robustifydcost(p.rk, s, rho, d1, d2);
-        double gc[DC];
+    // batches of four observations per thread: the index / measurement loads and then the point gathers of a batch are all
+    // issued before the first one is used (the one-at-a-time loop waited two dependent global round trips per observation)
+    constexpr int UB = 4;
+    for (int j0 = beg + tid; j0 < end; j0 += 256 * UB) {
+        int ptb[UB];
+        double2 zb[UB];
+        double Xb[UB][3];
 #pragma unroll
-        for (int a = 0; a < DC; ++a) gc[a] = Jc[0][a] * r[0] + Jc[1][a] * r[1];
-        const double td2 = 2 * d2;
-        int q = 0;
+        for (int u = 0; u < UB; ++u) { const int j = min(j0 + 256 * u, end - 1); ptb[u] = p.cm_pt[j]; zb[u] = p.cm_z[j]; }
 #pragma unroll
-        for (int a2 = 0; a2 < DC; ++a2)
+        for (int u = 0; u < UB; ++u) {
+            Xb[u][0] = __ldg(pts + (size_t)3 * ptb[u]); Xb[u][1] = __ldg(pts + (size_t)3 * ptb[u] + 1); Xb[u][2] = __ldg(pts + (size_t)3 * ptb[u] + 2);
+        }
 #pragma unroll
-            for (int a = a2; a < DC; ++a) {
-                double h = Jc[0][a] * Jc[0][a2] + Jc[1][a] * Jc[1][a2];
-                if (d1 != 1.0) h *= d1;
-                if (d2 != 0.0) h += (td2 * gc[a]) * gc[a2];
-                acc[q++] += h;
-            }
+        for (int u = 0; u < UB; ++u) {
+            if (j0 + 256 * u >= end) break;
+            const double2 z = zb[u];
+            const double X[3] = {Xb[u][0], Xb[u][1], Xb[u][2]};
+            double r[2], Jc[2][DC], Jp[2][3];
+            R::resjac(cv, X, z.x, z.y, r, Jc, Jp);
+            const double s = r[0] * r[0] + r[1] * r[1];
+            double rho, d1, d2;
+            robustifydcost(p.rk, s, rho, d1, d2);
+            // explicit FMAs (the file is compiled with -fmad=false): this pass is FP64-issue bound, not HBM bound — ncu.  The
+            // weights fold into the accumulation:  acc += d1 (J'J) + (2 d2 g) g'  (exact no-ops when d1 == 1 / d2 == 0)
+            double gc[DC], tg[DC];
 #pragma unroll
-        for (int a = 0; a < DC; ++a) acc[q++] += (d1 != 1.0) ? gc[a] * d1 : gc[a];
+            for (int a = 0; a < DC; ++a) { gc[a] = fma(Jc[1][a], r[1], Jc[0][a] * r[0]); tg[a] = (2 * d2) * gc[a]; }
+            int q = 0;
+#pragma unroll
+            for (int a2 = 0; a2 < DC; ++a2)
+#pragma unroll
+                for (int a = a2; a < DC; ++a) {
+                    const double h = fma(Jc[1][a], Jc[1][a2], Jc[0][a] * Jc[0][a2]);
+                    acc[q] = fma(tg[a], gc[a2], fma(d1, h, acc[q]));
+                    ++q;
+                }
+#pragma unroll
+            for (int a = 0; a < DC; ++a) { acc[q] = fma(d1, gc[a], acc[q]); ++q; }
+        }
     }
     const int lane = tid & 31, w = tid >> 5;
 #pragma unroll
@@ -632,8 +647,8 @@ template <int DC> struct Schur4Cfg {
     static constexpr int ROW = WB * OBS + 9 * PTS;  // doubles of H span per stage
     static constexpr int ROWS = ROW + 2 + ZPAD + 2; // + slack of an 8-byte-misaligned span, + zeros
     static constexpr int YSZ = YS * OBS + ZPAD;
-    static constexpr int MAXENT = 2560;             // staged contribution entries per tile (longer lists are read from global memory)
-    static constexpr int BLOB = MAXENT + OBS;       // u32 per stage: [per-observation table | contribution entries]
+    static constexpr int MAXENT = 5376;             // padded contribution entries per tile (the host cuts the tiles accordingly)
+    static constexpr int BLOB = OBS + MAXENT + 8;   // u32 per stage: [per-observation table | contribution entries | slack of the entry prefetch]
     static constexpr size_t bytes = 2 * ((size_t)(ROWS + YSZ) * sizeof(double) + (size_t)BLOB * sizeof(unsigned int)) + 64;
 };
 struct SchurUnit {
@@ -656,6 +671,56 @@ struct SchurPlan4 {
     long long ld;
 };
 
+// The products of one (block, tile): ng groups of four contributions, three DMMA steps each (inner index kk = fk of step s
+// is coordinate (4 s + fk) % 3 of contribution (4 s + fk) / 3, so a fragment load touches at most two operand rows).
+// Deliberately NOT inlined: the kernel calls it once per block slot.
+// Software pipeline: the operands of group g+1 and the entries of group g+2 are in flight during the DMMAs of group g
+// (entries behind a block's last group belong to the next block or to the slack of the blob stage — fetched, never used).
+// The lane's (contribution, d) pairs within a group are
+//   fk = 0: (0,0) (1,1) (2,2);  1: (0,1) (1,2) (3,0);  2: (0,2) (2,0) (3,1);  3: (1,0) (2,1) (3,2)
+// (measured alternative: step s <-> coordinate d, one contribution per lane — fewer instructions, more bank conflicts, 6 % slower)
+template <int MT, int NTC> struct SchurAcc { double c[MT][NTC][2]; };
+template <int MT, int NTC>
+__device__ __noinline__ SchurAcc<MT, NTC> schur4_groups(SchurAcc<MT, NTC> acc, uint32_t eb, int ng, uint32_t abase, uint32_t bbase, int fk) {
+    const bool fk3 = fk == 3, fk01 = fk < 2, fk0 = fk == 0;
+    const uint32_t o0 = 8u * (fk % 3), o1 = 8u * ((4 + fk) % 3), o2 = 8u * ((8 + fk) % 3);
+    auto fetch = [&](const uint4 e4, double (&av)[3][MT], double (&bv)[3][NTC]) {
+        const unsigned int en0 = fk3 ? e4.y : e4.x;
+        const unsigned int en1 = fk01 ? e4.y : e4.z;
+        const unsigned int en2 = fk0 ? e4.z : e4.w;
+#pragma unroll
+        for (int m = 0; m < MT; ++m) {
+            av[0][m] = lds_f64(abase + o0 + (en0 >> 16) + 192u * m);
+            av[1][m] = lds_f64(abase + o1 + (en1 >> 16) + 192u * m);
+            av[2][m] = lds_f64(abase + o2 + (en2 >> 16) + 192u * m);
+        }
+#pragma unroll
+        for (int n = 0; n < NTC; ++n) {
+            bv[0][n] = lds_f64(bbase + o0 + (en0 & 0xffffu) + 192u * n);
+            bv[1][n] = lds_f64(bbase + o1 + (en1 & 0xffffu) + 192u * n);
+            bv[2][n] = lds_f64(bbase + o2 + (en2 & 0xffffu) + 192u * n);
+        }
+    };
+    double av[2][3][MT], bv[2][3][NTC];
+    fetch(lds_u4(eb), av[0], bv[0]);
+    uint4 e4 = lds_u4(eb + 16u);
+    for (int g = 0; g < ng; g += 2) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            if (h == 1 && g + 1 >= ng) break;
+            fetch(e4, av[h ^ 1], bv[h ^ 1]);
+            e4 = lds_u4(eb + 16u * (uint32_t)(g + h + 2));
+#pragma unroll
+            for (int s3 = 0; s3 < 3; ++s3)
+#pragma unroll
+                for (int m = 0; m < MT; ++m)
+#pragma unroll
+                    for (int n = 0; n < NTC; ++n) dmma884(acc.c[m][n][0], acc.c[m][n][1], av[h][s3][m], bv[h][s3][n]);
+        }
+    }
+    return acc;
+}
+
 template <int DC>
 __global__ void __launch_bounds__(SCH4_THREADS, 1) schur4_kernel(DevProblem p, SchurPlan4 sp, double* __restrict__ S, double* __restrict__ rhs,
                                                                   double* __restrict__ Ainv_out, double lambda) {
@@ -672,35 +737,33 @@ __global__ void __launch_bounds__(SCH4_THREADS, 1) schur4_kernel(DevProblem p, S
     if (nitem <= 0) return;
     const SchurItem* items = sp.items + ka;
     const int fr = lane >> 2, fk = lane & 3;
-    // inner index kk = fk of DMMA step s within a group of four contributions: contribution (4 s + fk) / 3, coordinate (4 s + fk) % 3
-    const int d0 = fk % 3, d1 = (4 + fk) % 3, d2 = (8 + fk) % 3;
 
     if (tid == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); }
     for (int i = tid; i < 2 * C::ZPAD; i += SCH4_THREADS) {
         const int st = i / C::ZPAD, k = i - st * C::ZPAD;
         s_Y0[st * C::YSZ + YS * C::OBS + k] = 0.0;
     }
+    for (int i = tid; i < 2 * C::BLOB; i += SCH4_THREADS) s_blob0[i] = 0u;   // the entry prefetch may run past a list: keep every word a valid offset
     for (int i = tid; i < 2 * (C::ZPAD + 2); i += SCH4_THREADS) {
         const int st = i / (C::ZPAD + 2), k = i - st * (C::ZPAD + 2);
         s_row0[st * C::ROWS + C::ROW + 2 + k] = 0.0;
     }
     __syncthreads();
 
-    auto issue = [&](int k) {   // thread 0: TMA bulk loads of item k into stage k & 1
-        const SchurItem it = items[k];
+    auto issue = [&](const SchurItem& it, int k) {   // thread 0: TMA bulk loads of item k into stage k & 1
         const int st = k & 1;
         const int mis = (it.flags >> 2) & 1;   // the span starts 8 bytes off a 16-byte boundary: load from the element before it
         const double* gsrc = p.H + (size_t)p.hB + (size_t)WB * it.ob0 + (size_t)9 * it.pt0 - mis;
         const uint32_t span = (uint32_t)((WB * it.nob + 9 * it.npt + mis + 1) & ~1) * 8u;
         const uint32_t nob4 = (uint32_t)((it.nob + 3) & ~3);
-        const uint32_t bl = (nob4 + (it.ne4 <= C::MAXENT ? (uint32_t)it.ne4 : 0u)) * 4u;
+        const uint32_t bl = (nob4 + (uint32_t)it.ne4) * 4u;
         mbar_expect_tx(&bar[st], span + bl);
         bulk_load(s_row0 + st * C::ROWS, gsrc, span, &bar[st]);
         if (bl) bulk_load(s_blob0 + st * C::BLOB, sp.blob + it.blob0, bl, &bar[st]);
     };
-    auto yphase = [&](int k) {   // Y for item k (stage k & 1); two threads per observation
+    auto yphase = [&](const SchurItem& it, int k) {   // Y for item k (stage k & 1); two threads per observation
         const int st = k & 1;
-        const int pt0 = items[k].pt0, nob = items[k].nob, fl = items[k].flags;
+        const int pt0 = it.pt0, nob = it.nob, fl = it.flags;
         const double* row = s_row0 + st * C::ROWS + ((fl >> 2) & 1);
         const unsigned int* info = s_blob0 + st * C::BLOB;
         double* Y = s_Y0 + st * C::YSZ;
@@ -739,73 +802,44 @@ __global__ void __launch_bounds__(SCH4_THREADS, 1) schur4_kernel(DevProblem p, S
         }
     };
 
-    if (tid == 0) { issue(0); if (nitem > 1) issue(1); }
+    // item descriptors travel in registers, fetched two items ahead (a global round trip per tile would be exposed otherwise)
+    SchurItem itA = items[0], itB = items[nitem > 1 ? 1 : 0], itC = itB;
+    if (tid == 0) { issue(itA, 0); if (nitem > 1) issue(itB, 1); }
     mbar_wait(&bar[0], 0);
-    yphase(0);
+    yphase(itA, 0);
     unsigned int wt_next = 0;
-    if (lane < NB) wt_next = sp.wtab[(size_t)items[0].wrow * (SCH4_WARPS * NB) + warp * NB + lane];
+    if (lane < NB) wt_next = sp.wtab[(size_t)itA.wrow * (SCH4_WARPS * NB) + warp * NB + lane];
     __syncthreads();
 
-    // per-lane operand bases (shared-memory byte addresses): fragment row / column fr, coordinate d_s of DMMA step s.
+    // per-lane operand bases (shared-memory byte addresses): fragment row / column fr.
     // Lanes of fragment rows >= DC (and of the column behind the rhs column) read whatever follows the operand row — finite
     // or not, it only reaches accumulator rows / columns that are never written back.
-    const uint32_t rowb0 = smem_u32(s_row0), yb0 = smem_u32(s_Y0);
-    const uint32_t la0 = 8u * (3 * fr + d0), la1 = 8u * (3 * fr + d1), la2 = 8u * (3 * fr + d2);
-    const bool fk3 = fk == 3, fk01 = fk < 2, fk0 = fk == 0;
-    double acc[NB][MT][NTC][2];
+    const uint32_t rowb0 = smem_u32(s_row0) + 8u * (3 * fr), yb0 = smem_u32(s_Y0) + 8u * (3 * fr);
+    SchurAcc<MT, NTC> acc[NB];
     for (int k = 0; k < nitem; ++k) {
         const int st = k & 1;
-        const SchurItem it = items[k];
+        const SchurItem it = itA;
+        if (k + 2 < nitem) itC = items[k + 2];
         const unsigned int wt = wt_next;
-        if (k + 1 < nitem && lane < NB) wt_next = sp.wtab[(size_t)items[k + 1].wrow * (SCH4_WARPS * NB) + warp * NB + lane];
+        if (k + 1 < nitem && lane < NB) wt_next = sp.wtab[(size_t)itB.wrow * (SCH4_WARPS * NB) + warp * NB + lane];
         if (it.flags & 1) {
 #pragma unroll
             for (int b = 0; b < NB; ++b)
 #pragma unroll
                 for (int m = 0; m < MT; ++m)
 #pragma unroll
-                    for (int n = 0; n < NTC; ++n) { acc[b][m][n][0] = 0.0; acc[b][m][n][1] = 0.0; }
+                    for (int n = 0; n < NTC; ++n) { acc[b].c[m][n][0] = 0.0; acc[b].c[m][n][1] = 0.0; }
         }
         {
             const uint32_t rowb = rowb0 + 8u * (uint32_t)(st * C::ROWS + ((it.flags >> 2) & 1));
             const uint32_t yb = yb0 + 8u * (uint32_t)(st * C::YSZ);
-            const uint32_t a0 = rowb + la0, a1 = rowb + la1, a2 = rowb + la2;
-            const uint32_t b0a = yb + la0, b1a = yb + la1, b2a = yb + la2;
-            const unsigned int nob4 = (unsigned int)((it.nob + 3) & ~3);
-            const unsigned int* ents = (it.ne4 <= C::MAXENT) ? (s_blob0 + st * C::BLOB + nob4) : (sp.blob + it.blob0 + nob4);
+            const uint32_t entb = smem_u32(s_blob0 + st * C::BLOB) + 4u * (uint32_t)((it.nob + 3) & ~3);
 #pragma unroll
             for (int b = 0; b < NB; ++b) {
                 const unsigned int ue = __shfl_sync(0xffffffffu, wt, b);
                 const int ng = (int)(ue & 0xfffu);
                 if (ng == 0) continue;
-                const uint4* eb = reinterpret_cast<const uint4*>(ents + (ue >> 12));
-#pragma unroll 2
-                for (int g = 0; g < ng; ++g) {
-                    const uint4 e4 = eb[g];
-                    // the lane's three (contribution, d) pairs: fk = 0: (0,0) (1,1) (2,2); 1: (0,1) (1,2) (3,0); 2: (0,2) (2,0) (3,1); 3: (1,0) (2,1) (3,2)
-                    const unsigned int en0 = fk3 ? e4.y : e4.x;
-                    const unsigned int en1 = fk01 ? e4.y : e4.z;
-                    const unsigned int en2 = fk0 ? e4.z : e4.w;
-                    double av[3][MT], bv[3][NTC];
-#pragma unroll
-                    for (int m = 0; m < MT; ++m) {
-                        av[0][m] = lds_f64(a0 + (en0 >> 16) + 192u * m);
-                        av[1][m] = lds_f64(a1 + (en1 >> 16) + 192u * m);
-                        av[2][m] = lds_f64(a2 + (en2 >> 16) + 192u * m);
-                    }
-#pragma unroll
-                    for (int n = 0; n < NTC; ++n) {
-                        bv[0][n] = lds_f64(b0a + (en0 & 0xffffu) + 192u * n);
-                        bv[1][n] = lds_f64(b1a + (en1 & 0xffffu) + 192u * n);
-                        bv[2][n] = lds_f64(b2a + (en2 & 0xffffu) + 192u * n);
-                    }
-#pragma unroll
-                    for (int s3 = 0; s3 < 3; ++s3)
-#pragma unroll
-                        for (int m = 0; m < MT; ++m)
-#pragma unroll
-                            for (int n = 0; n < NTC; ++n) dmma884(acc[b][m][n][0], acc[b][m][n][1], av[s3][m], bv[s3][n]);
-                }
+                acc[b] = schur4_groups<MT, NTC>(acc[b], entb + 4u * (ue >> 12), ng, rowb, yb, fk);
             }
         }
         if (it.urow >= 0) {   // one FP64 reduction per block element for the whole (super-tile, round)
@@ -829,17 +863,18 @@ __global__ void __launch_bounds__(SCH4_THREADS, 1) schur4_kernel(DevProblem p, S
                         for (int h = 0; h < 2; ++h) {
                             const int a = 8 * m + fr, c = 8 * n + 2 * fk + h;
                             if (a >= DC) continue;
-                            if (c < DC) { if (!(diag && a < c)) atomicAdd(Sb + sa * a + sb * c, -acc[b][m][n][h]); }
-                            else if (c == DC && diag) atomicAdd(rhs + (size_t)cam * DC + a, -acc[b][m][n][h]);
+                            if (c < DC) { if (!(diag && a < c)) atomicAdd(Sb + sa * a + sb * c, -acc[b].c[m][n][h]); }
+                            else if (c == DC && diag) atomicAdd(rhs + (size_t)cam * DC + a, -acc[b].c[m][n][h]);
                         }
             }
         }
         if (k + 1 < nitem) {   // the bulk loads of item k+1 had the products above to land
             mbar_wait(&bar[st ^ 1], (uint32_t)(((k + 1) >> 1) & 1));
-            yphase(k + 1);
+            yphase(itB, k + 1);
         }
         __syncthreads();   // stage st is free, Y of item k+1 is complete
-        if (tid == 0 && k + 2 < nitem) issue(k + 2);
+        if (tid == 0 && k + 2 < nitem) issue(itC, k + 2);
+        itA = itB; itB = itC;
     }
 }
 

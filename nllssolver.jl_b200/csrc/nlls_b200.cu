@@ -1062,7 +1062,13 @@ int nlls_prepare(nlls_ctx* ctx) {
             int64_t p0 = 0;
             while (p0 < nB) {
                 int64_t p1 = p0;
-                while (p1 < nB && (p1 - p0) < spts && (ctx->h_obs_start[(size_t)p1 + 1] - ctx->h_obs_start[(size_t)p0]) <= sobs) ++p1;
+                int64_t contrib = 0;   // pairs (i, j <= i) of the tile: the v4 kernel stages the padded list in shared memory
+                while (p1 < nB && (p1 - p0) < spts && (ctx->h_obs_start[(size_t)p1 + 1] - ctx->h_obs_start[(size_t)p0]) <= sobs) {
+                    const int64_t kk = ctx->h_obs_start[(size_t)p1 + 1] - ctx->h_obs_start[(size_t)p1];
+                    if (p1 > p0 && contrib + kk * (kk + 1) / 2 > Schur4Cfg<6>::MAXENT / 2) break;
+                    contrib += kk * (kk + 1) / 2;
+                    ++p1;
+                }
                 if (p1 < nB && !aligned(p1) && p1 - 1 > p0 && aligned(p1 - 1)) --p1;
                 if (p1 == p0) FAIL(NLLS_ERR_UNSUPPORTED, "a point with more observations than a Schur tile holds");
                 stile_pt.push_back((int)p1);
@@ -1175,7 +1181,7 @@ int nlls_prepare(nlls_ctx* ctx) {
                 tile_groups[(size_t)t] = ne4[(size_t)t] / 4;
                 ngroups += tile_groups[(size_t)t];
                 if (blob.size() >= (1ull << 31)) FAIL(NLLS_ERR_UNSUPPORTED, "too many Schur contributions per rank");
-                if (ne4[(size_t)t] >= (1 << 20)) v4ok = false;
+                if (ne4[(size_t)t] > Schur4Cfg<6>::MAXENT) v4ok = false;   // (very long tracks or scattered blocks: v2 path)
             }
             // contiguous tile ranges of similar weight, one per CTA
             const int ncta = std::max(1, std::min(ctx->nsm, nst));
@@ -1193,6 +1199,7 @@ int nlls_prepare(nlls_ctx* ctx) {
             std::vector<long long> cnt_su;
             std::vector<int> order, slot_of, su_first;
             int nsu_total = 0;
+            long long stat_tot = 0, stat_maxw = 0, stat_maxq = 0;
             for (int c = 0; c < ncta; ++c) {
                 // super-tiles of this CTA's range
                 su_first.clear();
@@ -1282,6 +1289,14 @@ int nlls_prepare(nlls_ctx* ctx) {
                                 wtab[wb + (size_t)(slot - r * cap4)] = ((unsigned int)f4 << 12) | (unsigned int)g4;
                                 if (g4 >= (1 << 12)) v4ok = false;
                             }
+                            {   // balance statistics: the slowest warp (and the slowest scheduler: warp % 4) sets the pace of a tile
+                                long long wl[SCH4_WARPS] = {0}, ql[4] = {0}, tot = 0, mx = 0, mq = 0;
+                                for (int w = 0; w < SCH4_WARPS; ++w)
+                                    for (int b2 = 0; b2 < NB4; ++b2) { const long long gq = wtab[wb + (size_t)(w * NB4 + b2)] & 0xfffu; wl[w] += gq; ql[w & 3] += gq; tot += gq; }
+                                for (int w = 0; w < SCH4_WARPS; ++w) mx = std::max(mx, wl[w]);
+                                for (int q2 = 0; q2 < 4; ++q2) mq = std::max(mq, ql[q2]);
+                                stat_tot += tot; stat_maxw += mx * SCH4_WARPS; stat_maxq += mq * 4;
+                            }
                         }
                 }
                 cta_item[(size_t)c + 1] = (int)items.size();
@@ -1289,7 +1304,8 @@ int nlls_prepare(nlls_ctx* ctx) {
             // blocks that recur too rarely (unsorted points) leave the tensor-core groups mostly empty: keep the v2 path then
             const double fill = (double)ncontrib / std::max(1.0, 4.0 * (double)ngroups);
             if (getenv("NLLS_B200_VERBOSE"))
-                fprintf(stderr, "[nlls] schur v4 plan: %d CTAs, %d super-tiles over %d tiles, %zu items, DMMA group fill %.2f\n", ncta, nsu_total, nst, items.size(), fill);
+                fprintf(stderr, "[nlls] schur v4 plan: %d CTAs, %d super-tiles over %d tiles, %zu items, DMMA group fill %.2f, per-tile imbalance: warp %.2f scheduler %.2f\n", ncta, nsu_total, nst,
+                        items.size(), fill, (double)stat_maxw / std::max(1ll, stat_tot), (double)stat_maxq / std::max(1ll, stat_tot));
             if (fill < 0.3 && ctx->schur_v4 != 2) v4ok = false;
             if (v4ok) ctx->nsuper = ncta;
         }

@@ -120,6 +120,25 @@ def create_bal_shaped(ncam, npt, nobs, rng, noise=0.01, outlier_frac=0.0, outlie
     return BAProblem(cams, pts, cam_l + 1, pt_l + 1 + ncam, z)
 
 
+def create_scattered(ncam, npt, kmin, kmax, rng, noise=0.01):
+    """Affine BA whose points see RANDOM camera subsets (no locality at all): every camera pair is coupled, so the reduced
+    camera system is dense and consecutive points share no Schur blocks — the opposite corner from create_bal_shaped."""
+    cams = rng.standard_normal((ncam, 6)) + CAM_OFFSET
+    pts = rng.random((npt, 3)) + LM_OFFSET
+    cam_l, pt_l = [], []
+    for l in range(npt):
+        k = int(rng.integers(kmin, kmax + 1))
+        cs = np.sort(rng.choice(ncam, size=min(k, ncam), replace=False))
+        cam_l.append(cs)
+        pt_l.append(np.full(cs.size, l, dtype=np.int64))
+    cam_l = np.concatenate(cam_l).astype(np.int64)
+    pt_l = np.concatenate(pt_l)
+    order = np.lexsort((pt_l, cam_l))  # camera-major cost order, like the reference test
+    pt_l, cam_l = pt_l[order], cam_l[order]
+    z = project_affine(cams[cam_l], pts[pt_l]) + rng.standard_normal((cam_l.size, 2)) * noise
+    return BAProblem(cams, pts, cam_l + 1, pt_l + 1 + ncam, z)
+
+
 def create_shape(name, rng, **kw):
     ncam, npt, nobs = SHAPES[name]
     return create_bal_shaped(ncam, npt, nobs, rng, **kw)

@@ -203,6 +203,31 @@ def test_damped_solve_ladybug_shape(pkg, orc, schur):
         os.environ.pop("NLLS_B200_SCHUR", None)
 
 
+@pytest.mark.parametrize("schur", ["auto", "v4"])
+def test_damped_solve_scattered_visibility(pkg, orc, schur):
+    # points see random camera subsets: dense reduced system (every tile present), no block reuse between consecutive points —
+    # the automatic choice declines the tensor-core Schur plan (group fill) and runs the per-chunk kernel; "v4" forces it anyway
+    rng = np.random.default_rng(11)
+    p = pkg.synthetic.create_scattered(40, 600, 2, 9, rng)
+    pkg.synthetic.perturb_ba_problem(p, 1e-3, 1e-3, rng)
+    P = oracle_problem(orc, p)
+    c_ref = P.linearize()
+    lam = 1e-3
+    x_ref = P.solve(lam)
+    if schur != "auto":
+        os.environ["NLLS_B200_SCHUR"] = schur
+    try:
+        ctx = cuda_context(pkg, p)
+        c = ctx.linearize()
+        assert abs(c - c_ref) <= TOL_COST * abs(c_ref)
+        assert relerr(ctx.hessian_blocks(), P.hess_data()) <= TOL_H
+        ctx.solve(lam)
+        assert relerr(ctx.step(), x_ref) <= 1e-9
+        ctx.close()
+    finally:
+        os.environ.pop("NLLS_B200_SCHUR", None)
+
+
 def _compare_trajectories(pkg, orc, p, kernel_o=None, robust=0, kparams=(), maxiters=100):
     P = oracle_problem(orc, p, kernel=kernel_o)
     res_ref, tr_ref = P.optimize(orc.Options(maxiters=maxiters))
