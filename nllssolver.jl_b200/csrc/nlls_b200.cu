@@ -155,6 +155,8 @@ struct nlls_ctx {
     int nstiles = 0;
     int *d_stile_pt = nullptr, *d_chunk_off = nullptr, *d_ent_off = nullptr;
     // Schur v4 plan (super-tiles: tensor-core accumulation of whole S blocks across consecutive tiles); 2 = forced
+    cudaGraphExec_t red_graph_exec = nullptr;   // the reduced solve's launch sequence (tile-sparse path)
+    int use_graph = 1, red_graph_launches = 0;
     int schur_v4 = 1, nsuper = 0;   // nsuper: CTAs of the v4 kernel (0: v2 path)
     int* d_cta_item = nullptr;
     SchurItem* d_items = nullptr;
@@ -406,18 +408,41 @@ int launch_reduced_solve(nlls_ctx* ctx, bool lu) {
     if (ctx->s_tiled) {
         const RedSolveLists t = redlists(ctx);
         const int nx = ctx->NT * ST;
-        red_permute_kernel<<<(nx + 255) / 256, 256, 0, ctx->st>>>(ctx->d_rhs, ctx->d_xp, ctx->d_pos, ctx->NT, 1); ctx->launches++;
-        for (const auto& l : ctx->fact_launches) {   // factorisation + forward substitution (fused into the diagonal tasks)
-            if (l.kind == 0) ldl_diag_kernel<<<l.cnt, DIAG_THREADS, DIAG_SMEM, ctx->st>>>(ctx->d_S, ctx->d_Linv, ctx->d_red_tasks + l.off, ctx->d_xp);
-            else if (l.kind == 1) ldl_off_kernel<<<GEMM_CTAS * l.cnt, GEMM_THREADS, OFF_SMEM, ctx->st>>>(ctx->d_S, ctx->d_Linv, ctx->d_red_tasks + l.off, ctx->d_xp);
-            else ldl_upd_kernel<<<GEMM_CTAS * l.cnt, GEMM_THREADS, UPD_SMEM, ctx->st>>>(ctx->d_S, ctx->d_red_upds + l.off);
-            ctx->launches++;
+        // ~40 short dependent launches with constant arguments: captured once into a CUDA graph and replayed (the launch gaps of a
+        // plain stream are a quarter of this phase; NLLS_B200_GRAPH=0 keeps plain launches)
+        auto enqueue = [&](int& nl) -> int {
+            red_permute_kernel<<<(nx + 255) / 256, 256, 0, ctx->st>>>(ctx->d_rhs, ctx->d_xp, ctx->d_pos, ctx->NT, 1); ++nl;
+            for (const auto& l : ctx->fact_launches) {   // factorisation + forward substitution (fused into the diagonal tasks)
+                if (l.kind == 0) ldl_diag_kernel<<<l.cnt, DIAG_THREADS, DIAG_SMEM, ctx->st>>>(ctx->d_S, ctx->d_Linv, ctx->d_red_tasks + l.off, ctx->d_xp);
+                else if (l.kind == 1) ldl_off_kernel<<<GEMM_CTAS * l.cnt, GEMM_THREADS, OFF_SMEM, ctx->st>>>(ctx->d_S, ctx->d_Linv, ctx->d_red_tasks + l.off, ctx->d_xp);
+                else ldl_upd_kernel<<<GEMM_CTAS * l.cnt, GEMM_THREADS, UPD_SMEM, ctx->st>>>(ctx->d_S, ctx->d_red_upds + l.off);
+                ++nl;
+            }
+            for (size_t l = ctx->lvl_cols.size(); l-- > 0;) {
+                ldl_bwd_kernel<<<ctx->lvl_cols[l].second, RED_THREADS, BWD_SMEM, ctx->st>>>(ctx->d_S, ctx->d_Linv, t, ctx->d_lvl_cols + ctx->lvl_cols[l].first, ctx->d_xp);
+                ++nl;
+            }
+            red_permute_kernel<<<(nx + 255) / 256, 256, 0, ctx->st>>>(ctx->d_xp, ctx->d_rhs, ctx->d_pos, ctx->NT, 0); ++nl;
+            return NLLS_OK;
+        };
+        if (ctx->use_graph && !ctx->red_graph_exec) {
+            cudaGraph_t g = nullptr;
+            int nl = 0;
+            CK(cudaStreamBeginCapture(ctx->st, cudaStreamCaptureModeThreadLocal));
+            enqueue(nl);
+            CK(cudaStreamEndCapture(ctx->st, &g));
+            CK(cudaGraphInstantiate(&ctx->red_graph_exec, g, 0));
+            CK(cudaGraphDestroy(g));
+            ctx->red_graph_launches = nl;
         }
-        for (size_t l = ctx->lvl_cols.size(); l-- > 0;) {
-            ldl_bwd_kernel<<<ctx->lvl_cols[l].second, RED_THREADS, BWD_SMEM, ctx->st>>>(ctx->d_S, ctx->d_Linv, t, ctx->d_lvl_cols + ctx->lvl_cols[l].first, ctx->d_xp);
-            ctx->launches++;
+        if (ctx->red_graph_exec) {
+            CK(cudaGraphLaunch(ctx->red_graph_exec, ctx->st));
+            ctx->launches += ctx->red_graph_launches;
+        } else {
+            int nl = 0;
+            enqueue(nl);
+            ctx->launches += nl;
         }
-        red_permute_kernel<<<(nx + 255) / 256, 256, 0, ctx->st>>>(ctx->d_xp, ctx->d_rhs, ctx->d_pos, ctx->NT, 0); ctx->launches++;
         CK(cudaGetLastError());
         // every rank factors the same all-reduced system, but the update kernel's FP64 reductions commute only up to rounding:
         // rank 0's camera step is broadcast so that the camera replicas stay bit-identical
@@ -682,6 +707,7 @@ int nlls_create(nlls_ctx** out, int device) {
     ctx->use_tma = (e && e[0] == '0') ? 0 : 1;
     if (const char* g = getenv("NLLS_B200_SCHUR_STRIDE")) ctx->schur_stride = std::max(1, atoi(g));
     if (const char* g = getenv("NLLS_B200_REDUCED")) ctx->s_tiled = (std::string(g) == "dense") ? 0 : 1;
+    if (const char* g = getenv("NLLS_B200_GRAPH")) ctx->use_graph = atoi(g) != 0;
     if (const char* g = getenv("NLLS_B200_SCHUR")) ctx->schur_v4 = (std::string(g) == "v2") ? 0 : ((std::string(g) == "v4") ? 2 : 1);
     if (const char* g = getenv("NLLS_B200_TILE")) { const int v = atoi(g); ctx->tile_env = (v == 64 || v == 128) ? v : 256; }
     { int v = 0; if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && v > 0) ctx->nsm = v; }
@@ -702,6 +728,7 @@ int nlls_destroy(nlls_ctx* ctx) {
                     ctx->d_col_tile, ctx->d_col_row, ctx->d_Linv, ctx->d_xp, ctx->d_stile_pt, ctx->d_chunk_off, ctx->d_chunks, ctx->d_ents, ctx->d_tiles, ctx->d_camstat_part,
                     ctx->d_ad_data, ctx->d_ad_chunks, ctx->d_ad_moff, ctx->d_ad_part, ctx->d_ent_off, ctx->d_cta_item, ctx->d_items, ctx->d_units, ctx->d_wtab, ctx->d_blob};
     for (void* p : ptrs) if (p) cudaFree(p);
+    if (ctx->red_graph_exec) cudaGraphExecDestroy(ctx->red_graph_exec);
     if (ctx->h_scal) cudaFreeHost(ctx->h_scal);
     if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
     if (ctx->cusolver) cusolverDnDestroy(ctx->cusolver);
@@ -823,6 +850,7 @@ int nlls_prepare(nlls_ctx* ctx) {
     if (!ctx) return NLLS_ERR_INVALID;
     if (ctx->prepared) return NLLS_OK;
     CK(cudaSetDevice(ctx->device));
+    if (ctx->red_graph_exec) { cudaGraphExecDestroy(ctx->red_graph_exec); ctx->red_graph_exec = nullptr; }   // captured pointers go stale
     if (ctx->restype == 0) FAIL(NLLS_ERR_INVALID, "no costs set");
     if (ctx->restype == NLLS_RES_ADAPTIVE_OFFSET) return prepare_adaptive(ctx);
     ctx->adaptive = false; ctx->BS = 3;
