@@ -666,59 +666,35 @@ struct SchurPlan4 {
     const SchurItem* items;
     const SchurUnit* units;       // [urow][WARPS * NB]
     const unsigned int* blob;     // per tile: [nob padded to 4: (first obs of its point << 31) | (obs index behind the point's W blocks << 16) | local point]
-                                  //           [ne4 entries: (smem offset of W_i << 16) | smem offset of Y_j, sorted by block, groups of 4]
-    const unsigned int* wtab;     // [wrow][WARPS * NB]: (first entry relative to the tile << 12) | groups of 4     (20 + 12 bits)
+                                  //           [ne4 entries: (smem byte offset of W_i << 16) | smem byte offset of Y_j; per warp, by slot, groups of 4]
+    const unsigned int* wtab;     // [wrow][WARPS * NB + WARPS]: groups of four per (warp, slot), then the first entry of every warp's run
     long long ld;
 };
 
-// The products of one (block, tile): ng groups of four contributions, three DMMA steps each (inner index kk = fk of step s
-// is coordinate (4 s + fk) % 3 of contribution (4 s + fk) / 3, so a fragment load touches at most two operand rows).
-// Deliberately NOT inlined: the kernel calls it once per block slot.
-// Software pipeline: the operands of group g+1 and the entries of group g+2 are in flight during the DMMAs of group g
-// (entries behind a block's last group belong to the next block or to the slack of the blob stage — fetched, never used).
-// The lane's (contribution, d) pairs within a group are
+// Operands of one group of four contributions (three DMMA steps): inner index kk = fk of step s is coordinate (4 s + fk) % 3
+// of contribution (4 s + fk) / 3, so a fragment load touches at most two operand rows.  The lane's (contribution, d) pairs are
 //   fk = 0: (0,0) (1,1) (2,2);  1: (0,1) (1,2) (3,0);  2: (0,2) (2,0) (3,1);  3: (1,0) (2,1) (3,2)
 // (measured alternative: step s <-> coordinate d, one contribution per lane — fewer instructions, more bank conflicts, 6 % slower)
 template <int MT, int NTC> struct SchurAcc { double c[MT][NTC][2]; };
+template <int MT, int NTC> struct SchurOps { double a[3][MT], b[3][NTC]; };
 template <int MT, int NTC>
-__device__ __noinline__ SchurAcc<MT, NTC> schur4_groups(SchurAcc<MT, NTC> acc, uint32_t eb, int ng, uint32_t abase, uint32_t bbase, int fk) {
-    const bool fk3 = fk == 3, fk01 = fk < 2, fk0 = fk == 0;
+__device__ __forceinline__ void schur4_fetch(SchurOps<MT, NTC>& op, const uint4 e4, uint32_t abase, uint32_t bbase, int fk) {
+    const unsigned int en0 = (fk == 3) ? e4.y : e4.x;
+    const unsigned int en1 = (fk < 2) ? e4.y : e4.z;
+    const unsigned int en2 = (fk == 0) ? e4.z : e4.w;
     const uint32_t o0 = 8u * (fk % 3), o1 = 8u * ((4 + fk) % 3), o2 = 8u * ((8 + fk) % 3);
-    auto fetch = [&](const uint4 e4, double (&av)[3][MT], double (&bv)[3][NTC]) {
-        const unsigned int en0 = fk3 ? e4.y : e4.x;
-        const unsigned int en1 = fk01 ? e4.y : e4.z;
-        const unsigned int en2 = fk0 ? e4.z : e4.w;
 #pragma unroll
-        for (int m = 0; m < MT; ++m) {
-            av[0][m] = lds_f64(abase + o0 + (en0 >> 16) + 192u * m);
-            av[1][m] = lds_f64(abase + o1 + (en1 >> 16) + 192u * m);
-            av[2][m] = lds_f64(abase + o2 + (en2 >> 16) + 192u * m);
-        }
-#pragma unroll
-        for (int n = 0; n < NTC; ++n) {
-            bv[0][n] = lds_f64(bbase + o0 + (en0 & 0xffffu) + 192u * n);
-            bv[1][n] = lds_f64(bbase + o1 + (en1 & 0xffffu) + 192u * n);
-            bv[2][n] = lds_f64(bbase + o2 + (en2 & 0xffffu) + 192u * n);
-        }
-    };
-    double av[2][3][MT], bv[2][3][NTC];
-    fetch(lds_u4(eb), av[0], bv[0]);
-    uint4 e4 = lds_u4(eb + 16u);
-    for (int g = 0; g < ng; g += 2) {
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            if (h == 1 && g + 1 >= ng) break;
-            fetch(e4, av[h ^ 1], bv[h ^ 1]);
-            e4 = lds_u4(eb + 16u * (uint32_t)(g + h + 2));
-#pragma unroll
-            for (int s3 = 0; s3 < 3; ++s3)
-#pragma unroll
-                for (int m = 0; m < MT; ++m)
-#pragma unroll
-                    for (int n = 0; n < NTC; ++n) dmma884(acc.c[m][n][0], acc.c[m][n][1], av[h][s3][m], bv[h][s3][n]);
-        }
+    for (int m = 0; m < MT; ++m) {
+        op.a[0][m] = lds_f64(abase + o0 + (en0 >> 16) + 192u * m);
+        op.a[1][m] = lds_f64(abase + o1 + (en1 >> 16) + 192u * m);
+        op.a[2][m] = lds_f64(abase + o2 + (en2 >> 16) + 192u * m);
     }
-    return acc;
+#pragma unroll
+    for (int n = 0; n < NTC; ++n) {
+        op.b[0][n] = lds_f64(bbase + o0 + (en0 & 0xffffu) + 192u * n);
+        op.b[1][n] = lds_f64(bbase + o1 + (en1 & 0xffffu) + 192u * n);
+        op.b[2][n] = lds_f64(bbase + o2 + (en2 & 0xffffu) + 192u * n);
+    }
 }
 
 template <int DC>
@@ -808,7 +784,7 @@ __global__ void __launch_bounds__(SCH4_THREADS, 1) schur4_kernel(DevProblem p, S
     mbar_wait(&bar[0], 0);
     yphase(itA, 0);
     unsigned int wt_next = 0;
-    if (lane < NB) wt_next = sp.wtab[(size_t)itA.wrow * (SCH4_WARPS * NB) + warp * NB + lane];
+    if (lane <= NB) wt_next = sp.wtab[(size_t)itA.wrow * (SCH4_WARPS * NB + SCH4_WARPS) + (lane < NB ? warp * NB + lane : SCH4_WARPS * NB + warp)];
     __syncthreads();
 
     // per-lane operand bases (shared-memory byte addresses): fragment row / column fr.
@@ -821,7 +797,7 @@ __global__ void __launch_bounds__(SCH4_THREADS, 1) schur4_kernel(DevProblem p, S
         const SchurItem it = itA;
         if (k + 2 < nitem) itC = items[k + 2];
         const unsigned int wt = wt_next;
-        if (k + 1 < nitem && lane < NB) wt_next = sp.wtab[(size_t)itB.wrow * (SCH4_WARPS * NB) + warp * NB + lane];
+        if (k + 1 < nitem && lane <= NB) wt_next = sp.wtab[(size_t)itB.wrow * (SCH4_WARPS * NB + SCH4_WARPS) + (lane < NB ? warp * NB + lane : SCH4_WARPS * NB + warp)];
         if (it.flags & 1) {
 #pragma unroll
             for (int b = 0; b < NB; ++b)
@@ -834,12 +810,29 @@ __global__ void __launch_bounds__(SCH4_THREADS, 1) schur4_kernel(DevProblem p, S
             const uint32_t rowb = rowb0 + 8u * (uint32_t)(st * C::ROWS + ((it.flags >> 2) & 1));
             const uint32_t yb = yb0 + 8u * (uint32_t)(st * C::YSZ);
             const uint32_t entb = smem_u32(s_blob0 + st * C::BLOB) + 4u * (uint32_t)((it.nob + 3) & ~3);
+            // The warp's groups of this tile are ONE contiguous run of the blob, ordered by slot: the software pipeline (operands of
+            // the next group and entries of the one after in flight during the DMMAs of the current group) runs across slot
+            // boundaries, so a slot with one or two groups costs no start-up latency.  What is fetched behind the warp's last
+            // group (the next warp's entries, or the slack of the stage) is a valid offset and is never used.
+            uint32_t ep = entb + 4u * __shfl_sync(0xffffffffu, wt, NB);
+            SchurOps<MT, NTC> cur, nxt;
+            schur4_fetch<MT, NTC>(cur, lds_u4(ep), rowb, yb, fk);
+            uint4 e4 = lds_u4(ep + 16u);
 #pragma unroll
             for (int b = 0; b < NB; ++b) {
-                const unsigned int ue = __shfl_sync(0xffffffffu, wt, b);
-                const int ng = (int)(ue & 0xfffu);
-                if (ng == 0) continue;
-                acc[b] = schur4_groups<MT, NTC>(acc[b], entb + 4u * (ue >> 12), ng, rowb, yb, fk);
+                const int ng = (int)__shfl_sync(0xffffffffu, wt, b);
+                for (int g = 0; g < ng; ++g) {
+                    schur4_fetch<MT, NTC>(nxt, e4, rowb, yb, fk);
+                    e4 = lds_u4(ep + 32u);
+                    ep += 16u;
+#pragma unroll
+                    for (int s3 = 0; s3 < 3; ++s3)
+#pragma unroll
+                        for (int m = 0; m < MT; ++m)
+#pragma unroll
+                            for (int n = 0; n < NTC; ++n) dmma884(acc[b].c[m][n][0], acc[b].c[m][n][1], cur.a[s3][m], cur.b[s3][n]);
+                    cur = nxt;
+                }
             }
         }
         if (it.urow >= 0) {   // one FP64 reduction per block element for the whole (super-tile, round)

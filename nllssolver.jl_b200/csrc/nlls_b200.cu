@@ -1179,38 +1179,23 @@ int nlls_prepare(nlls_ctx* ctx) {
         bool v4ok = ctx->schur_v4 != 0;
         ctx->nsuper = 0;
         if (v4ok) {
-            // per tile: padded entry lists (groups of four per block) and the blob [per-observation table | entries]
+            // per tile: group counts of its blocks (contributions padded to groups of four)
             std::vector<long long> tile_groups((size_t)nst, 0);
-            std::vector<int> blob0((size_t)nst, 0), ne4((size_t)nst, 0);
-            std::vector<std::vector<int>> bstart4((size_t)nst);
             long long ngroups = 0, ncontrib = 0;
             const unsigned int nullent = ((8u * (unsigned int)(row4 + 2)) << 16) | (8u * (unsigned int)(ys4 * obs4));   // byte offsets of the zero pads
             for (int t = 0; t < nst; ++t) {
                 const TilePlan& pl = plans[(size_t)t];
-                const int pa = stile_pt[(size_t)t], pb = stile_pt[(size_t)t + 1];
-                const int oa = ctx->h_obs_start[(size_t)pa], ob = ctx->h_obs_start[(size_t)pb];
-                blob0[(size_t)t] = (int)blob.size();
-                for (int i = oa; i < ob; ++i) {
-                    const int pp = ctx->h_obs_pt[(size_t)i];
-                    const unsigned int first = (i == ctx->h_obs_start[(size_t)pp]) ? 0x80000000u : 0u;
-                    blob.push_back(first | ((unsigned int)(ctx->h_obs_start[(size_t)pp + 1] - oa) << 16) | (unsigned int)(pp - pa));
-                }
-                while (blob.size() & 3) blob.push_back(0u);
-                const size_t eb = blob.size();
-                std::vector<int>& bs4 = bstart4[(size_t)t];
+                long long gsum = 0;
                 for (size_t bb = 0; bb < pl.bkey.size(); ++bb) {
-                    bs4.push_back((int)(blob.size() - eb));
-                    for (int k = pl.bstart[bb]; k < pl.bstart[bb + 1]; ++k) blob.push_back(pl.ents4[(size_t)k]);
-                    while ((blob.size() - eb) & 3) blob.push_back(nullent);
+                    gsum += (pl.bstart[bb + 1] - pl.bstart[bb] + 3) / 4;
                     ncontrib += pl.bstart[bb + 1] - pl.bstart[bb];
                 }
-                bs4.push_back((int)(blob.size() - eb));
-                ne4[(size_t)t] = (int)(blob.size() - eb);
-                tile_groups[(size_t)t] = ne4[(size_t)t] / 4;
-                ngroups += tile_groups[(size_t)t];
-                if (blob.size() >= (1ull << 31)) FAIL(NLLS_ERR_UNSUPPORTED, "too many Schur contributions per rank");
-                if (ne4[(size_t)t] > Schur4Cfg<6>::MAXENT) v4ok = false;   // (very long tracks or scattered blocks: v2 path)
+                tile_groups[(size_t)t] = gsum;
+                ngroups += gsum;
+                if (4 * gsum > Schur4Cfg<6>::MAXENT) v4ok = false;   // (very long tracks or scattered blocks: v2 path)
             }
+            const int wstride = cap4 + SCH4_WARPS;   // wtab row: groups per (warp, slot), then the first entry of every warp
+            std::vector<int> blk_at_slot((size_t)cap4);
             // contiguous tile ranges of similar weight, one per CTA
             const int ncta = std::max(1, std::min(ctx->nsm, nst));
             std::vector<long long> wsum((size_t)nst + 1, 0);
@@ -1258,7 +1243,7 @@ int nlls_prepare(nlls_ctx* ctx) {
                         const TilePlan& pl = plans[(size_t)t];
                         for (size_t bb = 0; bb < pl.bkey.size(); ++bb) {
                             const int idx = (int)(std::lower_bound(keys_su.begin(), keys_su.end(), pl.bkey[bb]) - keys_su.begin());
-                            cnt_su[(size_t)idx] += (bstart4[(size_t)t][bb + 1] - bstart4[(size_t)t][bb]) / 4 + 1;
+                            cnt_su[(size_t)idx] += (pl.bstart[bb + 1] - pl.bstart[bb] + 3) / 4 + 1;
                         }
                     }
                     // heaviest blocks first, each to the least-loaded warp of its round that still has a free slot
@@ -1300,31 +1285,49 @@ int nlls_prepare(nlls_ctx* ctx) {
                             SchurItem it;
                             it.pt0 = stile_pt[(size_t)t]; it.npt = stile_pt[(size_t)t + 1] - it.pt0;
                             it.ob0 = ctx->h_obs_start[(size_t)it.pt0]; it.nob = ctx->h_obs_start[(size_t)stile_pt[(size_t)t + 1]] - it.ob0;
-                            it.blob0 = blob0[(size_t)t]; it.ne4 = ne4[(size_t)t];
-                            it.wrow = (int)(wtab.size() / (size_t)cap4);
+                            it.wrow = (int)(wtab.size() / (size_t)wstride);
                             it.urow = (t == tb - 1) ? urow0 + r : -1;
                             it.flags = ((t == ta) ? 1 : 0) | ((r == 0) ? 2 : 0) |
                                        ((((long long)DC * DC * nA + (long long)WB * it.ob0 + 9ll * it.pt0) & 1) ? 4 : 0);   // bit2: the H span starts 8 bytes off a 16-byte boundary
                             it.pad0 = it.pad1 = it.pad2 = 0;
-                            items.push_back(it);
-                            const size_t wb = wtab.size();
-                            wtab.resize(wb + (size_t)cap4, 0u);
+                            // the item's blob: [per-observation table | contribution entries in (warp, slot) order, groups of four]
+                            it.blob0 = (int)blob.size();
+                            for (int i = it.ob0; i < it.ob0 + it.nob; ++i) {
+                                const int pp = ctx->h_obs_pt[(size_t)i];
+                                const unsigned int first = (i == ctx->h_obs_start[(size_t)pp]) ? 0x80000000u : 0u;
+                                blob.push_back(first | ((unsigned int)(ctx->h_obs_start[(size_t)pp + 1] - it.ob0) << 16) | (unsigned int)(pp - it.pt0));
+                            }
+                            while (blob.size() & 3) blob.push_back(0u);
+                            const size_t eb = blob.size();
+                            std::fill(blk_at_slot.begin(), blk_at_slot.end(), -1);
                             for (size_t bb = 0; bb < pl.bkey.size(); ++bb) {
                                 const int idx = (int)(std::lower_bound(keys_su.begin(), keys_su.end(), pl.bkey[bb]) - keys_su.begin());
                                 const int slot = slot_of[(size_t)idx];
-                                if (slot / cap4 != r) continue;
-                                const int f4 = bstart4[(size_t)t][bb], g4 = (bstart4[(size_t)t][bb + 1] - f4) / 4;
-                                wtab[wb + (size_t)(slot - r * cap4)] = ((unsigned int)f4 << 12) | (unsigned int)g4;
-                                if (g4 >= (1 << 12)) v4ok = false;
+                                if (slot / cap4 == r) blk_at_slot[(size_t)(slot - r * cap4)] = (int)bb;
                             }
-                            {   // balance statistics: the slowest warp (and the slowest scheduler: warp % 4) sets the pace of a tile
-                                long long wl[SCH4_WARPS] = {0}, ql[4] = {0}, tot = 0, mx = 0, mq = 0;
-                                for (int w = 0; w < SCH4_WARPS; ++w)
-                                    for (int b2 = 0; b2 < NB4; ++b2) { const long long gq = wtab[wb + (size_t)(w * NB4 + b2)] & 0xfffu; wl[w] += gq; ql[w & 3] += gq; tot += gq; }
-                                for (int w = 0; w < SCH4_WARPS; ++w) mx = std::max(mx, wl[w]);
-                                for (int q2 = 0; q2 < 4; ++q2) mq = std::max(mq, ql[q2]);
-                                stat_tot += tot; stat_maxw += mx * SCH4_WARPS; stat_maxq += mq * 4;
+                            const size_t wb = wtab.size();
+                            wtab.resize(wb + (size_t)wstride, 0u);
+                            long long wl[SCH4_WARPS] = {0}, ql[4] = {0}, tot = 0, mx = 0, mq = 0;
+                            for (int w = 0; w < SCH4_WARPS; ++w) {
+                                wtab[wb + (size_t)cap4 + (size_t)w] = (unsigned int)(blob.size() - eb);
+                                for (int b2 = 0; b2 < NB4; ++b2) {
+                                    const int bb = blk_at_slot[(size_t)(w * NB4 + b2)];
+                                    if (bb < 0) continue;
+                                    const size_t e0 = blob.size();
+                                    for (int k = pl.bstart[(size_t)bb]; k < pl.bstart[(size_t)bb + 1]; ++k) blob.push_back(pl.ents4[(size_t)k]);
+                                    while ((blob.size() - eb) & 3) blob.push_back(nullent);
+                                    const long long g4 = (long long)(blob.size() - e0) / 4;
+                                    wtab[wb + (size_t)(w * NB4 + b2)] = (unsigned int)g4;
+                                    wl[w] += g4; ql[w & 3] += g4; tot += g4;
+                                }
                             }
+                            it.ne4 = (int)(blob.size() - eb);
+                            if (blob.size() >= (1ull << 31)) FAIL(NLLS_ERR_UNSUPPORTED, "too many Schur contributions per rank");
+                            items.push_back(it);
+                            // balance statistics: the slowest warp (and the slowest scheduler: warp % 4) sets the pace of a tile
+                            for (int w = 0; w < SCH4_WARPS; ++w) mx = std::max(mx, wl[w]);
+                            for (int q2 = 0; q2 < 4; ++q2) mq = std::max(mq, ql[q2]);
+                            stat_tot += tot; stat_maxw += mx * SCH4_WARPS; stat_maxq += mq * 4;
                         }
                 }
                 cta_item[(size_t)c + 1] = (int)items.size();
