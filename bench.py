@@ -131,11 +131,15 @@ def run_reference(args, rank):
     t_all = []
     total_iters = args.warmup + args.steps
     # the oracle's optimize() runs whole loops; time W+K iterations and K' = W iterations, report the difference
-    Pw = oracle_problem(p, orc)
-    Pw.linearize()
-    t0 = time.perf_counter(); rw, _ = Pw.optimize(orc.Options(maxiters=max(args.warmup, 1), maxtime=1e5)); tw = time.perf_counter() - t0
-    t0 = time.perf_counter(); rk, _ = P.optimize(orc.Options(maxiters=total_iters, maxtime=1e5)); tk = time.perf_counter() - t0
-    k_done = rk.niterations - rw.niterations
+    # (both runs are bounded in wall time — maxtime, the reference's own termination bit 9 — so that any K / W ends in minutes)
+    tw, nw = 0.0, 0
+    if args.warmup > 0:
+        Pw = oracle_problem(p, orc)
+        Pw.linearize()
+        t0 = time.perf_counter(); rw, _ = Pw.optimize(orc.Options(maxiters=args.warmup, maxtime=60.0)); tw = time.perf_counter() - t0
+        nw = rw.niterations
+    t0 = time.perf_counter(); rk, _ = P.optimize(orc.Options(maxiters=max(total_iters, nw + 1), maxtime=tw + 150.0)); tk = time.perf_counter() - t0
+    k_done = max(rk.niterations - nw, 0)
     dt = max(tk - tw, 1e-9)
     value = p.nobs * k_done / dt
     line = {
