@@ -215,10 +215,17 @@ def main():
     ctx.lm_begin(opts)
     trace = []
 
+    verbose = bool(os.environ.get("BENCH_VERBOSE"))
+    if os.environ.get("BENCH_FAULT_TIMEOUT"):   # debugging aid: dump every thread's stack and exit if the run stalls
+        import faulthandler
+        faulthandler.dump_traceback_later(float(os.environ["BENCH_FAULT_TIMEOUT"]), exit=True)
+
     def step():
         info = ctx.lm_iterate()
         conv = ctx.lm_advance(info.cost, 0)
         trace.append((info.cost, int(info.ntries), conv))
+        if verbose:
+            _log(f"rank {rank}: LM iteration {len(trace)}: cost {info.cost:.9g} tries {int(info.ntries)} conv {conv}")
         return conv
 
     for _ in range(args.warmup):

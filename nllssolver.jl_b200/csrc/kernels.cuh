@@ -719,7 +719,6 @@ __global__ void __launch_bounds__(SCH4_THREADS, 1) schur4_kernel(DevProblem p, S
         const int st = i / C::ZPAD, k = i - st * C::ZPAD;
         s_Y0[st * C::YSZ + YS * C::OBS + k] = 0.0;
     }
-    for (int i = tid; i < 2 * C::BLOB; i += SCH4_THREADS) s_blob0[i] = 0u;   // the entry prefetch may run past a list: keep every word a valid offset
     for (int i = tid; i < 2 * (C::ZPAD + 2); i += SCH4_THREADS) {
         const int st = i / (C::ZPAD + 2), k = i - st * (C::ZPAD + 2);
         s_row0[st * C::ROWS + C::ROW + 2 + k] = 0.0;
@@ -732,7 +731,7 @@ __global__ void __launch_bounds__(SCH4_THREADS, 1) schur4_kernel(DevProblem p, S
         const double* gsrc = p.H + (size_t)p.hB + (size_t)WB * it.ob0 + (size_t)9 * it.pt0 - mis;
         const uint32_t span = (uint32_t)((WB * it.nob + 9 * it.npt + mis + 1) & ~1) * 8u;
         const uint32_t nob4 = (uint32_t)((it.nob + 3) & ~3);
-        const uint32_t bl = (nob4 + (uint32_t)it.ne4) * 4u;
+        const uint32_t bl = (nob4 + (uint32_t)it.ne4 + 8u) * 4u;   // + the two padding groups behind the list
         mbar_expect_tx(&bar[st], span + bl);
         bulk_load(s_row0 + st * C::ROWS, gsrc, span, &bar[st]);
         if (bl) bulk_load(s_blob0 + st * C::BLOB, sp.blob + it.blob0, bl, &bar[st]);
@@ -813,7 +812,8 @@ __global__ void __launch_bounds__(SCH4_THREADS, 1) schur4_kernel(DevProblem p, S
             // The warp's groups of this tile are ONE contiguous run of the blob, ordered by slot: the software pipeline (operands of
             // the next group and entries of the one after in flight during the DMMAs of the current group) runs across slot
             // boundaries, so a slot with one or two groups costs no start-up latency.  What is fetched behind the warp's last
-            // group (the next warp's entries, or the slack of the stage) is a valid offset and is never used.
+            // group (the next warp's entries, or the two padding groups the host appends to every list) is a valid offset and is
+            // never used — stale words of an earlier tile would not be (its per-observation table is not made of offsets).
             uint32_t ep = entb + 4u * __shfl_sync(0xffffffffu, wt, NB);
             SchurOps<MT, NTC> cur, nxt;
             schur4_fetch<MT, NTC>(cur, lds_u4(ep), rowb, yb, fk);

@@ -1322,6 +1322,7 @@ int nlls_prepare(nlls_ctx* ctx) {
                                 }
                             }
                             it.ne4 = (int)(blob.size() - eb);
+                            for (int k = 0; k < 8; ++k) blob.push_back(nullent);   // the kernel's prefetch runs up to two groups past a warp's run
                             if (blob.size() >= (1ull << 31)) FAIL(NLLS_ERR_UNSUPPORTED, "too many Schur contributions per rank");
                             items.push_back(it);
                             // balance statistics: the slowest warp (and the slowest scheduler: warp % 4) sets the pace of a tile

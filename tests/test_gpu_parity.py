@@ -228,6 +228,38 @@ def test_damped_solve_scattered_visibility(pkg, orc, schur):
         os.environ.pop("NLLS_B200_SCHUR", None)
 
 
+def test_damped_solve_many_tiles_per_cta(pkg, orc):
+    # ~1200 Schur tiles: every persistent CTA of the tensor-core Schur kernel pipelines several tiles of different sizes through
+    # its two stages (regression: the operand prefetch past a warp's last group once read stale words of an earlier, larger tile)
+    p = _bal(pkg, 300, 60000, 300000, noise=0.01, outlier_frac=0.02)
+    ok, rid, kp = KERNELS["huber"]
+    P = oracle_problem(orc, p, kernel=ok)
+    P.linearize()
+    lam = 1e-2
+    x_ref = P.solve(lam)
+    for shard in (None, (1, 3)):   # the whole problem, then rank 1 of 3's share of the points (ragged last tiles, offset spans)
+        if shard is None:
+            q = p
+        else:
+            import bench
+            pts_sel, obs_sel = bench.shard_by_point(p, *shard)
+            q = pkg.synthetic.BAProblem(p.cameras, p.points[pts_sel], p.cam_idx[obs_sel], p.pt_idx[obs_sel] - int(pts_sel[0]), p.z[obs_sel])
+        xs = {}
+        for schur in ("v2", "v4"):
+            os.environ["NLLS_B200_SCHUR"] = schur
+            try:
+                ctx = cuda_context(pkg, q)
+                ctx.linearize()
+                ctx.solve(lam)
+                xs[schur] = ctx.step().copy()
+                ctx.close()
+            finally:
+                os.environ.pop("NLLS_B200_SCHUR", None)
+        if shard is None:
+            assert relerr(xs["v4"], x_ref) <= 1e-9
+        assert relerr(xs["v4"], xs["v2"]) <= 1e-9
+
+
 def _compare_trajectories(pkg, orc, p, kernel_o=None, robust=0, kparams=(), maxiters=100):
     P = oracle_problem(orc, p, kernel=kernel_o)
     res_ref, tr_ref = P.optimize(orc.Options(maxiters=maxiters))
