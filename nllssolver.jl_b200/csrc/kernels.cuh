@@ -621,13 +621,15 @@ __global__ void __launch_bounds__(SCH_THREADS, 2) schur2_kernel(DevProblem p, Sc
 // ncu on v2: shared-memory wavefronts at 80 % of peak (half of them bank conflicts — every lane walks its own block's
 // contributions, so the operand rows it reads are scattered), FP64 pipe 33 %, and ~11 us of exposed latency per tile
 // (dependent index loads -> TMA -> inverse -> products, separated by CTA barriers).  Here:
-//  * a WARP owns an S block for a whole super-tile and evaluates  S_ij -= sum_p W_pi' Y_pj  as ONE long GEMM over the
-//    concatenated inner index (contribution, d) with mma.sync.m8n8k4.f64:  A[a][kk] = W_i[d][a]  (rows a < DC of 8),
-//    B[kk][b] = Y_j[d][b]  (b < DC; column DC carries t_p = A_p^-1 g_p, so the rhs segment of a diagonal block falls out of
-//    the same product); four consecutive contributions feed three DMMA steps (12 inner indices).  A fragment load touches
-//    at most two contiguous operand rows, the block accumulator is two registers per lane, and the reductions into S are
-//    issued once per (block, super-tile).  Blocks are dealt to the warps by the host (longest-processing-time first); the
-//    contribution lists are padded to groups of four with entries that point at zeros.
+//  * a WARP owns an S block for a whole super-tile and evaluates  S_ij -= sum_p W_pi' Y_pj  with one mma.sync.m8n8k4.f64 per
+//    contribution:  A[a][kk] = W_i[kk][a]  (rows a < DC of 8),  B[kk][b] = Y_j[kk][b]  (b < DC; column DC carries
+//    t_p = A_p^-1 g_p, so the rhs segment of a diagonal block falls out of the same product).  The inner index has four
+//    slots for three coordinates: s_Y keeps every column as [y0 y1 y2 0], so whatever finite value the A fragment picks up
+//    at kk = 3 (the first element of the next operand row of the span) is multiplied by zero.  With that, the 16 lanes of a
+//    half warp read 13 consecutive doubles of ONE W row and 16 consecutive doubles of ONE Y row: no bank conflicts (the
+//    earlier packing of 4 contributions into 3 DMMAs mixed two rows per load: 2 wavefronts per half warp, and shared-memory
+//    wavefronts are what bounds this kernel).  The block accumulator is two registers per lane and the reductions into S
+//    are issued once per (block, super-tile).  Blocks are dealt to the warps by the host (longest-processing-time first).
 //  * one CTA per SM walks a contiguous range of tiles with a two-stage pipeline: while the warps run the products of tile k
 //    they also compute Y for tile k+1 (both stages resident), and the TMA bulk loads of tile k+2 (its H span and its
 //    contribution list / per-observation table) are in flight — ONE CTA barrier per tile.
@@ -636,20 +638,23 @@ __global__ void __launch_bounds__(SCH_THREADS, 2) schur2_kernel(DevProblem p, Sc
 constexpr int SCH4_WARPS = 16;
 constexpr int SCH4_THREADS = 32 * SCH4_WARPS;
 template <int DC> struct Schur4Cfg {
-    static constexpr int OBS = (DC <= 7) ? 256 : 128;   // tile capacity (observations / points) — two stages must fit 227 KB
+    static constexpr int OBS = (DC <= 7) ? 232 : 128;   // tile capacity (observations / points) — two stages must fit 227 KB
     static constexpr int PTS = OBS / 2;
     static constexpr int MT = (DC + 7) / 8;         // 8-row fragments of a block
     static constexpr int NTC = (DC + 1 + 7) / 8;    // 8-column fragments (DC block columns + the rhs column)
     static constexpr int NB = (MT * NTC == 1) ? 16 : 4;   // block slots per warp (accumulators: NB * MT * NTC * 2 doubles per lane)
     static constexpr int WB = 3 * DC;
-    static constexpr int YS = WB + 3;               // doubles per observation in s_Y: Y_j (3 x DC, column-major) then t_p
-    static constexpr int ZPAD = 3 * 8 * NTC + 8;    // zeros behind the operand arrays: target of the padding entries
+    static constexpr int YS = 4 * (DC + 1);         // doubles per observation in s_Y: (DC + 1) columns [Y_j[:, b] | 0], the last one [t_p | 0]
+    static constexpr int ZPADA = 3 * 8 * MT + 8;    // zeros behind the staged span / behind s_Y: operands of the padding entries
+    static constexpr int ZPADB = 4 * 8 * NTC + 8;
     static constexpr int ROW = WB * OBS + 9 * PTS;  // doubles of H span per stage
-    static constexpr int ROWS = ROW + 2 + ZPAD + 2; // + slack of an 8-byte-misaligned span, + zeros
-    static constexpr int YSZ = YS * OBS + ZPAD;
-    static constexpr int MAXENT = 5376;             // padded contribution entries per tile (the host cuts the tiles accordingly)
-    static constexpr int BLOB = OBS + MAXENT + 8;   // u32 per stage: [per-observation table | contribution entries | slack of the entry prefetch]
+    static constexpr int ROWS = ROW + 2 + ZPADA + 2; // + slack of an 8-byte-misaligned span, + zeros
+    static constexpr int YSZ = YS * OBS + ZPADB;
+    static constexpr int MAXENT = 4096;             // contribution entries per tile (the host cuts the tiles accordingly)
+    static constexpr int BLOB = OBS + MAXENT + 8;   // u32 per stage: [per-observation table | contribution entries | padding entries]
     static constexpr size_t bytes = 2 * ((size_t)(ROWS + YSZ) * sizeof(double) + (size_t)BLOB * sizeof(unsigned int)) + 64;
+    static_assert(ROWS % 2 == 0 && YSZ % 2 == 0 && BLOB % 4 == 0, "stages must stay 16-byte aligned");
+    static_assert(bytes <= 232448, "two stages must fit the 227 KB of shared memory a CTA can have");
 };
 struct SchurUnit {
     long long soff;   // element offset of block element (0,0) in S
@@ -666,35 +671,23 @@ struct SchurPlan4 {
     const SchurItem* items;
     const SchurUnit* units;       // [urow][WARPS * NB]
     const unsigned int* blob;     // per tile: [nob padded to 4: (first obs of its point << 31) | (obs index behind the point's W blocks << 16) | local point]
-                                  //           [ne4 entries: (smem byte offset of W_i << 16) | smem byte offset of Y_j; per warp, by slot, groups of 4]
-    const unsigned int* wtab;     // [wrow][WARPS * NB + WARPS]: groups of four per (warp, slot), then the first entry of every warp's run
+                                  //           [ne4 entries: (smem byte offset of W_i << 16) | smem byte offset of Y_j; per warp, by slot; padded with null entries]
+    const unsigned int* wtab;     // [wrow][WARPS * NB + WARPS]: contributions per (warp, slot), then the first entry of every warp's run
     long long ld;
 };
 
-// Operands of one group of four contributions (three DMMA steps): inner index kk = fk of step s is coordinate (4 s + fk) % 3
-// of contribution (4 s + fk) / 3, so a fragment load touches at most two operand rows.  The lane's (contribution, d) pairs are
-//   fk = 0: (0,0) (1,1) (2,2);  1: (0,1) (1,2) (3,0);  2: (0,2) (2,0) (3,1);  3: (1,0) (2,1) (3,2)
-// (measured alternative: step s <-> coordinate d, one contribution per lane — fewer instructions, more bank conflicts, 6 % slower)
+// Operands of one contribution (one DMMA): the lane's element of the A fragment, W_i[kk = fk][a = fr], and of the B fragment,
+// Y_j[kk = fk][b = fr] — the per-lane parts of the addresses are folded into abase / bbase.
+// (measured alternatives, both slower: 4 contributions packed into 3 DMMAs — two operand rows per load, twice the wavefronts;
+//  DMMA step <-> coordinate with one contribution per lane — four rows per load)
 template <int MT, int NTC> struct SchurAcc { double c[MT][NTC][2]; };
-template <int MT, int NTC> struct SchurOps { double a[3][MT], b[3][NTC]; };
+template <int MT, int NTC> struct SchurOps { double a[MT], b[NTC]; };
 template <int MT, int NTC>
-__device__ __forceinline__ void schur4_fetch(SchurOps<MT, NTC>& op, const uint4 e4, uint32_t abase, uint32_t bbase, int fk) {
-    const unsigned int en0 = (fk == 3) ? e4.y : e4.x;
-    const unsigned int en1 = (fk < 2) ? e4.y : e4.z;
-    const unsigned int en2 = (fk == 0) ? e4.z : e4.w;
-    const uint32_t o0 = 8u * (fk % 3), o1 = 8u * ((4 + fk) % 3), o2 = 8u * ((8 + fk) % 3);
+__device__ __forceinline__ void schur4_fetch(SchurOps<MT, NTC>& op, const uint32_t en, uint32_t abase, uint32_t bbase) {
 #pragma unroll
-    for (int m = 0; m < MT; ++m) {
-        op.a[0][m] = lds_f64(abase + o0 + (en0 >> 16) + 192u * m);
-        op.a[1][m] = lds_f64(abase + o1 + (en1 >> 16) + 192u * m);
-        op.a[2][m] = lds_f64(abase + o2 + (en2 >> 16) + 192u * m);
-    }
+    for (int m = 0; m < MT; ++m) op.a[m] = lds_f64(abase + (en >> 16) + 192u * m);        // 8 rows x 3 doubles further
 #pragma unroll
-    for (int n = 0; n < NTC; ++n) {
-        op.b[0][n] = lds_f64(bbase + o0 + (en0 & 0xffffu) + 192u * n);
-        op.b[1][n] = lds_f64(bbase + o1 + (en1 & 0xffffu) + 192u * n);
-        op.b[2][n] = lds_f64(bbase + o2 + (en2 & 0xffffu) + 192u * n);
-    }
+    for (int n = 0; n < NTC; ++n) op.b[n] = lds_f64(bbase + (en & 0xffffu) + 256u * n);   // 8 columns x 4 doubles further
 }
 
 template <int DC>
@@ -715,12 +708,11 @@ __global__ void __launch_bounds__(SCH4_THREADS, 1) schur4_kernel(DevProblem p, S
     const int fr = lane >> 2, fk = lane & 3;
 
     if (tid == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); }
-    for (int i = tid; i < 2 * C::ZPAD; i += SCH4_THREADS) {
-        const int st = i / C::ZPAD, k = i - st * C::ZPAD;
-        s_Y0[st * C::YSZ + YS * C::OBS + k] = 0.0;
-    }
-    for (int i = tid; i < 2 * (C::ZPAD + 2); i += SCH4_THREADS) {
-        const int st = i / (C::ZPAD + 2), k = i - st * (C::ZPAD + 2);
+    // s_Y: the fourth slot of every column and the pad behind the stage stay zero for the whole kernel; the pad behind the span
+    // is the A operand of the padding entries
+    for (int i = tid; i < 2 * C::YSZ; i += SCH4_THREADS) s_Y0[i] = 0.0;
+    for (int i = tid; i < 2 * (C::ZPADA + 2); i += SCH4_THREADS) {
+        const int st = i / (C::ZPADA + 2), k = i - st * (C::ZPADA + 2);
         s_row0[st * C::ROWS + C::ROW + 2 + k] = 0.0;
     }
     __syncthreads();
@@ -759,9 +751,9 @@ __global__ void __launch_bounds__(SCH4_THREADS, 1) schur4_kernel(DevProblem p, S
                 }
                 const double* gp = p.g + p.gB + (size_t)3 * pg;
                 const double g0 = gp[0], g1 = gp[1], g2 = gp[2];
-                y[WB] = inv[0] * g0 + inv[1] * g1 + inv[2] * g2;
-                y[WB + 1] = inv[1] * g0 + inv[3] * g1 + inv[4] * g2;
-                y[WB + 2] = inv[2] * g0 + inv[4] * g1 + inv[5] * g2;
+                y[4 * DC] = inv[0] * g0 + inv[1] * g1 + inv[2] * g2;
+                y[4 * DC + 1] = inv[1] * g0 + inv[3] * g1 + inv[4] * g2;
+                y[4 * DC + 2] = inv[2] * g0 + inv[4] * g1 + inv[5] * g2;
             }
             const double* w = row + WB * i + 9 * q;
 #pragma unroll
@@ -769,9 +761,9 @@ __global__ void __launch_bounds__(SCH4_THREADS, 1) schur4_kernel(DevProblem p, S
                 const int c = 2 * c2 + h;
                 if (c < DC) {
                     const double w0 = w[3 * c], w1 = w[3 * c + 1], w2 = w[3 * c + 2];
-                    y[3 * c] = fma(inv[2], w2, fma(inv[1], w1, inv[0] * w0));
-                    y[3 * c + 1] = fma(inv[4], w2, fma(inv[3], w1, inv[1] * w0));
-                    y[3 * c + 2] = fma(inv[5], w2, fma(inv[4], w1, inv[2] * w0));
+                    y[4 * c] = fma(inv[2], w2, fma(inv[1], w1, inv[0] * w0));
+                    y[4 * c + 1] = fma(inv[4], w2, fma(inv[3], w1, inv[1] * w0));
+                    y[4 * c + 2] = fma(inv[5], w2, fma(inv[4], w1, inv[2] * w0));
                 }
             }
         }
@@ -786,10 +778,11 @@ __global__ void __launch_bounds__(SCH4_THREADS, 1) schur4_kernel(DevProblem p, S
     if (lane <= NB) wt_next = sp.wtab[(size_t)itA.wrow * (SCH4_WARPS * NB + SCH4_WARPS) + (lane < NB ? warp * NB + lane : SCH4_WARPS * NB + warp)];
     __syncthreads();
 
-    // per-lane operand bases (shared-memory byte addresses): fragment row / column fr.
-    // Lanes of fragment rows >= DC (and of the column behind the rhs column) read whatever follows the operand row — finite
+    // per-lane operand bases (shared-memory byte addresses): A fragment element (row fr, inner fk) sits 3 fr + fk doubles into
+    // the W block, B fragment element (inner fk, column fr) 4 fr + fk doubles into the observation's s_Y row.
+    // Lanes of fragment rows >= DC (and of the columns behind the rhs column) read whatever follows the operand row — finite
     // or not, it only reaches accumulator rows / columns that are never written back.
-    const uint32_t rowb0 = smem_u32(s_row0) + 8u * (3 * fr), yb0 = smem_u32(s_Y0) + 8u * (3 * fr);
+    const uint32_t rowb0 = smem_u32(s_row0) + 8u * (3 * fr + fk), yb0 = smem_u32(s_Y0) + 8u * (4 * fr + fk);
     SchurAcc<MT, NTC> acc[NB];
     for (int k = 0; k < nitem; ++k) {
         const int st = k & 1;
@@ -809,28 +802,26 @@ __global__ void __launch_bounds__(SCH4_THREADS, 1) schur4_kernel(DevProblem p, S
             const uint32_t rowb = rowb0 + 8u * (uint32_t)(st * C::ROWS + ((it.flags >> 2) & 1));
             const uint32_t yb = yb0 + 8u * (uint32_t)(st * C::YSZ);
             const uint32_t entb = smem_u32(s_blob0 + st * C::BLOB) + 4u * (uint32_t)((it.nob + 3) & ~3);
-            // The warp's groups of this tile are ONE contiguous run of the blob, ordered by slot: the software pipeline (operands of
-            // the next group and entries of the one after in flight during the DMMAs of the current group) runs across slot
-            // boundaries, so a slot with one or two groups costs no start-up latency.  What is fetched behind the warp's last
-            // group (the next warp's entries, or the two padding groups the host appends to every list) is a valid offset and is
-            // never used — stale words of an earlier tile would not be (its per-observation table is not made of offsets).
+            // The warp's contributions of this tile are ONE contiguous run of the blob, ordered by slot: the software pipeline
+            // (operands of the next contribution and the entry of the one after in flight during the DMMA of the current one) runs
+            // across slot boundaries, so a slot with one or two contributions costs no start-up latency.  What is fetched behind
+            // the warp's last contribution (the next warp's entries, or the padding entries the host appends to every list) is a
+            // valid offset and is never used — stale words of an earlier tile would not be.
             uint32_t ep = entb + 4u * __shfl_sync(0xffffffffu, wt, NB);
             SchurOps<MT, NTC> cur, nxt;
-            schur4_fetch<MT, NTC>(cur, lds_u4(ep), rowb, yb, fk);
-            uint4 e4 = lds_u4(ep + 16u);
+            schur4_fetch<MT, NTC>(cur, lds_u32(ep), rowb, yb);
+            uint32_t en = lds_u32(ep + 4u);
 #pragma unroll
             for (int b = 0; b < NB; ++b) {
-                const int ng = (int)__shfl_sync(0xffffffffu, wt, b);
-                for (int g = 0; g < ng; ++g) {
-                    schur4_fetch<MT, NTC>(nxt, e4, rowb, yb, fk);
-                    e4 = lds_u4(ep + 32u);
-                    ep += 16u;
+                const int nc = (int)__shfl_sync(0xffffffffu, wt, b);
+                for (int c = 0; c < nc; ++c) {
+                    schur4_fetch<MT, NTC>(nxt, en, rowb, yb);
+                    en = lds_u32(ep + 8u);
+                    ep += 4u;
 #pragma unroll
-                    for (int s3 = 0; s3 < 3; ++s3)
+                    for (int m = 0; m < MT; ++m)
 #pragma unroll
-                        for (int m = 0; m < MT; ++m)
-#pragma unroll
-                            for (int n = 0; n < NTC; ++n) dmma884(acc[b].c[m][n][0], acc[b].c[m][n][1], cur.a[s3][m], cur.b[s3][n]);
+                        for (int n = 0; n < NTC; ++n) dmma884(acc[b].c[m][n][0], acc[b].c[m][n][1], cur.a[m], cur.b[n]);
                     cur = nxt;
                 }
             }

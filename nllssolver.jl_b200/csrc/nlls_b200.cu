@@ -1086,14 +1086,14 @@ int nlls_prepare(nlls_ctx* ctx) {
         stile_pt.push_back(0);
         {
             auto aligned = [&](int64_t pt) { return ((WB * (int64_t)ctx->h_obs_start[(size_t)pt] + 9 * pt) & 1) == 0; };
-            const int sobs = (DC <= 7) ? SCH_OBS : SCH_OBS / 2, spts = sobs / 2;   // == Schur4Cfg<DC>::OBS / PTS
+            const int sobs = (DC <= 7) ? 232 : 128, spts = sobs / 2;   // == Schur4Cfg<DC>::OBS / PTS (<= SCH_OBS / SCH_PTS of the v2 kernel)
             int64_t p0 = 0;
             while (p0 < nB) {
                 int64_t p1 = p0;
                 int64_t contrib = 0;   // pairs (i, j <= i) of the tile: the v4 kernel stages the padded list in shared memory
                 while (p1 < nB && (p1 - p0) < spts && (ctx->h_obs_start[(size_t)p1 + 1] - ctx->h_obs_start[(size_t)p0]) <= sobs) {
                     const int64_t kk = ctx->h_obs_start[(size_t)p1 + 1] - ctx->h_obs_start[(size_t)p1];
-                    if (p1 > p0 && contrib + kk * (kk + 1) / 2 > Schur4Cfg<6>::MAXENT / 2) break;
+                    if (p1 > p0 && contrib + kk * (kk + 1) / 2 > Schur4Cfg<6>::MAXENT - 4) break;
                     contrib += kk * (kk + 1) / 2;
                     ++p1;
                 }
@@ -1151,7 +1151,7 @@ int nlls_prepare(nlls_ctx* ctx) {
                         const unsigned int il = (unsigned int)((keys[k] >> 10) & 0x3ffu), jl = (unsigned int)(keys[k] & 0x3ffu);
                         pl.ents[k] = (il << 16) | jl;
                         // v4: shared-memory byte offsets of W_i (inside the staged H span) and of Y_j
-                        pl.ents4[k] = ((8u * (unsigned int)(WB * il + 9u * (unsigned int)(ctx->h_obs_pt[(size_t)ob0 + il] - pa))) << 16) | (8u * (unsigned int)((WB + 3) * jl));   // bytes
+                        pl.ents4[k] = ((8u * (unsigned int)(WB * il + 9u * (unsigned int)(ctx->h_obs_pt[(size_t)ob0 + il] - pa))) << 16) | (8u * (unsigned int)(4 * (DC + 1)) * jl);   // bytes
                     }
                     k0 = k1;
                 }
@@ -1171,7 +1171,7 @@ int nlls_prepare(nlls_ctx* ctx) {
         //      whose distinct S blocks fit the warps' accumulator slots); see schur4_kernel
         const int NB4 = (DC <= 7) ? 16 : 4;   // == Schur4Cfg<DC>::NB
         const int cap4 = SCH4_WARPS * NB4;
-        const int obs4 = (DC <= 7) ? 256 : 128, row4 = WB * obs4 + 9 * (obs4 / 2), ys4 = WB + 3;
+        const int obs4 = (DC <= 7) ? 232 : 128, row4 = WB * obs4 + 9 * (obs4 / 2), ys4 = 4 * (DC + 1);   // == Schur4Cfg<DC>::OBS, ROW, YS
         std::vector<int> cta_item;
         std::vector<SchurItem> items;
         std::vector<SchurUnit> units;
@@ -1179,20 +1179,16 @@ int nlls_prepare(nlls_ctx* ctx) {
         bool v4ok = ctx->schur_v4 != 0;
         ctx->nsuper = 0;
         if (v4ok) {
-            // per tile: group counts of its blocks (contributions padded to groups of four)
+            // per tile: contributions and distinct blocks
             std::vector<long long> tile_groups((size_t)nst, 0);
-            long long ngroups = 0, ncontrib = 0;
+            long long nblk_tiles = 0, ncontrib = 0;
             const unsigned int nullent = ((8u * (unsigned int)(row4 + 2)) << 16) | (8u * (unsigned int)(ys4 * obs4));   // byte offsets of the zero pads
             for (int t = 0; t < nst; ++t) {
                 const TilePlan& pl = plans[(size_t)t];
-                long long gsum = 0;
-                for (size_t bb = 0; bb < pl.bkey.size(); ++bb) {
-                    gsum += (pl.bstart[bb + 1] - pl.bstart[bb] + 3) / 4;
-                    ncontrib += pl.bstart[bb + 1] - pl.bstart[bb];
-                }
-                tile_groups[(size_t)t] = gsum;
-                ngroups += gsum;
-                if (4 * gsum > Schur4Cfg<6>::MAXENT) v4ok = false;   // (very long tracks or scattered blocks: v2 path)
+                const long long cnt = pl.bstart.empty() ? 0 : pl.bstart.back();
+                tile_groups[(size_t)t] = cnt;
+                ncontrib += cnt; nblk_tiles += (long long)pl.bkey.size();
+                if (cnt + 4 > Schur4Cfg<6>::MAXENT) v4ok = false;   // (very long tracks: v2 path)
             }
             const int wstride = cap4 + SCH4_WARPS;   // wtab row: groups per (warp, slot), then the first entry of every warp
             std::vector<int> blk_at_slot((size_t)cap4);
@@ -1243,7 +1239,7 @@ int nlls_prepare(nlls_ctx* ctx) {
                         const TilePlan& pl = plans[(size_t)t];
                         for (size_t bb = 0; bb < pl.bkey.size(); ++bb) {
                             const int idx = (int)(std::lower_bound(keys_su.begin(), keys_su.end(), pl.bkey[bb]) - keys_su.begin());
-                            cnt_su[(size_t)idx] += (pl.bstart[bb + 1] - pl.bstart[bb] + 3) / 4 + 1;
+                            cnt_su[(size_t)idx] += (pl.bstart[bb + 1] - pl.bstart[bb]) + 2;   // DMMAs + the slot's own overhead
                         }
                     }
                     // heaviest blocks first, each to the least-loaded warp of its round that still has a free slot
@@ -1313,14 +1309,13 @@ int nlls_prepare(nlls_ctx* ctx) {
                                 for (int b2 = 0; b2 < NB4; ++b2) {
                                     const int bb = blk_at_slot[(size_t)(w * NB4 + b2)];
                                     if (bb < 0) continue;
-                                    const size_t e0 = blob.size();
+                                    const long long nc = pl.bstart[(size_t)bb + 1] - pl.bstart[(size_t)bb];
                                     for (int k = pl.bstart[(size_t)bb]; k < pl.bstart[(size_t)bb + 1]; ++k) blob.push_back(pl.ents4[(size_t)k]);
-                                    while ((blob.size() - eb) & 3) blob.push_back(nullent);
-                                    const long long g4 = (long long)(blob.size() - e0) / 4;
-                                    wtab[wb + (size_t)(w * NB4 + b2)] = (unsigned int)g4;
-                                    wl[w] += g4; ql[w & 3] += g4; tot += g4;
+                                    wtab[wb + (size_t)(w * NB4 + b2)] = (unsigned int)nc;
+                                    wl[w] += nc; ql[w & 3] += nc; tot += nc;
                                 }
                             }
+                            while ((blob.size() - eb) & 3) blob.push_back(nullent);
                             it.ne4 = (int)(blob.size() - eb);
                             for (int k = 0; k < 8; ++k) blob.push_back(nullent);   // the kernel's prefetch runs up to two groups past a warp's run
                             if (blob.size() >= (1ull << 31)) FAIL(NLLS_ERR_UNSUPPORTED, "too many Schur contributions per rank");
@@ -1333,12 +1328,13 @@ int nlls_prepare(nlls_ctx* ctx) {
                 }
                 cta_item[(size_t)c + 1] = (int)items.size();
             }
-            // blocks that recur too rarely (unsorted points) leave the tensor-core groups mostly empty: keep the v2 path then
-            const double fill = (double)ncontrib / std::max(1.0, 4.0 * (double)ngroups);
+            // blocks that recur too rarely within a tile (unsorted points) make the per-slot bookkeeping and the final reductions
+            // dominate: keep the v2 path then
+            const double reuse = (double)ncontrib / std::max(1.0, (double)nblk_tiles);
             if (getenv("NLLS_B200_VERBOSE"))
-                fprintf(stderr, "[nlls] schur v4 plan: %d CTAs, %d super-tiles over %d tiles, %zu items, DMMA group fill %.2f, per-tile imbalance: warp %.2f scheduler %.2f\n", ncta, nsu_total, nst,
-                        items.size(), fill, (double)stat_maxw / std::max(1ll, stat_tot), (double)stat_maxq / std::max(1ll, stat_tot));
-            if (fill < 0.3 && ctx->schur_v4 != 2) v4ok = false;
+                fprintf(stderr, "[nlls] schur v4 plan: %d CTAs, %d super-tiles over %d tiles, %zu items, %.2f contributions per (tile, block), per-tile imbalance: warp %.2f scheduler %.2f\n", ncta, nsu_total, nst,
+                        items.size(), reuse, (double)stat_maxw / std::max(1ll, stat_tot), (double)stat_maxq / std::max(1ll, stat_tot));
+            if (reuse < 1.5 && ctx->schur_v4 != 2) v4ok = false;
             if (v4ok) ctx->nsuper = ncta;
         }
         if (ctx->nsuper == 0) {   // v2 structures

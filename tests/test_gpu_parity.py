@@ -248,7 +248,7 @@ def test_damped_solve_many_tiles_per_cta(pkg, orc):
         for schur in ("v2", "v4"):
             os.environ["NLLS_B200_SCHUR"] = schur
             try:
-                ctx = cuda_context(pkg, q)
+                ctx = cuda_context(pkg, q, rid, kp)
                 ctx.linearize()
                 ctx.solve(lam)
                 xs[schur] = ctx.step().copy()
