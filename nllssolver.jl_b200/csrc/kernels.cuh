@@ -644,7 +644,8 @@ template <int DC> struct Schur4Cfg {
     static constexpr int NTC = (DC + 1 + 7) / 8;    // 8-column fragments (DC block columns + the rhs column)
     static constexpr int NB = (MT * NTC == 1) ? 16 : 4;   // block slots per warp (accumulators: NB * MT * NTC * 2 doubles per lane)
     static constexpr int WB = 3 * DC;
-    static constexpr int YS = 4 * (DC + 1);         // doubles per observation in s_Y: (DC + 1) columns [Y_j[:, b] | 0], the last one [t_p | 0]
+    static constexpr int YS = 4 * (DC + 1) + 1;     // doubles per observation in s_Y: (DC + 1) columns [Y_j[:, b] | 0], the last one [t_p | 0];
+                                                    // + 1: an odd row stride keeps the Y phase's stores (one observation per lane pair) off each other's banks
     static constexpr int ZPADA = 3 * 8 * MT + 8;    // zeros behind the staged span / behind s_Y: operands of the padding entries
     static constexpr int ZPADB = 4 * 8 * NTC + 8;
     static constexpr int ROW = WB * OBS + 9 * PTS;  // doubles of H span per stage
@@ -653,7 +654,7 @@ template <int DC> struct Schur4Cfg {
     static constexpr int MAXENT = 4096;             // contribution entries per tile (the host cuts the tiles accordingly)
     static constexpr int BLOB = OBS + MAXENT + 8;   // u32 per stage: [per-observation table | contribution entries | padding entries]
     static constexpr size_t bytes = 2 * ((size_t)(ROWS + YSZ) * sizeof(double) + (size_t)BLOB * sizeof(unsigned int)) + 64;
-    static_assert(ROWS % 2 == 0 && YSZ % 2 == 0 && BLOB % 4 == 0, "stages must stay 16-byte aligned");
+    static_assert(ROWS % 2 == 0 && (2 * YSZ) % 2 == 0 && BLOB % 4 == 0, "stages must stay 16-byte aligned");
     static_assert(bytes <= 232448, "two stages must fit the 227 KB of shared memory a CTA can have");
 };
 struct SchurUnit {

@@ -1093,7 +1093,7 @@ int nlls_prepare(nlls_ctx* ctx) {
                 int64_t contrib = 0;   // pairs (i, j <= i) of the tile: the v4 kernel stages the padded list in shared memory
                 while (p1 < nB && (p1 - p0) < spts && (ctx->h_obs_start[(size_t)p1 + 1] - ctx->h_obs_start[(size_t)p0]) <= sobs) {
                     const int64_t kk = ctx->h_obs_start[(size_t)p1 + 1] - ctx->h_obs_start[(size_t)p1];
-                    if (p1 > p0 && contrib + kk * (kk + 1) / 2 > Schur4Cfg<6>::MAXENT - 4) break;
+                    if (p1 > p0 && contrib + kk * (kk + 1) / 2 > Schur4Cfg<6>::MAXENT - 4 * SCH4_WARPS) break;   // (+ quad padding per warp)
                     contrib += kk * (kk + 1) / 2;
                     ++p1;
                 }
@@ -1151,7 +1151,7 @@ int nlls_prepare(nlls_ctx* ctx) {
                         const unsigned int il = (unsigned int)((keys[k] >> 10) & 0x3ffu), jl = (unsigned int)(keys[k] & 0x3ffu);
                         pl.ents[k] = (il << 16) | jl;
                         // v4: shared-memory byte offsets of W_i (inside the staged H span) and of Y_j
-                        pl.ents4[k] = ((8u * (unsigned int)(WB * il + 9u * (unsigned int)(ctx->h_obs_pt[(size_t)ob0 + il] - pa))) << 16) | (8u * (unsigned int)(4 * (DC + 1)) * jl);   // bytes
+                        pl.ents4[k] = ((8u * (unsigned int)(WB * il + 9u * (unsigned int)(ctx->h_obs_pt[(size_t)ob0 + il] - pa))) << 16) | (8u * (unsigned int)(4 * (DC + 1) + 1) * jl);   // bytes
                     }
                     k0 = k1;
                 }
@@ -1171,7 +1171,7 @@ int nlls_prepare(nlls_ctx* ctx) {
         //      whose distinct S blocks fit the warps' accumulator slots); see schur4_kernel
         const int NB4 = (DC <= 7) ? 16 : 4;   // == Schur4Cfg<DC>::NB
         const int cap4 = SCH4_WARPS * NB4;
-        const int obs4 = (DC <= 7) ? 232 : 128, row4 = WB * obs4 + 9 * (obs4 / 2), ys4 = 4 * (DC + 1);   // == Schur4Cfg<DC>::OBS, ROW, YS
+        const int obs4 = (DC <= 7) ? 232 : 128, row4 = WB * obs4 + 9 * (obs4 / 2), ys4 = 4 * (DC + 1) + 1;   // == Schur4Cfg<DC>::OBS, ROW, YS
         std::vector<int> cta_item;
         std::vector<SchurItem> items;
         std::vector<SchurUnit> units;
@@ -1188,7 +1188,7 @@ int nlls_prepare(nlls_ctx* ctx) {
                 const long long cnt = pl.bstart.empty() ? 0 : pl.bstart.back();
                 tile_groups[(size_t)t] = cnt;
                 ncontrib += cnt; nblk_tiles += (long long)pl.bkey.size();
-                if (cnt + 4 > Schur4Cfg<6>::MAXENT) v4ok = false;   // (very long tracks: v2 path)
+                if (cnt + 4 * SCH4_WARPS > Schur4Cfg<6>::MAXENT) v4ok = false;   // (very long tracks: v2 path)
             }
             const int wstride = cap4 + SCH4_WARPS;   // wtab row: groups per (warp, slot), then the first entry of every warp
             std::vector<int> blk_at_slot((size_t)cap4);
@@ -1305,6 +1305,7 @@ int nlls_prepare(nlls_ctx* ctx) {
                             wtab.resize(wb + (size_t)wstride, 0u);
                             long long wl[SCH4_WARPS] = {0}, ql[4] = {0}, tot = 0, mx = 0, mq = 0;
                             for (int w = 0; w < SCH4_WARPS; ++w) {
+                                while ((blob.size() - eb) & 3) blob.push_back(nullent);   // every warp's run starts on a quad of entries
                                 wtab[wb + (size_t)cap4 + (size_t)w] = (unsigned int)(blob.size() - eb);
                                 for (int b2 = 0; b2 < NB4; ++b2) {
                                     const int bb = blk_at_slot[(size_t)(w * NB4 + b2)];
@@ -1317,7 +1318,7 @@ int nlls_prepare(nlls_ctx* ctx) {
                             }
                             while ((blob.size() - eb) & 3) blob.push_back(nullent);
                             it.ne4 = (int)(blob.size() - eb);
-                            for (int k = 0; k < 8; ++k) blob.push_back(nullent);   // the kernel's prefetch runs up to two groups past a warp's run
+                            for (int k = 0; k < 8; ++k) blob.push_back(nullent);   // the kernel's prefetch runs up to two quads past a warp's run
                             if (blob.size() >= (1ull << 31)) FAIL(NLLS_ERR_UNSUPPORTED, "too many Schur contributions per rank");
                             items.push_back(it);
                             // balance statistics: the slowest warp (and the slowest scheduler: warp % 4) sets the pace of a tile
