@@ -278,6 +278,18 @@ def main():
                 "linearize_total": {"algorithmic_bytes": ctx.algorithmic_bytes(capi.TIME_LINEARIZE), "ms": kern["linearize"],
                                     "achieved": ctx.algorithmic_bytes(capi.TIME_LINEARIZE) / (kern["linearize"] * 1e-3) / 1e9}}
 
+    # the other HBM-bound kernels of an LM try against the same peak (algorithmic bytes: H read once, + variables / lists)
+    other = {}
+    for name, which, key in [("schur4_kernel (Schur elimination of the point blocks, FP64 tensor cores)", capi.TIME_SCHUR, "schur"),
+                             ("backsub_kernel (point back-substitution + update + step statistics)", capi.TIME_BACKSUB, "backsub_update"),
+                             ("cost_kernel", capi.TIME_COST, "cost")]:
+        try:
+            ab = ctx.algorithmic_bytes(which)
+            if ab > 0:
+                other[name] = {"algorithmic_bytes": ab, "ms": kern[key], "achieved": ab / (kern[key] * 1e-3) / 1e9, "frac": ab / (kern[key] * 1e-3) / 1e9 / peak}
+        except Exception:
+            pass
+    roofline["other_kernels"] = other
     _log("kernel timing done")
     # ---- end to end through the C ABI with host buffers: every step uploads problem.variables from pinned host memory,
     # runs one LM iteration and reads the updated variables + cost back

@@ -1201,7 +1201,7 @@ int nlls_prepare(nlls_ctx* ctx) {
             for (int c = 1; c < ncta; ++c)
                 cta_tile[(size_t)c] = (int)(std::lower_bound(wsum.begin(), wsum.end(), wsum[(size_t)nst] * c / ncta) - wsum.begin());
             for (int c = 1; c <= ncta; ++c) cta_tile[(size_t)c] = std::max(cta_tile[(size_t)c], cta_tile[(size_t)c - 1]);
-            int maxrun = 64;
+            int maxrun = 32;   // tiles per super-tile: longer runs drift across cameras (per-tile warp imbalance), shorter ones flush more often
             if (const char* g = getenv("NLLS_B200_SCHUR_RUN")) maxrun = std::max(1, atoi(g));
             cta_item.assign((size_t)ncta + 1, 0);
             std::vector<unsigned long long> cur, merged, keys_su;
@@ -1761,6 +1761,10 @@ int nlls_algorithmic_bytes(nlls_ctx* ctx, int which, double* bytes) {
         case NLLS_TIME_LIN_POINT: *bytes = rd + 8 * (nobs * DC * 3 + nB * 9 + nB * 3); break;
         case NLLS_TIME_LIN_CAM: *bytes = rd + 8 * (nA * DC * DC + nA * DC); break;
         case NLLS_TIME_COST: *bytes = rd; break;
+        // Schur elimination: H's point rows (W, V) and g_p read once, A_p^-1 written; the reduced system itself is small
+        case NLLS_TIME_SCHUR: *bytes = 8 * (nobs * DC * 3 + nB * 9 + nB * 3 + nB * 6); break;
+        // back-substitution: H's point rows, A_p^-1, g_p, camera step read once; points read and written, point step written
+        case NLLS_TIME_BACKSUB: *bytes = 8 * (nobs * DC * 3 + nB * 9 + nB * 6 + nB * 3 + nA * DC + 3 * nB * 3); break;
         default: *bytes = 0; return NLLS_ERR_INVALID;
     }
     return NLLS_OK;
