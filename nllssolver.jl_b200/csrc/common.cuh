@@ -8,7 +8,7 @@ namespace nlls {
 constexpr int TILE_OBS = 256;   // observations per point-major tile (one thread each)
 constexpr int TILE_PTS = 128;   // points per tile (upper bound)
 constexpr int LIN_THREADS = 256;
-constexpr int CAM_CHUNK = 2048; // observations per camera-pass work item
+constexpr int CAM_CHUNK = 4096; // observations per camera-pass work item
 constexpr int DP = 3;           // point DoF
 
 // ---------------------------------------------------------------------------------------------------
@@ -114,6 +114,12 @@ __device__ __forceinline__ double lds_f64(uint32_t addr) {
     return v;
 }
 
+// a global load that stays where it is written (the compiler sinks plain loads into the branch that consumes them)
+__device__ __forceinline__ double ldg_f64_here(const double* p) {
+    double v;
+    asm volatile("ld.global.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
 __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
     uint32_t v;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
