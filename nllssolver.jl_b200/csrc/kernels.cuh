@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(TO) lin_point_kernel(DevProblem p, const int4*
             c = 0.5 * rho;                                            //                   src/residual.jl:110
             double gc[DC], gp[3];
 #pragma unroll
-            for (int a = 0; a < DC; ++a) gc[a] = fma(Jc[1][a], r[1], Jc[0][a] * r[0]);   // g = J' r   :73   (explicit FMAs: -fmad=false)
+            for (int a = 0; a < DC; ++a) gc[a] = jtr<R>(Jc, r, a);                        // g = J' r   :73   (explicit FMAs: -fmad=false)
 #pragma unroll
             for (int b = 0; b < 3; ++b) gp[b] = fma(Jp[1][b], r[1], Jp[0][b] * r[0]);
             const double td2 = 2 * d2;
@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(TO) lin_point_kernel(DevProblem p, const int4*
             for (int a = 0; a < DC; ++a)
 #pragma unroll
                 for (int b = 0; b < 3; ++b) {
-                    double h = fma(Jp[1][b], Jc[1][a], Jp[0][b] * Jc[0][a]);          // H = J' J   :74
+                    double h = jtj_pc<R>(Jp, Jc, b, a);                                // H = J' J   :74
                     if (d1 != 1.0) h *= d1;                                            // IRLS       :91-93
                     if (d2 != 0.0) h = fma(td2 * gp[b], gc[a], h);                     // Triggs     :95-97
                     w[b + 3 * a] = h;
@@ -327,14 +327,15 @@ __global__ void __launch_bounds__(256, (R::DC <= 6) ? 2 : 1) lin_cam_kernel(DevP
             // weights fold into the accumulation:  acc += d1 (J'J) + (2 d2 g) g'  (exact no-ops when d1 == 1 / d2 == 0)
             double gc[DC], tg[DC];
 #pragma unroll
-            for (int a = 0; a < DC; ++a) { gc[a] = fma(Jc[1][a], r[1], Jc[0][a] * r[0]); tg[a] = (2 * d2) * gc[a]; }
+            for (int a = 0; a < DC; ++a) { gc[a] = jtr<R>(Jc, r, a); tg[a] = (2 * d2) * gc[a]; }
             int q = 0;
 #pragma unroll
             for (int a2 = 0; a2 < DC; ++a2)
 #pragma unroll
                 for (int a = a2; a < DC; ++a) {
-                    const double h = fma(Jc[1][a], Jc[1][a2], Jc[0][a] * Jc[0][a2]);
-                    acc[q] = fma(tg[a], gc[a2], fma(d1, h, acc[q]));
+                    bool zero;
+                    const double h = jtj_cc<R>(Jc, a, a2, &zero);
+                    acc[q] = zero ? fma(tg[a], gc[a2], acc[q]) : fma(tg[a], gc[a2], fma(d1, h, acc[q]));
                     ++q;
                 }
 #pragma unroll
