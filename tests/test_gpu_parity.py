@@ -260,6 +260,39 @@ def test_damped_solve_many_tiles_per_cta(pkg, orc):
         assert relerr(xs["v4"], xs["v2"]) <= 1e-9
 
 
+@pytest.mark.parametrize("seed", [0, 1])
+def test_fuzz_damped_solve(pkg, orc, seed):
+    # randomised shapes (scripts/fuzz_solve.py): banded / scattered visibility, tracks of 2 .. 200 observations, 1 .. 500 Schur
+    # tiles, every fixed robust kernel family, damping over five decades — forced v2, forced v4 and the automatic Schur choice
+    # must all reproduce the oracle's full-system solve
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("fuzz_solve", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "scripts", "fuzz_solve.py"))
+    fz = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(fz)
+    rng = np.random.default_rng(seed)
+    for case in range(10):
+        kind, p = fz.random_problem(rng)
+        robust = int(rng.integers(0, 3))
+        ok = [(0, 0.0, False, 1.0), (1, 0.02, False, 1.0), (2, 0.02, False, 1.0)][robust]
+        kp = () if robust == 0 else (0.02,)
+        lam = float(10.0 ** rng.uniform(-3, 1))
+        P = oracle_problem(orc, p, kernel=ok)
+        c_ref = P.linearize()
+        x_ref = P.solve(lam)
+        for schur in ("v2", "v4", None):
+            if schur:
+                os.environ["NLLS_B200_SCHUR"] = schur
+            try:
+                ctx = cuda_context(pkg, p, robust, kp)
+                c = ctx.linearize()
+                assert abs(c - c_ref) <= TOL_COST * abs(c_ref), (case, kind, schur)
+                ctx.solve(lam)
+                assert relerr(ctx.step(), x_ref) <= 1e-8, (case, kind, schur, p.ncam, p.npt, p.nobs)
+                ctx.close()
+            finally:
+                os.environ.pop("NLLS_B200_SCHUR", None)
+
+
 def _compare_trajectories(pkg, orc, p, kernel_o=None, robust=0, kparams=(), maxiters=100):
     P = oracle_problem(orc, p, kernel=kernel_o)
     res_ref, tr_ref = P.optimize(orc.Options(maxiters=maxiters))
