@@ -466,11 +466,12 @@ def _pinhole_problem(pkg, orc, ncam, npt, nobs, seed=3):
     return cams, pts, shape.cam_idx, shape.pt_idx, z
 
 
+@pytest.mark.parametrize("shape", [(12, 400, 1900), (60, 8000, 40000)])   # one tile per CTA / several tiles per CTA, multi-round super-tiles
 @pytest.mark.parametrize("schur", ["v2", "v4"])
-def test_pinhole_linearize_and_solve(pkg, orc, schur):
+def test_pinhole_linearize_and_solve(pkg, orc, schur, shape):
     # 9-DoF camera blocks (two 8-row DMMA fragments per block in the v4 Schur kernel), SO(3) update on the cameras
     capi = pkg.capi
-    ncam, npt, nobs = 12, 400, 1900
+    ncam, npt, nobs = shape
     cams, pts, cam_idx, pt_idx, z = _pinhole_problem(pkg, orc, ncam, npt, nobs)
     P = orc.Problem()
     P.add_variables(orc.VT_PINHOLE, cams)
