@@ -833,7 +833,8 @@ void Problem::gethessian() {                                                    
 }
 
 // =======================================================================================
-// LM iteration + outer loop                     src/iterators.jl:120-172, src/optimize.jl:109-180
+// iterators + outer loop                        src/iterators.jl:11-208, src/optimize.jl:109-180
+// (Newton :11-27, Dogleg :30-115, Levenberg-Marquardt :120-172, gradient descent :177-208)
 // =======================================================================================
 Result Problem::optimize(const Options& opt, std::vector<IterRecord>* trace) {
     uint64_t starttime = time_ns();
@@ -843,6 +844,9 @@ Result Problem::optimize(const Options& opt, std::vector<IterRecord>* trace) {
     zero();
     if (varnext.size() != variables.size()) varnext = variables;   // :80-82
     double lambda = 0.0;                                       // LevMarData(0.0)  src/iterators.jl:124
+    double trustradius = 0.0;                                  // DoglegData       :36,42
+    double stepsize = 1.0;                                     // GradientDescentData :181,184
+    std::vector<double> cauchy;                                // DoglegData.cauchy
     int64_t fails = 0, iternum = 0;
     uint64_t stoptime = starttime + opt.maxtime_ns;            // :115
     t_init += time_ns() - starttime;
@@ -869,50 +873,129 @@ Result Problem::optimize(const Options& opt, std::vector<IterRecord>* trace) {
     };
     while (true) {
         iternum += 1;
-        // ---- iterate!(::LevMarData)                                       src/iterators.jl:139-172
-        gethessian();                                          // :141
-        if (lambda == 0) {                                     // initlambda :131-137,142-144
-            double mx = 0;
-            for (int64_t j = 0; j < dof; ++j) {
-                double d = sparse ? hessval[(size_t)diagpos[(size_t)j]] : Adense[(size_t)(j + dof * j)];
-                mx = std::max(mx, std::fabs(d));
-            }
-            lambda = mx * 1e-6;
-        }
-        double lastlambda = 0.0, mu = 2.0;
         int64_t ntries = 0;
-        double cost_;
+        double cost_ = 0.0;
         double maxstep = 0;
-        while (true) {
-            scale_diag(lambda - lastlambda);                   // :149
-            lastlambda = lambda;
+        auto solve_now = [&]() {                                // negate!(solve!(linsystem, options))  src/linearsolver.jl:20-32
             t0 = time_ns();
-            if (sparse) ldl_factor_solve(hess, hessval.data(), ldl, b.data(), x.data());     // src/linearsolver.jl:29
-            else solve_dense((int)dof, Adense.data(), b.data(), x.data());                  // :30
-            for (auto& xi : x) xi = -xi;                       // negate!  :152
+            if (sparse) ldl_factor_solve(hess, hessval.data(), ldl, b.data(), x.data());
+            else solve_dense((int)dof, Adense.data(), b.data(), x.data());
+            for (auto& xi : x) xi = -xi;
             t_solver += time_ns() - t0;
             res.linearsolvers += 1; ntries += 1;
-            for (size_t i = 0; i < variables.size(); ++i)      // update!  src/linearsystem.jl:206-213
-                varnext[i] = update(variables[i], x.data() + (boffsets[i] - 1));
+        };
+        auto update_and_cost = [&]() {                          // update! + cost(varnext)
+            for (size_t i = 0; i < variables.size(); ++i) varnext[i] = update(variables[i], x.data() + (boffsets[i] - 1));
             t0 = time_ns();
-            cost_ = this->cost(varnext);                       // :157
+            const double c = this->cost(varnext);
             t_cost += time_ns() - t0;
             res.costcomputations += 1;
-            maxstep = 0; bool stepnan = false;
-            for (double xi : x) { if (std::isnan(xi)) stepnan = true; maxstep = std::max(maxstep, std::fabs(xi)); }
-            if (stepnan) maxstep = std::numeric_limits<double>::quiet_NaN();  // maximum() propagates NaN
-            if (!(cost_ > bestcost) || maxstep < opt.dstep) {  // :160
-                scale_diag(-lastlambda);                       // :162
-                double bAb = sparse ? fast_bAb_sparse(hess, hessval.data(), x.data()) : fast_bAb_dense((int)dof, Adense.data(), x.data());
-                double gx = 0; for (int64_t j = 0; j < dof; ++j) gx += b[(size_t)j] * x[(size_t)j];
-                double q = (cost_ - bestcost) / (0.5 * bAb + gx);      // :163
-                double t = 2 * q - 1;
-                lambda *= q < 0.983 ? 1 - t * t * t : 0.1;             // :164
-                break;
+            return c;
+        };
+        auto maxabs_x = [&]() {                                 // maximum(abs, x), NaN-propagating
+            double m = 0; bool nan = false;
+            for (double xi : x) { if (std::isnan(xi)) nan = true; m = std::max(m, std::fabs(xi)); }
+            return nan ? std::numeric_limits<double>::quiet_NaN() : m;
+        };
+        auto norm_x = [&]() { double sq = 0; for (double xi : x) sq += xi * xi; return std::sqrt(sq); };
+        if (opt.iterator == 0) {
+            // ---- iterate!(::NewtonData)                                       src/iterators.jl:17-27
+            gethessian();
+            solve_now();
+            cost_ = update_and_cost();
+        } else if (opt.iterator == 2) {
+            // ---- iterate!(::DoglegData)                                       src/iterators.jl:48-113
+            gethessian();                                      // gethessgrad :49
+            double gnorm2 = 0; for (double g : b) gnorm2 += g * g;                                  // :52
+            const double bAb = sparse ? fast_bAb_sparse(hess, hessval.data(), b.data()) : fast_bAb_dense((int)dof, Adense.data(), b.data());
+            const double a = gnorm2 / (bAb + std::numeric_limits<double>::min());                   // :53 (floatmin)
+            cauchy.resize((size_t)dof);
+            for (int64_t j = 0; j < dof; ++j) cauchy[(size_t)j] = -a * b[(size_t)j];               // :54
+            const double alpha2 = a * a * gnorm2, alpha = std::sqrt(alpha2);                        // :55-56
+            if (trustradius == 0) trustradius = alpha;                                              // :57-60
+            double beta = 0;
+            if (alpha < trustradius) { solve_now(); beta = norm_x(); }                              // :61-66
+            cost_ = bestcost;                                                                       // :68
+            while (true) {
+                double linear_approx;
+                if (!(alpha < trustradius)) {                                                       // first leg :71-74
+                    for (int64_t j = 0; j < dof; ++j) x[(size_t)j] = (trustradius / alpha) * cauchy[(size_t)j];
+                    linear_approx = trustradius * (2 * alpha - trustradius) / (2 * a);
+                } else if (beta <= trustradius) {                                                   // full Newton step :77-79
+                    linear_approx = cost_;
+                } else {                                                                            // second leg :80-95
+                    double sq_leg = 0, c = 0;
+                    for (int64_t j = 0; j < dof; ++j) { x[(size_t)j] -= cauchy[(size_t)j]; }
+                    for (int64_t j = 0; j < dof; ++j) { sq_leg += x[(size_t)j] * x[(size_t)j]; c += cauchy[(size_t)j] * x[(size_t)j]; }
+                    const double trsq = trustradius * trustradius - alpha2;
+                    double step = std::sqrt(c * c + sq_leg * trsq);
+                    step = (c <= 0) ? (-c + step) / sq_leg : trsq / (c + step);
+                    for (int64_t j = 0; j < dof; ++j) x[(size_t)j] = x[(size_t)j] * step + cauchy[(size_t)j];
+                    linear_approx = 0.5 * (a * (1 - step) * (1 - step) * gnorm2) + step * (2 - step) * cost_;
+                }
+                cost_ = update_and_cost();                                                          // :98-101
+                const double mu_ = (bestcost - cost_) / linear_approx;                              // :103
+                if (mu_ > 0.375) trustradius = std::max(trustradius, 3 * norm_x());                 // :104-105
+                else if (mu_ < 0.125) trustradius *= 0.5;                                           // :106-107
+                maxstep = maxabs_x();
+                if (!(cost_ > bestcost) || maxstep < opt.dstep) break;                              // :110-113
             }
-            lambda *= mu;                                      // :169-170
-            mu *= 2.0;
+        } else if (opt.iterator == 3) {
+            // ---- iterate!(::GradientDescentData)                              src/iterators.jl:187-206
+            for (int64_t j = 0; j < dof; ++j) x[(size_t)j] = -b[(size_t)j] * stepsize;             // :190
+            cost_ = update_and_cost();
+            while (cost_ > bestcost) {                                                              // :195
+                double coststep = 0; for (int64_t j = 0; j < dof; ++j) coststep += x[(size_t)j] * b[(size_t)j];   // :197
+                const double costdiff = bestcost + coststep - cost_;                                // :198
+                stepsize *= 0.5 * coststep / costdiff;                                              // :200
+                for (int64_t j = 0; j < dof; ++j) x[(size_t)j] = -b[(size_t)j] * stepsize;         // :202
+                cost_ = update_and_cost();
+            }
+            stepsize *= 2;                                                                          // :207
+        } else {
+            // ---- iterate!(::LevMarData)                                       src/iterators.jl:139-172
+            gethessian();                                          // :141
+            if (lambda == 0) {                                     // initlambda :131-137,142-144
+                double mx = 0;
+                for (int64_t j = 0; j < dof; ++j) {
+                    double d = sparse ? hessval[(size_t)diagpos[(size_t)j]] : Adense[(size_t)(j + dof * j)];
+                    mx = std::max(mx, std::fabs(d));
+                }
+                lambda = mx * 1e-6;
+            }
+            double lastlambda = 0.0, mu = 2.0;
+            while (true) {
+                scale_diag(lambda - lastlambda);                   // :149
+                lastlambda = lambda;
+                t0 = time_ns();
+                if (sparse) ldl_factor_solve(hess, hessval.data(), ldl, b.data(), x.data());     // src/linearsolver.jl:29
+                else solve_dense((int)dof, Adense.data(), b.data(), x.data());                  // :30
+                for (auto& xi : x) xi = -xi;                       // negate!  :152
+                t_solver += time_ns() - t0;
+                res.linearsolvers += 1; ntries += 1;
+                for (size_t i = 0; i < variables.size(); ++i)      // update!  src/linearsystem.jl:206-213
+                    varnext[i] = update(variables[i], x.data() + (boffsets[i] - 1));
+                t0 = time_ns();
+                cost_ = this->cost(varnext);                       // :157
+                t_cost += time_ns() - t0;
+                res.costcomputations += 1;
+                maxstep = 0; bool stepnan = false;
+                for (double xi : x) { if (std::isnan(xi)) stepnan = true; maxstep = std::max(maxstep, std::fabs(xi)); }
+                if (stepnan) maxstep = std::numeric_limits<double>::quiet_NaN();  // maximum() propagates NaN
+                if (!(cost_ > bestcost) || maxstep < opt.dstep) {  // :160
+                    scale_diag(-lastlambda);                       // :162
+                    double bAb = sparse ? fast_bAb_sparse(hess, hessval.data(), x.data()) : fast_bAb_dense((int)dof, Adense.data(), x.data());
+                    double gx = 0; for (int64_t j = 0; j < dof; ++j) gx += b[(size_t)j] * x[(size_t)j];
+                    double q = (cost_ - bestcost) / (0.5 * bAb + gx);      // :163
+                    double t = 2 * q - 1;
+                    lambda *= q < 0.983 ? 1 - t * t * t : 0.1;             // :164
+                    break;
+                }
+                lambda *= mu;                                      // :169-170
+                mu *= 2.0;
+            }
         }
+        if (opt.iterator != 1) maxstep = maxabs_x();            // maximum(abs, linsystem.x)  src/optimize.jl:149
         cost = cost_;
         // ---- back in optimizeinternal!                                      src/optimize.jl:128-165
         int64_t terminate = opt.callback_terminate;            // callback(cost, ...) -> (cost, terminate)
@@ -924,7 +1007,7 @@ Result Problem::optimize(const Options& opt, std::vector<IterRecord>* trace) {
             if (fails == 1) varbest = variables;               // :137-144 (a swap when sizes match; content equal for our purposes)
         }
         std::swap(variables, varnext);                         // updatefromnext!  :147
-        if (trace) trace->push_back(IterRecord{cost, lambda, maxstep, ntries});
+        if (trace) trace->push_back(IterRecord{cost, opt.iterator == 2 ? trustradius : (opt.iterator == 3 ? stepsize : lambda), maxstep, ntries});
         converged = 0;
         converged |= (int64_t)std::isinf(cost) << 0;
         converged |= (int64_t)std::isnan(cost) << 1;

@@ -76,6 +76,7 @@ struct Options {               // src/structs.jl:22-35
     int64_t maxfails = 3, maxiters = 100;
     uint64_t maxtime_ns = 30000000000ull;
     int callback_terminate = 0;  // emulates a callback returning (cost, terminate)  test/functional.jl:51
+    int iterator = 1;            // src/structs.jl:4: 0 newton, 1 levenbergmarquardt, 2 dogleg, 3 gradientdescent
 };
 struct Result {                // src/structs.jl:37-50
     double startcost = 0, bestcost = 0, timetotal = 0, timeinit = 0, timecost = 0, timegradient = 0, timesolver = 0;
@@ -83,7 +84,7 @@ struct Result {                // src/structs.jl:37-50
 };
 struct IterRecord {            // what a storecostscallback / printoutcallback would see per outer iteration
     double cost;      // value returned by iterate!
-    double lambda;    // levmardata.lambda after the iteration
+    double lambda;    // levmardata.lambda after the iteration (dogleg: trust radius; gradient descent: step size; newton: 0)
     double maxstep;   // maximum(abs, x)
     int64_t ntries;   // inner LM tries (linear solves) in this outer iteration
 };

@@ -16,6 +16,7 @@ _LIB = None
 
 # ids shared with oracle/nlls_oracle.hpp
 VT_EUCLID, VT_CONTAMGAUSS, VT_PINHOLE = 0, 1, 2
+IT_NEWTON, IT_LM, IT_DOGLEG, IT_GD = 0, 1, 2, 3   # src/structs.jl:4
 RT_AFFINE_BA, RT_PINHOLE_BA, RT_ADAPTIVE_OFFSET, RT_ROSENBROCK_A, RT_ROSENBROCK_B = 1, 2, 3, 4, 5
 RK_NONE, RK_HUBER, RK_HUBER2O, RK_GEMANMCCLURE = 0, 1, 2, 3
 
@@ -110,10 +111,11 @@ class Options(C.Structure):
     """NLLSOptions (src/structs.jl:22-35); callback_terminate emulates a callback's `terminate`."""
     _fields_ = [("reldcost", C.c_double), ("absdcost", C.c_double), ("dstep", C.c_double),
                 ("maxfails", C.c_int64), ("maxiters", C.c_int64), ("maxtime_ns", C.c_uint64),
-                ("callback_terminate", C.c_int64)]
+                ("callback_terminate", C.c_int64), ("iterator", C.c_int64)]
 
-    def __init__(self, maxiters=100, reldcost=1e-15, absdcost=1e-15, dstep=1e-15, maxfails=3, maxtime=30.0, callback_terminate=0):
-        super().__init__(reldcost, absdcost, dstep, maxfails, maxiters, int(round(maxtime * 1e9)), callback_terminate)
+    def __init__(self, maxiters=100, reldcost=1e-15, absdcost=1e-15, dstep=1e-15, maxfails=3, maxtime=30.0, callback_terminate=0,
+                 iterator=1):
+        super().__init__(reldcost, absdcost, dstep, maxfails, maxiters, int(round(maxtime * 1e9)), callback_terminate, iterator)
 
 
 class Result(C.Structure):

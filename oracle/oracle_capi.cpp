@@ -130,7 +130,7 @@ void orc_solve(void* p, double lambda, double* xout) {
     for (int64_t j = 0; j < n; ++j) xout[j] = -xout[j];
 }
 
-struct orc_options { double reldcost, absdcost, dstep; int64_t maxfails, maxiters; uint64_t maxtime_ns; int64_t callback_terminate; };
+struct orc_options { double reldcost, absdcost, dstep; int64_t maxfails, maxiters; uint64_t maxtime_ns; int64_t callback_terminate; int64_t iterator; };
 struct orc_result { double startcost, bestcost, timetotal, timeinit, timecost, timegradient, timesolver;
                     int64_t termination, niterations, costcomputations, gradientcomputations, linearsolvers; };
 struct orc_iterrecord { double cost, lambda, maxstep; int64_t ntries; };
@@ -141,6 +141,7 @@ int64_t orc_optimize(void* p, const orc_options* o, orc_result* r, orc_iterrecor
     opt.reldcost = o->reldcost; opt.absdcost = o->absdcost; opt.dstep = o->dstep;
     opt.maxfails = o->maxfails; opt.maxiters = o->maxiters; opt.maxtime_ns = o->maxtime_ns;
     opt.callback_terminate = (int)o->callback_terminate;
+    opt.iterator = (int)o->iterator;
     std::vector<IterRecord> tr;
     Result res = pr->optimize(opt, &tr);
     r->startcost = res.startcost; r->bestcost = res.bestcost; r->timetotal = res.timetotal; r->timeinit = res.timeinit;

@@ -184,6 +184,29 @@ def test_functional_rosenbrock(orc):
     assert all(b <= a for a, b in zip(costs, costs[1:]))                      # :74
 
 
+def test_functional_rosenbrock_other_iterators(orc):
+    # test/functional.jl:57-61 (Newton), :78-86 (Dogleg), :88-96 (gradient descent) — the oracle side of SURVEY §8f row 1
+    # (the CUDA path implements Levenberg-Marquardt only and rejects the others with NLLS_ERR_UNSUPPORTED)
+    P = _rosenbrock(orc, 0.0, 0.0)
+    res, _ = P.optimize(orc.Options(maxtime=0.0, callback_terminate=13))      # the reference test runs this first (:51): one LM iteration
+    res, _ = P.optimize(orc.Options(iterator=orc.IT_NEWTON))                  # :57-61
+    assert P.cost() == res.bestcost
+    v = P.variables()
+    assert v[0] == pytest.approx(1.0, rel=1e-10) and v[1] == pytest.approx(1.0, rel=1e-10)
+    P = _rosenbrock(orc, -0.5, 2.5)                                           # :78-86
+    res, tr = P.optimize(orc.Options(iterator=orc.IT_DOGLEG))
+    assert P.cost() == res.bestcost
+    v = P.variables()
+    assert v[0] == pytest.approx(1.0, rel=1e-10) and v[1] == pytest.approx(1.0, rel=1e-10)
+    costs = [t.cost for t in tr]
+    assert all(b <= a for a, b in zip(costs, costs[1:]))                      # :86
+    P = _rosenbrock(orc, 1.0 - 1e-5, 1.0)                                     # :88-96
+    res, _ = P.optimize(orc.Options(iterator=orc.IT_GD))
+    assert P.cost() == res.bestcost
+    v = P.variables()
+    assert v[0] == pytest.approx(1.0, rel=1e-5) and v[1] == pytest.approx(1.0, rel=1e-5)
+
+
 def test_optimizeba_properties(orc, pkg):
     # test/optimizeba.jl:49-76 (LM parts; optimizesingles! is out of scope)
     syn = pkg.synthetic
