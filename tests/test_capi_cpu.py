@@ -51,3 +51,26 @@ def test_unsupported_options(pkg):
         pkg.optimize(prob, pkg.NLLSOptions(iterator=pkg.newton))
     with pytest.raises(pkg.capi.NLLSError):
         pkg.optimize(prob, pkg.NLLSOptions(), unfixed=[True])
+
+
+def test_bench_reference_arm(pkg):
+    """bench.py --impl reference (the CPU arm the driver runs next to ours): one JSON line with the contract's keys, also for
+    W = 0 and under a multi-rank launch where only rank 0 works."""
+    import json
+    import subprocess
+    import sys
+    for extra_env, args in [({}, ["--steps", "1", "--warmup", "0"]), ({}, ["--steps", "2", "--warmup", "1"]),
+                            ({"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"}, ["--gpus", "2", "--steps", "1", "--warmup", "0"])]:
+        env = dict(os.environ)
+        env.update(extra_env)
+        out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "ladybug"] + args,
+                             capture_output=True, text=True, env=env, timeout=300)
+        assert out.returncode == 0, out.stderr[-2000:]
+        lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+        if extra_env:
+            assert not lines   # the other ranks exit 0 without work
+            continue
+        line = json.loads(lines[-1])
+        assert line["impl"] == "reference" and line["value"] > 0 and line["unit"] == "residual blocks/s"
+        assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] == 1
+        assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"]
