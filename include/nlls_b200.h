@@ -64,7 +64,7 @@ enum nlls_robust {
     NLLS_ROBUST_SCALED = 16        /* OR-ed in: Scaled(kernel, height) kparams: w, height   */
 };
 
-/* NLLSOptions (src/structs.jl:22-35). iterator must be NLLS_ITER_LM. */
+/* NLLSOptions (src/structs.jl:22-35). iterator: NLLS_ITER_LM or NLLS_ITER_NEWTON (the others return NLLS_ERR_UNSUPPORTED). */
 enum nlls_iterator { NLLS_ITER_NEWTON = 0, NLLS_ITER_LM = 1, NLLS_ITER_DOGLEG = 2, NLLS_ITER_GD = 3 };
 typedef struct nlls_options {
     double reldcost;
@@ -132,6 +132,7 @@ int nlls_update(nlls_ctx* ctx);
 /* The outer loop of optimizeinternal! (src/optimize.jl:109-180), split where the reference calls the user callback:
  *   nlls_lm_begin    setupiterator + first costgradhess!                                   (:109-121)
  *   nlls_lm_iterate  iterate!(::LevMarData, ...) — damp/solve/update/cost until accepted    (:126, src/iterators.jl:139-172)
+ *                    (options.iterator == NLLS_ITER_NEWTON: iterate!(::NewtonData, ...) — one undamped try, :17-27)
  *   [the caller runs callback(cost, ...) -> (cost, terminate) here]                        (:128)
  *   nlls_lm_advance  best/fail bookkeeping, variables <-> varnext swap, termination word, re-linearisation when it is 0
  *                    (:130-171); `terminate` is OR-ed in << 16

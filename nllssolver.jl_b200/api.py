@@ -387,8 +387,8 @@ def optimize(problem, options=None, unfixed=None, callback=nullcallback):
     options = options or NLLSOptions()
     if unfixed is not None:
         raise capi.NLLSError(capi.ERR_UNSUPPORTED, "`unfixed` masks are not implemented (all variables are optimised)")
-    if options.iterator != levenbergmarquardt:
-        raise capi.NLLSError(capi.ERR_UNSUPPORTED, "only the Levenberg-Marquardt iterator is implemented")
+    if options.iterator not in (levenbergmarquardt, newton):
+        raise capi.NLLSError(capi.ERR_UNSUPPORTED, "only the Levenberg-Marquardt and Newton iterators are implemented")
     assert len(problem.variables) > 0
     ctx = problem.context()
     copts = options.c()

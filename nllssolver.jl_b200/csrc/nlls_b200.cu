@@ -1463,7 +1463,8 @@ int nlls_update(nlls_ctx* ctx) {
 int nlls_lm_begin(nlls_ctx* ctx, const nlls_options* opts) {
     if (!ctx || !opts) return NLLS_ERR_INVALID;
     const uint64_t t0 = now_ns();
-    if (opts->iterator != NLLS_ITER_LM) FAIL(NLLS_ERR_UNSUPPORTED, "only the Levenberg-Marquardt iterator is implemented");
+    if (opts->iterator != NLLS_ITER_LM && opts->iterator != NLLS_ITER_NEWTON)
+        FAIL(NLLS_ERR_UNSUPPORTED, "only the Levenberg-Marquardt and Newton iterators are implemented");
     TRY(nlls_prepare(ctx));
     CK(cudaSetDevice(ctx->device));
     ctx->opts = *opts;
@@ -1490,6 +1491,21 @@ int nlls_lm_iterate(nlls_ctx* ctx, nlls_iterinfo* info) {
     CK(cudaSetDevice(ctx->device));
     const nlls_options& o = ctx->opts;
     ctx->iternum += 1;                                           // src/optimize.jl:124
+    if (o.iterator == NLLS_ITER_NEWTON) {
+        // ---- iterate!(::NewtonData)                               src/iterators.jl:17-27: undamped solve, update, cost — no
+        // acceptance test; the outer loop's best / fails bookkeeping (nlls_lm_advance) handles a cost increase
+        const uint64_t ts = now_ns();
+        TRY(do_try(ctx, 0.0));
+        ctx->t_solver += now_ns() - ts;
+        ctx->linearsolvers += 1; ctx->costcomputations += 1;
+        const double* s = ctx->h_scal;
+        const double cost_ = s[SC_COST_TRY];
+        const double maxstep = (std::isnan(s[SC_P_MAX]) || std::isnan(s[SC_C_MAX])) ? std::numeric_limits<double>::quiet_NaN() : std::max(s[SC_P_MAX], s[SC_C_MAX]);
+        ctx->cost = cost_;
+        ctx->maxstep = maxstep;
+        if (info) { info->cost = cost_; info->lambda = 0.0; info->maxstep = maxstep; info->stepnorm = std::sqrt(s[SC_P_SQ] + s[SC_C_SQ]); info->ntries = 1; info->accepted = !(cost_ > ctx->bestcost); }
+        return NLLS_OK;
+    }
     // ---- iterate!(::LevMarData)                                 src/iterators.jl:139-172
     if (ctx->lambda == 0) {                                      // initlambda  :131-137,142-144
         if (ctx->adaptive) { adapt_maxdiag_kernel<<<1, 32, 0, ctx->st>>>(ctx->d_H, (int)ctx->dof, ctx->d_scal + SC_MAXDIAG); ctx->launches++; CK(cudaGetLastError()); }

@@ -48,7 +48,7 @@ def test_unsupported_options(pkg):
     prob = pkg.NLLSProblem()
     prob.addvariable(pkg.EuclideanVector([0.0] * 6))
     with pytest.raises(pkg.capi.NLLSError):
-        pkg.optimize(prob, pkg.NLLSOptions(iterator=pkg.newton))
+        pkg.optimize(prob, pkg.NLLSOptions(iterator=pkg.dogleg))
     with pytest.raises(pkg.capi.NLLSError):
         pkg.optimize(prob, pkg.NLLSOptions(), unfixed=[True])
 

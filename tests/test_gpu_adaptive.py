@@ -139,3 +139,38 @@ def test_adaptive_c3_scale(pkg, orc):
     assert np.allclose([1 / k[0], 1 / k[1], k[2]], [1.0, 10.0, 1 / 3], rtol=0.05)
     assert m == pytest.approx(1.0, abs=0.02)
     ctx.close()
+
+
+@pytest.mark.parametrize("start", [(0.9, 9.0, 0.75), (0.5, 5.0, 0.6)])
+def test_adaptive_newton_trajectory(pkg, orc, start):
+    """The Newton iterator (src/iterators.jl:17-27) on the dense adaptive problem: from the closer start it
+    converges like the reference's functional test; from the far start every step increases the cost, the outer loop counts
+    fails and restores the best variables.  Costs are compared while the iteration is still moving: once the decrease is at
+    rounding level (1e-13 relative here) the 1e-15 termination tests see summation-order noise, so the number of tail
+    iterations may differ between the device's tree sums and the oracle's sequential folds."""
+    data, vi, means = _two_means()
+    P = _oracle(orc, data, vi, means, start=start)
+    res_ref, tr_ref = P.optimize(orc.Options(iterator=orc.IT_NEWTON, maxiters=30))
+    ctx = _cuda(pkg, data, vi, means, start=start)
+    ctx.lm_begin(pkg.NLLSOptions(iterator=pkg.newton, maxiters=30).c())
+    tr, conv = [], 0
+    while conv == 0:
+        info = ctx.lm_iterate()
+        tr.append(info.cost)
+        conv = ctx.lm_advance(info.cost, 0)
+    res = ctx.lm_end()
+    ref = [t.cost for t in tr_ref]
+    moving = 1
+    while moving < min(len(tr), len(ref)) and abs(ref[moving] - ref[moving - 1]) > 1e-9 * abs(ref[moving]):
+        moving += 1
+    assert moving >= 4
+    for c, t in zip(tr[:moving], ref[:moving]):
+        assert c == pytest.approx(t, rel=1e-9)
+    assert res.bestcost == pytest.approx(res_ref.bestcost, rel=TOL_FINAL)
+    assert ctx.cost(0) == res.bestcost
+    if res_ref.termination & (1 << 7):   # diverging start: fails > maxfails, the start variables are restored on both sides
+        assert res.termination == res_ref.termination and res.niterations == res_ref.niterations
+    k = ctx.get_variables(pkg.capi.VAR_CONTAMGAUSS, 1, 3)[0]
+    m = ctx.get_variables(pkg.capi.VAR_SCALAR, 2, 1)[:, 0]
+    assert np.allclose(np.concatenate([k, m]), P.variables(), rtol=1e-6, atol=1e-9)
+    ctx.close()
