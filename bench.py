@@ -138,7 +138,7 @@ def run_reference(args, rank):
         Pw.linearize()
         t0 = time.perf_counter(); rw, _ = Pw.optimize(orc.Options(maxiters=args.warmup, maxtime=60.0)); tw = time.perf_counter() - t0
         nw = rw.niterations
-    t0 = time.perf_counter(); rk, _ = P.optimize(orc.Options(maxiters=max(total_iters, nw + 1), maxtime=tw + 150.0)); tk = time.perf_counter() - t0
+    t0 = time.perf_counter(); rk, trk = P.optimize(orc.Options(maxiters=max(total_iters, nw + 1), maxtime=tw + 150.0)); tk = time.perf_counter() - t0
     k_done = max(rk.niterations - nw, 0)
     dt = max(tk - tw, 1e-9)
     value = p.nobs * k_done / dt
@@ -152,6 +152,8 @@ def run_reference(args, rank):
                                    f"(Julia unavailable), 1 thread of {os.cpu_count()} — the reference's hot loop is single-threaded (SURVEY F4)"},
         "e2e": {"value": value, "unit": "residual blocks/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "lm_iters_per_sec": k_done / dt,
+        # per-iteration costs of the W + K iterations (same start, same generator as the CUDA arm): the two arms' traces are comparable
+        "cost_trace": [r.cost for r in trk], "tries_trace": [int(r.ntries) for r in trk],
     }
     print(json.dumps(line), flush=True)
 
@@ -340,7 +342,7 @@ def main():
         "lin_blocks_per_sec": p.nobs / (kern["linearize"] * 1e-3),
         "roofline": roofline, "kernel_ms": kern, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks.summary(),
         "setup_s": t_setup, "wall_ms_per_step": wall_ms / args.steps,
-        "cost_trace": [t[0] for t in trace],
+        "cost_trace": [t[0] for t in trace], "tries_trace": [t[1] for t in trace],
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(p, args.cpu_iters)

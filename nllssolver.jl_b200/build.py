@@ -11,7 +11,7 @@ NVCC_FLAGS = [
     "-fmad=false",  # residual/assembly kernels are HBM-bound; keeping mul/add unfused tracks the reference's (unfused) Julia arithmetic
     "-shared", "-Xcompiler", "-fPIC",
 ]
-LIBS = ["-lcusolver", "-lcublas", "-ldl", "-lpthread", "-Xlinker", "-rpath,/usr/local/cuda/lib64"]
+LIBS = ["-ldl", "-lpthread"]   # NCCL is resolved with dlopen at nlls_comm_init; no CUDA math library is linked
 
 
 def needs_build():

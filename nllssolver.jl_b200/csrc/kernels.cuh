@@ -410,28 +410,8 @@ __global__ void maxdiag_kernel(DevProblem p, unsigned long long* out) {
 // Schur elimination of the point blocks (new functionality, mathematically equal to the reference's
 // full-system solve (H + lambda I) x = g, src/linearsolver.jl:29 — SURVEY F3).
 //   A_p = V_p + lambda I ;  S = U + lambda I - sum_p W_p' A_p^-1 W_p ;  rhs = g_c - sum_p W_p' A_p^-1 g_p
-// S is the dense (DC nA)^2 reduced camera matrix, column-major, lower triangle.
+// S is the tile-sparse reduced camera matrix of reduced.cuh (lower triangle in the permuted tile numbering).
 // ---------------------------------------------------------------------------------------------------
-template <int DC>
-__global__ void schur_init_kernel(DevProblem p, double* __restrict__ S, double* __restrict__ rhs, double lambda, int add_u) {
-    // one thread per (camera, element of the lower triangle incl. diagonal) + rhs
-    constexpr int NE = DC * DC;
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long n = (long long)DC * p.nA;
-    if (idx < (long long)p.nA * NE) {
-        const long long cam = idx / NE; const int e = (int)(idx - cam * NE);
-        const int a = e % DC, b = e / DC;
-        if (a >= b && add_u) {
-            double v = p.H[(size_t)NE * cam + e];
-            if (a == b) v += lambda;
-            S[(size_t)(cam * DC + a) + (size_t)n * (cam * DC + b)] = v;
-        }
-    } else if (idx < (long long)p.nA * NE + n) {
-        const long long k = idx - (long long)p.nA * NE;
-        rhs[k] = add_u ? p.g[k] : 0.0;
-    }
-}
-
 // load the tile's contiguous H span into shared memory (TMA bulk load when 16-byte aligned)
 __device__ __forceinline__ void load_span(double* s_dst, const double* gsrc, int span, uint64_t* bar, int use_tma) {
     const bool aligned = ((reinterpret_cast<uintptr_t>(gsrc) & 15) == 0) && ((span & 1) == 0);
@@ -1096,14 +1076,6 @@ __global__ void __launch_bounds__(256) reduce_stats_kernel(const double* __restr
     if (blockIdx.x == 0) { for (int i = threadIdx.x; i < n; i += 256) v = nanmax(v, src[i]); v = block_nanmax(v, s_red); }
     else { for (int i = threadIdx.x; i < n; i += 256) v += src[i]; v = block_sum(v, s_red); }
     if (threadIdx.x == 0) out[blockIdx.x] = v;
-}
-
-// mirror the lower triangle of the dense n x n matrix into the upper one (LU fallback for non-PD systems)
-__global__ void symmetrize_kernel(double* S, long long n) {
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= n * n) return;
-    const long long r = idx % n, c = idx / n;
-    if (r < c) S[idx] = S[c + n * r];
 }
 
 }  // namespace nlls

@@ -2,7 +2,6 @@
 // Host logic mirrors src/optimize.jl:109-180 and src/iterators.jl:139-172; every numeric operation runs in the
 // sm_100a kernels of kernels.cuh.  There is no CPU compute path: without a CUDA device nlls_create fails.
 #include <cuda_runtime.h>
-#include <cusolverDn.h>
 #include <dlfcn.h>
 
 #include <algorithm>
@@ -76,14 +75,14 @@ enum Scal {
     SC_COST_LIN = 0, SC_COST_TRY = 1,
     SC_P_MAX = 2, SC_P_SQ = 3, SC_P_XHX = 4, SC_P_GX = 5,      // point-row terms (summed / maxed over ranks)
     SC_C_MAX = 6, SC_C_SQ = 7, SC_C_XHX = 8, SC_C_GX = 9,      // camera terms (replicated)
-    SC_MAXDIAG = 10, SC_INFO = 11, SC_COUNT = 16
+    SC_MAXDIAG = 10, SC_INFO = 11, SC_EXCH = 12 /* .. 15: host values exchanged between ranks */, SC_COUNT = 16
 };
 }  // namespace
 
 struct nlls_ctx {
     int device = 0;
     cudaStream_t st = nullptr, st2 = nullptr;
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_t0 = nullptr, ev_t1 = nullptr, ev_b0 = nullptr, ev_b1 = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_t0 = nullptr, ev_t1 = nullptr, ev_b0 = nullptr, ev_b1 = nullptr, ev_c0 = nullptr, ev_c1 = nullptr;
     std::string err;
     int64_t launches = 0;
 
@@ -125,11 +124,6 @@ struct nlls_ctx {
     double *d_scal = nullptr, *h_scal = nullptr;
     void* d_flush = nullptr;
     size_t flush_bytes = 0;
-    cusolverDnHandle_t cusolver = nullptr;
-    double* d_work = nullptr;
-    int lwork = 0;
-    int* d_info = nullptr;
-    int* d_ipiv = nullptr;
     int use_tma = 1;
     int tile_obs = 0;               // observations per point tile = threads per CTA of the tile kernels: the smallest of 64 / 128 / 256 that
                                     // holds the longest track (NLLS_B200_TILE overrides)
@@ -137,8 +131,8 @@ struct nlls_ctx {
     int4* d_tiles = nullptr;        // (pt0, npt, ob0, nob) per point tile
     int nsm = 148, lin_grid = 0, cost_grid = 0, bs_grid = 0;
     int schur_stride = 296;
-    // reduced camera system (tile-sparse level-scheduled LDL' by default; NLLS_B200_REDUCED=dense selects dense storage + cuSOLVER)
-    int s_tiled = 1;
+    // reduced camera system: tile-sparse level-scheduled LDL' (the only storage; a dense reduced system is the same code with every tile present)
+    const int s_tiled = 1;
     int NT = 0;
     int64_t ntiles_alloc = 0;
     int red_levels = 0;
@@ -177,6 +171,7 @@ struct nlls_ctx {
     uint64_t starttime = 0, stoptime = 0, t_init = 0, t_cost = 0, t_grad = 0, t_solver = 0;
     bool lm_active = false;
     bool have_best = false;
+    int lm_phase = 0;   // 0: nlls_lm_iterate is next, 1: nlls_lm_advance is next
 };
 
 #define CK(call)                                                                                              \
@@ -184,14 +179,6 @@ struct nlls_ctx {
         cudaError_t e__ = (call);                                                                             \
         if (e__ != cudaSuccess) {                                                                             \
             ctx->err = std::string(#call) + ": " + cudaGetErrorString(e__);                                   \
-            return NLLS_ERR_CUDA;                                                                             \
-        }                                                                                                     \
-    } while (0)
-#define CKS(call)                                                                                             \
-    do {                                                                                                      \
-        cusolverStatus_t s__ = (call);                                                                        \
-        if (s__ != CUSOLVER_STATUS_SUCCESS) {                                                                 \
-            ctx->err = std::string(#call) + ": cusolver status " + std::to_string((int)s__);                  \
             return NLLS_ERR_CUDA;                                                                             \
         }                                                                                                     \
     } while (0)
@@ -312,6 +299,17 @@ int allreduce(nlls_ctx* ctx, double* buf, size_t count, int op) {
     return NLLS_OK;
 }
 
+// max over ranks of n (<= 4) host doubles (termination inputs that are not replicated)
+int exchange_max(nlls_ctx* ctx, double* v, int n) {
+    if (ctx->nranks <= 1) return NLLS_OK;
+    CK(cudaMemcpyAsync(ctx->d_scal + SC_EXCH, v, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->st));
+    CKN(g_nccl.AllReduce(ctx->d_scal + SC_EXCH, ctx->d_scal + SC_EXCH, (size_t)n, ncclFloat64, ncclMax, ctx->comm, ctx->st));
+    CK(cudaMemcpyAsync(ctx->h_scal + SC_EXCH, ctx->d_scal + SC_EXCH, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    for (int i = 0; i < n; ++i) v[i] = ctx->h_scal[SC_EXCH + i];
+    return NLLS_OK;
+}
+
 template <class R>
 int launch_linearize(nlls_ctx* ctx, bool do_point = true, bool do_cam = true) {
     DevProblem p = devproblem(ctx);
@@ -365,19 +363,11 @@ int launch_schur(nlls_ctx* ctx, double lambda) {
     constexpr int DC = R::DC;
     DevProblem p = devproblem(ctx);
     const int64_t n = ctx->nred;
-    size_t scount;
-    if (ctx->s_tiled) {
-        scount = (size_t)ctx->ntiles_alloc * ST2;
-        CK(cudaMemsetAsync(ctx->d_S, 0, sizeof(double) * scount, ctx->st));
-        red_init_kernel<DC><<<ctx->NT, 256, 0, ctx->st>>>(ctx->d_S, ctx->d_diag_tile_nat, ctx->d_H, ctx->d_g, ctx->d_rhs, (int)ctx->nA, lambda,
-                                                            ctx->rank == 0 ? 1 : 0);
-        ctx->launches++;
-    } else {
-        scount = (size_t)n * n;
-        CK(cudaMemsetAsync(ctx->d_S, 0, sizeof(double) * scount, ctx->st));
-        const long long tot = (long long)ctx->nA * DC * DC + n;
-        schur_init_kernel<DC><<<(unsigned)((tot + 255) / 256), 256, 0, ctx->st>>>(p, ctx->d_S, ctx->d_rhs, lambda, ctx->rank == 0 ? 1 : 0); ctx->launches++;
-    }
+    const size_t scount = (size_t)ctx->ntiles_alloc * ST2;
+    CK(cudaMemsetAsync(ctx->d_S, 0, sizeof(double) * scount, ctx->st));
+    red_init_kernel<DC><<<ctx->NT, 256, 0, ctx->st>>>(ctx->d_S, ctx->d_diag_tile_nat, ctx->d_H, ctx->d_g, ctx->d_rhs, (int)ctx->nA, lambda,
+                                                        ctx->rank == 0 ? 1 : 0);
+    ctx->launches++;
     if (ctx->schur_v4 && ctx->nsuper > 0) {
         SchurPlan4 sp;
         sp.cta_item = ctx->d_cta_item; sp.items = ctx->d_items; sp.units = ctx->d_units; sp.blob = ctx->d_blob; sp.wtab = ctx->d_wtab;
@@ -397,15 +387,14 @@ int launch_schur(nlls_ctx* ctx, double lambda) {
     if (ctx->nranks > 1) {
         CKN(g_nccl.GroupStart());
         CKN(g_nccl.AllReduce(ctx->d_S, ctx->d_S, scount, ncclFloat64, ncclSum, ctx->comm, ctx->st));
-        CKN(g_nccl.AllReduce(ctx->d_rhs, ctx->d_rhs, (size_t)(ctx->s_tiled ? (int64_t)ctx->NT * ST : n), ncclFloat64, ncclSum, ctx->comm, ctx->st));
+        CKN(g_nccl.AllReduce(ctx->d_rhs, ctx->d_rhs, (size_t)((int64_t)ctx->NT * ST), ncclFloat64, ncclSum, ctx->comm, ctx->st));
         CKN(g_nccl.GroupEnd());
     }
     return NLLS_OK;
 }
 
-int launch_reduced_solve(nlls_ctx* ctx, bool lu) {
-    const int n = (int)ctx->nred;
-    if (ctx->s_tiled) {
+int launch_reduced_solve(nlls_ctx* ctx) {
+    {
         const RedSolveLists t = redlists(ctx);
         const int nx = ctx->NT * ST;
         // ~40 short dependent launches with constant arguments: captured once into a CUDA graph and replayed (the launch gaps of a
@@ -449,16 +438,6 @@ int launch_reduced_solve(nlls_ctx* ctx, bool lu) {
         if (ctx->nranks > 1) CKN(g_nccl.Broadcast(ctx->d_rhs, ctx->d_rhs, (size_t)nx, ncclFloat64, 0, ctx->comm, ctx->st));
         return NLLS_OK;
     }
-    if (!lu) {
-        CKS(cusolverDnDpotrf(ctx->cusolver, CUBLAS_FILL_MODE_LOWER, n, ctx->d_S, n, ctx->d_work, ctx->lwork, ctx->d_info));
-        // potrs on a failed factorisation yields garbage; the host checks info and redoes the try with LU
-        CKS(cusolverDnDpotrs(ctx->cusolver, CUBLAS_FILL_MODE_LOWER, n, 1, ctx->d_S, n, ctx->d_rhs, n, ctx->d_info + 1));
-    } else {
-        symmetrize_kernel<<<(unsigned)(((long long)n * n + 255) / 256), 256, 0, ctx->st>>>(ctx->d_S, n); ctx->launches++;
-        CKS(cusolverDnDgetrf(ctx->cusolver, n, n, ctx->d_S, n, ctx->d_work, ctx->d_ipiv, ctx->d_info));
-        CKS(cusolverDnDgetrs(ctx->cusolver, CUBLAS_OP_N, n, 1, ctx->d_S, n, ctx->d_ipiv, ctx->d_rhs, n, ctx->d_info + 1));
-    }
-    return NLLS_OK;
 }
 
 template <class R>
@@ -550,7 +529,6 @@ int adapt_solve_update(nlls_ctx* ctx, double lambda) {
 
 int fetch_scalars(nlls_ctx* ctx) {
     CK(cudaMemcpyAsync(ctx->h_scal, ctx->d_scal, sizeof(double) * SC_COUNT, cudaMemcpyDeviceToHost, ctx->st));
-    CK(cudaMemcpyAsync(ctx->h_scal + SC_COUNT, ctx->d_info, sizeof(int) * 2, cudaMemcpyDeviceToHost, ctx->st));
     CK(cudaStreamSynchronize(ctx->st));
     return NLLS_OK;
 }
@@ -578,26 +556,35 @@ int do_linearize(nlls_ctx* ctx, double* cost) {
 }
 
 // one LM try without the host sync: damp + Schur + reduced solve + back-substitution/update + cost(varnext)
-int enqueue_try(nlls_ctx* ctx, double lambda, bool lu) {
+int enqueue_try(nlls_ctx* ctx, double lambda) {
     if (ctx->adaptive) {
         TRY(adapt_solve_update(ctx, lambda));
-        return adapt_cost(ctx, ctx->nxt, SC_COST_TRY);
+        CK(cudaEventRecord(ctx->ev_c0, ctx->st));
+        TRY(adapt_cost(ctx, ctx->nxt, SC_COST_TRY));
+        CK(cudaEventRecord(ctx->ev_c1, ctx->st));
+        return NLLS_OK;
     }
     TRY(DISPATCH(ctx, launch_schur, ctx, lambda));
-    TRY(launch_reduced_solve(ctx, lu));
+    TRY(launch_reduced_solve(ctx));
     TRY(DISPATCH(ctx, launch_update, ctx));
+    CK(cudaEventRecord(ctx->ev_c0, ctx->st));
     TRY(DISPATCH(ctx, launch_cost, ctx, ctx->nxt, SC_COST_TRY));
+    CK(cudaEventRecord(ctx->ev_c1, ctx->st));
     return NLLS_OK;
 }
 
+// One LM try.  The fused try is booked like the reference's timers (src/iterators.jl:152,157): the cost evaluation (CUDA events around
+// its kernels) as timecost, everything else of the try (damp + solve + update, host wall clock minus the cost) as timesolver.
 int do_try(nlls_ctx* ctx, double lambda) {
-    TRY(enqueue_try(ctx, lambda, false));
+    const uint64_t ts = now_ns();
+    TRY(enqueue_try(ctx, lambda));
     TRY(fetch_scalars(ctx));
-    const int* info = reinterpret_cast<const int*>(ctx->h_scal + SC_COUNT);
-    if (!ctx->adaptive && !ctx->s_tiled && info[0] != 0) {  // dense path, not positive definite: the reference falls back to QR (src/linearsolver.jl:20-26); we use LU
-        TRY(enqueue_try(ctx, lambda, true));
-        TRY(fetch_scalars(ctx));
-    }
+    const uint64_t dt = now_ns() - ts;
+    float cms = 0.f;
+    CK(cudaEventElapsedTime(&cms, ctx->ev_c0, ctx->ev_c1));
+    const uint64_t tc = std::min<uint64_t>(dt, (uint64_t)(cms * 1e6));
+    ctx->t_cost += tc;
+    ctx->t_solver += dt - tc;
     return NLLS_OK;
 }
 
@@ -696,22 +683,20 @@ int nlls_create(nlls_ctx** out, int device) {
     cudaEventCreate(&ctx->ev_t1);
     cudaEventCreate(&ctx->ev_b0);
     cudaEventCreate(&ctx->ev_b1);
+    cudaEventCreate(&ctx->ev_c0);
+    cudaEventCreate(&ctx->ev_c1);
     cudaMalloc((void**)&ctx->d_scal, sizeof(double) * SC_COUNT);
     cudaMemset(ctx->d_scal, 0, sizeof(double) * SC_COUNT);
     cudaMallocHost((void**)&ctx->h_scal, sizeof(double) * (SC_COUNT + 2));
-    cudaMalloc((void**)&ctx->d_info, sizeof(int) * 2);
-    cudaMemset(ctx->d_info, 0, sizeof(int) * 2);
-    if (cusolverDnCreate(&ctx->cusolver) != CUSOLVER_STATUS_SUCCESS) { delete ctx; return NLLS_ERR_CUDA; }
-    cusolverDnSetStream(ctx->cusolver, ctx->st);
+    if (ctx->h_scal) std::memset(ctx->h_scal, 0, sizeof(double) * (SC_COUNT + 2));
     const char* e = getenv("NLLS_B200_TMA");
     ctx->use_tma = (e && e[0] == '0') ? 0 : 1;
     if (const char* g = getenv("NLLS_B200_SCHUR_STRIDE")) ctx->schur_stride = std::max(1, atoi(g));
-    if (const char* g = getenv("NLLS_B200_REDUCED")) ctx->s_tiled = (std::string(g) == "dense") ? 0 : 1;
     if (const char* g = getenv("NLLS_B200_GRAPH")) ctx->use_graph = atoi(g) != 0;
     if (const char* g = getenv("NLLS_B200_SCHUR")) ctx->schur_v4 = (std::string(g) == "v2") ? 0 : ((std::string(g) == "v4") ? 2 : 1);
     if (const char* g = getenv("NLLS_B200_TILE")) { const int v = atoi(g); ctx->tile_env = (v == 64 || v == 128) ? v : 256; }
     { int v = 0; if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && v > 0) ctx->nsm = v; }
-    if (cudaGetLastError() != cudaSuccess) { delete ctx; return NLLS_ERR_CUDA; }
+    if (cudaGetLastError() != cudaSuccess || !ctx->st || !ctx->st2 || !ctx->d_scal || !ctx->h_scal) { nlls_destroy(ctx); return NLLS_ERR_CUDA; }
     *out = ctx;
     return NLLS_OK;
 }
@@ -723,7 +708,7 @@ int nlls_destroy(nlls_ctx* ctx) {
     void* ptrs[] = {ctx->d_obs_cam, ctx->d_obs_pt, ctx->d_obs_start, ctx->d_tile_pt, ctx->d_obs_z, ctx->d_cm_pt, ctx->d_item_cam, ctx->d_item_beg,
                     ctx->d_item_end, ctx->d_cam_item_start, ctx->d_cm_z, ctx->d_A[0], ctx->d_A[1], ctx->d_A[2], ctx->d_B[0], ctx->d_B[1], ctx->d_B[2],
                     ctx->d_H, ctx->d_g, ctx->d_x, ctx->d_Ainv, ctx->d_S, ctx->d_rhs, ctx->d_cost_part, ctx->d_step_part, ctx->d_cam_part, ctx->d_scal,
-                    ctx->d_flush, ctx->d_work, ctx->d_info, ctx->d_ipiv, ctx->d_tile_id, ctx->d_pos, ctx->d_diag_tile, ctx->d_diag_tile_nat,
+                    ctx->d_flush, ctx->d_tile_id, ctx->d_pos, ctx->d_diag_tile, ctx->d_diag_tile_nat,
                     ctx->d_lvl_cols, ctx->d_red_tasks, ctx->d_red_upds, ctx->d_colptr,
                     ctx->d_col_tile, ctx->d_col_row, ctx->d_Linv, ctx->d_xp, ctx->d_stile_pt, ctx->d_chunk_off, ctx->d_chunks, ctx->d_ents, ctx->d_tiles, ctx->d_camstat_part,
                     ctx->d_ad_data, ctx->d_ad_chunks, ctx->d_ad_moff, ctx->d_ad_part, ctx->d_ent_off, ctx->d_cta_item, ctx->d_items, ctx->d_units, ctx->d_wtab, ctx->d_blob};
@@ -731,9 +716,9 @@ int nlls_destroy(nlls_ctx* ctx) {
     if (ctx->red_graph_exec) cudaGraphExecDestroy(ctx->red_graph_exec);
     if (ctx->h_scal) cudaFreeHost(ctx->h_scal);
     if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
-    if (ctx->cusolver) cusolverDnDestroy(ctx->cusolver);
-    cudaEventDestroy(ctx->ev_fork); cudaEventDestroy(ctx->ev_join); cudaEventDestroy(ctx->ev_t0); cudaEventDestroy(ctx->ev_t1); cudaEventDestroy(ctx->ev_b0); cudaEventDestroy(ctx->ev_b1);
-    cudaStreamDestroy(ctx->st); cudaStreamDestroy(ctx->st2);
+    for (cudaEvent_t e : {ctx->ev_fork, ctx->ev_join, ctx->ev_t0, ctx->ev_t1, ctx->ev_b0, ctx->ev_b1, ctx->ev_c0, ctx->ev_c1}) if (e) cudaEventDestroy(e);
+    if (ctx->st) cudaStreamDestroy(ctx->st);
+    if (ctx->st2) cudaStreamDestroy(ctx->st2);
     delete ctx;
     return NLLS_OK;
 }
@@ -1076,8 +1061,6 @@ int nlls_prepare(nlls_ctx* ctx) {
             for (int I : rows[(size_t)J2]) { col_tile.push_back(tile_id[(size_t)I * NT + J2]); col_row.push_back(I); }
             colptr[(size_t)J2 + 1] = (int)col_tile.size();
         }
-    } else {
-        if (ctx->nred > 46000) FAIL(NLLS_ERR_UNSUPPORTED, "reduced camera system larger than 46000 (dense cuSOLVER path)");
     }
 
     // ---- Schur v2 plan: larger point tiles + per-tile contribution lists sorted by target block
@@ -1395,21 +1378,11 @@ int nlls_prepare(nlls_ctx* ctx) {
         CK(cudaMemsetAsync(ctx->d_Linv, 0, sizeof(double) * (size_t)ctx->NT * ST2, ctx->st));
         TRY(upload(ctx, &ctx->d_lvl_cols, lvl_cols_flat));
         TRY(upload(ctx, &ctx->d_colptr, colptr)); TRY(upload(ctx, &ctx->d_col_tile, col_tile)); TRY(upload(ctx, &ctx->d_col_row, col_row));
-    } else {
-        TRY(dalloc(ctx, &ctx->d_S, (size_t)ctx->nred * ctx->nred)); TRY(dalloc(ctx, &ctx->d_rhs, (size_t)ctx->nred));
     }
     TRY(dalloc(ctx, &ctx->d_cost_part, (size_t)ctx->ntiles)); TRY(dalloc(ctx, &ctx->d_step_part, (size_t)4 * ctx->ntiles));
     const int NU = DC * (DC + 1) / 2 + DC;
     TRY(dalloc(ctx, &ctx->d_cam_part, (size_t)ctx->nitems * NU));
     TRY(dalloc(ctx, &ctx->d_camstat_part, (size_t)4 * ((nA + 127) / 128)));
-    if (!ctx->s_tiled) {
-        int lw1 = 0, lw2 = 0;
-        CKS(cusolverDnDpotrf_bufferSize(ctx->cusolver, CUBLAS_FILL_MODE_LOWER, (int)ctx->nred, ctx->d_S, (int)ctx->nred, &lw1));
-        CKS(cusolverDnDgetrf_bufferSize(ctx->cusolver, (int)ctx->nred, (int)ctx->nred, ctx->d_S, (int)ctx->nred, &lw2));
-        ctx->lwork = std::max(lw1, lw2);
-        TRY(dalloc(ctx, &ctx->d_work, (size_t)ctx->lwork));
-        TRY(dalloc(ctx, &ctx->d_ipiv, (size_t)ctx->nred));
-    }
     TRY(DISPATCH(ctx, set_smem_attrs, ctx));
     CK(cudaStreamSynchronize(ctx->st));
     ctx->prepared = true;
@@ -1441,13 +1414,7 @@ int nlls_solve(nlls_ctx* ctx, double lambda) {
     CK(cudaSetDevice(ctx->device));
     if (ctx->adaptive) { TRY(adapt_solve_update(ctx, lambda)); return fetch_scalars(ctx); }
     TRY(DISPATCH(ctx, launch_schur, ctx, lambda));
-    TRY(launch_reduced_solve(ctx, false));
-    TRY(fetch_scalars(ctx));
-    const int* info = reinterpret_cast<const int*>(ctx->h_scal + SC_COUNT);
-    if (!ctx->s_tiled && info[0] != 0) {
-        TRY(DISPATCH(ctx, launch_schur, ctx, lambda));
-        TRY(launch_reduced_solve(ctx, true));
-    }
+    TRY(launch_reduced_solve(ctx));
     // back-substitution also writes x and varnext; nlls_update is then a no-op kept for API symmetry
     TRY(DISPATCH(ctx, launch_update, ctx));
     TRY(fetch_scalars(ctx));
@@ -1474,7 +1441,7 @@ int nlls_lm_begin(nlls_ctx* ctx, const nlls_options* opts) {
     ctx->fails = 0; ctx->iternum = 0; ctx->converged = 0;
     ctx->costcomputations = ctx->gradientcomputations = ctx->linearsolvers = 0;
     ctx->t_init = ctx->t_cost = ctx->t_grad = ctx->t_solver = 0;
-    ctx->have_best = false;
+    ctx->have_best = false; ctx->lm_phase = 0;
     ctx->t_init += now_ns() - t0;                                // :116
     const uint64_t tg = now_ns();
     double c = 0.0;
@@ -1488,15 +1455,18 @@ int nlls_lm_begin(nlls_ctx* ctx, const nlls_options* opts) {
 
 int nlls_lm_iterate(nlls_ctx* ctx, nlls_iterinfo* info) {
     if (!ctx || !ctx->lm_active) return NLLS_ERR_INVALID;
+    // call order is begin -> (iterate -> advance)* -> end: after a non-zero termination word the linear system belongs to the
+    // previous point (advance skipped the re-linearisation, src/optimize.jl:165-171), so another iteration would be silently wrong
+    if (ctx->converged != 0) FAIL(NLLS_ERR_INVALID, "nlls_lm_iterate after termination (converged != 0): call nlls_lm_end");
+    if (ctx->lm_phase != 0) FAIL(NLLS_ERR_INVALID, "nlls_lm_iterate called twice without nlls_lm_advance");
+    ctx->lm_phase = 1;
     CK(cudaSetDevice(ctx->device));
     const nlls_options& o = ctx->opts;
     ctx->iternum += 1;                                           // src/optimize.jl:124
     if (o.iterator == NLLS_ITER_NEWTON) {
         // ---- iterate!(::NewtonData)                               src/iterators.jl:17-27: undamped solve, update, cost — no
         // acceptance test; the outer loop's best / fails bookkeeping (nlls_lm_advance) handles a cost increase
-        const uint64_t ts = now_ns();
         TRY(do_try(ctx, 0.0));
-        ctx->t_solver += now_ns() - ts;
         ctx->linearsolvers += 1; ctx->costcomputations += 1;
         const double* s = ctx->h_scal;
         const double cost_ = s[SC_COST_TRY];
@@ -1516,9 +1486,7 @@ int nlls_lm_iterate(nlls_ctx* ctx, nlls_iterinfo* info) {
     double mu = 2.0, cost_ = 0.0, maxstep = 0.0, sq = 0.0;
     int64_t ntries = 0, accepted = 0;
     while (true) {
-        const uint64_t ts = now_ns();
-        TRY(do_try(ctx, ctx->lambda));                           // :149-157 (damp, solve, negate, update, cost)
-        ctx->t_solver += now_ns() - ts;                          // the fused try (solve + update + cost) is booked as solver time
+        TRY(do_try(ctx, ctx->lambda));                           // :149-157 (damp, solve, negate, update, cost); books timesolver / timecost
         ctx->linearsolvers += 1; ctx->costcomputations += 1; ntries += 1;
         const double* s = ctx->h_scal;
         cost_ = s[SC_COST_TRY];
@@ -1543,6 +1511,8 @@ int nlls_lm_iterate(nlls_ctx* ctx, nlls_iterinfo* info) {
 
 int nlls_lm_advance(nlls_ctx* ctx, double cost, int64_t terminate, int64_t* converged) {
     if (!ctx || !ctx->lm_active) return NLLS_ERR_INVALID;
+    if (ctx->lm_phase != 1) FAIL(NLLS_ERR_INVALID, "nlls_lm_advance without a preceding nlls_lm_iterate");
+    ctx->lm_phase = 0;
     CK(cudaSetDevice(ctx->device));
     const nlls_options& o = ctx->opts;
     const double maxstep = ctx->maxstep;
@@ -1559,6 +1529,7 @@ int nlls_lm_advance(nlls_ctx* ctx, double cost, int64_t terminate, int64_t* conv
         }
     }
     std::swap(ctx->cur, ctx->nxt);                               // updatefromnext!  :147,207-209
+    for (auto& kv : ctx->vars) kv.second.stale = true;           // the device now holds newer variables than the host mirror
     ctx->cost = cost;
     int64_t conv = 0;                                            // :150-161
     conv |= (int64_t)std::isinf(cost) << 0;
@@ -1570,7 +1541,15 @@ int nlls_lm_advance(nlls_ctx* ctx, double cost, int64_t terminate, int64_t* conv
     conv |= (int64_t)(maxstep < o.dstep) << 6;
     conv |= (int64_t)(ctx->fails > o.maxfails) << 7;
     conv |= (int64_t)(ctx->iternum >= o.maxiters) << 8;
-    conv |= (int64_t)(now_ns() > ctx->stoptime) << 9;
+    int64_t timeup = now_ns() > ctx->stoptime;
+    if (ctx->nranks > 1) {
+        // every other input of the termination word is replicated; the clock and the callback's flag are per rank.  The decision
+        // must be the same on all ranks (a rank that leaves alone strands the others in the next all-reduce): take the maximum.
+        double v[2] = {(double)timeup, (double)terminate};
+        TRY(exchange_max(ctx, v, 2));
+        timeup = v[0] != 0.0; terminate = (int64_t)v[1];
+    }
+    conv |= timeup << 9;
     conv |= terminate << 16;
     ctx->converged = conv;
     if (converged) *converged = conv;
@@ -1587,6 +1566,7 @@ int nlls_lm_end(nlls_ctx* ctx, nlls_result* r) {
     if (!ctx || !ctx->lm_active) return NLLS_ERR_INVALID;
     CK(cudaSetDevice(ctx->device));
     if (!(ctx->bestcost >= ctx->cost) && ctx->have_best) std::swap(ctx->cur, ctx->bst);   // src/optimize.jl:173-176
+    for (auto& kv : ctx->vars) kv.second.stale = true;
     CK(cudaStreamSynchronize(ctx->st));
     ctx->lm_active = false;
     if (r) {
@@ -1802,7 +1782,7 @@ int nlls_time_kernels(nlls_ctx* ctx, int which, int reps, int flush_l2, double* 
         if (ctx->adaptive) {
             if (which == NLLS_TIME_LINEARIZE) TRY(adapt_linearize(ctx));
             else if (which == NLLS_TIME_COST) TRY(adapt_cost(ctx, ctx->cur, SC_COST_TRY));
-            else if (which == NLLS_TIME_TRY) TRY(enqueue_try(ctx, lambda, false));
+            else if (which == NLLS_TIME_TRY) TRY(enqueue_try(ctx, lambda));
             else return NLLS_ERR_INVALID;
         } else
         switch (which) {
@@ -1811,9 +1791,9 @@ int nlls_time_kernels(nlls_ctx* ctx, int which, int reps, int flush_l2, double* 
             case NLLS_TIME_LIN_CAM: TRY(DISPATCH(ctx, launch_linearize, ctx, false, true)); break;
             case NLLS_TIME_COST: TRY(DISPATCH(ctx, launch_cost, ctx, ctx->cur, SC_COST_TRY)); break;
             case NLLS_TIME_SCHUR: TRY(DISPATCH(ctx, launch_schur, ctx, lambda)); break;
-            case NLLS_TIME_SOLVE_REDUCED: TRY(DISPATCH(ctx, launch_schur, ctx, lambda)); CK(cudaEventRecord(ctx->ev_t0, ctx->st)); TRY(launch_reduced_solve(ctx, false)); break;
+            case NLLS_TIME_SOLVE_REDUCED: TRY(DISPATCH(ctx, launch_schur, ctx, lambda)); CK(cudaEventRecord(ctx->ev_t0, ctx->st)); TRY(launch_reduced_solve(ctx)); break;
             case NLLS_TIME_BACKSUB: TRY(DISPATCH(ctx, launch_update, ctx)); break;
-            case NLLS_TIME_TRY: TRY(enqueue_try(ctx, lambda, false)); break;
+            case NLLS_TIME_TRY: TRY(enqueue_try(ctx, lambda)); break;
             case NLLS_TIME_MEMSET_H: CK(cudaMemsetAsync(ctx->d_H + (size_t)ctx->DC * ctx->DC * ctx->nA, 0, sizeof(double) * (size_t)(ctx->hlen - (int64_t)ctx->DC * ctx->DC * ctx->nA), ctx->st)); break;
             default: return NLLS_ERR_INVALID;
         }

@@ -763,6 +763,7 @@ void Problem::makesymmvls() {                                                   
         std::vector<int64_t> deg(nb, 0), order(nb);
         for (size_t r = 0; r < nb; ++r) for (int64_t p = colptr[r] - 1; p < colptr[r + 1] - 1; ++p) { deg[r]++; if ((size_t)(rowval[p] - 1) != r) deg[rowval[p] - 1]++; }
         std::iota(order.begin(), order.end(), 0);
+        if (elimination_order == 1) std::reverse(order.begin(), order.end());
         std::stable_sort(order.begin(), order.end(), [&](int64_t a, int64_t c) { return std::min<int64_t>(deg[a], 64) < std::min<int64_t>(deg[c], 64); });
         std::vector<int64_t> perm; perm.reserve((size_t)dof);
         for (int64_t blk : order) for (int k = 0; k < bs[blk]; ++k) perm.push_back(boffsets[blk] - 1 + k);

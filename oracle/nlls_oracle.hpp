@@ -155,6 +155,9 @@ struct Problem {
     std::vector<double> hessval;
     LDLSymbolic ldl;
     bool lsready = false;
+    // 0: ascending block degree (default, see makesymmvls); 1: the same but ties taken in DESCENDING variable order — a second
+    // exact elimination order of the same system, used only to measure how far two exact solvers drift apart (tests, R18)
+    int elimination_order = 0;
     void makesymmvls();
     void zero();
     double costgradhess();                                   //                         src/cost.jl:29-54

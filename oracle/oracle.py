@@ -53,6 +53,7 @@ def lib():
         L.orc_resjac.argtypes = [C.c_int, _dp, C.c_int, _i32p, _i32p, _dp, _i32p, _i32p, _dp, _dp]
         L.orc_problem_new.restype = C.c_void_p
         L.orc_problem_free.argtypes = [C.c_void_p]
+        L.orc_set_elimination_order.argtypes = [C.c_void_p, C.c_int]
         L.orc_add_variables.restype = C.c_int64
         L.orc_add_variables.argtypes = [C.c_void_p, C.c_int, C.c_int64, _dp, C.c_int]
         L.orc_add_costs.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_int, _ip, C.c_int, _dp, C.c_int, C.c_double, C.c_int, C.c_double]
@@ -321,6 +322,10 @@ class Problem:
         if getattr(self, "h", None):
             lib().orc_problem_free(self.h)
             self.h = None
+
+    def set_elimination_order(self, mode):
+        """0: default order of the sparse LDL'; 1: a second exact order (ties reversed) — used to measure solver-vs-solver drift."""
+        lib().orc_set_elimination_order(self.h, mode)
 
     def add_variables(self, vtype, values):
         """values: (n, nstore) array. Returns the 1-based index of the first variable added."""

@@ -59,6 +59,7 @@ void orc_resjac(int type, const double* data, int ndeps, const int* vtypes, cons
 // ---- problem
 void* orc_problem_new() { return new Problem(); }
 void orc_problem_free(void* p) { delete (Problem*)p; }
+void orc_set_elimination_order(void* p, int mode) { Problem* pr = (Problem*)p; pr->elimination_order = mode; pr->lsready = false; }
 int64_t orc_add_variables(void* p, int type, int64_t n, const double* v, int nstore) {
     Problem* pr = (Problem*)p;
     int64_t first = 0;

@@ -325,35 +325,39 @@ def test_lm_trajectory_c1(pkg, orc):
 
 @pytest.mark.parametrize("kname", ["none", "huber", "huber2o"])
 def test_lm_trajectory_ladybug_shape(pkg, orc, kname):
+    # R18: same accept/reject sequence, per-iteration cost <= 1e-10, final cost <= 1e-8 — wherever those gates are well posed.
+    # The affine BA problem has a 12-DoF gauge freedom (H is singular) and the reference never clamps lambda: with plain Huber
+    # lambda falls to 1e-26, cond(H + lambda I) passes 1e16 and ANY two exact solvers drift apart along the gauge directions.
+    # That is measured, not assumed: the oracle is run a second time with a different elimination order of its sparse LDL'
+    # (scripts/oracle_order_drift.py, profiles/r2_oracle_order_drift.json: none 5e-15, huber2o 1.5e-13, huber 9.4e-8 in the
+    # final cost and a different inner-try count at iteration 25).  The CUDA path must agree with the oracle at least as well as
+    # the oracle agrees with itself: per iteration while the two oracle runs agree to 1e-10 with equal try counts, and in the
+    # final cost to max(1e-8, 10 x the oracle's own drift).
     ok, rid, kp = KERNELS[kname]
     p = _bal(pkg, *pkg.synthetic.SHAPES["ladybug"], noise=0.01, outlier_frac=0.05 if kname != "none" else 0.0)
     res, tr, res_ref, tr_ref, ctx, P = _compare_trajectories(pkg, orc, p, ok, rid, kp, maxiters=30)
+    P2 = oracle_problem(orc, p, kernel=ok)
+    P2.set_elimination_order(1)
+    res_ref2, tr_ref2 = P2.optimize(orc.Options(maxiters=30))
     assert res.startcost == pytest.approx(res_ref.startcost, rel=TOL_COST)
-    n = min(len(tr), len(tr_ref))
+    n = min(len(tr), len(tr_ref), len(tr_ref2))
     assert n >= 3
     compared = 0
-    lam0 = tr_ref[0].lambda_ * 10 if tr_ref[0].ntries == 1 else None   # lambda used by the first try (it shrinks x0.1 on a good step)
-    lam_used = lam0
     for i in range(n):
         c, nt, lam = tr[i]
-        r = tr_ref[i]
-        # once successive costs agree to ~1e-12 the accept/reject decisions are decided by rounding noise
-        if i > 0 and abs(tr_ref[i - 1].cost - r.cost) <= 1e-11 * r.cost:
-            break
-        # The affine BA problem has a 12-DoF gauge freedom, so H is singular and cond(H + lambda I) ~ max|H_ii| / lambda.
-        # The reference never clamps lambda (it reaches 1e-31 with plain Huber); once cond exceeds ~1e13 any two exact
-        # solvers (the reference's AMD-ordered LDL', the oracle's LDL', our Schur + Cholesky) drift apart along the gauge
-        # directions by more than the tolerance.  Compare strictly while the damped system is well conditioned.
-        if lam0 is not None and lam_used < 1e-7 * lam0:
-            break
-        assert c == pytest.approx(r.cost, rel=TOL_COST), (i, c, r.cost)
+        r, r2 = tr_ref[i], tr_ref2[i]
+        if r.ntries != r2.ntries or abs(r.cost - r2.cost) > TOL_COST * abs(r.cost):
+            break                                    # the oracle no longer agrees with itself: the gate is ill posed from here on
+        drift_i = abs(r.cost - r2.cost) / abs(r.cost)
+        assert c == pytest.approx(r.cost, rel=max(TOL_COST, 10 * drift_i)), (i, c, r.cost, drift_i)   # 1e-10 unless the oracle's own drift is within 10x of it
         assert nt == r.ntries, (i, nt, r.ntries)
         assert lam == pytest.approx(r.lambda_, rel=1e-6)
-        lam_used = r.lambda_
         compared += 1
-    assert compared >= 6
-    # final cost: 1e-8 where lambda stays in a well-conditioned range; the gauge drift above bounds the plain-Huber run
-    final_tol = TOL_FINAL if tr_ref[-1].lambda_ > 1e-7 * (lam0 or 1.0) or kname == "none" else 1e-6
+    assert compared >= (12 if kname == "huber" else n), (compared, n)   # huber: the oracle self-agrees to 1e-10 for 12 iterations
+    self_drift = abs(res_ref.bestcost - res_ref2.bestcost) / abs(res_ref.bestcost)
+    final_tol = max(TOL_FINAL, 10 * self_drift)
+    if kname != "huber":
+        assert final_tol == TOL_FINAL                # the 1e-8 gate stands wherever the oracle itself meets it
     assert res.bestcost == pytest.approx(res_ref.bestcost, rel=final_tol)
     assert ctx.cost(0) == res.bestcost
     ctx.close()

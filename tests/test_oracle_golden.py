@@ -248,3 +248,29 @@ def test_adaptivecost_lm(orc):
     assert np.allclose(params, [1.0, 10.0, 0.8], rtol=0.1), params            # :44
     assert v[3] == pytest.approx(-1.0, rel=0.1) and v[4] == pytest.approx(1.0, rel=0.1)
     assert P.cost() == res.bestcost
+
+
+def test_oracle_self_drift_under_two_elimination_orders(pkg, orc):
+    """R18 well-posedness, measured: two exact solvers of the same damped system (the oracle's sparse LDL' under two elimination
+    orders) stay together to ~1e-13 with Huber2o (lambda stays O(1)) but drift apart once plain Huber lets lambda fall below
+    ~1e-13 * lambda0 (gauge freedom of the affine BA problem, no lambda clamp in the reference): by more than the north star's 1e-8
+    final-cost gate, with a different inner-try count.  tests/test_gpu_parity.py::test_lm_trajectory_ladybug_shape gates the CUDA
+    path at max(1e-8, 10 x this drift)."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("oracle_order_drift", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "scripts", "oracle_order_drift.py"))
+    od = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(od)
+    r0, t0 = od.run("huber2o", 0)
+    r1, t1 = od.run("huber2o", 1)
+    assert abs(r0.bestcost - r1.bestcost) <= 1e-10 * r0.bestcost
+    assert [a.ntries for a in t0] == [b.ntries for b in t1]
+    r0, t0 = od.run("huber", 0)
+    r1, t1 = od.run("huber", 1)
+    agree = 0
+    for a, b in zip(t0, t1):
+        if a.ntries != b.ntries or abs(a.cost - b.cost) > 1e-10 * a.cost:
+            break
+        agree += 1
+    assert 8 <= agree < len(t0)                                         # well posed for the first iterations only
+    assert abs(r0.bestcost - r1.bestcost) > 1e-8 * r0.bestcost          # the 1e-8 final-cost gate is ill posed for this configuration
