@@ -459,7 +459,7 @@ struct SchurPlan {
     const SchurChunk* chunks;     // per tile sorted by length (long first)
     const unsigned int* ents;     // (i_local << 16) | j_local
     int nstiles;
-    long long ld;                 // leading dimension of an S tile (ST) or of the dense S (n)
+    long long ld;                 // leading dimension of an S tile (ST)
 };
 
 template <int DC>
@@ -1079,3 +1079,5 @@ __global__ void __launch_bounds__(256) reduce_stats_kernel(const double* __restr
 }
 
 }  // namespace nlls
+
+#include "schur5.cuh"

@@ -152,6 +152,12 @@ struct nlls_ctx {
     cudaGraphExec_t red_graph_exec = nullptr;   // the reduced solve's launch sequence (tile-sparse path)
     int use_graph = 1, red_graph_launches = 0;
     int schur_v4 = 1, nsuper = 0;   // nsuper: CTAs of the v4 kernel (0: v2 path)
+    // Schur v5 plan (window-aligned register accumulation, schur5.cuh); 1: automatic, 2: forced, 0: off.  n5cta: CTAs (0: not in use)
+    int schur_v5 = 0, n5cta = 0, nout_pts = 0, s5_ncons = S5_CONSUMERS;   // (off by default while it is slower than v4 on the bench shape)
+    int* d5_cta_item = nullptr;
+    Schur5Item* d5_items = nullptr;
+    unsigned int* d5_blob = nullptr;
+    int* d_out_pts = nullptr;       // points outside the v5 window plan (schur_outlier_kernel)
     int* d_cta_item = nullptr;
     SchurItem* d_items = nullptr;
     SchurUnit* d_units = nullptr;
@@ -286,6 +292,7 @@ int set_smem_attrs(nlls_ctx* ctx) {
     else TRY((set_tile_attrs<R, 256>(ctx)));
     CK(cudaFuncSetAttribute(schur2_kernel<R::DC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Schur2Smem<R::DC>::bytes));
     CK(cudaFuncSetAttribute(schur4_kernel<R::DC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Schur4Cfg<R::DC>::bytes));
+    CK(cudaFuncSetAttribute(schur5_kernel<R::DC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Schur5Smem<R::DC>::bytes));
     CK(cudaFuncSetAttribute(ldl_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DIAG_SMEM));
     CK(cudaFuncSetAttribute(ldl_off_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OFF_SMEM));
     CK(cudaFuncSetAttribute(ldl_upd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UPD_SMEM));
@@ -368,7 +375,35 @@ int launch_schur(nlls_ctx* ctx, double lambda) {
     red_init_kernel<DC><<<ctx->NT, 256, 0, ctx->st>>>(ctx->d_S, ctx->d_diag_tile_nat, ctx->d_H, ctx->d_g, ctx->d_rhs, (int)ctx->nA, lambda,
                                                         ctx->rank == 0 ? 1 : 0);
     ctx->launches++;
-    if (ctx->schur_v4 && ctx->nsuper > 0) {
+    if (ctx->n5cta > 0) {
+        Schur5Dev s5;
+        s5.cta_item = ctx->d5_cta_item; s5.items = ctx->d5_items; s5.blob = ctx->d5_blob; s5.dbg = nullptr; s5.ncons = ctx->s5_ncons;
+        static const bool s5dbg = getenv("NLLS_B200_S5DBG") != nullptr;
+        long long* d_dbg = nullptr;
+        if (s5dbg) { CK(cudaMalloc((void**)&d_dbg, sizeof(long long) * 64 * ctx->n5cta)); CK(cudaMemsetAsync(d_dbg, 0, sizeof(long long) * 64 * ctx->n5cta, ctx->st)); s5.dbg = d_dbg; }
+        schur5_kernel<DC><<<ctx->n5cta, S5_THREADS, Schur5Smem<DC>::bytes, ctx->st>>>(p, s5, ctx->d_S, ctx->d_rhs, ctx->d_Ainv, lambda);
+        ctx->launches++;
+        if (s5dbg) {   // development aid: where the warps of the Schur kernel spend their cycles
+            std::vector<long long> h((size_t)64 * ctx->n5cta);
+            CK(cudaStreamSynchronize(ctx->st));
+            CK(cudaMemcpy(h.data(), d_dbg, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost));
+            cudaFree(d_dbg);
+            double wsum[16] = {0}, tsum[16] = {0}, tmax = 0, idle = 0;
+            for (int c = 0; c < ctx->n5cta; ++c) for (int w = 0; w < 12; ++w) { wsum[w] += (double)h[((size_t)c * 16 + w) * 4]; tsum[w] += (double)h[((size_t)c * 16 + w) * 4 + 1]; tmax = std::max(tmax, (double)h[((size_t)c * 16 + w) * 4 + 1]); }
+            for (int c = 0; c < ctx->n5cta; ++c) idle += (double)h[((size_t)c * 16 + 11) * 4 + 2];
+            fprintf(stderr, "[nlls] schur5 cycles: longest warp %.0f; per consumer warp (mean over CTAs) total / waiting:", tmax);
+            for (int w = 0; w < 11; ++w) fprintf(stderr, " %d: %.0f/%.0f", w, tsum[w] / ctx->n5cta, wsum[w] / ctx->n5cta);
+            fprintf(stderr, "; producer total %.0f point phases %.0f idle polls %.0f\n", tsum[11] / ctx->n5cta, wsum[11] / ctx->n5cta, idle / ctx->n5cta);
+            // per CTA totals (consumer warp 0) to see the balance between CTAs
+            double cmin = 1e30, cmax = 0;
+            for (int c = 0; c < ctx->n5cta; ++c) { const double t = (double)h[((size_t)c * 16) * 4 + 1]; cmin = std::min(cmin, t); cmax = std::max(cmax, t); }
+            fprintf(stderr, "[nlls] schur5 CTA time (consumer 0): min %.0f max %.0f\n", cmin, cmax);
+        }
+        if (ctx->nout_pts > 0) {   // points outside the window plan (gaps in the camera list, very long tracks)
+            schur_outlier_kernel<DC><<<(ctx->nout_pts * 32 + 127) / 128, 128, 0, ctx->st>>>(p, ctx->d_out_pts, ctx->nout_pts, ctx->d_S, ctx->d_rhs, lambda);
+            ctx->launches++;
+        }
+    } else if (ctx->schur_v4 && ctx->nsuper > 0) {
         SchurPlan4 sp;
         sp.cta_item = ctx->d_cta_item; sp.items = ctx->d_items; sp.units = ctx->d_units; sp.blob = ctx->d_blob; sp.wtab = ctx->d_wtab;
         sp.ld = ctx->s_tiled ? ST : n;
@@ -693,7 +728,11 @@ int nlls_create(nlls_ctx** out, int device) {
     ctx->use_tma = (e && e[0] == '0') ? 0 : 1;
     if (const char* g = getenv("NLLS_B200_SCHUR_STRIDE")) ctx->schur_stride = std::max(1, atoi(g));
     if (const char* g = getenv("NLLS_B200_GRAPH")) ctx->use_graph = atoi(g) != 0;
-    if (const char* g = getenv("NLLS_B200_SCHUR")) ctx->schur_v4 = (std::string(g) == "v2") ? 0 : ((std::string(g) == "v4") ? 2 : 1);
+    if (const char* g = getenv("NLLS_B200_SCHUR")) {
+        const std::string m(g);
+        ctx->schur_v4 = (m == "v2" || m == "v5") ? 0 : ((m == "v4") ? 2 : 1);
+        ctx->schur_v5 = (m == "v5") ? 2 : ((m == "auto5") ? 1 : 0);
+    }
     if (const char* g = getenv("NLLS_B200_TILE")) { const int v = atoi(g); ctx->tile_env = (v == 64 || v == 128) ? v : 256; }
     { int v = 0; if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && v > 0) ctx->nsm = v; }
     if (cudaGetLastError() != cudaSuccess || !ctx->st || !ctx->st2 || !ctx->d_scal || !ctx->h_scal) { nlls_destroy(ctx); return NLLS_ERR_CUDA; }
@@ -711,7 +750,8 @@ int nlls_destroy(nlls_ctx* ctx) {
                     ctx->d_flush, ctx->d_tile_id, ctx->d_pos, ctx->d_diag_tile, ctx->d_diag_tile_nat,
                     ctx->d_lvl_cols, ctx->d_red_tasks, ctx->d_red_upds, ctx->d_colptr,
                     ctx->d_col_tile, ctx->d_col_row, ctx->d_Linv, ctx->d_xp, ctx->d_stile_pt, ctx->d_chunk_off, ctx->d_chunks, ctx->d_ents, ctx->d_tiles, ctx->d_camstat_part,
-                    ctx->d_ad_data, ctx->d_ad_chunks, ctx->d_ad_moff, ctx->d_ad_part, ctx->d_ent_off, ctx->d_cta_item, ctx->d_items, ctx->d_units, ctx->d_wtab, ctx->d_blob};
+                    ctx->d_ad_data, ctx->d_ad_chunks, ctx->d_ad_moff, ctx->d_ad_part, ctx->d_ent_off, ctx->d_cta_item, ctx->d_items, ctx->d_units, ctx->d_wtab, ctx->d_blob,
+                    ctx->d5_cta_item, ctx->d5_items, ctx->d5_blob, ctx->d_out_pts};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (ctx->red_graph_exec) cudaGraphExecDestroy(ctx->red_graph_exec);
     if (ctx->h_scal) cudaFreeHost(ctx->h_scal);
@@ -1063,8 +1103,36 @@ int nlls_prepare(nlls_ctx* ctx) {
         }
     }
 
+    // ---- Schur v5 plan (schur5_plan.hpp): window-aligned register accumulation; points that do not fit go to the per-chunk kernel
+    ctx->n5cta = 0; ctx->nout_pts = 0;
+    if (ctx->schur_v5) {
+        if (const char* e = getenv("NLLS_B200_S5_COST")) {   // development aid: "dmma,afrag,bfrag,fixed"
+            Schur5Cost& cm = schur5_cost();
+            sscanf(e, "%lf,%lf,%lf,%lf", &cm.dmma, &cm.afrag, &cm.bfrag, &cm.fixed);
+        }
+        ctx->s5_ncons = S5_CONSUMERS;
+        if (const char* e = getenv("NLLS_B200_S5_CONS")) ctx->s5_ncons = std::max(1, std::min(atoi(e), S5_CONSUMERS));
+        int maxrun = 48;
+        if (const char* e = getenv("NLLS_B200_S5_RUN")) maxrun = std::max(1, atoi(e));
+        Schur5Plan P5 = (DC == 6) ? schur5_build_plan<6>(ctx->h_obs_start, ctx->h_obs_cam, nA, ctx->nsm, maxrun, ctx->s5_ncons)
+                                  : schur5_build_plan<9>(ctx->h_obs_start, ctx->h_obs_cam, nA, ctx->nsm, maxrun, ctx->s5_ncons);
+        ctx->s5_ncons = std::max(ctx->s5_ncons, DC == 6 ? Schur5Cfg<6>::NBANDS : Schur5Cfg<9>::NBANDS);
+        const bool ok = !P5.cta_item.empty() && (ctx->schur_v5 == 2 || P5.out_frac <= 0.15) && P5.blob.size() < (1ull << 31);
+        if (getenv("NLLS_B200_VERBOSE"))
+            fprintf(stderr, "[nlls] schur v5 plan: %s, %zu CTAs, %zu tiles, %lld super-tiles, %lld entries, %lld DMMAs, %lld flushes, %zu outlier points (%.2f %% of the contributions), imbalance %.3f, blob %.1f MB\n",
+                    ok ? "in use" : "declined", P5.cta_item.empty() ? 0 : P5.cta_item.size() - 1, P5.items.size(), P5.n_super, P5.n_entries, P5.n_dmma, P5.n_flush, P5.outliers.size(),
+                    100.0 * P5.out_frac, P5.imbalance, P5.blob.size() * 4e-6);
+        if (ok) {
+            ctx->n5cta = (int)P5.cta_item.size() - 1;
+            TRY(upload(ctx, &ctx->d5_cta_item, P5.cta_item)); TRY(upload(ctx, &ctx->d5_items, P5.items)); TRY(upload(ctx, &ctx->d5_blob, P5.blob));
+            ctx->nout_pts = (int)P5.outliers.size();
+            TRY(upload(ctx, &ctx->d_out_pts, P5.outliers));
+        }
+    }
+
     // ---- Schur v2 plan: larger point tiles + per-tile contribution lists sorted by target block
-    if (ctx->schur_v2) {
+    ctx->nsuper = 0; ctx->nstiles = 0;
+    if (ctx->schur_v2 && ctx->n5cta == 0) {
         std::vector<int> stile_pt;
         stile_pt.push_back(0);
         {
@@ -1364,9 +1432,9 @@ int nlls_prepare(nlls_ctx* ctx) {
     ctx->cur = 0; ctx->nxt = 1; ctx->bst = 2;
     TRY(upload_vars(ctx, A, ctx->CS, ctx->d_A[0])); TRY(upload_vars(ctx, B, 3, ctx->d_B[0]));
     TRY(dalloc(ctx, &ctx->d_H, (size_t)ctx->hlen + 2));   // + slack: the Schur kernel's 16-byte-aligned bulk loads may read one element past a span
-    TRY(dalloc(ctx, &ctx->d_g, (size_t)ctx->dof)); TRY(dalloc(ctx, &ctx->d_x, (size_t)ctx->dof));
+    TRY(dalloc(ctx, &ctx->d_g, (size_t)ctx->dof + 2)); TRY(dalloc(ctx, &ctx->d_x, (size_t)ctx->dof));   // + slack: 16-byte-aligned bulk loads of g_p
     CK(cudaMemsetAsync(ctx->d_H, 0, sizeof(double) * (ctx->hlen + 2), ctx->st));
-    CK(cudaMemsetAsync(ctx->d_g, 0, sizeof(double) * ctx->dof, ctx->st));
+    CK(cudaMemsetAsync(ctx->d_g, 0, sizeof(double) * (ctx->dof + 2), ctx->st));
     CK(cudaMemsetAsync(ctx->d_x, 0, sizeof(double) * ctx->dof, ctx->st));
     TRY(dalloc(ctx, &ctx->d_Ainv, (size_t)6 * nB));
     if (ctx->s_tiled) {
