@@ -153,10 +153,11 @@ struct nlls_ctx {
     int use_graph = 1, red_graph_launches = 0;
     int schur_v4 = 1, nsuper = 0;   // nsuper: CTAs of the v4 kernel (0: v2 path)
     // Schur v5 plan (window-aligned register accumulation, schur5.cuh); 1: automatic, 2: forced, 0: off.  n5cta: CTAs (0: not in use)
-    int schur_v5 = 0, n5cta = 0, nout_pts = 0, s5_ncons = S5_CONSUMERS;   // (off by default while it is slower than v4 on the bench shape)
+    int schur_v5 = 1, n5cta = 0, nout_pts = 0, s5_ncons = S5_CONSUMERS;
     int* d5_cta_item = nullptr;
     Schur5Item* d5_items = nullptr;
     unsigned int* d5_blob = nullptr;
+    long long* d5_ftab = nullptr;
     int* d_out_pts = nullptr;       // points outside the v5 window plan (schur_outlier_kernel)
     int* d_cta_item = nullptr;
     SchurItem* d_items = nullptr;
@@ -377,7 +378,7 @@ int launch_schur(nlls_ctx* ctx, double lambda) {
     ctx->launches++;
     if (ctx->n5cta > 0) {
         Schur5Dev s5;
-        s5.cta_item = ctx->d5_cta_item; s5.items = ctx->d5_items; s5.blob = ctx->d5_blob; s5.dbg = nullptr; s5.ncons = ctx->s5_ncons;
+        s5.cta_item = ctx->d5_cta_item; s5.items = ctx->d5_items; s5.blob = ctx->d5_blob; s5.ftab = ctx->d5_ftab; s5.dbg = nullptr; s5.ncons = ctx->s5_ncons;
         static const bool s5dbg = getenv("NLLS_B200_S5DBG") != nullptr;
         long long* d_dbg = nullptr;
         if (s5dbg) { CK(cudaMalloc((void**)&d_dbg, sizeof(long long) * 64 * ctx->n5cta)); CK(cudaMemsetAsync(d_dbg, 0, sizeof(long long) * 64 * ctx->n5cta, ctx->st)); s5.dbg = d_dbg; }
@@ -731,7 +732,7 @@ int nlls_create(nlls_ctx** out, int device) {
     if (const char* g = getenv("NLLS_B200_SCHUR")) {
         const std::string m(g);
         ctx->schur_v4 = (m == "v2" || m == "v5") ? 0 : ((m == "v4") ? 2 : 1);
-        ctx->schur_v5 = (m == "v5") ? 2 : ((m == "auto5") ? 1 : 0);
+        ctx->schur_v5 = (m == "v2" || m == "v4") ? 0 : ((m == "v5") ? 2 : 1);
     }
     if (const char* g = getenv("NLLS_B200_TILE")) { const int v = atoi(g); ctx->tile_env = (v == 64 || v == 128) ? v : 256; }
     { int v = 0; if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && v > 0) ctx->nsm = v; }
@@ -751,7 +752,7 @@ int nlls_destroy(nlls_ctx* ctx) {
                     ctx->d_lvl_cols, ctx->d_red_tasks, ctx->d_red_upds, ctx->d_colptr,
                     ctx->d_col_tile, ctx->d_col_row, ctx->d_Linv, ctx->d_xp, ctx->d_stile_pt, ctx->d_chunk_off, ctx->d_chunks, ctx->d_ents, ctx->d_tiles, ctx->d_camstat_part,
                     ctx->d_ad_data, ctx->d_ad_chunks, ctx->d_ad_moff, ctx->d_ad_part, ctx->d_ent_off, ctx->d_cta_item, ctx->d_items, ctx->d_units, ctx->d_wtab, ctx->d_blob,
-                    ctx->d5_cta_item, ctx->d5_items, ctx->d5_blob, ctx->d_out_pts};
+                    ctx->d5_cta_item, ctx->d5_items, ctx->d5_blob, ctx->d5_ftab, ctx->d_out_pts};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (ctx->red_graph_exec) cudaGraphExecDestroy(ctx->red_graph_exec);
     if (ctx->h_scal) cudaFreeHost(ctx->h_scal);
@@ -1117,7 +1118,9 @@ int nlls_prepare(nlls_ctx* ctx) {
         Schur5Plan P5 = (DC == 6) ? schur5_build_plan<6>(ctx->h_obs_start, ctx->h_obs_cam, nA, ctx->nsm, maxrun, ctx->s5_ncons)
                                   : schur5_build_plan<9>(ctx->h_obs_start, ctx->h_obs_cam, nA, ctx->nsm, maxrun, ctx->s5_ncons);
         ctx->s5_ncons = std::max(ctx->s5_ncons, DC == 6 ? Schur5Cfg<6>::NBANDS : Schur5Cfg<9>::NBANDS);
-        const bool ok = !P5.cta_item.empty() && (ctx->schur_v5 == 2 || P5.out_frac <= 0.15) && P5.blob.size() < (1ull << 31);
+        // automatic choice: (almost) everything fits the window plan, and every CTA has a few tiles to pipeline (a problem of one tile
+        // per SM — Ladybug-shape — is 10 % faster with v4)
+        const bool ok = !P5.cta_item.empty() && (ctx->schur_v5 == 2 || (P5.out_frac <= 0.15 && (long long)P5.items.size() >= 4ll * ctx->nsm)) && P5.blob.size() < (1ull << 31);
         if (getenv("NLLS_B200_VERBOSE"))
             fprintf(stderr, "[nlls] schur v5 plan: %s, %zu CTAs, %zu tiles, %lld super-tiles, %lld entries, %lld DMMAs, %lld flushes, %zu outlier points (%.2f %% of the contributions), imbalance %.3f, blob %.1f MB\n",
                     ok ? "in use" : "declined", P5.cta_item.empty() ? 0 : P5.cta_item.size() - 1, P5.items.size(), P5.n_super, P5.n_entries, P5.n_dmma, P5.n_flush, P5.outliers.size(),
@@ -1125,6 +1128,8 @@ int nlls_prepare(nlls_ctx* ctx) {
         if (ok) {
             ctx->n5cta = (int)P5.cta_item.size() - 1;
             TRY(upload(ctx, &ctx->d5_cta_item, P5.cta_item)); TRY(upload(ctx, &ctx->d5_items, P5.items)); TRY(upload(ctx, &ctx->d5_blob, P5.blob));
+            const std::vector<long long> ft = (DC == 6) ? schur5_flush_table<6>(P5.super_base, tile_id, pos, ctx->NT) : schur5_flush_table<9>(P5.super_base, tile_id, pos, ctx->NT);
+            TRY(upload(ctx, &ctx->d5_ftab, ft));
             ctx->nout_pts = (int)P5.outliers.size();
             TRY(upload(ctx, &ctx->d_out_pts, P5.outliers));
         }

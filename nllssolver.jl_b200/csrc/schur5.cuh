@@ -24,7 +24,10 @@
 namespace nlls {
 
 constexpr int S5_THREADS = 32 * (S5_CONSUMERS + 1);
-constexpr int S5_NS = 3;      // stages
+#ifndef S5_NSTAGES
+#define S5_NSTAGES 3
+#endif
+constexpr int S5_NS = S5_NSTAGES;      // stages
 constexpr int S5_PAD = 3072;  // bytes in front of / behind the stages: fragment loads of window rows outside a point's own rows are
                               // not clamped (their values are discarded), they only have to stay inside the CTA's shared memory
 
@@ -46,6 +49,7 @@ struct Schur5Dev {
     const int* cta_item;
     const Schur5Item* items;
     const unsigned* blob;
+    const long long* ftab;   // FLUSH table (schur5_flush_table)
     int ncons;        // consumer warps in use (<= S5_CONSUMERS; the others leave at once)
     long long* dbg;   // != nullptr (NLLS_B200_S5DBG): per CTA and warp [16][4] cycle counters — consumers: {waiting for a tile, total};
                       // producer: {point phases, total, polls without work}
@@ -86,24 +90,30 @@ __device__ __forceinline__ double lds_f64_at(uint32_t base) {   // [base + OFF]:
 
 // ---- FLUSH helpers: one accumulator pair (window row R, window columns C0, C0 + 1) / one rhs partial into the reduced system ----
 template <int DC>
-__device__ __noinline__ void s5_flush_tile(double v0, double v1, int R, int C0, int base, int nA, const int* __restrict__ tile_id,
-                                           const int* __restrict__ tile_pos, int NT, double* __restrict__ S) {
+__device__ __noinline__ void s5_flush_tile(double v0, double v1, int R, int C0, const long long* __restrict__ ft, int nA, double* __restrict__ S) {
+    using F = Schur5Flush<DC>;
+    const int base = (int)ft[0], I0 = (int)ft[1];
     const int ca = R / DC, ar = R - ca * DC;
     const int crow = base + ca;
     if (ca >= Schur5Cfg<DC>::WC || crow >= nA) return;
+    const int ta = crow / F::TC - I0, r0 = (crow - (I0 + ta) * F::TC) * DC + ar;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
         const int Cc = C0 + h, cb = Cc / DC, cr = Cc - cb * DC;
         const double v = h ? v1 : v0;
-        if (v != 0.0 && (cb < ca || (cb == ca && cr <= ar))) atomicAdd(S + schur5_soff(crow, ar, base + cb, cr, tile_id, tile_pos, NT, DC, ST), -v);
+        if (v != 0.0 && (cb < ca || (cb == ca && cr <= ar))) {
+            const int ccol = base + cb, tb = ccol / F::TC - I0, c0 = (ccol - (I0 + tb) * F::TC) * DC + cr;
+            const long long pe = ft[2 + F::pair(ta, tb)];
+            atomicAdd(S + (pe >> 1) + ((pe & 1) ? c0 + (long long)ST * r0 : r0 + (long long)ST * c0), -v);
+        }
     }
 }
 template <int DC>
-__device__ __noinline__ void s5_flush_rhs(double rv, int R, int base, int nA, double* __restrict__ rhs, int kk) {
+__device__ __noinline__ void s5_flush_rhs(double rv, int R, const long long* __restrict__ ft, int nA, double* __restrict__ rhs, int kk) {
     rv += __shfl_xor_sync(0xffffffffu, rv, 1);
     rv += __shfl_xor_sync(0xffffffffu, rv, 2);
     const int ca = R / DC, ar = R - ca * DC;
-    const int crow = base + ca;
+    const int crow = (int)ft[0] + ca;
     if (kk == 0 && ca < Schur5Cfg<DC>::WC && crow < nA && rv != 0.0) atomicAdd(rhs + (size_t)crow * DC + ar, -rv);
 }
 
@@ -120,7 +130,7 @@ struct Schur5Band {
     __host__ __device__ static constexpr int MT(int r) { return C::row_tile(BAND, r); }
     static constexpr int NCOL = MT(BR - 1) + 1;
     // shape key = t_lo * (BR + 1) + number of active rows; for a static TLO the active rows are R0 .. R0 + NACT - 1
-    __host__ __device__ static constexpr int R0(int tlo) { return tlo <= BAND ? 0 : (tlo - BAND + NB - 1) / NB; }
+    __host__ __device__ static constexpr int R0(int tlo) { return C::r0(BAND, tlo); }
 
     template <int TLO, int NACT, int R>
     static __device__ __forceinline__ void row(double (&a)[BR], double (&racc)[BR], uint32_t wb, int u, int lim, const double2& pa, const double2& pb) {
@@ -170,16 +180,16 @@ struct Schur5Band {
     // end of a super-tile: add this warp's tiles to S (lower triangle of the window, cameras < nA) and clear them.  The per-tile work is
     // a shared, non-inlined routine (values passed in registers): inlined three times per band it was a third of the kernel's code,
     // and the instruction cache is what the consumers' straight-line shape code needs.
-    static __device__ __forceinline__ void flush(double (&acc)[BR][NTW][2], double (&racc)[BR], int base, const DevProblem& p, double* __restrict__ S,
-                                                 double* __restrict__ rhs, int fr, int kk) {
+    static __device__ __forceinline__ void flush(double (&acc)[BR][NTW][2], double (&racc)[BR], const long long* __restrict__ ft, const DevProblem& p,
+                                                 double* __restrict__ S, double* __restrict__ rhs, int fr, int kk) {
 #pragma unroll
         for (int r = 0; r < BR; ++r) {
-            s5_flush_rhs<DC>(racc[r], 8 * MT(r) + fr, base, p.nA, rhs, kk);
+            s5_flush_rhs<DC>(racc[r], 8 * MT(r) + fr, ft, p.nA, rhs, kk);
             racc[r] = 0.0;
 #pragma unroll
             for (int n = 0; n < NCOL; ++n) {
                 if (n <= MT(r)) {
-                    s5_flush_tile<DC>(acc[r][n][0], acc[r][n][1], 8 * MT(r) + fr, 8 * n + 2 * kk, base, p.nA, p.tile_id, p.tile_pos, p.NT, S);
+                    s5_flush_tile<DC>(acc[r][n][0], acc[r][n][1], 8 * MT(r) + fr, 8 * n + 2 * kk, ft, p.nA, S);
                     acc[r][n][0] = 0.0; acc[r][n][1] = 0.0;
                 }
             }
@@ -188,14 +198,14 @@ struct Schur5Band {
     // The host sorts a warp's entries of a tile by shape: the switch runs once per run of equal shapes, the run itself is a tight loop
     // over straight-line code (the compiler lowers the switch to a compare tree — paying that per entry cost 14 branches each).
     static __device__ __forceinline__ void run(double (&acc)[BR][NTW][2], double (&racc)[BR], uint32_t ep, unsigned cnt, uint32_t rowb, uint32_t ptb,
-                                               const DevProblem& p, double* __restrict__ S, double* __restrict__ rhs, int fr, int kk) {
+                                               const DevProblem& p, const long long* __restrict__ ftab, double* __restrict__ S, double* __restrict__ rhs, int fr, int kk) {
         constexpr auto RS = std::make_integer_sequence<int, BR>{};
         constexpr auto NS_ = std::make_integer_sequence<int, NCOL>{};
-        static_assert(C::nshapes(BAND) <= 20, "shape switch");
+        static_assert(C::nshapes(BAND) <= 24, "shape switch");
         const uint32_t eend = ep + 8u * cnt;
         uint2 ent = lds_u2(ep);
         while (ep < eend) {
-            if (ent.y & S5_FLUSH) { flush(acc, racc, (int)ent.x, p, S, rhs, fr, kk); break; }   // always the last entry of a list
+            if (ent.y & S5_FLUSH) { flush(acc, racc, ftab + (size_t)ent.x * Schur5Flush<DC>::STRIDE, p, S, rhs, fr, kk); break; }   // always the last entry of a list
             const unsigned id = (ent.y >> 8) & 255u;
 #define S5_CASE(K)                                                                   \
     case K:                                                                          \
@@ -209,6 +219,7 @@ struct Schur5Band {
             switch (id) {
                 S5_CASE(0) S5_CASE(1) S5_CASE(2) S5_CASE(3) S5_CASE(4) S5_CASE(5) S5_CASE(6) S5_CASE(7) S5_CASE(8) S5_CASE(9)
                 S5_CASE(10) S5_CASE(11) S5_CASE(12) S5_CASE(13) S5_CASE(14) S5_CASE(15) S5_CASE(16) S5_CASE(17) S5_CASE(18) S5_CASE(19)
+                S5_CASE(20) S5_CASE(21) S5_CASE(22) S5_CASE(23)
                 default: ep = eend; break;
             }
 #undef S5_CASE
@@ -343,18 +354,18 @@ __global__ void __launch_bounds__(S5_THREADS, 1) schur5_kernel(DevProblem p, Sch
             const unsigned band = (lds_u32(ep + 4u) >> 16) & 15u;   // a warp keeps its band for the whole super-tile, hence for the tile
             if constexpr (C::NBANDS == 3) {
                 switch (band) {
-                    case 0: Schur5Band<DC, 0>::run(acc, racc, ep, cnt, rowb, ptb, p, S, rhs, fr, kk); break;
-                    case 1: Schur5Band<DC, 1>::run(acc, racc, ep, cnt, rowb, ptb, p, S, rhs, fr, kk); break;
-                    default: Schur5Band<DC, 2>::run(acc, racc, ep, cnt, rowb, ptb, p, S, rhs, fr, kk); break;
+                    case 0: Schur5Band<DC, 0>::run(acc, racc, ep, cnt, rowb, ptb, p, sp.ftab, S, rhs, fr, kk); break;
+                    case 1: Schur5Band<DC, 1>::run(acc, racc, ep, cnt, rowb, ptb, p, sp.ftab, S, rhs, fr, kk); break;
+                    default: Schur5Band<DC, 2>::run(acc, racc, ep, cnt, rowb, ptb, p, sp.ftab, S, rhs, fr, kk); break;
                 }
             } else {
                 switch (band) {
-                    case 0: Schur5Band<DC, 0>::run(acc, racc, ep, cnt, rowb, ptb, p, S, rhs, fr, kk); break;
-                    case 1: Schur5Band<DC, 1>::run(acc, racc, ep, cnt, rowb, ptb, p, S, rhs, fr, kk); break;
-                    case 2: Schur5Band<DC, 2>::run(acc, racc, ep, cnt, rowb, ptb, p, S, rhs, fr, kk); break;
-                    case 3: Schur5Band<DC, 3>::run(acc, racc, ep, cnt, rowb, ptb, p, S, rhs, fr, kk); break;
-                    case 4: Schur5Band<DC, 4>::run(acc, racc, ep, cnt, rowb, ptb, p, S, rhs, fr, kk); break;
-                    default: Schur5Band<DC, 5>::run(acc, racc, ep, cnt, rowb, ptb, p, S, rhs, fr, kk); break;
+                    case 0: Schur5Band<DC, 0>::run(acc, racc, ep, cnt, rowb, ptb, p, sp.ftab, S, rhs, fr, kk); break;
+                    case 1: Schur5Band<DC, 1>::run(acc, racc, ep, cnt, rowb, ptb, p, sp.ftab, S, rhs, fr, kk); break;
+                    case 2: Schur5Band<DC, 2>::run(acc, racc, ep, cnt, rowb, ptb, p, sp.ftab, S, rhs, fr, kk); break;
+                    case 3: Schur5Band<DC, 3>::run(acc, racc, ep, cnt, rowb, ptb, p, sp.ftab, S, rhs, fr, kk); break;
+                    case 4: Schur5Band<DC, 4>::run(acc, racc, ep, cnt, rowb, ptb, p, sp.ftab, S, rhs, fr, kk); break;
+                    default: Schur5Band<DC, 5>::run(acc, racc, ep, cnt, rowb, ptb, p, sp.ftab, S, rhs, fr, kk); break;
                 }
             }
         }

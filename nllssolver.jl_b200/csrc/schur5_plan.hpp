@@ -26,6 +26,9 @@ namespace nlls {
 constexpr int S5_CONSUMERS = 11;       // consumer warps per CTA (+ 1 producer warp = 12 warps: registers are allocated per 4 warps)
 constexpr int S5_HDR = 16;             // header words of a tile blob: [w] (first entry << 16) | count of consumer warp w, [14] word offset of the entries, [15] span misalignment
 constexpr unsigned S5_FLUSH = 1u << 20;
+#ifndef S5_OBS6
+#define S5_OBS6 232
+#endif
 #ifndef S5_CAP3
 #define S5_CAP3 1.0     // relative capacity of consumer warps 3 and 7 (their sub-partition holds two consumers + the producer)
 #endif
@@ -44,11 +47,22 @@ template <int DC> struct Schur5Cfg {
     static constexpr int NTW = (DC <= 6) ? 9 : 12;          // row tiles of the window
     static constexpr int BR = (DC <= 6) ? 3 : 2;            // row tiles per band
     static constexpr int NBANDS = NTW / BR;
-    S5_CE static constexpr int row_tile(int band, int r) { return band + NBANDS * r; }   // r-th row tile of a band
+    // r-th row tile of a band.  DC = 9: interleaved (band b owns b, b + NBANDS, ...).  DC = 6: {0,1,5} {2,3,6} {4,7,8} — the window's
+    // middle rows carry most of the work (points start a few cameras above the base and span ~5 tiles); with 11 consumer warps the
+    // bands get 4 / 4 / 3 warps, and this split brings the three shares close to 4 : 4 : 3 on the BAL-shaped problems (the plainly
+    // interleaved split left the three-warp band 19 % over the mean on the Venice shape, this one 7 %).
+    S5_CE static constexpr int row_tile(int band, int r) {
+        if (DC <= 6) { return band == 0 ? (r == 0 ? 0 : (r == 1 ? 1 : 5)) : (band == 1 ? (r == 0 ? 2 : (r == 1 ? 3 : 6)) : (r == 0 ? 4 : (r == 1 ? 7 : 8))); }
+        return band + NBANDS * r;
+    }
     // Shapes of an entry of band `band`: (first window tile of the point TLO, number of active rows NACT); the band's rows >= TLO
     // are r0(TLO) .. BR - 1 and the first NACT of them are active.  Shapes are numbered densely (TLO ascending, NACT ascending):
     // the host stores the number in the entry, the kernel switches on it (a dense switch compiles to one indirect branch).
-    S5_CE static constexpr int r0(int band, int tlo) { return tlo <= band ? 0 : (tlo - band + NBANDS - 1) / NBANDS; }
+    S5_CE static constexpr int r0(int band, int tlo) {   // number of the band's rows above tile tlo
+        int n = 0;
+        for (int r = 0; r < BR; ++r) if (row_tile(band, r) < tlo) ++n;
+        return n;
+    }
     S5_CE static constexpr int nshapes(int band) {
         int n = 0;
         for (int tlo = 0; tlo <= row_tile(band, BR - 1); ++tlo) n += BR - r0(band, tlo);
@@ -68,7 +82,7 @@ template <int DC> struct Schur5Cfg {
     static constexpr int BIAS = 3 * 8 * NTW;                  // entry field wofs = (W_p offset in the span) - 3 (DC delta) + BIAS  >= 0
     static constexpr int WROWS = 8 * NTW;                   // scalar rows of the window
     static constexpr int WC = WROWS / DC;                   // cameras of the window
-    static constexpr int OBS = (DC <= 6) ? 232 : 128;       // tile capacity (observations / points)
+    static constexpr int OBS = (DC <= 6) ? S5_OBS6 : 128;   // tile capacity (observations / points)
     static constexpr int PTS = OBS / 2;
     static constexpr int WB = 3 * DC;
     static constexpr int ENT_CAP = PTS * NBANDS + S5_CONSUMERS + 5;   // entries per tile
@@ -88,6 +102,7 @@ struct Schur5Plan {
     std::vector<Schur5Item> items;
     std::vector<unsigned> blob;           // per tile: [S5_HDR header][point table: obs_end (u16) per point, padded to an even word count][entries: 2 words each]
     std::vector<int> outliers;            // points left to the fallback kernel
+    std::vector<int> super_base;          // window base camera of every super-tile (a FLUSH entry carries the super-tile's index)
     // statistics
     long long n_entries = 0, n_dmma = 0, n_flush = 0, n_super = 0, n_frag_a = 0, n_frag_b = 0;
     double out_frac = 0.0;                // share of the block contributions that belong to outlier points
@@ -108,6 +123,35 @@ S5_HD long long schur5_soff(int cr, int ar, int cc, int ac, const int* tile_id, 
     const int pI = pos[I], pJ = pos[J];
     if (pI >= pJ) return (long long)tile_id[(size_t)pI * NT + pJ] * ST * ST + r0 + (long long)ST * c0;
     return (long long)tile_id[(size_t)pJ * NT + pI] * ST * ST + c0 + (long long)ST * r0;
+}
+
+// FLUSH table: per super-tile [base camera, I0 = base / TC, then for every pair (a >= b) of the NTS consecutive S tiles the window can
+// touch: 2 * (element offset of the S tile (I0 + a, I0 + b)) + (1 if it is stored transposed), or -1 if the tile does not exist].
+template <int DC> struct Schur5Flush {
+    static constexpr int ST = 72, TC = ST / DC;
+    static constexpr int NTS = (Schur5Cfg<DC>::WC - 1 + TC - 1) / TC + 1;   // S tiles a window of WC cameras can span
+    static constexpr int NPAIR = NTS * (NTS + 1) / 2;
+    static constexpr int STRIDE = 2 + NPAIR;
+    S5_CE static constexpr int pair(int a, int b) { return a * (a + 1) / 2 + b; }
+};
+template <int DC>
+std::vector<long long> schur5_flush_table(const std::vector<int>& super_base, const std::vector<int>& tile_id, const std::vector<int>& pos, int NT) {
+    using F = Schur5Flush<DC>;
+    std::vector<long long> t(super_base.size() * (size_t)F::STRIDE, -1);
+    for (size_t s = 0; s < super_base.size(); ++s) {
+        long long* e = &t[s * (size_t)F::STRIDE];
+        const int I0 = super_base[s] / F::TC;
+        e[0] = super_base[s]; e[1] = I0;
+        for (int a = 0; a < F::NTS; ++a) for (int b = 0; b <= a; ++b) {
+            const int I = I0 + a, J = I0 + b;
+            if (I >= NT) continue;
+            const int pI = pos[(size_t)I], pJ = pos[(size_t)J];
+            const int id = pI >= pJ ? tile_id[(size_t)pI * NT + pJ] : tile_id[(size_t)pJ * NT + pI];
+            if (id < 0) continue;
+            e[2 + F::pair(a, b)] = 2 * ((long long)id * F::ST * F::ST) + (pI >= pJ ? 0 : 1);
+        }
+    }
+    return t;
 }
 
 // tile range [t_lo, t_hi] of a point with `k` cameras starting `delta` cameras above the window base
@@ -199,6 +243,7 @@ Schur5Plan schur5_build_plan(const std::vector<int>& obs_start, const std::vecto
             if (base == INT32_MAX) base = 0;
             // (a single tile whose own eligible points span more than the window: the late ones become outliers)
             ++P.n_super;
+            P.super_base.push_back(base);
             // ---- work per band, warps per band
             double work[C::NBANDS] = {0};
             auto unit_cost = [&](int delta, int k, int band, long long* dm, int* na, int* nb) {
@@ -215,8 +260,7 @@ Schur5Plan schur5_build_plan(const std::vector<int>& obs_start, const std::vecto
             auto fits = [&](int p) { return elig[(size_t)p] && pstart[(size_t)p] >= base && (long long)(pstart[(size_t)p] - base + pk[(size_t)p]) * DC <= C::WROWS; };
             for (int p = tile_pt[(size_t)t]; p < tile_pt[(size_t)u]; ++p) if (fits(p))
                 for (int b = 0; b < C::NBANDS; ++b) work[b] += unit_cost(pstart[(size_t)p] - base, pk[(size_t)p], b, nullptr, nullptr, nullptr);
-            // Warps of a band: counts in proportion to the work, then CONSECUTIVE warp ids per band, heaviest band first — warp w runs
-            // on SM sub-partition w % 4, so the warps of one band spread over the four FP64 pipes instead of sharing one.
+            // Warps of a band: counts in proportion to the work, heaviest band first.
             auto capw = [](int w) { return (w & 3) == 3 ? S5_CAP3 : 1.0; };
             std::vector<int> bw[C::NBANDS];
             {
@@ -231,8 +275,11 @@ Schur5Plan schur5_build_plan(const std::vector<int>& obs_start, const std::vecto
                 int border[C::NBANDS];
                 for (int b = 0; b < C::NBANDS; ++b) border[b] = b;
                 std::stable_sort(border, border + C::NBANDS, [&](int x, int y) { return work[x] > work[y]; });
+                // warp w runs on SM sub-partition w % 4: the warps of one band share a sub-partition where they can (they run the same
+                // straight-line shape code: the instruction cache was the second largest stall with the bands mixed)
+                static const int worder[S5_CONSUMERS] = {0, 4, 8, 3, 1, 5, 9, 7, 2, 6, 10};
                 int next = 0;
-                for (int i = 0; i < C::NBANDS; ++i) for (int q = 0; q < nw[border[i]]; ++q) bw[border[i]].push_back(next++);
+                for (int i = 0; i < C::NBANDS; ++i) for (int q = 0; q < nw[border[i]]; ++q) { while (worder[next] >= ncons) ++next; bw[border[i]].push_back(worder[next++]); }
             }
             double load[S5_CONSUMERS] = {0};
             bool touched[S5_CONSUMERS] = {false};
@@ -275,7 +322,7 @@ Schur5Plan schur5_build_plan(const std::vector<int>& obs_start, const std::vecto
                 }
                 if (tt == u - 1)
                     for (int b = 0; b < C::NBANDS; ++b) for (int w : bw[b]) if (touched[w]) {
-                        went[(size_t)w].push_back((unsigned)base);
+                        went[(size_t)w].push_back((unsigned)(P.super_base.size() - 1));
                         went[(size_t)w].push_back(((unsigned)b << 16) | S5_FLUSH);
                         P.n_flush++;
                     }

@@ -13,4 +13,5 @@ ctx.set_variables(capi.VAR_EUCLID6, p.cameras, first_index=1)
 ctx.set_variables(capi.VAR_EUCLID3, p.points, first_index=p.ncam + 1)
 ctx.set_costs(capi.RES_AFFINE_BA, p.costs_aos(), capi.ROBUST_HUBER, (bench.HUBER_WIDTH,))
 ctx.lm_begin(pkg.NLLSOptions(maxiters=100, maxtime=1e5).c())
+ctx.time_kernels(getattr(capi, "TIME_" + which), reps=1, flush_l2=False)   # first launch: lazy module load
 print(wl, which, ctx.time_kernels(getattr(capi, "TIME_" + which), reps=reps, flush_l2=True))

@@ -84,7 +84,10 @@ double run_case(unsigned seed, int nA, int nB, double kmean, int scatter_every, 
                     const int band = (int)((y >> 16) & 15);
                     Acc& A = acc[(size_t)w];
                     if (y & S5_FLUSH) {
-                        const int base = (int)x;
+                        const int base = P.super_base[x];
+                        const std::vector<long long> ft = schur5_flush_table<DC>(P.super_base, tile_id, pos, NT);
+                        const long long* fe = &ft[(size_t)x * Schur5Flush<DC>::STRIDE];
+                        if (fe[0] != base) return -10.0;
                         for (int r = 0; r < C::BR; ++r) {
                             const int mt = C::row_tile(band, r);
                             for (int fr = 0; fr < 8; ++fr) {
@@ -94,7 +97,17 @@ double run_case(unsigned seed, int nA, int nB, double kmean, int scatter_every, 
                                 for (int nt2 = 0; nt2 <= mt; ++nt2) for (int cc = 0; cc < 8; ++cc) {
                                     const int Cc = 8 * nt2 + cc, cb = Cc / DC, cr = Cc % DC;
                                     if (cb > ca || (cb == ca && cr > ar)) continue;
-                                    S[(size_t)schur5_soff(base + ca, ar, base + cb, cr, tile_id.data(), pos.data(), NT, DC, ST)] -= A.t[r][nt2][fr][cc];
+                                    const long long so = schur5_soff(base + ca, ar, base + cb, cr, tile_id.data(), pos.data(), NT, DC, ST);
+                                    {   // the table the kernel uses must give the same address
+                                        using F = Schur5Flush<DC>;
+                                        const int I0 = (int)fe[1], ta = (base + ca) / F::TC - I0, tb = (base + cb) / F::TC - I0;
+                                        const long long pe = fe[2 + F::pair(ta, tb)];
+                                        if (pe < 0) return -11.0;
+                                        const int r0 = (base + ca - (I0 + ta) * F::TC) * DC + ar, c0 = (base + cb - (I0 + tb) * F::TC) * DC + cr;
+                                        const long long so2 = (pe >> 1) + ((pe & 1) ? c0 + (long long)ST * r0 : r0 + (long long)ST * c0);
+                                        if (so2 != so) return -12.0;
+                                    }
+                                    S[(size_t)so] -= A.t[r][nt2][fr][cc];
                                 }
                             }
                         }
