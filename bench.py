@@ -255,7 +255,7 @@ def main():
 
     # ---- kernel-level numbers for the roofline (CUDA events on the library's stream, L2 flushed between reps)
     kern = {}
-    for name, which in [("linearize", capi.TIME_LINEARIZE), ("lin_point", capi.TIME_LIN_POINT), ("lin_cam", capi.TIME_LIN_CAM), ("cost", capi.TIME_COST),
+    for name, which in [("linearize", capi.TIME_LINEARIZE), ("linearize_in_loop", capi.TIME_LIN_LOOP), ("lin_point", capi.TIME_LIN_POINT), ("lin_cam", capi.TIME_LIN_CAM), ("cost", capi.TIME_COST),
                         ("schur", capi.TIME_SCHUR), ("reduced_solve", capi.TIME_SOLVE_REDUCED), ("backsub_update", capi.TIME_BACKSUB), ("lm_try", capi.TIME_TRY)]:
         kern[name] = ctx.time_kernels(which, reps=5, flush_l2=True)
     peaks = {}

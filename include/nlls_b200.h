@@ -162,7 +162,9 @@ int nlls_get_hessian_index(nlls_ctx* ctx, int64_t* rowblock, int64_t* colblock, 
  * by CUDA events on that stream and returns the average milliseconds per call of the named kernel group.  */
 enum nlls_timed { NLLS_TIME_LINEARIZE = 0, NLLS_TIME_LIN_POINT = 1, NLLS_TIME_LIN_CAM = 2, NLLS_TIME_COST = 3,
                   NLLS_TIME_SCHUR = 4, NLLS_TIME_SOLVE_REDUCED = 5, NLLS_TIME_BACKSUB = 6, NLLS_TIME_TRY = 7,
-                  NLLS_TIME_MEMSET_H = 8 /* write-only probe: cudaMemset over the point rows of H (destroys H until the next linearise) */ };
+                  NLLS_TIME_MEMSET_H = 8 /* write-only probe: cudaMemset over the point rows of H (destroys H until the next linearise) */,
+                  NLLS_TIME_LIN_LOOP = 9 /* the re-linearisation as the LM loop runs it: point pass + finalize of the camera partials the
+                                            accepted try's cost evaluation left behind */ };
 int nlls_time_kernels(nlls_ctx* ctx, int which, int reps, int flush_l2, double* ms_per_call);
 /* CUDA events on the context's stream around an arbitrary sequence of calls (bench.py's timed region). */
 int nlls_timer_start(nlls_ctx* ctx);

@@ -16,7 +16,7 @@ VAR_SCALAR, VAR_EUCLID3, VAR_EUCLID6, VAR_CONTAMGAUSS, VAR_PINHOLE = 1, 3, 6, 10
 RES_AFFINE_BA, RES_PINHOLE_BA, RES_ADAPTIVE_OFFSET = 1, 2, 3
 ROBUST_NONE, ROBUST_HUBER, ROBUST_HUBER2O, ROBUST_GEMANMCCLURE, ROBUST_SCALED = 0, 1, 2, 3, 16
 ITER_NEWTON, ITER_LM, ITER_DOGLEG, ITER_GD = 0, 1, 2, 3
-TIME_LINEARIZE, TIME_LIN_POINT, TIME_LIN_CAM, TIME_COST, TIME_SCHUR, TIME_SOLVE_REDUCED, TIME_BACKSUB, TIME_TRY, TIME_MEMSET_H = range(9)
+TIME_LINEARIZE, TIME_LIN_POINT, TIME_LIN_CAM, TIME_COST, TIME_SCHUR, TIME_SOLVE_REDUCED, TIME_BACKSUB, TIME_TRY, TIME_MEMSET_H, TIME_LIN_LOOP = range(10)
 
 EXPORTS = [
     "nlls_create", "nlls_destroy", "nlls_last_error", "nlls_version", "nlls_comm_unique_id", "nlls_comm_init",

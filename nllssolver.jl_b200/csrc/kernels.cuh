@@ -284,20 +284,25 @@ __global__ void __launch_bounds__(TO) cost_kernel(DevProblem p, const int4* __re
 }
 
 // ---------------------------------------------------------------------------------------------------
-// K2  lin_cam: camera diagonal blocks U_c = sum J_c' W J_c and g_c over the camera-major observation copy.
-// One CTA per work item (a camera and at most CAM_CHUNK of its observations); fixed-shape reduction.
+// K2  lin_cam: camera diagonal blocks U_c = sum J_c' W J_c and g_c over the camera-major observation copy, plus the cost
+// sum 0.5 rho(|r|^2) of the same observations (the residuals are computed anyway).
+// One CTA per work item (a camera and at most CAM_CHUNK of its observations); fixed-shape reduction; per item NU + 1 partials.
+// Inside the LM loop this kernel IS the cost evaluation of a try (cost(varnext, costs), src/iterators.jl:157): when the try is
+// accepted, the camera blocks it produced are exactly those of the re-linearisation at the accepted point (src/optimize.jl:169),
+// so the re-linearisation only runs the point pass and the camera pass costs nothing extra (launch_cost / do_linearize).
 // ---------------------------------------------------------------------------------------------------
 template <class R>
 __global__ void __launch_bounds__(256, (R::DC <= 6) ? 2 : 1) lin_cam_kernel(DevProblem p, const double* __restrict__ cams, const double* __restrict__ pts,
                                                       double* __restrict__ partials) {
     constexpr int DC = R::DC, NU = DC * (DC + 1) / 2 + DC;
-    __shared__ double s_red[8][NU];
+    __shared__ double s_red[8][NU + 1];
     const int tid = threadIdx.x, item = blockIdx.x;
     const int cam = p.item_cam[item];
     const int beg = p.item_beg[item], end = p.item_end[item];
     double cv[R::NC];
     R::load_cam(cams, cam, cv);
     double acc[NU];
+    double cacc = 0.0;
 #pragma unroll
     for (int i = 0; i < NU; ++i) acc[i] = 0.0;
     // batches of four observations per thread: the index / measurement loads and then the point gathers of a batch are all
@@ -323,6 +328,7 @@ __global__ void __launch_bounds__(256, (R::DC <= 6) ? 2 : 1) lin_cam_kernel(DevP
             const double s = r[0] * r[0] + r[1] * r[1];
             double rho, d1, d2;
             robustifydcost(p.rk, s, rho, d1, d2);
+            cacc += 0.5 * rho;
             // explicit FMAs (the file is compiled with -fmad=false): this pass is FP64-issue bound, not HBM bound — ncu.  The
             // weights fold into the accumulation:  acc += d1 (J'J) + (2 d2 g) g'  (exact no-ops when d1 == 1 / d2 == 0)
             double gc[DC], tg[DC];
@@ -348,13 +354,26 @@ __global__ void __launch_bounds__(256, (R::DC <= 6) ? 2 : 1) lin_cam_kernel(DevP
         const double v = warp_sum(acc[i]);
         if (lane == 0) s_red[w][i] = v;
     }
+    {
+        const double v = warp_sum(cacc);
+        if (lane == 0) s_red[w][NU] = v;
+    }
     __syncthreads();
-    if (tid < NU) {
+    if (tid <= NU) {
         double tsum = 0.0;
 #pragma unroll
         for (int k = 0; k < 8; ++k) tsum += s_red[k][tid];
-        partials[(size_t)item * NU + tid] = tsum;
+        partials[(size_t)item * (NU + 1) + tid] = tsum;
     }
+}
+
+// sum of the work items' cost partials (element NU of every item) in a fixed order -> *out  (single CTA)
+__global__ void __launch_bounds__(1024) cam_cost_reduce_kernel(const double* __restrict__ partials, int nitems, int stride, double* out) {
+    __shared__ double s_red[32];
+    double v = 0.0;
+    for (int i = threadIdx.x; i < nitems; i += 1024) v += partials[(size_t)i * stride + stride - 1];
+    v = block_sum(v, s_red);
+    if (threadIdx.x == 0) *out = v;
 }
 
 // K2b: per camera, add its work-item partials in order and write the full symmetric block + g_c.
@@ -365,7 +384,7 @@ __global__ void cam_finalize_kernel(DevProblem p, const double* __restrict__ par
     if (idx >= p.nA * NU) return;
     const int cam = idx / NU, e = idx - cam * NU;
     double s = 0.0;
-    for (int it = p.cam_item_start[cam]; it < p.cam_item_start[cam + 1]; ++it) s += partials[(size_t)it * NU + e];
+    for (int it = p.cam_item_start[cam]; it < p.cam_item_start[cam + 1]; ++it) s += partials[(size_t)it * (NU + 1) + e];
     constexpr int NL = DC * (DC + 1) / 2;
     if (e < NL) {
         // e enumerates the lower triangle column by column: (a >= a2)

@@ -120,7 +120,9 @@ struct nlls_ctx {
     double *d_A[3] = {nullptr, nullptr, nullptr}, *d_B[3] = {nullptr, nullptr, nullptr};
     int cur = 0, nxt = 1, bst = 2;
     double *d_H = nullptr, *d_g = nullptr, *d_x = nullptr, *d_Ainv = nullptr, *d_S = nullptr, *d_rhs = nullptr;
-    double *d_cost_part = nullptr, *d_step_part = nullptr, *d_cam_part = nullptr, *d_camstat_part = nullptr;
+    double *d_cost_part = nullptr, *d_step_part = nullptr, *d_cam_part = nullptr, *d_cam_part2 = nullptr, *d_camstat_part = nullptr;
+    int cam_part_vars = -1;          // variable buffer (index into d_A / d_B) whose camera-pass partials are in d_cam_part, -1: none
+    int cost_pointmajor = 0;
     double *d_scal = nullptr, *h_scal = nullptr;
     void* d_flush = nullptr;
     size_t flush_bytes = 0;
@@ -140,10 +142,14 @@ struct nlls_ctx {
     std::vector<RedLaunch> fact_launches;
     RedTask* d_red_tasks = nullptr;
     RedUpd* d_red_upds = nullptr;
+    RedTarget* d_red_targets = nullptr;
     std::vector<std::pair<int, int>> lvl_cols;           // (offset, count) into d_lvl_cols per level
     int *d_tile_id = nullptr, *d_pos = nullptr, *d_diag_tile = nullptr, *d_diag_tile_nat = nullptr, *d_lvl_cols = nullptr;
     int *d_colptr = nullptr, *d_col_tile = nullptr, *d_col_row = nullptr;
     double *d_Linv = nullptr, *d_xp = nullptr;
+    int bwd_flow = 0;                // NLLS_B200_BWD=flow: backward sweep as one dataflow launch instead of one launch per level (measured equal:
+                                     // 0.401 vs 0.396 ms per reduced solve on the Venice shape — the chain of dependent columns is the cost, not the launches)
+    int *d_bwd_order = nullptr, *d_bwd_flags = nullptr;
     // Schur v2 plan (per-tile sorted contribution lists)
     int schur_v2 = 1;
     int nstiles = 0;
@@ -298,6 +304,7 @@ int set_smem_attrs(nlls_ctx* ctx) {
     CK(cudaFuncSetAttribute(ldl_off_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OFF_SMEM));
     CK(cudaFuncSetAttribute(ldl_upd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UPD_SMEM));
     CK(cudaFuncSetAttribute(ldl_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWD_SMEM));
+    CK(cudaFuncSetAttribute(ldl_bwd_flow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWD_SMEM));
     return NLLS_OK;
 }
 
@@ -318,14 +325,16 @@ int exchange_max(nlls_ctx* ctx, double* v, int n) {
     return NLLS_OK;
 }
 
+// do_cam: 1 = camera pass (lin_cam on the second stream) + finalize, 2 = finalize only: the work-item partials in d_cam_part were
+// produced by the cost evaluation of the accepted try at exactly these variables (launch_cost)
 template <class R>
-int launch_linearize(nlls_ctx* ctx, bool do_point = true, bool do_cam = true) {
+int launch_linearize(nlls_ctx* ctx, bool do_point = true, int do_cam = 1) {
     DevProblem p = devproblem(ctx);
     constexpr int NU = R::DC * (R::DC + 1) / 2 + R::DC;
     if (do_cam) {
         CK(cudaEventRecord(ctx->ev_fork, ctx->st));
         CK(cudaStreamWaitEvent(ctx->st2, ctx->ev_fork, 0));
-        if (ctx->nitems > 0) { lin_cam_kernel<R><<<ctx->nitems, 256, 0, ctx->st2>>>(p, ctx->d_A[ctx->cur], ctx->d_B[ctx->cur], ctx->d_cam_part); ctx->launches++; }
+        if (do_cam == 1 && ctx->nitems > 0) { lin_cam_kernel<R><<<ctx->nitems, 256, 0, ctx->st2>>>(p, ctx->d_A[ctx->cur], ctx->d_B[ctx->cur], ctx->d_cam_part); ctx->launches++; }
         const int tot = (int)ctx->nA * NU;
         cam_finalize_kernel<R::DC><<<(tot + 255) / 256, 256, 0, ctx->st2>>>(p, ctx->d_cam_part); ctx->launches++;
         CK(cudaEventRecord(ctx->ev_join, ctx->st2));
@@ -344,16 +353,28 @@ int launch_linearize(nlls_ctx* ctx, bool do_point = true, bool do_cam = true) {
     return NLLS_OK;
 }
 
+// cost(vars[which], costs)  (src/cost.jl:11): the camera-major pass (lin_cam_kernel), which also leaves the camera blocks of
+// vars[which] in `part` (work-item partials).  part == d_cam_part: the LM try — the partials are reused by the re-linearisation if
+// the try is accepted; part == d_cam_part2: nlls_cost(), which must not disturb them.  Same kernel, same reduction tree in both
+// cases, so cost(problem) == bestcost exactly (test/optimizeba.jl:67).
 template <class R>
-int launch_cost(nlls_ctx* ctx, int which, int slot) {
+int launch_cost(nlls_ctx* ctx, int which, int slot, double* part = nullptr) {
     DevProblem p = devproblem(ctx);
-    if (ctx->ntiles > 0) {
-        if (ctx->tile_obs == 64) cost_kernel<R, 64><<<ctx->cost_grid, 64, 0, ctx->st>>>(p, ctx->d_tiles, ctx->d_A[which], ctx->d_B[which], ctx->d_cost_part);
-        else if (ctx->tile_obs == 128) cost_kernel<R, 128><<<ctx->cost_grid, 128, 0, ctx->st>>>(p, ctx->d_tiles, ctx->d_A[which], ctx->d_B[which], ctx->d_cost_part);
-        else cost_kernel<R, 256><<<ctx->cost_grid, 256, 0, ctx->st>>>(p, ctx->d_tiles, ctx->d_A[which], ctx->d_B[which], ctx->d_cost_part);
-        ctx->launches++;
+    constexpr int NU = R::DC * (R::DC + 1) / 2 + R::DC;
+    if (!part) part = ctx->d_cam_part;
+    if (ctx->cost_pointmajor) {   // NLLS_B200_COST=tiles: the round-1 cost kernel (point-major tiles)
+        if (ctx->ntiles > 0) {
+            if (ctx->tile_obs == 64) cost_kernel<R, 64><<<ctx->cost_grid, 64, 0, ctx->st>>>(p, ctx->d_tiles, ctx->d_A[which], ctx->d_B[which], ctx->d_cost_part);
+            else if (ctx->tile_obs == 128) cost_kernel<R, 128><<<ctx->cost_grid, 128, 0, ctx->st>>>(p, ctx->d_tiles, ctx->d_A[which], ctx->d_B[which], ctx->d_cost_part);
+            else cost_kernel<R, 256><<<ctx->cost_grid, 256, 0, ctx->st>>>(p, ctx->d_tiles, ctx->d_A[which], ctx->d_B[which], ctx->d_cost_part);
+            ctx->launches++;
+        }
+        reduce_partials_kernel<<<1, 1024, 0, ctx->st>>>(ctx->d_cost_part, ctx->ntiles, ctx->d_scal + slot, 0); ctx->launches++;
+    } else {
+        if (ctx->nitems > 0) { lin_cam_kernel<R><<<ctx->nitems, 256, 0, ctx->st>>>(p, ctx->d_A[which], ctx->d_B[which], part); ctx->launches++; }
+        cam_cost_reduce_kernel<<<1, 1024, 0, ctx->st>>>(part, ctx->nitems, NU + 1, ctx->d_scal + slot); ctx->launches++;
+        if (part == ctx->d_cam_part) ctx->cam_part_vars = which;   // the camera blocks of these variables are now in d_cam_part
     }
-    reduce_partials_kernel<<<1, 1024, 0, ctx->st>>>(ctx->d_cost_part, ctx->ntiles, ctx->d_scal + slot, 0); ctx->launches++;
     CK(cudaGetLastError());
     TRY(allreduce(ctx, ctx->d_scal + slot, 1, ncclSum));
     return NLLS_OK;
@@ -440,9 +461,14 @@ int launch_reduced_solve(nlls_ctx* ctx) {
             for (const auto& l : ctx->fact_launches) {   // factorisation + forward substitution (fused into the diagonal tasks)
                 if (l.kind == 0) ldl_diag_kernel<<<l.cnt, DIAG_THREADS, DIAG_SMEM, ctx->st>>>(ctx->d_S, ctx->d_Linv, ctx->d_red_tasks + l.off, ctx->d_xp);
                 else if (l.kind == 1) ldl_off_kernel<<<GEMM_CTAS * l.cnt, GEMM_THREADS, OFF_SMEM, ctx->st>>>(ctx->d_S, ctx->d_Linv, ctx->d_red_tasks + l.off, ctx->d_xp);
-                else ldl_upd_kernel<<<GEMM_CTAS * l.cnt, GEMM_THREADS, UPD_SMEM, ctx->st>>>(ctx->d_S, ctx->d_red_upds + l.off);
+                else ldl_upd_kernel<<<GEMM_CTAS * l.cnt, GEMM_THREADS, UPD_SMEM, ctx->st>>>(ctx->d_S, ctx->d_red_upds, ctx->d_red_targets + l.off, ctx->d_xp);
                 ++nl;
             }
+            if (ctx->bwd_flow) {   // one dataflow launch over all columns (levels from last to first)
+                CK(cudaMemsetAsync(ctx->d_bwd_flags, 0, sizeof(int) * ctx->NT, ctx->st));
+                ldl_bwd_flow_kernel<<<std::min(ctx->NT, ctx->nsm), RED_THREADS, BWD_SMEM, ctx->st>>>(ctx->d_S, ctx->d_Linv, t, ctx->d_bwd_order, ctx->NT, ctx->d_bwd_flags, ctx->d_xp);
+                ++nl;
+            } else
             for (size_t l = ctx->lvl_cols.size(); l-- > 0;) {
                 ldl_bwd_kernel<<<ctx->lvl_cols[l].second, RED_THREADS, BWD_SMEM, ctx->st>>>(ctx->d_S, ctx->d_Linv, t, ctx->d_lvl_cols + ctx->lvl_cols[l].first, ctx->d_xp);
                 ++nl;
@@ -469,9 +495,8 @@ int launch_reduced_solve(nlls_ctx* ctx) {
             ctx->launches += nl;
         }
         CK(cudaGetLastError());
-        // every rank factors the same all-reduced system, but the update kernel's FP64 reductions commute only up to rounding:
-        // rank 0's camera step is broadcast so that the camera replicas stay bit-identical
-        if (ctx->nranks > 1) CKN(g_nccl.Broadcast(ctx->d_rhs, ctx->d_rhs, (size_t)nx, ncclFloat64, 0, ctx->comm, ctx->st));
+        // every rank factors the same all-reduced system with owner-written updates (no reductions): the camera replicas stay
+        // bit-identical without an exchange
         return NLLS_OK;
     }
 }
@@ -576,7 +601,10 @@ int do_linearize(nlls_ctx* ctx, double* cost) {
         if (cost) *cost = ctx->h_scal[SC_COST_LIN];
         return NLLS_OK;
     }
-    TRY(DISPATCH(ctx, launch_linearize, ctx, true, true));
+    // the accepted try's cost evaluation already ran the camera pass at these variables: only its finalize is left
+    const int cam_mode = (ctx->cam_part_vars == ctx->cur) ? 2 : 1;
+    TRY(DISPATCH(ctx, launch_linearize, ctx, true, cam_mode));
+    ctx->cam_part_vars = -1;
     if (ctx->nranks > 1) {  // camera blocks + camera gradient are sums over all ranks' observations
         CKN(g_nccl.GroupStart());
         CKN(g_nccl.AllReduce(ctx->d_H, ctx->d_H, (size_t)ctx->DC * ctx->DC * ctx->nA, ncclFloat64, ncclSum, ctx->comm, ctx->st));
@@ -729,6 +757,8 @@ int nlls_create(nlls_ctx** out, int device) {
     ctx->use_tma = (e && e[0] == '0') ? 0 : 1;
     if (const char* g = getenv("NLLS_B200_SCHUR_STRIDE")) ctx->schur_stride = std::max(1, atoi(g));
     if (const char* g = getenv("NLLS_B200_GRAPH")) ctx->use_graph = atoi(g) != 0;
+    if (const char* g = getenv("NLLS_B200_BWD")) ctx->bwd_flow = std::string(g) == "flow";
+    if (const char* g = getenv("NLLS_B200_COST")) ctx->cost_pointmajor = std::string(g) == "tiles";
     if (const char* g = getenv("NLLS_B200_SCHUR")) {
         const std::string m(g);
         ctx->schur_v4 = (m == "v2" || m == "v5") ? 0 : ((m == "v4") ? 2 : 1);
@@ -747,12 +777,12 @@ int nlls_destroy(nlls_ctx* ctx) {
     cudaDeviceSynchronize();
     void* ptrs[] = {ctx->d_obs_cam, ctx->d_obs_pt, ctx->d_obs_start, ctx->d_tile_pt, ctx->d_obs_z, ctx->d_cm_pt, ctx->d_item_cam, ctx->d_item_beg,
                     ctx->d_item_end, ctx->d_cam_item_start, ctx->d_cm_z, ctx->d_A[0], ctx->d_A[1], ctx->d_A[2], ctx->d_B[0], ctx->d_B[1], ctx->d_B[2],
-                    ctx->d_H, ctx->d_g, ctx->d_x, ctx->d_Ainv, ctx->d_S, ctx->d_rhs, ctx->d_cost_part, ctx->d_step_part, ctx->d_cam_part, ctx->d_scal,
+                    ctx->d_H, ctx->d_g, ctx->d_x, ctx->d_Ainv, ctx->d_S, ctx->d_rhs, ctx->d_cost_part, ctx->d_step_part, ctx->d_cam_part, ctx->d_cam_part2, ctx->d_scal,
                     ctx->d_flush, ctx->d_tile_id, ctx->d_pos, ctx->d_diag_tile, ctx->d_diag_tile_nat,
-                    ctx->d_lvl_cols, ctx->d_red_tasks, ctx->d_red_upds, ctx->d_colptr,
+                    ctx->d_lvl_cols, ctx->d_red_tasks, ctx->d_red_upds, ctx->d_red_targets, ctx->d_colptr,
                     ctx->d_col_tile, ctx->d_col_row, ctx->d_Linv, ctx->d_xp, ctx->d_stile_pt, ctx->d_chunk_off, ctx->d_chunks, ctx->d_ents, ctx->d_tiles, ctx->d_camstat_part,
                     ctx->d_ad_data, ctx->d_ad_chunks, ctx->d_ad_moff, ctx->d_ad_part, ctx->d_ent_off, ctx->d_cta_item, ctx->d_items, ctx->d_units, ctx->d_wtab, ctx->d_blob,
-                    ctx->d5_cta_item, ctx->d5_items, ctx->d5_blob, ctx->d5_ftab, ctx->d_out_pts};
+                    ctx->d5_cta_item, ctx->d5_items, ctx->d5_blob, ctx->d5_ftab, ctx->d_out_pts, ctx->d_bwd_order, ctx->d_bwd_flags};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (ctx->red_graph_exec) cudaGraphExecDestroy(ctx->red_graph_exec);
     if (ctx->h_scal) cudaFreeHost(ctx->h_scal);
@@ -810,6 +840,7 @@ int nlls_set_variables(nlls_ctx* ctx, int vartype, const double* aos, int64_t n,
         }
         CK(cudaStreamSynchronize(ctx->st));
         vs.stale = true;
+        ctx->cam_part_vars = -1;
         return NLLS_OK;
     }
     std::vector<int64_t> gi((size_t)n);
@@ -994,6 +1025,7 @@ int nlls_prepare(nlls_ctx* ctx) {
     std::vector<int> tile_id, pos, diag_tile, diag_tile_nat, lvl_cols_flat, colptr, col_tile, col_row;
     std::vector<RedTask> red_tasks;
     std::vector<RedUpd> red_upds;
+    std::vector<RedTarget> red_targets;
     if (ctx->s_tiled) {
         const int TC = ST / DC;
         const int NT = (int)((nA + TC - 1) / TC);
@@ -1075,22 +1107,35 @@ int nlls_prepare(nlls_ctx* ctx) {
                 RedTask tk; tk.tile = diag_tile[(size_t)J2]; tk.dtile = tk.tile; tk.col = J2; tk.row = J2;
                 red_tasks.push_back(tk);
             }
-            const int o0 = (int)red_tasks.size(), u0 = (int)red_upds.size();
+            const int o0 = (int)red_tasks.size(), u0 = (int)red_upds.size(), g0 = (int)red_targets.size();
+            std::vector<std::pair<int, RedUpd>> lvl_upds;   // (target tile, update) of this level
             for (int q = c0; q < (int)lvl_cols_flat.size(); ++q) {
                 const int J2 = lvl_cols_flat[(size_t)q];
                 const std::vector<int>& r = rows[(size_t)J2];
                 for (int I : r) { RedTask tk; tk.tile = tile_id[(size_t)I * NT + J2]; tk.dtile = diag_tile[(size_t)J2]; tk.col = J2; tk.row = I; red_tasks.push_back(tk); }
                 // eliminating column J couples every pair (a >= b) of its rows: T_{r[a], r[b]} -= L_{r[a],J} D_J L_{r[b],J}'
                 for (size_t a = 0; a < r.size(); ++a) for (size_t b = 0; b <= a; ++b) {
-                    RedUpd u; u.a = tile_id[(size_t)r[a] * NT + J2]; u.b = tile_id[(size_t)r[b] * NT + J2]; u.dk = diag_tile[(size_t)J2];
-                    u.target = tile_id[(size_t)r[a] * NT + r[b]];
-                    red_upds.push_back(u);
+                    RedUpd u; u.a = tile_id[(size_t)r[a] * NT + J2]; u.b = tile_id[(size_t)r[b] * NT + J2]; u.dk = diag_tile[(size_t)J2]; u.col = J2;
+                    lvl_upds.push_back({tile_id[(size_t)r[a] * NT + r[b]], u});
                 }
+            }
+            // the level's updates grouped by target tile (stable: ascending source column inside a target) — one owner per target
+            std::stable_sort(lvl_upds.begin(), lvl_upds.end(), [](const std::pair<int, RedUpd>& x, const std::pair<int, RedUpd>& y) { return x.first < y.first; });
+            for (size_t k0 = 0; k0 < lvl_upds.size();) {
+                size_t k1 = k0;
+                RedTarget tg; tg.target = lvl_upds[k0].first; tg.u0 = (int)red_upds.size(); tg.row = -1;
+                while (k1 < lvl_upds.size() && lvl_upds[k1].first == tg.target) { red_upds.push_back(lvl_upds[k1].second); ++k1; }
+                tg.u1 = (int)red_upds.size();
+                if (lvl_upds[k0].second.a == lvl_upds[k0].second.b) {   // diagonal target (I, I): find I
+                    for (int I = 0; I < NT; ++I) if (diag_tile[(size_t)I] == tg.target) { tg.row = I; break; }
+                }
+                red_targets.push_back(tg);
+                k0 = k1;
             }
             ctx->lvl_cols.push_back({c0, (int)lvl_cols_flat.size() - c0});
             ctx->fact_launches.push_back({0, d0, o0 - d0});
             if ((int)red_tasks.size() > o0) ctx->fact_launches.push_back({1, o0, (int)red_tasks.size() - o0});
-            if ((int)red_upds.size() > u0) ctx->fact_launches.push_back({2, u0, (int)red_upds.size() - u0});
+            if ((int)red_upds.size() > u0) ctx->fact_launches.push_back({2, g0, (int)red_targets.size() - g0});
         }
         nupd_total = red_upds.size();
         if (getenv("NLLS_B200_VERBOSE"))
@@ -1447,14 +1492,22 @@ int nlls_prepare(nlls_ctx* ctx) {
         TRY(dalloc(ctx, &ctx->d_Linv, (size_t)ctx->NT * ST2)); TRY(dalloc(ctx, &ctx->d_xp, (size_t)ctx->NT * ST));
         TRY(upload(ctx, &ctx->d_tile_id, tile_id)); TRY(upload(ctx, &ctx->d_pos, pos));
         TRY(upload(ctx, &ctx->d_diag_tile, diag_tile)); TRY(upload(ctx, &ctx->d_diag_tile_nat, diag_tile_nat));
-        TRY(upload(ctx, &ctx->d_red_tasks, red_tasks)); TRY(upload(ctx, &ctx->d_red_upds, red_upds));
+        TRY(upload(ctx, &ctx->d_red_tasks, red_tasks)); TRY(upload(ctx, &ctx->d_red_upds, red_upds)); TRY(upload(ctx, &ctx->d_red_targets, red_targets));
         CK(cudaMemsetAsync(ctx->d_Linv, 0, sizeof(double) * (size_t)ctx->NT * ST2, ctx->st));
         TRY(upload(ctx, &ctx->d_lvl_cols, lvl_cols_flat));
+        {
+            std::vector<int> bwd_order;   // columns by level, last level first
+            for (size_t l = ctx->lvl_cols.size(); l-- > 0;)
+                for (int q = 0; q < ctx->lvl_cols[l].second; ++q) bwd_order.push_back(lvl_cols_flat[(size_t)(ctx->lvl_cols[l].first + q)]);
+            TRY(upload(ctx, &ctx->d_bwd_order, bwd_order));
+            TRY(dalloc(ctx, &ctx->d_bwd_flags, (size_t)ctx->NT));
+        }
         TRY(upload(ctx, &ctx->d_colptr, colptr)); TRY(upload(ctx, &ctx->d_col_tile, col_tile)); TRY(upload(ctx, &ctx->d_col_row, col_row));
     }
     TRY(dalloc(ctx, &ctx->d_cost_part, (size_t)ctx->ntiles)); TRY(dalloc(ctx, &ctx->d_step_part, (size_t)4 * ctx->ntiles));
     const int NU = DC * (DC + 1) / 2 + DC;
-    TRY(dalloc(ctx, &ctx->d_cam_part, (size_t)ctx->nitems * NU));
+    TRY(dalloc(ctx, &ctx->d_cam_part, (size_t)ctx->nitems * (NU + 1))); TRY(dalloc(ctx, &ctx->d_cam_part2, (size_t)ctx->nitems * (NU + 1)));
+    ctx->cam_part_vars = -1;
     TRY(dalloc(ctx, &ctx->d_camstat_part, (size_t)4 * ((nA + 127) / 128)));
     TRY(DISPATCH(ctx, set_smem_attrs, ctx));
     CK(cudaStreamSynchronize(ctx->st));
@@ -1476,7 +1529,7 @@ int nlls_cost(nlls_ctx* ctx, int which, double* cost) {
     CK(cudaSetDevice(ctx->device));
     const int buf = which == 0 ? ctx->cur : (which == 1 ? ctx->nxt : ctx->bst);
     if (ctx->adaptive) TRY(adapt_cost(ctx, buf, SC_COST_TRY));
-    else TRY(DISPATCH(ctx, launch_cost, ctx, buf, SC_COST_TRY));
+    else TRY(DISPATCH(ctx, launch_cost, ctx, buf, SC_COST_TRY, ctx->d_cam_part2));
     TRY(fetch_scalars(ctx));
     if (cost) *cost = ctx->h_scal[SC_COST_TRY];
     return NLLS_OK;
@@ -1486,6 +1539,7 @@ int nlls_solve(nlls_ctx* ctx, double lambda) {
     if (!ctx || !ctx->prepared) return NLLS_ERR_INVALID;
     CK(cudaSetDevice(ctx->device));
     if (ctx->adaptive) { TRY(adapt_solve_update(ctx, lambda)); return fetch_scalars(ctx); }
+    ctx->cam_part_vars = -1;   // varnext is rewritten without a cost evaluation
     TRY(DISPATCH(ctx, launch_schur, ctx, lambda));
     TRY(launch_reduced_solve(ctx));
     // back-substitution also writes x and varnext; nlls_update is then a no-op kept for API symmetry
@@ -1849,6 +1903,8 @@ int nlls_time_kernels(nlls_ctx* ctx, int which, int reps, int flush_l2, double* 
     double lambda = ctx->lambda;
     if (lambda == 0) lambda = 1e-3;
     double total = 0.0;
+    const int keep_cam = ctx->cam_part_vars;
+    if (which != NLLS_TIME_LIN_LOOP) ctx->cam_part_vars = -1;
     for (int r = 0; r < reps; ++r) {
         if (flush_l2) CK(cudaMemsetAsync(ctx->d_flush, r & 0xff, ctx->flush_bytes, ctx->st));
         CK(cudaEventRecord(ctx->ev_t0, ctx->st));
@@ -1859,10 +1915,11 @@ int nlls_time_kernels(nlls_ctx* ctx, int which, int reps, int flush_l2, double* 
             else return NLLS_ERR_INVALID;
         } else
         switch (which) {
-            case NLLS_TIME_LINEARIZE: TRY(DISPATCH(ctx, launch_linearize, ctx, true, true)); break;
-            case NLLS_TIME_LIN_POINT: TRY(DISPATCH(ctx, launch_linearize, ctx, true, false)); break;
-            case NLLS_TIME_LIN_CAM: TRY(DISPATCH(ctx, launch_linearize, ctx, false, true)); break;
-            case NLLS_TIME_COST: TRY(DISPATCH(ctx, launch_cost, ctx, ctx->cur, SC_COST_TRY)); break;
+            case NLLS_TIME_LINEARIZE: TRY(DISPATCH(ctx, launch_linearize, ctx, true, 1)); break;
+            case NLLS_TIME_LIN_POINT: TRY(DISPATCH(ctx, launch_linearize, ctx, true, 0)); break;
+            case NLLS_TIME_LIN_CAM: TRY(DISPATCH(ctx, launch_linearize, ctx, false, 1)); break;
+            case NLLS_TIME_LIN_LOOP: TRY(DISPATCH(ctx, launch_linearize, ctx, true, 2)); break;
+            case NLLS_TIME_COST: TRY(DISPATCH(ctx, launch_cost, ctx, ctx->cur, SC_COST_TRY, ctx->d_cam_part2)); break;
             case NLLS_TIME_SCHUR: TRY(DISPATCH(ctx, launch_schur, ctx, lambda)); break;
             case NLLS_TIME_SOLVE_REDUCED: TRY(DISPATCH(ctx, launch_schur, ctx, lambda)); CK(cudaEventRecord(ctx->ev_t0, ctx->st)); TRY(launch_reduced_solve(ctx)); break;
             case NLLS_TIME_BACKSUB: TRY(DISPATCH(ctx, launch_update, ctx)); break;
@@ -1877,6 +1934,7 @@ int nlls_time_kernels(nlls_ctx* ctx, int which, int reps, int flush_l2, double* 
         total += ms;
     }
     *ms_per_call = total / reps;
+    ctx->cam_part_vars = (which == NLLS_TIME_LIN_LOOP || which == NLLS_TIME_COST || which == NLLS_TIME_LIN_POINT) ? keep_cam : -1;
     return NLLS_OK;
 }
 

@@ -12,9 +12,9 @@
 //   ldl_diag_kernel  one CTA per column J of the level: in-register LDL' of the 72 x 72 tile, Linv_J = L_JJ^-1 obtained by
 //                    mirroring the row operations on an identity, and the forward substitution y_J = L_JJ^-1 b_J carried as
 //                    an extra column.  One barrier per pivot; the pivot reciprocal is computed one step ahead by its owner.
-//   ldl_off_kernel   two CTAs per tile (I, J), I > J:  L_IJ = T_IJ Linv_J' D_J^-1 (a triangular GEMM), then the right-hand
-//                    side push  b_I -= L_IJ y_J
-//   ldl_upd_kernel   two CTAs per pair (a >= b) of rows of J:  T_{ab} -= (L_aJ D_J) L_bJ'  (FP64 RED into the target tile)
+//   ldl_off_kernel   three CTAs per tile (I, J), I > J:  L_IJ = T_IJ Linv_J' D_J^-1 (a triangular GEMM)
+//   ldl_upd_kernel   three CTAs per TARGET tile (a, b) of the level:  T_{ab} -= sum_J (L_aJ D_J) L_bJ' in a fixed order, written once
+//                    by its owner (no reductions: the solve is bitwise reproducible); diagonal targets also push b_I -= L_IJ y_J
 // then the backward sweep ldl_bwd_kernel, one launch per level in reverse order.
 //
 // Measured on B200 (scripts/ubench/fp64_lat.cu): DFMA 8.4 cycles dependent / 2.07 cycles issue per warp and SM sub-partition,
@@ -39,7 +39,8 @@ struct RedSolveLists {        // device pointers for the backward sweep
 };
 
 struct RedTask { int tile, dtile, col, row; };        // diag: (tile, -, J, -); off-diagonal: (tile (I,J), diag tile of J, J, I)
-struct RedUpd { int a, b, dk, target; };              // tiles L_aJ, L_bJ, diagonal tile of J, target tile (a, b)
+struct RedUpd { int a, b, dk, col; };                 // tiles L_aJ, L_bJ, diagonal tile of J, column J (its y_J feeds the right-hand side push)
+struct RedTarget { int target, u0, u1, row; };        // target tile, its updates [u0, u1) in a fixed order, block row I of a DIAGONAL target (-1 otherwise)
 
 // reciprocal to ~1 ulp: MUFU seed + two Newton steps
 __device__ __forceinline__ double rcp_fast(double d) {
@@ -330,17 +331,14 @@ __global__ void __launch_bounds__(GEMM_THREADS) ldl_off_kernel(double* __restric
     double* As = sm;                  // T_IJ   [k][i]
     double* Bs = sm + ST * LDT;       // Linv_J [k][c]
     double* Ds = Bs + ST * LDT;       // [ST] 1 / D_J
-    double* ys = Ds + ST;             // [ST] y_J
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const RedTask tk = tasks[blockIdx.x / GEMM_CTAS];
     const int I = GEMM_CTAS * (blockIdx.x % GEMM_CTAS) + w;      // row block of this warp
     double* T = S + (size_t)tk.tile * ST2;
     tile_to_smem_ld<GEMM_THREADS>(As, T);
     tile_to_smem_ld<GEMM_THREADS>(Bs, Linv + (size_t)tk.col * ST2);
-    if (tid < ST) {
-        Ds[tid] = rcp_fast(S[(size_t)tk.dtile * ST2 + (size_t)(ST + 1) * tid]);
-        ys[tid] = xp[(size_t)tk.col * ST + tid];
-    }
+    if (tid < ST) Ds[tid] = rcp_fast(S[(size_t)tk.dtile * ST2 + (size_t)(ST + 1) * tid]);
+    (void)xp;
     cp_async_wait_all();
     __syncthreads();
     const int fr = lane >> 2, fk = lane & 3;
@@ -358,66 +356,79 @@ __global__ void __launch_bounds__(GEMM_THREADS) ldl_off_kernel(double* __restric
             dmma884(c0[cb], c1[cb], a, bp[ks * 4 * LDT + 8 * cb]);
         }
     }
-    // scale by 1 / d_c, store L_IJ, and push the right-hand side:  b_I -= L_IJ y_J
-    double pr = 0.0;
+    // scale by 1 / d_c and store L_IJ  (the right-hand side push b_I -= L_IJ y_J is done by the update kernel's diagonal targets,
+    // which own block row I for the level: no reductions, so the solve is deterministic)
 #pragma unroll
     for (int cb = 0; cb < NBLK; ++cb) {
         const int c = 8 * cb + 2 * fk;
-        const double x0 = c0[cb] * Ds[c], x1 = c1[cb] * Ds[c + 1];
-        T[(size_t)ST * c + 8 * I + fr] = x0;
-        T[(size_t)ST * (c + 1) + 8 * I + fr] = x1;
-        pr = fma(x0, ys[c], pr);
-        pr = fma(x1, ys[c + 1], pr);
+        T[(size_t)ST * c + 8 * I + fr] = c0[cb] * Ds[c];
+        T[(size_t)ST * (c + 1) + 8 * I + fr] = c1[cb] * Ds[c + 1];
     }
-    pr += __shfl_xor_sync(0xffffffffu, pr, 1);
-    pr += __shfl_xor_sync(0xffffffffu, pr, 2);
-    if (fk == 0) atomicAdd(xp + (size_t)tk.row * ST + 8 * I + fr, -pr);
 }
 
 // ---------------------------------------------------------------------------------------------------
-// Update  T_{ab} -= (L_aJ D_J) L_bJ'  for one pair of rows of column J; results are subtracted from the target tile with FP64
-// reductions (several columns of a level can hit the same tile).
+// Update, one CTA triple per TARGET tile of the level:  T_{ab} -= sum_J (L_aJ D_J) L_bJ'  over the target's updates in a fixed
+// order, accumulated in registers and subtracted once (owner-writes: several columns of a level hit the same tile; round 1 added
+// them with FP64 reductions, which made the solve depend on scheduling).  Diagonal targets (a == b, block row I) also push the
+// right-hand side  b_I -= sum_J L_IJ y_J  — every off-diagonal tile (I, J) of the level has exactly one such update.
 // ---------------------------------------------------------------------------------------------------
-constexpr size_t UPD_SMEM = (size_t)(2 * ST * LDT + ST) * sizeof(double);
+constexpr size_t UPD_SMEM = (size_t)(2 * ST * LDT + 2 * ST) * sizeof(double);
 
-__global__ void __launch_bounds__(GEMM_THREADS) ldl_upd_kernel(double* __restrict__ S, const RedUpd* __restrict__ upds) {
+__global__ void __launch_bounds__(GEMM_THREADS) ldl_upd_kernel(double* __restrict__ S, const RedUpd* __restrict__ upds, const RedTarget* __restrict__ targets,
+                                                               double* __restrict__ xp) {
     extern __shared__ __align__(16) double sm[];
     double* As = sm;                  // L_aJ [k][i]
     double* Bs = sm + ST * LDT;       // L_bJ [k][c]
     double* Ds = Bs + ST * LDT;       // [ST] D_J
+    double* ys = Ds + ST;             // [ST] y_J
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-    const RedUpd up = upds[blockIdx.x / GEMM_CTAS];
+    const RedTarget tg = targets[blockIdx.x / GEMM_CTAS];
     const int I = GEMM_CTAS * (blockIdx.x % GEMM_CTAS) + w;
-    const bool diag = up.b == up.a;
-    tile_to_smem_ld<GEMM_THREADS>(As, S + (size_t)up.a * ST2);
-    if (!diag) tile_to_smem_ld<GEMM_THREADS>(Bs, S + (size_t)up.b * ST2);
-    if (tid < ST) Ds[tid] = S[(size_t)up.dk * ST2 + (size_t)(ST + 1) * tid];
-    cp_async_wait_all();
-    __syncthreads();
-    const double* Bt = diag ? As : Bs;
     const int fr = lane >> 2, fk = lane & 3;
+    const bool diag = tg.row >= 0;
     const int ncb = diag ? I + 1 : NBLK;                      // diagonal targets: lower blocks only
     double c0[NBLK], c1[NBLK];
 #pragma unroll
     for (int cb = 0; cb < NBLK; ++cb) { c0[cb] = 0.0; c1[cb] = 0.0; }
-    const double* ap = As + fk * LDT + 8 * I + fr;
-    const double* bp = Bt + fk * LDT + fr;
+    double pr = 0.0;
+    for (int u = tg.u0; u < tg.u1; ++u) {
+        const RedUpd up = upds[u];
+        __syncthreads();             // the previous update is done with the staged tiles
+        tile_to_smem_ld<GEMM_THREADS>(As, S + (size_t)up.a * ST2);
+        if (!diag) tile_to_smem_ld<GEMM_THREADS>(Bs, S + (size_t)up.b * ST2);
+        if (tid < ST) {
+            Ds[tid] = S[(size_t)up.dk * ST2 + (size_t)(ST + 1) * tid];
+            if (diag) ys[tid] = xp[(size_t)up.col * ST + tid];
+        }
+        cp_async_wait_all();
+        __syncthreads();
+        const double* Bt = diag ? As : Bs;
+        const double* ap = As + fk * LDT + 8 * I + fr;
+        const double* bp = Bt + fk * LDT + fr;
 #pragma unroll
-    for (int ks = 0; ks < ST / 4; ++ks) {
-        const double a = ap[ks * 4 * LDT] * Ds[4 * ks + fk];
+        for (int ks = 0; ks < ST / 4; ++ks) {
+            const double araw = ap[ks * 4 * LDT];
+            const double a = araw * Ds[4 * ks + fk];
+            if (diag) pr = fma(araw, ys[4 * ks + fk], pr);
 #pragma unroll
-        for (int cb = 0; cb < NBLK; ++cb) {
-            if (cb >= ncb) continue;
-            dmma884(c0[cb], c1[cb], a, bp[ks * 4 * LDT + 8 * cb]);
+            for (int cb = 0; cb < NBLK; ++cb) {
+                if (cb >= ncb) continue;
+                dmma884(c0[cb], c1[cb], a, bp[ks * 4 * LDT + 8 * cb]);
+            }
         }
     }
-    double* T = S + (size_t)up.target * ST2;
+    double* T = S + (size_t)tg.target * ST2;
 #pragma unroll
     for (int cb = 0; cb < NBLK; ++cb) {
         if (cb >= ncb) continue;
         const int c = 8 * cb + 2 * fk;
-        atomicAdd(T + (size_t)ST * c + 8 * I + fr, -c0[cb]);
-        atomicAdd(T + (size_t)ST * (c + 1) + 8 * I + fr, -c1[cb]);
+        T[(size_t)ST * c + 8 * I + fr] -= c0[cb];
+        T[(size_t)ST * (c + 1) + 8 * I + fr] -= c1[cb];
+    }
+    if (diag) {
+        pr += __shfl_xor_sync(0xffffffffu, pr, 1);
+        pr += __shfl_xor_sync(0xffffffffu, pr, 2);
+        if (fk == 0) xp[(size_t)tg.row * ST + 8 * I + fr] -= pr;
     }
 }
 
@@ -472,6 +483,76 @@ __global__ void __launch_bounds__(RED_THREADS) ldl_bwd_kernel(const double* __re
     }
     __syncthreads();
     if (tid < ST) x[(size_t)J * ST + tid] = part[tid] + part[ST + tid];
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Backward sweep as ONE dataflow launch instead of one launch per level (12 dependent launches of ~11 us on the Venice shape):
+// CTA b walks the columns order[b], order[b + G], ... (order = levels from last to first, so everything a column needs comes
+// earlier in the list) and, instead of a kernel boundary, waits for the flag of every x_I it pulls.  All G <= #SM CTAs are
+// resident, and a column only waits for columns that precede it in the list, so the walk cannot deadlock.
+// flags[] is cleared (memset node) before the launch; flags[J] = 1 once x_J is in global memory.
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void wait_flag(const int* f) {
+    while (*reinterpret_cast<const volatile int*>(f) == 0) { __nanosleep(20); }
+    __threadfence();
+}
+__global__ void __launch_bounds__(RED_THREADS) ldl_bwd_flow_kernel(const double* __restrict__ S, const double* __restrict__ Linv, RedSolveLists t,
+                                                                   const int* __restrict__ order, int ncols, int* __restrict__ flags, double* __restrict__ x) {
+    extern __shared__ __align__(16) double sm[];
+    double* Ts = sm;                 // [2][ST2]
+    double* xi = sm + 2 * ST2;       // [2][ST]
+    double* part = xi + 2 * ST;      // [2][ST]
+    double* w = part + 2 * ST;       // [ST]
+    const int tid = threadIdx.x, c = tid % ST, h = tid / ST;
+    for (int pos = blockIdx.x; pos < ncols; pos += gridDim.x) {
+        const int J = order[pos];
+        const int q0 = t.colptr[J], q1 = t.colptr[J + 1];
+        double acc = 0.0;
+        __syncthreads();             // the previous column of this CTA is done with the buffers
+        if (q0 < q1) {
+            tile_to_smem<RED_THREADS>(Ts, S + (size_t)t.col_tile[q0] * ST2);      // the tiles do not depend on other columns: in flight while we wait
+            if (tid == 0) wait_flag(flags + t.col_row[q0]);
+            __syncthreads();
+            if (tid < ST) xi[tid] = __ldcg(x + (size_t)t.col_row[q0] * ST + tid);
+        }
+        for (int q = q0; q < q1; ++q) {
+            const int st = (q - q0) & 1;
+            cp_async_wait_all();
+            __syncthreads();
+            if (q + 1 < q1) {
+                tile_to_smem<RED_THREADS>(Ts + (st ^ 1) * ST2, S + (size_t)t.col_tile[q + 1] * ST2);
+                if (tid == 0) wait_flag(flags + t.col_row[q + 1]);
+            }
+            const double* M = Ts + st * ST2 + (size_t)ST * c + (ST / 2) * h;
+            const double* xv = xi + st * ST + (ST / 2) * h;
+#pragma unroll 12
+            for (int i = 0; i < ST / 2; ++i) acc = fma(M[i], xv[i], acc);
+            if (q + 1 < q1) {
+                __syncthreads();     // thread 0 has seen the flag
+                if (tid < ST) xi[(st ^ 1) * ST + tid] = __ldcg(x + (size_t)t.col_row[q + 1] * ST + tid);
+            }
+        }
+        __syncthreads();
+        tile_to_smem<RED_THREADS>(Ts, Linv + (size_t)J * ST2);
+        part[h * ST + c] = acc;
+        cp_async_wait_all();
+        __syncthreads();
+        if (tid < ST) w[tid] = __ldcg(x + (size_t)J * ST + tid) / S[(size_t)t.diag_tile[J] * ST2 + (size_t)(ST + 1) * tid] - (part[tid] + part[ST + tid]);
+        __syncthreads();
+        {   // x_J[c] = sum_{i >= c} Linv[i][c] w[i]
+            const double* M = Ts + (size_t)ST * c + (ST / 2) * h;
+            const double* wv = w + (ST / 2) * h;
+            double s = 0.0;
+#pragma unroll 12
+            for (int i = 0; i < ST / 2; ++i) s = fma(((ST / 2) * h + i >= c) ? M[i] : 0.0, wv[i], s);
+            part[h * ST + c] = s;
+        }
+        __syncthreads();
+        if (tid < ST) x[(size_t)J * ST + tid] = part[tid] + part[ST + tid];
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) atomicExch(flags + J, 1);
+    }
 }
 
 // natural <-> permuted tile numbering of the right-hand side / solution
