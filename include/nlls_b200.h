@@ -64,7 +64,7 @@ enum nlls_robust {
     NLLS_ROBUST_SCALED = 16        /* OR-ed in: Scaled(kernel, height) kparams: w, height   */
 };
 
-/* NLLSOptions (src/structs.jl:22-35). iterator: NLLS_ITER_LM or NLLS_ITER_NEWTON (the others return NLLS_ERR_UNSUPPORTED). */
+/* NLLSOptions (src/structs.jl:22-35). iterator: all four of src/structs.jl:4 (Dogleg and gradient descent: BA residuals, one rank). */
 enum nlls_iterator { NLLS_ITER_NEWTON = 0, NLLS_ITER_LM = 1, NLLS_ITER_DOGLEG = 2, NLLS_ITER_GD = 3 };
 typedef struct nlls_options {
     double reldcost;
@@ -116,6 +116,14 @@ int nlls_set_variables(nlls_ctx* ctx, int vartype, const double* aos, int64_t n,
  * In a multi-rank run each rank passes only the costs of the points it owns. */
 int nlls_set_costs(nlls_ctx* ctx, int restype, const void* aos, int64_t stride_bytes, int64_t n,
                    int robust, const double* kparams, int nkparams, int64_t kernel_var);
+/* optimize!(problem, options, unfixed) (src/optimize.jl:5-20): unfixed[i] != 0 <=> variable i + 1 is optimised, for i < n; variables
+ * beyond n are unfixed; n == 0 (or unfixed == NULL) clears the mask.  Fixed variables keep their values, contribute to the cost, and are
+ * left out of linsystem.b / x (nlls_dof, nlls_get_gradient, nlls_get_step); the Hessian read-back is not available under a mask. */
+int nlls_set_unfixed(nlls_ctx* ctx, const uint8_t* unfixed, int64_t n);
+/* optimizesingles!(problem, options, type) (src/optimize.jl:60-76,183-205): every variable of `vartype` on its own, all others fixed,
+ * over the costs that depend on it — a batch of independent small LM solves.  Registered for the point type (NLLS_VAR_EUCLID3) of the
+ * bundle-adjustment residuals.  iterations (may be NULL): summed iteration count. */
+int nlls_optimize_singles(nlls_ctx* ctx, int vartype, const nlls_options* opts, int64_t* iterations);
 /* makesymmvls (src/linearsystem.jl:91-124) + reordercostsforschur! (src/problem.jl:177-199): builds the
  * point-major collision-free scatter layout and uploads everything.  Called implicitly if needed. */
 int nlls_prepare(nlls_ctx* ctx);

@@ -379,18 +379,43 @@ def printoutcallback(cost, problem, data, iteratedata):                   # src/
 # ------------------------------------------------------------------------------------------------
 # optimize!
 # ------------------------------------------------------------------------------------------------
+def convertunfixed(unfixed, problem):
+    """src/optimize.jl:19-22: nothing -> all; a type -> the variables of that type; an integer -> that variable alone; else as given."""
+    if unfixed is None:
+        return None
+    n = len(problem.variables)
+    if isinstance(unfixed, type):
+        return np.array([isinstance(v, unfixed) for v in problem.variables], dtype=np.uint8)
+    if isinstance(unfixed, (int, np.integer)) and not isinstance(unfixed, bool):
+        m = np.zeros(n, dtype=np.uint8)
+        m[int(unfixed) - 1] = 1
+        return m
+    m = np.asarray(unfixed).astype(np.uint8)
+    assert len(m) == n, "unfixed must have one entry per variable"
+    return m
+
+
+def optimizesingles(problem, options=None, vartype=None):
+    """optimizesingles!(problem, options, type)  (src/optimize.jl:60-76): every variable of `vartype` optimised on its own with all
+    other variables fixed.  A batched CUDA kernel exists for the 3-D point type of the bundle-adjustment residuals; other types raise."""
+    options = options or NLLSOptions()
+    ctx = problem.context()
+    ctx.set_unfixed(None)
+    sample = next((v for v in problem.variables if isinstance(v, vartype)), None) if isinstance(vartype, type) else None
+    vt = _vartype(sample)[0] if sample is not None else vartype
+    ctx.optimize_singles(vt, options.c())
+    problem._pull_variables(0)
+
+
 def optimize(problem, options=None, unfixed=None, callback=nullcallback):
     """optimize!(problem, options, unfixed, callback)::NLLSResult  (src/optimize.jl:57).
     The LM loop runs in the CUDA library; variables are updated in place.  With a callback the loop is driven from
     here so that callback(cost, problem, data, iteratedata) -> (cost, terminate) runs exactly where the reference
     calls it (src/optimize.jl:128)."""
     options = options or NLLSOptions()
-    if unfixed is not None:
-        raise capi.NLLSError(capi.ERR_UNSUPPORTED, "`unfixed` masks are not implemented (all variables are optimised)")
-    if options.iterator not in (levenbergmarquardt, newton):
-        raise capi.NLLSError(capi.ERR_UNSUPPORTED, "only the Levenberg-Marquardt and Newton iterators are implemented")
     assert len(problem.variables) > 0
     ctx = problem.context()
+    ctx.set_unfixed(convertunfixed(unfixed, problem))
     copts = options.c()
     if callback is nullcallback:
         res = ctx.optimize(copts)

@@ -44,6 +44,11 @@ struct DevProblem {
     const int* tile_pos;   // natural camera tile -> position in the elimination order
     int NT;
     int s_tiled;
+    // optimize!(problem, options, unfixed): per camera / point 1 = FIXED (nullptr: none).  A fixed variable keeps its place in the
+    // system but is frozen: its diagonal block is the identity, its gradient and every cross block with it are zero, so its step
+    // is exactly zero and the other variables see the reference's reduced system (src/cost.jl:36-47, src/linearsystem.jl:93-102).
+    const unsigned char* fixA;
+    const unsigned char* fixB;
 };
 
 // ---------------------------------------------------------------------------------------------------
@@ -118,6 +123,8 @@ __global__ void __launch_bounds__(TO) lin_point_kernel(DevProblem p, const int4*
             double rho, d1, d2;
             robustifydcost(p.rk, s, rho, d1, d2);                     //                   src/residual.jl:78
             c = 0.5 * rho;                                            //                   src/residual.jl:110
+            const bool fpt = p.fixB != nullptr && p.fixB[ptg];
+            const bool fcross = fpt || (p.fixA != nullptr && p.fixA[cam]);
             double gc[DC], gp[3];
 #pragma unroll
             for (int a = 0; a < DC; ++a) gc[a] = jtr<R>(Jc, r, a);                        // g = J' r   :73   (explicit FMAs: -fmad=false)
@@ -132,7 +139,7 @@ __global__ void __launch_bounds__(TO) lin_point_kernel(DevProblem p, const int4*
                     double h = jtj_pc<R>(Jp, Jc, b, a);                                // H = J' J   :74
                     if (d1 != 1.0) h *= d1;                                            // IRLS       :91-93
                     if (d2 != 0.0) h = fma(td2 * gp[b], gc[a], h);                     // Triggs     :95-97
-                    w[b + 3 * a] = h;
+                    w[b + 3 * a] = fcross ? 0.0 : h;
                 }
             // 128-bit shared stores at the block's own parity
             const int off = WB * tid + 9 * pl;
@@ -153,10 +160,10 @@ __global__ void __launch_bounds__(TO) lin_point_kernel(DevProblem p, const int4*
                     double h = fma(Jp[1][b], Jp[1][b2], Jp[0][b] * Jp[0][b2]);
                     if (d1 != 1.0) h *= d1;
                     if (d2 != 0.0) h = fma(td2 * gp[b], gp[b2], h);
-                    s_pc[9 * tid + (q++)] = h;
+                    s_pc[9 * tid + (q++)] = fpt ? 0.0 : h;
                 }
 #pragma unroll
-            for (int b = 0; b < 3; ++b) s_pc[9 * tid + 6 + b] = (d1 != 1.0) ? gp[b] * d1 : gp[b];  // g *= dc  :99-101
+            for (int b = 0; b < 3; ++b) s_pc[9 * tid + 6 + b] = fpt ? 0.0 : ((d1 != 1.0) ? gp[b] * d1 : gp[b]);  // g *= dc  :99-101
         }
         // level-2 loads of tile k+1 (their addresses arrived one iteration ago)
         double ncv[R::NC], nX[3];
@@ -181,6 +188,7 @@ __global__ void __launch_bounds__(TO) lin_point_kernel(DevProblem p, const int4*
 #pragma unroll
                 for (int e = 0; e < 4; ++e) v += a[e];
             }
+            if (p.fixB != nullptr && p.fixB[pt0 + q]) v = (i == 0 || i == 3 || i == 5) ? 1.0 : 0.0;   // frozen point: V_p = I, g_p = 0
             if (i < 6) {   // lower-triangle element i of V_p -> its position(s) in the full column-major 3 x 3 block
                 double* V = s_base + WB * j1 + 9 * q;
                 const int pa = (0x854210 >> (4 * i)) & 15, pb = (0x874630 >> (4 * i)) & 15;
@@ -391,11 +399,12 @@ __global__ void cam_finalize_kernel(DevProblem p, const double* __restrict__ par
         int a2 = 0, rem = e;
         while (rem >= DC - a2) { rem -= DC - a2; ++a2; }
         const int a = a2 + rem;
+        if (p.fixA != nullptr && p.fixA[cam]) s = (a == a2) ? 1.0 : 0.0;   // frozen camera: U_c = I
         double* U = p.H + (size_t)DC * DC * cam;
         U[a + DC * a2] = s;
         U[a2 + DC * a] = s;
     } else {
-        p.g[(size_t)DC * cam + (e - NL)] = s;
+        p.g[(size_t)DC * cam + (e - NL)] = (p.fixA != nullptr && p.fixA[cam]) ? 0.0 : s;
     }
 }
 
@@ -416,10 +425,10 @@ __global__ void maxdiag_kernel(DevProblem p, unsigned long long* out) {
     double v = 0.0;
     if (idx < nc) {
         const long long cam = idx / DC; const int a = (int)(idx - cam * DC);
-        v = fabs(p.H[(size_t)DC * DC * cam + a + DC * a]);
+        v = (p.fixA != nullptr && p.fixA[cam]) ? 0.0 : fabs(p.H[(size_t)DC * DC * cam + a + DC * a]);
     } else if (idx < nc + np) {
         const long long k = idx - nc; const long long pt = k / 3; const int b = (int)(k - pt * 3);
-        v = fabs(p.H[(size_t)p.hB + (size_t)3 * DC * p.obs_start[pt + 1] + (size_t)9 * pt + 4 * b]);
+        v = (p.fixB != nullptr && p.fixB[pt]) ? 0.0 : fabs(p.H[(size_t)p.hB + (size_t)3 * DC * p.obs_start[pt + 1] + (size_t)9 * pt + 4 * b]);
     }
     v = warp_nanmax(v);
     if ((threadIdx.x & 31) == 0) atomicMax(out, (unsigned long long)__double_as_longlong(v));  // non-negative doubles order like integers
@@ -1086,6 +1095,16 @@ __global__ void __launch_bounds__(128) cam_update_kernel(DevProblem p, const dou
     }
 }
 
+// gathered[r * 5 + i], r < nranks: the five per-try scalars of every rank -> out[0] = sum of the costs, out[1] = NaN-propagating max
+// of max|x_p|, out[2..4] = sums, all in rank order (lane i owns scalar i)
+__global__ void combine_scalars_kernel(const double* __restrict__ gathered, int nranks, double* __restrict__ out) {
+    const int i = threadIdx.x;
+    if (i >= 5) return;
+    double v = gathered[i];
+    for (int r = 1; r < nranks; ++r) v = (i == 1) ? nanmax(v, gathered[r * 5 + i]) : v + gathered[r * 5 + i];
+    out[i] = v;
+}
+
 // CTA k reduces partials[k * n .. (k+1) * n) in a fixed order into out[k]; k == 0 is a NaN-propagating max, the others sums
 // (the {max|x|, sum x^2, x'Hx, g.x} quadruple of the step statistics).
 __global__ void __launch_bounds__(256) reduce_stats_kernel(const double* __restrict__ partials, int n, double* __restrict__ out) {
@@ -1100,3 +1119,5 @@ __global__ void __launch_bounds__(256) reduce_stats_kernel(const double* __restr
 }  // namespace nlls
 
 #include "schur5.cuh"
+#include "singles.cuh"
+#include "iterators.cuh"

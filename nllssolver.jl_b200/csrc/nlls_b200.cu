@@ -37,6 +37,7 @@ struct NcclApi {
     int (*CommDestroy)(ncclComm_t) = nullptr;
     int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     int (*Broadcast)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
     int (*GroupStart)() = nullptr;
     int (*GroupEnd)() = nullptr;
     const char* (*GetErrorString)(int) = nullptr;
@@ -50,10 +51,11 @@ struct NcclApi {
         CommDestroy = (int (*)(ncclComm_t))dlsym(h, "ncclCommDestroy");
         AllReduce = (int (*)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t))dlsym(h, "ncclAllReduce");
         Broadcast = (int (*)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t))dlsym(h, "ncclBroadcast");
+        AllGather = (int (*)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t))dlsym(h, "ncclAllGather");
         GroupStart = (int (*)())dlsym(h, "ncclGroupStart");
         GroupEnd = (int (*)())dlsym(h, "ncclGroupEnd");
         GetErrorString = (const char* (*)(int))dlsym(h, "ncclGetErrorString");
-        return GetUniqueId && CommInitRank && CommDestroy && AllReduce && Broadcast && GroupStart && GroupEnd;
+        return GetUniqueId && CommInitRank && CommDestroy && AllReduce && Broadcast && AllGather && GroupStart && GroupEnd;
     }
 };
 NcclApi g_nccl;
@@ -94,6 +96,10 @@ struct nlls_ctx {
     std::vector<int64_t> h_cam_g, h_pt_g;  // global 1-based indices per cost, storage order
     std::vector<double> h_z;               // 2 per cost
     bool prepared = false;
+    std::vector<unsigned char> h_unfixed;   // optimize!(…, unfixed): by 0-based variable position; empty = all unfixed
+    bool masked = false;                    // some variable of this problem is fixed
+    std::vector<unsigned char> h_fixA, h_fixB;
+    unsigned char *d_fixA = nullptr, *d_fixB = nullptr;
 
     // ---- layout (host copies kept for read-back)
     int vtA = 0, vtB = 0, DC = 0, NC = 0, CS = 0, BS = 3;   // BS: stored doubles per variable of the second class (3: points, 1: scalar means)
@@ -123,7 +129,7 @@ struct nlls_ctx {
     double *d_cost_part = nullptr, *d_step_part = nullptr, *d_cam_part = nullptr, *d_cam_part2 = nullptr, *d_camstat_part = nullptr;
     int cam_part_vars = -1;          // variable buffer (index into d_A / d_B) whose camera-pass partials are in d_cam_part, -1: none
     int cost_pointmajor = 0;
-    double *d_scal = nullptr, *h_scal = nullptr;
+    double *d_scal = nullptr, *h_scal = nullptr, *d_gather = nullptr;
     void* d_flush = nullptr;
     size_t flush_bytes = 0;
     int use_tma = 1;
@@ -184,6 +190,9 @@ struct nlls_ctx {
     uint64_t starttime = 0, stoptime = 0, t_init = 0, t_cost = 0, t_grad = 0, t_solver = 0;
     bool lm_active = false;
     bool have_best = false;
+    // Dogleg / gradient descent (src/iterators.jl:30-46,177-185)
+    double trustradius = 0.0, stepsize = 1.0;
+    double *d_cauchy = nullptr, *d_vec_part = nullptr;
     int lm_phase = 0;   // 0: nlls_lm_iterate is next, 1: nlls_lm_advance is next
 };
 
@@ -243,6 +252,7 @@ DevProblem devproblem(const nlls_ctx* c) {
     p.use_tma = c->use_tma;
     p.schur_stride = c->schur_stride;
     p.tile_id = c->d_tile_id; p.tile_pos = c->d_pos; p.NT = c->NT; p.s_tiled = c->s_tiled;
+    p.fixA = c->masked ? c->d_fixA : nullptr; p.fixB = c->masked ? c->d_fixB : nullptr;
     return p;
 }
 
@@ -358,7 +368,7 @@ int launch_linearize(nlls_ctx* ctx, bool do_point = true, int do_cam = 1) {
 // the try is accepted; part == d_cam_part2: nlls_cost(), which must not disturb them.  Same kernel, same reduction tree in both
 // cases, so cost(problem) == bestcost exactly (test/optimizeba.jl:67).
 template <class R>
-int launch_cost(nlls_ctx* ctx, int which, int slot, double* part = nullptr) {
+int launch_cost(nlls_ctx* ctx, int which, int slot, double* part = nullptr, bool reduce = true) {
     DevProblem p = devproblem(ctx);
     constexpr int NU = R::DC * (R::DC + 1) / 2 + R::DC;
     if (!part) part = ctx->d_cam_part;
@@ -376,7 +386,7 @@ int launch_cost(nlls_ctx* ctx, int which, int slot, double* part = nullptr) {
         if (part == ctx->d_cam_part) ctx->cam_part_vars = which;   // the camera blocks of these variables are now in d_cam_part
     }
     CK(cudaGetLastError());
-    TRY(allreduce(ctx, ctx->d_scal + slot, 1, ncclSum));
+    if (reduce) TRY(allreduce(ctx, ctx->d_scal + slot, 1, ncclSum));
     return NLLS_OK;
 }
 
@@ -523,12 +533,18 @@ int launch_update(nlls_ctx* ctx) {
     reduce_stats_kernel<<<4, 256, 0, ctx->st>>>(ctx->d_step_part, ctx->ntiles > 0 ? bg : 0, ctx->d_scal + SC_P_MAX); ctx->launches++;
     reduce_stats_kernel<<<4, 256, 0, ctx->st>>>(ctx->d_camstat_part, cg, ctx->d_scal + SC_C_MAX); ctx->launches++;
     CK(cudaGetLastError());
-    if (ctx->nranks > 1) {
-        CKN(g_nccl.GroupStart());
-        CKN(g_nccl.AllReduce(ctx->d_scal + SC_P_MAX, ctx->d_scal + SC_P_MAX, 1, ncclFloat64, ncclMax, ctx->comm, ctx->st));
-        CKN(g_nccl.AllReduce(ctx->d_scal + SC_P_SQ, ctx->d_scal + SC_P_SQ, 3, ncclFloat64, ncclSum, ctx->comm, ctx->st));
-        CKN(g_nccl.GroupEnd());
-    }
+    return NLLS_OK;
+}
+
+// The rank-local scalars of a try — cost(varnext) and the point rows' step statistics {max|x|, sum x^2, x'Hx, g.x}, five
+// consecutive slots — are combined over the ranks with ONE all-gather and a tiny kernel that adds them in rank order (the same
+// order on every rank, so the replicated accept / reject decision is taken on identical bits).  Round 1 used three all-reduces
+// per try here; at 8 ranks their launch latency was a quarter of the step.
+int exchange_try_scalars(nlls_ctx* ctx) {
+    if (ctx->nranks <= 1) return NLLS_OK;
+    CKN(g_nccl.AllGather(ctx->d_scal + SC_COST_TRY, ctx->d_gather, 5, ncclFloat64, ctx->comm, ctx->st));
+    combine_scalars_kernel<<<1, 32, 0, ctx->st>>>(ctx->d_gather, ctx->nranks, ctx->d_scal + SC_COST_TRY); ctx->launches++;
+    CK(cudaGetLastError());
     return NLLS_OK;
 }
 
@@ -588,6 +604,128 @@ int adapt_solve_update(nlls_ctx* ctx, double lambda) {
      : (ctx)->restype == NLLS_RES_PINHOLE_BA ? fn<PinholeBA>(__VA_ARGS__)                      \
                                              : (int)NLLS_ERR_NO_KERNEL)
 
+// ---- vector helpers of the Dogleg / gradient-descent iterators (single rank) -----------------------------------------
+int fetch_scalars(nlls_ctx* ctx);
+constexpr int VEC_GRID = 592;
+int vec_dot(nlls_ctx* ctx, const double* a, const double* b, double* out) {   // deterministic: fixed grid, ordered reduction
+    dot_kernel<<<VEC_GRID, 256, 0, ctx->st>>>(a, b, (long long)ctx->dof, ctx->d_vec_part); ctx->launches++;
+    reduce_partials_kernel<<<1, 1024, 0, ctx->st>>>(ctx->d_vec_part, VEC_GRID, ctx->d_scal + SC_EXCH, 0); ctx->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(ctx->h_scal + SC_EXCH, ctx->d_scal + SC_EXCH, sizeof(double), cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    *out = ctx->h_scal[SC_EXCH];
+    return NLLS_OK;
+}
+int vec_axpby(nlls_ctx* ctx, double* x, double sx, const double* y, double sy) {
+    axpby_kernel<<<(unsigned)((ctx->dof + 255) / 256), 256, 0, ctx->st>>>(x, sx, y, sy, (long long)ctx->dof); ctx->launches++;
+    CK(cudaGetLastError());
+    return NLLS_OK;
+}
+template <class R>
+int vec_quadform(nlls_ctx* ctx, const double* v, double* out) {               // v' H v, undamped H  (fast_bAb)
+    DevProblem p = devproblem(ctx);
+    const int grid = (int)((ctx->nA + ctx->nB + 127) / 128);
+    quadform_kernel<R::DC><<<grid, 128, 0, ctx->st>>>(p, v, ctx->d_vec_part); ctx->launches++;
+    reduce_partials_kernel<<<1, 1024, 0, ctx->st>>>(ctx->d_vec_part, grid, ctx->d_scal + SC_EXCH, 0); ctx->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(ctx->h_scal + SC_EXCH, ctx->d_scal + SC_EXCH, sizeof(double), cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    *out = ctx->h_scal[SC_EXCH];
+    return NLLS_OK;
+}
+// update!(varnext, variables, linsystem) with the current d_x, then cost(varnext): returns cost, max|x|, |x|
+template <class R>
+int step_and_cost(nlls_ctx* ctx, double* cost, double* maxstep, double* normx) {
+    DevProblem p = devproblem(ctx);
+    const int grid = (int)((ctx->nA + ctx->nB + 127) / 128);
+    apply_step_kernel<R><<<grid, 128, 0, ctx->st>>>(p, ctx->d_x, ctx->d_A[ctx->cur], ctx->d_B[ctx->cur], ctx->d_A[ctx->nxt], ctx->d_B[ctx->nxt], ctx->d_vec_part); ctx->launches++;
+    reduce_partials_kernel<<<1, 1024, 0, ctx->st>>>(ctx->d_vec_part, grid, ctx->d_scal + SC_EXCH, 1); ctx->launches++;
+    reduce_partials_kernel<<<1, 1024, 0, ctx->st>>>(ctx->d_vec_part + grid, grid, ctx->d_scal + SC_EXCH + 1, 0); ctx->launches++;
+    CK(cudaGetLastError());
+    const uint64_t tc = now_ns();
+    TRY(launch_cost<R>(ctx, ctx->nxt, SC_COST_TRY));
+    CK(cudaMemcpyAsync(ctx->h_scal, ctx->d_scal, sizeof(double) * SC_COUNT, cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    ctx->t_cost += now_ns() - tc;
+    ctx->costcomputations += 1;
+    *cost = ctx->h_scal[SC_COST_TRY]; *maxstep = ctx->h_scal[SC_EXCH]; *normx = std::sqrt(ctx->h_scal[SC_EXCH + 1]);
+    return NLLS_OK;
+}
+
+// iterate!(::DoglegData)                                                     src/iterators.jl:48-113
+template <class R>
+int iterate_dogleg(nlls_ctx* ctx, nlls_iterinfo* info) {
+    const nlls_options& o = ctx->opts;
+    double gnorm2 = 0, bAb = 0;
+    const uint64_t ts = now_ns();
+    TRY(vec_dot(ctx, ctx->d_g, ctx->d_g, &gnorm2));                                             // :52
+    TRY(vec_quadform<R>(ctx, ctx->d_g, &bAb));
+    const double a = gnorm2 / (bAb + std::numeric_limits<double>::min());                       // :53
+    TRY(vec_axpby(ctx, ctx->d_cauchy, 0.0, ctx->d_g, -a));                                      // :54
+    const double alpha2 = a * a * gnorm2, alpha = std::sqrt(alpha2);                            // :55-56
+    if (ctx->trustradius == 0) ctx->trustradius = alpha;                                        // :57-60
+    double beta = 0;
+    if (alpha < ctx->trustradius) {                                                             // Newton step :61-66
+        TRY(launch_schur<R>(ctx, 0.0));
+        TRY(launch_reduced_solve(ctx));
+        TRY(launch_update<R>(ctx));
+        TRY(fetch_scalars(ctx));
+        beta = std::sqrt(ctx->h_scal[SC_P_SQ] + ctx->h_scal[SC_C_SQ]);
+        ctx->linearsolvers += 1;
+    }
+    ctx->t_solver += now_ns() - ts;
+    double cost_ = ctx->bestcost, maxstep = 0, normx = 0;                                       // :68
+    int64_t ntries = (alpha < ctx->trustradius) ? 1 : 0;   // linear solves of this iteration (what nlls_iterinfo.ntries counts)
+    while (true) {
+        double linear_approx;
+        if (!(alpha < ctx->trustradius)) {                                                      // first leg :71-74
+            TRY(vec_axpby(ctx, ctx->d_x, 0.0, ctx->d_cauchy, ctx->trustradius / alpha));
+            linear_approx = ctx->trustradius * (2 * alpha - ctx->trustradius) / (2 * a);
+        } else if (beta <= ctx->trustradius) {                                                  // full Newton step :77-79
+            linear_approx = cost_;
+        } else {                                                                                // second leg :80-95
+            double sq_leg = 0, c = 0;
+            TRY(vec_axpby(ctx, ctx->d_x, 1.0, ctx->d_cauchy, -1.0));
+            TRY(vec_dot(ctx, ctx->d_x, ctx->d_x, &sq_leg));
+            TRY(vec_dot(ctx, ctx->d_cauchy, ctx->d_x, &c));
+            const double trsq = ctx->trustradius * ctx->trustradius - alpha2;
+            double step = std::sqrt(c * c + sq_leg * trsq);
+            step = (c <= 0) ? (-c + step) / sq_leg : trsq / (c + step);
+            TRY(vec_axpby(ctx, ctx->d_x, step, ctx->d_cauchy, 1.0));
+            linear_approx = 0.5 * (a * (1 - step) * (1 - step) * gnorm2) + step * (2 - step) * cost_;
+        }
+        TRY(step_and_cost<R>(ctx, &cost_, &maxstep, &normx));                                   // :98-101
+        const double mu_ = (ctx->bestcost - cost_) / linear_approx;                             // :103
+        if (mu_ > 0.375) ctx->trustradius = std::max(ctx->trustradius, 3 * normx);              // :104-105
+        else if (mu_ < 0.125) ctx->trustradius *= 0.5;                                          // :106-107
+        if (!(cost_ > ctx->bestcost) || maxstep < o.dstep) break;                               // :110-113
+    }
+    ctx->cost = cost_; ctx->maxstep = maxstep;
+    if (info) { info->cost = cost_; info->lambda = ctx->trustradius; info->maxstep = maxstep; info->stepnorm = normx; info->ntries = ntries; info->accepted = !(cost_ > ctx->bestcost); }
+    return NLLS_OK;
+}
+
+// iterate!(::GradientDescentData)                                            src/iterators.jl:187-208
+template <class R>
+int iterate_gd(nlls_ctx* ctx, nlls_iterinfo* info) {
+    double cost_ = 0, maxstep = 0, normx = 0;
+    const int64_t ntries = 0;   // no linear solve in this iterator
+    TRY(vec_axpby(ctx, ctx->d_x, 0.0, ctx->d_g, -ctx->stepsize));                               // :190
+    TRY(step_and_cost<R>(ctx, &cost_, &maxstep, &normx));
+    while (cost_ > ctx->bestcost) {                                                             // :195
+        double coststep = 0;
+        TRY(vec_dot(ctx, ctx->d_x, ctx->d_g, &coststep));                                       // :197
+        const double costdiff = ctx->bestcost + coststep - cost_;                               // :198
+        ctx->stepsize *= 0.5 * coststep / costdiff;                                             // :200
+        TRY(vec_axpby(ctx, ctx->d_x, 0.0, ctx->d_g, -ctx->stepsize));                           // :202
+        TRY(step_and_cost<R>(ctx, &cost_, &maxstep, &normx));
+    }
+    ctx->stepsize *= 2;                                                                         // :207
+    ctx->cost = cost_; ctx->maxstep = maxstep;
+    if (info) { info->cost = cost_; info->lambda = ctx->stepsize; info->maxstep = maxstep; info->stepnorm = normx; info->ntries = ntries; info->accepted = 1; }
+    return NLLS_OK;
+}
+
 int fetch_scalars(nlls_ctx* ctx) {
     CK(cudaMemcpyAsync(ctx->h_scal, ctx->d_scal, sizeof(double) * SC_COUNT, cudaMemcpyDeviceToHost, ctx->st));
     CK(cudaStreamSynchronize(ctx->st));
@@ -605,15 +743,15 @@ int do_linearize(nlls_ctx* ctx, double* cost) {
     const int cam_mode = (ctx->cam_part_vars == ctx->cur) ? 2 : 1;
     TRY(DISPATCH(ctx, launch_linearize, ctx, true, cam_mode));
     ctx->cam_part_vars = -1;
-    if (ctx->nranks > 1) {  // camera blocks + camera gradient are sums over all ranks' observations
+    reduce_partials_kernel<<<1, 1024, 0, ctx->st>>>(ctx->d_cost_part, ctx->ntiles, ctx->d_scal + SC_COST_LIN, 0); ctx->launches++;
+    CK(cudaGetLastError());
+    if (ctx->nranks > 1) {  // camera blocks, camera gradient and the cost are sums over all ranks' observations: one grouped launch
         CKN(g_nccl.GroupStart());
         CKN(g_nccl.AllReduce(ctx->d_H, ctx->d_H, (size_t)ctx->DC * ctx->DC * ctx->nA, ncclFloat64, ncclSum, ctx->comm, ctx->st));
         CKN(g_nccl.AllReduce(ctx->d_g, ctx->d_g, (size_t)ctx->DC * ctx->nA, ncclFloat64, ncclSum, ctx->comm, ctx->st));
+        CKN(g_nccl.AllReduce(ctx->d_scal + SC_COST_LIN, ctx->d_scal + SC_COST_LIN, 1, ncclFloat64, ncclSum, ctx->comm, ctx->st));
         CKN(g_nccl.GroupEnd());
     }
-    reduce_partials_kernel<<<1, 1024, 0, ctx->st>>>(ctx->d_cost_part, ctx->ntiles, ctx->d_scal + SC_COST_LIN, 0); ctx->launches++;
-    CK(cudaGetLastError());
-    TRY(allreduce(ctx, ctx->d_scal + SC_COST_LIN, 1, ncclSum));
     TRY(fetch_scalars(ctx));
     if (cost) *cost = ctx->h_scal[SC_COST_LIN];
     return NLLS_OK;
@@ -632,9 +770,9 @@ int enqueue_try(nlls_ctx* ctx, double lambda) {
     TRY(launch_reduced_solve(ctx));
     TRY(DISPATCH(ctx, launch_update, ctx));
     CK(cudaEventRecord(ctx->ev_c0, ctx->st));
-    TRY(DISPATCH(ctx, launch_cost, ctx, ctx->nxt, SC_COST_TRY));
+    TRY(DISPATCH(ctx, launch_cost, ctx, ctx->nxt, SC_COST_TRY, nullptr, false));
     CK(cudaEventRecord(ctx->ev_c1, ctx->st));
-    return NLLS_OK;
+    return exchange_try_scalars(ctx);
 }
 
 // One LM try.  The fused try is booked like the reference's timers (src/iterators.jl:152,157): the cost evaluation (CUDA events around
@@ -722,6 +860,28 @@ int prepare_adaptive(nlls_ctx* ctx) {
     CK(cudaStreamSynchronize(ctx->st));
     ctx->prepared = true;
     ctx->lm_active = false;
+    ctx->masked = false;
+    for (unsigned char u : ctx->h_unfixed) if (!u) FAIL(NLLS_ERR_UNSUPPORTED, "unfixed masks are not implemented for the adaptive-kernel residuals");
+    return NLLS_OK;
+}
+}  // namespace
+
+namespace {
+// (re)build the per-class fixed flags from h_unfixed and upload them (prepared contexts only)
+int apply_unfixed(nlls_ctx* ctx) {
+    ctx->masked = false;
+    if (!ctx->prepared || ctx->adaptive) {
+        if (ctx->adaptive) for (unsigned char u : ctx->h_unfixed) if (!u) FAIL(NLLS_ERR_UNSUPPORTED, "unfixed masks are not implemented for the adaptive-kernel residuals");
+        return NLLS_OK;
+    }
+    const VarSet& A = ctx->vars[ctx->vtA];
+    const VarSet& B = ctx->vars[ctx->vtB];
+    auto fixed = [&](int64_t gidx) { return (size_t)(gidx - 1) < ctx->h_unfixed.size() && !ctx->h_unfixed[(size_t)(gidx - 1)]; };
+    ctx->h_fixA.assign(A.gidx.size(), 0); ctx->h_fixB.assign(B.gidx.size(), 0);
+    for (size_t i = 0; i < A.gidx.size(); ++i) if (fixed(A.gidx[i])) { ctx->h_fixA[i] = 1; ctx->masked = true; }
+    for (size_t i = 0; i < B.gidx.size(); ++i) if (fixed(B.gidx[i])) { ctx->h_fixB[i] = 1; ctx->masked = true; }
+    if (ctx->masked) { TRY(upload(ctx, &ctx->d_fixA, ctx->h_fixA)); TRY(upload(ctx, &ctx->d_fixB, ctx->h_fixB)); }
+    ctx->cam_part_vars = -1;
     return NLLS_OK;
 }
 }  // namespace
@@ -729,7 +889,42 @@ int prepare_adaptive(nlls_ctx* ctx) {
 // =====================================================================================================
 extern "C" {
 
-int nlls_version(void) { return 100; }
+int nlls_version(void) { return 200; }
+
+int nlls_set_unfixed(nlls_ctx* ctx, const uint8_t* unfixed, int64_t n) {
+    if (!ctx || n < 0 || (n > 0 && !unfixed)) return NLLS_ERR_INVALID;
+    if (ctx->lm_active && ctx->lm_phase != 0) FAIL(NLLS_ERR_INVALID, "nlls_set_unfixed inside an LM iteration");
+    ctx->h_unfixed.assign(unfixed, unfixed + n);
+    CK(cudaSetDevice(ctx->device));
+    return apply_unfixed(ctx);
+}
+
+int nlls_optimize_singles(nlls_ctx* ctx, int vartype, const nlls_options* opts, int64_t* iterations) {
+    if (!ctx || !opts) return NLLS_ERR_INVALID;
+    if (opts->iterator != NLLS_ITER_LM) FAIL(NLLS_ERR_UNSUPPORTED, "optimizesingles: only the Levenberg-Marquardt iterator has a batched kernel");
+    TRY(nlls_prepare(ctx));
+    if (ctx->adaptive || vartype != ctx->vtB) FAIL(NLLS_ERR_NO_KERNEL, "optimizesingles has a registered kernel for the point type of the BA residuals only");
+    CK(cudaSetDevice(ctx->device));
+    SinglesOpts so;
+    so.reldcost = opts->reldcost; so.absdcost = opts->absdcost; so.dstep = opts->dstep; so.maxfails = opts->maxfails; so.maxiters = opts->maxiters;
+    so.timeup = opts->maxtime_ns == 0 ? 1 : 0;
+    unsigned long long* d_it = reinterpret_cast<unsigned long long*>(ctx->d_scal + SC_INFO);
+    CK(cudaMemsetAsync(d_it, 0, sizeof(unsigned long long), ctx->st));
+    DevProblem p = devproblem(ctx);
+    const int grid = (int)((ctx->nB + 127) / 128);
+    if (ctx->restype == NLLS_RES_AFFINE_BA) singles_point_kernel<AffineBA><<<grid, 128, 0, ctx->st>>>(p, ctx->d_A[ctx->cur], ctx->d_B[ctx->cur], so, d_it);
+    else singles_point_kernel<PinholeBA><<<grid, 128, 0, ctx->st>>>(p, ctx->d_A[ctx->cur], ctx->d_B[ctx->cur], so, d_it);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    unsigned long long h_it = 0;
+    CK(cudaMemcpyAsync(&h_it, d_it, sizeof(h_it), cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    if (iterations) *iterations = (int64_t)h_it;
+    for (auto& kv : ctx->vars) kv.second.stale = true;   // the device holds newer variables than the host mirror
+    ctx->cam_part_vars = -1;
+    ctx->lm_active = false;
+    return NLLS_OK;
+}
 
 int nlls_create(nlls_ctx** out, int device) {
     if (!out) return NLLS_ERR_INVALID;
@@ -749,6 +944,7 @@ int nlls_create(nlls_ctx** out, int device) {
     cudaEventCreate(&ctx->ev_b1);
     cudaEventCreate(&ctx->ev_c0);
     cudaEventCreate(&ctx->ev_c1);
+    cudaMalloc((void**)&ctx->d_gather, sizeof(double) * 8 * 64);
     cudaMalloc((void**)&ctx->d_scal, sizeof(double) * SC_COUNT);
     cudaMemset(ctx->d_scal, 0, sizeof(double) * SC_COUNT);
     cudaMallocHost((void**)&ctx->h_scal, sizeof(double) * (SC_COUNT + 2));
@@ -777,12 +973,12 @@ int nlls_destroy(nlls_ctx* ctx) {
     cudaDeviceSynchronize();
     void* ptrs[] = {ctx->d_obs_cam, ctx->d_obs_pt, ctx->d_obs_start, ctx->d_tile_pt, ctx->d_obs_z, ctx->d_cm_pt, ctx->d_item_cam, ctx->d_item_beg,
                     ctx->d_item_end, ctx->d_cam_item_start, ctx->d_cm_z, ctx->d_A[0], ctx->d_A[1], ctx->d_A[2], ctx->d_B[0], ctx->d_B[1], ctx->d_B[2],
-                    ctx->d_H, ctx->d_g, ctx->d_x, ctx->d_Ainv, ctx->d_S, ctx->d_rhs, ctx->d_cost_part, ctx->d_step_part, ctx->d_cam_part, ctx->d_cam_part2, ctx->d_scal,
+                    ctx->d_H, ctx->d_g, ctx->d_x, ctx->d_Ainv, ctx->d_S, ctx->d_rhs, ctx->d_cost_part, ctx->d_step_part, ctx->d_cam_part, ctx->d_cam_part2, ctx->d_scal, ctx->d_gather,
                     ctx->d_flush, ctx->d_tile_id, ctx->d_pos, ctx->d_diag_tile, ctx->d_diag_tile_nat,
                     ctx->d_lvl_cols, ctx->d_red_tasks, ctx->d_red_upds, ctx->d_red_targets, ctx->d_colptr,
                     ctx->d_col_tile, ctx->d_col_row, ctx->d_Linv, ctx->d_xp, ctx->d_stile_pt, ctx->d_chunk_off, ctx->d_chunks, ctx->d_ents, ctx->d_tiles, ctx->d_camstat_part,
                     ctx->d_ad_data, ctx->d_ad_chunks, ctx->d_ad_moff, ctx->d_ad_part, ctx->d_ent_off, ctx->d_cta_item, ctx->d_items, ctx->d_units, ctx->d_wtab, ctx->d_blob,
-                    ctx->d5_cta_item, ctx->d5_items, ctx->d5_blob, ctx->d5_ftab, ctx->d_out_pts, ctx->d_bwd_order, ctx->d_bwd_flags};
+                    ctx->d5_cta_item, ctx->d5_items, ctx->d5_blob, ctx->d5_ftab, ctx->d_out_pts, ctx->d_bwd_order, ctx->d_bwd_flags, ctx->d_fixA, ctx->d_fixB, ctx->d_cauchy, ctx->d_vec_part};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (ctx->red_graph_exec) cudaGraphExecDestroy(ctx->red_graph_exec);
     if (ctx->h_scal) cudaFreeHost(ctx->h_scal);
@@ -808,6 +1004,7 @@ int nlls_comm_init(nlls_ctx* ctx, int rank, int nranks, const void* id128) {
     if (!ctx || nranks < 1 || rank < 0 || rank >= nranks) return NLLS_ERR_INVALID;
     ctx->rank = rank; ctx->nranks = nranks;
     if (nranks == 1) return NLLS_OK;
+    if (nranks > 64) FAIL(NLLS_ERR_UNSUPPORTED, "more than 64 ranks");
     if (!g_nccl.load()) FAIL(NLLS_ERR_NCCL, "libnccl.so.2 not found");
     CK(cudaSetDevice(ctx->device));
     ncclUniqueId id;
@@ -1513,7 +1710,7 @@ int nlls_prepare(nlls_ctx* ctx) {
     CK(cudaStreamSynchronize(ctx->st));
     ctx->prepared = true;
     ctx->lm_active = false;
-    return NLLS_OK;
+    return apply_unfixed(ctx);
 }
 
 int nlls_linearize(nlls_ctx* ctx, double* cost) {
@@ -1544,6 +1741,8 @@ int nlls_solve(nlls_ctx* ctx, double lambda) {
     TRY(launch_reduced_solve(ctx));
     // back-substitution also writes x and varnext; nlls_update is then a no-op kept for API symmetry
     TRY(DISPATCH(ctx, launch_update, ctx));
+    CK(cudaMemsetAsync(ctx->d_scal + SC_COST_TRY, 0, sizeof(double), ctx->st));
+    TRY(exchange_try_scalars(ctx));
     TRY(fetch_scalars(ctx));
     return NLLS_OK;
 }
@@ -1557,10 +1756,16 @@ int nlls_update(nlls_ctx* ctx) {
 int nlls_lm_begin(nlls_ctx* ctx, const nlls_options* opts) {
     if (!ctx || !opts) return NLLS_ERR_INVALID;
     const uint64_t t0 = now_ns();
-    if (opts->iterator != NLLS_ITER_LM && opts->iterator != NLLS_ITER_NEWTON)
-        FAIL(NLLS_ERR_UNSUPPORTED, "only the Levenberg-Marquardt and Newton iterators are implemented");
+    if (opts->iterator < NLLS_ITER_NEWTON || opts->iterator > NLLS_ITER_GD) FAIL(NLLS_ERR_INVALID, "unknown iterator");
     TRY(nlls_prepare(ctx));
     CK(cudaSetDevice(ctx->device));
+    if (opts->iterator == NLLS_ITER_DOGLEG || opts->iterator == NLLS_ITER_GD) {
+        if (ctx->adaptive) FAIL(NLLS_ERR_UNSUPPORTED, "Dogleg / gradient descent are implemented for the bundle-adjustment residuals");
+        if (ctx->nranks > 1) FAIL(NLLS_ERR_UNSUPPORTED, "Dogleg / gradient descent run on one rank");
+        const size_t npart = std::max<size_t>(2 * ((size_t)(ctx->nA + ctx->nB + 127) / 128), VEC_GRID);
+        TRY(dalloc(ctx, &ctx->d_cauchy, (size_t)ctx->dof)); TRY(dalloc(ctx, &ctx->d_vec_part, npart));
+    }
+    ctx->trustradius = 0.0; ctx->stepsize = 1.0;                 // DoglegData / GradientDescentData  src/iterators.jl:35,184
     ctx->opts = *opts;
     ctx->starttime = t0;
     ctx->stoptime = t0 + opts->maxtime_ns;                       // src/optimize.jl:115
@@ -1603,6 +1808,8 @@ int nlls_lm_iterate(nlls_ctx* ctx, nlls_iterinfo* info) {
         if (info) { info->cost = cost_; info->lambda = 0.0; info->maxstep = maxstep; info->stepnorm = std::sqrt(s[SC_P_SQ] + s[SC_C_SQ]); info->ntries = 1; info->accepted = !(cost_ > ctx->bestcost); }
         return NLLS_OK;
     }
+    if (o.iterator == NLLS_ITER_DOGLEG) return DISPATCH(ctx, iterate_dogleg, ctx, info);
+    if (o.iterator == NLLS_ITER_GD) return DISPATCH(ctx, iterate_gd, ctx, info);
     // ---- iterate!(::LevMarData)                                 src/iterators.jl:139-172
     if (ctx->lambda == 0) {                                      // initlambda  :131-137,142-144
         if (ctx->adaptive) { adapt_maxdiag_kernel<<<1, 32, 0, ctx->st>>>(ctx->d_H, (int)ctx->dof, ctx->d_scal + SC_MAXDIAG); ctx->launches++; CK(cudaGetLastError()); }
@@ -1739,7 +1946,14 @@ int nlls_get_variables(nlls_ctx* ctx, int vartype, int which, double* aos, int64
     return NLLS_OK;
 }
 
-int64_t nlls_dof(nlls_ctx* ctx) { return (ctx && ctx->prepared) ? ctx->dof : -1; }
+int64_t nlls_dof(nlls_ctx* ctx) {   // length of linsystem.b / x: the unfixed variables' DoF
+    if (!ctx || !ctx->prepared) return -1;
+    if (!ctx->masked) return ctx->dof;
+    int64_t d = 0;
+    for (unsigned char f : ctx->h_fixA) if (!f) d += ctx->DC;
+    for (unsigned char f : ctx->h_fixB) if (!f) d += 3;
+    return d;
+}
 int64_t nlls_hessian_len(nlls_ctx* ctx) { return (ctx && ctx->prepared) ? ctx->hlen : -1; }
 int64_t nlls_hessian_nblocks(nlls_ctx* ctx) { return (ctx && ctx->prepared && !ctx->adaptive) ? ctx->nA + ctx->nB + ctx->nobs : -1; }
 
@@ -1751,15 +1965,16 @@ int reorder_vec(nlls_ctx* ctx, const double* dsrc, double* out) {
     std::vector<double> tmp((size_t)ctx->dof);
     CK(cudaMemcpyAsync(tmp.data(), dsrc, sizeof(double) * ctx->dof, cudaMemcpyDeviceToHost, ctx->st));
     CK(cudaStreamSynchronize(ctx->st));
-    if (ctx->cams_first) { std::memcpy(out, tmp.data(), sizeof(double) * ctx->dof); return NLLS_OK; }
+    if (ctx->cams_first && !ctx->masked) { std::memcpy(out, tmp.data(), sizeof(double) * ctx->dof); return NLLS_OK; }
     const VarSet& A = ctx->vars[ctx->vtA];
     const VarSet& B = ctx->vars[ctx->vtB];
     size_t ia = 0, ib = 0, o = 0;
     const int DC = ctx->DC;
     while (ia < A.gidx.size() || ib < B.gidx.size()) {
         const bool takeA = ib >= B.gidx.size() || (ia < A.gidx.size() && A.gidx[ia] < B.gidx[ib]);
-        if (takeA) { std::memcpy(out + o, &tmp[(size_t)DC * ia], sizeof(double) * DC); o += DC; ++ia; }
-        else { std::memcpy(out + o, &tmp[(size_t)DC * ctx->nA + 3 * ib], sizeof(double) * 3); o += 3; ++ib; }
+        // (fixed variables have no block in the reference's linear system: they are skipped)
+        if (takeA) { if (!(ctx->masked && ctx->h_fixA[ia])) { std::memcpy(out + o, &tmp[(size_t)DC * ia], sizeof(double) * DC); o += DC; } ++ia; }
+        else { if (!(ctx->masked && ctx->h_fixB[ib])) { std::memcpy(out + o, &tmp[(size_t)DC * ctx->nA + 3 * ib], sizeof(double) * 3); o += 3; } ++ib; }
     }
     return NLLS_OK;
 }
@@ -1822,6 +2037,7 @@ int nlls_get_step(nlls_ctx* ctx, double* x) {
 
 int nlls_get_hessian_blocks(nlls_ctx* ctx, double* data) {
     if (!ctx || !ctx->prepared || !data) return NLLS_ERR_INVALID;
+    if (ctx->masked) FAIL(NLLS_ERR_UNSUPPORTED, "Hessian read-back under an unfixed mask (fixed variables are frozen in place, not removed)");
     CK(cudaSetDevice(ctx->device));
     if (ctx->cams_first) {  // internal layout == reference layout
         CK(cudaMemcpyAsync(data, ctx->d_H, sizeof(double) * ctx->hlen, cudaMemcpyDeviceToHost, ctx->st));

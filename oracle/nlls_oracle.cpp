@@ -721,10 +721,15 @@ double fast_bAb_dense(int n, const double* A, const double* b) {                
 // Linear system                                                        src/linearsystem.jl
 // =======================================================================================
 void Problem::makesymmvls() {                                                             // :91-124
-    size_t nb = variables.size();  // all unfixed: block index == variable index
-    std::vector<int> bs(nb);
+    // blockindices / blocksizes over the unfixed variables                               :93-102
+    blockindices.assign(variables.size(), 0);
+    std::vector<int> bs;
+    for (size_t i = 0; i < variables.size(); ++i)
+        if (unfixed.empty() || unfixed[i]) { bs.push_back(variables[i].ndof); blockindices[i] = (int64_t)bs.size(); }
+    const size_t nb = bs.size();
+    nblocks = (int64_t)nb;
     boffsets.assign(nb + 1, 1);
-    for (size_t i = 0; i < nb; ++i) { bs[i] = variables[i].ndof; boffsets[i + 1] = boffsets[i] + bs[i]; }
+    for (size_t i = 0; i < nb; ++i) boffsets[i + 1] = boffsets[i] + bs[i];
     dof = boffsets[nb] - 1;
     sparse = false;
     std::vector<int64_t> colptr, rowval;
@@ -735,7 +740,9 @@ void Problem::makesymmvls() {                                                   
         pairs.reserve(ncost * 3 + nb);
         for (auto& vec : costs) for (const Cost& c : vec)
             for (int a = 0; a < c.ndeps; ++a) for (int bb = 0; bb <= a; ++bb) {
-                uint64_t i = (uint64_t)std::max(c.vi[a], c.vi[bb]), j = (uint64_t)std::min(c.vi[a], c.vi[bb]);
+                const int64_t ba = blockindices[(size_t)c.vi[a] - 1], b2 = blockindices[(size_t)c.vi[bb] - 1];
+                if (ba == 0 || b2 == 0) continue;                                         // sparsity[unfixed, :]  :108
+                uint64_t i = (uint64_t)std::max(ba, b2), j = (uint64_t)std::min(ba, b2);
                 pairs.push_back((i << 32) | j);  // key sorts by block row then block column
             }
         std::sort(pairs.begin(), pairs.end());
@@ -766,7 +773,7 @@ void Problem::makesymmvls() {                                                   
         if (elimination_order == 1) std::reverse(order.begin(), order.end());
         std::stable_sort(order.begin(), order.end(), [&](int64_t a, int64_t c) { return std::min<int64_t>(deg[a], 64) < std::min<int64_t>(deg[c], 64); });
         std::vector<int64_t> perm; perm.reserve((size_t)dof);
-        for (int64_t blk : order) for (int k = 0; k < bs[blk]; ++k) perm.push_back(boffsets[blk] - 1 + k);
+        for (int64_t blk : order) for (int k = 0; k < bs[(size_t)blk]; ++k) perm.push_back(boffsets[(size_t)blk] - 1 + k);
         ldl_analyze(hess, perm, ldl);                                                     // :68
     } else {
         Adense.assign((size_t)(dof * dof), 0.0);                                          // :80-86
@@ -785,21 +792,29 @@ double Problem::costgradhess() {
         double sub = 0.0;
         for (const Cost& c : costs[t]) {
             const Variable* v[4];
-            for (int i = 0; i < c.ndeps; ++i) v[i] = &variables[c.vi[i] - 1];
+            bool any = false;
+            for (int i = 0; i < c.ndeps; ++i) { v[i] = &variables[c.vi[i] - 1]; any = any || blockindices[(size_t)c.vi[i] - 1] != 0; }
+            if (!any) { sub += computecost(c, kernels[t], v); continue; }                 // no unfixed variable: cost only  src/cost.jl:51
             double g[20], H[20 * 20]; int Pt;
+            // the reference differentiates only w.r.t. the unfixed variables (varflags, src/cost.jl:36-47); the blocks it obtains are
+            // the corresponding sub-blocks of the all-unfixed (g, H) computed here (J'r, rho' J'J + 2 rho'' g g' are separable)
             sub += computecostgradhess(c, kernels[t], v, Pt, g, H);
             // updateb!                                                                    :159-170
             int loff = 0;
             for (int i = 0; i < c.ndeps; ++i) {
                 int nv = v[i]->ndof;
-                int64_t off = boffsets[c.vi[i] - 1] - 1;
-                for (int k = 0; k < nv; ++k) b[(size_t)(off + k)] += g[loff + k];
+                const int64_t bi = blockindices[(size_t)c.vi[i] - 1];
+                if (bi != 0) {
+                    int64_t off = boffsets[bi - 1] - 1;
+                    for (int k = 0; k < nv; ++k) b[(size_t)(off + k)] += g[loff + k];
+                }
                 loff += nv;
             }
             // updatesymA!                                                                 :132-157
             int loffi = 0;
             for (int i = 0; i < c.ndeps; ++i) {
-                int nvi = v[i]->ndof; int64_t bi = c.vi[i];
+                int nvi = v[i]->ndof; int64_t bi = blockindices[(size_t)c.vi[i] - 1];
+                if (bi == 0) { loffi += nvi; continue; }
                 auto add = [&](int64_t brow, int64_t bcol, int nr, int nc, int ro, int co) {
                     // block(A, brow, bcol) .+= H[ro.., co..]
                     if (sparse) {
@@ -813,9 +828,11 @@ double Problem::costgradhess() {
                 add(bi, bi, nvi, nvi, loffi, loffi);
                 int loffj = 0;
                 for (int j = 0; j < i; ++j) {
-                    int nvj = v[j]->ndof; int64_t bj = c.vi[j];
-                    if (bi >= bj) add(bi, bj, nvi, nvj, loffi, loffj);
-                    else add(bj, bi, nvj, nvi, loffj, loffi);
+                    int nvj = v[j]->ndof; int64_t bj = blockindices[(size_t)c.vi[j] - 1];
+                    if (bj != 0) {
+                        if (bi >= bj) add(bi, bj, nvi, nvj, loffi, loffj);
+                        else add(bj, bi, nvj, nvi, loffj, loffi);
+                    }
                     loffj += nvj;
                 }
                 loffi += nvi;
@@ -886,7 +903,8 @@ Result Problem::optimize(const Options& opt, std::vector<IterRecord>* trace) {
             res.linearsolvers += 1; ntries += 1;
         };
         auto update_and_cost = [&]() {                          // update! + cost(varnext)
-            for (size_t i = 0; i < variables.size(); ++i) varnext[i] = update(variables[i], x.data() + (boffsets[i] - 1));
+            for (size_t i = 0; i < variables.size(); ++i)          // update!  src/linearsystem.jl:206-213 (fixed variables are left alone)
+                if (blockindices[i]) varnext[i] = update(variables[i], x.data() + (boffsets[(size_t)blockindices[i] - 1] - 1));
             t0 = time_ns();
             const double c = this->cost(varnext);
             t_cost += time_ns() - t0;
@@ -975,7 +993,7 @@ Result Problem::optimize(const Options& opt, std::vector<IterRecord>* trace) {
                 t_solver += time_ns() - t0;
                 res.linearsolvers += 1; ntries += 1;
                 for (size_t i = 0; i < variables.size(); ++i)      // update!  src/linearsystem.jl:206-213
-                    varnext[i] = update(variables[i], x.data() + (boffsets[i] - 1));
+                    if (blockindices[i]) varnext[i] = update(variables[i], x.data() + (boffsets[(size_t)blockindices[i] - 1] - 1));
                 t0 = time_ns();
                 cost_ = this->cost(varnext);                       // :157
                 t_cost += time_ns() - t0;
@@ -1035,6 +1053,41 @@ Result Problem::optimize(const Options& opt, std::vector<IterRecord>* trace) {
     res.timetotal = (time_ns() - starttime) * 1e-9;
     res.timeinit = t_init * 1e-9; res.timecost = t_cost * 1e-9; res.timegradient = t_grad * 1e-9; res.timesolver = t_solver * 1e-9;
     return res;
+}
+
+// optimizesingles!                                                  src/optimize.jl:60-76,183-205
+// Every variable in `indices` (the reference sorts them by size; callers pass one size) is optimised on its own: all other variables
+// fixed, only the costs that depend on it (selectcosts!), a fresh iterator (reset!) per variable.  Restated with a sub-problem per
+// variable that holds just those costs and the variables they touch.
+int64_t Problem::optimizesingles(const Options& opt, const std::vector<int64_t>& indices) {
+    std::vector<std::vector<std::pair<int, int64_t>>> dep(variables.size());   // var -> (cost type, position)
+    for (size_t t = 0; t < costs.size(); ++t)
+        for (size_t q = 0; q < costs[t].size(); ++q)
+            for (int i = 0; i < costs[t][q].ndeps; ++i) dep[(size_t)costs[t][q].vi[i] - 1].push_back({(int)t, (int64_t)q});
+    int64_t iters = 0;
+    for (int64_t ind : indices) {
+        Problem sp;
+        std::vector<int64_t> l2g;
+        auto local = [&](int64_t gidx) {
+            for (size_t k = 0; k < l2g.size(); ++k) if (l2g[k] == gidx) return (int64_t)k + 1;
+            l2g.push_back(gidx);
+            sp.variables.push_back(variables[(size_t)gidx - 1]);
+            return (int64_t)l2g.size();
+        };
+        for (const auto& d : dep[(size_t)ind - 1]) {
+            Cost c = costs[(size_t)d.first][(size_t)d.second];
+            for (int i = 0; i < c.ndeps; ++i) c.vi[i] = local(c.vi[i]);
+            sp.addcost(c, kernels[(size_t)d.first]);
+        }
+        if (sp.variables.empty()) continue;
+        sp.unfixed.assign(sp.variables.size(), 0);
+        sp.unfixed[(size_t)local(ind) - 1] = 1;
+        Result r = sp.optimize(opt, nullptr);
+        iters += r.niterations;
+        variables[(size_t)ind - 1] = sp.variables[(size_t)local(ind) - 1];
+    }
+    lsready = false;
+    return iters;
 }
 
 }  // namespace orc

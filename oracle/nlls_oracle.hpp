@@ -144,7 +144,12 @@ struct Problem {
     double cost() const { return cost(variables); }         //                          src/cost.jl:10-11
     double cost(const std::vector<Variable>& vars) const;
 
-    // linear system (all variables unfixed)                                   src/linearsystem.jl:91-124
+    // linear system                                                           src/linearsystem.jl:91-124
+    // unfixed: which variables are optimised (optimize!(problem, options, unfixed), src/optimize.jl:5-20); empty = all.
+    // blockindices[var] = 1-based block of an unfixed variable, 0 for a fixed one (src/linearsystem.jl:93-102).
+    std::vector<char> unfixed;
+    std::vector<int64_t> blockindices;
+    int64_t nblocks = 0;
     bool sparse = false;
     std::vector<int64_t> boffsets;  // 1-based scalar offsets per block
     int64_t dof = 0;
@@ -163,6 +168,9 @@ struct Problem {
     double costgradhess();                                   //                         src/cost.jl:29-54
     void gethessian();                                       //                         src/linearsystem.jl:180-190
     Result optimize(const Options& opt, std::vector<IterRecord>* trace = nullptr);  // src/optimize.jl:109-180
+    // optimizesingles!(problem, options, indices): every listed variable on its own, all others fixed, over the costs that depend
+    // on it (src/optimize.jl:60-76,183-205).  Returns the summed iteration count.
+    int64_t optimizesingles(const Options& opt, const std::vector<int64_t>& indices);
     std::string lasterror;
 };
 

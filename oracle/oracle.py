@@ -54,6 +54,9 @@ def lib():
         L.orc_problem_new.restype = C.c_void_p
         L.orc_problem_free.argtypes = [C.c_void_p]
         L.orc_set_elimination_order.argtypes = [C.c_void_p, C.c_int]
+        L.orc_set_unfixed.argtypes = [C.c_void_p, C.POINTER(C.c_ubyte), C.c_int64]
+        L.orc_optimizesingles.restype = C.c_int64
+        L.orc_optimizesingles.argtypes = [C.c_void_p, C.c_void_p, _ip, C.c_int64]
         L.orc_add_variables.restype = C.c_int64
         L.orc_add_variables.argtypes = [C.c_void_p, C.c_int, C.c_int64, _dp, C.c_int]
         L.orc_add_costs.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_int, _ip, C.c_int, _dp, C.c_int, C.c_double, C.c_int, C.c_double]
@@ -326,6 +329,20 @@ class Problem:
     def set_elimination_order(self, mode):
         """0: default order of the sparse LDL'; 1: a second exact order (ties reversed) — used to measure solver-vs-solver drift."""
         lib().orc_set_elimination_order(self.h, mode)
+
+    def set_unfixed(self, mask=None):
+        """optimize!(problem, options, unfixed): boolean vector over the variables (None: all unfixed)."""
+        if mask is None:
+            lib().orc_set_unfixed(self.h, None, 0)
+        else:
+            m = np.ascontiguousarray(mask, dtype=np.uint8)
+            lib().orc_set_unfixed(self.h, m.ctypes.data_as(C.POINTER(C.c_ubyte)), len(m))
+
+    def optimizesingles(self, indices, options=None):
+        """optimizesingles!(problem, options, indices) with 1-based variable indices (src/optimize.jl:60-76)."""
+        options = options or Options()
+        idx = np.ascontiguousarray(indices, dtype=np.int64)
+        return lib().orc_optimizesingles(self.h, C.byref(options), _pi(idx), len(idx))
 
     def add_variables(self, vtype, values):
         """values: (n, nstore) array. Returns the 1-based index of the first variable added."""

@@ -59,6 +59,12 @@ void orc_resjac(int type, const double* data, int ndeps, const int* vtypes, cons
 // ---- problem
 void* orc_problem_new() { return new Problem(); }
 void orc_problem_free(void* p) { delete (Problem*)p; }
+// optimize!(problem, options, unfixed): mask[i] != 0 -> variable i + 1 is optimised; n == 0 clears the mask (all unfixed)
+void orc_set_unfixed(void* p, const unsigned char* mask, int64_t n) {
+    Problem* pr = (Problem*)p;
+    pr->unfixed.assign(mask, mask + n);
+    pr->lsready = false;
+}
 void orc_set_elimination_order(void* p, int mode) { Problem* pr = (Problem*)p; pr->elimination_order = mode; pr->lsready = false; }
 int64_t orc_add_variables(void* p, int type, int64_t n, const double* v, int nstore) {
     Problem* pr = (Problem*)p;
@@ -206,3 +212,13 @@ double orc_fast_bAb_sparse(int64_t n, const int64_t* colptr, const int64_t* rowv
 }
 
 }  // extern "C"
+
+extern "C" int64_t orc_optimizesingles(void* p, const orc_options* o, const int64_t* indices, int64_t n) {
+    Problem* pr = (Problem*)p;
+    Options opt;
+    opt.reldcost = o->reldcost; opt.absdcost = o->absdcost; opt.dstep = o->dstep;
+    opt.maxfails = o->maxfails; opt.maxiters = o->maxiters; opt.maxtime_ns = o->maxtime_ns;
+    opt.callback_terminate = 0;
+    opt.iterator = (int)o->iterator;
+    return pr->optimizesingles(opt, std::vector<int64_t>(indices, indices + n));
+}
