@@ -36,10 +36,21 @@ def _log(msg):
 HUBER_WIDTH = 0.03
 NOISE, OUTLIERS = 0.01, 0.02
 PERTURB = 1e-3
+# --camera pinhole: the repo-defined SO(3) / pinhole residual (9-DoF camera, minimal update; measurements in pixels)
+PIN_HUBER_WIDTH = 1.5
+PIN_NOISE, PIN_PERTURB_PT, PIN_PERTURB_ROT = 0.5, 1e-3, 1e-4
+CAMERA = "affine"
+
+
+def huber_width():
+    return PIN_HUBER_WIDTH if CAMERA == "pinhole" else HUBER_WIDTH
 
 
 def make_problem(pkg, workload, seed=0):
     rng = np.random.default_rng(seed)
+    if CAMERA == "pinhole":
+        p = pkg.synthetic.create_bal_shaped_pinhole(*pkg.synthetic.SHAPES[workload], rng, noise=PIN_NOISE, outlier_frac=OUTLIERS)
+        return pkg.synthetic.perturb_pinhole_problem(p, PIN_PERTURB_PT, PIN_PERTURB_ROT, rng)
     p = pkg.synthetic.create_shape(workload, rng, noise=NOISE, outlier_frac=OUTLIERS)
     pkg.synthetic.perturb_ba_problem(p, PERTURB, PERTURB, rng)
     return p
@@ -98,9 +109,10 @@ class ClockSampler:
 
 def oracle_problem(p, orc):
     P = orc.Problem()
-    P.add_variables(orc.VT_EUCLID, p.cameras)
+    P.add_variables(orc.VT_PINHOLE if CAMERA == "pinhole" else orc.VT_EUCLID, p.cameras)
     P.add_variables(orc.VT_EUCLID, p.points)
-    P.add_costs(orc.RT_AFFINE_BA, np.stack([p.cam_idx, p.pt_idx], 1), p.z, kernel=(orc.RK_HUBER, HUBER_WIDTH, False, 1.0))
+    P.add_costs(orc.RT_PINHOLE_BA if CAMERA == "pinhole" else orc.RT_AFFINE_BA, np.stack([p.cam_idx, p.pt_idx], 1), p.z,
+                kernel=(orc.RK_HUBER, huber_width(), False, 1.0))
     return P
 
 
@@ -159,7 +171,8 @@ def run_reference(args, rank):
 
 
 def workload_config(workload, p, ngpus):
-    return {"workload": f"{workload}-shaped synthetic BA (affine camera of test/optimizeba.jl), Huber({HUBER_WIDTH})",
+    cam = "SO(3) pinhole camera, 9 DoF, repo-defined residual" if CAMERA == "pinhole" else "affine camera of test/optimizeba.jl"
+    return {"workload": f"{workload}-shaped synthetic BA ({cam}), Huber({huber_width()})",
             "cameras": p.ncam, "points": p.npt, "observations": p.nobs, "parallelism": f"points sharded over {ngpus} GPU(s)",
             "cache": "working set (H + observations) larger than L2 for venice; L2 flushed between kernel-timing reps"}
 
@@ -171,9 +184,12 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--workload", default="venice", choices=["venice", "ladybug", "final"])
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--camera", default="affine", choices=["affine", "pinhole"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-iters", type=int, default=2)
     args = ap.parse_args()
+    global CAMERA
+    CAMERA = args.camera
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -206,9 +222,10 @@ def main():
     pt_first = p.ncam + 1 + int(pts_sel[0])
     aos = p.costs_aos()[obs_sel]
     t0 = time.perf_counter()
-    ctx.set_variables(capi.VAR_EUCLID6, cams, first_index=1)
+    vt_cam, res_t = (capi.VAR_PINHOLE, capi.RES_PINHOLE_BA) if CAMERA == "pinhole" else (capi.VAR_EUCLID6, capi.RES_AFFINE_BA)
+    ctx.set_variables(vt_cam, cams, first_index=1)
     ctx.set_variables(capi.VAR_EUCLID3, pts, first_index=pt_first)
-    ctx.set_costs(capi.RES_AFFINE_BA, aos, capi.ROBUST_HUBER, (HUBER_WIDTH,))
+    ctx.set_costs(res_t, aos, capi.ROBUST_HUBER, (huber_width(),))
     ctx.prepare()
     t_setup = time.perf_counter() - t0
     _log(f"context prepared ({t_setup:.2f}s)")
@@ -264,34 +281,54 @@ def main():
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    alg_bytes = ctx.algorithmic_bytes(capi.TIME_LIN_POINT)
-    achieved = alg_bytes / (kern["lin_point"] * 1e-3) / 1e9
-    traffic = None
-    try:  # DRAM bytes of the same kernel from the committed ncu --set full capture (1-GPU venice only)
-        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload, {}).get("lin_point_kernel")
-        if tr and tr.get("gpus") == world:
-            traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
+    peak_source = "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+    # FP64 peak of the DMMA path (mma.sync.m8n8k4.f64): 61 FMA / clk / SM measured by scripts/ubench/dmma_lat.cu, at the sampled SM clock
+    sm_mhz = clocks.summary().get("sm_mhz") or 1965.0
+    fp64_peak = 61.0 * 2 * 148 * sm_mhz * 1e6 / 1e12
+    traffic_db = {}
+    try:  # DRAM bytes per launch from the committed ncu --set full captures (1-GPU venice only)
+        traffic_db = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(f"{args.workload}" + ("_pinhole" if CAMERA == "pinhole" else ""), {})
     except Exception:
         pass
-    roofline = {"bound": "hbm", "kernel": "lin_point_kernel<AffineBA> (fused residual + Jacobian + robust + J'WJ, TMA tile store)",
-                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
-                "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": kern["lin_point"], "traffic": traffic,
-                "linearize_total": {"algorithmic_bytes": ctx.algorithmic_bytes(capi.TIME_LINEARIZE), "ms": kern["linearize"],
-                                    "achieved": ctx.algorithmic_bytes(capi.TIME_LINEARIZE) / (kern["linearize"] * 1e-3) / 1e9}}
 
-    # the other HBM-bound kernels of an LM try against the same peak (algorithmic bytes: H read once, + variables / lists)
-    other = {}
-    for name, which, key in [("schur4_kernel (Schur elimination of the point blocks, FP64 tensor cores)", capi.TIME_SCHUR, "schur"),
-                             ("backsub_kernel (point back-substitution + update + step statistics)", capi.TIME_BACKSUB, "backsub_update"),
-                             ("cost_kernel", capi.TIME_COST, "cost")]:
-        try:
-            ab = ctx.algorithmic_bytes(which)
-            if ab > 0:
-                other[name] = {"algorithmic_bytes": ab, "ms": kern[key], "achieved": ab / (kern[key] * 1e-3) / 1e9, "frac": ab / (kern[key] * 1e-3) / 1e9 / peak}
-        except Exception:
-            pass
-    roofline["other_kernels"] = other
+    def traffic_of(kname):
+        tr = traffic_db.get(kname)
+        return tr["dram_bytes_read"] + tr["dram_bytes_write"] if tr and tr.get("gpus") == world else None
+
+    def hbm_entry(which, key, kname=None):
+        ab = ctx.algorithmic_bytes(which)
+        ach = ab / (kern[key] * 1e-3) / 1e9
+        return {"algorithmic_bytes": ab, "ms": kern[key], "achieved": ach, "frac": ach / peak, "traffic": traffic_of(kname) if kname else None}
+
+    def fp64_entry(which, key):
+        fl = ctx.algorithmic_flops(which)
+        return {"algorithmic_flops": fl, "achieved_tflops": fl / (kern[key] * 1e-3) / 1e12, "peak_tflops": fp64_peak, "frac": fl / (kern[key] * 1e-3) / 1e12 / fp64_peak,
+                "peak_source": "61 FMA/clk/SM (scripts/ubench/dmma_lat.cu, measured DMMA issue rate) x 148 SMs x sampled SM clock"}
+
+    resname = "PinholeBA" if CAMERA == "pinhole" else "AffineBA"
+    # the dominant kernel of the step: the Schur elimination of the point blocks (reads H's point rows once)
+    sch = hbm_entry(capi.TIME_SCHUR, "schur", "schur5_kernel")
+    b_lin, b_cost = ctx.algorithmic_bytes(capi.TIME_LINEARIZE), ctx.algorithmic_bytes(capi.TIME_COST)
+    t_loop = kern["linearize_in_loop"] + kern["cost"]
+    roofline = {"bound": "hbm", "kernel": "schur5_kernel (Schur elimination of the point blocks on the FP64 tensor cores; the largest share of the step; "
+                                          "timed with the S memset + red_init it needs)",
+                "achieved": sch["achieved"], "peak": peak, "unit": "GB/s", "frac": sch["frac"], "peak_source": peak_source,
+                "algorithmic_bytes_per_launch": sch["algorithmic_bytes"], "ms_per_launch": sch["ms"], "traffic": sch["traffic"],
+                "fp64": fp64_entry(capi.TIME_SCHUR, "schur"),
+                # residual + Jacobian + assembly as a whole, B_lin / t.  standalone = nlls_linearize (point pass || camera pass +
+                # finalize); in_loop = what an LM iteration pays: the camera blocks ride on the accepted try's cost evaluation, so the
+                # iteration's residual work is (cost pass + point pass + finalize) and produces B_lin + B_cost algorithmic bytes
+                "residual_assembly": {
+                    "standalone": {"algorithmic_bytes": b_lin, "ms": kern["linearize"], "achieved": b_lin / (kern["linearize"] * 1e-3) / 1e9,
+                                   "frac": b_lin / (kern["linearize"] * 1e-3) / 1e9 / peak},
+                    "in_loop": {"algorithmic_bytes": b_lin + b_cost, "ms": t_loop, "achieved": (b_lin + b_cost) / (t_loop * 1e-3) / 1e9,
+                                "frac": (b_lin + b_cost) / (t_loop * 1e-3) / 1e9 / peak,
+                                "what": "cost pass of the accepted try (camera-major, leaves U_c / g_c partials) + point pass + finalize"}},
+                "other_kernels": {
+                    f"lin_point_kernel<{resname}> (fused residual + Jacobian + robust + J'WJ, TMA tile store)": hbm_entry(capi.TIME_LIN_POINT, "lin_point", "lin_point_kernel"),
+                    "backsub_kernel (point back-substitution + update + step statistics)": hbm_entry(capi.TIME_BACKSUB, "backsub_update", "backsub_kernel"),
+                    f"lin_cam_kernel<{resname}> as the cost pass (cost + camera blocks)": hbm_entry(capi.TIME_COST, "cost", "lin_cam_kernel"),
+                    "reduced solve (tile LDL' + sweeps, latency bound)": dict(fp64_entry(capi.TIME_SOLVE_REDUCED, "reduced_solve"), ms=kern["reduced_solve"])}}
     _log("kernel timing done")
     # ---- end to end through the C ABI with host buffers: every step uploads problem.variables from pinned host memory,
     # runs one LM iteration and reads the updated variables + cost back
@@ -301,16 +338,16 @@ def main():
         cam_pin = torch.from_numpy(cams.copy()).pin_memory()
         pts_pin = torch.from_numpy(pts.copy()).pin_memory()
         cam_np, pts_np = cam_pin.numpy(), pts_pin.numpy()
-        ctx.set_variables(capi.VAR_EUCLID6, cam_np, first_index=1)
+        ctx.set_variables(vt_cam, cam_np, first_index=1)
         ctx.set_variables(capi.VAR_EUCLID3, pts_np, first_index=pt_first)
         esteps = args.steps
         opts1 = pkg.NLLSOptions(maxiters=1, maxtime=1e5).c()
 
         def estep():
-            ctx.set_variables(capi.VAR_EUCLID6, cam_np, first_index=1)      # H2D (problem.variables)
+            ctx.set_variables(vt_cam, cam_np, first_index=1)                 # H2D (problem.variables)
             ctx.set_variables(capi.VAR_EUCLID3, pts_np, first_index=pt_first)
             r = ctx.optimize(opts1)                                          # optimize!(problem, NLLSOptions(maxiters=1))
-            ctx.get_variables(capi.VAR_EUCLID6, cam_np.shape[0], 6, 0, out=cam_np)   # D2H (variables updated in place)
+            ctx.get_variables(vt_cam, cam_np.shape[0], cam_np.shape[1], 0, out=cam_np)   # D2H (variables updated in place)
             ctx.get_variables(capi.VAR_EUCLID3, pts_np.shape[0], 3, 0, out=pts_np)
             return r.bestcost
         for _ in range(3):

@@ -179,6 +179,8 @@ int nlls_timer_start(nlls_ctx* ctx);
 int nlls_timer_stop(nlls_ctx* ctx, double* ms);
 int64_t nlls_kernel_launches(nlls_ctx* ctx);            /* kernels launched by this context so far                     */
 int nlls_algorithmic_bytes(nlls_ctx* ctx, int which, double* bytes);  /* SURVEY §8d figures for this problem         */
+/* FP64 operations per launch of NLLS_TIME_SCHUR / NLLS_TIME_SOLVE_REDUCED (multiply and add counted separately) */
+int nlls_algorithmic_flops(nlls_ctx* ctx, int which, double* flops);
 
 #ifdef __cplusplus
 }

@@ -23,7 +23,7 @@ EXPORTS = [
     "nlls_set_variables", "nlls_set_costs", "nlls_set_unfixed", "nlls_optimize_singles", "nlls_prepare", "nlls_linearize", "nlls_cost", "nlls_solve", "nlls_update",
     "nlls_lm_begin", "nlls_lm_iterate", "nlls_lm_advance", "nlls_lm_end", "nlls_optimize", "nlls_get_variables", "nlls_dof",
     "nlls_get_gradient", "nlls_get_step", "nlls_hessian_len", "nlls_get_hessian_blocks", "nlls_hessian_nblocks",
-    "nlls_get_hessian_index", "nlls_time_kernels", "nlls_timer_start", "nlls_timer_stop", "nlls_kernel_launches", "nlls_algorithmic_bytes",
+    "nlls_get_hessian_index", "nlls_time_kernels", "nlls_timer_start", "nlls_timer_stop", "nlls_kernel_launches", "nlls_algorithmic_bytes", "nlls_algorithmic_flops",
 ]
 
 
@@ -92,6 +92,7 @@ def lib():
         L.nlls_get_hessian_index.argtypes = [vp, _ip, _ip, _ip]
         L.nlls_time_kernels.argtypes = [vp, C.c_int, C.c_int, C.c_int, _dp]
         L.nlls_algorithmic_bytes.argtypes = [vp, C.c_int, _dp]
+        L.nlls_algorithmic_flops.argtypes = [vp, C.c_int, _dp]
         L.nlls_timer_start.argtypes = [vp]
         L.nlls_timer_stop.argtypes = [vp, _dp]
         _LIB = L
@@ -255,6 +256,11 @@ class Context:
     def algorithmic_bytes(self, which):
         b = C.c_double()
         self._ck(lib().nlls_algorithmic_bytes(self.h, which, C.byref(b)))
+        return b.value
+
+    def algorithmic_flops(self, which):
+        b = C.c_double()
+        self._ck(lib().nlls_algorithmic_flops(self.h, which, C.byref(b)))
         return b.value
 
 

@@ -144,6 +144,7 @@ struct nlls_ctx {
     int NT = 0;
     int64_t ntiles_alloc = 0;
     int red_levels = 0;
+    double red_flops = 0.0;          // algorithmic FP64 operations of one reduced solve (tile LDL' + sweeps), counted at prepare
     struct RedLaunch { int kind, off, cnt; };          // kind 0: diagonal tiles of a level, 1: its off-diagonal tiles, 2: its updates
     std::vector<RedLaunch> fact_launches;
     RedTask* d_red_tasks = nullptr;
@@ -1335,6 +1336,16 @@ int nlls_prepare(nlls_ctx* ctx) {
             if ((int)red_upds.size() > u0) ctx->fact_launches.push_back({2, g0, (int)red_targets.size() - g0});
         }
         nupd_total = red_upds.size();
+        {   // algorithmic flops (multiply and add counted separately) of one factorisation + both sweeps, ST^3 = one dense tile GEMM / 2
+            const double t3 = (double)ST * ST * ST, t2 = (double)ST * ST;
+            const double ndiag = NT, noff = (double)red_tasks.size() - NT;
+            double nupd_diag = 0;
+            for (const RedTarget& tg : red_targets) if (tg.row >= 0) nupd_diag += tg.u1 - tg.u0;
+            ctx->red_flops = ndiag * (t3 / 3 + t3 / 3)            // LDL' of the diagonal tile + its triangular inverse
+                             + noff * t3                          // L_IJ = T_IJ L_JJ^-T D^-1 (triangular)
+                             + ((double)nupd_total - nupd_diag) * 2 * t3 + nupd_diag * t3   // Schur updates (symmetric targets: half)
+                             + (ndiag * 2 + noff * 2) * 2 * t2;   // forward + backward sweeps
+        }
         if (getenv("NLLS_B200_VERBOSE"))
             fprintf(stderr, "[nlls] reduced system: NT=%d tiles=%d half-bandwidth=%d nd=%d levels=%d fact_launches=%zu tasks=%zu updates=%zu\n", NT, nt, w,
                     (int)use_nd, nlev, ctx->fact_launches.size(), red_tasks.size(), nupd_total);
@@ -2109,6 +2120,26 @@ int nlls_algorithmic_bytes(nlls_ctx* ctx, int which, double* bytes) {
     return NLLS_OK;
 }
 
+// Algorithmic FP64 operations per launch (multiply and add counted separately) of the two phases north_star wants against the FP64
+// peak: the Schur elimination (per point with k observations: 3 x 3 inverse, Y = A_p^-1 W (k blocks of 3 x 3 x DC), k (k + 1) / 2
+// products W_i' Y_j (DC x 3 x DC) and k right-hand side terms) and the reduced solve.
+int nlls_algorithmic_flops(nlls_ctx* ctx, int which, double* flops) {
+    if (!ctx || !ctx->prepared || !flops || ctx->adaptive) return NLLS_ERR_INVALID;
+    const double DC = ctx->DC;
+    if (which == NLLS_TIME_SCHUR) {
+        double f = 0;
+        for (int64_t p = 0; p < ctx->nB; ++p) {
+            const double k = ctx->h_obs_start[(size_t)p + 1] - ctx->h_obs_start[(size_t)p];
+            f += 60.0 + k * (2 * 9 * DC) + 0.5 * k * (k + 1) * (2 * 3 * DC * DC) + k * (2 * 3 * DC) + 18.0;
+        }
+        *flops = f;
+        return NLLS_OK;
+    }
+    if (which == NLLS_TIME_SOLVE_REDUCED) { *flops = ctx->red_flops; return NLLS_OK; }
+    *flops = 0;
+    return NLLS_ERR_INVALID;
+}
+
 int nlls_time_kernels(nlls_ctx* ctx, int which, int reps, int flush_l2, double* ms_per_call) {
     if (!ctx || !ctx->prepared || reps < 1 || !ms_per_call) return NLLS_ERR_INVALID;
     CK(cudaSetDevice(ctx->device));
@@ -2135,7 +2166,7 @@ int nlls_time_kernels(nlls_ctx* ctx, int which, int reps, int flush_l2, double* 
             case NLLS_TIME_LIN_POINT: TRY(DISPATCH(ctx, launch_linearize, ctx, true, 0)); break;
             case NLLS_TIME_LIN_CAM: TRY(DISPATCH(ctx, launch_linearize, ctx, false, 1)); break;
             case NLLS_TIME_LIN_LOOP: TRY(DISPATCH(ctx, launch_linearize, ctx, true, 2)); break;
-            case NLLS_TIME_COST: TRY(DISPATCH(ctx, launch_cost, ctx, ctx->cur, SC_COST_TRY, ctx->d_cam_part2)); break;
+            case NLLS_TIME_COST: TRY(DISPATCH(ctx, launch_cost, ctx, ctx->cur, SC_COST_TRY, ctx->d_cam_part2, false)); break;   // kernels only: the LM try combines its scalars in exchange_try_scalars
             case NLLS_TIME_SCHUR: TRY(DISPATCH(ctx, launch_schur, ctx, lambda)); break;
             case NLLS_TIME_SOLVE_REDUCED: TRY(DISPATCH(ctx, launch_schur, ctx, lambda)); CK(cudaEventRecord(ctx->ev_t0, ctx->st)); TRY(launch_reduced_solve(ctx)); break;
             case NLLS_TIME_BACKSUB: TRY(DISPATCH(ctx, launch_update, ctx)); break;

@@ -149,3 +149,62 @@ def create_adaptive_problem(ninliers, noutliers, rng, inliersigma=1.0, outliersi
     start ContaminatedGaussian(0.5, 5.0, 0.6), mean 0."""
     data = offset + np.concatenate([rng.standard_normal(ninliers) * inliersigma, rng.standard_normal(noutliers) * outliersigma])
     return {"data": data, "start_kernel": (0.5, 5.0, 0.6), "start_mean": 0.0}
+
+
+# ------------------------------------------------------------------------------------------------
+# Pinhole / SO(3) cameras (repo-defined residual, BAL convention: P = R X + t, p = -P.xy / P.z, r = f (1 + k1 |p|^2 + k2 |p|^4) p - z)
+# ------------------------------------------------------------------------------------------------
+def so3_exp(w):
+    """Rodrigues formula, vectorised: w (n, 3) -> R (n, 3, 3)."""
+    w = np.asarray(w, dtype=np.float64)
+    th = np.linalg.norm(w, axis=1)
+    K = np.zeros((len(w), 3, 3))
+    K[:, 0, 1], K[:, 0, 2] = -w[:, 2], w[:, 1]
+    K[:, 1, 0], K[:, 1, 2] = w[:, 2], -w[:, 0]
+    K[:, 2, 0], K[:, 2, 1] = -w[:, 1], w[:, 0]
+    small = th < 1e-5
+    ths = np.where(small, 1.0, th)
+    A = np.where(small, 1.0 - th ** 2 / 6.0, np.sin(ths) / ths)
+    B = np.where(small, 0.5 - th ** 2 / 24.0, (1.0 - np.cos(ths)) / ths ** 2)
+    return np.eye(3)[None] + A[:, None, None] * K + B[:, None, None] * (K @ K)
+
+
+def pinhole_cameras(rod, t, f, k1, k2):
+    """Stored form of NLLS_VAR_PINHOLE: R column-major (9), t (3), f, k1, k2."""
+    R = so3_exp(rod)
+    return np.concatenate([R.transpose(0, 2, 1).reshape(len(rod), 9), t, f[:, None], k1[:, None], k2[:, None]], axis=1)
+
+
+def project_pinhole(cams, pts):
+    R = cams[:, :9].reshape(-1, 3, 3).transpose(0, 2, 1)
+    P = np.einsum("nij,nj->ni", R, pts) + cams[:, 9:12]
+    pxy = -P[:, :2] / P[:, 2:3]
+    n2 = np.sum(pxy * pxy, axis=1)
+    s = cams[:, 12] * (1.0 + n2 * (cams[:, 13] + cams[:, 14] * n2))
+    return s[:, None] * pxy
+
+
+def create_bal_shaped_pinhole(ncam, npt, nobs, rng, noise=0.5, outlier_frac=0.0, outlier_scale=20.0):
+    """The same visibility structure as create_bal_shaped with 9-DoF pinhole cameras (15 stored doubles)."""
+    shape = create_bal_shaped(ncam, npt, nobs, rng, noise=0.0)
+    cams = pinhole_cameras(rng.standard_normal((ncam, 3)) * 0.05, np.array([0.0, 0.0, -10.0]) + rng.standard_normal((ncam, 3)) * 0.1,
+                           500.0 + 20.0 * rng.standard_normal(ncam), 1e-2 * rng.standard_normal(ncam), 1e-3 * rng.standard_normal(ncam))
+    pts = rng.uniform(-1.0, 1.0, (npt, 3))
+    cl, pl = shape.cam_idx - 1, shape.pt_idx - ncam - 1
+    z = project_pinhole(cams[cl], pts[pl]) + rng.standard_normal((shape.nobs, 2)) * noise
+    if outlier_frac > 0:
+        nout = int(round(outlier_frac * shape.nobs))
+        sel = rng.choice(shape.nobs, size=nout, replace=False)
+        z[sel] += rng.standard_normal((nout, 2)) * (noise * outlier_scale)
+    return BAProblem(cams, pts, shape.cam_idx, shape.pt_idx, z)
+
+
+def perturb_pinhole_problem(problem, pointnoise, rotnoise, rng):
+    """Landmarks += N(0, pointnoise); camera rotations <- Exp(N(0, rotnoise)) R  (the minimal update of NLLS_VAR_PINHOLE)."""
+    problem.points = problem.points + rng.standard_normal(problem.points.shape) * pointnoise
+    E = so3_exp(rng.standard_normal((problem.ncam, 3)) * rotnoise)
+    R = problem.cameras[:, :9].reshape(-1, 3, 3).transpose(0, 2, 1)
+    cams = problem.cameras.copy()
+    cams[:, :9] = (E @ R).transpose(0, 2, 1).reshape(-1, 9)
+    problem.cameras = cams
+    return problem

@@ -274,3 +274,37 @@ def test_oracle_self_drift_under_two_elimination_orders(pkg, orc):
         agree += 1
     assert 8 <= agree < len(t0)                                         # well posed for the first iterations only
     assert abs(r0.bestcost - r1.bestcost) > 1e-8 * r0.bestcost          # the 1e-8 final-cost gate is ill posed for this configuration
+
+
+def test_oracle_unfixed_and_optimizesingles(pkg, orc):
+    """test/optimizeba.jl:52-62 on the oracle: landmarks perturbed, every landmark optimised on its own (optimizesingles!) -> cost
+    < 1e-15; and optimize!(problem, options, unfixed) with a mask: fixed variables keep their values, the linear system holds the
+    unfixed blocks only (src/linearsystem.jl:93-102)."""
+    rng = np.random.default_rng(1)
+    for shape in [(3, 5, 1.0), (10, 50, 0.3)]:
+        p = pkg.synthetic.create_ba_problem(*shape, rng)
+        pkg.synthetic.perturb_ba_problem(p, 0.003, 0.0, rng)
+
+        def mk():
+            P = orc.Problem()
+            P.add_variables(orc.VT_EUCLID, p.cameras)
+            P.add_variables(orc.VT_EUCLID, p.points)
+            P.add_costs(orc.RT_AFFINE_BA, np.stack([p.cam_idx, p.pt_idx], 1), p.z)
+            return P
+        P = mk()
+        assert P.cost() > 1e-8
+        P.optimizesingles(np.arange(p.ncam + 1, p.ncam + p.npt + 1))
+        assert P.cost() < 1e-15                                         # :62
+        assert np.array_equal(P.variables()[:6 * p.ncam], p.cameras.ravel())
+        P = mk()
+        mask = np.zeros(p.ncam + p.npt, dtype=np.uint8)
+        mask[p.ncam:] = 1
+        P.set_unfixed(mask)
+        res, _ = P.optimize()
+        assert P.dof == 3 * p.npt and res.bestcost < 1e-15
+        assert np.array_equal(P.variables()[:6 * p.ncam], p.cameras.ravel())
+        # the masked gradient is the unfixed part of the full gradient
+        Pf, Pm = mk(), mk()
+        Pm.set_unfixed(mask)
+        Pf.linearize(); Pm.linearize()
+        assert np.array_equal(Pm.grad(), Pf.grad()[6 * p.ncam:])
