@@ -154,9 +154,10 @@ struct nlls_ctx {
     int *d_tile_id = nullptr, *d_pos = nullptr, *d_diag_tile = nullptr, *d_diag_tile_nat = nullptr, *d_lvl_cols = nullptr;
     int *d_colptr = nullptr, *d_col_tile = nullptr, *d_col_row = nullptr;
     double *d_Linv = nullptr, *d_xp = nullptr;
-    int bwd_flow = 0;                // NLLS_B200_BWD=flow: backward sweep as one dataflow launch instead of one launch per level (measured equal:
-                                     // 0.401 vs 0.396 ms per reduced solve on the Venice shape — the chain of dependent columns is the cost, not the launches)
-    int *d_bwd_order = nullptr, *d_bwd_flags = nullptr;
+    int bwd_flow = 2;                // backward sweep: 2 = one dataflow launch, everything column-independent staged before the first wait (default);
+                                     // NLLS_B200_BWD=flow: first dataflow version (measured equal to per-level launches: 0.401 vs 0.396 ms per reduced
+                                     // solve on the Venice shape — the dependent chain inside a column is the cost, not the launches); =levels: one launch per level
+    int *d_bwd_order = nullptr, *d_bwd_flags = nullptr, *d_nat_of_pos = nullptr;
     // Schur v2 plan (per-tile sorted contribution lists)
     int schur_v2 = 1;
     int nstiles = 0;
@@ -164,6 +165,7 @@ struct nlls_ctx {
     // Schur v4 plan (super-tiles: tensor-core accumulation of whole S blocks across consecutive tiles); 2 = forced
     cudaGraphExec_t red_graph_exec = nullptr;   // the reduced solve's launch sequence (tile-sparse path)
     int use_graph = 1, red_graph_launches = 0;
+    int use_pdl = 1;                 // programmatic dependent launch along the reduced solve's kernel chain (NLLS_B200_PDL=0: plain stream order)
     int schur_v4 = 1, nsuper = 0;   // nsuper: CTAs of the v4 kernel (0: v2 path)
     // Schur v5 plan (window-aligned register accumulation, schur5.cuh); 1: automatic, 2: forced, 0: off.  n5cta: CTAs (0: not in use)
     int schur_v5 = 1, n5cta = 0, nout_pts = 0, s5_ncons = S5_CONSUMERS;
@@ -316,6 +318,7 @@ int set_smem_attrs(nlls_ctx* ctx) {
     CK(cudaFuncSetAttribute(ldl_upd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UPD_SMEM));
     CK(cudaFuncSetAttribute(ldl_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWD_SMEM));
     CK(cudaFuncSetAttribute(ldl_bwd_flow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWD_SMEM));
+    CK(cudaFuncSetAttribute(ldl_bwd_flow2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWD2_SMEM));
     return NLLS_OK;
 }
 
@@ -467,24 +470,38 @@ int launch_reduced_solve(nlls_ctx* ctx) {
         const int nx = ctx->NT * ST;
         // ~40 short dependent launches with constant arguments: captured once into a CUDA graph and replayed (the launch gaps of a
         // plain stream are a quarter of this phase; NLLS_B200_GRAPH=0 keeps plain launches)
+        const bool pdl = ctx->use_pdl != 0;
+        auto go = [&](auto kernel, int grid, int block, size_t smem, auto... args) -> cudaError_t {
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)block); cfg.dynamicSmemBytes = smem; cfg.stream = ctx->st;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
+            cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+            return cudaLaunchKernelEx(&cfg, kernel, args...);
+        };
         auto enqueue = [&](int& nl) -> int {
-            red_permute_kernel<<<(nx + 255) / 256, 256, 0, ctx->st>>>(ctx->d_rhs, ctx->d_xp, ctx->d_pos, ctx->NT, 1); ++nl;
+            CK(go(red_permute_kernel, (nx + 255) / 256, 256, 0, (const double*)ctx->d_rhs, ctx->d_xp, (const int*)ctx->d_pos, ctx->NT, 1, ctx->bwd_flow == 2 ? ctx->d_bwd_flags : (int*)nullptr)); ++nl;
             for (const auto& l : ctx->fact_launches) {   // factorisation + forward substitution (fused into the diagonal tasks)
-                if (l.kind == 0) ldl_diag_kernel<<<l.cnt, DIAG_THREADS, DIAG_SMEM, ctx->st>>>(ctx->d_S, ctx->d_Linv, ctx->d_red_tasks + l.off, ctx->d_xp);
-                else if (l.kind == 1) ldl_off_kernel<<<GEMM_CTAS * l.cnt, GEMM_THREADS, OFF_SMEM, ctx->st>>>(ctx->d_S, ctx->d_Linv, ctx->d_red_tasks + l.off, ctx->d_xp);
-                else ldl_upd_kernel<<<GEMM_CTAS * l.cnt, GEMM_THREADS, UPD_SMEM, ctx->st>>>(ctx->d_S, ctx->d_red_upds, ctx->d_red_targets + l.off, ctx->d_xp);
+                if (l.kind == 0) CK(go(ldl_diag_kernel, l.cnt, DIAG_THREADS, DIAG_SMEM, ctx->d_S, ctx->d_Linv, (const RedTask*)(ctx->d_red_tasks + l.off), ctx->d_xp));
+                else if (l.kind == 1) CK(go(ldl_off_kernel, GEMM_CTAS * l.cnt, GEMM_THREADS, OFF_SMEM, ctx->d_S, (const double*)ctx->d_Linv, (const RedTask*)(ctx->d_red_tasks + l.off), ctx->d_xp));
+                else CK(go(ldl_upd_kernel, GEMM_CTAS * l.cnt, GEMM_THREADS, UPD_SMEM, ctx->d_S, (const RedUpd*)ctx->d_red_upds, (const RedTarget*)(ctx->d_red_targets + l.off), ctx->d_xp));
                 ++nl;
             }
-            if (ctx->bwd_flow) {   // one dataflow launch over all columns (levels from last to first)
+            if (ctx->bwd_flow == 2) {   // one dataflow launch; also writes the solution in natural numbering (no trailing permutation)
+                CK(go(ldl_bwd_flow2_kernel, std::min(ctx->NT, ctx->nsm), BW_THREADS, BWD2_SMEM, (const double*)ctx->d_S, (const double*)ctx->d_Linv, t, (const int*)ctx->d_bwd_order,
+                      (const int*)ctx->d_nat_of_pos, ctx->NT, ctx->d_bwd_flags, ctx->d_xp, ctx->d_rhs));
+                ++nl;
+                return NLLS_OK;
+            } else if (ctx->bwd_flow) {   // first dataflow version
                 CK(cudaMemsetAsync(ctx->d_bwd_flags, 0, sizeof(int) * ctx->NT, ctx->st));
                 ldl_bwd_flow_kernel<<<std::min(ctx->NT, ctx->nsm), RED_THREADS, BWD_SMEM, ctx->st>>>(ctx->d_S, ctx->d_Linv, t, ctx->d_bwd_order, ctx->NT, ctx->d_bwd_flags, ctx->d_xp);
                 ++nl;
             } else
             for (size_t l = ctx->lvl_cols.size(); l-- > 0;) {
-                ldl_bwd_kernel<<<ctx->lvl_cols[l].second, RED_THREADS, BWD_SMEM, ctx->st>>>(ctx->d_S, ctx->d_Linv, t, ctx->d_lvl_cols + ctx->lvl_cols[l].first, ctx->d_xp);
+                CK(go(ldl_bwd_kernel, ctx->lvl_cols[l].second, RED_THREADS, BWD_SMEM, (const double*)ctx->d_S, (const double*)ctx->d_Linv, t, (const int*)(ctx->d_lvl_cols + ctx->lvl_cols[l].first), ctx->d_xp));
                 ++nl;
             }
-            red_permute_kernel<<<(nx + 255) / 256, 256, 0, ctx->st>>>(ctx->d_xp, ctx->d_rhs, ctx->d_pos, ctx->NT, 0); ++nl;
+            CK(go(red_permute_kernel, (nx + 255) / 256, 256, 0, (const double*)ctx->d_xp, ctx->d_rhs, (const int*)ctx->d_pos, ctx->NT, 0, (int*)nullptr)); ++nl;
             return NLLS_OK;
         };
         if (ctx->use_graph && !ctx->red_graph_exec) {
@@ -954,7 +971,8 @@ int nlls_create(nlls_ctx** out, int device) {
     ctx->use_tma = (e && e[0] == '0') ? 0 : 1;
     if (const char* g = getenv("NLLS_B200_SCHUR_STRIDE")) ctx->schur_stride = std::max(1, atoi(g));
     if (const char* g = getenv("NLLS_B200_GRAPH")) ctx->use_graph = atoi(g) != 0;
-    if (const char* g = getenv("NLLS_B200_BWD")) ctx->bwd_flow = std::string(g) == "flow";
+    if (const char* g = getenv("NLLS_B200_PDL")) ctx->use_pdl = atoi(g);
+    if (const char* g = getenv("NLLS_B200_BWD")) ctx->bwd_flow = std::string(g) == "flow" ? 1 : (std::string(g) == "levels" ? 0 : 2);
     if (const char* g = getenv("NLLS_B200_COST")) ctx->cost_pointmajor = std::string(g) == "tiles";
     if (const char* g = getenv("NLLS_B200_SCHUR")) {
         const std::string m(g);
@@ -979,7 +997,7 @@ int nlls_destroy(nlls_ctx* ctx) {
                     ctx->d_lvl_cols, ctx->d_red_tasks, ctx->d_red_upds, ctx->d_red_targets, ctx->d_colptr,
                     ctx->d_col_tile, ctx->d_col_row, ctx->d_Linv, ctx->d_xp, ctx->d_stile_pt, ctx->d_chunk_off, ctx->d_chunks, ctx->d_ents, ctx->d_tiles, ctx->d_camstat_part,
                     ctx->d_ad_data, ctx->d_ad_chunks, ctx->d_ad_moff, ctx->d_ad_part, ctx->d_ent_off, ctx->d_cta_item, ctx->d_items, ctx->d_units, ctx->d_wtab, ctx->d_blob,
-                    ctx->d5_cta_item, ctx->d5_items, ctx->d5_blob, ctx->d5_ftab, ctx->d_out_pts, ctx->d_bwd_order, ctx->d_bwd_flags, ctx->d_fixA, ctx->d_fixB, ctx->d_cauchy, ctx->d_vec_part};
+                    ctx->d5_cta_item, ctx->d5_items, ctx->d5_blob, ctx->d5_ftab, ctx->d_out_pts, ctx->d_bwd_order, ctx->d_bwd_flags, ctx->d_nat_of_pos, ctx->d_fixA, ctx->d_fixB, ctx->d_cauchy, ctx->d_vec_part};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (ctx->red_graph_exec) cudaGraphExecDestroy(ctx->red_graph_exec);
     if (ctx->h_scal) cudaFreeHost(ctx->h_scal);
@@ -1709,6 +1727,9 @@ int nlls_prepare(nlls_ctx* ctx) {
                 for (int q = 0; q < ctx->lvl_cols[l].second; ++q) bwd_order.push_back(lvl_cols_flat[(size_t)(ctx->lvl_cols[l].first + q)]);
             TRY(upload(ctx, &ctx->d_bwd_order, bwd_order));
             TRY(dalloc(ctx, &ctx->d_bwd_flags, (size_t)ctx->NT));
+            std::vector<int> nat_of((size_t)ctx->NT);
+            for (int o = 0; o < ctx->NT; ++o) nat_of[(size_t)pos[(size_t)o]] = o;
+            TRY(upload(ctx, &ctx->d_nat_of_pos, nat_of));
         }
         TRY(upload(ctx, &ctx->d_colptr, colptr)); TRY(upload(ctx, &ctx->d_col_tile, col_tile)); TRY(upload(ctx, &ctx->d_col_row, col_row));
     }

@@ -53,6 +53,14 @@ __device__ __forceinline__ double rcp_fast(double d) {
     return x;
 }
 
+// Programmatic dependent launch (the reduced solve is ~40 short dependent kernels): a kernel of the chain waits for its predecessor
+// with pdl_wait() and immediately allows its successor to be scheduled, so the successor's launch latency and whatever it does before
+// its own pdl_wait() overlap this kernel.  Because the trigger comes after the wait, a kernel that is running knows that everything up
+// to its predecessor's predecessor is complete and visible — that is what may be touched before pdl_wait().  Without the launch
+// attribute both instructions are no-ops.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ void cp_async16(void* sdst, const void* gsrc) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(sdst)), "l"(gsrc) : "memory");
 }
@@ -211,8 +219,9 @@ __global__ void __launch_bounds__(DIAG_THREADS) ldl_diag_kernel(double* __restri
     const int fr = lane >> 2, fk = lane & 3;
     const RedTask tk = tasks[blockIdx.x];
     double* T = S + (size_t)tk.tile * ST2;
-    tile_to_smem_ld<DIAG_THREADS>(As, T);
     for (int q = tid; q < MCOLS * LDT / 2; q += DIAG_THREADS) reinterpret_cast<double2*>(Rs)[q] = make_double2(0.0, 0.0);
+    pdl_wait(); pdl_trigger();           // the tile and b_J were last written by the previous level's update kernel
+    tile_to_smem_ld<DIAG_THREADS>(As, T);
     const double bval = (tid < ST) ? xp[(size_t)tk.col * ST + tid] : 0.0;
     __syncthreads();
     if (tid < ST) { Rs[tid * LDT + tid] = 1.0; Rs[ST * LDT + tid] = bval; }
@@ -256,7 +265,14 @@ __global__ void __launch_bounds__(DIAG_THREADS) ldl_diag_kernel(double* __restri
                 }
                 cp[0] = c0r; cp[LDT] = c1r;
                 __syncwarp();
+#ifdef LDL_PROFILE
+                const long long t_f0 = clock64();
+                t_acc[4] += t_f0 - t_ph;
+#endif
                 diag_block_factor(As, g, NW + (pb ^ 1) * 128, NW + (pb ^ 1) * 128 + 64, dpan2 + 8 * (pb ^ 1), dall);
+#ifdef LDL_PROFILE
+                t_acc[5] += clock64() - t_f0;
+#endif
             }
         } else {
             // ---------------- B: trailing blocks (I, J), p < J <= I, except the next diagonal block;  C: (I, J) with I >= p and
@@ -335,7 +351,8 @@ __global__ void __launch_bounds__(GEMM_THREADS) ldl_off_kernel(double* __restric
     const RedTask tk = tasks[blockIdx.x / GEMM_CTAS];
     const int I = GEMM_CTAS * (blockIdx.x % GEMM_CTAS) + w;      // row block of this warp
     double* T = S + (size_t)tk.tile * ST2;
-    tile_to_smem_ld<GEMM_THREADS>(As, T);
+    tile_to_smem_ld<GEMM_THREADS>(As, T);      // T_IJ was last written by the previous level's update kernel, two launches back: safe before the wait
+    pdl_wait(); pdl_trigger();
     tile_to_smem_ld<GEMM_THREADS>(Bs, Linv + (size_t)tk.col * ST2);
     if (tid < ST) Ds[tid] = rcp_fast(S[(size_t)tk.dtile * ST2 + (size_t)(ST + 1) * tid]);
     (void)xp;
@@ -391,6 +408,7 @@ __global__ void __launch_bounds__(GEMM_THREADS) ldl_upd_kernel(double* __restric
 #pragma unroll
     for (int cb = 0; cb < NBLK; ++cb) { c0[cb] = 0.0; c1[cb] = 0.0; }
     double pr = 0.0;
+    pdl_wait(); pdl_trigger();
     for (int u = tg.u0; u < tg.u1; ++u) {
         const RedUpd up = upds[u];
         __syncthreads();             // the previous update is done with the staged tiles
@@ -449,6 +467,7 @@ __global__ void __launch_bounds__(RED_THREADS) ldl_bwd_kernel(const double* __re
     const int J = cols[blockIdx.x];
     const int q0 = t.colptr[J], q1 = t.colptr[J + 1];
     double acc = 0.0;
+    pdl_wait(); pdl_trigger();
     if (q0 < q1) {
         tile_to_smem<RED_THREADS>(Ts, S + (size_t)t.col_tile[q0] * ST2);
         if (tid < ST) xi[tid] = x[(size_t)t.col_row[q0] * ST + tid];
@@ -504,6 +523,7 @@ __global__ void __launch_bounds__(RED_THREADS) ldl_bwd_flow_kernel(const double*
     double* part = xi + 2 * ST;      // [2][ST]
     double* w = part + 2 * ST;       // [ST]
     const int tid = threadIdx.x, c = tid % ST, h = tid / ST;
+    pdl_wait(); pdl_trigger();
     for (int pos = blockIdx.x; pos < ncols; pos += gridDim.x) {
         const int J = order[pos];
         const int q0 = t.colptr[J], q1 = t.colptr[J + 1];
@@ -555,9 +575,109 @@ __global__ void __launch_bounds__(RED_THREADS) ldl_bwd_flow_kernel(const double*
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Backward sweep, dataflow form, second version (the default).  The first version above measured no faster than one launch per
+// level: what a level costs is not the launch but the dependent chain INSIDE a column — wait for x_I, stage it, a 36-long FMA
+// chain on bank-conflicted columns (stride 72 doubles: a half-warp hits 2 bank pairs), then a 41 KB load of Linv_J that only
+// starts after the products, another 36-long chain, fence, flag.  Here everything that does not depend on other columns is in
+// shared memory before the first wait (up to BW_NBUF row tiles, Linv_J, y_J / D_J), tiles are staged with a row stride of 74
+// doubles (a half-warp reads 8 distinct bank pairs), x_I goes straight from L2 into registers, and 288 threads split every
+// dot product into four 18-element pieces with two accumulators each (9 dependent FMAs).  The column also writes its part of
+// the solution in natural numbering (out), which removes the trailing permutation launch.
+// ---------------------------------------------------------------------------------------------------
+constexpr int BW_LD = 74;
+constexpr int BW_THREADS = 4 * ST;        // 288
+constexpr int BW_NBUF = 3;
+constexpr int BW_Q = ST / 4;              // 18 elements per thread
+constexpr size_t BWD2_SMEM = (size_t)((BW_NBUF + 1) * ST * BW_LD + 4 * ST + 2 * ST) * sizeof(double);
+
+template <int NT_>
+__device__ __forceinline__ void tile_to_smem_bw(double* sdst, const double* gsrc) {
+    for (int q = threadIdx.x; q < ST2 / 2; q += NT_) {
+        const int k = q / (ST / 2), c = q - k * (ST / 2);
+        cp_async16(sdst + k * BW_LD + 2 * c, gsrc + k * ST + 2 * c);
+    }
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__global__ void __launch_bounds__(BW_THREADS) ldl_bwd_flow2_kernel(const double* __restrict__ S, const double* __restrict__ Linv, RedSolveLists t,
+                                                                    const int* __restrict__ order, const int* __restrict__ nat_of_pos, int ncols,
+                                                                    int* __restrict__ flags, double* __restrict__ x, double* __restrict__ out) {
+    extern __shared__ __align__(16) double sm[];
+    double* Ts = sm;                                   // [BW_NBUF][ST * BW_LD]
+    double* Li = sm + BW_NBUF * ST * BW_LD;            // Linv_J
+    double* part = Li + ST * BW_LD;                    // [4][ST]
+    double* yd = part + 4 * ST;                        // y_J / D_J
+    double* w = yd + ST;
+    const int tid = threadIdx.x, c = tid % ST, h = tid / ST;
+    pdl_wait(); pdl_trigger();
+    for (int pos = blockIdx.x; pos < ncols; pos += gridDim.x) {
+        const int J = order[pos];
+        const int q0 = t.colptr[J], q1 = t.colptr[J + 1], nq = q1 - q0;
+        __syncthreads();             // the previous column of this CTA is done with the buffers
+        // ---- everything that does not depend on other columns: Linv_J (group 0), the first row tiles (one group each), y_J / D_J
+        tile_to_smem_bw<BW_THREADS>(Li, Linv + (size_t)J * ST2);
+        cp_async_commit();
+#pragma unroll
+        for (int b = 0; b < BW_NBUF; ++b) {
+            if (b < nq) tile_to_smem_bw<BW_THREADS>(Ts + b * ST * BW_LD, S + (size_t)t.col_tile[q0 + b] * ST2);
+            cp_async_commit();
+        }
+        if (tid < ST) yd[tid] = x[(size_t)J * ST + tid] / S[(size_t)t.diag_tile[J] * ST2 + (size_t)(ST + 1) * tid];   // y_J: forward phase, complete
+        double a0 = 0.0, a1 = 0.0;
+        for (int q = 0; q < nq; ++q) {
+            const int row = t.col_row[q0 + q];
+            if (tid == 0) wait_flag(flags + row);
+            // groups are committed in order: Linv, tiles 0 .. BW_NBUF - 1, then one (possibly empty) refill group per iteration, so tile q
+            // is group 1 + q of 1 + BW_NBUF + q committed: complete once at most BW_NBUF - 1 groups are pending
+            cp_async_wait_group<BW_NBUF - 1>();
+            __syncthreads();         // flag seen by thread 0, tile q visible to everyone
+            double xv[BW_Q];
+            const double2* xg = reinterpret_cast<const double2*>(x + (size_t)row * ST + BW_Q * h);
+#pragma unroll
+            for (int i = 0; i < BW_Q / 2; ++i) { const double2 v = __ldcg(xg + i); xv[2 * i] = v.x; xv[2 * i + 1] = v.y; }
+            const double* M = Ts + (q % BW_NBUF) * ST * BW_LD + (size_t)BW_LD * c + BW_Q * h;
+#pragma unroll
+            for (int i = 0; i < BW_Q; i += 2) { a0 = fma(M[i], xv[i], a0); a1 = fma(M[i + 1], xv[i + 1], a1); }
+            __syncthreads();         // buffer q % BW_NBUF is free
+            if (q + BW_NBUF < nq) tile_to_smem_bw<BW_THREADS>(Ts + (q % BW_NBUF) * ST * BW_LD, S + (size_t)t.col_tile[q0 + q + BW_NBUF] * ST2);
+            cp_async_commit();       // (possibly empty) keeps the group count in step with q
+        }
+        part[h * ST + c] = a0 + a1;
+        cp_async_wait_group<0>();
+        __syncthreads();
+        if (tid < ST) w[tid] = yd[tid] - ((part[tid] + part[ST + tid]) + (part[2 * ST + tid] + part[3 * ST + tid]));
+        __syncthreads();
+        {   // x_J[c] = sum_{i >= c} Linv[i][c] w[i]
+            const double* M = Li + (size_t)BW_LD * c + BW_Q * h;
+            const double* wv = w + BW_Q * h;
+            double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+            for (int i = 0; i < BW_Q; i += 2) {
+                s0 = fma((BW_Q * h + i >= c) ? M[i] : 0.0, wv[i], s0);
+                s1 = fma((BW_Q * h + i + 1 >= c) ? M[i + 1] : 0.0, wv[i + 1], s1);
+            }
+            part[h * ST + c] = s0 + s1;
+        }
+        __syncthreads();
+        if (tid < ST) {
+            const double v = (part[tid] + part[ST + tid]) + (part[2 * ST + tid] + part[3 * ST + tid]);
+            x[(size_t)J * ST + tid] = v;
+            out[(size_t)nat_of_pos[J] * ST + tid] = v;
+        }
+        __syncthreads();
+        if (tid == 0) { __threadfence(); atomicExch(flags + J, 1); }
+    }
+}
+
 // natural <-> permuted tile numbering of the right-hand side / solution
-__global__ void red_permute_kernel(const double* __restrict__ src, double* __restrict__ dst, const int* __restrict__ pos, int NT, int to_permuted) {
+__global__ void red_permute_kernel(const double* __restrict__ src, double* __restrict__ dst, const int* __restrict__ pos, int NT, int to_permuted,
+                                   int* __restrict__ flags = nullptr) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    pdl_wait(); pdl_trigger();
+    if (flags && k < NT) flags[k] = 0;          // the dataflow backward sweep's column flags (first node of the solve)
     if (k >= NT * ST) return;
     const int o = k / ST, r = k - o * ST;
     if (to_permuted) dst[(size_t)pos[o] * ST + r] = src[k];

@@ -49,7 +49,7 @@ int main(int argc, char** argv) {
 #ifdef LDL_PROFILE
     std::vector<long long> pr(1024); cudaMemcpy(pr.data(), dprof, 8 * 1024, cudaMemcpyDeviceToHost);
     printf("prologue %lld  loop %lld  epilogue %lld (cycles)\n", pr[1] - pr[0], pr[2] - pr[1], pr[3] - pr[2]);
-    for (int w = 0; w < 8; ++w) printf("warp %d: A2 %lld  sync %lld  M-tasks (or A1) %lld  sync %lld  T-tasks %lld\n", w, pr[64 + 8 * w], pr[65 + 8 * w], pr[66 + 8 * w], pr[67 + 8 * w], pr[68 + 8 * w]);
+    for (int w = 0; w < 8; ++w) printf("warp %d: A2 %lld  sync %lld  tasks (or A1) %lld  sync %lld  [warp 0: look-ahead update %lld  8x8 factor %lld]\n", w, pr[64 + 8 * w], pr[65 + 8 * w], pr[66 + 8 * w], pr[67 + 8 * w], pr[68 + 8 * w], pr[69 + 8 * w]);
 #endif
     return 0;
 }
