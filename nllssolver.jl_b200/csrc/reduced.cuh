@@ -117,15 +117,19 @@ constexpr int DIAG_WARPS = DIAG_THREADS / 32;
 constexpr int MCOLS = ST + 8;                              // Linv columns + one block holding the right-hand side
 
 // Static task table of the B / C phase (element offsets precomputed: a warp spends its time in dependent integer
-// instructions otherwise).  For panel p, entry t = {kind, o0, o1, o2}:
-//   kind 0  trailing block (I, J):            C at As + o0,  A operand rows at As + o1,  B operand rows at As + o2
-//   kind 1  Mfin[p][J] = N11 R[p][J]:         R operand at Rs + o0,  output at Mf + o1
-//   kind 2  R[I][J] -= L21[I] (N11 R[p][J]):  R operand at Rs + o0,  C at Rs + o1,  A operand rows at As + o2
+// instructions otherwise).  Every task is one 8 x 8 block update  C -= A B  over the panel's 8 columns (two DMMAs); offsets are
+// relative to the start of shared memory (As, Rs and Mf are consecutive).  For panel p, entry t = {kind, oC, oA, oB}:
+//   kind 0  trailing block (I, J), p < J <= I:  C = A(I, J),  A = L21[I] D (scaled on load),  B = L21[J]'     (both operands in As)
+//   kind 1  R[I][J] -= L21[I] Mfin[p][J], I > p, J in {0..p, rhs}:  C in Rs,  A = L21[I] in As,  B = Mfin[p][J] in Mf
+// Mfin[p][J] = N11 R[p][J] itself is computed in the A2 phase by the warps that have no L21 block there, so the B / C tasks are
+// uniform and need no layout change through scratch memory.
 // (lane-dependent parts are added by the kernel: fragment row / k offsets.)
+constexpr int DIAG_RS_OFF = ST * LDT;
+constexpr int DIAG_MF_OFF = DIAG_RS_OFF + (ST + 8) * LDT;
 struct DiagTaskTable {
+    alignas(16) int v[NBLK][64][4];
     int n[NBLK];
-    int v[NBLK][64][4];
-    constexpr DiagTaskTable() : n(), v() {
+    constexpr DiagTaskTable() : v(), n() {
         for (int p = 0; p < NBLK; ++p) {
             const int nb = NBLK - 1 - p, c0 = 8 * p;
             int c = 0;
@@ -135,18 +139,24 @@ struct DiagTaskTable {
                     v[p][c][0] = 0; v[p][c][1] = gj * LDT + gi; v[p][c][2] = c0 * LDT + gi; v[p][c][3] = c0 * LDT + gj; ++c;
                 }
             for (int jj = 0; jj < p + 2; ++jj)
-                for (int ii = 0; ii <= nb; ++ii) {
+                for (int ii = 1; ii <= nb; ++ii) {
                     const int J = (jj == p + 1) ? NBLK : jj, I = p + ii;
-                    v[p][c][0] = ii == 0 ? 1 : 2; v[p][c][1] = 8 * J * LDT + c0;
-                    v[p][c][2] = ii == 0 ? 8 * J * LDT + c0 : 8 * J * LDT + 8 * I; v[p][c][3] = c0 * LDT + 8 * I; ++c;
+                    v[p][c][0] = 1; v[p][c][1] = DIAG_RS_OFF + 8 * J * LDT + 8 * I; v[p][c][2] = c0 * LDT + 8 * I; v[p][c][3] = DIAG_MF_OFF + 8 * J * LDT + c0; ++c;
                 }
             n[p] = c;
         }
     }
 };
-__constant__ DiagTaskTable c_diag_tasks = DiagTaskTable();
-constexpr size_t DIAG_SMEM = (size_t)(ST * LDT + 2 * MCOLS * LDT + 2 * 128 + ST + 16 + DIAG_WARPS * 64) * sizeof(double);
+// The table lives in global memory and is copied into shared memory in the kernel's prologue (before the dependency wait): indexed
+// constant-bank loads (LDC with a per-warp register index) measured ~40 % of a worker warp's time in the B / C phase (mio / short
+// scoreboard stalls on the four LDCs of every task).
+__device__ const DiagTaskTable g_diag_tasks = DiagTaskTable();
+constexpr int DIAG_TAB_INT4 = NBLK * 64;
+constexpr size_t DIAG_SMEM = (size_t)(ST * LDT + 2 * MCOLS * LDT + 2 * 128 + ST + 16) * sizeof(double) + (size_t)(DIAG_TAB_INT4 + 4) * sizeof(int4);
 
+#ifndef LDL_ABLATE
+#define LDL_ABLATE 0      // development aid (scripts/ubench): bit mask of phases of ldl_diag_kernel to skip, timing only
+#endif
 #ifdef LDL_PROFILE
 #define LDL_STAMP(i) do { if (threadIdx.x == 0) prof[i] = clock64(); } while (0)
 #define LDL_T0() t_ph = clock64()
@@ -158,34 +168,66 @@ constexpr size_t DIAG_SMEM = (size_t)(ST * LDT + 2 * MCOLS * LDT + 2 * 128 + ST 
 #endif
 
 // LDL' of the 8 x 8 block at (c0, c0) of As, N11 = L11^-1 and W = N11' D^-1 (one warp).  Lane (r, g) = 4 r + g owns columns
-// 2 g, 2 g + 1 of row r of both the block and N11, so a pivot costs 6 shuffles, one reciprocal and 4 FMAs per lane; the
-// critical chain per pivot is reciprocal -> l = a / d -> next pivot element -> shuffle.
+// 2 g, 2 g + 1 of row r of both the block and N11.  This routine is the critical path of the whole reduced solve (72 pivots per
+// tile, one tile per level): a pivot-at-a-time loop measured 190 cycles per pivot — shuffle, reciprocal (MUFU + two Newton steps),
+// multiplier, update, all dependent.  Pivots are therefore taken in PAIRS (j, j + 1):
+//     d_j = a,   d_{j+1} = c - b^2 / a = det / a   with det = a c - b^2,   so   1 / d_j = rcp(a)  and  1 / d_{j+1} = a rcp(det)
+// — two reciprocals that start together from values known at the start of the pair — and both columns of multipliers and the rank-2
+// update of the remaining block follow from one round of shuffles:
+//     l_rj = a_rj / d_j,   t_r = a_r,j+1 - l_rj b  (= the once-updated column j + 1),   l_r,j+1 = t_r / d_{j+1},
+//     a_rk -= l_rj a_kj + l_r,j+1 t_k.
+// Same factorisation (no pivoting, same L and D up to rounding), about 2.3 x shorter dependent chain.
 __device__ __forceinline__ void diag_block_factor(double* As, int c0, double* N11, double* W11, double* dpan, double* dall) {
     const int lane = threadIdx.x & 31, r = lane >> 2, g = lane & 3;
+    const unsigned FULL = 0xffffffffu;
     double P[2], N[2];
 #pragma unroll
     for (int e = 0; e < 2; ++e) { P[e] = As[(c0 + 2 * g + e) * LDT + c0 + r]; N[e] = (r == 2 * g + e) ? 1.0 : 0.0; }
     double rdrow = 0.0;                                                     // 1 / d_r
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const int gj = j >> 1, ej = j & 1;                                  // column j lives in lanes (., gj), slot ej
-        const double d = __shfl_sync(0xffffffffu, P[ej], 4 * j + gj);
-        const double rd = rcp_fast(d);
-        const double arj = __shfl_sync(0xffffffffu, P[ej], (lane & ~3) | gj);          // A[r][j]
-        const double ak0 = __shfl_sync(0xffffffffu, P[ej], 4 * (2 * g) + gj);          // A[2g][j], A[2g+1][j]
-        const double ak1 = __shfl_sync(0xffffffffu, P[ej], 4 * (2 * g + 1) + gj);
-        const double nj0 = __shfl_sync(0xffffffffu, N[0], 4 * j + g);                  // N[j][2g], N[j][2g+1]
-        const double nj1 = __shfl_sync(0xffffffffu, N[1], 4 * j + g);
-        if (lane == 4 * j) { dpan[j] = d; dall[c0 + j] = d; }
-        if (r == j) rdrow = rd;
+    for (int q = 0; q < 4; ++q) {
+        const int j = 2 * q;                                                // columns j, j + 1 live in lanes (., q)
+        const double a = __shfl_sync(FULL, P[0], 4 * j + q);                // A[j][j]
+        const double b = __shfl_sync(FULL, P[0], 4 * (j + 1) + q);          // A[j+1][j]
+        const double c = __shfl_sync(FULL, P[1], 4 * (j + 1) + q);          // A[j+1][j+1]
+        const double ar0 = __shfl_sync(FULL, P[0], (lane & ~3) | q);        // A[r][j], A[r][j+1]
+        const double ar1 = __shfl_sync(FULL, P[1], (lane & ~3) | q);
+        double ak0[2], ak1[2], nj0[2], nj1[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            ak0[e] = __shfl_sync(FULL, P[0], 4 * (2 * g + e) + q);          // A[2g+e][j], A[2g+e][j+1]
+            ak1[e] = __shfl_sync(FULL, P[1], 4 * (2 * g + e) + q);
+            nj0[e] = __shfl_sync(FULL, N[e], 4 * j + g);                    // N[j][2g+e], N[j+1][2g+e]
+            nj1[e] = __shfl_sync(FULL, N[e], 4 * (j + 1) + g);
+        }
+        const double rd0 = rcp_fast(a);
+        const double det = fma(a, c, -(b * b));
+        const double rd1 = a * rcp_fast(det);
+        const double l10 = b * rd0;                                         // l_{j+1,j}
+        const double d1 = fma(-l10, b, c);                                  // d_{j+1} as the pivot-at-a-time recurrence rounds it
+        if (lane == 0) { dpan[j] = a; dpan[j + 1] = d1; dall[c0 + j] = a; dall[c0 + j + 1] = d1; }
+        if (r == j) rdrow = rd0;
+        if (r == j + 1) rdrow = rd1;
+        const double l0 = ar0 * rd0;
+        const double l1 = fma(-l0, b, ar1) * rd1;
         if (r > j) {
-            const double li = arj * rd;
-            if (2 * g > j) P[0] = fma(-li, ak0, P[0]);
-            if (2 * g + 1 > j) P[1] = fma(-li, ak1, P[1]);
-            if (2 * g == j) P[0] = li;
-            if (2 * g + 1 == j) P[1] = li;
-            if (2 * g <= j) N[0] = fma(-li, nj0, N[0]);
-            if (2 * g + 1 <= j) N[1] = fma(-li, nj1, N[1]);
+            // N_r -= l_rj N_j ;  rows below j + 1 also  N_r -= l_r,j+1 (N_{j+1} - l_{j+1,j} N_j)     (entries right of the diagonal are exact zeros)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                double n = fma(-l0, nj0[e], N[e]);
+                if (r > j + 1) n = fma(-l1, fma(-l10, nj0[e], nj1[e]), n);
+                N[e] = n;
+            }
+            if (g == q) {                                                   // the two finished columns of L
+                P[0] = l0;
+                if (r > j + 1) P[1] = l1;
+            } else if (g > q && r > j + 1) {                                // rank-2 update of the remaining block
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const double tk = fma(-(ak0[e] * rd0), b, ak1[e]);
+                    P[e] = fma(-l1, tk, fma(-l0, ak0[e], P[e]));
+                }
+            }
         }
     }
 #pragma unroll
@@ -214,12 +256,15 @@ __global__ void __launch_bounds__(DIAG_THREADS) ldl_diag_kernel(double* __restri
     double* NW = Mf + MCOLS * LDT;       // 2 x { N11 [8][8] row-major, W11 [8][8] (W[k * 8 + c] = N11[c][k] / d_c) }
     double* dall = NW + 2 * 128;         // [ST] pivots
     double* dpan2 = dall + ST;           // 2 x [8] pivots of a panel
-    double* scr = dpan2 + 16;            // per-warp 8 x 8 scratch (C-fragment -> B-fragment layout change)
+    int4* tab = reinterpret_cast<int4*>(dpan2 + 16);   // [NBLK][64] task table, then the per-panel task counts
+    int* tabn = reinterpret_cast<int*>(tab + DIAG_TAB_INT4);
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const int fr = lane >> 2, fk = lane & 3;
     const RedTask tk = tasks[blockIdx.x];
     double* T = S + (size_t)tk.tile * ST2;
     for (int q = tid; q < MCOLS * LDT / 2; q += DIAG_THREADS) reinterpret_cast<double2*>(Rs)[q] = make_double2(0.0, 0.0);
+    for (int q = tid; q < DIAG_TAB_INT4; q += DIAG_THREADS) tab[q] = reinterpret_cast<const int4*>(&g_diag_tasks.v[0][0][0])[q];
+    if (tid < NBLK) tabn[tid] = g_diag_tasks.n[tid];
     pdl_wait(); pdl_trigger();           // the tile and b_J were last written by the previous level's update kernel
     tile_to_smem_ld<DIAG_THREADS>(As, T);
     const double bval = (tid < ST) ? xp[(size_t)tk.col * ST + tid] : 0.0;
@@ -238,6 +283,7 @@ __global__ void __launch_bounds__(DIAG_THREADS) ldl_diag_kernel(double* __restri
         const double* dpan = dpan2 + 8 * pb;
         LDL_T0();
         // ---------------- A2: L21 = A21 W, one 8-row block per warp (in place)
+        if (!(LDL_ABLATE & 4))
         for (int I = p + 1 + w; I < NBLK; I += DIAG_WARPS) {
             double c0r = 0.0, c1r = 0.0, aq[2];
 #pragma unroll
@@ -248,13 +294,25 @@ __global__ void __launch_bounds__(DIAG_THREADS) ldl_diag_kernel(double* __restri
             double* cp = As + (c0 + 2 * fk) * LDT + 8 * I + fr;
             cp[0] = c0r; cp[LDT] = c1r;
         }
+        {   // Mfin[p][J] = N11 R[p][J], J in {0..p, rhs}: one task per warp that has no L21 block in this panel
+            const int jj = w - (NBLK - 1 - p);
+            if (jj >= 0 && jj < p + 2) {
+                const int J = (jj == p + 1) ? NBLK : jj;
+                const double* rp = Rs + 8 * J * LDT + c0 + fr * LDT + fk;
+                double m0 = 0.0, m1 = 0.0;
+                dmma884(m0, m1, N11[fr * 8 + fk], rp[0]);
+                dmma884(m0, m1, N11[fr * 8 + 4 + fk], rp[4]);
+                double* cp = Mf + 8 * J * LDT + c0 + 2 * fk * LDT + fr;
+                cp[0] = m0; cp[LDT] = m1;
+            }
+        }
         LDL_ACC(64);
         __syncthreads();
         LDL_ACC(65);
         const int nb = NBLK - 1 - p;                                            // block rows below the panel
         if (w == 0) {
             // ---------------- look-ahead: update the next diagonal block, then factor it (A1 of panel p + 1)
-            if (nb > 0) {
+            if (nb > 0 && !(LDL_ABLATE & 8)) {
                 const int g = c0 + 8;
                 double* cp = As + (g + 2 * fk) * LDT + g + fr;
                 double c0r = cp[0], c1r = cp[LDT];
@@ -269,51 +327,48 @@ __global__ void __launch_bounds__(DIAG_THREADS) ldl_diag_kernel(double* __restri
                 const long long t_f0 = clock64();
                 t_acc[4] += t_f0 - t_ph;
 #endif
-                diag_block_factor(As, g, NW + (pb ^ 1) * 128, NW + (pb ^ 1) * 128 + 64, dpan2 + 8 * (pb ^ 1), dall);
+                if (!(LDL_ABLATE & 1)) diag_block_factor(As, g, NW + (pb ^ 1) * 128, NW + (pb ^ 1) * 128 + 64, dpan2 + 8 * (pb ^ 1), dall);
 #ifdef LDL_PROFILE
                 t_acc[5] += clock64() - t_f0;
 #endif
             }
-        } else {
-            // ---------------- B: trailing blocks (I, J), p < J <= I, except the next diagonal block;  C: (I, J) with I >= p and
-            // J in {0..p, rhs}: Mfin[p][J] = N11 R[p][J] (I == p), R[I][J] -= L21[I] (N11 R[p][J]) (I > p)
-            double* my = scr + w * 64;
-            double n11f[2], dpf[2];
+        } else if ((w & 3) != 0 && !(LDL_ABLATE & 2)) {
+            // ---------------- B / C: the panel's block updates (table above), two per warp in flight.  Warps 4, 8 and 12 share warp 0's
+            // SM sub-partition and stay out: the 8 x 8 factorisation of the look-ahead is a chain of dependent FP64 instructions that
+            // measured 265 cycles per pivot while DMMAs of three other warps queued on the same FP64 pipe, against ~100 alone.
+            constexpr int NWORK = 12;
+            const int wi = w - 1 - (w >> 2);
+            double dpf[2];
 #pragma unroll
-            for (int ks = 0; ks < 2; ++ks) { n11f[ks] = N11[fr * 8 + 4 * ks + fk]; dpf[ks] = dpan[4 * ks + fk]; }
-            const int ntask = c_diag_tasks.n[p];
+            for (int ks = 0; ks < 2; ++ks) dpf[ks] = dpan[4 * ks + fk];
+            const int ntask = tabn[p];
             const int laneA = fk * LDT + fr, laneC = 2 * fk * LDT + fr, laneR = fr * LDT + fk;
-            for (int t = w - 1; t < ntask; t += DIAG_WARPS - 1) {
-                const int4 td = *reinterpret_cast<const int4*>(c_diag_tasks.v[p][t]);
-                if (td.x == 0) {
-                    double* cp = As + td.y + laneC;
-                    const double* ap = As + td.z + laneA;
-                    const double* bp = As + td.w + laneA;
-                    double c0r = cp[0], c1r = cp[LDT];
-                    dmma884(c0r, c1r, -(ap[0] * dpf[0]), bp[0]);
-                    dmma884(c0r, c1r, -(ap[4 * LDT] * dpf[1]), bp[4 * LDT]);
-                    cp[0] = c0r; cp[LDT] = c1r;
-                } else {
-                    const double* rp = Rs + td.y + laneR;
-                    double m0 = 0.0, m1 = 0.0;                                    // N11 R[p][J]
-                    dmma884(m0, m1, n11f[0], rp[0]);
-                    dmma884(m0, m1, n11f[1], rp[4]);
-                    if (td.x == 1) {
-                        double* cp = Mf + td.z + laneC;
-                        cp[0] = m0; cp[LDT] = m1;
-                    } else {
-                        double* cp = Rs + td.z + laneC;
-                        const double* ap = As + td.w + laneA;
-                        double c0r = cp[0], c1r = cp[LDT];
-                        const double a0 = -ap[0], a1 = -ap[4 * LDT];
-                        __syncwarp();
-                        my[(2 * fk) * 8 + fr] = m0; my[(2 * fk + 1) * 8 + fr] = m1;   // scratch[col][row]
-                        __syncwarp();
-                        dmma884(c0r, c1r, a0, my[fr * 8 + fk]);
-                        dmma884(c0r, c1r, a1, my[fr * 8 + 4 + fk]);
-                        cp[0] = c0r; cp[LDT] = c1r;
-                    }
+            constexpr int U = 3;         // block updates in flight per warp (51 tasks at most: two rounds)
+            for (int t0 = wi; t0 < ntask; t0 += U * NWORK) {
+                int4 td[U];
+                double cr0[U], cr1[U], av[U][2], bv[U][2];
+                double* cp[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) td[u] = tab[p * 64 + min(t0 + u * NWORK, ntask - 1)];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    cp[u] = sm + td[u].y + laneC;
+                    const double* ap = sm + td[u].z + laneA;
+                    const double* bp = sm + td[u].w + (td[u].x ? laneR : laneA);
+                    const int bstep = td[u].x ? 4 : 4 * LDT;
+                    cr0[u] = cp[u][0]; cr1[u] = cp[u][LDT];
+                    av[u][0] = ap[0]; av[u][1] = ap[4 * LDT];
+                    bv[u][0] = bp[0]; bv[u][1] = bp[bstep];
                 }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const double s0 = td[u].x ? 1.0 : dpf[0], s1 = td[u].x ? 1.0 : dpf[1];
+                    dmma884(cr0[u], cr1[u], -(av[u][0] * s0), bv[u][0]);
+                    dmma884(cr0[u], cr1[u], -(av[u][1] * s1), bv[u][1]);
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+                    if (u == 0 || t0 + u * NWORK < ntask) { cp[u][0] = cr0[u]; cp[u][LDT] = cr1[u]; }
             }
         }
         LDL_ACC(66);
@@ -323,6 +378,7 @@ __global__ void __launch_bounds__(DIAG_THREADS) ldl_diag_kernel(double* __restri
     LDL_STAMP(2);
     // ---- write L (strict lower) + D (diagonal), Linv (lower incl. the unit diagonal; the upper triangle stays zero) and y_J
     double* Li = Linv + (size_t)tk.col * ST2;
+    if (!(LDL_ABLATE & 16))
     for (int k = w; k < ST; k += DIAG_WARPS)
         for (int i = k + lane; i < ST; i += 32) {
             if (i > k) { T[k * ST + i] = As[k * LDT + i]; Li[k * ST + i] = Mf[k * LDT + i]; }

@@ -22,6 +22,23 @@ int main(int argc, char** argv) {
     for (int g = 0; g < NG; ++g) tks[g] = RedTask{g, g, g, g};
     cudaMemcpy(dt, tks.data(), sizeof(RedTask) * NG, cudaMemcpyHostToDevice);
     cudaFuncSetAttribute(ldl_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DIAG_SMEM);
+    {   // latency of one tile with every SM busy on its own copy: 20 launches back to back between two events
+        const int NREP = 20;
+        cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+        for (int g = 0; g < NG; ++g) { cudaMemcpy(dS + (size_t)g * n * n, A.data(), 8 * n * n, cudaMemcpyHostToDevice); cudaMemcpy(dx + (size_t)g * n, b.data(), 8 * n, cudaMemcpyHostToDevice); }
+        for (int rep = 0; rep < 2; ++rep) {
+            cudaEventRecord(e0);
+            for (int r = 0; r < NREP; ++r)
+#ifdef LDL_PROFILE
+                ldl_diag_kernel<<<NG, DIAG_THREADS, DIAG_SMEM>>>(dS, dL, dt, dx, dprof);
+#else
+                ldl_diag_kernel<<<NG, DIAG_THREADS, DIAG_SMEM>>>(dS, dL, dt, dx);
+#endif
+            cudaEventRecord(e1); cudaEventSynchronize(e1);
+            float ms; cudaEventElapsedTime(&ms, e0, e1);
+            printf("ablate %d: %d launches of %d tiles: %.2f us per launch\n", (int)LDL_ABLATE, NREP, NG, ms * 1e3 / NREP);
+        }
+    }
     float best = 1e9;
     for (int rep = 0; rep < 5; ++rep) {
         for (int g = 0; g < NG; ++g) { cudaMemcpy(dS + (size_t)g * n * n, A.data(), 8 * n * n, cudaMemcpyHostToDevice); cudaMemcpy(dx + (size_t)g * n, b.data(), 8 * n, cudaMemcpyHostToDevice); }
