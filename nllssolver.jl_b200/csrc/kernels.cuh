@@ -481,7 +481,7 @@ struct SchurChunk {
     short flags;      // bit0: block is stored transposed; bit1: diagonal block (cam_i == cam_j)
 };
 struct SchurPlan {
-    const int* stile_pt;          // [nstiles + 1]
+    const int* stile_pt;          // [2 * nstiles]: first point, one past the last point of every tile
     const int* chunk_off;         // [nstiles + 1]
     const int* ent_off;           // [nstiles + 1] entry range of a tile
     const SchurChunk* chunks;     // per tile sorted by length (long first)
@@ -523,7 +523,7 @@ __global__ void __launch_bounds__(SCH_THREADS, 2) schur2_kernel(DevProblem p, Sc
     int t = (blockIdx.x % G) * per + blockIdx.x / G;     // strided tile order: co-resident CTAs touch distant cameras
     if (G <= 1) t = blockIdx.x;
     if (t >= sp.nstiles) return;
-    const int pt0 = sp.stile_pt[t], pt1 = sp.stile_pt[t + 1];
+    const int pt0 = sp.stile_pt[2 * t], pt1 = sp.stile_pt[2 * t + 1];
     const int ob0 = p.obs_start[pt0], ob1 = p.obs_start[pt1];
     const int npt = pt1 - pt0, nob = ob1 - ob0;
     const int c0 = sp.chunk_off[t], c1 = sp.chunk_off[t + 1];
@@ -911,7 +911,7 @@ struct BacksubSmem {
 template <int DC, int TO, int TP>
 __global__ void __launch_bounds__(TO) backsub_kernel(DevProblem p, const int4* __restrict__ tiles, const double* __restrict__ dxc,
                                                      const double* __restrict__ Ainv, const double* __restrict__ pts, double* __restrict__ pts_next,
-                                                     double* __restrict__ x, double* __restrict__ partials) {
+                                                     double* __restrict__ x, double* __restrict__ partials, int pstride) {
     constexpr int WB = 3 * DC, NW = TO / 32;
     using SM = BacksubSmem<DC, TO, TP>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -1046,9 +1046,9 @@ __global__ void __launch_bounds__(TO) backsub_kernel(DevProblem p, const int4* _
 #pragma unroll
         for (int i = 0; i < NW; ++i) { a = nanmax(a, s_red[i]); b += s_red[NW + i]; c += s_red[2 * NW + i]; e += s_red[3 * NW + i]; }
         partials[blockIdx.x] = a;
-        partials[G + blockIdx.x] = b;
-        partials[2 * G + blockIdx.x] = c;
-        partials[3 * G + blockIdx.x] = e;
+        partials[pstride + blockIdx.x] = b;
+        partials[2 * pstride + blockIdx.x] = c;
+        partials[3 * pstride + blockIdx.x] = e;
     }
 }
 
@@ -1114,6 +1114,161 @@ __global__ void __launch_bounds__(256) reduce_stats_kernel(const double* __restr
     if (blockIdx.x == 0) { for (int i = threadIdx.x; i < n; i += 256) v = nanmax(v, src[i]); v = block_nanmax(v, s_red); }
     else { for (int i = threadIdx.x; i < n; i += 256) v += src[i]; v = block_sum(v, s_red); }
     if (threadIdx.x == 0) out[blockIdx.x] = v;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Irregular points: tracks longer than a tile holds and points with several costs on the same camera (the reference accepts both:
+// updatesymA! / updateb! just accumulate, src/linearsystem.jl:132-175).  They stay in place in the layout but belong to no tile
+// of any tile kernel / Schur plan; one CTA per point does the point pass and the back-substitution straight from global memory,
+// and schur_outlier_kernel (schur5.cuh) eliminates them.  Per-point sums keep observation order.
+// ---------------------------------------------------------------------------------------------------
+constexpr int LONG_THREADS = 256;
+
+template <class R>
+__global__ void __launch_bounds__(LONG_THREADS) lin_point_long_kernel(DevProblem p, const int* __restrict__ long_pts, const double* __restrict__ cams,
+                                                                      const double* __restrict__ pts, double* __restrict__ cost_partials) {
+    constexpr int DC = R::DC, WB = 3 * DC, NW = LONG_THREADS / 32;
+    __shared__ double s_pc[9 * LONG_THREADS];
+    __shared__ double s_red[NW];
+    __shared__ double s_acc[9];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int pt = long_pts[blockIdx.x];
+    const int ob0 = p.obs_start[pt], k = p.obs_start[pt + 1] - ob0;
+    double* hrow = p.H + (size_t)p.hB + (size_t)WB * ob0 + (size_t)9 * pt;
+    const double X[3] = {pts[(size_t)3 * pt], pts[(size_t)3 * pt + 1], pts[(size_t)3 * pt + 2]};
+    const bool fpt = p.fixB != nullptr && p.fixB[pt];
+    if (tid < 9) s_acc[tid] = 0.0;
+    double c = 0.0;
+    for (int base = 0; base < k; base += LONG_THREADS) {
+        const int i = base + tid;
+        if (i < k) {
+            const int j = ob0 + i;
+            const int cam = p.obs_cam[j];
+            const double2 z = p.obs_z[j];
+            double cv[R::NC];
+            R::load_cam(cams, cam, cv);
+            double r[2], Jc[2][DC], Jp[2][3];
+            R::resjac(cv, X, z.x, z.y, r, Jc, Jp);
+            const double s = r[0] * r[0] + r[1] * r[1];
+            double rho, d1, d2;
+            robustifydcost(p.rk, s, rho, d1, d2);
+            c += 0.5 * rho;
+            const bool fcross = fpt || (p.fixA != nullptr && p.fixA[cam]);
+            double gc[DC], gp[3];
+#pragma unroll
+            for (int a = 0; a < DC; ++a) gc[a] = jtr<R>(Jc, r, a);
+#pragma unroll
+            for (int b = 0; b < 3; ++b) gp[b] = fma(Jp[1][b], r[1], Jp[0][b] * r[0]);
+            const double td2 = 2 * d2;
+            double* wd = hrow + (size_t)WB * i;
+#pragma unroll
+            for (int a = 0; a < DC; ++a)
+#pragma unroll
+                for (int b = 0; b < 3; ++b) {
+                    double h = jtj_pc<R>(Jp, Jc, b, a);
+                    if (d1 != 1.0) h *= d1;
+                    if (d2 != 0.0) h = fma(td2 * gp[b], gc[a], h);
+                    wd[b + 3 * a] = fcross ? 0.0 : h;
+                }
+            int q = 0;
+#pragma unroll
+            for (int b2 = 0; b2 < 3; ++b2)
+#pragma unroll
+                for (int b = b2; b < 3; ++b) {
+                    double h = fma(Jp[1][b], Jp[1][b2], Jp[0][b] * Jp[0][b2]);
+                    if (d1 != 1.0) h *= d1;
+                    if (d2 != 0.0) h = fma(td2 * gp[b], gp[b2], h);
+                    s_pc[9 * tid + (q++)] = fpt ? 0.0 : h;
+                }
+#pragma unroll
+            for (int b = 0; b < 3; ++b) s_pc[9 * tid + 6 + b] = fpt ? 0.0 : ((d1 != 1.0) ? gp[b] * d1 : gp[b]);
+        }
+        __syncthreads();
+        if (tid < 9) {   // element tid of (V_p lower triangle, g_p): this chunk's observations in order
+            double v = s_acc[tid];
+            const int n = min(LONG_THREADS, k - base);
+            for (int j = 0; j < n; ++j) v += s_pc[9 * j + tid];
+            s_acc[tid] = v;
+        }
+        __syncthreads();
+    }
+    if (tid < 9) {
+        double v = s_acc[tid];
+        if (fpt) v = (tid == 0 || tid == 3 || tid == 5) ? 1.0 : 0.0;
+        if (tid < 6) {
+            double* V = hrow + (size_t)WB * k;
+            const int pa = (0x854210 >> (4 * tid)) & 15, pb = (0x874630 >> (4 * tid)) & 15;
+            V[pa] = v;
+            if (pb != pa) V[pb] = v;
+        } else {
+            p.g[p.gB + (size_t)3 * pt + (tid - 6)] = v;
+        }
+    }
+    c = warp_sum(c);
+    if (lane == 0) s_red[wid] = c;
+    __syncthreads();
+    if (tid == 0) {
+        double tsum = 0.0;
+#pragma unroll
+        for (int i = 0; i < NW; ++i) tsum += s_red[i];
+        cost_partials[blockIdx.x] = tsum;
+    }
+}
+
+// x_p = -A_p^-1 (g_p - sum_c W_pc dx_c), varnext, step statistics: one CTA per irregular point; partials[k * pstride + slot0 + blockIdx.x]
+template <int DC>
+__global__ void __launch_bounds__(LONG_THREADS) backsub_long_kernel(DevProblem p, const int* __restrict__ long_pts, const double* __restrict__ dxc,
+                                                                    const double* __restrict__ Ainv, const double* __restrict__ pts, double* __restrict__ pts_next,
+                                                                    double* __restrict__ x, double* __restrict__ partials, int pstride, int slot0) {
+    constexpr int WB = 3 * DC;
+    __shared__ double s_u[3 * LONG_THREADS];
+    __shared__ double s_acc[3];
+    const int tid = threadIdx.x;
+    const int pt = long_pts[blockIdx.x];
+    const int ob0 = p.obs_start[pt], k = p.obs_start[pt + 1] - ob0;
+    const double* hrow = p.H + (size_t)p.hB + (size_t)WB * ob0 + (size_t)9 * pt;
+    if (tid < 3) s_acc[tid] = 0.0;
+    for (int base = 0; base < k; base += LONG_THREADS) {
+        const int i = base + tid;
+        if (i < k) {
+            const int cam = p.obs_cam[ob0 + i];
+            const double* w = hrow + (size_t)WB * i;
+            double u0 = 0, u1 = 0, u2 = 0;
+#pragma unroll
+            for (int a = 0; a < DC; ++a) { const double d = dxc[(size_t)cam * DC + a]; u0 += w[3 * a] * d; u1 += w[3 * a + 1] * d; u2 += w[3 * a + 2] * d; }
+            s_u[tid] = u0; s_u[LONG_THREADS + tid] = u1; s_u[2 * LONG_THREADS + tid] = u2;
+        }
+        __syncthreads();
+        if (tid < 3) {
+            double v = s_acc[tid];
+            const int n = min(LONG_THREADS, k - base);
+            for (int j = 0; j < n; ++j) v += s_u[tid * LONG_THREADS + j];
+            s_acc[tid] = v;
+        }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        const double u0 = s_acc[0], u1 = s_acc[1], u2 = s_acc[2];
+        const double* pg = p.g + p.gB + (size_t)3 * pt;
+        const double* pa = Ainv + (size_t)6 * pt;
+        const double r0 = pg[0] - u0, r1 = pg[1] - u1, r2 = pg[2] - u2;
+        const double x0 = -(pa[0] * r0 + pa[1] * r1 + pa[2] * r2);
+        const double x1 = -(pa[1] * r0 + pa[3] * r1 + pa[4] * r2);
+        const double x2 = -(pa[2] * r0 + pa[4] * r1 + pa[5] * r2);
+        x[p.gB + (size_t)3 * pt] = x0; x[p.gB + (size_t)3 * pt + 1] = x1; x[p.gB + (size_t)3 * pt + 2] = x2;
+        pts_next[(size_t)3 * pt] = pts[(size_t)3 * pt] + x0;
+        pts_next[(size_t)3 * pt + 1] = pts[(size_t)3 * pt + 1] + x1;
+        pts_next[(size_t)3 * pt + 2] = pts[(size_t)3 * pt + 2] + x2;
+        const double* V = hrow + (size_t)WB * k;
+        const double v0 = V[0] * x0 + V[3] * x1 + V[6] * x2;
+        const double v1 = V[1] * x0 + V[4] * x1 + V[7] * x2;
+        const double v2 = V[2] * x0 + V[5] * x1 + V[8] * x2;
+        const int o = slot0 + blockIdx.x;
+        partials[o] = nanmax(nanmax(fabs(x0), fabs(x1)), fabs(x2));
+        partials[pstride + o] = x0 * x0 + x1 * x1 + x2 * x2;
+        partials[2 * pstride + o] = (x0 * v0 + x1 * v1 + x2 * v2) - 2.0 * (x0 * u0 + x1 * u1 + x2 * u2);
+        partials[3 * pstride + o] = pg[0] * x0 + pg[1] * x1 + pg[2] * x2;
+    }
 }
 
 }  // namespace nlls

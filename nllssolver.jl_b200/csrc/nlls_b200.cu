@@ -173,7 +173,12 @@ struct nlls_ctx {
     Schur5Item* d5_items = nullptr;
     unsigned int* d5_blob = nullptr;
     long long* d5_ftab = nullptr;
-    int* d_out_pts = nullptr;       // points outside the v5 window plan (schur_outlier_kernel)
+    int* d_out_pts = nullptr;       // points outside the Schur plans (schur_outlier_kernel): the v5 plan's own outliers, then from first_irr on the irregular points
+    // irregular points (tracks longer than a tile holds, several costs on one camera): no tile of any kernel / plan holds them
+    std::vector<unsigned char> h_irr;
+    int nlong = 0, first_irr = 0;
+    bool has_dups = false;
+    int* d_long_pts = nullptr;
     int* d_cta_item = nullptr;
     SchurItem* d_items = nullptr;
     SchurUnit* d_units = nullptr;
@@ -362,6 +367,10 @@ int launch_linearize(nlls_ctx* ctx, bool do_point = true, int do_cam = 1) {
             lin_point_kernel<R, 256, 128><<<ctx->lin_grid, 256, LinSmem<R, 256, 128>::bytes, ctx->st>>>(p, ctx->d_tiles, ctx->d_A[ctx->cur], ctx->d_B[ctx->cur], ctx->d_cost_part);
         ctx->launches++;
     }
+    if (do_point && ctx->nlong > 0) {   // irregular points: one CTA each, cost partials behind the tiles'
+        lin_point_long_kernel<R><<<ctx->nlong, LONG_THREADS, 0, ctx->st>>>(p, ctx->d_long_pts, ctx->d_A[ctx->cur], ctx->d_B[ctx->cur], ctx->d_cost_part + ctx->ntiles);
+        ctx->launches++;
+    }
     if (do_cam) CK(cudaStreamWaitEvent(ctx->st, ctx->ev_join, 0));
     CK(cudaGetLastError());
     return NLLS_OK;
@@ -376,7 +385,7 @@ int launch_cost(nlls_ctx* ctx, int which, int slot, double* part = nullptr, bool
     DevProblem p = devproblem(ctx);
     constexpr int NU = R::DC * (R::DC + 1) / 2 + R::DC;
     if (!part) part = ctx->d_cam_part;
-    if (ctx->cost_pointmajor) {   // NLLS_B200_COST=tiles: the round-1 cost kernel (point-major tiles)
+    if (ctx->cost_pointmajor && ctx->nlong == 0) {   // NLLS_B200_COST=tiles: the round-1 cost kernel (point-major tiles)
         if (ctx->ntiles > 0) {
             if (ctx->tile_obs == 64) cost_kernel<R, 64><<<ctx->cost_grid, 64, 0, ctx->st>>>(p, ctx->d_tiles, ctx->d_A[which], ctx->d_B[which], ctx->d_cost_part);
             else if (ctx->tile_obs == 128) cost_kernel<R, 128><<<ctx->cost_grid, 128, 0, ctx->st>>>(p, ctx->d_tiles, ctx->d_A[which], ctx->d_B[which], ctx->d_cost_part);
@@ -435,10 +444,6 @@ int launch_schur(nlls_ctx* ctx, double lambda) {
             for (int c = 0; c < ctx->n5cta; ++c) { const double t = (double)h[((size_t)c * 16) * 4 + 1]; cmin = std::min(cmin, t); cmax = std::max(cmax, t); }
             fprintf(stderr, "[nlls] schur5 CTA time (consumer 0): min %.0f max %.0f\n", cmin, cmax);
         }
-        if (ctx->nout_pts > 0) {   // points outside the window plan (gaps in the camera list, very long tracks)
-            schur_outlier_kernel<DC><<<(ctx->nout_pts * 32 + 127) / 128, 128, 0, ctx->st>>>(p, ctx->d_out_pts, ctx->nout_pts, ctx->d_S, ctx->d_rhs, lambda);
-            ctx->launches++;
-        }
     } else if (ctx->schur_v4 && ctx->nsuper > 0) {
         SchurPlan4 sp;
         sp.cta_item = ctx->d_cta_item; sp.items = ctx->d_items; sp.units = ctx->d_units; sp.blob = ctx->d_blob; sp.wtab = ctx->d_wtab;
@@ -452,6 +457,10 @@ int launch_schur(nlls_ctx* ctx, double lambda) {
         const int G = std::max(1, ctx->schur_stride);
         const int grid = G * ((ctx->nstiles + G - 1) / G);
         schur2_kernel<DC><<<grid, SCH_THREADS, Schur2Smem<DC>::bytes, ctx->st>>>(p, sp, ctx->d_S, ctx->d_rhs, ctx->d_Ainv, lambda);
+        ctx->launches++;
+    }
+    if (ctx->nout_pts > 0) {   // points outside the plans: gaps in the camera list / wide tracks (v5), and the irregular points (their A_p^-1 too)
+        schur_outlier_kernel<DC><<<(ctx->nout_pts * 32 + 127) / 128, 128, 0, ctx->st>>>(p, ctx->d_out_pts, ctx->nout_pts, ctx->d_S, ctx->d_rhs, lambda, ctx->first_irr, ctx->d_Ainv);
         ctx->launches++;
     }
     CK(cudaGetLastError());
@@ -533,22 +542,28 @@ template <class R>
 int launch_update(nlls_ctx* ctx) {
     constexpr int DC = R::DC;
     DevProblem p = devproblem(ctx);
-    const int bg = ctx->bs_grid;
+    const int bg = ctx->ntiles > 0 ? ctx->bs_grid : 0;
+    const int ps = bg + ctx->nlong;      // step-statistics partials per quantity: the tile kernel's CTAs, then one per irregular point
     if (ctx->ntiles > 0) {
         if (ctx->tile_obs == 64)
             backsub_kernel<DC, 64, 32><<<bg, 64, BacksubSmem<DC, 64, 32>::bytes, ctx->st>>>(p, ctx->d_tiles, ctx->d_rhs, ctx->d_Ainv, ctx->d_B[ctx->cur],
-                                                                                             ctx->d_B[ctx->nxt], ctx->d_x, ctx->d_step_part);
+                                                                                             ctx->d_B[ctx->nxt], ctx->d_x, ctx->d_step_part, ps);
         else if (ctx->tile_obs == 128)
             backsub_kernel<DC, 128, 64><<<bg, 128, BacksubSmem<DC, 128, 64>::bytes, ctx->st>>>(p, ctx->d_tiles, ctx->d_rhs, ctx->d_Ainv, ctx->d_B[ctx->cur],
-                                                                                                ctx->d_B[ctx->nxt], ctx->d_x, ctx->d_step_part);
+                                                                                                ctx->d_B[ctx->nxt], ctx->d_x, ctx->d_step_part, ps);
         else
             backsub_kernel<DC, 256, 128><<<bg, 256, BacksubSmem<DC, 256, 128>::bytes, ctx->st>>>(p, ctx->d_tiles, ctx->d_rhs, ctx->d_Ainv, ctx->d_B[ctx->cur],
-                                                                                                  ctx->d_B[ctx->nxt], ctx->d_x, ctx->d_step_part);
+                                                                                                  ctx->d_B[ctx->nxt], ctx->d_x, ctx->d_step_part, ps);
+        ctx->launches++;
+    }
+    if (ctx->nlong > 0) {
+        backsub_long_kernel<DC><<<ctx->nlong, LONG_THREADS, 0, ctx->st>>>(p, ctx->d_long_pts, ctx->d_rhs, ctx->d_Ainv, ctx->d_B[ctx->cur], ctx->d_B[ctx->nxt], ctx->d_x,
+                                                                         ctx->d_step_part, ps, bg);
         ctx->launches++;
     }
     const int cg = (int)((ctx->nA + 127) / 128);
     cam_update_kernel<R><<<cg, 128, 0, ctx->st>>>(p, ctx->d_rhs, ctx->d_A[ctx->cur], ctx->d_A[ctx->nxt], ctx->d_x, ctx->d_camstat_part); ctx->launches++;
-    reduce_stats_kernel<<<4, 256, 0, ctx->st>>>(ctx->d_step_part, ctx->ntiles > 0 ? bg : 0, ctx->d_scal + SC_P_MAX); ctx->launches++;
+    reduce_stats_kernel<<<4, 256, 0, ctx->st>>>(ctx->d_step_part, ps, ctx->d_scal + SC_P_MAX); ctx->launches++;
     reduce_stats_kernel<<<4, 256, 0, ctx->st>>>(ctx->d_camstat_part, cg, ctx->d_scal + SC_C_MAX); ctx->launches++;
     CK(cudaGetLastError());
     return NLLS_OK;
@@ -761,7 +776,7 @@ int do_linearize(nlls_ctx* ctx, double* cost) {
     const int cam_mode = (ctx->cam_part_vars == ctx->cur) ? 2 : 1;
     TRY(DISPATCH(ctx, launch_linearize, ctx, true, cam_mode));
     ctx->cam_part_vars = -1;
-    reduce_partials_kernel<<<1, 1024, 0, ctx->st>>>(ctx->d_cost_part, ctx->ntiles, ctx->d_scal + SC_COST_LIN, 0); ctx->launches++;
+    reduce_partials_kernel<<<1, 1024, 0, ctx->st>>>(ctx->d_cost_part, ctx->ntiles + ctx->nlong, ctx->d_scal + SC_COST_LIN, 0); ctx->launches++;
     CK(cudaGetLastError());
     if (ctx->nranks > 1) {  // camera blocks, camera gradient and the cost are sums over all ranks' observations: one grouped launch
         CKN(g_nccl.GroupStart());
@@ -997,7 +1012,7 @@ int nlls_destroy(nlls_ctx* ctx) {
                     ctx->d_lvl_cols, ctx->d_red_tasks, ctx->d_red_upds, ctx->d_red_targets, ctx->d_colptr,
                     ctx->d_col_tile, ctx->d_col_row, ctx->d_Linv, ctx->d_xp, ctx->d_stile_pt, ctx->d_chunk_off, ctx->d_chunks, ctx->d_ents, ctx->d_tiles, ctx->d_camstat_part,
                     ctx->d_ad_data, ctx->d_ad_chunks, ctx->d_ad_moff, ctx->d_ad_part, ctx->d_ent_off, ctx->d_cta_item, ctx->d_items, ctx->d_units, ctx->d_wtab, ctx->d_blob,
-                    ctx->d5_cta_item, ctx->d5_items, ctx->d5_blob, ctx->d5_ftab, ctx->d_out_pts, ctx->d_bwd_order, ctx->d_bwd_flags, ctx->d_nat_of_pos, ctx->d_fixA, ctx->d_fixB, ctx->d_cauchy, ctx->d_vec_part};
+                    ctx->d5_cta_item, ctx->d5_items, ctx->d5_blob, ctx->d5_ftab, ctx->d_out_pts, ctx->d_bwd_order, ctx->d_bwd_flags, ctx->d_nat_of_pos, ctx->d_long_pts, ctx->d_fixA, ctx->d_fixB, ctx->d_cauchy, ctx->d_vec_part};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (ctx->red_graph_exec) cudaGraphExecDestroy(ctx->red_graph_exec);
     if (ctx->h_scal) cudaFreeHost(ctx->h_scal);
@@ -1176,22 +1191,33 @@ int nlls_prepare(nlls_ctx* ctx) {
     }
     ctx->h_obs_start.assign((size_t)nB + 1, 0);
     for (int64_t p = 0; p < nB; ++p) ctx->h_obs_start[(size_t)p + 1] = ctx->h_obs_start[(size_t)p] + cnt[(size_t)p + 1];
-    {
-        int maxk = 0;
-        for (int64_t p = 0; p < nB; ++p) maxk = std::max(maxk, cnt[(size_t)p + 1]);
-        ctx->tile_obs = ctx->tile_env ? ctx->tile_env : (maxk <= 64 ? 64 : (maxk <= 128 ? 128 : 256));
-    }
+    // irregular points: more observations than the smallest tile capacity of the kernels / Schur plans in use (KCAP), or two costs
+    // on one camera.  The reference accepts both (src/linearsystem.jl:132-175 accumulates); here they are left out of every tile and
+    // handled by one-CTA-per-point kernels (lin_point_long / backsub_long) and the Schur fallback kernel.
+    const int KCAP = std::min(ctx->tile_env ? ctx->tile_env : 256, (DC <= 6) ? 232 : 128);
+    ctx->h_irr.assign((size_t)nB, 0);
+    ctx->has_dups = false;
     std::vector<int> fill(ctx->h_obs_start.begin(), ctx->h_obs_start.end() - 1);
     std::vector<int> order((size_t)nobs);
     for (int64_t i = 0; i < nobs; ++i) order[(size_t)fill[(size_t)ptl[(size_t)i]]++] = (int)i;
-    for (int64_t p = 0; p < nB; ++p) {
-        int* b = order.data() + ctx->h_obs_start[(size_t)p];
-        int* e = order.data() + ctx->h_obs_start[(size_t)p + 1];
-        if (e - b > ctx->tile_obs) FAIL(NLLS_ERR_UNSUPPORTED, "a point with more than " + std::to_string(ctx->tile_obs) + " observations");
-        std::stable_sort(b, e, [&](int x, int y) { return caml[(size_t)x] < caml[(size_t)y]; });
-        for (int* q = b + 1; q < e; ++q)
-            if (caml[(size_t)*q] == caml[(size_t)*(q - 1)]) FAIL(NLLS_ERR_UNSUPPORTED, "two costs on the same (camera, point) pair");
+    {
+        int maxk = 0;
+        for (int64_t p = 0; p < nB; ++p) {
+            int* b = order.data() + ctx->h_obs_start[(size_t)p];
+            int* e = order.data() + ctx->h_obs_start[(size_t)p + 1];
+            std::stable_sort(b, e, [&](int x, int y) { return caml[(size_t)x] < caml[(size_t)y]; });
+            if (e - b > KCAP) ctx->h_irr[(size_t)p] = 1;
+            for (int* q = b + 1; q < e; ++q)
+                if (caml[(size_t)*q] == caml[(size_t)*(q - 1)]) { ctx->h_irr[(size_t)p] = 1; ctx->has_dups = true; }
+            if (!ctx->h_irr[(size_t)p]) maxk = std::max(maxk, (int)(e - b));
+        }
+        ctx->tile_obs = ctx->tile_env ? ctx->tile_env : (maxk <= 64 ? 64 : (maxk <= 128 ? 128 : 256));
     }
+    std::vector<int> long_pts;
+    for (int64_t p = 0; p < nB; ++p) if (ctx->h_irr[(size_t)p]) long_pts.push_back((int)p);
+    ctx->nlong = (int)long_pts.size();
+    TRY(upload(ctx, &ctx->d_long_pts, long_pts));
+    if (getenv("NLLS_B200_VERBOSE") && ctx->nlong) fprintf(stderr, "[nlls] %d irregular points (more than %d observations, or several costs on one camera)\n", ctx->nlong, KCAP);
     ctx->h_obs_cam.resize((size_t)nobs); ctx->h_obs_pt.resize((size_t)nobs);
     std::vector<double2> obs_z((size_t)nobs);
     for (int64_t j = 0; j < nobs; ++j) {
@@ -1199,19 +1225,19 @@ int nlls_prepare(nlls_ctx* ctx) {
         ctx->h_obs_cam[(size_t)j] = caml[(size_t)i]; ctx->h_obs_pt[(size_t)j] = ptl[(size_t)i];
         obs_z[(size_t)j] = make_double2(ctx->h_z[(size_t)2 * i], ctx->h_z[(size_t)2 * i + 1]);
     }
-    // tiles: consecutive points, <= tile_obs observations and <= tile_obs / 2 points
+    // tiles: consecutive regular points, <= tile_obs observations and <= tile_obs / 2 points; h_tile_pt holds (first, one past last) pairs
     ctx->h_tile_pt.clear();
-    ctx->h_tile_pt.push_back(0);
     {
         int64_t p0 = 0;
         while (p0 < nB) {
+            if (ctx->h_irr[(size_t)p0]) { ++p0; continue; }
             int64_t p1 = p0;
-            while (p1 < nB && (p1 - p0) < ctx->tile_obs / 2 && (ctx->h_obs_start[(size_t)p1 + 1] - ctx->h_obs_start[(size_t)p0]) <= ctx->tile_obs) ++p1;
-            ctx->h_tile_pt.push_back((int)p1);
+            while (p1 < nB && !ctx->h_irr[(size_t)p1] && (p1 - p0) < ctx->tile_obs / 2 && (ctx->h_obs_start[(size_t)p1 + 1] - ctx->h_obs_start[(size_t)p0]) <= ctx->tile_obs) ++p1;
+            ctx->h_tile_pt.push_back((int)p0); ctx->h_tile_pt.push_back((int)p1);
             p0 = p1;
         }
     }
-    ctx->ntiles = (int)ctx->h_tile_pt.size() - 1;
+    ctx->ntiles = (int)ctx->h_tile_pt.size() / 2;
     // camera-major copy + work items
     ctx->h_cam_start.assign((size_t)nA + 1, 0);
     for (int64_t j = 0; j < nobs; ++j) ctx->h_cam_start[(size_t)ctx->h_obs_cam[(size_t)j] + 1]++;
@@ -1377,6 +1403,7 @@ int nlls_prepare(nlls_ctx* ctx) {
 
     // ---- Schur v5 plan (schur5_plan.hpp): window-aligned register accumulation; points that do not fit go to the per-chunk kernel
     ctx->n5cta = 0; ctx->nout_pts = 0;
+    std::vector<int> out_pts;
     if (ctx->schur_v5) {
         if (const char* e = getenv("NLLS_B200_S5_COST")) {   // development aid: "dmma,afrag,bfrag,fixed"
             Schur5Cost& cm = schur5_cost();
@@ -1386,8 +1413,9 @@ int nlls_prepare(nlls_ctx* ctx) {
         if (const char* e = getenv("NLLS_B200_S5_CONS")) ctx->s5_ncons = std::max(1, std::min(atoi(e), S5_CONSUMERS));
         int maxrun = 48;
         if (const char* e = getenv("NLLS_B200_S5_RUN")) maxrun = std::max(1, atoi(e));
-        Schur5Plan P5 = (DC == 6) ? schur5_build_plan<6>(ctx->h_obs_start, ctx->h_obs_cam, nA, ctx->nsm, maxrun, ctx->s5_ncons)
-                                  : schur5_build_plan<9>(ctx->h_obs_start, ctx->h_obs_cam, nA, ctx->nsm, maxrun, ctx->s5_ncons);
+        const std::vector<unsigned char>* irr = ctx->nlong ? &ctx->h_irr : nullptr;
+        Schur5Plan P5 = (DC == 6) ? schur5_build_plan<6>(ctx->h_obs_start, ctx->h_obs_cam, nA, ctx->nsm, maxrun, ctx->s5_ncons, irr)
+                                  : schur5_build_plan<9>(ctx->h_obs_start, ctx->h_obs_cam, nA, ctx->nsm, maxrun, ctx->s5_ncons, irr);
         ctx->s5_ncons = std::max(ctx->s5_ncons, DC == 6 ? Schur5Cfg<6>::NBANDS : Schur5Cfg<9>::NBANDS);
         // automatic choice: (almost) everything fits the window plan, and every CTA has a few tiles to pipeline (a problem of one tile
         // per SM — Ladybug-shape — is 10 % faster with v4)
@@ -1401,24 +1429,28 @@ int nlls_prepare(nlls_ctx* ctx) {
             TRY(upload(ctx, &ctx->d5_cta_item, P5.cta_item)); TRY(upload(ctx, &ctx->d5_items, P5.items)); TRY(upload(ctx, &ctx->d5_blob, P5.blob));
             const std::vector<long long> ft = (DC == 6) ? schur5_flush_table<6>(P5.super_base, tile_id, pos, ctx->NT) : schur5_flush_table<9>(P5.super_base, tile_id, pos, ctx->NT);
             TRY(upload(ctx, &ctx->d5_ftab, ft));
-            ctx->nout_pts = (int)P5.outliers.size();
-            TRY(upload(ctx, &ctx->d_out_pts, P5.outliers));
+            out_pts = P5.outliers;
         }
     }
+    // the fallback kernel's list: the plan's own outliers (their A_p^-1 comes from the plan's kernel), then the irregular points
+    ctx->first_irr = (int)out_pts.size();
+    for (int64_t p2 = 0; p2 < nB; ++p2) if (ctx->h_irr[(size_t)p2]) out_pts.push_back((int)p2);
+    ctx->nout_pts = (int)out_pts.size();
+    TRY(upload(ctx, &ctx->d_out_pts, out_pts));
 
     // ---- Schur v2 plan: larger point tiles + per-tile contribution lists sorted by target block
     ctx->nsuper = 0; ctx->nstiles = 0;
     if (ctx->schur_v2 && ctx->n5cta == 0) {
-        std::vector<int> stile_pt;
-        stile_pt.push_back(0);
+        std::vector<int> stile_pt;     // (first point, one past the last point) per tile; irregular points belong to no tile
         {
             auto aligned = [&](int64_t pt) { return ((WB * (int64_t)ctx->h_obs_start[(size_t)pt] + 9 * pt) & 1) == 0; };
             const int sobs = (DC <= 7) ? 232 : 128, spts = sobs / 2;   // == Schur4Cfg<DC>::OBS / PTS (<= SCH_OBS / SCH_PTS of the v2 kernel)
             int64_t p0 = 0;
             while (p0 < nB) {
+                if (ctx->h_irr[(size_t)p0]) { ++p0; continue; }
                 int64_t p1 = p0;
                 int64_t contrib = 0;   // pairs (i, j <= i) of the tile: the v4 kernel stages the padded list in shared memory
-                while (p1 < nB && (p1 - p0) < spts && (ctx->h_obs_start[(size_t)p1 + 1] - ctx->h_obs_start[(size_t)p0]) <= sobs) {
+                while (p1 < nB && !ctx->h_irr[(size_t)p1] && (p1 - p0) < spts && (ctx->h_obs_start[(size_t)p1 + 1] - ctx->h_obs_start[(size_t)p0]) <= sobs) {
                     const int64_t kk = ctx->h_obs_start[(size_t)p1 + 1] - ctx->h_obs_start[(size_t)p1];
                     if (p1 > p0 && contrib + kk * (kk + 1) / 2 > Schur4Cfg<6>::MAXENT - 4 * SCH4_WARPS) break;   // (+ quad padding per warp)
                     contrib += kk * (kk + 1) / 2;
@@ -1426,11 +1458,11 @@ int nlls_prepare(nlls_ctx* ctx) {
                 }
                 if (p1 < nB && !aligned(p1) && p1 - 1 > p0 && aligned(p1 - 1)) --p1;
                 if (p1 == p0) FAIL(NLLS_ERR_UNSUPPORTED, "a point with more observations than a Schur tile holds");
-                stile_pt.push_back((int)p1);
+                stile_pt.push_back((int)p0); stile_pt.push_back((int)p1);
                 p0 = p1;
             }
         }
-        const int nst = (int)stile_pt.size() - 1;
+        const int nst = (int)stile_pt.size() / 2;
         ctx->nstiles = nst;
         const int TC = ST / DC;
         const int NTl = ctx->NT;
@@ -1440,7 +1472,7 @@ int nlls_prepare(nlls_ctx* ctx) {
         auto build = [&](int t0, int t1) {
             std::vector<unsigned long long> keys;
             for (int t = t0; t < t1; ++t) {
-                const int pa = stile_pt[(size_t)t], pb = stile_pt[(size_t)t + 1];
+                const int pa = stile_pt[(size_t)2 * t], pb = stile_pt[(size_t)2 * t + 1];
                 const int ob0 = ctx->h_obs_start[(size_t)pa];
                 keys.clear();
                 for (int pp = pa; pp < pb; ++pp) {
@@ -1606,8 +1638,8 @@ int nlls_prepare(nlls_ctx* ctx) {
                         for (int t = ta; t < tb; ++t) {
                             const TilePlan& pl = plans[(size_t)t];
                             SchurItem it;
-                            it.pt0 = stile_pt[(size_t)t]; it.npt = stile_pt[(size_t)t + 1] - it.pt0;
-                            it.ob0 = ctx->h_obs_start[(size_t)it.pt0]; it.nob = ctx->h_obs_start[(size_t)stile_pt[(size_t)t + 1]] - it.ob0;
+                            it.pt0 = stile_pt[(size_t)2 * t]; it.npt = stile_pt[(size_t)2 * t + 1] - it.pt0;
+                            it.ob0 = ctx->h_obs_start[(size_t)it.pt0]; it.nob = ctx->h_obs_start[(size_t)stile_pt[(size_t)2 * t + 1]] - it.ob0;
                             it.wrow = (int)(wtab.size() / (size_t)wstride);
                             it.urow = (t == tb - 1) ? urow0 + r : -1;
                             it.flags = ((t == ta) ? 1 : 0) | ((r == 0) ? 2 : 0) |
@@ -1696,7 +1728,7 @@ int nlls_prepare(nlls_ctx* ctx) {
     {
         std::vector<int4> tiles((size_t)ctx->ntiles);
         for (int t = 0; t < ctx->ntiles; ++t) {
-            const int a = ctx->h_tile_pt[(size_t)t], b = ctx->h_tile_pt[(size_t)t + 1];
+            const int a = ctx->h_tile_pt[(size_t)2 * t], b = ctx->h_tile_pt[(size_t)2 * t + 1];
             tiles[(size_t)t] = make_int4(a, b - a, ctx->h_obs_start[(size_t)a], ctx->h_obs_start[(size_t)b] - ctx->h_obs_start[(size_t)a]);
         }
         TRY(upload(ctx, &ctx->d_tiles, tiles));
@@ -1733,7 +1765,7 @@ int nlls_prepare(nlls_ctx* ctx) {
         }
         TRY(upload(ctx, &ctx->d_colptr, colptr)); TRY(upload(ctx, &ctx->d_col_tile, col_tile)); TRY(upload(ctx, &ctx->d_col_row, col_row));
     }
-    TRY(dalloc(ctx, &ctx->d_cost_part, (size_t)ctx->ntiles)); TRY(dalloc(ctx, &ctx->d_step_part, (size_t)4 * ctx->ntiles));
+    TRY(dalloc(ctx, &ctx->d_cost_part, (size_t)ctx->ntiles + ctx->nlong)); TRY(dalloc(ctx, &ctx->d_step_part, (size_t)4 * (ctx->ntiles + ctx->nlong)));
     const int NU = DC * (DC + 1) / 2 + DC;
     TRY(dalloc(ctx, &ctx->d_cam_part, (size_t)ctx->nitems * (NU + 1))); TRY(dalloc(ctx, &ctx->d_cam_part2, (size_t)ctx->nitems * (NU + 1)));
     ctx->cam_part_vars = -1;
@@ -2070,6 +2102,7 @@ int nlls_get_step(nlls_ctx* ctx, double* x) {
 int nlls_get_hessian_blocks(nlls_ctx* ctx, double* data) {
     if (!ctx || !ctx->prepared || !data) return NLLS_ERR_INVALID;
     if (ctx->masked) FAIL(NLLS_ERR_UNSUPPORTED, "Hessian read-back under an unfixed mask (fixed variables are frozen in place, not removed)");
+    if (ctx->has_dups) FAIL(NLLS_ERR_UNSUPPORTED, "Hessian read-back with several costs on one (camera, point) pair (the device keeps one block per cost)");
     CK(cudaSetDevice(ctx->device));
     if (ctx->cams_first) {  // internal layout == reference layout
         CK(cudaMemcpyAsync(data, ctx->d_H, sizeof(double) * ctx->hlen, cudaMemcpyDeviceToHost, ctx->st));

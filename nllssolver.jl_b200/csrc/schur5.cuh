@@ -379,12 +379,14 @@ __global__ void __launch_bounds__(S5_THREADS, 1) schur5_kernel(DevProblem p, Sch
 }
 
 // ---------------------------------------------------------------------------------------------------
-// The points the window plan leaves out (gaps in the camera list, tracks wider than the window): one warp per point straight
-// from global memory, one lane per block pair (i >= j), FP64 reductions into S.  A few thousand points at most.
+// The points the plans leave out (gaps in the camera list, tracks wider than the window; from index first_irr on: irregular points
+// — tracks longer than a tile, several costs on one camera — that belong to no tile at all, so their A_p^-1 is written here): one
+// warp per point straight from global memory, one lane per block pair (i >= j), FP64 reductions into S.  A few thousand points at
+// most.  Two costs of a point on the SAME camera (i != j, ci == cj) add W_i' Y_j + W_j' Y_i to the diagonal block.
 // ---------------------------------------------------------------------------------------------------
 template <int DC>
 __global__ void __launch_bounds__(128) schur_outlier_kernel(DevProblem p, const int* __restrict__ pts, int npts, double* __restrict__ S,
-                                                            double* __restrict__ rhs, double lambda) {
+                                                            double* __restrict__ rhs, double lambda, int first_irr = 0x7fffffff, double* __restrict__ Ainv = nullptr) {
     constexpr int WB = 3 * DC;
     const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (wid >= npts) return;
@@ -395,6 +397,10 @@ __global__ void __launch_bounds__(128) schur_outlier_kernel(DevProblem p, const 
     const double a6[6] = {V[0] + lambda, V[1], V[2], V[4] + lambda, V[5], V[8] + lambda};
     double inv[6];
     inv_sym3(a6, inv);
+    if (wid >= first_irr && lane == 0) {
+#pragma unroll
+        for (int e = 0; e < 6; ++e) Ainv[(size_t)6 * pt + e] = inv[e];
+    }
     const double Ai[3][3] = {{inv[0], inv[1], inv[2]}, {inv[1], inv[3], inv[4]}, {inv[2], inv[4], inv[5]}};
     const double* gp = p.g + p.gB + (size_t)3 * pt;
     const double g0 = gp[0], g1 = gp[1], g2 = gp[2];
@@ -423,6 +429,9 @@ __global__ void __launch_bounds__(128) schur_outlier_kernel(DevProblem p, const 
             for (int a = 0; a < DC; ++a) {
                 if (i == j && b > a) continue;
                 const double v = Wi[3 * a] * y0 + Wi[3 * a + 1] * y1 + Wi[3 * a + 2] * y2;
+                if (i != j && ci == cj) {   // M + M' on the lower triangle of the diagonal block
+                    atomicAdd(S + schur5_soff(ci, a > b ? a : b, cj, a > b ? b : a, p.tile_id, p.tile_pos, p.NT, DC, ST), a == b ? -2.0 * v : -v);
+                } else
                 atomicAdd(S + schur5_soff(ci, a, cj, b, p.tile_id, p.tile_pos, p.NT, DC, ST), -v);
             }
         }

@@ -162,28 +162,31 @@ inline void schur5_tile_range(int DC, int delta, int k, int& t_lo, int& t_hi) {
 
 // Builds the plan.  obs_start[nB + 1] / obs_cam[nobs]: point-major observations (cameras ascending inside a point);
 // hB: offset of the point rows in H (DC*DC*nA);  ncta: CTAs (one per SM);  maxrun: tiles per super-tile at most.
+// irr (optional): points that must stay outside every tile (they are appended to the outliers by the caller).
 template <int DC>
-Schur5Plan schur5_build_plan(const std::vector<int>& obs_start, const std::vector<int>& obs_cam, long long nA, int ncta, int maxrun = 48, int ncons = S5_CONSUMERS) {
+Schur5Plan schur5_build_plan(const std::vector<int>& obs_start, const std::vector<int>& obs_cam, long long nA, int ncta, int maxrun = 48, int ncons = S5_CONSUMERS,
+                             const std::vector<unsigned char>* irr = nullptr) {
     using C = Schur5Cfg<DC>;
     Schur5Plan P;
     const long long nB = (long long)obs_start.size() - 1;
     const long long hB = (long long)DC * DC * nA;
     // ---- point tiles: consecutive points, <= OBS observations, <= PTS points, boundaries preferably 16-byte aligned in H
-    std::vector<int> tile_pt;
-    tile_pt.push_back(0);
+    std::vector<int> tile_pt;     // (first point, one past the last point) per tile
     {
         auto aligned = [&](long long pt) { return ((hB + (long long)C::WB * obs_start[(size_t)pt] + 9 * pt) & 1) == 0; };
+        auto skip = [&](long long pt) { return irr != nullptr && (*irr)[(size_t)pt] != 0; };
         long long p0 = 0;
         while (p0 < nB) {
+            if (skip(p0)) { ++p0; continue; }
             long long p1 = p0;
-            while (p1 < nB && (p1 - p0) < C::PTS && (obs_start[(size_t)p1 + 1] - obs_start[(size_t)p0]) <= C::OBS) ++p1;
+            while (p1 < nB && !skip(p1) && (p1 - p0) < C::PTS && (obs_start[(size_t)p1 + 1] - obs_start[(size_t)p0]) <= C::OBS) ++p1;
             if (p1 < nB && !aligned(p1) && p1 - 1 > p0 && aligned(p1 - 1)) --p1;
             if (p1 == p0) { P.cta_item.clear(); return P; }   // a point with more observations than a tile holds: no v5 plan
-            tile_pt.push_back((int)p1);
+            tile_pt.push_back((int)p0); tile_pt.push_back((int)p1);
             p0 = p1;
         }
     }
-    const int nt = (int)tile_pt.size() - 1;
+    const int nt = (int)tile_pt.size() / 2;
     // ---- per point: start camera, track length, eligibility (contiguous camera list, not wider than the window minus slack)
     std::vector<int> pstart((size_t)nB), pk((size_t)nB);
     std::vector<unsigned char> elig((size_t)nB);
@@ -194,7 +197,7 @@ Schur5Plan schur5_build_plan(const std::vector<int>& obs_start, const std::vecto
         const int b = obs_start[(size_t)p], e = obs_start[(size_t)p + 1], k = e - b;
         pk[(size_t)p] = k;
         pstart[(size_t)p] = k > 0 ? obs_cam[(size_t)b] : 0;
-        elig[(size_t)p] = (k > 0 && k <= kmax_fit && obs_cam[(size_t)e - 1] - obs_cam[(size_t)b] + 1 == k) ? 1 : 0;
+        elig[(size_t)p] = (k > 0 && k <= kmax_fit && obs_cam[(size_t)e - 1] - obs_cam[(size_t)b] + 1 == k && !(irr != nullptr && (*irr)[(size_t)p])) ? 1 : 0;
         contrib_all += 0.5 * k * (k + 1);
     }
     // ---- contiguous tile ranges of similar weight, one per CTA
@@ -210,7 +213,7 @@ Schur5Plan schur5_build_plan(const std::vector<int>& obs_start, const std::vecto
         }
         for (int t = 0; t < nt; ++t) {
             double w = 300.0;
-            for (int p = tile_pt[(size_t)t]; p < tile_pt[(size_t)t + 1]; ++p) w += kcost[(size_t)std::min(pk[(size_t)p], 257)];
+            for (int p = tile_pt[(size_t)2 * t]; p < tile_pt[(size_t)2 * t + 1]; ++p) w += kcost[(size_t)std::min(pk[(size_t)p], 257)];
             wsum[(size_t)t + 1] = wsum[(size_t)t] + w;
         }
     }
@@ -234,7 +237,7 @@ Schur5Plan schur5_build_plan(const std::vector<int>& obs_start, const std::vecto
             int u = t;
             while (u < tb && u - t < maxrun) {
                 int b2 = base, h2 = hi;
-                for (int p = tile_pt[(size_t)u]; p < tile_pt[(size_t)u + 1]; ++p) if (elig[(size_t)p]) {
+                for (int p = tile_pt[(size_t)2 * u]; p < tile_pt[(size_t)2 * u + 1]; ++p) if (elig[(size_t)p]) {
                     b2 = std::min(b2, pstart[(size_t)p]); h2 = std::max(h2, pstart[(size_t)p] + pk[(size_t)p]);
                 }
                 if (u > t && h2 > INT32_MIN && (long long)(h2 - b2) * DC > C::WROWS) break;
@@ -258,7 +261,7 @@ Schur5Plan schur5_build_plan(const std::vector<int>& obs_start, const std::vecto
                 return cm.dmma * d + cm.afrag * a + cm.bfrag * b + cm.fixed;
             };
             auto fits = [&](int p) { return elig[(size_t)p] && pstart[(size_t)p] >= base && (long long)(pstart[(size_t)p] - base + pk[(size_t)p]) * DC <= C::WROWS; };
-            for (int p = tile_pt[(size_t)t]; p < tile_pt[(size_t)u]; ++p) if (fits(p))
+            for (int p = tile_pt[(size_t)2 * t]; p < tile_pt[(size_t)2 * (u - 1) + 1]; ++p) if (fits(p))
                 for (int b = 0; b < C::NBANDS; ++b) work[b] += unit_cost(pstart[(size_t)p] - base, pk[(size_t)p], b, nullptr, nullptr, nullptr);
             // Warps of a band: counts in proportion to the work, heaviest band first.
             auto capw = [](int w) { return (w & 3) == 3 ? S5_CAP3 : 1.0; };
@@ -285,7 +288,7 @@ Schur5Plan schur5_build_plan(const std::vector<int>& obs_start, const std::vecto
             bool touched[S5_CONSUMERS] = {false};
             // ---- tiles of the super-tile
             for (int tt = t; tt < u; ++tt) {
-                const int pt0 = tile_pt[(size_t)tt], pt1 = tile_pt[(size_t)tt + 1];
+                const int pt0 = tile_pt[(size_t)2 * tt], pt1 = tile_pt[(size_t)2 * tt + 1];
                 const int ob0 = obs_start[(size_t)pt0];
                 for (auto& v : went) v.clear();
                 double tload[S5_CONSUMERS] = {0};

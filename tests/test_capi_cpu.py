@@ -17,6 +17,24 @@ def test_exports_match_header(pkg):
     assert set(pkg.capi.EXPORTS) == declared
 
 
+def test_julia_glue_binds_declared_symbols(pkg):
+    """julia/NLLSsolverB200.jl cannot run here (no Julia): at least every symbol it ccalls must be declared in the header and
+    exported by the library, and the enum values it hard-codes must be the header's."""
+    jl = open(os.path.join(ROOT, "julia", "NLLSsolverB200.jl")).read()
+    hdr = open(os.path.join(ROOT, "include", "nlls_b200.h")).read()
+    bound = set(re.findall(r"ccall\(\(:(nlls_[a-z0-9_]+)", jl))
+    declared = set(re.findall(r"\b(nlls_[a-z0-9_]+)\s*\(", hdr))
+    assert bound and bound <= declared, bound - declared
+    L = pkg.capi.lib()
+    assert all(hasattr(L, s) for s in bound)
+    for jname, hname in [("VAR_PINHOLE", "NLLS_VAR_PINHOLE"), ("VAR_CONTAMGAUSS", "NLLS_VAR_CONTAMGAUSS"), ("RES_ADAPTIVE_OFFSET", "NLLS_RES_ADAPTIVE_OFFSET"),
+                         ("RES_PINHOLE_BA", "NLLS_RES_PINHOLE_BA"), ("ROBUST_SCALED", "NLLS_ROBUST_SCALED"), ("ITER_DOGLEG", "NLLS_ITER_DOGLEG"),
+                         ("ITER_GD", "NLLS_ITER_GD"), ("ROBUST_GEMANMCCLURE", "NLLS_ROBUST_GEMANMCCLURE")]:
+        jv = int(re.search(rf"const {jname} = \w+\((\d+)\)", jl).group(1))
+        hv = int(re.search(rf"{hname} = (\d+)", hdr).group(1))
+        assert jv == hv, (jname, jv, hv)
+
+
 def test_struct_sizes(pkg):
     import ctypes as C
     assert C.sizeof(pkg.capi.Options) == 56
