@@ -116,6 +116,11 @@ int nlls_set_variables(nlls_ctx* ctx, int vartype, const double* aos, int64_t n,
  * In a multi-rank run each rank passes only the costs of the points it owns. */
 int nlls_set_costs(nlls_ctx* ctx, int restype, const void* aos, int64_t stride_bytes, int64_t n,
                    int robust, const double* kparams, int nkparams, int64_t kernel_var);
+/* A further Vector{T} of problem.costs.data: costs of the same residual struct (same restype) whose type carries a different
+ * robustkernel().  cost, gradient and Hessian are summed over all cost sets (src/cost.jl:54, src/VectorRepo.jl:64-69).  Up to 8 sets;
+ * nlls_set_costs starts over with one set. */
+int nlls_add_costs(nlls_ctx* ctx, int restype, const void* aos, int64_t stride_bytes, int64_t n,
+                   int robust, const double* kparams, int nkparams);
 /* optimize!(problem, options, unfixed) (src/optimize.jl:5-20): unfixed[i] != 0 <=> variable i + 1 is optimised, for i < n; variables
  * beyond n are unfixed; n == 0 (or unfixed == NULL) clears the mask.  Fixed variables keep their values, contribute to the cost, and are
  * left out of linsystem.b / x (nlls_dof, nlls_get_gradient, nlls_get_step); the Hessian read-back is not available under a mask. */

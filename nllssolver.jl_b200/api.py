@@ -260,11 +260,7 @@ class NLLSProblem:
             g[1].append(vals)
         return {vt: (np.array(idx, dtype=np.int64), np.stack(vals)) for vt, (idx, vals) in groups.items()}
 
-    def _cost_aos(self):
-        live = {t: c for t, c in self.costs.items() if len(c)}
-        if len(live) != 1:
-            raise capi.NLLSError(capi.ERR_UNSUPPORTED, "exactly one residual type per problem is supported by this build")
-        (ctype, lst), = live.items()
+    def _one_cost_aos(self, ctype, lst):
         if getattr(ctype, "restype", None) is None:
             raise capi.NLLSError(capi.ERR_NO_KERNEL, f"residual type {ctype.__name__} has no registered sm_100a kernel (no CPU fallback)")
         if isinstance(lst, np.ndarray):
@@ -280,7 +276,22 @@ class NLLSProblem:
             aos = np.zeros(len(lst), dtype=COST_DTYPE)
             aos["z"] = np.stack([c.measurement for c in lst])
             aos["varind"] = np.array([c.varind for c in lst], dtype=np.int64)
-        return ctype, aos
+        return aos
+
+    def _cost_sets(self):
+        """[(residual type, AoS image)] of the non-empty Vector{T}s of problem.costs (src/VectorRepo.jl:3), in insertion order.  Several
+        residual types are summed (src/cost.jl:54) when they share one registered kernel family (same `restype`: same residual
+        struct, same variable classes) and differ in their robustkernel(); anything else has no kernel."""
+        live = [(t, c) for t, c in self.costs.items() if len(c)]
+        if not live:
+            raise capi.NLLSError(capi.ERR_INVALID, "no costs")
+        sets = [(t, self._one_cost_aos(t, c)) for t, c in live]
+        if len({t.restype for t, _ in sets}) != 1 or (len(sets) > 1 and sets[0][0].restype == capi.RES_ADAPTIVE_OFFSET):
+            raise capi.NLLSError(capi.ERR_UNSUPPORTED, "residual types of one problem must share one registered kernel family (they may differ in the robust kernel)")
+        return sets
+
+    def _cost_aos(self):
+        return self._cost_sets()[0]
 
     def context(self):
         """Create / refresh the device context (≙ makesymmvls + NLLSInternal, src/optimize.jl:16)."""
@@ -291,7 +302,8 @@ class NLLSProblem:
             self._dirty = True
         groups = self._gather_variables()
         if self._dirty:
-            ctype, aos = self._cost_aos()
+            sets = self._cost_sets()
+            ctype, aos = sets[0]
             for vt, (idx, vals) in groups.items():
                 self._ctx.set_variables(vt, vals, indices=idx)
             k = ctype.robustkernel
@@ -299,6 +311,8 @@ class NLLSProblem:
             if ctype.restype == capi.RES_ADAPTIVE_OFFSET:
                 kernel_var = getattr(self, "_kernel_var", None) or next(i + 1 for i, v in enumerate(self.variables) if isinstance(v, ContaminatedGaussian))
             self._ctx.set_costs(ctype.restype, aos, k.id, k.params, kernel_var)
+            for t2, aos2 in sets[1:]:
+                self._ctx.add_costs(t2.restype, aos2, t2.robustkernel.id, t2.robustkernel.params)
             self._ctx.prepare()
             self._dirty = False
         else:

@@ -15,6 +15,10 @@
 
 namespace nlls {
 
+struct DevProblem;
+__device__ __forceinline__ RobustParams rk_point(const DevProblem& p, int j);   // robust kernel of point-major observation j
+__device__ __forceinline__ RobustParams rk_cam(const DevProblem& p, int k);     // ... of camera-major observation k
+
 struct DevProblem {
     // point-major observations
     const int* obs_cam;
@@ -37,6 +41,11 @@ struct DevProblem {
     long long hB;  // DC*DC*nA
     long long gB;  // DC*nA
     RobustParams rk;
+    // several cost sets (addcost! with residual types that differ in their robust kernel, src/cost.jl:54): per-observation set id in
+    // point-major (obs_set) and camera-major (cm_set) order and the sets' kernels; nullptr for the usual single set (rk)
+    const unsigned char* obs_set;
+    const unsigned char* cm_set;
+    const RobustParams* rk_tab;
     int use_tma;
     int schur_stride;
     // reduced camera system: tile-sparse (tile_id[I * NT + J], -1 = structurally zero) or dense n x n
@@ -50,6 +59,9 @@ struct DevProblem {
     const unsigned char* fixA;
     const unsigned char* fixB;
 };
+
+__device__ __forceinline__ RobustParams rk_point(const DevProblem& p, int j) { return p.obs_set ? p.rk_tab[p.obs_set[j]] : p.rk; }
+__device__ __forceinline__ RobustParams rk_cam(const DevProblem& p, int k) { return p.cm_set ? p.rk_tab[p.cm_set[k]] : p.rk; }
 
 // ---------------------------------------------------------------------------------------------------
 // K1  lin_point: fused residual + analytic Jacobian + robust weights + J'WJ for tiles of points (persistent, pipelined).
@@ -121,7 +133,7 @@ __global__ void __launch_bounds__(TO) lin_point_kernel(DevProblem p, const int4*
             R::resjac(cv, X, z.x, z.y, r, Jc, Jp);
             const double s = r[0] * r[0] + r[1] * r[1];               // sqnorm            src/residual.jl:72
             double rho, d1, d2;
-            robustifydcost(p.rk, s, rho, d1, d2);                     //                   src/residual.jl:78
+            robustifydcost(rk_point(p, ob0 + tid), s, rho, d1, d2);   //                   src/residual.jl:78
             c = 0.5 * rho;                                            //                   src/residual.jl:110
             const bool fpt = p.fixB != nullptr && p.fixB[ptg];
             const bool fcross = fpt || (p.fixA != nullptr && p.fixA[cam]);
@@ -270,7 +282,7 @@ __global__ void __launch_bounds__(TO) cost_kernel(DevProblem p, const int4* __re
         if (tid < d.w) {
             double r[2];
             R::residual(cv, X, z.x, z.y, r);
-            c = 0.5 * robustify(p.rk, r[0] * r[0] + r[1] * r[1]);
+            c = 0.5 * robustify(rk_point(p, d.z + tid), r[0] * r[0] + r[1] * r[1]);
         }
         c = warp_sum(c);
         if (lane == 0) s_red[(it & 1) * NW + wid] = c;
@@ -335,7 +347,7 @@ __global__ void __launch_bounds__(256, (R::DC <= 6) ? 2 : 1) lin_cam_kernel(DevP
             R::resjac(cv, X, z.x, z.y, r, Jc, Jp);
             const double s = r[0] * r[0] + r[1] * r[1];
             double rho, d1, d2;
-            robustifydcost(p.rk, s, rho, d1, d2);
+            robustifydcost(rk_cam(p, j0 + 256 * u), s, rho, d1, d2);
             cacc += 0.5 * rho;
             // explicit FMAs (the file is compiled with -fmad=false): this pass is FP64-issue bound, not HBM bound — ncu.  The
             // weights fold into the accumulation:  acc += d1 (J'J) + (2 d2 g) g'  (exact no-ops when d1 == 1 / d2 == 0)
@@ -1095,13 +1107,13 @@ __global__ void __launch_bounds__(128) cam_update_kernel(DevProblem p, const dou
     }
 }
 
-// gathered[r * 5 + i], r < nranks: the five per-try scalars of every rank -> out[0] = sum of the costs, out[1] = NaN-propagating max
-// of max|x_p|, out[2..4] = sums, all in rank order (lane i owns scalar i)
+// gathered[r * 6 + i], r < nranks: the six per-try scalars of every rank -> out[0] = sum of the costs, out[1] = NaN-propagating max
+// of max|x_p|, out[2..4] = sums, all in rank order (lane i owns scalar i); out[5] = rank 0's "maxtime reached" flag
 __global__ void combine_scalars_kernel(const double* __restrict__ gathered, int nranks, double* __restrict__ out) {
     const int i = threadIdx.x;
-    if (i >= 5) return;
+    if (i >= 6) return;
     double v = gathered[i];
-    for (int r = 1; r < nranks; ++r) v = (i == 1) ? nanmax(v, gathered[r * 5 + i]) : v + gathered[r * 5 + i];
+    if (i < 5) for (int r = 1; r < nranks; ++r) v = (i == 1) ? nanmax(v, gathered[r * 6 + i]) : v + gathered[r * 6 + i];
     out[i] = v;
 }
 
@@ -1151,7 +1163,7 @@ __global__ void __launch_bounds__(LONG_THREADS) lin_point_long_kernel(DevProblem
             R::resjac(cv, X, z.x, z.y, r, Jc, Jp);
             const double s = r[0] * r[0] + r[1] * r[1];
             double rho, d1, d2;
-            robustifydcost(p.rk, s, rho, d1, d2);
+            robustifydcost(rk_point(p, j), s, rho, d1, d2);
             c += 0.5 * rho;
             const bool fcross = fpt || (p.fixA != nullptr && p.fixA[cam]);
             double gc[DC], gp[3];

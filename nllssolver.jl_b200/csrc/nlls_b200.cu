@@ -76,15 +76,18 @@ struct VarSet {
 enum Scal {
     SC_COST_LIN = 0, SC_COST_TRY = 1,
     SC_P_MAX = 2, SC_P_SQ = 3, SC_P_XHX = 4, SC_P_GX = 5,      // point-row terms (summed / maxed over ranks)
-    SC_C_MAX = 6, SC_C_SQ = 7, SC_C_XHX = 8, SC_C_GX = 9,      // camera terms (replicated)
-    SC_MAXDIAG = 10, SC_INFO = 11, SC_EXCH = 12 /* .. 15: host values exchanged between ranks */, SC_COUNT = 16
+    SC_TIMEUP = 6,                                             // multi-rank: rank 0's "maxtime reached" flag, rides on the try's all-gather
+    SC_C_MAX = 7, SC_C_SQ = 8, SC_C_XHX = 9, SC_C_GX = 10,     // camera terms (replicated)
+    SC_MAXDIAG = 11, SC_INFO = 12, SC_EXCH = 13 /* .. 16: host values exchanged between ranks */, SC_COUNT = 17,
+    SC_TRY_N = 6                                               // scalars per rank in the try's all-gather: SC_COST_TRY .. SC_TIMEUP
 };
 }  // namespace
 
 struct nlls_ctx {
     int device = 0;
     cudaStream_t st = nullptr, st2 = nullptr;
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_t0 = nullptr, ev_t1 = nullptr, ev_b0 = nullptr, ev_b1 = nullptr, ev_c0 = nullptr, ev_c1 = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_t0 = nullptr, ev_t1 = nullptr, ev_b0 = nullptr, ev_b1 = nullptr, ev_c0 = nullptr, ev_c1 = nullptr, ev_g0 = nullptr, ev_g1 = nullptr;
+    bool grad_pending = false;       // a re-linearisation was enqueued without a host sync: its time (ev_g0 .. ev_g1) is booked at the next sync
     std::string err;
     int64_t launches = 0;
 
@@ -95,6 +98,12 @@ struct nlls_ctx {
     double kparams[2] = {0, 1};
     std::vector<int64_t> h_cam_g, h_pt_g;  // global 1-based indices per cost, storage order
     std::vector<double> h_z;               // 2 per cost
+    // further cost sets of the same residual struct with their own robust kernel (nlls_add_costs): set id per cost, kernels per set
+    struct SetSpec { int robust; double kp[2]; };
+    std::vector<SetSpec> sets;
+    std::vector<unsigned char> h_set;
+    unsigned char *d_obs_set = nullptr, *d_cm_set = nullptr;
+    RobustParams* d_rk_tab = nullptr;
     bool prepared = false;
     std::vector<unsigned char> h_unfixed;   // optimize!(…, unfixed): by 0-based variable position; empty = all unfixed
     bool masked = false;                    // some variable of this problem is fixed
@@ -258,6 +267,8 @@ DevProblem devproblem(const nlls_ctx* c) {
     p.rk.kind = c->robust & 15; p.rk.scaled = (c->robust & NLLS_ROBUST_SCALED) ? 1 : 0;
     p.rk.width = c->kparams[0]; p.rk.width2 = c->kparams[0] * c->kparams[0]; p.rk.height = c->kparams[1];
     p.use_tma = c->use_tma;
+    const bool multi = c->sets.size() > 1;
+    p.obs_set = multi ? c->d_obs_set : nullptr; p.cm_set = multi ? c->d_cm_set : nullptr; p.rk_tab = multi ? c->d_rk_tab : nullptr;
     p.schur_stride = c->schur_stride;
     p.tile_id = c->d_tile_id; p.tile_pos = c->d_pos; p.NT = c->NT; p.s_tiled = c->s_tiled;
     p.fixA = c->masked ? c->d_fixA : nullptr; p.fixB = c->masked ? c->d_fixB : nullptr;
@@ -330,17 +341,6 @@ int set_smem_attrs(nlls_ctx* ctx) {
 int allreduce(nlls_ctx* ctx, double* buf, size_t count, int op) {
     if (ctx->nranks <= 1) return NLLS_OK;
     CKN(g_nccl.AllReduce(buf, buf, count, ncclFloat64, op, ctx->comm, ctx->st));
-    return NLLS_OK;
-}
-
-// max over ranks of n (<= 4) host doubles (termination inputs that are not replicated)
-int exchange_max(nlls_ctx* ctx, double* v, int n) {
-    if (ctx->nranks <= 1) return NLLS_OK;
-    CK(cudaMemcpyAsync(ctx->d_scal + SC_EXCH, v, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->st));
-    CKN(g_nccl.AllReduce(ctx->d_scal + SC_EXCH, ctx->d_scal + SC_EXCH, (size_t)n, ncclFloat64, ncclMax, ctx->comm, ctx->st));
-    CK(cudaMemcpyAsync(ctx->h_scal + SC_EXCH, ctx->d_scal + SC_EXCH, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->st));
-    CK(cudaStreamSynchronize(ctx->st));
-    for (int i = 0; i < n; ++i) v[i] = ctx->h_scal[SC_EXCH + i];
     return NLLS_OK;
 }
 
@@ -572,10 +572,14 @@ int launch_update(nlls_ctx* ctx) {
 // The rank-local scalars of a try — cost(varnext) and the point rows' step statistics {max|x|, sum x^2, x'Hx, g.x}, five
 // consecutive slots — are combined over the ranks with ONE all-gather and a tiny kernel that adds them in rank order (the same
 // order on every rank, so the replicated accept / reject decision is taken on identical bits).  Round 1 used three all-reduces
-// per try here; at 8 ranks their launch latency was a quarter of the step.
+// per try here; at 8 ranks their launch latency was a quarter of the step.  A sixth slot carries rank 0's "maxtime reached" flag:
+// the one termination input that is not replicated (each rank has its own clock) is thereby decided by rank 0 for everyone, with
+// no collective of its own (a rank that left the loop alone would strand the others in the next all-reduce).
 int exchange_try_scalars(nlls_ctx* ctx) {
     if (ctx->nranks <= 1) return NLLS_OK;
-    CKN(g_nccl.AllGather(ctx->d_scal + SC_COST_TRY, ctx->d_gather, 5, ncclFloat64, ctx->comm, ctx->st));
+    ctx->h_scal[SC_COUNT] = (ctx->lm_active && now_ns() > ctx->stoptime) ? 1.0 : 0.0;   // pinned staging slot outside the read-back range
+    CK(cudaMemcpyAsync(ctx->d_scal + SC_TIMEUP, ctx->h_scal + SC_COUNT, sizeof(double), cudaMemcpyHostToDevice, ctx->st));
+    CKN(g_nccl.AllGather(ctx->d_scal + SC_COST_TRY, ctx->d_gather, SC_TRY_N, ncclFloat64, ctx->comm, ctx->st));
     combine_scalars_kernel<<<1, 32, 0, ctx->st>>>(ctx->d_gather, ctx->nranks, ctx->d_scal + SC_COST_TRY); ctx->launches++;
     CK(cudaGetLastError());
     return NLLS_OK;
@@ -774,6 +778,7 @@ int do_linearize(nlls_ctx* ctx, double* cost) {
     }
     // the accepted try's cost evaluation already ran the camera pass at these variables: only its finalize is left
     const int cam_mode = (ctx->cam_part_vars == ctx->cur) ? 2 : 1;
+    if (!cost) CK(cudaEventRecord(ctx->ev_g0, ctx->st));
     TRY(DISPATCH(ctx, launch_linearize, ctx, true, cam_mode));
     ctx->cam_part_vars = -1;
     reduce_partials_kernel<<<1, 1024, 0, ctx->st>>>(ctx->d_cost_part, ctx->ntiles + ctx->nlong, ctx->d_scal + SC_COST_LIN, 0); ctx->launches++;
@@ -785,8 +790,10 @@ int do_linearize(nlls_ctx* ctx, double* cost) {
         CKN(g_nccl.AllReduce(ctx->d_scal + SC_COST_LIN, ctx->d_scal + SC_COST_LIN, 1, ncclFloat64, ncclSum, ctx->comm, ctx->st));
         CKN(g_nccl.GroupEnd());
     }
-    TRY(fetch_scalars(ctx));
-    if (cost) *cost = ctx->h_scal[SC_COST_LIN];
+    // the LM loop discards this cost (src/optimize.jl:169): no read-back, the host goes on to enqueue the next try; the time of this
+    // linearisation (events) is booked as timegradient at the next host sync (do_try / nlls_lm_end)
+    if (cost) { TRY(fetch_scalars(ctx)); *cost = ctx->h_scal[SC_COST_LIN]; }
+    else { CK(cudaEventRecord(ctx->ev_g1, ctx->st)); ctx->grad_pending = true; }
     return NLLS_OK;
 }
 
@@ -814,7 +821,14 @@ int do_try(nlls_ctx* ctx, double lambda) {
     const uint64_t ts = now_ns();
     TRY(enqueue_try(ctx, lambda));
     TRY(fetch_scalars(ctx));
-    const uint64_t dt = now_ns() - ts;
+    uint64_t dt = now_ns() - ts;
+    if (ctx->grad_pending) {   // the asynchronous re-linearisation before this try finished inside this wait
+        float gms = 0.f;
+        CK(cudaEventElapsedTime(&gms, ctx->ev_g0, ctx->ev_g1));
+        const uint64_t tg = std::min<uint64_t>(dt, (uint64_t)(gms * 1e6));
+        ctx->t_grad += tg; dt -= tg;
+        ctx->grad_pending = false;
+    }
     float cms = 0.f;
     CK(cudaEventElapsedTime(&cms, ctx->ev_c0, ctx->ev_c1));
     const uint64_t tc = std::min<uint64_t>(dt, (uint64_t)(cms * 1e6));
@@ -977,6 +991,8 @@ int nlls_create(nlls_ctx** out, int device) {
     cudaEventCreate(&ctx->ev_b1);
     cudaEventCreate(&ctx->ev_c0);
     cudaEventCreate(&ctx->ev_c1);
+    cudaEventCreate(&ctx->ev_g0);
+    cudaEventCreate(&ctx->ev_g1);
     cudaMalloc((void**)&ctx->d_gather, sizeof(double) * 8 * 64);
     cudaMalloc((void**)&ctx->d_scal, sizeof(double) * SC_COUNT);
     cudaMemset(ctx->d_scal, 0, sizeof(double) * SC_COUNT);
@@ -1012,12 +1028,12 @@ int nlls_destroy(nlls_ctx* ctx) {
                     ctx->d_lvl_cols, ctx->d_red_tasks, ctx->d_red_upds, ctx->d_red_targets, ctx->d_colptr,
                     ctx->d_col_tile, ctx->d_col_row, ctx->d_Linv, ctx->d_xp, ctx->d_stile_pt, ctx->d_chunk_off, ctx->d_chunks, ctx->d_ents, ctx->d_tiles, ctx->d_camstat_part,
                     ctx->d_ad_data, ctx->d_ad_chunks, ctx->d_ad_moff, ctx->d_ad_part, ctx->d_ent_off, ctx->d_cta_item, ctx->d_items, ctx->d_units, ctx->d_wtab, ctx->d_blob,
-                    ctx->d5_cta_item, ctx->d5_items, ctx->d5_blob, ctx->d5_ftab, ctx->d_out_pts, ctx->d_bwd_order, ctx->d_bwd_flags, ctx->d_nat_of_pos, ctx->d_long_pts, ctx->d_fixA, ctx->d_fixB, ctx->d_cauchy, ctx->d_vec_part};
+                    ctx->d5_cta_item, ctx->d5_items, ctx->d5_blob, ctx->d5_ftab, ctx->d_out_pts, ctx->d_bwd_order, ctx->d_bwd_flags, ctx->d_nat_of_pos, ctx->d_long_pts, ctx->d_obs_set, ctx->d_cm_set, ctx->d_rk_tab, ctx->d_fixA, ctx->d_fixB, ctx->d_cauchy, ctx->d_vec_part};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (ctx->red_graph_exec) cudaGraphExecDestroy(ctx->red_graph_exec);
     if (ctx->h_scal) cudaFreeHost(ctx->h_scal);
     if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
-    for (cudaEvent_t e : {ctx->ev_fork, ctx->ev_join, ctx->ev_t0, ctx->ev_t1, ctx->ev_b0, ctx->ev_b1, ctx->ev_c0, ctx->ev_c1}) if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : {ctx->ev_fork, ctx->ev_join, ctx->ev_t0, ctx->ev_t1, ctx->ev_b0, ctx->ev_b1, ctx->ev_c0, ctx->ev_c1, ctx->ev_g0, ctx->ev_g1}) if (e) cudaEventDestroy(e);
     if (ctx->st) cudaStreamDestroy(ctx->st);
     if (ctx->st2) cudaStreamDestroy(ctx->st2);
     delete ctx;
@@ -1130,6 +1146,45 @@ int nlls_set_costs(nlls_ctx* ctx, int restype, const void* aos, int64_t stride_b
         ctx->h_z[(size_t)2 * i] = z[0]; ctx->h_z[(size_t)2 * i + 1] = z[1];
         ctx->h_cam_g[(size_t)i] = vi[0]; ctx->h_pt_g[(size_t)i] = vi[1];
     }
+    ctx->sets.assign(1, nlls_ctx::SetSpec{robust, {ctx->kparams[0], ctx->kparams[1]}});
+    ctx->h_set.assign((size_t)n, 0);
+    ctx->prepared = false;
+    return NLLS_OK;
+}
+
+// A further Vector{T} of problem.costs.data (src/VectorRepo.jl:3): costs of the same residual struct whose residual type carries a
+// different robustkernel().  The reference sums cost, gradient and Hessian over all cost types (src/cost.jl:54).
+int nlls_add_costs(nlls_ctx* ctx, int restype, const void* aos, int64_t stride_bytes, int64_t n, int robust, const double* kparams, int nkparams) {
+    if (!ctx || (!aos && n > 0) || n < 0) return NLLS_ERR_INVALID;
+    if (ctx->sets.empty() || ctx->restype == 0) FAIL(NLLS_ERR_INVALID, "nlls_add_costs before nlls_set_costs");
+    if (restype == NLLS_RES_ADAPTIVE_OFFSET || ctx->restype == NLLS_RES_ADAPTIVE_OFFSET || restype != ctx->restype)
+        FAIL(NLLS_ERR_UNSUPPORTED, "cost sets of one problem must share the residual struct (same variables, same kernel family); they may differ in the robust kernel");
+    if (ctx->sets.size() >= 8) FAIL(NLLS_ERR_UNSUPPORTED, "more than 8 cost sets");
+    const int kind = robust & 15;
+    if (kind > NLLS_ROBUST_GEMANMCCLURE || (robust & ~(15 | NLLS_ROBUST_SCALED)))
+        FAIL(NLLS_ERR_NO_KERNEL, "robust kernel " + std::to_string(robust) + " has no registered device implementation");
+    if (stride_bytes < 32) FAIL(NLLS_ERR_INVALID, "cost stride must be >= 32 bytes (2 x f64 measurement + 2 x i64 varind)");
+    nlls_ctx::SetSpec sp{robust, {0.0, 1.0}};
+    if (kind != NLLS_ROBUST_NONE) {
+        if (nkparams < 1 || !kparams) FAIL(NLLS_ERR_INVALID, "robust kernel needs its width in kparams[0]");
+        sp.kp[0] = kparams[0];
+    }
+    if (robust & NLLS_ROBUST_SCALED) {
+        if (nkparams < 2 || !kparams) FAIL(NLLS_ERR_INVALID, "Scaled kernel needs (width, height) in kparams");
+        sp.kp[1] = kparams[1];
+    }
+    const size_t n0 = ctx->h_cam_g.size();
+    ctx->h_cam_g.resize(n0 + (size_t)n); ctx->h_pt_g.resize(n0 + (size_t)n); ctx->h_z.resize(2 * (n0 + (size_t)n)); ctx->h_set.resize(n0 + (size_t)n);
+    const unsigned char* base = (const unsigned char*)aos;
+    for (int64_t i = 0; i < n; ++i) {
+        const unsigned char* e = base + (size_t)i * stride_bytes;
+        double z[2]; int64_t vi[2];
+        std::memcpy(z, e, 16); std::memcpy(vi, e + 16, 16);
+        ctx->h_z[2 * (n0 + (size_t)i)] = z[0]; ctx->h_z[2 * (n0 + (size_t)i) + 1] = z[1];
+        ctx->h_cam_g[n0 + (size_t)i] = vi[0]; ctx->h_pt_g[n0 + (size_t)i] = vi[1];
+        ctx->h_set[n0 + (size_t)i] = (unsigned char)ctx->sets.size();
+    }
+    ctx->sets.push_back(sp);
     ctx->prepared = false;
     return NLLS_OK;
 }
@@ -1259,6 +1314,17 @@ int nlls_prepare(nlls_ctx* ctx) {
     }
     cam_item_start[(size_t)nA] = (int)item_cam.size();
     ctx->nitems = (int)item_cam.size();
+    if (ctx->sets.size() > 1) {   // per-observation cost set in both orders + the sets' kernels
+        std::vector<unsigned char> oset((size_t)nobs), cset((size_t)nobs);
+        for (int64_t j = 0; j < nobs; ++j) oset[(size_t)j] = ctx->h_set[(size_t)order[(size_t)j]];
+        for (int64_t k = 0; k < nobs; ++k) cset[(size_t)k] = oset[(size_t)ctx->h_cm_obs[(size_t)k]];
+        std::vector<RobustParams> tab(ctx->sets.size());
+        for (size_t q = 0; q < ctx->sets.size(); ++q) {
+            tab[q].kind = ctx->sets[q].robust & 15; tab[q].scaled = (ctx->sets[q].robust & NLLS_ROBUST_SCALED) ? 1 : 0;
+            tab[q].width = ctx->sets[q].kp[0]; tab[q].width2 = ctx->sets[q].kp[0] * ctx->sets[q].kp[0]; tab[q].height = ctx->sets[q].kp[1];
+        }
+        TRY(upload(ctx, &ctx->d_obs_set, oset)); TRY(upload(ctx, &ctx->d_cm_set, cset)); TRY(upload(ctx, &ctx->d_rk_tab, tab));
+    }
 
     ctx->dof = (int64_t)DC * nA + 3 * nB;
     ctx->hlen = (int64_t)DC * DC * nA + (int64_t)WB * nobs + 9 * nB;
@@ -1939,14 +2005,10 @@ int nlls_lm_advance(nlls_ctx* ctx, double cost, int64_t terminate, int64_t* conv
     conv |= (int64_t)(maxstep < o.dstep) << 6;
     conv |= (int64_t)(ctx->fails > o.maxfails) << 7;
     conv |= (int64_t)(ctx->iternum >= o.maxiters) << 8;
-    int64_t timeup = now_ns() > ctx->stoptime;
-    if (ctx->nranks > 1) {
-        // every other input of the termination word is replicated; the clock and the callback's flag are per rank.  The decision
-        // must be the same on all ranks (a rank that leaves alone strands the others in the next all-reduce): take the maximum.
-        double v[2] = {(double)timeup, (double)terminate};
-        TRY(exchange_max(ctx, v, 2));
-        timeup = v[0] != 0.0; terminate = (int64_t)v[1];
-    }
+    // Multi-rank: every rank must take the same decision (a rank that leaves alone strands the others in the next all-reduce).  All
+    // inputs of the termination word are replicated except the clock — rank 0's reading came with the try's scalars — and the
+    // callback's flag, which the caller must pass identically on every rank (the callback sees replicated data).
+    const int64_t timeup = (ctx->nranks > 1) ? (ctx->h_scal[SC_TIMEUP] != 0.0) : (now_ns() > ctx->stoptime);
     conv |= timeup << 9;
     conv |= terminate << 16;
     ctx->converged = conv;
@@ -1966,6 +2028,12 @@ int nlls_lm_end(nlls_ctx* ctx, nlls_result* r) {
     if (!(ctx->bestcost >= ctx->cost) && ctx->have_best) std::swap(ctx->cur, ctx->bst);   // src/optimize.jl:173-176
     for (auto& kv : ctx->vars) kv.second.stale = true;
     CK(cudaStreamSynchronize(ctx->st));
+    if (ctx->grad_pending) {
+        float gms = 0.f;
+        CK(cudaEventElapsedTime(&gms, ctx->ev_g0, ctx->ev_g1));
+        ctx->t_grad += (uint64_t)(gms * 1e6);
+        ctx->grad_pending = false;
+    }
     ctx->lm_active = false;
     if (r) {
         r->startcost = ctx->startcost; r->bestcost = ctx->bestcost;

@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(128) singles_point_kernel(DevProblem p, const 
             R::resjac(cv, Xc, z.x, z.y, r, Jc, Jp);
             const double s = r[0] * r[0] + r[1] * r[1];
             double rho, d1, d2;
-            robustifydcost(p.rk, s, rho, d1, d2);
+            robustifydcost(rk_point(p, j), s, rho, d1, d2);
             c += 0.5 * rho;
             double gp[3];
 #pragma unroll
@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(128) singles_point_kernel(DevProblem p, const 
             const double2 z = p.obs_z[j];
             double r[2];
             R::residual(cv, Xc, z.x, z.y, r);
-            c += 0.5 * robustify(p.rk, r[0] * r[0] + r[1] * r[1]);
+            c += 0.5 * robustify(rk_point(p, j), r[0] * r[0] + r[1] * r[1]);
         }
         return c;
     };

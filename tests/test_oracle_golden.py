@@ -308,3 +308,31 @@ def test_oracle_unfixed_and_optimizesingles(pkg, orc):
         Pm.set_unfixed(mask)
         Pf.linearize(); Pm.linearize()
         assert np.array_equal(Pm.grad(), Pf.grad()[6 * p.ncam:])
+
+
+def test_bal_reader_round_trip(pkg, orc, tmp_path):
+    """BAL text format (plain and bz2): write -> read reproduces cameras, points and observations; the oracle's cost of the loaded
+    problem equals the cost of the original (the data format on the caller's side of the path)."""
+    rng = np.random.default_rng(3)
+    S = pkg.synthetic
+    p = S.create_bal_shaped_pinhole(12, 80, 400, rng, noise=0.3)
+    for name in ("problem.txt", "problem.txt.bz2"):
+        path = tmp_path / name
+        pkg.bal.write_bal(path, p)
+        q = pkg.bal.read_bal(path)
+        assert (q.ncam, q.npt, q.nobs) == (p.ncam, p.npt, p.nobs)
+        assert np.array_equal(q.cam_idx, p.cam_idx) and np.array_equal(q.pt_idx, p.pt_idx) and np.array_equal(q.z, p.z)
+        assert np.array_equal(q.points, p.points)
+        assert np.allclose(q.cameras, p.cameras, rtol=0, atol=1e-14)
+
+        def cost(b):
+            P = orc.Problem()
+            P.add_variables(orc.VT_PINHOLE, b.cameras)
+            P.add_variables(orc.VT_EUCLID, b.points)
+            P.add_costs(orc.RT_PINHOLE_BA, np.stack([b.cam_idx, b.pt_idx], 1), b.z)
+            return P.cost()
+        assert abs(cost(q) - cost(p)) <= 1e-10 * cost(p)
+    with open(tmp_path / "bad.txt", "w") as f:
+        f.write("2 2 1\n0 0 1.0 2.0\n")
+    with pytest.raises(ValueError):
+        pkg.bal.read_bal(tmp_path / "bad.txt")
