@@ -138,6 +138,10 @@ int nlls_prepare(nlls_ctx* ctx);
 int nlls_linearize(nlls_ctx* ctx, double* cost);
 /* cost(vars, costs)  src/cost.jl:11 ; which: 0 = variables, 1 = varnext, 2 = varbest                      */
 int nlls_cost(nlls_ctx* ctx, int which, double* cost);
+/* optimize(kernel::ContaminatedGaussian, squarederrors, maxiters) (src/robustadaptive.jl:48-73): Expectation-Maximisation refit of the
+ * adaptive kernel variable of buffer `which` (as nlls_cost) from the squared residuals at that buffer's means — what the EM callback of
+ * test/adaptivecost.jl:15-25 does between iterations (followed there by nlls_cost(ctx, 1, ..) for the new cost). */
+int nlls_adaptive_em(nlls_ctx* ctx, int which, int maxiters);
 /* uniformscaling!(H, lambda) + solve! + negate!   src/iterators.jl:149-152 ;  x = -(H + lambda I)^-1 g    */
 int nlls_solve(nlls_ctx* ctx, double lambda);
 /* update!(varnext, variables, linsystem)   src/iterators.jl:155, src/linearsystem.jl:206-213              */

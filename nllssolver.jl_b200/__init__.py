@@ -6,6 +6,6 @@ from .api import (  # noqa: F401,E402
     NLLSProblem, NLLSOptions, NLLSResult, EuclideanVector, PinholeCamera, SimpleError2, AffineReprojection, PinholeReprojection,
     NoRobust, HuberKernel, Huber2oKernel, GemanMcclureKernel, Scaled, robustified, COST_DTYPE,
     ContaminatedGaussian, OffsetResidual, ADAPTIVE_DTYPE,
-    optimize, optimizesingles, convertunfixed, cost, nullcallback, printoutcallback, storecostscallback, CostTrajectory,
+    optimize, optimizesingles, convertunfixed, cost, nullcallback, printoutcallback, storecostscallback, emcallback, CostTrajectory,
     newton, levenbergmarquardt, dogleg, gradientdescent,
 )

@@ -390,6 +390,13 @@ def printoutcallback(cost, problem, data, iteratedata):                   # src/
     return cost, 0
 
 
+def emcallback(cost, problem, data, iteratedata):                         # test/adaptivecost.jl:15-25
+    """The reference test's EM callback: refit the adaptive kernel of varnext from the squared residuals (optimize(kernel,
+    squarederrors), src/robustadaptive.jl:48-73 — on the device), recompute the cost of varnext, count the evaluation."""
+    data.ctx.adaptive_em(which=1)
+    return data.ctx.cost(1), 0
+
+
 # ------------------------------------------------------------------------------------------------
 # optimize!
 # ------------------------------------------------------------------------------------------------

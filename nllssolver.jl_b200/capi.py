@@ -20,7 +20,7 @@ TIME_LINEARIZE, TIME_LIN_POINT, TIME_LIN_CAM, TIME_COST, TIME_SCHUR, TIME_SOLVE_
 
 EXPORTS = [
     "nlls_create", "nlls_destroy", "nlls_last_error", "nlls_version", "nlls_comm_unique_id", "nlls_comm_init",
-    "nlls_set_variables", "nlls_set_costs", "nlls_add_costs", "nlls_set_unfixed", "nlls_optimize_singles", "nlls_prepare", "nlls_linearize", "nlls_cost", "nlls_solve", "nlls_update",
+    "nlls_set_variables", "nlls_set_costs", "nlls_add_costs", "nlls_set_unfixed", "nlls_optimize_singles", "nlls_prepare", "nlls_linearize", "nlls_cost", "nlls_adaptive_em", "nlls_solve", "nlls_update",
     "nlls_lm_begin", "nlls_lm_iterate", "nlls_lm_advance", "nlls_lm_end", "nlls_optimize", "nlls_get_variables", "nlls_dof",
     "nlls_get_gradient", "nlls_get_step", "nlls_hessian_len", "nlls_get_hessian_blocks", "nlls_hessian_nblocks",
     "nlls_get_hessian_index", "nlls_time_kernels", "nlls_timer_start", "nlls_timer_stop", "nlls_kernel_launches", "nlls_algorithmic_bytes", "nlls_algorithmic_flops",
@@ -70,6 +70,7 @@ def lib():
         L.nlls_comm_init.argtypes = [vp, C.c_int, C.c_int, C.c_void_p]
         L.nlls_set_variables.argtypes = [vp, C.c_int, _dp, C.c_int64, C.c_int64, C.c_int64, _ip]
         L.nlls_set_costs.argtypes = [vp, C.c_int, C.c_void_p, C.c_int64, C.c_int64, C.c_int, _dp, C.c_int, C.c_int64]
+        L.nlls_adaptive_em.argtypes = [vp, C.c_int, C.c_int]
         L.nlls_add_costs.argtypes = [vp, C.c_int, C.c_void_p, C.c_int64, C.c_int64, C.c_int, _dp, C.c_int]
         L.nlls_prepare.argtypes = [vp]
         L.nlls_set_unfixed.argtypes = [vp, C.POINTER(C.c_ubyte), C.c_int64]
@@ -158,6 +159,10 @@ class Context:
 
     def prepare(self):
         self._ck(lib().nlls_prepare(self.h))
+
+    def adaptive_em(self, which=1, maxiters=10):
+        """optimize(kernel, squarederrors, maxiters) (src/robustadaptive.jl:48-73) on the kernel variable of buffer `which`."""
+        self._ck(lib().nlls_adaptive_em(self.h, which, maxiters))
 
     def set_unfixed(self, mask=None):
         """optimize!(problem, options, unfixed): boolean vector by variable position (None: all variables are optimised)."""

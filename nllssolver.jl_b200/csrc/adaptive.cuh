@@ -125,6 +125,7 @@ struct AdaptDev {
     int nchunks, nmeans, dof;
     const int* moff;        // [nmeans] 0-based offset of each mean in the gradient / Hessian
     int koff;               // offset of the kernel variable's 3 DoF
+    const unsigned char* fixdof;   // optimize!(problem, options, unfixed): per DoF 1 = FIXED (nullptr: none), frozen in place like the BA path
 };
 
 // K_A1  linearisation: per chunk the 15 sums of computerescostgradhess (src/residual.jl:57-111, adaptive branch :81-88,103-107)
@@ -240,6 +241,11 @@ __global__ void adapt_solve_kernel(AdaptDev p, const double* __restrict__ H, con
     double A[AD_MAXDOF * AD_MAXDOF], b[AD_MAXDOF], y[AD_MAXDOF];
     for (int i = 0; i < d * d; ++i) A[i] = H[i];
     for (int i = 0; i < d; ++i) { A[i + d * i] += lambda; b[i] = g[i]; }   // uniformscaling!  src/iterators.jl:149
+    if (p.fixdof != nullptr)     // fixed variables: identity row / column and zero right-hand side — their step is exactly zero and the
+        for (int i = 0; i < d; ++i) if (p.fixdof[i]) {   // others see the reference's reduced system (src/linearsystem.jl:93-102)
+            for (int k = 0; k < d; ++k) { A[i + d * k] = 0.0; A[k + d * i] = 0.0; }
+            A[i + d * i] = 1.0; b[i] = 0.0;
+        }
     bool pd = true;
     {   // Cholesky A = L L' (lower, in place)
         double L[AD_MAXDOF * AD_MAXDOF];
@@ -262,7 +268,7 @@ __global__ void adapt_solve_kernel(AdaptDev p, const double* __restrict__ H, con
         }
     }
     if (!pd) {   // LU with partial pivoting
-        for (int i = 0; i < d; ++i) b[i] = g[i];
+        for (int i = 0; i < d; ++i) b[i] = (p.fixdof != nullptr && p.fixdof[i]) ? 0.0 : g[i];
         for (int j = 0; j < d; ++j) {
             int piv = j; double best = fabs(A[j + d * j]);
             for (int i = j + 1; i < d; ++i) if (fabs(A[i + d * j]) > best) { best = fabs(A[i + d * j]); piv = i; }
@@ -289,11 +295,66 @@ __global__ void adapt_solve_kernel(AdaptDev p, const double* __restrict__ H, con
 }
 
 // max_i |H_ii| (initlambda, src/iterators.jl:131-137)
-__global__ void adapt_maxdiag_kernel(const double* __restrict__ H, int d, double* out) {
+__global__ void adapt_maxdiag_kernel(const double* __restrict__ H, int d, double* out, const unsigned char* __restrict__ fixdof = nullptr) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     double m = 0.0;
-    for (int i = 0; i < d; ++i) m = nanmax(m, fabs(H[i + d * i]));
+    for (int i = 0; i < d; ++i) if (fixdof == nullptr || !fixdof[i]) m = nanmax(m, fabs(H[i + d * i]));
     *out = m;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// optimize(kernel::ContaminatedGaussian, squarederrors, maxiters)  (src/robustadaptive.jl:48-73): Expectation-Maximisation refit of
+// the kernel from the squared residuals — what the EM callback of test/adaptivecost.jl:15-25 calls between Newton steps on the means.
+// Per iteration: adapt_em_partial_kernel (one CTA per chunk: sum w err, sum w, sum err, count; squared errors are recomputed from
+// the means, never stored), adapt_em_sums_kernel (the chunk partials in order -> 4 totals; all-reduced over the ranks by the host
+// code), adapt_em_update_kernel (one thread: new parameters, the constructor's re-sort, isapprox stop -> `done` flag that turns the
+// remaining iterations into no-ops, so the whole refit is enqueued without a host round trip).
+// state[0..2] = oldparams (sigma1, sigma2, w), state[3] = done flag (0 / 1).
+// ---------------------------------------------------------------------------------------------------
+__global__ void adapt_em_init_kernel(const double* __restrict__ kern, double* __restrict__ state) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    state[0] = 1.0 / kern[0]; state[1] = 1.0 / kern[1]; state[2] = kern[2]; state[3] = 0.0;   // params(kernel)  :23,51
+}
+__global__ void __launch_bounds__(AD_THREADS) adapt_em_partial_kernel(AdaptDev p, const double* __restrict__ kern, const double* __restrict__ means,
+                                                                      const double* __restrict__ state, double* __restrict__ partials) {
+    __shared__ double s_red[AD_THREADS / 32];
+    if (state[3] != 0.0) return;
+    const int4 ch = p.chunks[blockIdx.x];
+    const double is1 = kern[0], is2 = kern[1], w = kern[2];
+    const double wratio = ((1 - w) * is2) / (is1 * w);                       // :53
+    const double hd = -(0.5 * (is2 * is2 - is1 * is1));                      // :54
+    const double mean = means[ch.x];
+    double a = 0.0, b = 0.0, c = 0.0, n = 0.0;
+    for (int j = ch.y + threadIdx.x; j < ch.z; j += AD_THREADS) {
+        const double r = mean - p.data[j];
+        const double err = r * r;
+        const double wi = 1 / (1 + wratio * exp(hd * err));                  // :59
+        a += wi * err; b += wi; c += err; n += 1.0;                          // :61-62, :50
+    }
+    a = block_sum(a, s_red); __syncthreads();
+    b = block_sum(b, s_red); __syncthreads();
+    c = block_sum(c, s_red); __syncthreads();
+    n = block_sum(n, s_red);
+    if (threadIdx.x == 0) { double* o = partials + (size_t)4 * blockIdx.x; o[0] = a; o[1] = b; o[2] = c; o[3] = n; }
+}
+__global__ void adapt_em_sums_kernel(const double* __restrict__ partials, int nchunks, const double* __restrict__ state, double* __restrict__ sums) {
+    const int i = threadIdx.x;
+    if (i >= 4 || state[3] != 0.0) return;
+    double t = 0.0;
+    for (int c = 0; c < nchunks; ++c) t += partials[(size_t)4 * c + i];
+    sums[i] = t;
+}
+__global__ void adapt_em_update_kernel(const double* __restrict__ sums, double* __restrict__ kern, double* __restrict__ state) {
+    if (threadIdx.x != 0 || blockIdx.x != 0 || state[3] != 0.0) return;
+    const double sigma1 = sums[0], tw = sums[1], total = sums[2], n = sums[3];
+    const double np3[3] = {sqrt(sigma1 / tw), sqrt((total - sigma1) / (n - tw)), tw / n};     // :65
+    double a = 1.0 / np3[0], b = 1.0 / np3[1];                                                // :66 (constructor :21, re-sort :13-15)
+    if (!(a >= b)) { const double t = a; a = b; b = t; }
+    kern[0] = a; kern[1] = b; kern[2] = np3[2];
+    double dn = 0, no = 0, nn = 0;                                                            // :67 isapprox(oldparams, newparams; rtol = 1e-6)
+    for (int i = 0; i < 3; ++i) { const double d = state[i] - np3[i]; dn += d * d; no += state[i] * state[i]; nn += np3[i] * np3[i]; }
+    if (sqrt(dn) <= 1e-6 * fmax(sqrt(no), sqrt(nn))) state[3] = 1.0;
+    for (int i = 0; i < 3; ++i) state[i] = np3[i];                                            // :70
 }
 
 }  // namespace nlls

@@ -15,10 +15,6 @@
 
 namespace nlls {
 
-struct DevProblem;
-__device__ __forceinline__ RobustParams rk_point(const DevProblem& p, int j);   // robust kernel of point-major observation j
-__device__ __forceinline__ RobustParams rk_cam(const DevProblem& p, int k);     // ... of camera-major observation k
-
 struct DevProblem {
     // point-major observations
     const int* obs_cam;
@@ -60,8 +56,11 @@ struct DevProblem {
     const unsigned char* fixB;
 };
 
-__device__ __forceinline__ RobustParams rk_point(const DevProblem& p, int j) { return p.obs_set ? p.rk_tab[p.obs_set[j]] : p.rk; }
-__device__ __forceinline__ RobustParams rk_cam(const DevProblem& p, int k) { return p.cm_set ? p.rk_tab[p.cm_set[k]] : p.rk; }
+// robust kernel of point-major observation j / camera-major observation k.  MS (several cost sets) is a template parameter of the
+// residual kernels: the single-set instantiations read p.rk from the parameter bank exactly as before (a run-time test on
+// p.obs_set measured +13 % on the camera pass)
+template <bool MS> __device__ __forceinline__ RobustParams rk_point(const DevProblem& p, int j) { if constexpr (MS) return p.rk_tab[p.obs_set[j]]; else return p.rk; }
+template <bool MS> __device__ __forceinline__ RobustParams rk_cam(const DevProblem& p, int k) { if constexpr (MS) return p.rk_tab[p.cm_set[k]]; else return p.rk; }
 
 // ---------------------------------------------------------------------------------------------------
 // K1  lin_point: fused residual + analytic Jacobian + robust weights + J'WJ for tiles of points (persistent, pipelined).
@@ -87,7 +86,7 @@ struct LinSmem {
     static constexpr size_t bytes = (size_t)(2 * OUT + PC + 16) * sizeof(double) + (size_t)(TP + 4) * sizeof(int);
 };
 
-template <class R, int TO, int TP>
+template <class R, int TO, int TP, bool MS = false>
 __global__ void __launch_bounds__(TO) lin_point_kernel(DevProblem p, const int4* __restrict__ tiles, const double* __restrict__ cams,
                                                        const double* __restrict__ pts, double* __restrict__ cost_partials) {
     constexpr int DC = R::DC, WB = 3 * DC, NP = (WB - 1) / 2, NW = TO / 32;
@@ -133,7 +132,7 @@ __global__ void __launch_bounds__(TO) lin_point_kernel(DevProblem p, const int4*
             R::resjac(cv, X, z.x, z.y, r, Jc, Jp);
             const double s = r[0] * r[0] + r[1] * r[1];               // sqnorm            src/residual.jl:72
             double rho, d1, d2;
-            robustifydcost(rk_point(p, ob0 + tid), s, rho, d1, d2);   //                   src/residual.jl:78
+            robustifydcost(rk_point<MS>(p, ob0 + tid), s, rho, d1, d2);   //                   src/residual.jl:78
             c = 0.5 * rho;                                            //                   src/residual.jl:110
             const bool fpt = p.fixB != nullptr && p.fixB[ptg];
             const bool fcross = fpt || (p.fixA != nullptr && p.fixA[cam]);
@@ -282,7 +281,7 @@ __global__ void __launch_bounds__(TO) cost_kernel(DevProblem p, const int4* __re
         if (tid < d.w) {
             double r[2];
             R::residual(cv, X, z.x, z.y, r);
-            c = 0.5 * robustify(rk_point(p, d.z + tid), r[0] * r[0] + r[1] * r[1]);
+            c = 0.5 * robustify(p.rk, r[0] * r[0] + r[1] * r[1]);   // (single cost set only: several sets always take the camera-major pass)
         }
         c = warp_sum(c);
         if (lane == 0) s_red[(it & 1) * NW + wid] = c;
@@ -311,7 +310,7 @@ __global__ void __launch_bounds__(TO) cost_kernel(DevProblem p, const int4* __re
 // accepted, the camera blocks it produced are exactly those of the re-linearisation at the accepted point (src/optimize.jl:169),
 // so the re-linearisation only runs the point pass and the camera pass costs nothing extra (launch_cost / do_linearize).
 // ---------------------------------------------------------------------------------------------------
-template <class R>
+template <class R, bool MS = false>
 __global__ void __launch_bounds__(256, (R::DC <= 6) ? 2 : 1) lin_cam_kernel(DevProblem p, const double* __restrict__ cams, const double* __restrict__ pts,
                                                       double* __restrict__ partials) {
     constexpr int DC = R::DC, NU = DC * (DC + 1) / 2 + DC;
@@ -347,7 +346,7 @@ __global__ void __launch_bounds__(256, (R::DC <= 6) ? 2 : 1) lin_cam_kernel(DevP
             R::resjac(cv, X, z.x, z.y, r, Jc, Jp);
             const double s = r[0] * r[0] + r[1] * r[1];
             double rho, d1, d2;
-            robustifydcost(rk_cam(p, j0 + 256 * u), s, rho, d1, d2);
+            robustifydcost(rk_cam<MS>(p, j0 + 256 * u), s, rho, d1, d2);
             cacc += 0.5 * rho;
             // explicit FMAs (the file is compiled with -fmad=false): this pass is FP64-issue bound, not HBM bound — ncu.  The
             // weights fold into the accumulation:  acc += d1 (J'J) + (2 d2 g) g'  (exact no-ops when d1 == 1 / d2 == 0)
@@ -1136,7 +1135,7 @@ __global__ void __launch_bounds__(256) reduce_stats_kernel(const double* __restr
 // ---------------------------------------------------------------------------------------------------
 constexpr int LONG_THREADS = 256;
 
-template <class R>
+template <class R, bool MS = false>
 __global__ void __launch_bounds__(LONG_THREADS) lin_point_long_kernel(DevProblem p, const int* __restrict__ long_pts, const double* __restrict__ cams,
                                                                       const double* __restrict__ pts, double* __restrict__ cost_partials) {
     constexpr int DC = R::DC, WB = 3 * DC, NW = LONG_THREADS / 32;
@@ -1163,7 +1162,7 @@ __global__ void __launch_bounds__(LONG_THREADS) lin_point_long_kernel(DevProblem
             R::resjac(cv, X, z.x, z.y, r, Jc, Jp);
             const double s = r[0] * r[0] + r[1] * r[1];
             double rho, d1, d2;
-            robustifydcost(rk_point(p, j), s, rho, d1, d2);
+            robustifydcost(rk_point<MS>(p, j), s, rho, d1, d2);
             c += 0.5 * rho;
             const bool fcross = fpt || (p.fixA != nullptr && p.fixA[cam]);
             double gc[DC], gp[3];

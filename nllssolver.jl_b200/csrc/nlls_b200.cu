@@ -122,6 +122,8 @@ struct nlls_ctx {
     int4* d_ad_chunks = nullptr;
     int* d_ad_moff = nullptr;
     double* d_ad_part = nullptr;
+    unsigned char* d_fixdof = nullptr;   // adaptive problems under an unfixed mask: per DoF 1 = fixed
+    double* d_em = nullptr;              // EM refit: [0..3] state (old parameters, done flag), [4..7] sums, then 4 partials per chunk
     int64_t nA = 0, nB = 0, nobs = 0, dof = 0, hlen = 0, nred = 0;
     bool cams_first = true;
     std::vector<int> h_obs_cam, h_obs_pt, h_obs_start, h_tile_pt, h_cam_start, h_cm_obs;
@@ -305,6 +307,7 @@ template <class R, int TO>
 int set_tile_attrs(nlls_ctx* ctx) {
     constexpr int TP = TO / 2;
     CK(cudaFuncSetAttribute(lin_point_kernel<R, TO, TP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LinSmem<R, TO, TP>::bytes));
+    CK(cudaFuncSetAttribute(lin_point_kernel<R, TO, TP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LinSmem<R, TO, TP>::bytes));
     CK(cudaFuncSetAttribute(backsub_kernel<R::DC, TO, TP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BacksubSmem<R::DC, TO, TP>::bytes));
     int occ = 1;
     auto grid_for = [&](int o, const char* env) {
@@ -350,25 +353,36 @@ template <class R>
 int launch_linearize(nlls_ctx* ctx, bool do_point = true, int do_cam = 1) {
     DevProblem p = devproblem(ctx);
     constexpr int NU = R::DC * (R::DC + 1) / 2 + R::DC;
+    const bool ms = ctx->sets.size() > 1;   // several cost sets: the kernels look the robust kernel up per observation
     if (do_cam) {
         CK(cudaEventRecord(ctx->ev_fork, ctx->st));
         CK(cudaStreamWaitEvent(ctx->st2, ctx->ev_fork, 0));
-        if (do_cam == 1 && ctx->nitems > 0) { lin_cam_kernel<R><<<ctx->nitems, 256, 0, ctx->st2>>>(p, ctx->d_A[ctx->cur], ctx->d_B[ctx->cur], ctx->d_cam_part); ctx->launches++; }
+        if (do_cam == 1 && ctx->nitems > 0) {
+            if (ms) lin_cam_kernel<R, true><<<ctx->nitems, 256, 0, ctx->st2>>>(p, ctx->d_A[ctx->cur], ctx->d_B[ctx->cur], ctx->d_cam_part);
+            else lin_cam_kernel<R><<<ctx->nitems, 256, 0, ctx->st2>>>(p, ctx->d_A[ctx->cur], ctx->d_B[ctx->cur], ctx->d_cam_part);
+            ctx->launches++;
+        }
         const int tot = (int)ctx->nA * NU;
         cam_finalize_kernel<R::DC><<<(tot + 255) / 256, 256, 0, ctx->st2>>>(p, ctx->d_cam_part); ctx->launches++;
         CK(cudaEventRecord(ctx->ev_join, ctx->st2));
     }
     if (do_point && ctx->ntiles > 0) {
-        if (ctx->tile_obs == 64)
-            lin_point_kernel<R, 64, 32><<<ctx->lin_grid, 64, LinSmem<R, 64, 32>::bytes, ctx->st>>>(p, ctx->d_tiles, ctx->d_A[ctx->cur], ctx->d_B[ctx->cur], ctx->d_cost_part);
-        else if (ctx->tile_obs == 128)
-            lin_point_kernel<R, 128, 64><<<ctx->lin_grid, 128, LinSmem<R, 128, 64>::bytes, ctx->st>>>(p, ctx->d_tiles, ctx->d_A[ctx->cur], ctx->d_B[ctx->cur], ctx->d_cost_part);
-        else
-            lin_point_kernel<R, 256, 128><<<ctx->lin_grid, 256, LinSmem<R, 256, 128>::bytes, ctx->st>>>(p, ctx->d_tiles, ctx->d_A[ctx->cur], ctx->d_B[ctx->cur], ctx->d_cost_part);
+        const double *cA = ctx->d_A[ctx->cur], *cB = ctx->d_B[ctx->cur];
+        if (ctx->tile_obs == 64) {
+            if (ms) lin_point_kernel<R, 64, 32, true><<<ctx->lin_grid, 64, LinSmem<R, 64, 32>::bytes, ctx->st>>>(p, ctx->d_tiles, cA, cB, ctx->d_cost_part);
+            else lin_point_kernel<R, 64, 32><<<ctx->lin_grid, 64, LinSmem<R, 64, 32>::bytes, ctx->st>>>(p, ctx->d_tiles, cA, cB, ctx->d_cost_part);
+        } else if (ctx->tile_obs == 128) {
+            if (ms) lin_point_kernel<R, 128, 64, true><<<ctx->lin_grid, 128, LinSmem<R, 128, 64>::bytes, ctx->st>>>(p, ctx->d_tiles, cA, cB, ctx->d_cost_part);
+            else lin_point_kernel<R, 128, 64><<<ctx->lin_grid, 128, LinSmem<R, 128, 64>::bytes, ctx->st>>>(p, ctx->d_tiles, cA, cB, ctx->d_cost_part);
+        } else {
+            if (ms) lin_point_kernel<R, 256, 128, true><<<ctx->lin_grid, 256, LinSmem<R, 256, 128>::bytes, ctx->st>>>(p, ctx->d_tiles, cA, cB, ctx->d_cost_part);
+            else lin_point_kernel<R, 256, 128><<<ctx->lin_grid, 256, LinSmem<R, 256, 128>::bytes, ctx->st>>>(p, ctx->d_tiles, cA, cB, ctx->d_cost_part);
+        }
         ctx->launches++;
     }
     if (do_point && ctx->nlong > 0) {   // irregular points: one CTA each, cost partials behind the tiles'
-        lin_point_long_kernel<R><<<ctx->nlong, LONG_THREADS, 0, ctx->st>>>(p, ctx->d_long_pts, ctx->d_A[ctx->cur], ctx->d_B[ctx->cur], ctx->d_cost_part + ctx->ntiles);
+        if (ms) lin_point_long_kernel<R, true><<<ctx->nlong, LONG_THREADS, 0, ctx->st>>>(p, ctx->d_long_pts, ctx->d_A[ctx->cur], ctx->d_B[ctx->cur], ctx->d_cost_part + ctx->ntiles);
+        else lin_point_long_kernel<R><<<ctx->nlong, LONG_THREADS, 0, ctx->st>>>(p, ctx->d_long_pts, ctx->d_A[ctx->cur], ctx->d_B[ctx->cur], ctx->d_cost_part + ctx->ntiles);
         ctx->launches++;
     }
     if (do_cam) CK(cudaStreamWaitEvent(ctx->st, ctx->ev_join, 0));
@@ -385,7 +399,8 @@ int launch_cost(nlls_ctx* ctx, int which, int slot, double* part = nullptr, bool
     DevProblem p = devproblem(ctx);
     constexpr int NU = R::DC * (R::DC + 1) / 2 + R::DC;
     if (!part) part = ctx->d_cam_part;
-    if (ctx->cost_pointmajor && ctx->nlong == 0) {   // NLLS_B200_COST=tiles: the round-1 cost kernel (point-major tiles)
+    const bool ms = ctx->sets.size() > 1;
+    if (ctx->cost_pointmajor && ctx->nlong == 0 && !ms) {   // NLLS_B200_COST=tiles: the round-1 cost kernel (point-major tiles)
         if (ctx->ntiles > 0) {
             if (ctx->tile_obs == 64) cost_kernel<R, 64><<<ctx->cost_grid, 64, 0, ctx->st>>>(p, ctx->d_tiles, ctx->d_A[which], ctx->d_B[which], ctx->d_cost_part);
             else if (ctx->tile_obs == 128) cost_kernel<R, 128><<<ctx->cost_grid, 128, 0, ctx->st>>>(p, ctx->d_tiles, ctx->d_A[which], ctx->d_B[which], ctx->d_cost_part);
@@ -394,7 +409,11 @@ int launch_cost(nlls_ctx* ctx, int which, int slot, double* part = nullptr, bool
         }
         reduce_partials_kernel<<<1, 1024, 0, ctx->st>>>(ctx->d_cost_part, ctx->ntiles, ctx->d_scal + slot, 0); ctx->launches++;
     } else {
-        if (ctx->nitems > 0) { lin_cam_kernel<R><<<ctx->nitems, 256, 0, ctx->st>>>(p, ctx->d_A[which], ctx->d_B[which], part); ctx->launches++; }
+        if (ctx->nitems > 0) {
+            if (ms) lin_cam_kernel<R, true><<<ctx->nitems, 256, 0, ctx->st>>>(p, ctx->d_A[which], ctx->d_B[which], part);
+            else lin_cam_kernel<R><<<ctx->nitems, 256, 0, ctx->st>>>(p, ctx->d_A[which], ctx->d_B[which], part);
+            ctx->launches++;
+        }
         cam_cost_reduce_kernel<<<1, 1024, 0, ctx->st>>>(part, ctx->nitems, NU + 1, ctx->d_scal + slot); ctx->launches++;
         if (part == ctx->d_cam_part) ctx->cam_part_vars = which;   // the camera blocks of these variables are now in d_cam_part
     }
@@ -602,6 +621,7 @@ AdaptDev adaptdev(const nlls_ctx* c) {
     AdaptDev p;
     p.data = c->d_ad_data; p.chunks = c->d_ad_chunks; p.nchunks = c->ad_nchunks; p.nmeans = (int)c->nB; p.dof = (int)c->dof;
     p.moff = c->d_ad_moff; p.koff = c->ad_koff;
+    p.fixdof = c->masked ? c->d_fixdof : nullptr;
     return p;
 }
 int adapt_linearize(nlls_ctx* ctx) {
@@ -841,6 +861,7 @@ int do_try(nlls_ctx* ctx, double lambda) {
 
 
 namespace {
+int apply_unfixed(nlls_ctx* ctx);
 // makesymmvls for an adaptive-kernel problem: variable -> offset map (block order = variable order, src/linearsystem.jl:93-102),
 // residuals grouped by mean variable and cut into single-mean chunks.
 int prepare_adaptive(nlls_ctx* ctx) {
@@ -908,8 +929,7 @@ int prepare_adaptive(nlls_ctx* ctx) {
     ctx->prepared = true;
     ctx->lm_active = false;
     ctx->masked = false;
-    for (unsigned char u : ctx->h_unfixed) if (!u) FAIL(NLLS_ERR_UNSUPPORTED, "unfixed masks are not implemented for the adaptive-kernel residuals");
-    return NLLS_OK;
+    return apply_unfixed(ctx);
 }
 }  // namespace
 
@@ -917,8 +937,16 @@ namespace {
 // (re)build the per-class fixed flags from h_unfixed and upload them (prepared contexts only)
 int apply_unfixed(nlls_ctx* ctx) {
     ctx->masked = false;
-    if (!ctx->prepared || ctx->adaptive) {
-        if (ctx->adaptive) for (unsigned char u : ctx->h_unfixed) if (!u) FAIL(NLLS_ERR_UNSUPPORTED, "unfixed masks are not implemented for the adaptive-kernel residuals");
+    if (!ctx->prepared) return NLLS_OK;
+    if (ctx->adaptive) {   // dense system: a per-DoF mask (kernel variable: 3 DoF at ad_koff, mean m: 1 DoF at moff[m])
+        const VarSet& K = ctx->vars[ctx->vtA];
+        const VarSet& M = ctx->vars[ctx->vtB];
+        auto fixedv = [&](int64_t gidx) { return (size_t)(gidx - 1) < ctx->h_unfixed.size() && !ctx->h_unfixed[(size_t)(gidx - 1)]; };
+        std::vector<unsigned char> fd((size_t)ctx->dof, 0);
+        ctx->h_fixA.assign(K.gidx.size(), 0); ctx->h_fixB.assign(M.gidx.size(), 0);
+        if (!K.gidx.empty() && fixedv(K.gidx[0])) { ctx->h_fixA[0] = 1; ctx->masked = true; for (int a = 0; a < 3; ++a) fd[(size_t)ctx->ad_koff + a] = 1; }
+        for (size_t m = 0; m < M.gidx.size(); ++m) if (fixedv(M.gidx[m])) { ctx->h_fixB[m] = 1; ctx->masked = true; fd[(size_t)ctx->h_ad_moff[m]] = 1; }
+        if (ctx->masked) TRY(upload(ctx, &ctx->d_fixdof, fd));
         return NLLS_OK;
     }
     const VarSet& A = ctx->vars[ctx->vtA];
@@ -959,8 +987,14 @@ int nlls_optimize_singles(nlls_ctx* ctx, int vartype, const nlls_options* opts, 
     CK(cudaMemsetAsync(d_it, 0, sizeof(unsigned long long), ctx->st));
     DevProblem p = devproblem(ctx);
     const int grid = (int)((ctx->nB + 127) / 128);
-    if (ctx->restype == NLLS_RES_AFFINE_BA) singles_point_kernel<AffineBA><<<grid, 128, 0, ctx->st>>>(p, ctx->d_A[ctx->cur], ctx->d_B[ctx->cur], so, d_it);
-    else singles_point_kernel<PinholeBA><<<grid, 128, 0, ctx->st>>>(p, ctx->d_A[ctx->cur], ctx->d_B[ctx->cur], so, d_it);
+    const bool ms = ctx->sets.size() > 1;
+    if (ctx->restype == NLLS_RES_AFFINE_BA) {
+        if (ms) singles_point_kernel<AffineBA, true><<<grid, 128, 0, ctx->st>>>(p, ctx->d_A[ctx->cur], ctx->d_B[ctx->cur], so, d_it);
+        else singles_point_kernel<AffineBA><<<grid, 128, 0, ctx->st>>>(p, ctx->d_A[ctx->cur], ctx->d_B[ctx->cur], so, d_it);
+    } else {
+        if (ms) singles_point_kernel<PinholeBA, true><<<grid, 128, 0, ctx->st>>>(p, ctx->d_A[ctx->cur], ctx->d_B[ctx->cur], so, d_it);
+        else singles_point_kernel<PinholeBA><<<grid, 128, 0, ctx->st>>>(p, ctx->d_A[ctx->cur], ctx->d_B[ctx->cur], so, d_it);
+    }
     ctx->launches++;
     CK(cudaGetLastError());
     unsigned long long h_it = 0;
@@ -1028,7 +1062,7 @@ int nlls_destroy(nlls_ctx* ctx) {
                     ctx->d_lvl_cols, ctx->d_red_tasks, ctx->d_red_upds, ctx->d_red_targets, ctx->d_colptr,
                     ctx->d_col_tile, ctx->d_col_row, ctx->d_Linv, ctx->d_xp, ctx->d_stile_pt, ctx->d_chunk_off, ctx->d_chunks, ctx->d_ents, ctx->d_tiles, ctx->d_camstat_part,
                     ctx->d_ad_data, ctx->d_ad_chunks, ctx->d_ad_moff, ctx->d_ad_part, ctx->d_ent_off, ctx->d_cta_item, ctx->d_items, ctx->d_units, ctx->d_wtab, ctx->d_blob,
-                    ctx->d5_cta_item, ctx->d5_items, ctx->d5_blob, ctx->d5_ftab, ctx->d_out_pts, ctx->d_bwd_order, ctx->d_bwd_flags, ctx->d_nat_of_pos, ctx->d_long_pts, ctx->d_obs_set, ctx->d_cm_set, ctx->d_rk_tab, ctx->d_fixA, ctx->d_fixB, ctx->d_cauchy, ctx->d_vec_part};
+                    ctx->d5_cta_item, ctx->d5_items, ctx->d5_blob, ctx->d5_ftab, ctx->d_out_pts, ctx->d_bwd_order, ctx->d_bwd_flags, ctx->d_nat_of_pos, ctx->d_long_pts, ctx->d_obs_set, ctx->d_cm_set, ctx->d_rk_tab, ctx->d_fixdof, ctx->d_em, ctx->d_fixA, ctx->d_fixB, ctx->d_cauchy, ctx->d_vec_part};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (ctx->red_graph_exec) cudaGraphExecDestroy(ctx->red_graph_exec);
     if (ctx->h_scal) cudaFreeHost(ctx->h_scal);
@@ -1850,6 +1884,30 @@ int nlls_linearize(nlls_ctx* ctx, double* cost) {
     return do_linearize(ctx, cost);
 }
 
+// optimize(kernel, squarederrors, maxiters) of src/robustadaptive.jl:48-73 on the device: refits the adaptive kernel variable of
+// buffer `which` (0 variables, 1 varnext, 2 varbest) in place from the squared residuals at that buffer's means.
+int nlls_adaptive_em(nlls_ctx* ctx, int which, int maxiters) {
+    if (!ctx || which < 0 || which > 2 || maxiters < 0) return NLLS_ERR_INVALID;
+    TRY(nlls_prepare(ctx));
+    if (!ctx->adaptive) FAIL(NLLS_ERR_INVALID, "nlls_adaptive_em: the problem has no adaptive robust kernel");
+    CK(cudaSetDevice(ctx->device));
+    const int buf = which == 0 ? ctx->cur : (which == 1 ? ctx->nxt : ctx->bst);
+    const AdaptDev p = adaptdev(ctx);
+    if (!ctx->d_em) TRY(dalloc(ctx, &ctx->d_em, (size_t)8 + 4 * (size_t)std::max(ctx->ad_nchunks, 1)));
+    double *state = ctx->d_em, *sums = ctx->d_em + 4, *part = ctx->d_em + 8;
+    adapt_em_init_kernel<<<1, 32, 0, ctx->st>>>(ctx->d_A[buf], state); ctx->launches++;
+    for (int it = 0; it < maxiters; ++it) {
+        if (ctx->ad_nchunks > 0) { adapt_em_partial_kernel<<<ctx->ad_nchunks, AD_THREADS, 0, ctx->st>>>(p, ctx->d_A[buf], ctx->d_B[buf], state, part); ctx->launches++; }
+        adapt_em_sums_kernel<<<1, 32, 0, ctx->st>>>(part, ctx->ad_nchunks, state, sums); ctx->launches++;
+        TRY(allreduce(ctx, sums, 4, ncclSum));   // residuals are sharded over the ranks; `done` is replicated, so every rank takes part
+        adapt_em_update_kernel<<<1, 32, 0, ctx->st>>>(sums, ctx->d_A[buf], state); ctx->launches++;
+    }
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(ctx->st));
+    for (auto& kv : ctx->vars) kv.second.stale = true;
+    return NLLS_OK;
+}
+
 int nlls_cost(nlls_ctx* ctx, int which, double* cost) {
     if (!ctx || which < 0 || which > 2) return NLLS_ERR_INVALID;
     TRY(nlls_prepare(ctx));
@@ -1859,6 +1917,7 @@ int nlls_cost(nlls_ctx* ctx, int which, double* cost) {
     else TRY(DISPATCH(ctx, launch_cost, ctx, buf, SC_COST_TRY, ctx->d_cam_part2));
     TRY(fetch_scalars(ctx));
     if (cost) *cost = ctx->h_scal[SC_COST_TRY];
+    if (ctx->lm_active && ctx->lm_phase == 1) ctx->costcomputations += 1;   // a callback re-evaluating the cost (test/adaptivecost.jl:21-22)
     return NLLS_OK;
 }
 
@@ -1942,7 +2001,7 @@ int nlls_lm_iterate(nlls_ctx* ctx, nlls_iterinfo* info) {
     if (o.iterator == NLLS_ITER_GD) return DISPATCH(ctx, iterate_gd, ctx, info);
     // ---- iterate!(::LevMarData)                                 src/iterators.jl:139-172
     if (ctx->lambda == 0) {                                      // initlambda  :131-137,142-144
-        if (ctx->adaptive) { adapt_maxdiag_kernel<<<1, 32, 0, ctx->st>>>(ctx->d_H, (int)ctx->dof, ctx->d_scal + SC_MAXDIAG); ctx->launches++; CK(cudaGetLastError()); }
+        if (ctx->adaptive) { adapt_maxdiag_kernel<<<1, 32, 0, ctx->st>>>(ctx->d_H, (int)ctx->dof, ctx->d_scal + SC_MAXDIAG, ctx->masked ? ctx->d_fixdof : nullptr); ctx->launches++; CK(cudaGetLastError()); }
         else TRY(DISPATCH(ctx, launch_maxdiag, ctx));
         TRY(fetch_scalars(ctx));
         ctx->lambda = ctx->h_scal[SC_MAXDIAG] * 1e-6;
@@ -2080,7 +2139,7 @@ int nlls_get_variables(nlls_ctx* ctx, int vartype, int which, double* aos, int64
 
 int64_t nlls_dof(nlls_ctx* ctx) {   // length of linsystem.b / x: the unfixed variables' DoF
     if (!ctx || !ctx->prepared) return -1;
-    if (!ctx->masked) return ctx->dof;
+    if (!ctx->masked || ctx->adaptive) return ctx->dof;   // (adaptive problems keep the full dense system: fixed entries of b / x are zero)
     int64_t d = 0;
     for (unsigned char f : ctx->h_fixA) if (!f) d += ctx->DC;
     for (unsigned char f : ctx->h_fixB) if (!f) d += 3;

@@ -39,7 +39,7 @@ __device__ __forceinline__ void solve_sym3(const double a[6], const double b[3],
     }
 }
 
-template <class R>
+template <class R, bool MS = false>
 __global__ void __launch_bounds__(128) singles_point_kernel(DevProblem p, const double* __restrict__ cams, double* __restrict__ pts, SinglesOpts o,
                                                             unsigned long long* __restrict__ iters) {
     const int pt = blockIdx.x * blockDim.x + threadIdx.x;
@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(128) singles_point_kernel(DevProblem p, const 
             R::resjac(cv, Xc, z.x, z.y, r, Jc, Jp);
             const double s = r[0] * r[0] + r[1] * r[1];
             double rho, d1, d2;
-            robustifydcost(rk_point(p, j), s, rho, d1, d2);
+            robustifydcost(rk_point<MS>(p, j), s, rho, d1, d2);
             c += 0.5 * rho;
             double gp[3];
 #pragma unroll
@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(128) singles_point_kernel(DevProblem p, const 
             const double2 z = p.obs_z[j];
             double r[2];
             R::residual(cv, Xc, z.x, z.y, r);
-            c += 0.5 * robustify(rk_point(p, j), r[0] * r[0] + r[1] * r[1]);
+            c += 0.5 * robustify(rk_point<MS>(p, j), r[0] * r[0] + r[1] * r[1]);
         }
         return c;
     };

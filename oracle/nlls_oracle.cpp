@@ -169,6 +169,32 @@ Variable make_pinhole(const double* rod, const double* t, double f, double k1, d
     return c;
 }
 
+// optimize(kernel::ContaminatedGaussian{T}, squarederrors, maxiters=10)            src/robustadaptive.jl:48-73
+void em_optimize(double k[3], const double* sq, int64_t n, int maxiters) {
+    double total = 0;                                                        // :50  totalsquarederror = sum(squarederrors)
+    for (int64_t i = 0; i < n; ++i) total += sq[i];
+    double oldp[3] = {1.0 / k[0], 1.0 / k[1], k[2]};                         // :51  params(kernel)  (src/robustadaptive.jl:23)
+    for (int iter = 0; iter < maxiters; ++iter) {                            // :52
+        const double is1 = k[0], is2 = k[1], w = k[2];
+        const double wratio = ((1 - w) * is2) / (is1 * w);                   // :53
+        const double halfs1sqminuss2sq = -(0.5 * (is2 * is2 - is1 * is1));   // :54  -kernel.halfs2sqminuss1sq  (:19)
+        double sigma1 = 0, totalweight = 0;
+        for (int64_t i = 0; i < n; ++i) {                                    // :57-63
+            const double wi = 1 / (1 + wratio * std::exp(halfs1sqminuss2sq * sq[i]));
+            sigma1 += wi * sq[i];
+            totalweight += wi;
+        }
+        const double newp[3] = {std::sqrt(sigma1 / totalweight), std::sqrt((total - sigma1) / ((double)n - totalweight)), totalweight / (double)n};   // :65
+        double a = 1.0 / newp[0], b = 1.0 / newp[1];                         // :66  ContaminatedGaussian(newparams...)  (:21, re-sort :13-15)
+        if (!(a >= b)) std::swap(a, b);
+        k[0] = a; k[1] = b; k[2] = newp[2];
+        double dn = 0, no = 0, nn = 0;                                       // :67  isapprox(oldparams, newparams; rtol = 1e-6)
+        for (int i = 0; i < 3; ++i) { dn += (oldp[i] - newp[i]) * (oldp[i] - newp[i]); no += oldp[i] * oldp[i]; nn += newp[i] * newp[i]; }
+        if (std::sqrt(dn) <= 1e-6 * std::max(std::sqrt(no), std::sqrt(nn))) break;
+        for (int i = 0; i < 3; ++i) oldp[i] = newp[i];                       // :70
+    }
+}
+
 Variable update(const Variable& var, const double* x) {
     Variable out = var;
     switch (var.type) {
@@ -399,8 +425,11 @@ int64_t Problem::addvariable(const Variable& v) {
     return (int64_t)variables.size();
 }
 void Problem::addcost(const Cost& c, const RobustSpec& k) {
+    // a VectorRepo slot per concrete residual TYPE (src/VectorRepo.jl:3): in Julia robustkernel(res) belongs to the type, so the same
+    // residual struct with another kernel is another type with its own vector (test/functional.jl:14-24 registers two types)
     size_t t = 0;
-    for (; t < costtypes.size(); ++t) if (costtypes[t] == c.type) break;
+    for (; t < costtypes.size(); ++t)
+        if (costtypes[t] == c.type && kernels[t].kind == k.kind && kernels[t].width == k.width && kernels[t].scaled == k.scaled && kernels[t].height == k.height) break;
     if (t == costtypes.size()) { costtypes.push_back(c.type); costs.emplace_back(); kernels.push_back(k); }
     costs[t].push_back(c);
     lsready = false;
@@ -1018,6 +1047,19 @@ Result Problem::optimize(const Options& opt, std::vector<IterRecord>* trace) {
         cost = cost_;
         // ---- back in optimizeinternal!                                      src/optimize.jl:128-165
         int64_t terminate = opt.callback_terminate;            // callback(cost, ...) -> (cost, terminate)
+        if (callback_kind == 1) {                              // emcallback  test/adaptivecost.jl:15-25
+            std::vector<double> sq;                            // :17  squared errors at varnext, cost storage order
+            int64_t kvar = 0;
+            for (size_t t = 0; t < costs.size(); ++t) if (costtypes[t] == RT_ADAPTIVE_OFFSET)
+                for (const Cost& c : costs[t]) { const double r = varnext[(size_t)c.vi[1] - 1].v[0] - c.data[0]; sq.push_back(r * r); kvar = c.vi[0]; }
+            if (kvar > 0) {
+                em_optimize(varnext[(size_t)kvar - 1].v, sq.data(), (int64_t)sq.size());   // :19
+                t0 = time_ns();
+                cost = this->cost(varnext);                    // :21
+                t_cost += time_ns() - t0;
+                res.costcomputations += 1;                     // :22
+            }
+        }
         double dcost = bestcost - cost;
         if (dcost >= 0) { bestcost = cost; fails = 0; }
         else {

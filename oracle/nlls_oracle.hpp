@@ -171,8 +171,15 @@ struct Problem {
     // optimizesingles!(problem, options, indices): every listed variable on its own, all others fixed, over the costs that depend
     // on it (src/optimize.jl:60-76,183-205).  Returns the summed iteration count.
     int64_t optimizesingles(const Options& opt, const std::vector<int64_t>& indices);
+    // callback emulation: 0 none (nullcallback), 1 the EM callback of test/adaptivecost.jl:15-25 (refit the adaptive kernel of varnext
+    // from the squared residuals, recompute the cost, costcomputations += 1)
+    int callback_kind = 0;
     std::string lasterror;
 };
+
+// optimize(kernel::ContaminatedGaussian, squarederrors, maxiters = 10): Expectation-Maximisation refit of the kernel parameters
+// (src/robustadaptive.jl:48-73).  k = (invsigma1, invsigma2, w) in, refitted kernel out (constructor re-sort applied).
+void em_optimize(double k[3], const double* squarederrors, int64_t n, int maxiters = 10);
 
 // Exact forward-mode derivatives of the adaptive kernel: value, 4-gradient, 4x4 Hessian of
 // x -> robustify(update(kernel, x[0:3]), cost + x[3]) at x = 0.    src/autodiff.jl:164-165

@@ -73,6 +73,10 @@ def lib():
         L.orc_solve.argtypes = [C.c_void_p, C.c_double, _dp]
         L.orc_optimize.restype = C.c_int64
         L.orc_optimize.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]
+        L.orc_set_callback.argtypes = [C.c_void_p, C.c_int]
+        L.orc_set_callback.restype = None
+        L.orc_em_optimize.argtypes = [_dp, _dp, C.c_int64, C.c_int]
+        L.orc_em_optimize.restype = None
         L.orc_bsm_new.restype = C.c_void_p
         L.orc_bsm_new.argtypes = [C.c_int64, C.c_int64, _ip, _ip, _i32p, _i32p]
         L.orc_bsm_free.argtypes = [C.c_void_p]
@@ -402,9 +406,22 @@ class Problem:
         lib().orc_solve(self.h, lam, _p(out))
         return out
 
+    def set_callback(self, kind):
+        """0: nullcallback; 1: the EM callback of test/adaptivecost.jl:15-25 (refit the adaptive kernel of varnext, recompute the cost)."""
+        lib().orc_set_callback(self.h, int(kind))
+
     def optimize(self, options=None, maxtrace=4096):
         options = options or Options()
         res = Result()
         trace = (IterRecord * maxtrace)()
         n = lib().orc_optimize(self.h, C.byref(options), C.byref(res), trace, maxtrace)
         return res, [trace[i] for i in range(min(n, maxtrace))]
+
+
+def em_optimize(kernel3, squarederrors, maxiters=10):
+    """optimize(kernel::ContaminatedGaussian, squarederrors, maxiters) (src/robustadaptive.jl:48-73): kernel3 = stored
+    (invsigma1, invsigma2, w) -> refitted stored triple."""
+    k = _d(np.array(kernel3, dtype=np.float64).copy())
+    sq = _d(squarederrors)
+    lib().orc_em_optimize(_p(k), _p(sq), len(sq), int(maxiters))
+    return k

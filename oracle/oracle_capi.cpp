@@ -137,6 +137,9 @@ void orc_solve(void* p, double lambda, double* xout) {
     for (int64_t j = 0; j < n; ++j) xout[j] = -xout[j];
 }
 
+void orc_set_callback(void* p, int kind) { ((Problem*)p)->callback_kind = kind; }
+void orc_em_optimize(double* k3, const double* sq, int64_t n, int maxiters) { em_optimize(k3, sq, n, maxiters); }
+
 struct orc_options { double reldcost, absdcost, dstep; int64_t maxfails, maxiters; uint64_t maxtime_ns; int64_t callback_terminate; int64_t iterator; };
 struct orc_result { double startcost, bestcost, timetotal, timeinit, timecost, timegradient, timesolver;
                     int64_t termination, niterations, costcomputations, gradientcomputations, linearsolvers; };

@@ -174,3 +174,44 @@ def test_adaptive_newton_trajectory(pkg, orc, start):
     m = ctx.get_variables(pkg.capi.VAR_SCALAR, 2, 1)[:, 0]
     assert np.allclose(np.concatenate([k, m]), P.variables(), rtol=1e-6, atol=1e-9)
     ctx.close()
+
+
+def test_adaptive_em_refit_matches_oracle(pkg, orc):
+    """optimize(kernel, squarederrors, maxiters) (src/robustadaptive.jl:48-73) on the device against the oracle's restatement, on
+    the squared residuals of the two-mean problem at non-trivial means; 1, 3 and 10 iterations (10 stops early by isapprox)."""
+    data, vi, _ = _two_means()
+    means = [-0.7, 1.2]
+    r = np.where(vi == 2, means[0], means[1]) - data
+    for iters in (1, 3, 10):
+        ref = orc.em_optimize(pkg.ContaminatedGaussian(0.5, 5.0, 0.6).stored(), r * r, iters)
+        ctx = _cuda(pkg, data, vi, means)
+        ctx.adaptive_em(which=0, maxiters=iters)
+        k = ctx.get_variables(pkg.capi.VAR_CONTAMGAUSS, 1, 3)[0]
+        assert np.allclose(k, ref, rtol=1e-12, atol=0)
+        ctx.close()
+
+
+def test_adaptive_em_callback_with_fixed_kernel(pkg, orc):
+    """test/adaptivecost.jl:48-59: Newton on the means only (unfixed = [false, true, true]) alternating with the EM refit of the
+    kernel in the callback.  Same iteration count and final cost as the oracle running the same callback; the reference test's own
+    assertion (parameters ~ (1, 10, 0.8), means ~ -1 / +1, rtol 0.1) holds."""
+    data, vi, means = _two_means()
+    P = _oracle(orc, data, vi, means)
+    P.set_unfixed(np.array([0, 1, 1], dtype=np.uint8))
+    P.set_callback(1)
+    res_ref, tr_ref = P.optimize(orc.Options(iterator=orc.IT_NEWTON))
+    prob = pkg.NLLSProblem()
+    prob.addvariable(pkg.ContaminatedGaussian(0.5, 5.0, 0.6))
+    prob.addvariable(0.0)
+    prob.addvariable(0.0)
+    aos = np.zeros(len(data), dtype=pkg.ADAPTIVE_DTYPE)
+    aos["data"], aos["varind"] = data, vi
+    prob.addcosts(pkg.OffsetResidual, aos)
+    res = pkg.optimize(prob, pkg.NLLSOptions(iterator=pkg.newton), unfixed=[False, True, True], callback=pkg.emcallback)
+    assert res.niterations == res_ref.niterations
+    assert res.costcomputations == res_ref.costcomputations
+    assert res.bestcost == pytest.approx(res_ref.bestcost, rel=TOL_FINAL)
+    assert np.allclose(prob.variables[0].params(), [1.0, 10.0, 0.8], rtol=0.1)          # test/adaptivecost.jl:57
+    assert prob.variables[1] == pytest.approx(-1.0, rel=0.1) and prob.variables[2] == pytest.approx(1.0, rel=0.1)   # :58-59
+    ref_vars = P.variables()
+    assert np.allclose(np.concatenate([prob.variables[0].stored(), [prob.variables[1], prob.variables[2]]]), ref_vars, rtol=1e-6)

@@ -336,3 +336,29 @@ def test_bal_reader_round_trip(pkg, orc, tmp_path):
         f.write("2 2 1\n0 0 1.0 2.0\n")
     with pytest.raises(ValueError):
         pkg.bal.read_bal(tmp_path / "bad.txt")
+
+
+def test_oracle_em_refit_and_callback(orc):
+    """test/adaptivecost.jl:48-59 on the oracle: Newton on the two means with the kernel fixed, alternating with the EM refit of the
+    kernel (optimize(kernel, squarederrors), src/robustadaptive.jl:48-73) in the callback -> parameters ~ (1, 10, 0.8), means ~ -1 / +1
+    (rtol 0.1, the reference's own assertion); and EM alone recovers the mixture it was drawn from."""
+    rng = np.random.default_rng(1)
+    pts = np.concatenate([rng.standard_normal(800), rng.standard_normal(200) * 10.0])
+    data = np.zeros(2 * len(pts)); vi = np.ones((2 * len(pts), 2), dtype=np.int64)
+    data[0::2], vi[0::2, 1] = pts - 1, 2
+    data[1::2], vi[1::2, 1] = pts + 1, 3
+    P = orc.Problem()
+    P.add_variables(orc.VT_CONTAMGAUSS, [orc.cg_make(0.5, 5.0, 0.6)])
+    P.add_variables(orc.VT_EUCLID, [[0.0], [0.0]])
+    P.add_costs(orc.RT_ADAPTIVE_OFFSET, vi, data.reshape(-1, 1))
+    P.set_unfixed(np.array([0, 1, 1], dtype=np.uint8))
+    P.set_callback(1)
+    res, _ = P.optimize(orc.Options(iterator=orc.IT_NEWTON))
+    v = P.variables()
+    assert np.allclose([1 / v[0], 1 / v[1], v[2]], [1.0, 10.0, 0.8], rtol=0.1)          # :57
+    assert v[3] == pytest.approx(-1.0, rel=0.1) and v[4] == pytest.approx(1.0, rel=0.1)  # :58-59
+    assert res.costcomputations == 2 * res.niterations                                   # the callback's own cost evaluation (:21-22)
+    r = np.concatenate([rng.standard_normal(8000), rng.standard_normal(2000) * 10.0])
+    k = orc.em_optimize([1 / 0.5, 1 / 5.0, 0.6], r * r, 200)
+    assert np.allclose([1 / k[0], 1 / k[1], k[2]], [1.0, 10.0, 0.8], rtol=0.03)
+    assert k[0] >= k[1]                                                                  # constructor re-sort (:13-15)
