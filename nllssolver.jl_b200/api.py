@@ -443,12 +443,11 @@ def optimize(problem, options=None, unfixed=None, callback=nullcallback):
     else:
         data = IterData(ctx)
         ctx.lm_begin(copts)
+        data.startcost = data.bestcost = ctx.cost(0)
         conv = 0
         while conv == 0:
             info = ctx.lm_iterate()
             data.iternum += 1
-            if data.iternum == 1:
-                data.startcost = data.bestcost = ctx.cost(0)
             cost_, terminate = callback(info.cost, problem, data, info)
             conv = ctx.lm_advance(cost_, int(terminate))
             data.bestcost = min(data.bestcost, cost_) if cost_ == cost_ else data.bestcost

@@ -290,8 +290,11 @@ __global__ void adapt_solve_kernel(AdaptDev p, const double* __restrict__ H, con
     double a = update_zerotoinf(kern[0], y[p.koff]), bb = update_zerotoinf(kern[1], y[p.koff + 1]);
     const double w = update_zerotoone(kern[2], y[p.koff + 2]);
     if (!(a >= bb)) { const double t = a; a = bb; bb = t; }
-    kern_next[0] = a; kern_next[1] = bb; kern_next[2] = w;
-    for (int m = 0; m < p.nmeans; ++m) means_next[m] = means[m] + y[p.moff[m]];   // src/variable.jl:5
+    // update! leaves the fixed entries of varnext alone (src/linearsystem.jl:206-213: only blockindices != 0), and the outer loop
+    // swaps the two vectors — a fixed variable that a callback changed in varnext (the EM refit of test/adaptivecost.jl:19) is
+    // therefore two iterations stale when it comes back.  Restated as is.
+    if (p.fixdof == nullptr || !p.fixdof[p.koff]) { kern_next[0] = a; kern_next[1] = bb; kern_next[2] = w; }
+    for (int m = 0; m < p.nmeans; ++m) if (p.fixdof == nullptr || !p.fixdof[p.moff[m]]) means_next[m] = means[m] + y[p.moff[m]];   // src/variable.jl:5
 }
 
 // max_i |H_ii| (initlambda, src/iterators.jl:131-137)

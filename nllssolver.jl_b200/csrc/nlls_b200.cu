@@ -1963,6 +1963,10 @@ int nlls_lm_begin(nlls_ctx* ctx, const nlls_options* opts) {
     ctx->costcomputations = ctx->gradientcomputations = ctx->linearsolvers = 0;
     ctx->t_init = ctx->t_cost = ctx->t_grad = ctx->t_solver = 0;
     ctx->have_best = false; ctx->lm_phase = 0;
+    if (ctx->adaptive && ctx->masked) {   // varnext = deepcopy(variables) (src/optimize.jl:80-82): update! never writes its fixed entries
+        CK(cudaMemcpyAsync(ctx->d_A[ctx->nxt], ctx->d_A[ctx->cur], sizeof(double) * ctx->nA * ctx->CS, cudaMemcpyDeviceToDevice, ctx->st));
+        CK(cudaMemcpyAsync(ctx->d_B[ctx->nxt], ctx->d_B[ctx->cur], sizeof(double) * ctx->nB * ctx->BS, cudaMemcpyDeviceToDevice, ctx->st));
+    }
     ctx->t_init += now_ns() - t0;                                // :116
     const uint64_t tg = now_ns();
     double c = 0.0;

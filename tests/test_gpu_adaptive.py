@@ -207,9 +207,23 @@ def test_adaptive_em_callback_with_fixed_kernel(pkg, orc):
     aos = np.zeros(len(data), dtype=pkg.ADAPTIVE_DTYPE)
     aos["data"], aos["varind"] = data, vi
     prob.addcosts(pkg.OffsetResidual, aos)
-    res = pkg.optimize(prob, pkg.NLLSOptions(iterator=pkg.newton), unfixed=[False, True, True], callback=pkg.emcallback)
-    assert res.niterations == res_ref.niterations
-    assert res.costcomputations == res_ref.costcomputations
+    costs = []
+
+    def cb(cost, problem, data, iteratedata):
+        c, t = pkg.emcallback(cost, problem, data, iteratedata)
+        costs.append(c)
+        return c, t
+    res = pkg.optimize(prob, pkg.NLLSOptions(iterator=pkg.newton), unfixed=[False, True, True], callback=cb)
+    # same costs while the iteration is still moving (the 1e-15 termination tests see summation-order noise once the decrease is at
+    # rounding level, so the number of tail iterations may differ — as in test_adaptive_newton_trajectory)
+    ref = [t.cost for t in tr_ref]
+    moving = 1
+    while moving < min(len(costs), len(ref)) and abs(ref[moving] - ref[moving - 1]) > 1e-9 * abs(ref[moving]):
+        moving += 1
+    assert moving >= 5
+    for c, t in zip(costs[:moving], ref[:moving]):
+        assert c == pytest.approx(t, rel=1e-9)
+    assert res.costcomputations == 2 * res.niterations                                  # the callback's own evaluation (:21-22)
     assert res.bestcost == pytest.approx(res_ref.bestcost, rel=TOL_FINAL)
     assert np.allclose(prob.variables[0].params(), [1.0, 10.0, 0.8], rtol=0.1)          # test/adaptivecost.jl:57
     assert prob.variables[1] == pytest.approx(-1.0, rel=0.1) and prob.variables[2] == pytest.approx(1.0, rel=0.1)   # :58-59
