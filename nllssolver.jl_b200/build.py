@@ -5,7 +5,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 SO = os.path.join(HERE, "libnlls_b200.so")
 SRCS = ["csrc/nlls_b200.cu"]
-DEPS = SRCS + ["csrc/kernels.cuh", "csrc/common.cuh", "csrc/residuals.cuh", "csrc/reduced.cuh", "csrc/adaptive.cuh", "../include/nlls_b200.h"]
+DEPS = SRCS + sorted("csrc/" + f for f in os.listdir(os.path.join(HERE, "csrc")) if f.endswith((".cuh", ".hpp"))) + ["../include/nlls_b200.h"]
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
     "-fmad=false",  # residual/assembly kernels are HBM-bound; keeping mul/add unfused tracks the reference's (unfused) Julia arithmetic

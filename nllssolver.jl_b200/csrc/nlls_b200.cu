@@ -1399,7 +1399,9 @@ int nlls_prepare(nlls_ctx* ctx) {
         std::vector<int> nat_of_pos;
         nat_of_pos.reserve((size_t)NT);
         const bool use_nd = w >= 1 && NT >= 8 * w && !getenv("NLLS_B200_NO_ND");
-        if (use_nd) {
+        if (use_nd && getenv("NLLS_B200_ND_BAND")) {
+            // round-1/2a order: separators as wide as the half-bandwidth, leaves of up to 2 w + w columns eliminated one after the other
+            // (Venice shape: w = 2 because ~70 of 10^6 points reach a third tile -> 12 levels)
             const int leaf = std::max(2 * w, 4);
             struct Rec { static void nd(int lo, int hi, int w, int leaf, std::vector<int>& out) {
                 if (hi - lo <= leaf + w) { for (int i = lo; i < hi; ++i) out.push_back(i); return; }
@@ -1408,6 +1410,31 @@ int nlls_prepare(nlls_ctx* ctx) {
                 for (int i = s0; i < s0 + w; ++i) out.push_back(i);
             } };
             Rec::nd(0, NT, w, leaf, nat_of_pos);
+        } else if (use_nd) {
+            // Nested dissection on the ACTUAL tile graph, down to single columns: the separator of a node list is its middle column plus,
+            // for every edge that still joins the two sides, the endpoint nearer to the middle.  The reduced solve is a chain of dependent
+            // levels (~27 us each: diagonal tile, off-diagonal tiles, updates), so what counts is the height of the elimination tree, not
+            // the fill: Venice shape 12 -> 8 levels with 437 instead of 443 tiles (a handful of long tracks no longer widen every
+            // separator, and the leaves are no longer eliminated sequentially).
+            struct Rec { static void nd(const std::vector<int>& nodes, const std::vector<unsigned char>& pat, int NT, std::vector<int>& out) {
+                const int n = (int)nodes.size();
+                if (n <= 2) { for (int v : nodes) out.push_back(v); return; }
+                const int m = n / 2;
+                std::vector<unsigned char> insep((size_t)n, 0);
+                insep[(size_t)m] = 1;
+                for (int a = m - 1; a >= 0; --a)
+                    for (int b = m + 1; b < n && !insep[(size_t)a]; ++b)
+                        if (!insep[(size_t)b] && pat[(size_t)nodes[(size_t)b] * NT + nodes[(size_t)a]]) {   // nodes ascend: (b, a) is in the lower triangle
+                            if (m - a <= b - m) insep[(size_t)a] = 1; else insep[(size_t)b] = 1;
+                        }
+                std::vector<int> left, right, sep;
+                for (int i = 0; i < n; ++i) (insep[(size_t)i] ? sep : (i < m ? left : right)).push_back(nodes[(size_t)i]);
+                nd(left, pat, NT, out); nd(right, pat, NT, out);
+                for (int v : sep) out.push_back(v);
+            } };
+            std::vector<int> all((size_t)NT);
+            for (int i = 0; i < NT; ++i) all[(size_t)i] = i;
+            Rec::nd(all, natpat, NT, nat_of_pos);
         } else {
             for (int i = 0; i < NT; ++i) nat_of_pos.push_back(i);
         }
