@@ -240,8 +240,7 @@ def main():
         faulthandler.dump_traceback_later(float(os.environ["BENCH_FAULT_TIMEOUT"]), exit=True)
 
     def step():
-        info = ctx.lm_iterate()
-        conv = ctx.lm_advance(info.cost, 0)
+        info, conv = ctx.lm_step()   # iterate! + the loop body of optimizeinternal! with the null callback (what nlls_optimize runs)
         trace.append((info.cost, int(info.ntries), conv))
         if verbose:
             _log(f"rank {rank}: LM iteration {len(trace)}: cost {info.cost:.9g} tries {int(info.ntries)} conv {conv}")

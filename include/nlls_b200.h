@@ -157,6 +157,10 @@ int nlls_update(nlls_ctx* ctx);
 int nlls_lm_begin(nlls_ctx* ctx, const nlls_options* opts);
 int nlls_lm_iterate(nlls_ctx* ctx, nlls_iterinfo* info);
 int nlls_lm_advance(nlls_ctx* ctx, double cost, int64_t terminate, int64_t* converged);
+/* nlls_lm_iterate + nlls_lm_advance(info->cost, 0): one outer iteration with the null callback (src/callbacks.jl:20), as nlls_optimize
+ * runs it.  Multi-rank: nlls_lm_advance combines `terminate` over the ranks (maximum; one 8-byte all-reduce per iteration, so that one
+ * rank's callback stops every rank at the same iteration); this call has no flag to exchange and no collective of its own. */
+int nlls_lm_step(nlls_ctx* ctx, nlls_iterinfo* info, int64_t* converged);
 int nlls_lm_end(nlls_ctx* ctx, nlls_result* result);
 /* optimizeinternal! with nullcallback   src/optimize.jl:109-180                                           */
 int nlls_optimize(nlls_ctx* ctx, const nlls_options* opts, nlls_result* result);

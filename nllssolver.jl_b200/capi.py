@@ -21,7 +21,7 @@ TIME_LINEARIZE, TIME_LIN_POINT, TIME_LIN_CAM, TIME_COST, TIME_SCHUR, TIME_SOLVE_
 EXPORTS = [
     "nlls_create", "nlls_destroy", "nlls_last_error", "nlls_version", "nlls_comm_unique_id", "nlls_comm_init",
     "nlls_set_variables", "nlls_set_costs", "nlls_add_costs", "nlls_set_unfixed", "nlls_optimize_singles", "nlls_prepare", "nlls_linearize", "nlls_cost", "nlls_adaptive_em", "nlls_solve", "nlls_update",
-    "nlls_lm_begin", "nlls_lm_iterate", "nlls_lm_advance", "nlls_lm_end", "nlls_optimize", "nlls_get_variables", "nlls_dof",
+    "nlls_lm_begin", "nlls_lm_iterate", "nlls_lm_advance", "nlls_lm_step", "nlls_lm_end", "nlls_optimize", "nlls_get_variables", "nlls_dof",
     "nlls_get_gradient", "nlls_get_step", "nlls_hessian_len", "nlls_get_hessian_blocks", "nlls_hessian_nblocks",
     "nlls_get_hessian_index", "nlls_time_kernels", "nlls_timer_start", "nlls_timer_stop", "nlls_kernel_launches", "nlls_algorithmic_bytes", "nlls_algorithmic_flops",
 ]
@@ -82,6 +82,7 @@ def lib():
         L.nlls_lm_begin.argtypes = [vp, C.POINTER(Options)]
         L.nlls_lm_iterate.argtypes = [vp, C.POINTER(IterInfo)]
         L.nlls_lm_advance.argtypes = [vp, C.c_double, C.c_int64, _ip]
+        L.nlls_lm_step.argtypes = [vp, C.c_void_p, _ip]
         L.nlls_lm_end.argtypes = [vp, C.POINTER(Result)]
         L.nlls_optimize.argtypes = [vp, C.POINTER(Options), C.POINTER(Result)]
         L.nlls_get_variables.argtypes = [vp, C.c_int, C.c_int, _dp, C.c_int64, C.c_int64]
@@ -207,6 +208,12 @@ class Context:
         conv = C.c_int64()
         self._ck(lib().nlls_lm_advance(self.h, cost, terminate, C.byref(conv)))
         return conv.value
+
+    def lm_step(self):
+        """One outer iteration with the null callback: (info, converged)."""
+        info, conv = IterInfo(), C.c_int64()
+        self._ck(lib().nlls_lm_step(self.h, C.byref(info), C.byref(conv)))
+        return info, conv.value
 
     def lm_end(self):
         r = Result()

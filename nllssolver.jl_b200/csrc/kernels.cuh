@@ -1107,12 +1107,13 @@ __global__ void __launch_bounds__(128) cam_update_kernel(DevProblem p, const dou
 }
 
 // gathered[r * 6 + i], r < nranks: the six per-try scalars of every rank -> out[0] = sum of the costs, out[1] = NaN-propagating max
-// of max|x_p|, out[2..4] = sums, all in rank order (lane i owns scalar i); out[5] = rank 0's "maxtime reached" flag
+// of max|x_p|, out[2..4] = sums, all in rank order (lane i owns scalar i); out[5] = OR of the ranks' "maxtime reached" flags
 __global__ void combine_scalars_kernel(const double* __restrict__ gathered, int nranks, double* __restrict__ out) {
     const int i = threadIdx.x;
     if (i >= 6) return;
     double v = gathered[i];
     if (i < 5) for (int r = 1; r < nranks; ++r) v = (i == 1) ? nanmax(v, gathered[r * 6 + i]) : v + gathered[r * 6 + i];
+    else for (int r = 1; r < nranks; ++r) v = (gathered[r * 6 + i] != 0.0) ? 1.0 : v;   // any rank's clock stops every rank
     out[i] = v;
 }
 

@@ -76,7 +76,7 @@ struct VarSet {
 enum Scal {
     SC_COST_LIN = 0, SC_COST_TRY = 1,
     SC_P_MAX = 2, SC_P_SQ = 3, SC_P_XHX = 4, SC_P_GX = 5,      // point-row terms (summed / maxed over ranks)
-    SC_TIMEUP = 6,                                             // multi-rank: rank 0's "maxtime reached" flag, rides on the try's all-gather
+    SC_TIMEUP = 6,                                             // multi-rank: OR of the ranks' "maxtime reached" flags, rides on the try's all-gather
     SC_C_MAX = 7, SC_C_SQ = 8, SC_C_XHX = 9, SC_C_GX = 10,     // camera terms (replicated)
     SC_MAXDIAG = 11, SC_INFO = 12, SC_EXCH = 13 /* .. 16: host values exchanged between ranks */, SC_COUNT = 17,
     SC_TRY_N = 6                                               // scalars per rank in the try's all-gather: SC_COST_TRY .. SC_TIMEUP
@@ -591,9 +591,9 @@ int launch_update(nlls_ctx* ctx) {
 // The rank-local scalars of a try — cost(varnext) and the point rows' step statistics {max|x|, sum x^2, x'Hx, g.x}, five
 // consecutive slots — are combined over the ranks with ONE all-gather and a tiny kernel that adds them in rank order (the same
 // order on every rank, so the replicated accept / reject decision is taken on identical bits).  Round 1 used three all-reduces
-// per try here; at 8 ranks their launch latency was a quarter of the step.  A sixth slot carries rank 0's "maxtime reached" flag:
-// the one termination input that is not replicated (each rank has its own clock) is thereby decided by rank 0 for everyone, with
-// no collective of its own (a rank that left the loop alone would strand the others in the next all-reduce).
+// per try here; at 8 ranks their launch latency was a quarter of the step.  A sixth slot carries the rank's "maxtime reached" flag:
+// the one termination input that is not replicated (each rank has its own clock) is OR-ed over the ranks, so all of them stop at the
+// same iteration, with no collective of its own (a rank that left the loop alone would strand the others in the next all-reduce).
 int exchange_try_scalars(nlls_ctx* ctx) {
     if (ctx->nranks <= 1) return NLLS_OK;
     ctx->h_scal[SC_COUNT] = (ctx->lm_active && now_ns() > ctx->stoptime) ? 1.0 : 0.0;   // pinned staging slot outside the read-back range
@@ -2063,11 +2063,22 @@ int nlls_lm_iterate(nlls_ctx* ctx, nlls_iterinfo* info) {
     return NLLS_OK;
 }
 
-int nlls_lm_advance(nlls_ctx* ctx, double cost, int64_t terminate, int64_t* converged) {
+static int lm_advance(nlls_ctx* ctx, double cost, int64_t terminate, int64_t* converged, bool collective_terminate) {
     if (!ctx || !ctx->lm_active) return NLLS_ERR_INVALID;
     if (ctx->lm_phase != 1) FAIL(NLLS_ERR_INVALID, "nlls_lm_advance without a preceding nlls_lm_iterate");
     ctx->lm_phase = 0;
     CK(cudaSetDevice(ctx->device));
+    if (collective_terminate && ctx->nranks > 1) {
+        // The callback's flag is the caller's: one rank's callback may ask to stop while the others' do not.  A rank that left the loop
+        // alone would strand the others in the next all-reduce, so the flag is combined (maximum) over the ranks: one 8-byte
+        // all-reduce per iteration, only on this callback path (nlls_optimize / nlls_lm_step pass the null callback's 0).
+        ctx->h_scal[SC_COUNT + 1] = (double)terminate;
+        CK(cudaMemcpyAsync(ctx->d_scal + SC_EXCH + 2, ctx->h_scal + SC_COUNT + 1, sizeof(double), cudaMemcpyHostToDevice, ctx->st));
+        TRY(allreduce(ctx, ctx->d_scal + SC_EXCH + 2, 1, ncclMax));
+        CK(cudaMemcpyAsync(ctx->h_scal + SC_COUNT + 1, ctx->d_scal + SC_EXCH + 2, sizeof(double), cudaMemcpyDeviceToHost, ctx->st));
+        CK(cudaStreamSynchronize(ctx->st));
+        terminate = (int64_t)ctx->h_scal[SC_COUNT + 1];
+    }
     const nlls_options& o = ctx->opts;
     const double maxstep = ctx->maxstep;
     // ---- optimizeinternal! after the callback                    src/optimize.jl:130-171
@@ -2096,8 +2107,8 @@ int nlls_lm_advance(nlls_ctx* ctx, double cost, int64_t terminate, int64_t* conv
     conv |= (int64_t)(ctx->fails > o.maxfails) << 7;
     conv |= (int64_t)(ctx->iternum >= o.maxiters) << 8;
     // Multi-rank: every rank must take the same decision (a rank that leaves alone strands the others in the next all-reduce).  All
-    // inputs of the termination word are replicated except the clock — rank 0's reading came with the try's scalars — and the
-    // callback's flag, which the caller must pass identically on every rank (the callback sees replicated data).
+    // inputs of the termination word are replicated except the clock — the OR of the ranks' readings came with the try's scalars —
+    // and the callback's flag (combined over the ranks above).
     const int64_t timeup = (ctx->nranks > 1) ? (ctx->h_scal[SC_TIMEUP] != 0.0) : (now_ns() > ctx->stoptime);
     conv |= timeup << 9;
     conv |= terminate << 16;
@@ -2110,6 +2121,17 @@ int nlls_lm_advance(nlls_ctx* ctx, double cost, int64_t terminate, int64_t* conv
         ctx->gradientcomputations += 1;
     }
     return NLLS_OK;
+}
+
+int nlls_lm_advance(nlls_ctx* ctx, double cost, int64_t terminate, int64_t* converged) { return lm_advance(ctx, cost, terminate, converged, true); }
+
+// One outer iteration with the null callback (src/callbacks.jl:20): nlls_lm_iterate + nlls_lm_advance(info.cost, 0) — what nlls_optimize
+// runs per iteration, for callers that want the per-iteration record without a callback's flag to exchange.
+int nlls_lm_step(nlls_ctx* ctx, nlls_iterinfo* info, int64_t* converged) {
+    nlls_iterinfo local;
+    if (!info) info = &local;
+    TRY(nlls_lm_iterate(ctx, info));
+    return lm_advance(ctx, info->cost, 0, converged, false);
 }
 
 int nlls_lm_end(nlls_ctx* ctx, nlls_result* r) {
@@ -2141,7 +2163,7 @@ int nlls_optimize(nlls_ctx* ctx, const nlls_options* opts, nlls_result* result) 
     while (conv == 0) {
         nlls_iterinfo info;
         TRY(nlls_lm_iterate(ctx, &info));
-        TRY(nlls_lm_advance(ctx, info.cost, 0, &conv));          // nullcallback returns (cost, 0)  src/callbacks.jl:20
+        TRY(lm_advance(ctx, info.cost, 0, &conv, false));        // nullcallback returns (cost, 0)  src/callbacks.jl:20
     }
     return nlls_lm_end(ctx, result);
 }
