@@ -21,13 +21,17 @@ def needs_build():
     return any(os.path.getmtime(os.path.join(HERE, d)) > t for d in DEPS)
 
 
-def build(force=False, verbose=False):
-    if not force and not needs_build():
+def build(force=False, verbose=False, extra_flags=(), out=None):
+    """extra_flags / out: development variants (A/B timing of compile-time switches), e.g.
+    build(force=True, extra_flags=["-DS5_FULL6=0"], out="build/variants/libnlls_bands.so"), loaded with NLLS_B200_LIB=<path>."""
+    if out is None and not force and not needs_build():
         return SO
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", SO] + SRCS + LIBS
+    target = os.path.abspath(out) if out else SO
+    os.makedirs(os.path.dirname(target), exist_ok=True)
+    cmd = [nvcc] + NVCC_FLAGS + list(extra_flags) + (["-Xptxas", "-v"] if verbose else []) + ["-o", target] + SRCS + LIBS
     subprocess.check_call(cmd, cwd=HERE)
-    return SO
+    return target
 
 
 if __name__ == "__main__":

@@ -58,9 +58,10 @@ _ip = C.POINTER(C.c_int64)
 def lib():
     global _LIB
     if _LIB is None:
-        if not os.path.exists(SO):
-            raise RuntimeError(f"{SO} is missing: build it with __graft_entry__.build() (nvcc, sm_100a). There is no CPU fallback.")
-        L = C.CDLL(SO)
+        so = os.environ.get("NLLS_B200_LIB", SO)   # development aid: a variant build of the same library (build.py: extra_flags / out)
+        if not os.path.exists(so):
+            raise RuntimeError(f"{so} is missing: build it with __graft_entry__.build() (nvcc, sm_100a). There is no CPU fallback.")
+        L = C.CDLL(so)
         vp = C.c_void_p
         L.nlls_create.argtypes = [C.POINTER(vp), C.c_int]
         L.nlls_destroy.argtypes = [vp]

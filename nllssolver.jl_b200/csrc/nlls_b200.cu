@@ -445,7 +445,7 @@ int launch_schur(nlls_ctx* ctx, double lambda) {
         static const bool s5dbg = getenv("NLLS_B200_S5DBG") != nullptr;
         long long* d_dbg = nullptr;
         if (s5dbg) { CK(cudaMalloc((void**)&d_dbg, sizeof(long long) * 64 * ctx->n5cta)); CK(cudaMemsetAsync(d_dbg, 0, sizeof(long long) * 64 * ctx->n5cta, ctx->st)); s5.dbg = d_dbg; }
-        schur5_kernel<DC><<<ctx->n5cta, S5_THREADS, Schur5Smem<DC>::bytes, ctx->st>>>(p, s5, ctx->d_S, ctx->d_rhs, ctx->d_Ainv, lambda);
+        schur5_kernel<DC><<<ctx->n5cta, Schur5Cfg<DC>::THREADS, Schur5Smem<DC>::bytes, ctx->st>>>(p, s5, ctx->d_S, ctx->d_rhs, ctx->d_Ainv, lambda);
         ctx->launches++;
         if (s5dbg) {   // development aid: where the warps of the Schur kernel spend their cycles
             std::vector<long long> h((size_t)64 * ctx->n5cta);
@@ -453,11 +453,12 @@ int launch_schur(nlls_ctx* ctx, double lambda) {
             CK(cudaMemcpy(h.data(), d_dbg, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost));
             cudaFree(d_dbg);
             double wsum[16] = {0}, tsum[16] = {0}, tmax = 0, idle = 0;
-            for (int c = 0; c < ctx->n5cta; ++c) for (int w = 0; w < 12; ++w) { wsum[w] += (double)h[((size_t)c * 16 + w) * 4]; tsum[w] += (double)h[((size_t)c * 16 + w) * 4 + 1]; tmax = std::max(tmax, (double)h[((size_t)c * 16 + w) * 4 + 1]); }
-            for (int c = 0; c < ctx->n5cta; ++c) idle += (double)h[((size_t)c * 16 + 11) * 4 + 2];
+            const int pw = Schur5Cfg<DC>::CONS;   // the producer warp
+            for (int c = 0; c < ctx->n5cta; ++c) for (int w = 0; w <= pw; ++w) { wsum[w] += (double)h[((size_t)c * 16 + w) * 4]; tsum[w] += (double)h[((size_t)c * 16 + w) * 4 + 1]; tmax = std::max(tmax, (double)h[((size_t)c * 16 + w) * 4 + 1]); }
+            for (int c = 0; c < ctx->n5cta; ++c) idle += (double)h[((size_t)c * 16 + pw) * 4 + 2];
             fprintf(stderr, "[nlls] schur5 cycles: longest warp %.0f; per consumer warp (mean over CTAs) total / waiting:", tmax);
-            for (int w = 0; w < 11; ++w) fprintf(stderr, " %d: %.0f/%.0f", w, tsum[w] / ctx->n5cta, wsum[w] / ctx->n5cta);
-            fprintf(stderr, "; producer total %.0f point phases %.0f idle polls %.0f\n", tsum[11] / ctx->n5cta, wsum[11] / ctx->n5cta, idle / ctx->n5cta);
+            for (int w = 0; w < pw; ++w) fprintf(stderr, " %d: %.0f/%.0f", w, tsum[w] / ctx->n5cta, wsum[w] / ctx->n5cta);
+            fprintf(stderr, "; producer total %.0f point phases %.0f idle polls %.0f\n", tsum[pw] / ctx->n5cta, wsum[pw] / ctx->n5cta, idle / ctx->n5cta);
             // per CTA totals (consumer warp 0) to see the balance between CTAs
             double cmin = 1e30, cmax = 0;
             for (int c = 0; c < ctx->n5cta; ++c) { const double t = (double)h[((size_t)c * 16) * 4 + 1]; cmin = std::min(cmin, t); cmax = std::max(cmax, t); }
@@ -608,8 +609,9 @@ template <class R>
 int launch_maxdiag(nlls_ctx* ctx) {
     DevProblem p = devproblem(ctx);
     CK(cudaMemsetAsync(ctx->d_scal + SC_MAXDIAG, 0, sizeof(double), ctx->st));
-    const long long tot = ctx->dof;
-    maxdiag_kernel<R::DC><<<(unsigned)((tot + 255) / 256), 256, 0, ctx->st>>>(p, (unsigned long long*)(ctx->d_scal + SC_MAXDIAG)); ctx->launches++;
+    const long long nv = (long long)ctx->nA + ctx->nB;
+    const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>((nv + 255) / 256, 8LL * ctx->nsm));
+    maxdiag_kernel<R::DC><<<grid, 256, 0, ctx->st>>>(p, (unsigned long long*)(ctx->d_scal + SC_MAXDIAG)); ctx->launches++;
     CK(cudaGetLastError());
     TRY(allreduce(ctx, ctx->d_scal + SC_MAXDIAG, 1, ncclMax));
     return NLLS_OK;
@@ -1536,8 +1538,9 @@ int nlls_prepare(nlls_ctx* ctx) {
             Schur5Cost& cm = schur5_cost();
             sscanf(e, "%lf,%lf,%lf,%lf", &cm.dmma, &cm.afrag, &cm.bfrag, &cm.fixed);
         }
-        ctx->s5_ncons = S5_CONSUMERS;
-        if (const char* e = getenv("NLLS_B200_S5_CONS")) ctx->s5_ncons = std::max(1, std::min(atoi(e), S5_CONSUMERS));
+        const int cons_max = (DC == 6) ? Schur5Cfg<6>::CONS : Schur5Cfg<9>::CONS;
+        ctx->s5_ncons = cons_max;
+        if (const char* e = getenv("NLLS_B200_S5_CONS")) ctx->s5_ncons = std::max(1, std::min(atoi(e), cons_max));
         int maxrun = 48;
         if (const char* e = getenv("NLLS_B200_S5_RUN")) maxrun = std::max(1, atoi(e));
         const std::vector<unsigned char>* irr = ctx->nlong ? &ctx->h_irr : nullptr;

@@ -23,7 +23,6 @@
 
 namespace nlls {
 
-constexpr int S5_THREADS = 32 * (S5_CONSUMERS + 1);
 #ifndef S5_NSTAGES
 #define S5_NSTAGES 3
 #endif
@@ -89,32 +88,38 @@ __device__ __forceinline__ double lds_f64_at(uint32_t base) {   // [base + OFF]:
 }
 
 // ---- FLUSH helpers: one accumulator pair (window row R, window columns C0, C0 + 1) / one rhs partial into the reduced system ----
+// Everything that depends only on the super-tile (window base relative to its first camera tile, number of valid cameras, the S tiles
+// the window can touch) is worked out once per FLUSH by the caller; the per-pair routine is ~30 instructions.  (The first version
+// re-derived all of it per pair from the table in global memory — 150 instructions per call; harmless with three bands, a quarter of
+// the kernel once a warp flushes the whole window: 45 pairs per lane.)
+template <int DC> struct S5FlushCtx {
+    int boff;        // window base camera - first camera of camera tile I0
+    int camlim;      // cameras of the window that exist: min(WC, nA - base)
+    long long pe[Schur5Flush<DC>::NPAIR];   // 2 * element offset of S tile (I0 + a, I0 + b) + transposed flag, or -1
+};
 template <int DC>
-__device__ __noinline__ void s5_flush_tile(double v0, double v1, int R, int C0, const long long* __restrict__ ft, int nA, double* __restrict__ S) {
+__device__ __noinline__ void s5_flush_tile(double v0, double v1, int R, int C0, const S5FlushCtx<DC>& fc, double* __restrict__ S) {
     using F = Schur5Flush<DC>;
-    const int base = (int)ft[0], I0 = (int)ft[1];
     const int ca = R / DC, ar = R - ca * DC;
-    const int crow = base + ca;
-    if (ca >= Schur5Cfg<DC>::WC || crow >= nA) return;
-    const int ta = crow / F::TC - I0, r0 = (crow - (I0 + ta) * F::TC) * DC + ar;
+    if (ca >= fc.camlim) return;
+    const int crel = fc.boff + ca, ta = crel / F::TC, r0 = (crel - ta * F::TC) * DC + ar;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
         const int Cc = C0 + h, cb = Cc / DC, cr = Cc - cb * DC;
         const double v = h ? v1 : v0;
         if (v != 0.0 && (cb < ca || (cb == ca && cr <= ar))) {
-            const int ccol = base + cb, tb = ccol / F::TC - I0, c0 = (ccol - (I0 + tb) * F::TC) * DC + cr;
-            const long long pe = ft[2 + F::pair(ta, tb)];
-            atomicAdd(S + (pe >> 1) + ((pe & 1) ? c0 + (long long)ST * r0 : r0 + (long long)ST * c0), -v);
+            const int crelb = fc.boff + cb, tb = crelb / F::TC, c0 = (crelb - tb * F::TC) * DC + cr;
+            const long long pe = fc.pe[F::pair(ta, tb)];
+            atomicAdd(S + (pe >> 1) + ((pe & 1) ? c0 + ST * r0 : r0 + ST * c0), -v);
         }
     }
 }
 template <int DC>
-__device__ __noinline__ void s5_flush_rhs(double rv, int R, const long long* __restrict__ ft, int nA, double* __restrict__ rhs, int kk) {
+__device__ __noinline__ void s5_flush_rhs(double rv, int R, int base, int camlim, double* __restrict__ rhs, int kk) {
     rv += __shfl_xor_sync(0xffffffffu, rv, 1);
     rv += __shfl_xor_sync(0xffffffffu, rv, 2);
     const int ca = R / DC, ar = R - ca * DC;
-    const int crow = (int)ft[0] + ca;
-    if (kk == 0 && ca < Schur5Cfg<DC>::WC && crow < nA && rv != 0.0) atomicAdd(rhs + (size_t)crow * DC + ar, -rv);
+    if (kk == 0 && ca < camlim && rv != 0.0) atomicAdd(rhs + (size_t)(base + ca) * DC + ar, -rv);
 }
 
 // ---- the entries of one consumer warp for one tile ------------------------------------------------------------------------------
@@ -182,14 +187,21 @@ struct Schur5Band {
     // and the instruction cache is what the consumers' straight-line shape code needs.
     static __device__ __forceinline__ void flush(double (&acc)[BR][NTW][2], double (&racc)[BR], const long long* __restrict__ ft, const DevProblem& p,
                                                  double* __restrict__ S, double* __restrict__ rhs, int fr, int kk) {
+        using F = Schur5Flush<DC>;
+        S5FlushCtx<DC> fc;
+        const int base = (int)ft[0];
+        fc.boff = base - (int)ft[1] * F::TC;
+        fc.camlim = min((int)C::WC, p.nA - base);
+#pragma unroll
+        for (int q = 0; q < F::NPAIR; ++q) fc.pe[q] = ft[2 + q];
 #pragma unroll
         for (int r = 0; r < BR; ++r) {
-            s5_flush_rhs<DC>(racc[r], 8 * MT(r) + fr, ft, p.nA, rhs, kk);
+            s5_flush_rhs<DC>(racc[r], 8 * MT(r) + fr, base, fc.camlim, rhs, kk);
             racc[r] = 0.0;
 #pragma unroll
             for (int n = 0; n < NCOL; ++n) {
                 if (n <= MT(r)) {
-                    s5_flush_tile<DC>(acc[r][n][0], acc[r][n][1], 8 * MT(r) + fr, 8 * n + 2 * kk, ft, p.nA, S);
+                    s5_flush_tile<DC>(acc[r][n][0], acc[r][n][1], 8 * MT(r) + fr, 8 * n + 2 * kk, fc, S);
                     acc[r][n][0] = 0.0; acc[r][n][1] = 0.0;
                 }
             }
@@ -201,7 +213,7 @@ struct Schur5Band {
                                                const DevProblem& p, const long long* __restrict__ ftab, double* __restrict__ S, double* __restrict__ rhs, int fr, int kk) {
         constexpr auto RS = std::make_integer_sequence<int, BR>{};
         constexpr auto NS_ = std::make_integer_sequence<int, NCOL>{};
-        static_assert(C::nshapes(BAND) <= 24, "shape switch");
+        static_assert(C::nshapes(BAND) <= 48, "shape switch");
         const uint32_t eend = ep + 8u * cnt;
         uint2 ent = lds_u2(ep);
         while (ep < eend) {
@@ -219,7 +231,9 @@ struct Schur5Band {
             switch (id) {
                 S5_CASE(0) S5_CASE(1) S5_CASE(2) S5_CASE(3) S5_CASE(4) S5_CASE(5) S5_CASE(6) S5_CASE(7) S5_CASE(8) S5_CASE(9)
                 S5_CASE(10) S5_CASE(11) S5_CASE(12) S5_CASE(13) S5_CASE(14) S5_CASE(15) S5_CASE(16) S5_CASE(17) S5_CASE(18) S5_CASE(19)
-                S5_CASE(20) S5_CASE(21) S5_CASE(22) S5_CASE(23)
+                S5_CASE(20) S5_CASE(21) S5_CASE(22) S5_CASE(23) S5_CASE(24) S5_CASE(25) S5_CASE(26) S5_CASE(27) S5_CASE(28) S5_CASE(29)
+                S5_CASE(30) S5_CASE(31) S5_CASE(32) S5_CASE(33) S5_CASE(34) S5_CASE(35) S5_CASE(36) S5_CASE(37) S5_CASE(38) S5_CASE(39)
+                S5_CASE(40) S5_CASE(41) S5_CASE(42) S5_CASE(43) S5_CASE(44) S5_CASE(45) S5_CASE(46) S5_CASE(47)
                 default: ep = eend; break;
             }
 #undef S5_CASE
@@ -228,11 +242,11 @@ struct Schur5Band {
 };
 
 template <int DC>
-__global__ void __launch_bounds__(S5_THREADS, 1) schur5_kernel(DevProblem p, Schur5Dev sp, double* __restrict__ S, double* __restrict__ rhs,
+__global__ void __launch_bounds__(Schur5Cfg<DC>::THREADS, 1) schur5_kernel(DevProblem p, Schur5Dev sp, double* __restrict__ S, double* __restrict__ rhs,
                                                                 double* __restrict__ Ainv_out, double lambda) {
     using C = Schur5Cfg<DC>;
     using SM = Schur5Smem<DC>;
-    constexpr int WB = C::WB, NTW = C::NTW, BR = C::BR, NS = S5_NS;
+    constexpr int WB = C::WB, NTW = C::NTW, BR = C::BR, NS = S5_NS, S5_THREADS = C::THREADS;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int ka = sp.cta_item[blockIdx.x], nitem = sp.cta_item[blockIdx.x + 1] - ka;
@@ -257,7 +271,7 @@ __global__ void __launch_bounds__(S5_THREADS, 1) schur5_kernel(DevProblem p, Sch
     }
     __syncthreads();
 
-    if (warp == S5_CONSUMERS) {
+    if (warp == C::CONS) {
         // =============================================== producer ===============================================
         auto issue = [&](int j) {   // lane 0: bulk loads of item j into stage j % NS
             const int st = j % NS;
@@ -352,7 +366,13 @@ __global__ void __launch_bounds__(S5_THREADS, 1) schur5_kernel(DevProblem p, Sch
             const uint32_t ptb = smem_u32(s_pt(st)) + 32u * (unsigned)kk;
             const uint32_t ep = blobb + 4u * eoff + 8u * (hdr >> 16);
             const unsigned band = (lds_u32(ep + 4u) >> 16) & 15u;   // a warp keeps its band for the whole super-tile, hence for the tile
-            if constexpr (C::NBANDS == 3) {
+            if constexpr (C::NBANDS == 1) {
+                (void)band;
+                Schur5Band<DC, 0>::run(acc, racc, ep, cnt, rowb, ptb, p, sp.ftab, S, rhs, fr, kk);
+            } else if constexpr (C::NBANDS == 2) {
+                if (band == 0) Schur5Band<DC, 0>::run(acc, racc, ep, cnt, rowb, ptb, p, sp.ftab, S, rhs, fr, kk);
+                else Schur5Band<DC, 1>::run(acc, racc, ep, cnt, rowb, ptb, p, sp.ftab, S, rhs, fr, kk);
+            } else if constexpr (C::NBANDS == 3) {
                 switch (band) {
                     case 0: Schur5Band<DC, 0>::run(acc, racc, ep, cnt, rowb, ptb, p, sp.ftab, S, rhs, fr, kk); break;
                     case 1: Schur5Band<DC, 1>::run(acc, racc, ep, cnt, rowb, ptb, p, sp.ftab, S, rhs, fr, kk); break;

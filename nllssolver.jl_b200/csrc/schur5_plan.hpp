@@ -23,7 +23,13 @@
 
 namespace nlls {
 
-constexpr int S5_CONSUMERS = 11;       // consumer warps per CTA (+ 1 producer warp = 12 warps: registers are allocated per 4 warps)
+constexpr int S5_CONSUMERS = 11;       // most consumer warps a CTA can have (+ 1 producer warp = 12 warps: registers are allocated per 4 warps); Schur5Cfg<DC>::CONS are used
+#ifndef S5_FULL6
+#define S5_FULL6 1      // DC <= 6: one band that owns the whole window (a warp takes ALL row tiles of a point), 7 consumer warps with 255 registers
+#endif
+#ifndef S5_BR9
+#define S5_BR9 6        // DC = 9: row tiles per band (2: six interleaved bands, 11 consumer warps; 6: two interleaved bands, 7 consumer warps with 255 registers)
+#endif
 constexpr int S5_HDR = 16;             // header words of a tile blob: [w] (first entry << 16) | count of consumer warp w, [14] word offset of the entries, [15] span misalignment
 constexpr unsigned S5_FLUSH = 1u << 20;
 #ifndef S5_OBS6
@@ -45,13 +51,23 @@ static_assert(S5_CONSUMERS <= 14, "header layout");
 #endif
 template <int DC> struct Schur5Cfg {
     static constexpr int NTW = (DC <= 6) ? 9 : 12;          // row tiles of the window
-    static constexpr int BR = (DC <= 6) ? 3 : 2;            // row tiles per band
+    // Whole-window mode (DC <= 6, round 2c).  With three bands a point became three entries (one per band, each with its own decode,
+    // A_p^-1 loads and B fragments): ncu counted 20 issued instructions per DMMA and the 2.75 warps a scheduler had could issue one
+    // dependent instruction every ~5.5 cycles each — the DMMA pipe was 36 % busy.  One band = one entry per point: the B fragments are
+    // loaded once, the row tiles' DMMAs interleave with the next rows' A fragments, ~7 instructions per DMMA.  The price is the whole
+    // lower triangle of the window in registers (45 tiles = 180 registers), hence 7 consumer warps + 1 producer at 255 registers.
+    static constexpr bool FULL = (DC <= 6) && (S5_FULL6 != 0);
+    static constexpr int BR = FULL ? NTW : ((DC <= 6) ? 3 : S5_BR9);   // row tiles per band
     static constexpr int NBANDS = NTW / BR;
+    static constexpr bool WIDE = FULL || BR * NTW > 27;     // more accumulators than 12 warps' 168 registers hold: 8 warps with 255 registers
+    static constexpr int CONS = WIDE ? 7 : S5_CONSUMERS;    // consumer warps of a CTA
+    static constexpr int THREADS = 32 * (CONS + 1);
     // r-th row tile of a band.  DC = 9: interleaved (band b owns b, b + NBANDS, ...).  DC = 6: {0,1,5} {2,3,6} {4,7,8} — the window's
     // middle rows carry most of the work (points start a few cameras above the base and span ~5 tiles); with 11 consumer warps the
     // bands get 4 / 4 / 3 warps, and this split brings the three shares close to 4 : 4 : 3 on the BAL-shaped problems (the plainly
     // interleaved split left the three-warp band 19 % over the mean on the Venice shape, this one 7 %).
     S5_CE static constexpr int row_tile(int band, int r) {
+        if (FULL) return r;
         if (DC <= 6) { return band == 0 ? (r == 0 ? 0 : (r == 1 ? 1 : 5)) : (band == 1 ? (r == 0 ? 2 : (r == 1 ? 3 : 6)) : (r == 0 ? 4 : (r == 1 ? 7 : 8))); }
         return band + NBANDS * r;
     }
@@ -86,7 +102,7 @@ template <int DC> struct Schur5Cfg {
     static constexpr int PTS = OBS / 2;
     static constexpr int WB = 3 * DC;
     static constexpr int ENT_CAP = PTS * NBANDS + S5_CONSUMERS + 5;   // entries per tile
-    static_assert(NTW % BR == 0 && BR * NTW <= 27, "accumulators: BR x NTW tiles of two doubles per lane");
+    static_assert(NTW % BR == 0, "bands of equal height");
 };
 
 struct Schur5Item {       // one point tile of a CTA's range (32 bytes)
@@ -164,7 +180,7 @@ inline void schur5_tile_range(int DC, int delta, int k, int& t_lo, int& t_hi) {
 // hB: offset of the point rows in H (DC*DC*nA);  ncta: CTAs (one per SM);  maxrun: tiles per super-tile at most.
 // irr (optional): points that must stay outside every tile (they are appended to the outliers by the caller).
 template <int DC>
-Schur5Plan schur5_build_plan(const std::vector<int>& obs_start, const std::vector<int>& obs_cam, long long nA, int ncta, int maxrun = 48, int ncons = S5_CONSUMERS,
+Schur5Plan schur5_build_plan(const std::vector<int>& obs_start, const std::vector<int>& obs_cam, long long nA, int ncta, int maxrun = 48, int ncons = Schur5Cfg<DC>::CONS,
                              const std::vector<unsigned char>* irr = nullptr) {
     using C = Schur5Cfg<DC>;
     Schur5Plan P;
@@ -191,7 +207,7 @@ Schur5Plan schur5_build_plan(const std::vector<int>& obs_start, const std::vecto
     std::vector<int> pstart((size_t)nB), pk((size_t)nB);
     std::vector<unsigned char> elig((size_t)nB);
     const int kmax_fit = C::WC;
-    ncons = std::max(C::NBANDS, std::min(ncons, S5_CONSUMERS));
+    ncons = std::max(C::NBANDS, std::min(ncons, C::CONS));
     double contrib_all = 0.0, contrib_out = 0.0;
     for (long long p = 0; p < nB; ++p) {
         const int b = obs_start[(size_t)p], e = obs_start[(size_t)p + 1], k = e - b;
@@ -280,7 +296,8 @@ Schur5Plan schur5_build_plan(const std::vector<int>& obs_start, const std::vecto
                 std::stable_sort(border, border + C::NBANDS, [&](int x, int y) { return work[x] > work[y]; });
                 // warp w runs on SM sub-partition w % 4: the warps of one band share a sub-partition where they can (they run the same
                 // straight-line shape code: the instruction cache was the second largest stall with the bands mixed)
-                static const int worder[S5_CONSUMERS] = {0, 4, 8, 3, 1, 5, 9, 7, 2, 6, 10};
+                static const int worder[11] = {0, 4, 8, 3, 1, 5, 9, 7, 2, 6, 10};
+                static_assert(S5_CONSUMERS == 11, "warp order table");
                 int next = 0;
                 for (int i = 0; i < C::NBANDS; ++i) for (int q = 0; q < nw[border[i]]; ++q) { while (worder[next] >= ncons) ++next; bw[border[i]].push_back(worder[next++]); }
             }
@@ -358,7 +375,7 @@ Schur5Plan schur5_build_plan(const std::vector<int>& obs_start, const std::vecto
             }
             double mx = 0, sum = 0; int nact = 0;
             double capsum = 0;
-            for (int w = 0; w < S5_CONSUMERS; ++w) { mx = std::max(mx, load[w] / capw(w)); sum += load[w]; capsum += capw(w); nact += 1; }
+            for (int w = 0; w < ncons; ++w) { mx = std::max(mx, load[w] / capw(w)); sum += load[w]; capsum += capw(w); nact += 1; }
             imb_num += mx * capsum; imb_den += sum;
             t = u;
         }
