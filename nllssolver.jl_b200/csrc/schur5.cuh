@@ -23,6 +23,9 @@
 
 namespace nlls {
 
+#ifndef S5_FLUSH_TABLE
+#define S5_FLUSH_TABLE 1   // narrow-band configurations (12 warps) flush with the table-walk routines, the wide ones with a per-FLUSH context
+#endif
 #ifndef S5_NSTAGES
 #define S5_NSTAGES 3
 #endif
@@ -36,7 +39,7 @@ template <int DC> struct Schur5Smem {
     static constexpr int ROWS = ROW + 4;                            // + slack of an 8-byte-misaligned span (stays even)
     static constexpr int PTAB = 16 * C::PTS;                        // per point 4 x [Ainv[kk][0..2], g[kk]]; kk = 3 stays zero
     static constexpr int GST = (3 * C::PTS + 4) & ~1;               // staged g_p
-    static constexpr int BLOB = (S5_HDR + C::PTS / 2 + 2 + 2 * C::ENT_CAP + 3) & ~3;   // u32 words
+    static constexpr int BLOB = (S5_HDR + C::PTS / 2 + 2 + C::OBS / 4 + 2 + 2 * C::ENT_CAP + 3) & ~3;   // u32 words
     static constexpr size_t stage_bytes = (size_t)(ROWS + PTAB + GST) * sizeof(double) + (size_t)BLOB * sizeof(unsigned);
     static constexpr size_t bytes = 2 * S5_PAD + S5_NS * stage_bytes + 3 * S5_NS * sizeof(uint64_t) + 16;
     static_assert(stage_bytes % 16 == 0, "stages must stay 16-byte aligned");
@@ -80,6 +83,7 @@ __device__ __forceinline__ uint2 lds_u2(uint32_t addr) {
     asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
     return v;
 }
+__device__ __forceinline__ void sts_f64(uint32_t addr, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory"); }
 template <int OFF>
 __device__ __forceinline__ double lds_f64_at(uint32_t base) {   // [base + OFF]: the offset goes into the instruction's immediate field
     double v;
@@ -122,6 +126,35 @@ __device__ __noinline__ void s5_flush_rhs(double rv, int R, int base, int camlim
     if (kk == 0 && ca < camlim && rv != 0.0) atomicAdd(rhs + (size_t)(base + ca) * DC + ar, -rv);
 }
 
+// table-walk variants (S5_FLUSH_TABLE): everything re-derived per pair from the FLUSH table in global memory
+template <int DC>
+__device__ __noinline__ void s5_flush_tile_t(double v0, double v1, int R, int C0, const long long* __restrict__ ft, int nA, double* __restrict__ S) {
+    using F = Schur5Flush<DC>;
+    const int base = (int)ft[0], I0 = (int)ft[1];
+    const int ca = R / DC, ar = R - ca * DC;
+    const int crow = base + ca;
+    if (ca >= Schur5Cfg<DC>::WC || crow >= nA) return;
+    const int ta = crow / F::TC - I0, r0 = (crow - (I0 + ta) * F::TC) * DC + ar;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int Cc = C0 + h, cb = Cc / DC, cr = Cc - cb * DC;
+        const double v = h ? v1 : v0;
+        if (v != 0.0 && (cb < ca || (cb == ca && cr <= ar))) {
+            const int ccol = base + cb, tb = ccol / F::TC - I0, c0 = (ccol - (I0 + tb) * F::TC) * DC + cr;
+            const long long pe = ft[2 + F::pair(ta, tb)];
+            atomicAdd(S + (pe >> 1) + ((pe & 1) ? c0 + (long long)ST * r0 : r0 + (long long)ST * c0), -v);
+        }
+    }
+}
+template <int DC>
+__device__ __noinline__ void s5_flush_rhs_t(double rv, int R, const long long* __restrict__ ft, int nA, double* __restrict__ rhs, int kk) {
+    rv += __shfl_xor_sync(0xffffffffu, rv, 1);
+    rv += __shfl_xor_sync(0xffffffffu, rv, 2);
+    const int ca = R / DC, ar = R - ca * DC;
+    const int crow = (int)ft[0] + ca;
+    if (kk == 0 && ca < Schur5Cfg<DC>::WC && crow < nA && rv != 0.0) atomicAdd(rhs + (size_t)crow * DC + ar, -rv);
+}
+
 // ---- the entries of one consumer warp for one tile ------------------------------------------------------------------------------
 // BAND (and with it every accumulator index) is a compile-time constant, and so is the SHAPE of an entry: the first window tile of
 // the point (TLO) and how far into the band it reaches (E = min(t_hi, M0 + BR - 1) - M0).  One indirect branch per entry picks the
@@ -137,6 +170,16 @@ struct Schur5Band {
     // shape key = t_lo * (BR + 1) + number of active rows; for a static TLO the active rows are R0 .. R0 + NACT - 1
     __host__ __device__ static constexpr int R0(int tlo) { return C::r0(BAND, tlo); }
 
+    // The staged W_p has been replaced in place by Z_p = L_p' W_p (producer), A_p^-1 = L_p D_p L_p':  S_p = Z_p' D_p Z_p.  The A fragment
+    // of row tile r is then d[kk] times the B fragment of column tile r — ONE load per tile of the point serves both (round 2b formed
+    // Y = A_p^-1 W on the fly: three loads, three FP64 operations and a mask per row tile and lane, the instructions ncu showed throttled
+    // by the other warps' DMMAs on the shared FP64 pipe).  Columns run from the point's last tile down, so a row's A fragment exists
+    // exactly when the first column that needs it comes up and only one B fragment is live at a time.
+    __host__ __device__ static constexpr int row_of_tile(int mt) {   // index of window tile mt among the band's rows, or -1
+        for (int r = 0; r < BR; ++r) if (MT(r) == mt) return r;
+        return -1;
+    }
+    // ---- classic formulation (ZT == false): Y = A_p^-1 W formed on the fly from three loads per row tile
     template <int TLO, int NACT, int R>
     static __device__ __forceinline__ void row(double (&a)[BR], double (&racc)[BR], uint32_t wb, int u, int lim, const double2& pa, const double2& pb) {
         if constexpr (R >= R0(TLO) && R < R0(TLO) + NACT) {   // A fragment: Y[kk][window row 8 MT + fr] = sum_m Ainv[kk][m] W[m][row]
@@ -160,15 +203,36 @@ struct Schur5Band {
                 if (r >= R0(TLO) && r < R0(TLO) + NACT && MT(r) >= N) dmma884(acc[r][N][0], acc[r][N][1], a[r], b);
         }
     }
+    // ---- Z formulation
+    template <int TLO, int NACT, int N>
+    static __device__ __forceinline__ void colz(double (&acc)[BR][NTW][2], double (&a)[BR], double (&racc)[BR], uint32_t wbb, int u, int lim, const double2& pa) {
+        constexpr int last = MT(R0(TLO) + NACT - 1);           // the last active row tile: columns run up to it
+        if constexpr (N >= TLO && N <= last) {                 // B fragment: Z[kk][window column 8 N + fr]
+            double b = lds_f64_at<192 * N>(wbb);
+            if constexpr (N == TLO || N == last) b = ((unsigned)(u + 8 * N) < (unsigned)lim) ? b : 0.0;   // only the point's first / last tile can be partial
+            constexpr int rn = row_of_tile(N);
+            if constexpr (rn >= 0) {                           // N is one of the band's (active) rows: its A fragment d[kk] Z[kk][row]
+                a[rn] = pa.x * b;
+                racc[rn] = fma(a[rn], pa.y, racc[rn]);         // rhs: (D Z)' (L' g)
+            }
+#pragma unroll
+            for (int r = 0; r < BR; ++r)
+                if (r >= R0(TLO) && r < R0(TLO) + NACT && MT(r) >= N) dmma884(acc[r][N][0], acc[r][N][1], a[r], b);
+        }
+    }
     template <int ID, int... Rs, int... Ns>
     static __device__ __forceinline__ void shape(double (&acc)[BR][NTW][2], double (&racc)[BR], uint32_t wb, int kk, int u, int lim, const double2& pa,
                                                  const double2& pb, std::integer_sequence<int, Rs...>, std::integer_sequence<int, Ns...>) {
         if constexpr (ID < C::nshapes(BAND)) {
             constexpr int TLO = C::shape_tlo(BAND, ID), NACT = C::shape_nact(BAND, ID);
             double a[BR];
-            (row<TLO, NACT, Rs>(a, racc, wb, u, lim, pa, pb), ...);
             const uint32_t wbb = wb + 8u * (unsigned)kk;
-            (col<TLO, NACT, Ns>(acc, a, wbb, u, lim), ...);
+            if constexpr (C::ZT) {
+                (colz<TLO, NACT, NCOL - 1 - Ns>(acc, a, racc, wbb, u, lim, pa), ...);
+            } else {
+                (row<TLO, NACT, Rs>(a, racc, wb, u, lim, pa, pb), ...);
+                (col<TLO, NACT, Ns>(acc, a, wbb, u, lim), ...);
+            }
         }
     }
     // entry words (host: schur5_plan.hpp): x = wofs | DC k << 16 | DC delta << 24,  y = local point | shape << 8 | band << 16
@@ -179,7 +243,9 @@ struct Schur5Band {
         const int u = fr - (int)(ent.x >> 24);
         const uint32_t wb = rowb + 8u * (ent.x & 0xffffu) + 24u * (unsigned)fr;   // W[0][window row fr]   (rowb carries - 8 BIAS)
         const uint32_t pq = ptb + 128u * (ent.y & 255u);
-        const double2 pa = lds_f64x2(pq), pb = lds_f64x2(pq + 16u);            // Ainv[kk][0..2], g[kk]
+        const double2 pa = lds_f64x2(pq);                                      // ZT: d[kk], (L' g)[kk]; classic: Ainv[kk][0..1]   (kk = 3: zeros)
+        double2 pb = make_double2(0.0, 0.0);
+        if constexpr (!C::ZT) pb = lds_f64x2(pq + 16u);                        // classic: Ainv[kk][2], g[kk]
         shape<ID>(acc, racc, wb, kk, u, lim, pa, pb, rs, ns);
     }
     // end of a super-tile: add this warp's tiles to S (lower triangle of the window, cameras < nA) and clear them.  The per-tile work is
@@ -187,6 +253,23 @@ struct Schur5Band {
     // and the instruction cache is what the consumers' straight-line shape code needs.
     static __device__ __forceinline__ void flush(double (&acc)[BR][NTW][2], double (&racc)[BR], const long long* __restrict__ ft, const DevProblem& p,
                                                  double* __restrict__ S, double* __restrict__ rhs, int fr, int kk) {
+#if S5_FLUSH_TABLE
+        if constexpr (!C::WIDE) {
+#pragma unroll
+            for (int r = 0; r < BR; ++r) {
+                s5_flush_rhs_t<DC>(racc[r], 8 * MT(r) + fr, ft, p.nA, rhs, kk);
+                racc[r] = 0.0;
+#pragma unroll
+                for (int n = 0; n < NCOL; ++n) {
+                    if (n <= MT(r)) {
+                        s5_flush_tile_t<DC>(acc[r][n][0], acc[r][n][1], 8 * MT(r) + fr, 8 * n + 2 * kk, ft, p.nA, S);
+                        acc[r][n][0] = 0.0; acc[r][n][1] = 0.0;
+                    }
+                }
+            }
+            return;
+        }
+#endif
         using F = Schur5Flush<DC>;
         S5FlushCtx<DC> fc;
         const int base = (int)ft[0];
@@ -228,13 +311,22 @@ struct Schur5Band {
             entry<K>(acc, racc, cur, rowb, ptb, fr, kk, RS, NS_);                    \
         } while (ep < eend && ((ent.y >> 8) & 0x10ffu) == K);                        \
         break;
-            switch (id) {
-                S5_CASE(0) S5_CASE(1) S5_CASE(2) S5_CASE(3) S5_CASE(4) S5_CASE(5) S5_CASE(6) S5_CASE(7) S5_CASE(8) S5_CASE(9)
-                S5_CASE(10) S5_CASE(11) S5_CASE(12) S5_CASE(13) S5_CASE(14) S5_CASE(15) S5_CASE(16) S5_CASE(17) S5_CASE(18) S5_CASE(19)
-                S5_CASE(20) S5_CASE(21) S5_CASE(22) S5_CASE(23) S5_CASE(24) S5_CASE(25) S5_CASE(26) S5_CASE(27) S5_CASE(28) S5_CASE(29)
-                S5_CASE(30) S5_CASE(31) S5_CASE(32) S5_CASE(33) S5_CASE(34) S5_CASE(35) S5_CASE(36) S5_CASE(37) S5_CASE(38) S5_CASE(39)
-                S5_CASE(40) S5_CASE(41) S5_CASE(42) S5_CASE(43) S5_CASE(44) S5_CASE(45) S5_CASE(46) S5_CASE(47)
-                default: ep = eend; break;
+            if constexpr (C::nshapes(BAND) <= 24) {   // (the unused cases of the larger switch are not free: deeper compare tree, larger code)
+                switch (id) {
+                    S5_CASE(0) S5_CASE(1) S5_CASE(2) S5_CASE(3) S5_CASE(4) S5_CASE(5) S5_CASE(6) S5_CASE(7) S5_CASE(8) S5_CASE(9)
+                    S5_CASE(10) S5_CASE(11) S5_CASE(12) S5_CASE(13) S5_CASE(14) S5_CASE(15) S5_CASE(16) S5_CASE(17) S5_CASE(18) S5_CASE(19)
+                    S5_CASE(20) S5_CASE(21) S5_CASE(22) S5_CASE(23)
+                    default: ep = eend; break;
+                }
+            } else {
+                switch (id) {
+                    S5_CASE(0) S5_CASE(1) S5_CASE(2) S5_CASE(3) S5_CASE(4) S5_CASE(5) S5_CASE(6) S5_CASE(7) S5_CASE(8) S5_CASE(9)
+                    S5_CASE(10) S5_CASE(11) S5_CASE(12) S5_CASE(13) S5_CASE(14) S5_CASE(15) S5_CASE(16) S5_CASE(17) S5_CASE(18) S5_CASE(19)
+                    S5_CASE(20) S5_CASE(21) S5_CASE(22) S5_CASE(23) S5_CASE(24) S5_CASE(25) S5_CASE(26) S5_CASE(27) S5_CASE(28) S5_CASE(29)
+                    S5_CASE(30) S5_CASE(31) S5_CASE(32) S5_CASE(33) S5_CASE(34) S5_CASE(35) S5_CASE(36) S5_CASE(37) S5_CASE(38) S5_CASE(39)
+                    S5_CASE(40) S5_CASE(41) S5_CASE(42) S5_CASE(43) S5_CASE(44) S5_CASE(45) S5_CASE(46) S5_CASE(47)
+                    default: ep = eend; break;
+                }
             }
 #undef S5_CASE
         }
@@ -319,15 +411,48 @@ __global__ void __launch_bounds__(Schur5Cfg<DC>::THREADS, 1) schur5_kernel(DevPr
                 const double a[6] = {V[0] + lambda, V[1], V[2], V[4] + lambda, V[5], V[8] + lambda};
                 double inv[6];
                 inv_sym3(a, inv);
-                double* o = pt + 16 * q;
-                o[0] = inv[0]; o[1] = inv[1]; o[2] = inv[2]; o[3] = sg[3 * q];
-                o[4] = inv[1]; o[5] = inv[3]; o[6] = inv[4]; o[7] = sg[3 * q + 1];
-                o[8] = inv[2]; o[9] = inv[4]; o[10] = inv[5]; o[11] = sg[3 * q + 2];
                 double* ao = Ainv_out + (size_t)6 * (it.pt0 + q);
 #pragma unroll
                 for (int e = 0; e < 6; ++e) ao[e] = inv[e];
+                if constexpr (!C::ZT) {      // classic point table: [Ainv row kk | g_kk]
+                    double* o = pt + 16 * q;
+                    o[0] = inv[0]; o[1] = inv[1]; o[2] = inv[2]; o[3] = sg[3 * q];
+                    o[4] = inv[1]; o[5] = inv[3]; o[6] = inv[4]; o[7] = sg[3 * q + 1];
+                    o[8] = inv[2]; o[9] = inv[4]; o[10] = inv[5]; o[11] = sg[3 * q + 2];
+                    continue;
+                }
+                // A_p^-1 = L D L' (unit lower L, no pivoting: indefinite point blocks keep their signs in D)
+                const double d0 = inv[0], l10 = inv[1] / d0, l20 = inv[2] / d0;
+                const double d1 = fma(-l10, inv[1], inv[3]);
+                const double l21 = fma(-l20, inv[1], inv[4]) / d1;
+                const double d2 = fma(-l21 * l21, d1, fma(-l20, inv[2], inv[5]));
+                const double g0 = sg[3 * q], g1 = sg[3 * q + 1], g2 = sg[3 * q + 2];
+                double* o = pt + 16 * q;     // per inner index kk: [d_kk, (L' g)_kk, and the factors the W -> Z pass needs]
+                o[0] = d0; o[1] = fma(l20, g2, fma(l10, g1, g0)); o[2] = l10; o[3] = l20;
+                o[4] = d1; o[5] = fma(l21, g2, g1); o[6] = l21;
+                o[8] = d2; o[9] = g2;
             }
             __syncwarp();
+            __syncwarp();
+            if constexpr (C::ZT) {   // W -> Z = L' W in place, one observation (3 x DC block, column-major) per lane:  z0 = w0 + l10 w1 + l20 w2,  z1 = w1 + l21 w2,  z2 = w2
+                // (tried and measured slower: the owning consumer warp transforming its own points one entry ahead — whole-window mode —
+                //  and the tile's observations dealt to the consumer warps one tile ahead behind an mbarrier)
+                const unsigned char* opt = reinterpret_cast<const unsigned char*>(s_blob(st) + s_blob(st)[13]);
+                double* wrow = s_row(st) + mis;
+                for (int j = lane; j < it.nob; j += 32) {
+                    const int q = opt[j];
+                    const double* o = pt + 16 * q;
+                    const double l10 = o[2], l20 = o[3], l21 = o[6];
+                    double* w = wrow + WB * j + 9 * q;
+#pragma unroll
+                    for (int c = 0; c < DC; ++c) {
+                        const double w0 = w[3 * c], w1 = w[3 * c + 1], w2 = w[3 * c + 2];
+                        w[3 * c] = fma(l20, w2, fma(l10, w1, w0));
+                        w[3 * c + 1] = fma(l21, w2, w1);
+                    }
+                }
+                __syncwarp();
+            }
             if (lane == 0) mbar_arrive(&bar_ready[st]);
             ++jp;
             t_pp += clock64() - t_p0;

@@ -25,12 +25,20 @@ namespace nlls {
 
 constexpr int S5_CONSUMERS = 11;       // most consumer warps a CTA can have (+ 1 producer warp = 12 warps: registers are allocated per 4 warps); Schur5Cfg<DC>::CONS are used
 #ifndef S5_FULL6
-#define S5_FULL6 1      // DC <= 6: one band that owns the whole window (a warp takes ALL row tiles of a point), 7 consumer warps with 255 registers
+#define S5_FULL6 0      // DC <= 6: 1 = one band that owns the whole window (a warp takes ALL row tiles of a point: one entry per point, 184 M instead of 231 M
+                        // instructions), 7 consumer warps with 254 registers; 0 = three bands, 11 consumer warps.  Venice shape, same box: 0.61 vs 0.57 ms —
+                        // 1.75 warps per scheduler hide less of the DMMA / FP64 latencies than 2.75
+#endif
+#ifndef S5_ZT6
+#define S5_ZT6 0        // DC <= 6: 1 = consumers work on Z = L' W (A_p^-1 = L D L'; the producer warp transforms the staged W in place), 0 = Y = A_p^-1 W
+                        // formed on the fly.  Venice shape, same box: Z made the 11 consumer warps 13 % faster (778 K instead of 900 K busy cycles) but
+                        // the producer's pass (3 700 cycles per tile) became the critical path: 0.65 vs 0.57 ms.  For dc = 9 (7 consumer warps, two per
+                        // point) Z wins: 1.75 -> 1.27 ms
 #endif
 #ifndef S5_BR9
 #define S5_BR9 6        // DC = 9: row tiles per band (2: six interleaved bands, 11 consumer warps; 6: two interleaved bands, 7 consumer warps with 255 registers)
 #endif
-constexpr int S5_HDR = 16;             // header words of a tile blob: [w] (first entry << 16) | count of consumer warp w, [14] word offset of the entries, [15] span misalignment
+constexpr int S5_HDR = 16;             // header words of a tile blob: [w] (first entry << 16) | count of consumer warp w, [13] word offset of the observation -> point bytes, [14] word offset of the entries, [15] span misalignment
 constexpr unsigned S5_FLUSH = 1u << 20;
 #ifndef S5_OBS6
 #define S5_OBS6 232
@@ -42,7 +50,7 @@ constexpr unsigned S5_FLUSH = 1u << 20;
 // (3 FMAs + the rhs FMA + masks), B fragments, and a shape-independent part
 struct Schur5Cost { double dmma = 17.0, afrag = 10.0, bfrag = 4.0, fixed = 40.0; };
 inline Schur5Cost& schur5_cost() { static Schur5Cost c; return c; }
-static_assert(S5_CONSUMERS <= 14, "header layout");
+static_assert(S5_CONSUMERS <= 13, "header layout");
 
 #ifdef __CUDACC__
 #define S5_CE __host__ __device__
@@ -61,6 +69,7 @@ template <int DC> struct Schur5Cfg {
     static constexpr int NBANDS = NTW / BR;
     static constexpr bool WIDE = FULL || BR * NTW > 27;     // more accumulators than 12 warps' 168 registers hold: 8 warps with 255 registers
     static constexpr int CONS = WIDE ? 7 : S5_CONSUMERS;    // consumer warps of a CTA
+    static constexpr bool ZT = (DC > 6) || (S5_ZT6 != 0);   // Z = L' W formulation (schur5.cuh)
     static constexpr int THREADS = 32 * (CONS + 1);
     // r-th row tile of a band.  DC = 9: interleaved (band b owns b, b + NBANDS, ...).  DC = 6: {0,1,5} {2,3,6} {4,7,8} — the window's
     // middle rows carry most of the work (points start a few cameras above the base and span ~5 tiles); with 11 consumer warps the
@@ -116,7 +125,7 @@ struct Schur5Item {       // one point tile of a CTA's range (32 bytes)
 struct Schur5Plan {
     std::vector<int> cta_item;            // [ncta + 1]
     std::vector<Schur5Item> items;
-    std::vector<unsigned> blob;           // per tile: [S5_HDR header][point table: obs_end (u16) per point, padded to an even word count][entries: 2 words each]
+    std::vector<unsigned> blob;           // per tile: [S5_HDR header][point table: obs_end (u16) per point, padded to an even word count][local point (u8) per observation, padded to an even word count][entries: 2 words each]
     std::vector<int> outliers;            // points left to the fallback kernel
     std::vector<int> super_base;          // window base camera of every super-tile (a FLUSH entry carries the super-tile's index)
     // statistics
@@ -358,6 +367,17 @@ Schur5Plan schur5_build_plan(const std::vector<int>& obs_start, const std::vecto
                     const unsigned lo = (unsigned)(obs_start[(size_t)p + 1] - ob0);
                     const unsigned hi2 = (p + 1 < pt1) ? (unsigned)(obs_start[(size_t)p + 2] - ob0) : 0u;
                     P.blob.push_back(lo | (hi2 << 16));
+                }
+                if ((P.blob.size() - h) & 1) P.blob.push_back(0u);
+                P.blob[h + 13] = (unsigned)(P.blob.size() - h);   // word offset of the observation -> local point bytes (the producer's W -> Z pass goes by observation)
+                {
+                    unsigned word = 0; int nb = 0;
+                    for (int p = pt0; p < pt1; ++p)
+                        for (int j = obs_start[(size_t)p]; j < obs_start[(size_t)p + 1]; ++j) {
+                            word |= (unsigned)(p - pt0) << (8 * nb);
+                            if (++nb == 4) { P.blob.push_back(word); word = 0; nb = 0; }
+                        }
+                    if (nb) P.blob.push_back(word);
                 }
                 if ((P.blob.size() - h) & 1) P.blob.push_back(0u);
                 P.blob[h + 14] = (unsigned)(P.blob.size() - h);   // word offset of the entries

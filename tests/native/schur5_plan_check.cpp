@@ -74,7 +74,15 @@ double run_case(unsigned seed, int nA, int nB, double kmean, int scatter_every, 
             const unsigned* blob = &P.blob[it.blob0];
             const unsigned* ptab = blob + S5_HDR;
             const unsigned* ents = blob + blob[14];
-            if (ents != ptab + ((it.npt + 1) / 2 + (((it.npt + 1) / 2) & 1)) || (int)blob[15] != ((it.flags >> 2) & 1)) return -7.0;
+            {   // layout: header, point table (even word count), observation -> local point bytes (even word count), entries
+                const int pw = (it.npt + 1) / 2 + (((it.npt + 1) / 2) & 1), ow = (it.nob + 3) / 4 + (((it.nob + 3) / 4) & 1);
+                if ((int)blob[13] != S5_HDR + pw || ents != ptab + pw + ow || (int)blob[15] != ((it.flags >> 2) & 1)) return -7.0;
+                const unsigned char* opt = reinterpret_cast<const unsigned char*>(blob + blob[13]);
+                for (int q = 0, j = 0; q < it.npt; ++q) {
+                    const int oe = (int)((ptab[q >> 1] >> (16 * (q & 1))) & 0xffffu);
+                    for (; j < oe; ++j) if (opt[j] != q) return -13.0;
+                }
+            }
             const double* span = &H[(size_t)(hB + (long long)WB * it.ob0 + 9ll * it.pt0)];
             if ((((hB + (long long)WB * it.ob0 + 9ll * it.pt0) & 1) ? 4 : 0) != it.flags) return -2.0;
             for (int w = 0; w < S5_CONSUMERS; ++w) {
