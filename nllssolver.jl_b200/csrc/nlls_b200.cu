@@ -154,6 +154,11 @@ struct nlls_ctx {
     const int s_tiled = 1;
     int NT = 0;
     int64_t ntiles_alloc = 0;
+    // multi-rank exchange of the reduced system by tile ownership (nlls_prepare): tiles only this rank's points touch ("exclusive") are
+    // stored rank by rank in blocks of xg_block tiles and travel in ONE all-gather; tiles several ranks touch are summed with an
+    // all-reduce; fill-only tiles are zero everywhere and are not exchanged
+    int64_t xg_block = 0, xg_shared0 = 0, xg_nshared = 0;
+    int* d_add_u = nullptr;          // [NT] natural camera tile: this rank adds U_c + lambda I to its diagonal tile
     int red_levels = 0;
     double red_flops = 0.0;          // algorithmic FP64 operations of one reduced solve (tile LDL' + sweeps), counted at prepare
     struct RedLaunch { int kind, off, cnt; };          // kind 0: diagonal tiles of a level, 1: its off-diagonal tiles, 2: its updates
@@ -437,7 +442,7 @@ int launch_schur(nlls_ctx* ctx, double lambda) {
     const size_t scount = (size_t)ctx->ntiles_alloc * ST2;
     CK(cudaMemsetAsync(ctx->d_S, 0, sizeof(double) * scount, ctx->st));
     red_init_kernel<DC><<<ctx->NT, 256, 0, ctx->st>>>(ctx->d_S, ctx->d_diag_tile_nat, ctx->d_H, ctx->d_g, ctx->d_rhs, (int)ctx->nA, lambda,
-                                                        ctx->rank == 0 ? 1 : 0);
+                                                        ctx->d_add_u, ctx->rank == 0 ? 1 : 0);
     ctx->launches++;
     if (ctx->n5cta > 0) {
         Schur5Dev s5;
@@ -486,7 +491,15 @@ int launch_schur(nlls_ctx* ctx, double lambda) {
     CK(cudaGetLastError());
     if (ctx->nranks > 1) {
         CKN(g_nccl.GroupStart());
-        CKN(g_nccl.AllReduce(ctx->d_S, ctx->d_S, scount, ncclFloat64, ncclSum, ctx->comm, ctx->st));
+        if (ctx->xg_shared0 > 0 || ctx->xg_nshared > 0) {   // exchange by tile ownership (nlls_prepare)
+            const size_t blk = (size_t)ctx->xg_block * ST2;
+            if (blk > 0) CKN(g_nccl.AllGather(ctx->d_S + blk * (size_t)ctx->rank, ctx->d_S, blk, ncclFloat64, ctx->comm, ctx->st));
+            if (ctx->xg_nshared > 0)
+                CKN(g_nccl.AllReduce(ctx->d_S + (size_t)ctx->xg_shared0 * ST2, ctx->d_S + (size_t)ctx->xg_shared0 * ST2, (size_t)ctx->xg_nshared * ST2, ncclFloat64, ncclSum,
+                                     ctx->comm, ctx->st));
+        } else {
+            CKN(g_nccl.AllReduce(ctx->d_S, ctx->d_S, scount, ncclFloat64, ncclSum, ctx->comm, ctx->st));
+        }
         CKN(g_nccl.AllReduce(ctx->d_rhs, ctx->d_rhs, (size_t)((int64_t)ctx->NT * ST), ncclFloat64, ncclSum, ctx->comm, ctx->st));
         CKN(g_nccl.GroupEnd());
     }
@@ -1060,7 +1073,7 @@ int nlls_destroy(nlls_ctx* ctx) {
     void* ptrs[] = {ctx->d_obs_cam, ctx->d_obs_pt, ctx->d_obs_start, ctx->d_tile_pt, ctx->d_obs_z, ctx->d_cm_pt, ctx->d_item_cam, ctx->d_item_beg,
                     ctx->d_item_end, ctx->d_cam_item_start, ctx->d_cm_z, ctx->d_A[0], ctx->d_A[1], ctx->d_A[2], ctx->d_B[0], ctx->d_B[1], ctx->d_B[2],
                     ctx->d_H, ctx->d_g, ctx->d_x, ctx->d_Ainv, ctx->d_S, ctx->d_rhs, ctx->d_cost_part, ctx->d_step_part, ctx->d_cam_part, ctx->d_cam_part2, ctx->d_scal, ctx->d_gather,
-                    ctx->d_flush, ctx->d_tile_id, ctx->d_pos, ctx->d_diag_tile, ctx->d_diag_tile_nat,
+                    ctx->d_flush, ctx->d_tile_id, ctx->d_pos, ctx->d_diag_tile, ctx->d_diag_tile_nat, ctx->d_add_u,
                     ctx->d_lvl_cols, ctx->d_red_tasks, ctx->d_red_upds, ctx->d_red_targets, ctx->d_colptr,
                     ctx->d_col_tile, ctx->d_col_row, ctx->d_Linv, ctx->d_xp, ctx->d_stile_pt, ctx->d_chunk_off, ctx->d_chunks, ctx->d_ents, ctx->d_tiles, ctx->d_camstat_part,
                     ctx->d_ad_data, ctx->d_ad_chunks, ctx->d_ad_moff, ctx->d_ad_part, ctx->d_ent_off, ctx->d_cta_item, ctx->d_items, ctx->d_units, ctx->d_wtab, ctx->d_blob,
@@ -1366,7 +1379,7 @@ int nlls_prepare(nlls_ctx* ctx) {
     ctx->hlen = (int64_t)DC * DC * nA + (int64_t)WB * nobs + 9 * nB;
     ctx->nred = (int64_t)DC * nA;
     // ---- reduced camera system: tile order, tile-level symbolic factorisation, level schedule
-    std::vector<int> tile_id, pos, diag_tile, diag_tile_nat, lvl_cols_flat, colptr, col_tile, col_row;
+    std::vector<int> tile_id, pos, diag_tile, diag_tile_nat, lvl_cols_flat, colptr, col_tile, col_row, add_u_tiles;
     std::vector<RedTask> red_tasks;
     std::vector<RedUpd> red_upds;
     std::vector<RedTarget> red_targets;
@@ -1384,17 +1397,27 @@ int nlls_prepare(nlls_ctx* ctx) {
                 const int tI = ctx->h_obs_cam[(size_t)j] / TC;
                 if (tl.empty() || tl.back() != tI) tl.push_back(tI);   // cameras ascend within a point
             }
-            for (size_t a = 0; a < tl.size(); ++a) for (size_t b = 0; b <= a; ++b) natpat[(size_t)tl[a] * NT + tl[b]] = 1;
+            for (size_t a = 0; a < tl.size(); ++a) for (size_t b = 0; b <= a; ++b) natpat[(size_t)tl[a] * NT + tl[b]] = 2;   // 2: touched by a point of this rank (1: structural diagonal)
         }
-        if (ctx->nranks > 1) {  // ranks see different points: every rank needs the union pattern (same tile map, same factorisation)
+        // toucher[tile] (natural numbering, lower triangle): -1 nobody's points touch it, r >= 0 only rank r's do, -2 several ranks'
+        std::vector<int> toucher;
+        if (ctx->nranks > 1) {  // ranks see different points: every rank needs the union pattern (same tile map, same factorisation) and who touches what
+            const size_t np = natpat.size();
             unsigned char* d_pat = nullptr;
-            CK(cudaMalloc((void**)&d_pat, natpat.size()));
-            CK(cudaMemcpy(d_pat, natpat.data(), natpat.size(), cudaMemcpyHostToDevice));
-            CKN(g_nccl.AllReduce(d_pat, d_pat, natpat.size(), /*ncclUint8*/ 1, ncclMax, ctx->comm, ctx->st));
+            CK(cudaMalloc((void**)&d_pat, np * (size_t)ctx->nranks));
+            CK(cudaMemcpy(d_pat + np * (size_t)ctx->rank, natpat.data(), np, cudaMemcpyHostToDevice));
+            CKN(g_nccl.AllGather(d_pat + np * (size_t)ctx->rank, d_pat, np, /*ncclUint8*/ 1, ctx->comm, ctx->st));
             CK(cudaStreamSynchronize(ctx->st));
-            CK(cudaMemcpy(natpat.data(), d_pat, natpat.size(), cudaMemcpyDeviceToHost));
+            std::vector<unsigned char> all(np * (size_t)ctx->nranks);
+            CK(cudaMemcpy(all.data(), d_pat, all.size(), cudaMemcpyDeviceToHost));
             CK(cudaFree(d_pat));
+            toucher.assign(np, -1);
+            for (int r = 0; r < ctx->nranks; ++r) {
+                const unsigned char* pr = all.data() + np * (size_t)r;
+                for (size_t e = 0; e < np; ++e) if (pr[e] == 2) { toucher[e] = toucher[e] == -1 ? r : -2; natpat[e] = 2; }
+            }
         }
+        for (unsigned char& v : natpat) v = v ? 1 : 0;
         // tile order: nested dissection by index when the pattern is banded (half-bandwidth w tiles), identity otherwise
         int w = 0;
         for (int I = 0; I < NT; ++I) for (int J2 = 0; J2 < I; ++J2) if (natpat[(size_t)I * NT + J2]) w = std::max(w, I - J2);
@@ -1457,6 +1480,45 @@ int nlls_prepare(nlls_ctx* ctx) {
         int nt = 0;
         for (int J2 = 0; J2 < NT; ++J2) for (int I = J2; I < NT; ++I) if (pat[(size_t)I * NT + J2]) tile_id[(size_t)I * NT + J2] = nt++;
         ctx->ntiles_alloc = nt;
+        ctx->xg_block = ctx->xg_shared0 = ctx->xg_nshared = 0;
+        std::vector<int> add_u((size_t)NT, (ctx->nranks > 1 && ctx->rank != 0) ? 0 : 1);   // without the ownership exchange: rank 0 adds U_c
+        if (ctx->nranks > 1 && !getenv("NLLS_B200_XG_ALLREDUCE")) {
+            // Storage order by ownership (a tile id is only a storage slot): [rank 0's exclusive tiles | rank 1's | ... ] in blocks of
+            // xg_block tiles, then the tiles several ranks touch, then the fill-only tiles.  A rank's points cover a contiguous camera band,
+            // so most tiles have one toucher: the try exchanges S with one all-gather of the blocks (every rank RECEIVES the other ranks'
+            // tiles, nothing is summed) + an all-reduce of the few shared tiles, instead of all-reducing all of S (Venice shape, 8 ranks:
+            // 18 MB all-reduced = 0.22 ms of a 0.75 ms iteration).  The diagonal tile's U_c + lambda I is added by the tile's owner.
+            const int N = ctx->nranks;
+            std::vector<std::vector<int>> excl((size_t)N);
+            std::vector<int> shared, fill;
+            for (int pJ = 0; pJ < NT; ++pJ) for (int pI = pJ; pI < NT; ++pI) {
+                const int id = tile_id[(size_t)pI * NT + pJ];
+                if (id < 0) continue;
+                const int I = nat_of_pos[(size_t)pI], J = nat_of_pos[(size_t)pJ];
+                int t = toucher[(size_t)std::max(I, J) * NT + std::min(I, J)];
+                if (pI == pJ) {                       // diagonal tile of natural camera tile I: somebody has to add U_c
+                    if (t == -1) t = 0;
+                    add_u[(size_t)I] = (t >= 0 ? t : 0) == ctx->rank ? 1 : 0;
+                }
+                if (t >= 0) excl[(size_t)t].push_back(id);
+                else if (t == -2) shared.push_back(id);
+                else fill.push_back(id);
+            }
+            size_t maxc = 0;
+            for (const auto& v : excl) maxc = std::max(maxc, v.size());
+            std::vector<int> newid((size_t)nt, -1);
+            for (int r = 0; r < N; ++r) for (size_t i = 0; i < excl[(size_t)r].size(); ++i) newid[(size_t)excl[(size_t)r][i]] = (int)((size_t)r * maxc + i);
+            for (size_t i = 0; i < shared.size(); ++i) newid[(size_t)shared[i]] = (int)((size_t)N * maxc + i);
+            for (size_t i = 0; i < fill.size(); ++i) newid[(size_t)fill[i]] = (int)((size_t)N * maxc + shared.size() + i);
+            for (int& v : tile_id) if (v >= 0) v = newid[(size_t)v];
+            ctx->xg_block = (int64_t)maxc; ctx->xg_shared0 = (int64_t)N * (int64_t)maxc; ctx->xg_nshared = (int64_t)shared.size();
+            ctx->ntiles_alloc = (int64_t)N * (int64_t)maxc + (int64_t)shared.size() + (int64_t)fill.size();
+            nt = (int)ctx->ntiles_alloc;
+            if (getenv("NLLS_B200_VERBOSE"))
+                fprintf(stderr, "[nlls] rank %d: reduced-system exchange by ownership: %zu exclusive tiles (block %zu), %zu shared, %zu fill-only\n", ctx->rank,
+                        excl[(size_t)ctx->rank].size(), maxc, shared.size(), fill.size());
+        }
+        add_u_tiles = add_u;
         if ((double)nt * ST2 * 8.0 > 60e9) FAIL(NLLS_ERR_UNSUPPORTED, "reduced camera system needs more than 60 GB");
         diag_tile.resize((size_t)NT); diag_tile_nat.resize((size_t)NT);
         for (int J2 = 0; J2 < NT; ++J2) diag_tile[(size_t)J2] = tile_id[(size_t)J2 * NT + J2];
@@ -1880,6 +1942,7 @@ int nlls_prepare(nlls_ctx* ctx) {
         TRY(dalloc(ctx, &ctx->d_Linv, (size_t)ctx->NT * ST2)); TRY(dalloc(ctx, &ctx->d_xp, (size_t)ctx->NT * ST));
         TRY(upload(ctx, &ctx->d_tile_id, tile_id)); TRY(upload(ctx, &ctx->d_pos, pos));
         TRY(upload(ctx, &ctx->d_diag_tile, diag_tile)); TRY(upload(ctx, &ctx->d_diag_tile_nat, diag_tile_nat));
+        TRY(upload(ctx, &ctx->d_add_u, add_u_tiles));
         TRY(upload(ctx, &ctx->d_red_tasks, red_tasks)); TRY(upload(ctx, &ctx->d_red_upds, red_upds)); TRY(upload(ctx, &ctx->d_red_targets, red_targets));
         CK(cudaMemsetAsync(ctx->d_Linv, 0, sizeof(double) * (size_t)ctx->NT * ST2, ctx->st));
         TRY(upload(ctx, &ctx->d_lvl_cols, lvl_cols_flat));

@@ -740,14 +740,16 @@ __global__ void red_permute_kernel(const double* __restrict__ src, double* __res
     else dst[k] = src[(size_t)pos[o] * ST + r];
 }
 
-// S tiles <- 0 (memset) except diagonal tiles: lower triangle of U_c + lambda I (rank 0 only in a multi-rank run);
-// padding rows get a unit diagonal.  rhs (natural numbering) <- g_c.
+// S tiles <- 0 (memset) except diagonal tiles: lower triangle of U_c + lambda I (multi-rank: added by ONE rank per tile — add_u_tile,
+// the tile's owner in the exchange by ownership); padding rows get a unit diagonal.  rhs (natural numbering) <- g_c (rank 0).
 template <int DC>
 __global__ void red_init_kernel(double* __restrict__ S, const int* __restrict__ diag_tile_nat, const double* __restrict__ H, const double* __restrict__ g,
-                                double* __restrict__ rhs, int nA, double lambda, int add_u) {
+                                double* __restrict__ rhs, int nA, double lambda, const int* __restrict__ add_u_tile, int add_g) {
     constexpr int TC = ST / DC;
     const int o = blockIdx.x;   // natural tile index
+    const int add_u = add_u_tile[o];
     double* T = S + (size_t)diag_tile_nat[o] * ST2;
+    if (add_u)
     for (int e = threadIdx.x; e < ST2; e += blockDim.x) {
         const int r = e % ST, c = e / ST;
         const int cr = r / DC, cc = c / DC;
@@ -762,7 +764,7 @@ __global__ void red_init_kernel(double* __restrict__ S, const int* __restrict__ 
     }
     for (int r = threadIdx.x; r < ST; r += blockDim.x) {
         const long long k = (long long)o * ST + r;
-        rhs[k] = (add_u && k < (long long)DC * nA) ? g[k] : 0.0;
+        rhs[k] = (add_g && k < (long long)DC * nA) ? g[k] : 0.0;
     }
 }
 

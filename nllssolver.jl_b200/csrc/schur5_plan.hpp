@@ -78,6 +78,10 @@ template <int DC> struct Schur5Cfg {
     S5_CE static constexpr int row_tile(int band, int r) {
         if (FULL) return r;
         if (DC <= 6) { return band == 0 ? (r == 0 ? 0 : (r == 1 ? 1 : 5)) : (band == 1 ? (r == 0 ? 2 : (r == 1 ? 3 : 6)) : (r == 0 ? 4 : (r == 1 ? 7 : 8))); }
+        if (DC > 6 && BR == 6) {   // two bands for 3 + 4 warps: {0,2,4,6,7,9} (34 of the 78 tiles) and {1,3,5,8,10,11} (44) — the plainly interleaved split
+                                   // (36 : 42) left the three-warp band 14 % over the four-warp one (its warps never waited, the others 25 % of the time)
+            return band == 0 ? (r < 4 ? 2 * r : (r == 4 ? 7 : 9)) : (r < 3 ? 2 * r + 1 : (r == 3 ? 8 : r + 6));
+        }
         return band + NBANDS * r;
     }
     // Shapes of an entry of band `band`: (first window tile of the point TLO, number of active rows NACT); the band's rows >= TLO
