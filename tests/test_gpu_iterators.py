@@ -69,3 +69,36 @@ def test_python_api_iterators(pkg):
         costs[it] = res.bestcost
     assert costs[pkg.newton] == pytest.approx(costs[pkg.levenbergmarquardt], rel=1e-6)
     assert costs[pkg.dogleg] == pytest.approx(costs[pkg.levenbergmarquardt], rel=1e-6)
+
+
+def test_lm_step_is_iterate_plus_advance(pkg):
+    """nlls_lm_step (one outer iteration with the null callback, what nlls_optimize runs and bench.py times) must reproduce the split
+    nlls_lm_iterate / nlls_lm_advance(cost, 0) loop bit for bit, and both must end where nlls_optimize ends."""
+    p, mask = _problem(pkg, seed=5)
+    opts = pkg.NLLSOptions(maxiters=7)
+    runs = []
+    for mode in ("split", "step", "optimize"):
+        ctx = cuda_context(pkg, p, pkg.capi.ROBUST_HUBER, (0.05,))
+        tr = []
+        if mode == "optimize":
+            res = ctx.optimize(opts.c())
+        else:
+            ctx.lm_begin(opts.c())
+            conv = 0
+            while conv == 0:
+                if mode == "split":
+                    info = ctx.lm_iterate()
+                    conv = ctx.lm_advance(info.cost, 0)
+                else:
+                    info, conv = ctx.lm_step()
+                tr.append((info.cost, int(info.ntries), info.lambda_, conv))
+            res = ctx.lm_end()
+        runs.append((tr, res.bestcost, res.niterations, res.termination, ctx.get_variables(pkg.capi.VAR_EUCLID6, p.ncam, 6)))
+        ctx.close()
+    a, b = np.array(runs[0][0]), np.array(runs[1][0])
+    assert a.shape == b.shape and len(a) == runs[0][2]
+    assert np.array_equal(a[:, 1], b[:, 1]) and np.array_equal(a[:, 3], b[:, 3])        # inner tries, termination words
+    assert np.allclose(a[:, 0], b[:, 0], rtol=1e-10, atol=0) and np.allclose(a[:, 2], b[:, 2], rtol=1e-6, atol=0)
+    for r in runs[1:]:
+        assert abs(r[1] - runs[0][1]) <= 1e-10 * runs[0][1] and r[2] == runs[0][2] and r[3] == runs[0][3]
+        assert np.allclose(r[4], runs[0][4], rtol=1e-8, atol=1e-10)
