@@ -98,7 +98,10 @@ def test_lm_step_is_iterate_plus_advance(pkg):
     a, b = np.array(runs[0][0]), np.array(runs[1][0])
     assert a.shape == b.shape and len(a) == runs[0][2]
     assert np.array_equal(a[:, 1], b[:, 1]) and np.array_equal(a[:, 3], b[:, 3])        # inner tries, termination words
-    assert np.allclose(a[:, 0], b[:, 0], rtol=1e-10, atol=0) and np.allclose(a[:, 2], b[:, 2], rtol=1e-6, atol=0)
+    assert np.allclose(a[:, 0], b[:, 0], rtol=1e-10, atol=0)
+    # lambda: while the cost still moves; once successive costs agree to 1e-9 the gain ratio q is a quotient of rounding errors
+    moving = np.concatenate([[True], np.abs(np.diff(a[:, 0])) > 1e-9 * a[1:, 0]])
+    assert np.allclose(a[moving, 2], b[moving, 2], rtol=1e-6, atol=0)
     for r in runs[1:]:
         assert abs(r[1] - runs[0][1]) <= 1e-10 * runs[0][1] and r[2] == runs[0][2] and r[3] == runs[0][3]
         assert np.allclose(r[4], runs[0][4], rtol=1e-8, atol=1e-10)
