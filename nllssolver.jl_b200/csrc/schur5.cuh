@@ -354,7 +354,7 @@ __global__ void __launch_bounds__(Schur5Cfg<DC>::THREADS, 1) schur5_kernel(DevPr
     uint64_t* bar_empty = bar_ready + NS;
 
     if (tid == 0) {
-        for (int s = 0; s < NS; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_ready[s], 1); mbar_init(&bar_empty[s], (uint32_t)sp.ncons); }
+        for (int s = 0; s < NS; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_ready[s], (uint32_t)C::PROD); mbar_init(&bar_empty[s], (uint32_t)sp.ncons); }
     }
     // the point tables' kk = 3 slots stay zero for the whole kernel: they make the fourth inner slot of every A fragment zero
     for (int s = 0; s < NS; ++s) {
@@ -439,7 +439,8 @@ __global__ void __launch_bounds__(Schur5Cfg<DC>::THREADS, 1) schur5_kernel(DevPr
                 //  and the tile's observations dealt to the consumer warps one tile ahead behind an mbarrier)
                 const unsigned char* opt = reinterpret_cast<const unsigned char*>(s_blob(st) + s_blob(st)[13]);
                 double* wrow = s_row(st) + mis;
-                for (int j = lane; j < it.nob; j += 32) {
+                if constexpr (C::PROD == 2) asm volatile("bar.sync 1, 64;" ::: "memory");   // the helper warp needs this tile's factors
+                for (int j = lane; j < it.nob; j += 32 * C::PROD) {
                     const int q = opt[j];
                     const double* o = pt + 16 * q;
                     const double l10 = o[2], l20 = o[3], l21 = o[6];
@@ -464,6 +465,36 @@ __global__ void __launch_bounds__(Schur5Cfg<DC>::THREADS, 1) schur5_kernel(DevPr
         return;
     }
 
+    if constexpr (C::PROD == 2) {
+        if (warp == C::CONS + 1) {
+            // ========================================= second producer warp: half of the W -> Z pass =========================================
+            for (int jp = 0; jp < nitem; ++jp) {
+                const int st = jp % NS;
+                mbar_wait(&bar_full[st], (uint32_t)((jp / NS) & 1));              // the tile's bulk loads, seen by this warp itself
+                const Schur5Item it = items[jp];
+                const int mis = (it.flags >> 2) & 1;
+                const double* pt = s_pt(st);
+                asm volatile("bar.sync 1, 64;" ::: "memory");                      // the first producer warp has written the tile's factors
+                const unsigned char* opt = reinterpret_cast<const unsigned char*>(s_blob(st) + s_blob(st)[13]);
+                double* wrow = s_row(st) + mis;
+                for (int j = lane + 32; j < it.nob; j += 64) {
+                    const int q = opt[j];
+                    const double* o = pt + 16 * q;
+                    const double l10 = o[2], l20 = o[3], l21 = o[6];
+                    double* w = wrow + WB * j + 9 * q;
+#pragma unroll
+                    for (int c = 0; c < DC; ++c) {
+                        const double w0 = w[3 * c], w1 = w[3 * c + 1], w2 = w[3 * c + 2];
+                        w[3 * c] = fma(l20, w2, fma(l10, w1, w0));
+                        w[3 * c + 1] = fma(l21, w2, w1);
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bar_ready[st]);
+            }
+            return;
+        }
+    }
     // ================================================= consumers =================================================
     if (warp >= sp.ncons) return;
     const int fr = lane >> 2, kk = lane & 3;

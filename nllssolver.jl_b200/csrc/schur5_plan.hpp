@@ -35,6 +35,9 @@ constexpr int S5_CONSUMERS = 11;       // most consumer warps a CTA can have (+ 
                         // the producer's pass (3 700 cycles per tile) became the critical path: 0.65 vs 0.57 ms.  For dc = 9 (7 consumer warps, two per
                         // point) Z wins: 1.75 -> 1.27 ms
 #endif
+#ifndef S5_PROD2
+#define S5_PROD2 1      // (12-warp configurations with the Z formulation) two producer warps share the W -> Z pass
+#endif
 #ifndef S5_BR9
 #define S5_BR9 6        // DC = 9: row tiles per band (2: six interleaved bands, 11 consumer warps; 6: two interleaved bands, 7 consumer warps with 255 registers)
 #endif
@@ -68,9 +71,12 @@ template <int DC> struct Schur5Cfg {
     static constexpr int BR = FULL ? NTW : ((DC <= 6) ? 3 : S5_BR9);   // row tiles per band
     static constexpr int NBANDS = NTW / BR;
     static constexpr bool WIDE = FULL || BR * NTW > 27;     // more accumulators than 12 warps' 168 registers hold: 8 warps with 255 registers
-    static constexpr int CONS = WIDE ? 7 : S5_CONSUMERS;    // consumer warps of a CTA
     static constexpr bool ZT = (DC > 6) || (S5_ZT6 != 0);   // Z = L' W formulation (schur5.cuh)
-    static constexpr int THREADS = 32 * (CONS + 1);
+    // producer warps: with 12 warps and the Z formulation the W -> Z pass of ONE producer warp is the critical path (3 700 cycles per tile);
+    // a second producer warp takes half of the tile's observations and one consumer warp is given up for it
+    static constexpr int PROD = (!WIDE && ZT && S5_PROD2 != 0) ? 2 : 1;
+    static constexpr int CONS = WIDE ? 7 : S5_CONSUMERS + 1 - PROD;    // consumer warps of a CTA
+    static constexpr int THREADS = 32 * (CONS + PROD);
     // r-th row tile of a band.  DC = 9: interleaved (band b owns b, b + NBANDS, ...).  DC = 6: {0,1,5} {2,3,6} {4,7,8} — the window's
     // middle rows carry most of the work (points start a few cameras above the base and span ~5 tiles); with 11 consumer warps the
     // bands get 4 / 4 / 3 warps, and this split brings the three shares close to 4 : 4 : 3 on the BAL-shaped problems (the plainly
