@@ -100,6 +100,15 @@ __device__ __forceinline__ void tile_to_smem_ld(double* sdst, const double* gsrc
     }
 }
 
+// rows [row0, row0 + 24) of a tile only (what the three warps of one CTA of a tile task read of their A operand: a third of the bytes)
+template <int NT_>
+__device__ __forceinline__ void tile_rows24_to_smem_ld(double* sdst, const double* gsrc, int row0) {
+    for (int q = threadIdx.x; q < ST * 12; q += NT_) {
+        const int k = q / 12, c = q - k * 12;
+        cp_async16(sdst + k * LDT + row0 + 2 * c, gsrc + k * ST + row0 + 2 * c);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // Diagonal tile: blocked right-looking LDL' with panels of 8 columns (9 panels), everything in shared memory, with look-ahead:
 //   A1 (warp 0)        LDL' of the next 8 x 8 diagonal block in registers (lane = row; pivot row / reciprocal broadcast by
@@ -407,7 +416,7 @@ __global__ void __launch_bounds__(GEMM_THREADS) ldl_off_kernel(double* __restric
     const RedTask tk = tasks[blockIdx.x / GEMM_CTAS];
     const int I = GEMM_CTAS * (blockIdx.x % GEMM_CTAS) + w;      // row block of this warp
     double* T = S + (size_t)tk.tile * ST2;
-    tile_to_smem_ld<GEMM_THREADS>(As, T);      // T_IJ was last written by the previous level's update kernel, two launches back: safe before the wait
+    tile_rows24_to_smem_ld<GEMM_THREADS>(As, T, 24 * (blockIdx.x % GEMM_CTAS));   // (this CTA's 24 rows) T_IJ was last written by the previous level's update kernel, two launches back: safe before the wait
     pdl_wait(); pdl_trigger();
     tile_to_smem_ld<GEMM_THREADS>(Bs, Linv + (size_t)tk.col * ST2);
     if (tid < ST) Ds[tid] = rcp_fast(S[(size_t)tk.dtile * ST2 + (size_t)(ST + 1) * tid]);
@@ -468,8 +477,11 @@ __global__ void __launch_bounds__(GEMM_THREADS) ldl_upd_kernel(double* __restric
     for (int u = tg.u0; u < tg.u1; ++u) {
         const RedUpd up = upds[u];
         __syncthreads();             // the previous update is done with the staged tiles
-        tile_to_smem_ld<GEMM_THREADS>(As, S + (size_t)up.a * ST2);
-        if (!diag) tile_to_smem_ld<GEMM_THREADS>(Bs, S + (size_t)up.b * ST2);
+        if (diag) tile_to_smem_ld<GEMM_THREADS>(As, S + (size_t)up.a * ST2);                       // A doubles as B
+        else {
+            tile_rows24_to_smem_ld<GEMM_THREADS>(As, S + (size_t)up.a * ST2, 24 * (blockIdx.x % GEMM_CTAS));   // this CTA's 24 rows of L_aJ
+            tile_to_smem_ld<GEMM_THREADS>(Bs, S + (size_t)up.b * ST2);
+        }
         if (tid < ST) {
             Ds[tid] = S[(size_t)up.dk * ST2 + (size_t)(ST + 1) * tid];
             if (diag) ys[tid] = xp[(size_t)up.col * ST + tid];
