@@ -310,8 +310,11 @@ __global__ void __launch_bounds__(TO) cost_kernel(DevProblem p, const int4* __re
 // accepted, the camera blocks it produced are exactly those of the re-linearisation at the accepted point (src/optimize.jl:169),
 // so the re-linearisation only runs the point pass and the camera pass costs nothing extra (launch_cost / do_linearize).
 // ---------------------------------------------------------------------------------------------------
+#ifndef LINCAM_OCC6
+#define LINCAM_OCC6 2
+#endif
 template <class R, bool MS = false>
-__global__ void __launch_bounds__(256, (R::DC <= 6) ? 2 : 1) lin_cam_kernel(DevProblem p, const double* __restrict__ cams, const double* __restrict__ pts,
+__global__ void __launch_bounds__(256, (R::DC <= 6) ? LINCAM_OCC6 : 1) lin_cam_kernel(DevProblem p, const double* __restrict__ cams, const double* __restrict__ pts,
                                                       double* __restrict__ partials) {
     constexpr int DC = R::DC, NU = DC * (DC + 1) / 2 + DC;
     __shared__ double s_red[8][NU + 1];
