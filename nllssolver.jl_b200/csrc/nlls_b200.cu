@@ -19,6 +19,7 @@
 #include "../../include/nlls_b200.h"
 #include "kernels.cuh"
 #include "adaptive.cuh"
+#include "reduced_plan.hpp"
 
 using namespace nlls;
 
@@ -1419,63 +1420,16 @@ int nlls_prepare(nlls_ctx* ctx) {
         }
         for (unsigned char& v : natpat) v = v ? 1 : 0;
         // tile order: nested dissection by index when the pattern is banded (half-bandwidth w tiles), identity otherwise
-        int w = 0;
-        for (int I = 0; I < NT; ++I) for (int J2 = 0; J2 < I; ++J2) if (natpat[(size_t)I * NT + J2]) w = std::max(w, I - J2);
+        const int w = red_half_bandwidth(natpat, NT);
         std::vector<int> nat_of_pos;
-        nat_of_pos.reserve((size_t)NT);
         const bool use_nd = w >= 1 && NT >= 8 * w && !getenv("NLLS_B200_NO_ND");
-        if (use_nd && getenv("NLLS_B200_ND_BAND")) {
-            // round-1/2a order: separators as wide as the half-bandwidth, leaves of up to 2 w + w columns eliminated one after the other
-            // (Venice shape: w = 2 because ~70 of 10^6 points reach a third tile -> 12 levels)
-            const int leaf = std::max(2 * w, 4);
-            struct Rec { static void nd(int lo, int hi, int w, int leaf, std::vector<int>& out) {
-                if (hi - lo <= leaf + w) { for (int i = lo; i < hi; ++i) out.push_back(i); return; }
-                const int s0 = lo + (hi - lo - w) / 2;
-                nd(lo, s0, w, leaf, out); nd(s0 + w, hi, w, leaf, out);
-                for (int i = s0; i < s0 + w; ++i) out.push_back(i);
-            } };
-            Rec::nd(0, NT, w, leaf, nat_of_pos);
-        } else if (use_nd) {
-            // Nested dissection on the ACTUAL tile graph, down to single columns: the separator of a node list is its middle column plus,
-            // for every edge that still joins the two sides, the endpoint nearer to the middle.  The reduced solve is a chain of dependent
-            // levels (~27 us each: diagonal tile, off-diagonal tiles, updates), so what counts is the height of the elimination tree, not
-            // the fill: Venice shape 12 -> 8 levels with 437 instead of 443 tiles (a handful of long tracks no longer widen every
-            // separator, and the leaves are no longer eliminated sequentially).
-            struct Rec { static void nd(const std::vector<int>& nodes, const std::vector<unsigned char>& pat, int NT, std::vector<int>& out) {
-                const int n = (int)nodes.size();
-                if (n <= 2) { for (int v : nodes) out.push_back(v); return; }
-                const int m = n / 2;
-                std::vector<unsigned char> insep((size_t)n, 0);
-                insep[(size_t)m] = 1;
-                for (int a = m - 1; a >= 0; --a)
-                    for (int b = m + 1; b < n && !insep[(size_t)a]; ++b)
-                        if (!insep[(size_t)b] && pat[(size_t)nodes[(size_t)b] * NT + nodes[(size_t)a]]) {   // nodes ascend: (b, a) is in the lower triangle
-                            if (m - a <= b - m) insep[(size_t)a] = 1; else insep[(size_t)b] = 1;
-                        }
-                std::vector<int> left, right, sep;
-                for (int i = 0; i < n; ++i) (insep[(size_t)i] ? sep : (i < m ? left : right)).push_back(nodes[(size_t)i]);
-                nd(left, pat, NT, out); nd(right, pat, NT, out);
-                for (int v : sep) out.push_back(v);
-            } };
-            std::vector<int> all((size_t)NT);
-            for (int i = 0; i < NT; ++i) all[(size_t)i] = i;
-            Rec::nd(all, natpat, NT, nat_of_pos);
-        } else {
-            for (int i = 0; i < NT; ++i) nat_of_pos.push_back(i);
-        }
-        pos.assign((size_t)NT, 0);
-        for (int q = 0; q < NT; ++q) pos[(size_t)nat_of_pos[(size_t)q]] = q;
-        std::vector<unsigned char> pat((size_t)NT * NT, 0);      // permuted numbering, lower triangle
-        for (int I = 0; I < NT; ++I) for (int J2 = 0; J2 <= I; ++J2) if (natpat[(size_t)I * NT + J2]) {
-            const int a = std::max(pos[(size_t)I], pos[(size_t)J2]), b = std::min(pos[(size_t)I], pos[(size_t)J2]);
-            pat[(size_t)a * NT + b] = 1;
-        }
-        std::vector<std::vector<int>> rows((size_t)NT);
-        for (int J2 = 0; J2 < NT; ++J2) {   // symbolic fill: eliminating column J couples every pair of its rows
-            std::vector<int>& r = rows[(size_t)J2];
-            for (int I = J2 + 1; I < NT; ++I) if (pat[(size_t)I * NT + J2]) r.push_back(I);
-            for (size_t a = 0; a < r.size(); ++a) for (size_t b = 0; b <= a; ++b) pat[(size_t)r[a] * NT + r[b]] = 1;
-        }
+        if (use_nd && getenv("NLLS_B200_ND_BAND")) nat_of_pos = red_order_band(NT, w);        // round-1/2a order (Venice shape: 12 levels)
+        else if (use_nd) nat_of_pos = red_order_graph(natpat, NT);                              // nested dissection on the actual tile graph (8 levels)
+        else for (int i = 0; i < NT; ++i) nat_of_pos.push_back(i);
+        const RedSymbolic sym = red_symbolic(natpat, NT, nat_of_pos);                           // reduced_plan.hpp
+        pos = sym.pos;
+        const std::vector<unsigned char>& pat = sym.pat;
+        const std::vector<std::vector<int>>& rows = sym.rows;
         tile_id.assign((size_t)NT * NT, -1);
         int nt = 0;
         for (int J2 = 0; J2 < NT; ++J2) for (int I = J2; I < NT; ++I) if (pat[(size_t)I * NT + J2]) tile_id[(size_t)I * NT + J2] = nt++;
@@ -1488,35 +1442,14 @@ int nlls_prepare(nlls_ctx* ctx) {
             // so most tiles have one toucher: the try exchanges S with one all-gather of the blocks (every rank RECEIVES the other ranks'
             // tiles, nothing is summed) + an all-reduce of the few shared tiles, instead of all-reducing all of S (Venice shape, 8 ranks:
             // 18 MB all-reduced = 0.22 ms of a 0.75 ms iteration).  The diagonal tile's U_c + lambda I is added by the tile's owner.
-            const int N = ctx->nranks;
-            std::vector<std::vector<int>> excl((size_t)N);
-            std::vector<int> shared, fill;
-            for (int pJ = 0; pJ < NT; ++pJ) for (int pI = pJ; pI < NT; ++pI) {
-                const int id = tile_id[(size_t)pI * NT + pJ];
-                if (id < 0) continue;
-                const int I = nat_of_pos[(size_t)pI], J = nat_of_pos[(size_t)pJ];
-                int t = toucher[(size_t)std::max(I, J) * NT + std::min(I, J)];
-                if (pI == pJ) {                       // diagonal tile of natural camera tile I: somebody has to add U_c
-                    if (t == -1) t = 0;
-                    add_u[(size_t)I] = (t >= 0 ? t : 0) == ctx->rank ? 1 : 0;
-                }
-                if (t >= 0) excl[(size_t)t].push_back(id);
-                else if (t == -2) shared.push_back(id);
-                else fill.push_back(id);
-            }
-            size_t maxc = 0;
-            for (const auto& v : excl) maxc = std::max(maxc, v.size());
-            std::vector<int> newid((size_t)nt, -1);
-            for (int r = 0; r < N; ++r) for (size_t i = 0; i < excl[(size_t)r].size(); ++i) newid[(size_t)excl[(size_t)r][i]] = (int)((size_t)r * maxc + i);
-            for (size_t i = 0; i < shared.size(); ++i) newid[(size_t)shared[i]] = (int)((size_t)N * maxc + i);
-            for (size_t i = 0; i < fill.size(); ++i) newid[(size_t)fill[i]] = (int)((size_t)N * maxc + shared.size() + i);
-            for (int& v : tile_id) if (v >= 0) v = newid[(size_t)v];
-            ctx->xg_block = (int64_t)maxc; ctx->xg_shared0 = (int64_t)N * (int64_t)maxc; ctx->xg_nshared = (int64_t)shared.size();
-            ctx->ntiles_alloc = (int64_t)N * (int64_t)maxc + (int64_t)shared.size() + (int64_t)fill.size();
+            const RedOwnership own = red_order_by_owner(tile_id, NT, nat_of_pos, toucher, ctx->nranks, ctx->rank);   // reduced_plan.hpp
+            add_u = own.add_u;
+            ctx->xg_block = own.block; ctx->xg_shared0 = own.shared0; ctx->xg_nshared = own.nshared;
+            ctx->ntiles_alloc = own.nslots;
             nt = (int)ctx->ntiles_alloc;
             if (getenv("NLLS_B200_VERBOSE"))
-                fprintf(stderr, "[nlls] rank %d: reduced-system exchange by ownership: %zu exclusive tiles (block %zu), %zu shared, %zu fill-only\n", ctx->rank,
-                        excl[(size_t)ctx->rank].size(), maxc, shared.size(), fill.size());
+                fprintf(stderr, "[nlls] rank %d: reduced-system exchange by ownership: %lld exclusive tiles (block %lld), %lld shared, %lld fill-only\n", ctx->rank,
+                        own.nexcl[(size_t)ctx->rank], own.block, own.nshared, own.nfill);
         }
         add_u_tiles = add_u;
         if ((double)nt * ST2 * 8.0 > 60e9) FAIL(NLLS_ERR_UNSUPPORTED, "reduced camera system needs more than 60 GB");
@@ -1524,12 +1457,8 @@ int nlls_prepare(nlls_ctx* ctx) {
         for (int J2 = 0; J2 < NT; ++J2) diag_tile[(size_t)J2] = tile_id[(size_t)J2 * NT + J2];
         for (int o = 0; o < NT; ++o) diag_tile_nat[(size_t)o] = diag_tile[(size_t)pos[(size_t)o]];
         // levels of the elimination tree: column I waits for every column J < I that has I among its rows
-        std::vector<int> level((size_t)NT, 0);
-        int nlev = 0;
-        for (int J2 = 0; J2 < NT; ++J2) {
-            for (int I : rows[(size_t)J2]) level[(size_t)I] = std::max(level[(size_t)I], level[(size_t)J2] + 1);
-            nlev = std::max(nlev, level[(size_t)J2] + 1);
-        }
+        const std::vector<int>& level = sym.level;
+        const int nlev = sym.nlev;
         ctx->red_levels = nlev;
         ctx->fact_launches.clear(); ctx->lvl_cols.clear();
         size_t nupd_total = 0;
