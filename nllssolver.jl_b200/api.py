@@ -130,6 +130,30 @@ class SimpleError2:
         self.varind = (int(vi1), int(vi2))
 
 
+class SimpleError3:
+    """SimpleError3{N,T,V1,V2,V3}(measurement, vi1, vi2, vi3)  (src/residual.jl:16-27): a measurement-error residual over three
+    variables.  The reference ships the type without any `generatemeasurement`; no sm_100a kernel is registered for it here, so a
+    problem that holds one is rejected with NLLS_ERR_NO_KERNEL when it is optimised (no CPU fallback)."""
+    restype = None
+    robustkernel = NoRobust()
+    ndeps = 3
+
+    def __init__(self, measurement, vi1, vi2, vi3):
+        self.measurement = np.asarray(measurement, dtype=np.float64).ravel()
+        self.varind = (int(vi1), int(vi2), int(vi3))
+
+
+class SimpleError4:
+    """SimpleError4{N,T,V1,V2,V3,V4}(measurement, vi1, vi2, vi3, vi4)  (src/residual.jl:29-38); see SimpleError3."""
+    restype = None
+    robustkernel = NoRobust()
+    ndeps = 4
+
+    def __init__(self, measurement, vi1, vi2, vi3, vi4):
+        self.measurement = np.asarray(measurement, dtype=np.float64).ravel()
+        self.varind = (int(vi1), int(vi2), int(vi3), int(vi4))
+
+
 class AffineReprojection(SimpleError2):
     """SimpleError2{2,Float64,EuclideanVector{6},EuclideanVector{3}} with generatemeasurement(pose, X) =
     (pose[1:3].X, pose[4:6].X)  (test/optimizeba.jl:4)."""
@@ -222,7 +246,7 @@ class NLLSProblem:
 
     def addcost(self, cost):
         """addcost!(problem, cost)  (src/problem.jl:90-107)."""
-        if not isinstance(cost, (SimpleError2, OffsetResidual)):
+        if not isinstance(cost, (SimpleError2, SimpleError3, SimpleError4, OffsetResidual)):
             raise TypeError("unsupported cost")
         if isinstance(cost, OffsetResidual):                               # src/problem.jl:97
             assert isinstance(self.variables[cost.varind[0] - 1], ContaminatedGaussian), "adaptive residual: first variable must be the kernel"

@@ -62,6 +62,20 @@ def test_unregistered_residual_rejected(pkg):
     assert e.value.code == pkg.capi.ERR_NO_KERNEL
 
 
+def test_simpleerror3_and_4_are_rejected_without_a_kernel(pkg):
+    """src/residual.jl:16-38: the reference exports the types; north star: residual types with no registered kernel are rejected."""
+    for cls, nv in ((pkg.SimpleError3, 3), (pkg.SimpleError4, 4)):
+        prob = pkg.NLLSProblem()
+        idx = [prob.addvariable(pkg.EuclideanVector([0.0] * 3)) for _ in range(nv)]
+        prob.addcost(cls([0.0, 0.0], *idx))
+        assert prob.numcosts() == 1
+        with pytest.raises(pkg.capi.NLLSError) as e:
+            prob._cost_aos()
+        assert e.value.code == pkg.capi.ERR_NO_KERNEL
+    with pytest.raises(AssertionError):                       # varindices are checked like src/problem.jl:99-101
+        prob.addcost(pkg.SimpleError3([0.0, 0.0], 1, 2, 99))
+
+
 def test_unsupported_options(pkg):
     prob = pkg.NLLSProblem()
     prob.addvariable(pkg.EuclideanVector([0.0] * 6))
