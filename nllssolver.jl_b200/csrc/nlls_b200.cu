@@ -445,6 +445,7 @@ int launch_schur(nlls_ctx* ctx, double lambda) {
     red_init_kernel<DC><<<ctx->NT, 256, 0, ctx->st>>>(ctx->d_S, ctx->d_diag_tile_nat, ctx->d_H, ctx->d_g, ctx->d_rhs, (int)ctx->nA, lambda,
                                                         ctx->d_add_u, ctx->rank == 0 ? 1 : 0);
     ctx->launches++;
+    if (ctx->nout_pts > 0) CK(cudaEventRecord(ctx->ev_fork, ctx->st));   // S and rhs are initialised: the outlier kernel (second stream) may start adding
     if (ctx->n5cta > 0) {
         Schur5Dev s5;
         s5.cta_item = ctx->d5_cta_item; s5.items = ctx->d5_items; s5.blob = ctx->d5_blob; s5.ftab = ctx->d5_ftab; s5.dbg = nullptr; s5.ncons = ctx->s5_ncons;
@@ -486,8 +487,14 @@ int launch_schur(nlls_ctx* ctx, double lambda) {
         ctx->launches++;
     }
     if (ctx->nout_pts > 0) {   // points outside the plans: gaps in the camera list / wide tracks (v5), and the irregular points (their A_p^-1 too)
-        schur_outlier_kernel<DC><<<(ctx->nout_pts * 32 + 127) / 128, 128, 0, ctx->st>>>(p, ctx->d_out_pts, ctx->nout_pts, ctx->d_S, ctx->d_rhs, lambda, ctx->first_irr, ctx->d_Ainv);
+        // a few hundred warps of work (29 us alone: latency): on the second stream, behind red_init, so that it fills the tail of the
+        // persistent Schur kernel (launched first, it holds every SM's registers until its CTAs finish) instead of following it
+        static const bool side = getenv("NLLS_B200_OUTLIER_SERIAL") == nullptr;
+        cudaStream_t so = side ? ctx->st2 : ctx->st;
+        if (side) CK(cudaStreamWaitEvent(ctx->st2, ctx->ev_fork, 0));
+        schur_outlier_kernel<DC><<<(ctx->nout_pts * 32 + 127) / 128, 128, 0, so>>>(p, ctx->d_out_pts, ctx->nout_pts, ctx->d_S, ctx->d_rhs, lambda, ctx->first_irr, ctx->d_Ainv);
         ctx->launches++;
+        if (side) { CK(cudaEventRecord(ctx->ev_join, ctx->st2)); CK(cudaStreamWaitEvent(ctx->st, ctx->ev_join, 0)); }
     }
     CK(cudaGetLastError());
     if (ctx->nranks > 1) {
