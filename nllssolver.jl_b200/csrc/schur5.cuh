@@ -8,7 +8,13 @@
 // super-tile (window coordinates make the tiles of different points coincide).  No Y buffer, no per-contribution entries:
 // ~33 M wavefronts and 12.8 M DMMAs on the Venice shape instead of 121 M and 16.5 M.
 //
-// CTA = 11 consumer warps + 1 producer warp, one CTA per SM, a contiguous range of point tiles each:
+// Two formulations (Schur5Cfg<DC>::ZT, schur5_plan.hpp): the classic one above (dc = 6: three bands of the window, 11 consumer warps)
+// and the factored one (dc = 9: two six-row bands, 7 consumer warps with 253 registers):  A_p^-1 = L_p D_p L_p' (3 x 3 LDL'),
+// Z_p = L_p' W_p written over the staged W_p by the producer, S_p = Z_p' D_p Z_p — one load per 8-row tile of a point then serves
+// the B fragment, the A fragment (d[kk] times the same values) and the rhs.  The variants tried around these two and their
+// same-box timings are listed in DESIGN.md section 4.
+//
+// CTA = Schur5Cfg<DC>::CONS consumer warps + 1 producer warp, one CTA per SM, a contiguous range of point tiles each:
 //   producer   TMA bulk loads (H span, g_p, the tile's entry blob) NS - 1 tiles ahead into a ring of NS stages
 //              (mbarrier complete_tx), then per point A_p^-1 = (V_p + lambda I)^-1 into the stage's point table
 //              ([Ainv row kk | g_kk] per inner index kk) and to global memory for the back-substitution;
